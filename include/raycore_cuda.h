@@ -1,0 +1,215 @@
+/*
+ * raycore_cuda.h — C ABI of libraycore_cuda.so, the B200 (sm_100a) implementation of
+ * Raycore.jl's ray-query hot path.  This is the drop-in boundary: a Julia shim (or any FFI)
+ * binds exactly these entry points; INTEGRATION.md shows the ccall stubs.
+ *
+ * Every entry point cites the reference interface it replaces (file:line in
+ * JuliaGeometry/Raycore.jl v0.2.0).  Plain pointers and sizes only; all functions return an
+ * int32 status (RC_OK == 0) and record a message retrievable with rc_last_error().
+ *
+ * There is no CPU fallback: every call needs a CUDA device and fails with RC_ERR_CUDA without one.
+ *
+ * Conventions
+ *   - Mat3x4f: 12 floats, Vulkan row-major 3x4 [R|t]  (src/instanced-bvh.jl:28-31).
+ *   - Triangle soups: n_faces x 9 floats (v0,v1,v2), i.e. the decomposed mesh the reference
+ *     builds Triangles from (src/instanced-bvh.jl:555-566).  Degenerate faces are dropped by the
+ *     library with the reference's exact rule (src/triangle_mesh.jl:14-17).
+ *   - Indices returned in RTHitResult are 0-based (src/rt_transport.jl:26-31); the Julia shim
+ *     adds 1 where closest_hit's tuple is 1-based (src/instanced-bvh.jl:2011).
+ *   - Not thread-safe per context for mutation; trace calls on a synced context are re-entrant
+ *     only when issued on the same stream (reference: single-threaded mutation, concurrent pure
+ *     reads, src/kernels.jl:64).
+ */
+#ifndef RAYCORE_CUDA_H
+#define RAYCORE_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RC_ABI_VERSION 1
+
+/* status codes */
+enum {
+    RC_OK = 0,
+    RC_ERR_INVALID_ARGUMENT = 1, /* Julia: ArgumentError / ErrorException for arity mismatch (:664-666, :759, :788) */
+    RC_ERR_INVALID_HANDLE = 2,   /* Julia: error("Invalid handle") (:715, :756, :785, :809) */
+    RC_ERR_DELETED_HANDLE = 3,   /* Julia: error("Handle has been deleted") (:716, :757, :786, :810) */
+    RC_ERR_NO_VALID_TRIANGLES = 4, /* Julia: error("Geometry has no valid triangles") (:601, :837) */
+    RC_ERR_CUDA = 5,
+    RC_ERR_NOT_SYNCED = 6,
+    RC_ERR_OUT_OF_MEMORY = 7,
+    RC_ERR_STACK_OVERFLOW = 8    /* traversal stack exhausted for >=1 ray (the reference has UB here, :1912) */
+};
+
+/* RTRay, 32 bytes — src/rt_transport.jl:10-19 */
+typedef struct rc_ray {
+    float origin[3];
+    float tmin;
+    float dir[3];
+    float tmax;
+} rc_ray;
+
+/* RTHitResult, 32 bytes — src/rt_transport.jl:33-42.  The reference's trailing pad word carries
+ * Triangle.metadata of the hit primitive (face_meta / 1-based face index, src/instanced-bvh.jl:595). */
+typedef struct rc_hit {
+    uint32_t hit;                   /* 0 / 1 */
+    float t;                        /* miss: 0 (src/instanced-bvh.jl:2022) */
+    uint32_t primitive_id;          /* 0-based index into the BLAS's degenerate-filtered input triangle list */
+    uint32_t instance_custom_index; /* InstanceDescriptor.instance_id (src/instanced-bvh.jl:92) */
+    float bary_u, bary_v;           /* bary = (1-u-v, u, v) (src/instanced-bvh.jl:2015-2016) */
+    uint32_t instance_id;           /* 0-based position in instances[] */
+    uint32_t metadata;
+} rc_hit;
+
+/* InstanceDescriptor, 108 bytes — src/instanced-bvh.jl:90-96 */
+typedef struct rc_instance_desc {
+    uint32_t blas_index; /* 1-based */
+    uint32_t instance_id;
+    float transform[12];
+    float inv_transform[12];
+    uint32_t flags;
+} rc_instance_desc;
+
+/* BVHNode2, 60 bytes — src/instanced-bvh.jl:50-63 (read-back format of rc_read_*_nodes) */
+typedef struct rc_bvh_node2 {
+    float aabb0_min[3], aabb0_max[3], aabb1_min[3], aabb1_max[3];
+    uint32_t child0, child1, parent;
+} rc_bvh_node2;
+
+typedef struct rc_context rc_context; /* one mutable TLAS (src/instanced-bvh.jl:261-310) */
+
+/* trace / pointer flags */
+#define RC_RAYS_ON_DEVICE 0x1u  /* rays pointer is device memory */
+#define RC_HITS_ON_DEVICE 0x2u  /* hits pointer is device memory */
+#define RC_MODE_REFERENCE_ORDER 0x4u /* traverse the reference-identical BVH2 in the reference's own order
+                                        (bit-identical results incl. ties); default = wide BVH4 fast path */
+#define RC_COUNTERS 0x8u        /* accumulate per-ray work counters (rc_get_counters) — instrumented build of the same kernel */
+#define RC_VERTS_ON_DEVICE 0x10u /* rc_push / rc_update_geometry: verts (and face_meta) are device pointers */
+#define RC_NO_SYNC 0x20u        /* trace: do not cudaStreamSynchronize before returning (device buffers only) */
+
+/* sync actions reported by rc_sync */
+enum { RC_SYNC_NONE = 0, RC_SYNC_REFIT = 1, RC_SYNC_REBUILD = 2 };
+
+/* ---- lifecycle ----------------------------------------------------------------------- */
+/* TLAS(backend) — src/instanced-bvh.jl:334-358.  device < 0: current device. */
+int32_t rc_create(int32_t device, rc_context **out);
+/* free!(tlas) — src/instanced-bvh.jl:383-399 */
+int32_t rc_destroy(rc_context *ctx);
+const char *rc_last_error(const rc_context *ctx); /* ctx may be NULL: last creation error */
+int32_t rc_abi_version(void);
+/* the context's CUDA stream (cudaStream_t) — all work of this context is ordered on it */
+void *rc_stream(rc_context *ctx);
+
+/* ---- mutation (handle API) ----------------------------------------------------------- */
+/* push!(tlas, mesh, transform; instance_id) / push!(tlas, mesh, transforms; instance_ids)
+ * — src/instanced-bvh.jl:639-676 (+ build_and_append_blas! :581-608, build_blas :1376-1443).
+ * Builds the BLAS immediately on the GPU, appends m instance descriptors, marks the TLAS dirty.
+ *   verts: n_faces*9 floats; face_meta: NULL => metadata = 1-based face index before filtering.
+ *   transforms: m*12 floats; inv_transforms: NULL => mat3x4_inverse (:1675-1687) is evaluated by the
+ *   library, else used verbatim (lets the Julia shim pass its own results for bit identity);
+ *   instance_ids: NULL => 0 ("inherit", :656-657).  m must be >= 1. */
+int32_t rc_push(rc_context *ctx, const float *verts, uint32_t n_faces, const uint32_t *face_meta, const float *transforms,
+                const float *inv_transforms, const uint32_t *instance_ids, uint32_t m, uint32_t flags, uint32_t *handle_out);
+/* delete!(tlas, handle)::Bool — src/instanced-bvh.jl:690-699.  *deleted = 0 for unknown / already deleted. */
+int32_t rc_delete(rc_context *ctx, uint32_t handle, int32_t *deleted);
+/* update_transform!/update_transforms! — src/instanced-bvh.jl:755-797 (+ kernels.jl:434-476).
+ * m must equal the handle's instance count. */
+int32_t rc_update_transforms(rc_context *ctx, uint32_t handle, const float *transforms, const float *inv_transforms, uint32_t m);
+/* update!(tlas, handle, new_geometry) — src/instanced-bvh.jl:808-857: rebuild the handle's BLAS in place. */
+int32_t rc_update_geometry(rc_context *ctx, uint32_t handle, const float *verts, uint32_t n_faces, const uint32_t *face_meta, uint32_t flags);
+/* sync!(tlas) — src/instanced-bvh.jl:894-921: no-op when clean, refit when only transforms changed,
+ * else compact + rebuild; returns with the stream idle.  *action: RC_SYNC_*. */
+int32_t rc_sync(rc_context *ctx, int32_t *action);
+
+/* ---- introspection ------------------------------------------------------------------- */
+int32_t rc_is_valid(const rc_context *ctx, uint32_t handle);                 /* :524-526 */
+uint32_t rc_n_instances(const rc_context *ctx);                              /* live, :2391-2398 */
+uint32_t rc_n_instances_of(const rc_context *ctx, uint32_t handle);          /* :533-537 */
+uint32_t rc_n_total_instances(const rc_context *ctx);                        /* :544 */
+uint32_t rc_n_geometries(const rc_context *ctx);                             /* :2405 */
+int32_t rc_is_dirty(const rc_context *ctx, int32_t *dirty, int32_t *transforms_dirty);
+/* get_instances(tlas, handle) — :732-738; out must hold rc_n_instances_of() entries */
+int32_t rc_get_instances(const rc_context *ctx, uint32_t handle, rc_instance_desc *out);
+/* world_bound(tlas) — :2147-2149; (p_min, p_max); Bounds3() = (+Inf, -Inf) when empty */
+int32_t rc_world_bound(const rc_context *ctx, float out[6]);
+/* wait_for_gpu!(accel) — :2418-2421 */
+int32_t rc_wait(rc_context *ctx);
+/* sizes of the synced structure in the reference's terms: TLAS nodes (max(1,2n-1), 0 if empty),
+ * Σ live BLAS nodes (2n_b-1) and prims — the flat-array invariants of test/test_mesh_update.jl:261-294 */
+int32_t rc_sizes(const rc_context *ctx, uint32_t *tlas_nodes, uint32_t *blas_nodes, uint32_t *blas_prims, uint32_t *pending_deletes);
+/* read back the reference-layout BVH2 (for parity tests of the builder).  blas_index 1-based (post-sync numbering). */
+int32_t rc_read_tlas_nodes(rc_context *ctx, rc_bvh_node2 *out, uint32_t capacity);
+int32_t rc_read_blas_nodes(rc_context *ctx, uint32_t blas_index, rc_bvh_node2 *out, uint32_t capacity);
+/* sorted primitive order of a BLAS: out[k] = primitive_id of the k-th Morton-sorted triangle */
+int32_t rc_read_blas_order(rc_context *ctx, uint32_t blas_index, uint32_t *out, uint32_t capacity);
+uint32_t rc_blas_n_prims(const rc_context *ctx, uint32_t blas_index);
+/* out[primitive_id] = index of that triangle in the submitted soup (before the degenerate filter), so a shim can
+ * materialise the reference's Triangle (vertices, normals, uv, metadata) from its own copy of the mesh */
+int32_t rc_read_blas_faces(rc_context *ctx, uint32_t blas_index, uint32_t *out, uint32_t capacity);
+/* out[i] = handle id owning instance position i (0-based), n_total_instances entries */
+int32_t rc_get_instance_handles(const rc_context *ctx, uint32_t *out, uint32_t capacity);
+
+/* ---- queries ------------------------------------------------------------------------- */
+/* Batched closest_hit(::StaticTLAS, ray) — src/instanced-bvh.jl:1902-2024; batch shape of
+ * Lava.trace_closest_hits!(hits, rays, accel, n) (docs/src/hw_acceleration.md:143-146) and
+ * trace_rays (ext/RaycoreMakieExt.jl:81-87).  Host pointers are staged through pinned chunks with
+ * copies overlapped with tracing; device pointers are used in place.  The context must be synced. */
+int32_t rc_trace_closest(rc_context *ctx, const rc_ray *rays, rc_hit *hits, uint64_t n, uint32_t flags);
+/* Batched any_hit — src/instanced-bvh.jl:2034-2140 (t_min forced to 0, :2039). */
+int32_t rc_trace_any(rc_context *ctx, const rc_ray *rays, rc_hit *hits, uint64_t n, uint32_t flags);
+/* work counters accumulated by RC_COUNTERS traces since the last reset:
+ * out = {rays, node fetches, child-box tests, triangle tests, instance entries, max stack depth} */
+int32_t rc_get_counters(rc_context *ctx, uint64_t out[6], int32_t reset);
+/* milliseconds of the last trace's kernel(s), measured with CUDA events on the context stream */
+float rc_last_kernel_ms(const rc_context *ctx);
+uint32_t rc_last_kernel_launches(const rc_context *ctx);
+
+/* ---- analysis (src/kernels.jl) --------------------------------------------------------- */
+/* hits_from_grid(tlas, viewdir; grid_size) — :58-72 with generate_ray_grid :10-56.
+ * hits: grid*grid records, cell (i,j) 1-based at (j-1)*grid + (i-1) (Julia column-major);
+ * points (nullable): grid*grid*3 floats = sum_mul(bary, vertices).  Host pointers. */
+int32_t rc_hits_from_grid(rc_context *ctx, const float viewdir[3], uint32_t grid, rc_hit *hits, float *points);
+/* get_illumination(tlas, viewdir; grid_size=1000) — :112-124; out: n_prims floats (hit counts per metadata 1..n_prims) */
+int32_t rc_get_illumination(rc_context *ctx, const float viewdir[3], uint32_t grid, float *out, uint32_t n_out);
+/* get_centroid(tlas, viewdir; grid_size=32) — :106-110; points (nullable, capacity grid*grid*3): hit points, compacted */
+int32_t rc_get_centroid(rc_context *ctx, const float viewdir[3], uint32_t grid, float centroid[3], uint32_t *n_hits, float *points);
+/* view_factors(tlas; rays_per_triangle) — :74-104.  Sources are the primitives of the flat array
+ * (_primitives(tlas), :8: every BLAS in order, local-space vertices, as the reference uses them) whose
+ * metadata - 1 lies in [row_base, row_base + n_rows); each shoots rays_per_triangle rays and
+ *   out[(meta_src - 1 - row_base) * n_prims + (meta_hit - 1)] += 1     (self hits skipped, :95-97)
+ * i.e. out is the row block [row_base, row_base+n_rows) of the row-major [src][hit] matrix = the transpose of
+ * Julia's column-major result[src, hit].  A multi-GPU caller gives each rank its own row block.
+ * Requires metadata dense in 1..n_prims as the reference does (unchecked there, :85); primitives with
+ * out-of-range metadata are skipped and counted in *skipped (reported for row_base == 0 only).
+ * Randomness: counter-based RNG keyed by (seed, (meta_src-1)*rays_per_triangle + i, dim) — see DESIGN.md;
+ * the reference's task-local rand() stream is not reproducible, parity is statistical.
+ * out is zeroed first.  RC_HITS_ON_DEVICE => out is a device pointer. */
+int32_t rc_view_factors(rc_context *ctx, uint32_t rays_per_triangle, uint64_t seed, uint32_t *out, uint32_t row_base, uint32_t n_rows,
+                        uint32_t flags, uint64_t *skipped);
+/* the rays rc_view_factors generates for that row block: host buffer of n_rows*rays_per_triangle records,
+ * ray (meta_src-1-row_base)*rays_per_triangle + i (rows without a source stay zero) */
+int32_t rc_view_factor_rays(rc_context *ctx, uint32_t rays_per_triangle, uint64_t seed, uint32_t row_base, uint32_t n_rows, rc_ray *out);
+/* metadata of the flat primitive array (position -> metadata), n_prims entries */
+int32_t rc_read_flat_metadata(rc_context *ctx, uint32_t *out, uint32_t capacity);
+
+/* ---- device memory helpers for callers that keep rays/hits resident -------------------- */
+int32_t rc_device_alloc(rc_context *ctx, size_t bytes, void **out);
+int32_t rc_device_free(rc_context *ctx, void *ptr);
+int32_t rc_host_alloc(rc_context *ctx, size_t bytes, void **out); /* pinned */
+int32_t rc_host_free(rc_context *ctx, void *ptr);
+int32_t rc_memcpy_h2d(rc_context *ctx, void *dst, const void *src, size_t bytes);
+int32_t rc_memcpy_d2h(rc_context *ctx, void *dst, const void *src, size_t bytes);
+/* cross-process peer access for the fused multi-GPU gather: export a device allocation as a 64-byte IPC
+ * handle / open one exported by another rank (one process per GPU). */
+int32_t rc_ipc_export(rc_context *ctx, void *ptr, uint8_t handle_out[64]);
+int32_t rc_ipc_open(rc_context *ctx, const uint8_t handle[64], void **out);
+int32_t rc_ipc_close(rc_context *ctx, void *ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAYCORE_CUDA_H */

@@ -1,0 +1,207 @@
+// rc_analysis.cu — fused ray-generation + trace + accumulate kernels for the analysis functions of
+// src/kernels.jl: hits_from_grid / get_centroid / get_illumination (:58-72, :106-124) and view_factors! (:80-104).
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include <string>
+
+#include "rc_trace.h"
+#include "rc_trace_core.cuh"
+
+// ------------------------------------------------------------------------------------------------ grid
+// Host-side restatement of generate_ray_grid's frame (src/kernels.jl:10-47).  Float32 arithmetic in the
+// reference's order (this TU is compiled with -ffp-contract=off for host code).
+static inline void h_normalize(const float a[3], float o[3]) {  // StaticArrays: inv(norm(a)) * a
+    float n = sqrtf(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+    float inv = 1.0f / n;
+    for (int k = 0; k < 3; k++) o[k] = inv * a[k];
+}
+static inline void h_cross(const float a[3], const float b[3], float o[3]) {
+    float x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+    o[0] = x; o[1] = y; o[2] = z;
+}
+static inline float h_dot(const float a[3], const float b[3]) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+bool rc_grid_frame(const float b[6], const float viewdir[3], uint32_t grid, RcGridFrame *f) {
+    float d0[3], direction[3];
+    h_normalize(viewdir, d0);     // hits_from_grid :59
+    h_normalize(d0, direction);   // generate_ray_grid :11
+    for (int k = 0; k < 3; k++) f->dir[k] = d0[k];
+    float temp[3] = {1.0f, 0.0f, 0.0f};
+    if (!(fabsf(direction[0]) < 0.9f)) { temp[0] = 0.0f; temp[1] = 1.0f; }
+    float c1[3], c2[3];
+    h_cross(direction, temp, c1); h_normalize(c1, f->basis1);
+    h_cross(direction, f->basis1, c2); h_normalize(c2, f->basis2);
+    float min1 = INFINITY, max1 = -INFINITY, min2 = INFINITY, max2 = -INFINITY, mind = INFINITY;
+    for (int c = 0; c < 8; c++) {  // corners of the world box (bounds.jl:53-59); only extrema are used
+        float p[3] = {(c & 1) ? b[3] : b[0], (c & 2) ? b[4] : b[1], (c & 4) ? b[5] : b[2]};
+        float p1 = h_dot(p, f->basis1), p2 = h_dot(p, f->basis2), pd = h_dot(p, direction);
+        min1 = fminf(min1, p1); max1 = fmaxf(max1, p1);
+        min2 = fminf(min2, p2); max2 = fmaxf(max2, p2);
+        mind = fminf(mind, pd);
+    }
+    float margin = 0.05f * fmaxf(max1 - min1, max2 - min2);
+    float grid_width = max1 - min1 + 2 * margin;
+    float grid_height = max2 - min2 + 2 * margin;
+    float min_depth = mind - margin;
+    float h1 = (min1 + max1) / 2, h2 = (min2 + max2) / 2;
+    for (int k = 0; k < 3; k++) f->gc[k] = ((0.0f + min_depth * direction[k]) + h1 * f->basis1[k]) + h2 * f->basis2[k];
+    f->cell_w = grid_width / (float)grid;
+    f->cell_h = grid_height / (float)grid;
+    f->grid = grid;
+    return true;
+}
+
+// ray of cell k (Julia column-major: i = k % grid + 1, j = k / grid + 1); origin evaluated in Float64 then
+// rounded, as the reference's mixed Int/Float64/Float32 expression does (:50-53)
+__device__ __forceinline__ rc_ray grid_ray(const RcGridFrame &f, uint32_t k) {
+    uint32_t i = k % f.grid + 1, j = k / f.grid + 1;
+    double half = ((double)f.grid + 1.0) / 2.0;
+    double u = __dmul_rn((double)i - half, (double)f.cell_w);
+    double v = __dmul_rn((double)j - half, (double)f.cell_h);
+    rc_ray r;
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+        r.origin[c] = (float)__dadd_rn(__dadd_rn((double)f.gc[c], __dmul_rn(u, (double)f.basis1[c])), __dmul_rn(v, (double)f.basis2[c]));
+    r.dir[0] = f.dir[0]; r.dir[1] = f.dir[1]; r.dir[2] = f.dir[2];
+    r.tmin = 0.0f;
+    r.tmax = INFINITY;
+    return r;
+}
+
+__global__ void k_grid_rays(RcGridFrame f, rc_ray *__restrict__ rays) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= f.grid * f.grid) return;
+    rays[k] = grid_ray(f, k);
+}
+
+void rc_launch_grid_rays(cudaStream_t st, const RcGridFrame &f, rc_ray *rays) {
+    uint32_t n = f.grid * f.grid;
+    k_grid_rays<<<(n + 255) / 256, 256, 0, st>>>(f, rays);
+}
+
+__global__ void __launch_bounds__(RC_TRACE_THREADS) k_grid_trace(RcScene sc, RcGridFrame f, rc_hit *__restrict__ hits, float *__restrict__ points, float *__restrict__ illum,
+                                                                 uint32_t n_illum, double *__restrict__ centroid_acc, uint32_t *__restrict__ overflow) {
+    uint32_t n = f.grid * f.grid;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        rc_ray r = grid_ray(f, k);
+        rc_hit h;
+        const RcTri *tri = nullptr;
+        if (!rc_trace_wide<false, false>(sc, r, h, nullptr, &tri)) atomicAdd(overflow, 1u);
+        if (hits) hits[k] = h;
+        float px = 0.f, py = 0.f, pz = 0.f;
+        if (h.hit) {  // sum_mul(bary, prim.vertices) (math.jl:52), bary = (1-u-v, u, v) (:2015)
+            float w = x_sub(x_sub(1.0f, h.bary_u), h.bary_v);
+            px = x_add(x_add(x_mul(w, tri->v0[0]), x_mul(h.bary_u, tri->v1[0])), x_mul(h.bary_v, tri->v2[0]));
+            py = x_add(x_add(x_mul(w, tri->v0[1]), x_mul(h.bary_u, tri->v1[1])), x_mul(h.bary_v, tri->v2[1]));
+            pz = x_add(x_add(x_mul(w, tri->v0[2]), x_mul(h.bary_u, tri->v1[2])), x_mul(h.bary_v, tri->v2[2]));
+            if (illum && h.metadata >= 1 && h.metadata <= n_illum) atomicAdd(&illum[h.metadata - 1], 1.0f);
+            if (centroid_acc) {
+                atomicAdd(&centroid_acc[0], (double)px);
+                atomicAdd(&centroid_acc[1], (double)py);
+                atomicAdd(&centroid_acc[2], (double)pz);
+                atomicAdd(&centroid_acc[3], 1.0);
+            }
+        }
+        if (points) { points[3 * (size_t)k] = px; points[3 * (size_t)k + 1] = py; points[3 * (size_t)k + 2] = pz; }
+    }
+}
+
+void rc_launch_grid_trace(cudaStream_t st, const RcScene &sc, const RcGridFrame &f, rc_hit *hits, float *points, float *illum, uint32_t n_illum,
+                          double *centroid_acc, uint32_t *overflow, int max_blocks) {
+    uint32_t n = f.grid * f.grid;
+    uint32_t want = (n + RC_TRACE_THREADS - 1) / RC_TRACE_THREADS;
+    int blocks = (int)(want < (uint32_t)max_blocks ? want : (uint32_t)max_blocks);
+    if (blocks < 1) blocks = 1;
+    k_grid_trace<<<blocks, RC_TRACE_THREADS, 0, st>>>(sc, f, hits, points, illum, n_illum, centroid_acc, overflow);
+}
+
+// ------------------------------------------------------------------------------------------------ view factors
+// One ray of view_factors! (src/kernels.jl:84-92) for source triangle `tri`: random_triangle_point (math.jl:158-174),
+// origin offset 0.01*normal (:91), random_hemisphere_uniform (math.jl:125-141), frame from get_orthogonal_basis (:143-156).
+// Randomness: counter RNG keyed by (seed, ray_index, dim) since Julia's task-local rand() is not reproducible.
+__device__ __forceinline__ rc_ray vf_make_ray(const RcTri *tri, unsigned long long seed, unsigned long long ray_index) {
+    f3 p1 = mk3(tri->v0[0], tri->v0[1], tri->v0[2]), p2 = mk3(tri->v1[0], tri->v1[1], tri->v1[2]), p3 = mk3(tri->v2[0], tri->v2[1], tri->v2[2]);
+    f3 normal = x_normalize(x_cross(x_sub3(p2, p1), x_sub3(p3, p1)));  // GB.orthogonal_vector ∝ (v2-v1)x(v3-v1)
+    f3 n = x_normalize(normal);
+    float ax = fabsf(normal.x), ay = fabsf(normal.y), az = fabsf(normal.z);
+    int mi = 0;
+    float best = ax;
+    if (ay < best) { best = ay; mi = 1; }
+    if (az < best) { best = az; mi = 2; }
+    f3 cand = mk3(mi == 0 ? 1.f : 0.f, mi == 1 ? 1.f : 0.f, mi == 2 ? 1.f : 0.f);
+    f3 vv = x_normalize(x_cross(n, cand));
+    f3 uu = x_normalize(x_cross(vv, n));
+    float r1 = rc_rng_uniform(seed, ray_index, 0), r2 = rc_rng_uniform(seed, ray_index, 1);
+    float sq = x_sqrt(r1);
+    float bu = x_sub(1.0f, sq), bv = x_mul(sq, x_sub(1.0f, r2)), bw = x_mul(sq, r2);
+    f3 pt = mk3(x_add(x_add(x_mul(bu, p1.x), x_mul(bv, p2.x)), x_mul(bw, p3.x)), x_add(x_add(x_mul(bu, p1.y), x_mul(bv, p2.y)), x_mul(bw, p3.y)),
+                x_add(x_add(x_mul(bu, p1.z), x_mul(bv, p2.z)), x_mul(bw, p3.z)));
+    rc_ray r;
+    r.origin[0] = x_add(pt.x, x_mul(normal.x, 0.01f));
+    r.origin[1] = x_add(pt.y, x_mul(normal.y, 0.01f));
+    r.origin[2] = x_add(pt.z, x_mul(normal.z, 0.01f));
+    float xi1 = rc_rng_uniform(seed, ray_index, 2), xi2 = rc_rng_uniform(seed, ray_index, 3);
+    float theta = acosf(xi1);
+    float phi = x_mul(x_mul(2.0f, 3.14159265358979323846f), xi2);
+    float st, ct, sp, cp;
+    sincosf(theta, &st, &ct);
+    sincosf(phi, &sp, &cp);
+    float xl = x_mul(st, cp), yl = x_mul(st, sp), zl = ct;
+    r.dir[0] = x_add(x_add(x_mul(uu.x, xl), x_mul(vv.x, yl)), x_mul(normal.x, zl));
+    r.dir[1] = x_add(x_add(x_mul(uu.y, xl), x_mul(vv.y, yl)), x_mul(normal.y, zl));
+    r.dir[2] = x_add(x_add(x_mul(uu.z, xl), x_mul(vv.z, yl)), x_mul(normal.z, zl));
+    r.tmin = 0.0f;
+    r.tmax = INFINITY;
+    return r;
+}
+
+__device__ __forceinline__ const RcTri *flat_tri(const RcFlatBlas *flat, uint32_t n_blas, uint32_t pos) {
+    uint32_t b = 0;
+    while (b + 1 < n_blas && pos >= flat[b + 1].offset) b++;
+    return flat[b].tris + (pos - flat[b].offset);
+}
+
+__global__ void __launch_bounds__(RC_TRACE_THREADS) k_view_factors(RcScene sc, const RcFlatBlas *__restrict__ flat, uint32_t n_blas, uint32_t n_prims, uint32_t rpt,
+                                                                   unsigned long long seed, uint32_t row_base, uint32_t n_rows, uint32_t n_cols, uint32_t *__restrict__ out,
+                                                                   rc_ray *__restrict__ rays_out, unsigned long long *__restrict__ skipped, uint32_t *__restrict__ overflow) {
+    unsigned long long total = (unsigned long long)n_prims * rpt;
+    for (unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (unsigned long long)gridDim.x * blockDim.x) {
+        uint32_t pos = (uint32_t)(g / rpt), i = (uint32_t)(g % rpt);
+        const RcTri *tri = flat_tri(flat, n_blas, pos);
+        uint32_t meta = tri->metadata;
+        if (meta < 1 || meta > n_cols) {  // the reference indexes result[meta, ...] unchecked (:85,95-97)
+            if (i == 0 && skipped && row_base == 0) atomicAdd(skipped, 1ull);
+            continue;
+        }
+        uint32_t row = meta - 1;
+        if (row < row_base || row >= row_base + n_rows) continue;
+        rc_ray r = vf_make_ray(tri, seed, (unsigned long long)row * rpt + i);
+        if (rays_out) { rays_out[(size_t)(row - row_base) * rpt + i] = r; continue; }
+        rc_hit h;
+        if (!rc_trace_wide<false, false>(sc, r, h, nullptr)) atomicAdd(overflow, 1u);
+        if (h.hit && h.metadata != meta && h.metadata >= 1 && h.metadata <= n_cols)
+            atomicAdd(&out[(size_t)(row - row_base) * n_cols + (h.metadata - 1)], 1u);
+    }
+}
+
+void rc_launch_view_factors(cudaStream_t st, const RcScene &sc, const RcFlatBlas *d_flat, uint32_t n_blas, uint32_t n_prims, uint32_t rpt, unsigned long long seed,
+                            uint32_t row_base, uint32_t n_rows, uint32_t n_cols, uint32_t *out, rc_ray *rays_out, unsigned long long *skipped,
+                            uint32_t *overflow, int max_blocks) {
+    unsigned long long total = (unsigned long long)n_prims * rpt;
+    if (total == 0) return;
+    unsigned long long want = (total + RC_TRACE_THREADS - 1) / RC_TRACE_THREADS;
+    int blocks = (int)(want < (unsigned long long)max_blocks ? want : (unsigned long long)max_blocks);
+    k_view_factors<<<blocks, RC_TRACE_THREADS, 0, st>>>(sc, d_flat, n_blas, n_prims, rpt, seed, row_base, n_rows, n_cols, out, rays_out, skipped, overflow);
+}
+
+__global__ void k_flat_metadata(const RcFlatBlas *__restrict__ flat, uint32_t n_blas, uint32_t n_prims, uint32_t *__restrict__ out) {
+    uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= n_prims) return;
+    out[pos] = flat_tri(flat, n_blas, pos)->metadata;
+}
+
+void rc_launch_flat_metadata(cudaStream_t st, const RcFlatBlas *d_flat, uint32_t n_blas, uint32_t n_prims, uint32_t *out) {
+    if (n_prims == 0) return;
+    k_flat_metadata<<<(n_prims + 255) / 256, 256, 0, st>>>(d_flat, n_blas, n_prims, out);
+}

@@ -1,0 +1,784 @@
+// rc_api.cu — the C ABI of libraycore_cuda.so (include/raycore_cuda.h): the mutable-TLAS lifecycle of
+// src/instanced-bvh.jl:261-1134 (handles, push!/delete!/update*/sync!, compaction) kept on the host in C++,
+// with all geometry work on the GPU (rc_build.cu), and the batched query / analysis entry points.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "rc_build.h"
+#include "rc_device.cuh"
+#include "rc_trace.h"
+
+namespace {
+
+struct HandleInfo {
+    uint32_t start, count;
+    bool deleted;
+};
+
+std::string g_create_error;
+
+}  // namespace
+
+struct rc_context {
+    int device = 0;
+    cudaStream_t stream = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    std::string last_error;
+    std::vector<RcDeviceBlas> blas;           // blas_index b+1 <-> blas[b]
+    std::vector<rc_instance_desc> instances;  // host mirror of tlas.instances
+    std::map<uint32_t, HandleInfo> handles;   // ordered by id (Julia: Dict{TLASHandle,UnitRange})
+    bool dirty = true, transforms_dirty = false, built = false;
+    uint32_t next_handle = 1;
+    RcDeviceTlas tlas;
+    RcFlatBlas *d_flat = nullptr;
+    uint32_t n_flat_blas = 0, n_flat_prims = 0, synced_blas_nodes = 0, synced_tlas_nodes = 0;
+    // trace resources
+    unsigned long long *d_work = nullptr;
+    RcCounters *d_counters = nullptr;
+    uint32_t *d_overflow = nullptr;
+    rc_ray *d_rays = nullptr;
+    rc_hit *d_hits = nullptr;
+    size_t cap_rays = 0, cap_hits = 0;
+    static const int NEV = 8;
+    cudaEvent_t ev_h2d[NEV], ev_k[NEV], ev_t0 = nullptr, ev_t1 = nullptr;
+    float last_ms = 0.f;
+    uint32_t last_launches = 0;
+    int max_blocks = 148;
+};
+
+#define RC_FAIL(ctx, code, msg)        \
+    do {                               \
+        (ctx)->last_error = (msg);     \
+        return (code);                 \
+    } while (0)
+
+#define RC_CUDA(ctx, call)                                                                       \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess) {                                                                 \
+            (ctx)->last_error = std::string(#call) + ": " + cudaGetErrorString(e_);              \
+            return e_ == cudaErrorMemoryAllocation ? RC_ERR_OUT_OF_MEMORY : RC_ERR_CUDA;         \
+        }                                                                                        \
+    } while (0)
+
+static inline void use_device(const rc_context *ctx) { cudaSetDevice(ctx->device); }
+
+static RcScene make_scene(const rc_context *ctx) {
+    RcScene sc;
+    sc.tlas4 = ctx->tlas.nodes4;
+    sc.tlas2 = ctx->tlas.nodes2;
+    sc.inst = ctx->tlas.rec;
+    sc.aux = ctx->tlas.aux;
+    sc.n_instances = ctx->tlas.n;
+    return sc;
+}
+
+extern "C" {
+
+int32_t rc_abi_version(void) { return RC_ABI_VERSION; }
+
+const char *rc_last_error(const rc_context *ctx) { return ctx ? ctx->last_error.c_str() : g_create_error.c_str(); }
+
+int32_t rc_create(int32_t device, rc_context **out) {
+    if (!out) return RC_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_error = std::string("no CUDA device available: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                         " (libraycore_cuda has no CPU fallback)";
+        return RC_ERR_CUDA;
+    }
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+    }
+    if (device >= count) { g_create_error = "device index out of range"; return RC_ERR_INVALID_ARGUMENT; }
+    rc_context *ctx = new rc_context();
+    ctx->device = device;
+    for (int k = 0; k < 3; k++) { ctx->tlas.root_aabb[k] = INFINITY; ctx->tlas.root_aabb[3 + k] = -INFINITY; }
+#define CREATE_CK(call)                                                          \
+    do {                                                                         \
+        cudaError_t e2 = (call);                                                 \
+        if (e2 != cudaSuccess) {                                                 \
+            g_create_error = std::string(#call) + ": " + cudaGetErrorString(e2); \
+            delete ctx;                                                          \
+            return RC_ERR_CUDA;                                                  \
+        }                                                                        \
+    } while (0)
+    CREATE_CK(cudaSetDevice(device));
+    CREATE_CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CREATE_CK(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+    CREATE_CK(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < rc_context::NEV; i++) {
+        CREATE_CK(cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
+        CREATE_CK(cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming));
+    }
+    CREATE_CK(cudaEventCreate(&ctx->ev_t0));
+    CREATE_CK(cudaEventCreate(&ctx->ev_t1));
+    CREATE_CK(cudaMalloc(&ctx->d_work, sizeof(unsigned long long)));
+    CREATE_CK(cudaMalloc(&ctx->d_counters, sizeof(RcCounters)));
+    CREATE_CK(cudaMalloc(&ctx->d_overflow, sizeof(uint32_t)));
+    CREATE_CK(cudaMemset(ctx->d_counters, 0, sizeof(RcCounters)));
+    CREATE_CK(cudaMemset(ctx->d_overflow, 0, sizeof(uint32_t)));
+    // keep freed blocks cached in the stream-ordered pool: rebuild-per-frame workloads reuse them
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long thresh = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
+    }
+    ctx->max_blocks = rc_trace_max_blocks(device);
+#undef CREATE_CK
+    *out = ctx;
+    return RC_OK;
+}
+
+int32_t rc_destroy(rc_context *ctx) {
+    if (!ctx) return RC_OK;
+    use_device(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->s_h2d);
+    cudaStreamSynchronize(ctx->s_d2h);
+    for (auto &b : ctx->blas) rc_free_blas(&b, ctx->stream);
+    rc_free_tlas(&ctx->tlas, ctx->stream);
+    if (ctx->d_flat) cudaFreeAsync(ctx->d_flat, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_work); cudaFree(ctx->d_counters); cudaFree(ctx->d_overflow);
+    if (ctx->d_rays) cudaFree(ctx->d_rays);
+    if (ctx->d_hits) cudaFree(ctx->d_hits);
+    for (int i = 0; i < rc_context::NEV; i++) { cudaEventDestroy(ctx->ev_h2d[i]); cudaEventDestroy(ctx->ev_k[i]); }
+    cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1);
+    cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->s_h2d); cudaStreamDestroy(ctx->s_d2h);
+    delete ctx;
+    return RC_OK;
+}
+
+void *rc_stream(rc_context *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+// ------------------------------------------------------------------------------------------------ mutation
+static int32_t build_blas_from(rc_context *ctx, const float *verts, uint32_t n_faces, const uint32_t *face_meta, uint32_t flags, RcDeviceBlas *out) {
+    if (!verts || n_faces == 0) RC_FAIL(ctx, RC_ERR_NO_VALID_TRIANGLES, "Geometry has no valid triangles");
+    const float *d_verts = verts;
+    const uint32_t *d_meta = face_meta;
+    float *tmp_v = nullptr;
+    uint32_t *tmp_m = nullptr;
+    if (!(flags & RC_VERTS_ON_DEVICE)) {
+        RC_CUDA(ctx, cudaMallocAsync(&tmp_v, sizeof(float) * 9 * (size_t)n_faces, ctx->stream));
+        RC_CUDA(ctx, cudaMemcpyAsync(tmp_v, verts, sizeof(float) * 9 * (size_t)n_faces, cudaMemcpyHostToDevice, ctx->stream));
+        d_verts = tmp_v;
+        if (face_meta) {
+            RC_CUDA(ctx, cudaMallocAsync(&tmp_m, sizeof(uint32_t) * (size_t)n_faces, ctx->stream));
+            RC_CUDA(ctx, cudaMemcpyAsync(tmp_m, face_meta, sizeof(uint32_t) * (size_t)n_faces, cudaMemcpyHostToDevice, ctx->stream));
+            d_meta = tmp_m;
+        }
+    }
+    std::string err;
+    bool ok = rc_build_blas(ctx->stream, d_verts, d_meta, n_faces, out, err);
+    if (tmp_v) cudaFreeAsync(tmp_v, ctx->stream);
+    if (tmp_m) cudaFreeAsync(tmp_m, ctx->stream);
+    if (!ok) {
+        rc_free_blas(out, ctx->stream);
+        if (err == "Geometry has no valid triangles") RC_FAIL(ctx, RC_ERR_NO_VALID_TRIANGLES, err);
+        RC_FAIL(ctx, RC_ERR_CUDA, err);
+    }
+    return RC_OK;
+}
+
+int32_t rc_push(rc_context *ctx, const float *verts, uint32_t n_faces, const uint32_t *face_meta, const float *transforms, const float *inv_transforms,
+                const uint32_t *instance_ids, uint32_t m, uint32_t flags, uint32_t *handle_out) {
+    if (!ctx) return RC_ERR_INVALID_ARGUMENT;
+    use_device(ctx);
+    if (!transforms || m == 0 || !handle_out) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "rc_push: transforms, m >= 1 and handle_out are required");
+    RcDeviceBlas b;
+    int32_t rc = build_blas_from(ctx, verts, n_faces, face_meta, flags, &b);
+    if (rc != RC_OK) return rc;
+    ctx->blas.push_back(b);
+    uint32_t blas_idx = (uint32_t)ctx->blas.size();  // :607
+    uint32_t start = (uint32_t)ctx->instances.size();
+    for (uint32_t i = 0; i < m; i++) {
+        rc_instance_desc d;
+        d.blas_index = blas_idx;
+        d.instance_id = instance_ids ? instance_ids[i] : 0u;  // :672
+        memcpy(d.transform, transforms + 12 * (size_t)i, 48);
+        if (inv_transforms) memcpy(d.inv_transform, inv_transforms + 12 * (size_t)i, 48);
+        else x_mat3x4_inverse(d.transform, d.inv_transform);  // :644, :673
+        d.flags = 0;
+        ctx->instances.push_back(d);
+    }
+    uint32_t h = ctx->next_handle++;  // append_instances_with_handle!, :612-623
+    ctx->handles[h] = HandleInfo{start, m, false};
+    ctx->dirty = true;
+    *handle_out = h;
+    return RC_OK;
+}
+
+static int32_t find_handle(rc_context *ctx, uint32_t handle, HandleInfo **out) {
+    auto it = ctx->handles.find(handle);
+    if (it == ctx->handles.end()) RC_FAIL(ctx, RC_ERR_INVALID_HANDLE, "Invalid handle");
+    if (it->second.deleted) RC_FAIL(ctx, RC_ERR_DELETED_HANDLE, "Handle has been deleted");
+    *out = &it->second;
+    return RC_OK;
+}
+
+int32_t rc_delete(rc_context *ctx, uint32_t handle, int32_t *deleted) {  // :690-699
+    if (!ctx) return RC_ERR_INVALID_ARGUMENT;
+    if (deleted) *deleted = 0;
+    auto it = ctx->handles.find(handle);
+    if (it == ctx->handles.end() || it->second.deleted) return RC_OK;
+    it->second.deleted = true;
+    ctx->dirty = true;
+    if (deleted) *deleted = 1;
+    return RC_OK;
+}
+
+int32_t rc_update_transforms(rc_context *ctx, uint32_t handle, const float *transforms, const float *inv_transforms, uint32_t m) {  // :755-797
+    if (!ctx) return RC_ERR_INVALID_ARGUMENT;
+    HandleInfo *hi = nullptr;
+    int32_t rc = find_handle(ctx, handle, &hi);
+    if (rc != RC_OK) return rc;
+    if (!transforms) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "rc_update_transforms: transforms is NULL");
+    if (m != hi->count)
+        RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "Transform count (" + std::to_string(m) + ") != instance count (" + std::to_string(hi->count) + ")");
+    for (uint32_t i = 0; i < m; i++) {  // update_instance_transforms_offset_kernel!, kernels.jl:455-476
+        rc_instance_desc &d = ctx->instances[hi->start + i];
+        memcpy(d.transform, transforms + 12 * (size_t)i, 48);
+        if (inv_transforms) memcpy(d.inv_transform, inv_transforms + 12 * (size_t)i, 48);
+        else x_mat3x4_inverse(d.transform, d.inv_transform);
+    }
+    ctx->transforms_dirty = true;
+    return RC_OK;
+}
+
+int32_t rc_update_geometry(rc_context *ctx, uint32_t handle, const float *verts, uint32_t n_faces, const uint32_t *face_meta, uint32_t flags) {  // :808-857
+    if (!ctx) return RC_ERR_INVALID_ARGUMENT;
+    use_device(ctx);
+    HandleInfo *hi = nullptr;
+    int32_t rc = find_handle(ctx, handle, &hi);
+    if (rc != RC_OK) return rc;
+    if (hi->count == 0) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "Handle has no instances");
+    uint32_t blas_idx = ctx->instances[hi->start].blas_index;
+    RcDeviceBlas nb;
+    rc = build_blas_from(ctx, verts, n_faces, face_meta, flags, &nb);
+    if (rc != RC_OK) {
+        if (rc == RC_ERR_NO_VALID_TRIANGLES) ctx->last_error = "New geometry has no valid triangles";
+        return rc;
+    }
+    rc_free_blas(&ctx->blas[blas_idx - 1], ctx->stream);
+    ctx->blas[blas_idx - 1] = nb;
+    ctx->dirty = true;
+    return RC_OK;
+}
+
+// compact_instances!, :996-1065.  Handles are visited in ascending id order (Julia iterates its Dict in hash
+// order, which no caller can rely on); unreferenced BLASes are freed and blas_index values remapped.
+static void compact_instances(rc_context *ctx) {
+    std::vector<rc_instance_desc> ni;
+    ni.reserve(ctx->instances.size());
+    for (auto it = ctx->handles.begin(); it != ctx->handles.end();) {
+        if (it->second.deleted) { it = ctx->handles.erase(it); continue; }
+        uint32_t ns = (uint32_t)ni.size();
+        ni.insert(ni.end(), ctx->instances.begin() + it->second.start, ctx->instances.begin() + it->second.start + it->second.count);
+        it->second.start = ns;
+        ++it;
+    }
+    std::vector<uint32_t> remap(ctx->blas.size() + 1, 0);
+    for (auto &d : ni) remap[d.blas_index] = 1;
+    uint32_t used = 0;
+    for (size_t b = 1; b < remap.size(); b++) used += remap[b];
+    if (!ctx->blas.empty() && used < ctx->blas.size()) {
+        std::vector<RcDeviceBlas> nb;
+        uint32_t k = 0;
+        for (size_t b = 1; b < remap.size(); b++) {
+            if (remap[b]) { remap[b] = ++k; nb.push_back(ctx->blas[b - 1]); }
+            else rc_free_blas(&ctx->blas[b - 1], ctx->stream);
+        }
+        for (auto &d : ni) d.blas_index = remap[d.blas_index];
+        ctx->blas.swap(nb);
+    }
+    ctx->instances.swap(ni);
+}
+
+static int32_t rebuild(rc_context *ctx) {  // rebuild_bvh! :962-993 + build_flat_blas_arrays! :470-517 + rebuild_static_tlas! :930-959
+    bool any_deleted = false;
+    for (auto &kv : ctx->handles) any_deleted |= kv.second.deleted;
+    if (any_deleted) compact_instances(ctx);
+    std::vector<RcBlasPtrs> ptrs(ctx->blas.size());
+    std::vector<float> roots(6 * ctx->blas.size());
+    std::vector<RcFlatBlas> flat(ctx->blas.size());
+    uint32_t off = 0, nodes = 0;
+    for (size_t b = 0; b < ctx->blas.size(); b++) {
+        const RcDeviceBlas &B = ctx->blas[b];
+        ptrs[b] = RcBlasPtrs{B.nodes2, B.nodes4, B.tris, B.n, 0};
+        memcpy(&roots[6 * b], B.root_aabb, 24);
+        flat[b] = RcFlatBlas{B.tris, off, B.n};
+        off += B.n;
+        nodes += 2 * B.n - 1;
+    }
+    uint32_t n = (uint32_t)ctx->instances.size();
+    std::string err;
+    if (!rc_build_tlas(ctx->stream, ctx->instances.data(), n, ptrs, roots, &ctx->tlas, err)) RC_FAIL(ctx, RC_ERR_CUDA, err);
+    if (ctx->d_flat) { cudaFreeAsync(ctx->d_flat, ctx->stream); ctx->d_flat = nullptr; }
+    // the reference drains the flat arrays when no instance is left (:969-978) but keeps every BLAS otherwise
+    ctx->n_flat_blas = n == 0 && ctx->blas.empty() ? 0 : (uint32_t)flat.size();
+    ctx->n_flat_prims = off;
+    ctx->synced_blas_nodes = nodes;
+    ctx->synced_tlas_nodes = n == 0 ? 0 : (2 * n - 1 > 1 ? 2 * n - 1 : 1);
+    if (!flat.empty()) {
+        RC_CUDA(ctx, cudaMallocAsync(&ctx->d_flat, sizeof(RcFlatBlas) * flat.size(), ctx->stream));
+        RC_CUDA(ctx, cudaMemcpyAsync(ctx->d_flat, flat.data(), sizeof(RcFlatBlas) * flat.size(), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->dirty = false;
+    ctx->transforms_dirty = false;
+    ctx->built = true;
+    return RC_OK;
+}
+
+int32_t rc_sync(rc_context *ctx, int32_t *action) {  // sync!, :894-921
+    if (!ctx) return RC_ERR_INVALID_ARGUMENT;
+    if (action) *action = RC_SYNC_NONE;
+    if (!ctx->dirty && !ctx->transforms_dirty && ctx->built) return RC_OK;  // clean fast path: no GPU work, no sync (:898-900)
+    use_device(ctx);
+    if (ctx->dirty || !ctx->built) {
+        int32_t rc = rebuild(ctx);
+        if (rc != RC_OK) return rc;
+        if (action) *action = RC_SYNC_REBUILD;
+    } else {
+        std::string err;  // refit_tlas!, :2197-2222
+        if (!rc_refit_tlas(ctx->stream, ctx->instances.data(), (uint32_t)ctx->instances.size(), &ctx->tlas, err)) RC_FAIL(ctx, RC_ERR_CUDA, err);
+        ctx->transforms_dirty = false;
+        if (action) *action = RC_SYNC_REFIT;
+    }
+    RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // KA.synchronize, :919
+    return RC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ introspection
+int32_t rc_is_valid(const rc_context *ctx, uint32_t handle) {
+    if (!ctx) return 0;
+    auto it = ctx->handles.find(handle);
+    return it != ctx->handles.end() && !it->second.deleted;
+}
+uint32_t rc_n_total_instances(const rc_context *ctx) { return ctx ? (uint32_t)ctx->instances.size() : 0; }
+uint32_t rc_n_instances(const rc_context *ctx) {  // :2391-2398
+    if (!ctx) return 0;
+    uint32_t pending = 0;
+    for (auto &kv : ctx->handles)
+        if (kv.second.deleted) pending += kv.second.count;
+    return (uint32_t)ctx->instances.size() - pending;
+}
+uint32_t rc_n_instances_of(const rc_context *ctx, uint32_t handle) {
+    if (!ctx) return 0;
+    auto it = ctx->handles.find(handle);
+    return (it == ctx->handles.end() || it->second.deleted) ? 0 : it->second.count;
+}
+uint32_t rc_n_geometries(const rc_context *ctx) { return ctx ? (uint32_t)ctx->blas.size() : 0; }
+int32_t rc_is_dirty(const rc_context *ctx, int32_t *dirty, int32_t *transforms_dirty) {
+    if (!ctx) return RC_ERR_INVALID_ARGUMENT;
+    if (dirty) *dirty = ctx->dirty;
+    if (transforms_dirty) *transforms_dirty = ctx->transforms_dirty;
+    return RC_OK;
+}
+int32_t rc_get_instances(const rc_context *cctx, uint32_t handle, rc_instance_desc *out) {
+    rc_context *ctx = const_cast<rc_context *>(cctx);
+    if (!ctx || !out) return RC_ERR_INVALID_ARGUMENT;
+    HandleInfo *hi = nullptr;
+    int32_t rc = find_handle(ctx, handle, &hi);
+    if (rc != RC_OK) return rc;
+    memcpy(out, ctx->instances.data() + hi->start, sizeof(rc_instance_desc) * hi->count);
+    return RC_OK;
+}
+int32_t rc_world_bound(const rc_context *ctx, float out[6]) {
+    if (!ctx || !out) return RC_ERR_INVALID_ARGUMENT;
+    memcpy(out, ctx->tlas.root_aabb, 24);
+    return RC_OK;
+}
+int32_t rc_wait(rc_context *ctx) {
+    if (!ctx) return RC_ERR_INVALID_ARGUMENT;
+    use_device(ctx);
+    RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    RC_CUDA(ctx, cudaStreamSynchronize(ctx->s_h2d));
+    RC_CUDA(ctx, cudaStreamSynchronize(ctx->s_d2h));
+    return RC_OK;
+}
+int32_t rc_sizes(const rc_context *ctx, uint32_t *tlas_nodes, uint32_t *blas_nodes, uint32_t *blas_prims, uint32_t *pending_deletes) {
+    if (!ctx) return RC_ERR_INVALID_ARGUMENT;
+    if (tlas_nodes) *tlas_nodes = ctx->synced_tlas_nodes;
+    if (blas_nodes) *blas_nodes = ctx->synced_blas_nodes;
+    if (blas_prims) *blas_prims = ctx->n_flat_prims;
+    if (pending_deletes) {
+        uint32_t p = 0;
+        for (auto &kv : ctx->handles) p += kv.second.deleted ? 1u : 0u;
+        *pending_deletes = p;
+    }
+    return RC_OK;
+}
+
+static int32_t read_nodes2(rc_context *ctx, const RcNode2 *d_nodes, uint32_t count, rc_bvh_node2 *out, uint32_t capacity) {
+    if (capacity < count) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "capacity too small");
+    if (count == 0) return RC_OK;
+    std::vector<RcNode2> tmp(count);
+    RC_CUDA(ctx, cudaMemcpyAsync(tmp.data(), d_nodes, sizeof(RcNode2) * count, cudaMemcpyDeviceToHost, ctx->stream));
+    RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (uint32_t i = 0; i < count; i++) memcpy(&out[i], &tmp[i], sizeof(rc_bvh_node2));  // drop the pad word
+    return RC_OK;
+}
+int32_t rc_read_tlas_nodes(rc_context *ctx, rc_bvh_node2 *out, uint32_t capacity) {
+    if (!ctx || !out) return RC_ERR_INVALID_ARGUMENT;
+    use_device(ctx);
+    if (!ctx->built || ctx->dirty) RC_FAIL(ctx, RC_ERR_NOT_SYNCED, "call rc_sync first");
+    return read_nodes2(ctx, ctx->tlas.nodes2, ctx->synced_tlas_nodes, out, capacity);
+}
+int32_t rc_read_blas_nodes(rc_context *ctx, uint32_t blas_index, rc_bvh_node2 *out, uint32_t capacity) {
+    if (!ctx || !out) return RC_ERR_INVALID_ARGUMENT;
+    use_device(ctx);
+    if (blas_index < 1 || blas_index > ctx->blas.size()) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "blas_index out of range");
+    const RcDeviceBlas &B = ctx->blas[blas_index - 1];
+    return read_nodes2(ctx, B.nodes2, 2 * B.n - 1, out, capacity);
+}
+int32_t rc_read_blas_order(rc_context *ctx, uint32_t blas_index, uint32_t *out, uint32_t capacity) {
+    if (!ctx || !out) return RC_ERR_INVALID_ARGUMENT;
+    use_device(ctx);
+    if (blas_index < 1 || blas_index > ctx->blas.size()) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "blas_index out of range");
+    const RcDeviceBlas &B = ctx->blas[blas_index - 1];
+    if (capacity < B.n) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "capacity too small");
+    std::vector<RcTri> tmp(B.n);
+    RC_CUDA(ctx, cudaMemcpyAsync(tmp.data(), B.tris, sizeof(RcTri) * B.n, cudaMemcpyDeviceToHost, ctx->stream));
+    RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (uint32_t i = 0; i < B.n; i++) out[i] = tmp[i].prim_id;
+    return RC_OK;
+}
+int32_t rc_read_blas_faces(rc_context *ctx, uint32_t blas_index, uint32_t *out, uint32_t capacity) {
+    if (!ctx || !out) return RC_ERR_INVALID_ARGUMENT;
+    use_device(ctx);
+    if (blas_index < 1 || blas_index > ctx->blas.size()) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "blas_index out of range");
+    const RcDeviceBlas &B = ctx->blas[blas_index - 1];
+    if (capacity < B.n) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "capacity too small");
+    std::vector<RcTri> tmp(B.n);
+    RC_CUDA(ctx, cudaMemcpyAsync(tmp.data(), B.tris, sizeof(RcTri) * B.n, cudaMemcpyDeviceToHost, ctx->stream));
+    RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (uint32_t i = 0; i < B.n; i++) out[tmp[i].prim_id] = tmp[i].face_index;
+    return RC_OK;
+}
+int32_t rc_get_instance_handles(const rc_context *ctx, uint32_t *out, uint32_t capacity) {
+    if (!ctx || !out) return RC_ERR_INVALID_ARGUMENT;
+    if (capacity < ctx->instances.size()) return RC_ERR_INVALID_ARGUMENT;
+    for (auto &kv : ctx->handles)
+        for (uint32_t i = 0; i < kv.second.count; i++) out[kv.second.start + i] = kv.first;
+    return RC_OK;
+}
+uint32_t rc_blas_n_prims(const rc_context *ctx, uint32_t blas_index) {
+    if (!ctx || blas_index < 1 || blas_index > ctx->blas.size()) return 0;
+    return ctx->blas[blas_index - 1].n;
+}
+
+// ------------------------------------------------------------------------------------------------ queries
+static int32_t ensure_capacity(rc_context *ctx, void **buf, size_t *cap, size_t bytes) {
+    if (*cap >= bytes) return RC_OK;
+    if (*buf) { cudaFree(*buf); *buf = nullptr; *cap = 0; }
+    RC_CUDA(ctx, cudaMalloc(buf, bytes));
+    *cap = bytes;
+    return RC_OK;
+}
+
+static int32_t check_overflow(rc_context *ctx) {
+    uint32_t ov = 0;
+    RC_CUDA(ctx, cudaMemcpyAsync(&ov, ctx->d_overflow, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ov) {
+        cudaMemsetAsync(ctx->d_overflow, 0, 4, ctx->stream);
+        RC_FAIL(ctx, RC_ERR_STACK_OVERFLOW, "traversal stack overflow for " + std::to_string(ov) + " ray(s)");
+    }
+    return RC_OK;
+}
+
+static int32_t trace_common(rc_context *ctx, const rc_ray *rays, rc_hit *hits, uint64_t n, uint32_t flags, bool any) {
+    if (!ctx) return RC_ERR_INVALID_ARGUMENT;
+    use_device(ctx);
+    if (n == 0) return RC_OK;
+    if (!rays || !hits) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "rays / hits is NULL");
+    if (!ctx->built || ctx->dirty || ctx->transforms_dirty) RC_FAIL(ctx, RC_ERR_NOT_SYNCED, "TLAS has pending mutations: call rc_sync before tracing");
+    const bool rays_dev = flags & RC_RAYS_ON_DEVICE, hits_dev = flags & RC_HITS_ON_DEVICE;
+    RcTraceLaunch L;
+    L.scene = make_scene(ctx);
+    L.any = any;
+    L.wide = !(flags & RC_MODE_REFERENCE_ORDER);
+    L.count = flags & RC_COUNTERS;
+    L.work = ctx->d_work;
+    L.counters = ctx->d_counters;
+    L.overflow = ctx->d_overflow;
+    L.max_blocks = ctx->max_blocks;
+    std::string err;
+    ctx->last_launches = 0;
+    if (rays_dev && hits_dev) {
+        L.rays = rays; L.hits = hits; L.n = n;
+        cudaEventRecord(ctx->ev_t0, ctx->stream);
+        if (!rc_launch_trace(ctx->stream, L, err)) RC_FAIL(ctx, RC_ERR_CUDA, err);
+        cudaEventRecord(ctx->ev_t1, ctx->stream);
+        ctx->last_launches = 1;
+        if (flags & RC_NO_SYNC) return RC_OK;
+        RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaEventElapsedTime(&ctx->last_ms, ctx->ev_t0, ctx->ev_t1);
+        return check_overflow(ctx);
+    }
+    // host buffers: stage through device memory in chunks; H2D of chunk c+1, trace of chunk c and D2H of chunk c-1 overlap
+    const rc_ray *d_rays = rays;
+    rc_hit *d_hits = hits;
+    if (!rays_dev) {
+        int32_t rc = ensure_capacity(ctx, (void **)&ctx->d_rays, &ctx->cap_rays, n * sizeof(rc_ray));
+        if (rc != RC_OK) return rc;
+        d_rays = ctx->d_rays;
+    }
+    if (!hits_dev) {
+        int32_t rc = ensure_capacity(ctx, (void **)&ctx->d_hits, &ctx->cap_hits, n * sizeof(rc_hit));
+        if (rc != RC_OK) return rc;
+        d_hits = ctx->d_hits;
+    }
+    const uint64_t chunk = 1ull << 20;
+    cudaEventRecord(ctx->ev_t0, ctx->stream);
+    int c = 0;
+    for (uint64_t off = 0; off < n; off += chunk, c++) {
+        uint64_t cn = n - off < chunk ? n - off : chunk;
+        int e = c % rc_context::NEV;
+        if (!rays_dev) {
+            RC_CUDA(ctx, cudaMemcpyAsync((void *)(d_rays + off), rays + off, cn * sizeof(rc_ray), cudaMemcpyHostToDevice, ctx->s_h2d));
+            RC_CUDA(ctx, cudaEventRecord(ctx->ev_h2d[e], ctx->s_h2d));
+            RC_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[e], 0));
+        }
+        L.rays = d_rays + off; L.hits = d_hits + off; L.n = cn;
+        if (!rc_launch_trace(ctx->stream, L, err)) RC_FAIL(ctx, RC_ERR_CUDA, err);
+        ctx->last_launches++;
+        if (!hits_dev) {
+            RC_CUDA(ctx, cudaEventRecord(ctx->ev_k[e], ctx->stream));
+            RC_CUDA(ctx, cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_k[e], 0));
+            RC_CUDA(ctx, cudaMemcpyAsync(hits + off, d_hits + off, cn * sizeof(rc_hit), cudaMemcpyDeviceToHost, ctx->s_d2h));
+        }
+    }
+    cudaEventRecord(ctx->ev_t1, ctx->stream);
+    RC_CUDA(ctx, cudaStreamSynchronize(ctx->s_h2d));
+    RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    RC_CUDA(ctx, cudaStreamSynchronize(ctx->s_d2h));
+    cudaEventElapsedTime(&ctx->last_ms, ctx->ev_t0, ctx->ev_t1);
+    return check_overflow(ctx);
+}
+
+int32_t rc_trace_closest(rc_context *ctx, const rc_ray *rays, rc_hit *hits, uint64_t n, uint32_t flags) { return trace_common(ctx, rays, hits, n, flags, false); }
+int32_t rc_trace_any(rc_context *ctx, const rc_ray *rays, rc_hit *hits, uint64_t n, uint32_t flags) { return trace_common(ctx, rays, hits, n, flags, true); }
+
+int32_t rc_get_counters(rc_context *ctx, uint64_t out[6], int32_t reset) {
+    if (!ctx || !out) return RC_ERR_INVALID_ARGUMENT;
+    use_device(ctx);
+    RcCounters c;
+    RC_CUDA(ctx, cudaMemcpyAsync(&c, ctx->d_counters, sizeof c, cudaMemcpyDeviceToHost, ctx->stream));
+    if (reset) RC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof c, ctx->stream));
+    RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    out[0] = c.rays; out[1] = c.nodes; out[2] = c.box_tests; out[3] = c.tri_tests; out[4] = c.inst_entries; out[5] = c.max_stack;
+    return RC_OK;
+}
+float rc_last_kernel_ms(const rc_context *ctx) { return ctx ? ctx->last_ms : 0.f; }
+uint32_t rc_last_kernel_launches(const rc_context *ctx) { return ctx ? ctx->last_launches : 0; }
+
+// ------------------------------------------------------------------------------------------------ analysis
+static int32_t require_synced(rc_context *ctx) {
+    if (!ctx->built || ctx->dirty || ctx->transforms_dirty) RC_FAIL(ctx, RC_ERR_NOT_SYNCED, "TLAS has pending mutations: call rc_sync first");
+    return RC_OK;
+}
+
+static int32_t grid_common(rc_context *ctx, const float viewdir[3], uint32_t grid, rc_hit *hits, float *points, float *illum, uint32_t n_illum, double *centroid4) {
+    use_device(ctx);
+    int32_t rc = require_synced(ctx);
+    if (rc != RC_OK) return rc;
+    if (!viewdir || grid == 0) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "viewdir / grid");
+    size_t n = (size_t)grid * grid;
+    RcGridFrame f;
+    rc_grid_frame(ctx->tlas.root_aabb, viewdir, grid, &f);
+    rc_hit *d_hits = nullptr;
+    float *d_points = nullptr, *d_illum = nullptr;
+    double *d_cent = nullptr;
+    if (hits) RC_CUDA(ctx, cudaMallocAsync(&d_hits, n * sizeof(rc_hit), ctx->stream));
+    if (points) RC_CUDA(ctx, cudaMallocAsync(&d_points, n * 3 * sizeof(float), ctx->stream));
+    if (illum) {
+        RC_CUDA(ctx, cudaMallocAsync(&d_illum, (size_t)n_illum * sizeof(float), ctx->stream));
+        RC_CUDA(ctx, cudaMemsetAsync(d_illum, 0, (size_t)n_illum * sizeof(float), ctx->stream));
+    }
+    if (centroid4) {
+        RC_CUDA(ctx, cudaMallocAsync(&d_cent, 4 * sizeof(double), ctx->stream));
+        RC_CUDA(ctx, cudaMemsetAsync(d_cent, 0, 4 * sizeof(double), ctx->stream));
+    }
+    rc_launch_grid_trace(ctx->stream, make_scene(ctx), f, d_hits, d_points, d_illum, n_illum, d_cent, ctx->d_overflow, ctx->max_blocks);
+    ctx->last_launches = 1;
+    if (hits) RC_CUDA(ctx, cudaMemcpyAsync(hits, d_hits, n * sizeof(rc_hit), cudaMemcpyDeviceToHost, ctx->stream));
+    if (points) RC_CUDA(ctx, cudaMemcpyAsync(points, d_points, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (illum) RC_CUDA(ctx, cudaMemcpyAsync(illum, d_illum, (size_t)n_illum * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (centroid4) RC_CUDA(ctx, cudaMemcpyAsync(centroid4, d_cent, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    for (void *p : {(void *)d_hits, (void *)d_points, (void *)d_illum, (void *)d_cent})
+        if (p) cudaFreeAsync(p, ctx->stream);
+    RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return check_overflow(ctx);
+}
+
+int32_t rc_hits_from_grid(rc_context *ctx, const float viewdir[3], uint32_t grid, rc_hit *hits, float *points) {
+    if (!ctx || !hits) return RC_ERR_INVALID_ARGUMENT;
+    return grid_common(ctx, viewdir, grid, hits, points, nullptr, 0, nullptr);
+}
+
+int32_t rc_get_illumination(rc_context *ctx, const float viewdir[3], uint32_t grid, float *out, uint32_t n_out) {
+    if (!ctx || !out) return RC_ERR_INVALID_ARGUMENT;
+    if (n_out == 0) return RC_OK;
+    return grid_common(ctx, viewdir, grid, nullptr, nullptr, out, n_out, nullptr);
+}
+
+int32_t rc_get_centroid(rc_context *ctx, const float viewdir[3], uint32_t grid, float centroid[3], uint32_t *n_hits, float *points) {
+    if (!ctx || !centroid) return RC_ERR_INVALID_ARGUMENT;
+    size_t n = (size_t)grid * grid;
+    std::vector<rc_hit> hits(points ? n : 0);
+    std::vector<float> pts(points ? 3 * n : 0);
+    double acc[4] = {0, 0, 0, 0};
+    int32_t rc = grid_common(ctx, viewdir, grid, points ? hits.data() : nullptr, points ? pts.data() : nullptr, nullptr, 0, acc);
+    if (rc != RC_OK) return rc;
+    uint32_t cnt = (uint32_t)acc[3];
+    if (n_hits) *n_hits = cnt;
+    for (int k = 0; k < 3; k++) centroid[k] = cnt ? (float)(acc[k] / acc[3]) : NAN;  // mean of an empty collection is NaN
+    if (points) {  // [hit.point for hit in hits if hit.hit] (:108), in cell order
+        size_t w = 0;
+        for (size_t k = 0; k < n; k++)
+            if (hits[k].hit) { memcpy(points + 3 * w, &pts[3 * k], 12); w++; }
+    }
+    return RC_OK;
+}
+
+int32_t rc_view_factors(rc_context *ctx, uint32_t rays_per_triangle, uint64_t seed, uint32_t *out, uint32_t row_base, uint32_t n_rows, uint32_t flags,
+                        uint64_t *skipped) {
+    if (!ctx || !out) return RC_ERR_INVALID_ARGUMENT;
+    use_device(ctx);
+    int32_t rc = require_synced(ctx);
+    if (rc != RC_OK) return rc;
+    uint32_t n_cols = ctx->n_flat_prims;
+    if (skipped) *skipped = 0;
+    if (n_cols == 0 || n_rows == 0) return RC_OK;
+    size_t bytes = (size_t)n_rows * n_cols * sizeof(uint32_t);
+    uint32_t *d_out = out;
+    if (!(flags & RC_HITS_ON_DEVICE)) RC_CUDA(ctx, cudaMallocAsync(&d_out, bytes, ctx->stream));
+    RC_CUDA(ctx, cudaMemsetAsync(d_out, 0, bytes, ctx->stream));
+    unsigned long long *d_skipped = nullptr;
+    RC_CUDA(ctx, cudaMallocAsync(&d_skipped, 8, ctx->stream));
+    RC_CUDA(ctx, cudaMemsetAsync(d_skipped, 0, 8, ctx->stream));
+    cudaEventRecord(ctx->ev_t0, ctx->stream);
+    rc_launch_view_factors(ctx->stream, make_scene(ctx), ctx->d_flat, ctx->n_flat_blas, ctx->n_flat_prims, rays_per_triangle, seed, row_base, n_rows, n_cols, d_out,
+                           nullptr, d_skipped, ctx->d_overflow, ctx->max_blocks);
+    cudaEventRecord(ctx->ev_t1, ctx->stream);
+    ctx->last_launches = 1;
+    unsigned long long sk = 0;
+    RC_CUDA(ctx, cudaMemcpyAsync(&sk, d_skipped, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!(flags & RC_HITS_ON_DEVICE)) {
+        RC_CUDA(ctx, cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        cudaFreeAsync(d_out, ctx->stream);
+    }
+    cudaFreeAsync(d_skipped, ctx->stream);
+    if (flags & RC_NO_SYNC) return RC_OK;
+    RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->last_ms, ctx->ev_t0, ctx->ev_t1);
+    if (skipped) *skipped = sk;
+    return check_overflow(ctx);
+}
+
+int32_t rc_view_factor_rays(rc_context *ctx, uint32_t rays_per_triangle, uint64_t seed, uint32_t row_base, uint32_t n_rows, rc_ray *out) {
+    if (!ctx || !out) return RC_ERR_INVALID_ARGUMENT;
+    use_device(ctx);
+    int32_t rc = require_synced(ctx);
+    if (rc != RC_OK) return rc;
+    size_t n = (size_t)n_rows * rays_per_triangle;
+    if (n == 0) return RC_OK;
+    rc_ray *d_rays = nullptr;
+    RC_CUDA(ctx, cudaMallocAsync(&d_rays, n * sizeof(rc_ray), ctx->stream));
+    RC_CUDA(ctx, cudaMemsetAsync(d_rays, 0, n * sizeof(rc_ray), ctx->stream));
+    rc_launch_view_factors(ctx->stream, make_scene(ctx), ctx->d_flat, ctx->n_flat_blas, ctx->n_flat_prims, rays_per_triangle, seed, row_base, n_rows, ctx->n_flat_prims,
+                           nullptr, d_rays, nullptr, ctx->d_overflow, ctx->max_blocks);
+    RC_CUDA(ctx, cudaMemcpyAsync(out, d_rays, n * sizeof(rc_ray), cudaMemcpyDeviceToHost, ctx->stream));
+    cudaFreeAsync(d_rays, ctx->stream);
+    RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RC_OK;
+}
+
+int32_t rc_read_flat_metadata(rc_context *ctx, uint32_t *out, uint32_t capacity) {
+    if (!ctx || !out) return RC_ERR_INVALID_ARGUMENT;
+    use_device(ctx);
+    int32_t rc = require_synced(ctx);
+    if (rc != RC_OK) return rc;
+    if (capacity < ctx->n_flat_prims) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "capacity too small");
+    if (ctx->n_flat_prims == 0) return RC_OK;
+    uint32_t *d = nullptr;
+    RC_CUDA(ctx, cudaMallocAsync(&d, sizeof(uint32_t) * ctx->n_flat_prims, ctx->stream));
+    rc_launch_flat_metadata(ctx->stream, ctx->d_flat, ctx->n_flat_blas, ctx->n_flat_prims, d);
+    RC_CUDA(ctx, cudaMemcpyAsync(out, d, sizeof(uint32_t) * ctx->n_flat_prims, cudaMemcpyDeviceToHost, ctx->stream));
+    cudaFreeAsync(d, ctx->stream);
+    RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ memory helpers
+int32_t rc_device_alloc(rc_context *ctx, size_t bytes, void **out) {
+    if (!ctx || !out) return RC_ERR_INVALID_ARGUMENT;
+    use_device(ctx);
+    RC_CUDA(ctx, cudaMalloc(out, bytes));
+    return RC_OK;
+}
+int32_t rc_device_free(rc_context *ctx, void *ptr) {
+    if (!ctx) return RC_ERR_INVALID_ARGUMENT;
+    use_device(ctx);
+    RC_CUDA(ctx, cudaFree(ptr));
+    return RC_OK;
+}
+int32_t rc_host_alloc(rc_context *ctx, size_t bytes, void **out) {
+    if (!ctx || !out) return RC_ERR_INVALID_ARGUMENT;
+    use_device(ctx);
+    RC_CUDA(ctx, cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return RC_OK;
+}
+int32_t rc_host_free(rc_context *ctx, void *ptr) {
+    if (!ctx) return RC_ERR_INVALID_ARGUMENT;
+    RC_CUDA(ctx, cudaFreeHost(ptr));
+    return RC_OK;
+}
+int32_t rc_memcpy_h2d(rc_context *ctx, void *dst, const void *src, size_t bytes) {
+    if (!ctx) return RC_ERR_INVALID_ARGUMENT;
+    use_device(ctx);
+    RC_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RC_OK;
+}
+int32_t rc_memcpy_d2h(rc_context *ctx, void *dst, const void *src, size_t bytes) {
+    if (!ctx) return RC_ERR_INVALID_ARGUMENT;
+    use_device(ctx);
+    RC_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RC_OK;
+}
+int32_t rc_ipc_export(rc_context *ctx, void *ptr, uint8_t handle_out[64]) {
+    if (!ctx || !ptr || !handle_out) return RC_ERR_INVALID_ARGUMENT;
+    use_device(ctx);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    RC_CUDA(ctx, cudaIpcGetMemHandle(&h, ptr));
+    memcpy(handle_out, &h, 64);
+    return RC_OK;
+}
+int32_t rc_ipc_open(rc_context *ctx, const uint8_t handle[64], void **out) {
+    if (!ctx || !handle || !out) return RC_ERR_INVALID_ARGUMENT;
+    use_device(ctx);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    RC_CUDA(ctx, cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+    return RC_OK;
+}
+int32_t rc_ipc_close(rc_context *ctx, void *ptr) {
+    if (!ctx) return RC_ERR_INVALID_ARGUMENT;
+    use_device(ctx);
+    RC_CUDA(ctx, cudaIpcCloseMemHandle(ptr));
+    return RC_OK;
+}
+
+}  // extern "C"

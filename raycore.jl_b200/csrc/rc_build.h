@@ -1,0 +1,53 @@
+// rc_build.h — library-internal interface of the GPU builder (rc_build.cu)
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "rc_types.h"
+
+struct RcBox;
+struct RcTopo;
+
+struct RcDeviceBlas {
+    uint32_t n = 0;           // valid (non-degenerate) triangles
+    uint32_t n_faces_in = 0;  // faces submitted
+    RcNode2 *nodes2 = nullptr;  // 2n-1, reference layout, node k at [k-1]
+    RcNode4 *nodes4 = nullptr;  // n+1 slots, indexed by BVH2 internal node number, root = [1]
+    RcTri *tris = nullptr;      // n, Morton-sorted
+    float root_aabb[6] = {0, 0, 0, 0, 0, 0};
+};
+
+struct RcBlasPtrs {  // device-visible BLAS table entry
+    const RcNode2 *nodes2;
+    const RcNode4 *nodes4;
+    const RcTri *tris;
+    uint32_t n, pad;
+};
+
+struct RcDeviceTlas {
+    uint32_t n = 0;
+    RcNode2 *nodes2 = nullptr;
+    RcNode4 *nodes4 = nullptr;
+    RcInstanceRec *rec = nullptr;
+    RcInstanceAux *aux = nullptr;
+    rc_instance_desc *d_inst = nullptr;
+    float *d_blas_roots = nullptr;
+    RcBlasPtrs *d_blas_ptrs = nullptr;
+    RcBox *inst_boxes = nullptr;
+    uint32_t *leaf_map = nullptr;  // sorted position -> instance index
+    RcTopo *topo = nullptr;
+    uint32_t *parent = nullptr;
+    uint32_t *flags = nullptr;
+    RcBox *boxes = nullptr;
+    uint32_t *d_small = nullptr;
+    float root_aabb[6] = {0, 0, 0, 0, 0, 0};
+};
+
+bool rc_build_blas(cudaStream_t st, const float *d_verts, const uint32_t *d_face_meta, uint32_t n_faces, RcDeviceBlas *out, std::string &err);
+void rc_free_blas(RcDeviceBlas *b, cudaStream_t st);
+bool rc_build_tlas(cudaStream_t st, const rc_instance_desc *h_inst, uint32_t n, const std::vector<RcBlasPtrs> &blas, const std::vector<float> &blas_roots,
+                   RcDeviceTlas *t, std::string &err);
+bool rc_refit_tlas(cudaStream_t st, const rc_instance_desc *h_inst, uint32_t n, RcDeviceTlas *t, std::string &err);
+void rc_free_tlas(RcDeviceTlas *t, cudaStream_t st);

@@ -1,0 +1,169 @@
+// rc_build_core.cuh — per-element bodies of the LBVH builder (Karras radix tree, bottom-up fit,
+// BVH2 -> quantised BVH4 collapse).  RC_HD so tests/hostsim can run them on the CPU.
+//
+// Index conventions follow the reference (src/instanced-bvh.jl:1293-1295): nodes are numbered
+// 1..2n-1, internal 1..n-1, leaves n..2n-1 (leaf of sorted primitive p (1-based) = n-1+p), root = 1.
+// Arrays indexed by node number are stored 0-based ([node-1]) except the wide-node array, which is
+// indexed directly by the BVH2 internal-node number (slot 0 unused, root = slot 1).
+#pragma once
+#include "rc_device.cuh"
+
+struct RcBox {  // own AABB of a BVH2 node, 32 B
+    float lo[3], pad0;
+    float hi[3], pad1;
+};
+
+struct RcTopo {  // per internal node
+    uint32_t child0, child1;  // 1-based node numbers
+    uint32_t span_lo, span_hi;  // 1-based sorted primitive range covered
+};
+
+// Karras 2012 as restated by the reference: find_span_for_node :1232-1262, find_split_in_span :1265-1290,
+// build_topology_for_node (kernels.jl:119-143)
+RC_HD RcTopo rc_topology_for_node(int idx, const uint32_t *codes, int n) {
+    int d_left = rc_delta(idx, idx - 1, codes, n);
+    int d_right = rc_delta(idx, idx + 1, codes, n);
+    int d = d_right > d_left ? 1 : -1;
+    int delta_min = rc_delta(idx, idx - d, codes, n);
+    int l_max = 2;
+    while (rc_delta(idx, idx + l_max * d, codes, n) > delta_min) l_max *= 2;
+    int l = 0, t = l_max;
+    while (t > 1) {
+        t = t / 2;
+        if (rc_delta(idx, idx + (l + t) * d, codes, n) > delta_min) l = l + t;
+    }
+    int j = idx + l * d;
+    int span_left = d > 0 ? idx : j, span_right = d > 0 ? j : idx;
+    int numidentical = rc_delta(span_left, span_right, codes, n);
+    int left = span_left, right = span_right;
+    while (right > left + 1) {
+        int newsplit = (right + left) / 2;
+        if (rc_delta(left, newsplit, codes, n) > numidentical) left = newsplit;
+        else right = newsplit;
+    }
+    int split = left;
+    RcTopo r;
+    r.child0 = (uint32_t)((split == span_left) ? (n - 1 + split) : split);
+    int c1 = split + 1;
+    r.child1 = (uint32_t)((c1 == span_right) ? (n - 1 + c1) : c1);
+    r.span_lo = (uint32_t)span_left;
+    r.span_hi = (uint32_t)span_right;
+    return r;
+}
+
+RC_HD float rc_half_area(const RcBox &b) {
+    float dx = b.hi[0] - b.lo[0], dy = b.hi[1] - b.lo[1], dz = b.hi[2] - b.lo[2];
+    return dx * dy + dy * dz + dz * dx;
+}
+
+// Smallest biased exponent e with 255 * 2^(e-127) >= extent
+RC_HD uint32_t rc_quant_exponent(float extent) {
+    if (!(extent > 0.0f)) return 1u;
+    float s = extent / 255.0f;
+    uint32_t bits = f2u(s);
+    uint32_t e = (bits >> 23) & 0xFFu;
+    if (bits & 0x7FFFFFu) e += 1;
+    if (e < 1u) e = 1u;
+    if (e > 254u) e = 254u;
+    // guard the rounding of extent/255: make sure 255 * scale really covers the extent
+    while (e < 254u && u2f(e << 23) * 255.0f < extent) e += 1;
+    return e;
+}
+
+// Conservative 8-bit plane codes: decoded lo plane <= v (floor), decoded hi plane >= v (ceil)
+RC_HD uint32_t rc_quant_lo(float v, float origin, float scale) {
+    float q = floorf((v - origin) / scale);
+    q = q < 0.0f ? 0.0f : (q > 255.0f ? 255.0f : q);
+    while (q > 0.0f && fmaf(q, scale, origin) > v) q -= 1.0f;
+    return (uint32_t)q;
+}
+RC_HD uint32_t rc_quant_hi(float v, float origin, float scale) {
+    float q = ceilf((v - origin) / scale);
+    q = q < 0.0f ? 0.0f : (q > 255.0f ? 255.0f : q);
+    while (q < 255.0f && fmaf(q, scale, origin) < v) q += 1.0f;
+    return (uint32_t)q;
+}
+
+// Collapse the BVH2 subtree rooted at internal node `idx` into one wide node.
+//   boxes/topo: BVH2 arrays; n: primitive count; leaf_max: triangles per wide leaf;
+//   leaf_map (nullable): sorted position -> payload index (TLAS: instance index), only with leaf_max == 1.
+// A BVH2 node covering <= leaf_max primitives becomes a leaf reference, otherwise the child with the
+// largest surface area is opened until four slots are used (greedy; precedent: src/bvh4.jl:234-277).
+RC_HD RcNode4 rc_collapse_node(uint32_t idx, const RcBox *boxes, const RcTopo *topo, uint32_t n, uint32_t leaf_max, const uint32_t *leaf_map) {
+    uint32_t slots[4];
+    int ns = 0;
+    auto count_of = [&](uint32_t c) -> uint32_t { return c >= n ? 1u : (topo[c - 1].span_hi - topo[c - 1].span_lo + 1u); };
+    const RcBox own = boxes[idx - 1];
+    uint32_t own_count = count_of(idx);
+    if (idx >= n || own_count <= leaf_max) {
+        slots[ns++] = idx;  // degenerate root: whole BLAS is one leaf
+    } else {
+        slots[ns++] = topo[idx - 1].child0;
+        slots[ns++] = topo[idx - 1].child1;
+        while (ns < 4) {
+            int best = -1;
+            float best_area = -1.0f;
+            for (int k = 0; k < ns; k++) {
+                uint32_t c = slots[k];
+                if (c < n && count_of(c) > leaf_max) {
+                    float a = rc_half_area(boxes[c - 1]);
+                    if (a > best_area) { best_area = a; best = k; }
+                }
+            }
+            if (best < 0) break;
+            uint32_t c = slots[best];
+            slots[best] = topo[c - 1].child0;
+            slots[ns++] = topo[c - 1].child1;
+        }
+    }
+    RcNode4 nd;
+    nd.ox = own.lo[0]; nd.oy = own.lo[1]; nd.oz = own.lo[2];
+    uint32_t ex = rc_quant_exponent(own.hi[0] - own.lo[0]);
+    uint32_t ey = rc_quant_exponent(own.hi[1] - own.lo[1]);
+    uint32_t ez = rc_quant_exponent(own.hi[2] - own.lo[2]);
+    nd.exp = ex | (ey << 8) | (ez << 16);
+    float sx = u2f(ex << 23), sy = u2f(ey << 23), sz = u2f(ez << 23);
+    uint32_t qlo[3] = {0, 0, 0}, qhi[3] = {0, 0, 0}, ch[4];
+    for (int k = 0; k < 4; k++) {
+        if (k >= ns) {
+            ch[k] = RC_INVALID;
+            for (int a = 0; a < 3; a++) { qlo[a] |= 255u << (8 * k); }  // inverted box: never hit
+            continue;
+        }
+        uint32_t c = slots[k];
+        const RcBox b = boxes[c - 1];
+        qlo[0] |= rc_quant_lo(b.lo[0], nd.ox, sx) << (8 * k);
+        qlo[1] |= rc_quant_lo(b.lo[1], nd.oy, sy) << (8 * k);
+        qlo[2] |= rc_quant_lo(b.lo[2], nd.oz, sz) << (8 * k);
+        qhi[0] |= rc_quant_hi(b.hi[0], nd.ox, sx) << (8 * k);
+        qhi[1] |= rc_quant_hi(b.hi[1], nd.oy, sy) << (8 * k);
+        qhi[2] |= rc_quant_hi(b.hi[2], nd.oz, sz) << (8 * k);
+        uint32_t cnt = count_of(c);
+        if (c >= n) {
+            uint32_t pos = c - n;  // 0-based sorted position
+            ch[k] = RC_LEAF_BIT | (leaf_map ? leaf_map[pos] : pos);
+        } else if (cnt <= leaf_max) {
+            uint32_t pos = topo[c - 1].span_lo - 1u;
+            ch[k] = RC_LEAF_BIT | ((cnt - 1u) << RC_LEAF_COUNT_SHIFT) | (leaf_map ? leaf_map[pos] : pos);
+        } else {
+            ch[k] = c;
+        }
+    }
+    nd.qlox = qlo[0]; nd.qloy = qlo[1]; nd.qloz = qlo[2];
+    nd.qhix = qhi[0]; nd.qhiy = qhi[1]; nd.qhiz = qhi[2];
+    nd.child0 = ch[0]; nd.child1 = ch[1]; nd.child2 = ch[2]; nd.child3 = ch[3];
+    nd.src_node = idx;
+    nd.pad = (uint32_t)ns;
+    return nd;
+}
+
+// world AABB of an instance: bounds of the 8 transformed corners of the BLAS root box
+// (compute_instance_world_aabb, kernels.jl:38-62; corner order bounds.jl:53-59)
+RC_HD void rc_instance_world_aabb(const float *xf, const float *local, f3 &mn, f3 &mx) {
+    for (int c = 0; c < 8; c++) {
+        f3 p = mk3((c & 1) ? local[3] : local[0], (c & 2) ? local[4] : local[1], (c & 4) ? local[5] : local[2]);
+        f3 w = x_transform_point(xf, p);
+        if (c == 0) { mn = w; mx = w; }
+        else { mn = jl_min3(mn, w); mx = jl_max3(mx, w); }
+    }
+}

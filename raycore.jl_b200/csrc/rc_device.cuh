@@ -1,0 +1,232 @@
+// rc_device.cuh — per-element arithmetic shared by the builder, traversal and analysis kernels.
+//
+// "Exact" helpers (x_ prefix) evaluate the reference's expressions with IEEE round-to-nearest
+// single operations in the reference's order and are never contracted into FMAs
+// (__fmul_rn / __fadd_rn / __fsub_rn / __fdiv_rn), so ids, t and barycentrics are bit-identical
+// to the CPU evaluation of the same formulas.  Everything else is free to use FMAs.
+//
+// Functions are RC_HD (__host__ __device__) so that tests/hostsim can compile the very same
+// per-element code with g++ (-ffp-contract=off) and unit-test it on a machine without a GPU.
+// The host instantiation is test infrastructure only: libraycore_cuda never calls it.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "rc_types.h"
+
+#if defined(__CUDACC__)
+#include <cuda_runtime.h>
+#define RC_HD __host__ __device__ __forceinline__
+#else
+#define RC_HD inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define RC_ON_DEVICE 1
+#else
+#define RC_ON_DEVICE 0
+#endif
+
+struct f3 {
+    float x, y, z;
+};
+RC_HD f3 mk3(float x, float y, float z) {
+    f3 r;
+    r.x = x; r.y = y; r.z = z;
+    return r;
+}
+
+RC_HD uint32_t f2u(float f) {
+#if RC_ON_DEVICE
+    return __float_as_uint(f);
+#else
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    return u;
+#endif
+}
+RC_HD float u2f(uint32_t u) {
+#if RC_ON_DEVICE
+    return __uint_as_float(u);
+#else
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+#endif
+}
+RC_HD bool rc_isnan(float x) { return x != x; }
+RC_HD bool rc_signbit(float x) { return (f2u(x) >> 31) != 0; }
+RC_HD int rc_clz(uint32_t x) {
+#if RC_ON_DEVICE
+    return __clz((int)x);
+#else
+    return x == 0 ? 32 : __builtin_clz(x);
+#endif
+}
+
+// ---- exact scalar ops -------------------------------------------------------------------------
+#if RC_ON_DEVICE
+RC_HD float x_mul(float a, float b) { return __fmul_rn(a, b); }
+RC_HD float x_add(float a, float b) { return __fadd_rn(a, b); }
+RC_HD float x_sub(float a, float b) { return __fsub_rn(a, b); }
+RC_HD float x_div(float a, float b) { return __fdiv_rn(a, b); }
+RC_HD float x_sqrt(float a) { return __fsqrt_rn(a); }
+#else  // host TU must be compiled with -ffp-contract=off
+RC_HD float x_mul(float a, float b) { return a * b; }
+RC_HD float x_add(float a, float b) { return a + b; }
+RC_HD float x_sub(float a, float b) { return a - b; }
+RC_HD float x_div(float a, float b) { return a / b; }
+RC_HD float x_sqrt(float a) { return sqrtf(a); }
+#endif
+
+// Julia min/max on Float32 (base/math.jl): NaN-propagating, -0 < +0.
+RC_HD float jl_min(float x, float y) {
+    float diff = x_sub(x, y);
+    float arg = rc_signbit(diff) ? x : y;
+    return (rc_isnan(x) || rc_isnan(y)) ? diff : arg;
+}
+RC_HD float jl_max(float x, float y) {
+    float diff = x_sub(x, y);
+    float arg = rc_signbit(diff) ? y : x;
+    return (rc_isnan(x) || rc_isnan(y)) ? diff : arg;
+}
+
+RC_HD f3 x_sub3(f3 a, f3 b) { return mk3(x_sub(a.x, b.x), x_sub(a.y, b.y), x_sub(a.z, b.z)); }
+// StaticArrays cross / dot: component formulas, left fold, no muladd
+RC_HD f3 x_cross(f3 a, f3 b) {
+    return mk3(x_sub(x_mul(a.y, b.z), x_mul(a.z, b.y)), x_sub(x_mul(a.z, b.x), x_mul(a.x, b.z)),
+               x_sub(x_mul(a.x, b.y), x_mul(a.y, b.x)));
+}
+RC_HD float x_dot(f3 a, f3 b) { return x_add(x_add(x_mul(a.x, b.x), x_mul(a.y, b.y)), x_mul(a.z, b.z)); }
+RC_HD f3 jl_min3(f3 a, f3 b) { return mk3(jl_min(a.x, b.x), jl_min(a.y, b.y), jl_min(a.z, b.z)); }
+RC_HD f3 jl_max3(f3 a, f3 b) { return mk3(jl_max(a.x, b.x), jl_max(a.y, b.y), jl_max(a.z, b.z)); }
+// StaticArrays normalize(a) = inv(norm(a)) * a
+RC_HD f3 x_normalize(f3 a) {
+    float n = x_sqrt(x_add(x_add(x_mul(a.x, a.x), x_mul(a.y, a.y)), x_mul(a.z, a.z)));
+    float inv = x_div(1.0f, n);
+    return mk3(x_mul(inv, a.x), x_mul(inv, a.y), x_mul(inv, a.z));
+}
+
+// transform_point / transform_direction with a Mat3x4f (rows), src/instanced-bvh.jl:1692-1717
+RC_HD f3 x_transform_point(const float *m, f3 p) {
+    return mk3(x_add(x_add(x_add(x_mul(m[0], p.x), x_mul(m[1], p.y)), x_mul(m[2], p.z)), m[3]),
+               x_add(x_add(x_add(x_mul(m[4], p.x), x_mul(m[5], p.y)), x_mul(m[6], p.z)), m[7]),
+               x_add(x_add(x_add(x_mul(m[8], p.x), x_mul(m[9], p.y)), x_mul(m[10], p.z)), m[11]));
+}
+RC_HD f3 x_transform_direction(const float *m, f3 v) {
+    return mk3(x_add(x_add(x_mul(m[0], v.x), x_mul(m[1], v.y)), x_mul(m[2], v.z)),
+               x_add(x_add(x_mul(m[4], v.x), x_mul(m[5], v.y)), x_mul(m[6], v.z)),
+               x_add(x_add(x_mul(m[8], v.x), x_mul(m[9], v.y)), x_mul(m[10], v.z)));
+}
+
+// mat3x4_inverse, src/instanced-bvh.jl:1675-1687, with StaticArrays' 3x3 inv (src/inv.jl): columns
+// x0,x1,x2; y0 = x1 x x2; d = x0.y0; x0 /= d; y0 /= d; y1 = x2 x x0; y2 = x0 x x1; rows of B = y0,y1,y2.
+RC_HD void x_mat3x4_inverse(const float *m, float *out) {
+    // Mat3x4f element m[r,c] (1-based; SMatrix{4,3} column-major) = mem[(c-1)*4 + (r-1)]
+    f3 x0 = mk3(m[0], m[1], m[2]);   // R[:,1] = (m[1,1], m[2,1], m[3,1])
+    f3 x1 = mk3(m[4], m[5], m[6]);
+    f3 x2 = mk3(m[8], m[9], m[10]);
+    f3 y0 = x_cross(x1, x2);
+    float d = x_dot(x0, y0);
+    x0 = mk3(x_div(x0.x, d), x_div(x0.y, d), x_div(x0.z, d));
+    y0 = mk3(x_div(y0.x, d), x_div(y0.y, d), x_div(y0.z, d));
+    f3 y1 = x_cross(x2, x0);
+    f3 y2 = x_cross(x0, x1);
+    // B[i,j] = (row i = y_{i-1})[j]
+    float tx = m[3], ty = m[7], tz = m[11];
+    float tix = -x_add(x_add(x_mul(y0.x, tx), x_mul(y1.x, ty)), x_mul(y2.x, tz));
+    float tiy = -x_add(x_add(x_mul(y0.y, tx), x_mul(y1.y, ty)), x_mul(y2.y, tz));
+    float tiz = -x_add(x_add(x_mul(y0.z, tx), x_mul(y1.z, ty)), x_mul(y2.z, tz));
+    out[0] = y0.x; out[1] = y1.x; out[2] = y2.x; out[3] = tix;
+    out[4] = y0.y; out[5] = y1.y; out[6] = y2.y; out[7] = tiy;
+    out[8] = y0.z; out[9] = y1.z; out[10] = y2.z; out[11] = tiz;
+}
+
+// check_direction, src/ray.jl:39-49: components equal to +-0 become +0
+RC_HD float x_fix_zero(float d) { return d == 0.0f ? 0.0f : d; }
+
+// safe_invdir, src/instanced-bvh.jl:1742-1748
+RC_HD float x_safe_inv(float d) {
+    const float ooeps = 1.0e-5f;
+    return x_div(1.0f, fabsf(d) > ooeps ? d : copysignf(ooeps, d));
+}
+
+// is_degenerate, src/triangle_mesh.jl:14-17
+RC_HD bool x_is_degenerate(f3 v1, f3 v2, f3 v3) {
+    f3 c = x_cross(x_sub3(v3, v1), x_sub3(v2, v1));
+    return x_dot(c, c) == 0.0f;
+}
+
+// fast_intersect_triangle (Moeller-Trumbore), src/instanced-bvh.jl:1756-1797.
+// Returns true when the reference would accept ("not rejected": NaN passes, as it does there).
+RC_HD bool x_intersect_triangle(f3 o, f3 dir, f3 v0, f3 v1, f3 v2, float t_min, float closest_t, float &t, float &u, float &v) {
+    f3 e1 = x_sub3(v1, v0);
+    f3 e2 = x_sub3(v2, v0);
+    f3 s1 = x_cross(dir, e2);
+    float det = x_dot(s1, e1);
+    float invd = x_div(1.0f, det);
+    f3 d = x_sub3(o, v0);
+    u = x_mul(x_dot(d, s1), invd);
+    if (u < 0.0f || u > 1.0f) return false;
+    f3 s2 = x_cross(d, e1);
+    v = x_mul(x_dot(dir, s2), invd);
+    if (v < 0.0f || x_add(u, v) > 1.0f) return false;
+    t = x_mul(x_dot(e2, s2), invd);
+    if (t < t_min || t > closest_t) return false;
+    return true;
+}
+
+// fast_intersect_bbox, src/instanced-bvh.jl:1841-1859 (exact, Julia min/max)
+RC_HD void x_intersect_bbox(f3 o, f3 inv, f3 pmin, f3 pmax, float t_min, float t_max, float &out_min, float &out_max) {
+    float ox = x_mul(-o.x, inv.x), oy = x_mul(-o.y, inv.y), oz = x_mul(-o.z, inv.z);
+    float fx = x_add(x_mul(pmax.x, inv.x), ox), fy = x_add(x_mul(pmax.y, inv.y), oy), fz = x_add(x_mul(pmax.z, inv.z), oz);
+    float nx = x_add(x_mul(pmin.x, inv.x), ox), ny = x_add(x_mul(pmin.y, inv.y), oy), nz = x_add(x_mul(pmin.z, inv.z), oz);
+    float mxx = jl_max(fx, nx), mxy = jl_max(fy, ny), mxz = jl_max(fz, nz);
+    float mnx = jl_min(fx, nx), mny = jl_min(fy, ny), mnz = jl_min(fz, nz);
+    out_max = jl_min(jl_min(jl_min(mxx, mxy), mxz), t_max);
+    out_min = jl_max(jl_max(jl_max(mnx, mny), mnz), t_min);
+}
+
+// expand_bits / morton_code_30bit, src/instanced-bvh.jl:1177-1200
+RC_HD uint32_t rc_expand_bits(uint32_t x) {
+    x = (x * 0x00010001u) & 0xFF0000FFu;
+    x = (x * 0x00000101u) & 0x0F00F00Fu;
+    x = (x * 0x00000011u) & 0xC30C30C3u;
+    x = (x * 0x00000005u) & 0x49249249u;
+    return x;
+}
+RC_HD uint32_t rc_morton_axis(float p) {
+    float x = x_mul(p, 1024.0f);
+    x = x > 1023.0f ? 1023.0f : (x < 0.0f ? 0.0f : x);  // Base.clamp keeps NaN
+    return rc_isnan(x) ? 0u : (uint32_t)x;               // unsafe_trunc(UInt32, NaN) == 0 on x86-64
+}
+RC_HD uint32_t rc_morton30(f3 p) {
+    return (rc_expand_bits(rc_morton_axis(p.x)) << 2) | (rc_expand_bits(rc_morton_axis(p.y)) << 1) | rc_expand_bits(rc_morton_axis(p.z));
+}
+
+// clz32 / delta, src/instanced-bvh.jl:1203-1229 (1-based i1,i2; codes 0-based storage)
+RC_HD int rc_delta(int i1, int i2, const uint32_t *codes, int n) {
+    int left = i1 < i2 ? i1 : i2;
+    int right = i1 < i2 ? i2 : i1;
+    if (left < 1 || right > n) return -1;
+    uint32_t lc = codes[left - 1], rc = codes[right - 1];
+    if (lc != rc) return rc_clz(lc ^ rc);
+    return 32 + rc_clz((uint32_t)left ^ (uint32_t)right);
+}
+
+// Counter-based RNG (DESIGN.md "RNG"): uniform in [0,1) with 24 bits
+RC_HD float rc_rng_uniform(unsigned long long seed, unsigned long long index, uint32_t dim) {
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (index * 4ull + (unsigned long long)dim + 1ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    return (float)(z >> 40) * (1.0f / 16777216.0f);
+}
+
+// float <-> order-preserving uint (atomicMin/Max on floats; -0 orders below +0 like Julia's min)
+RC_HD uint32_t rc_float_to_ordered(float f) {
+    uint32_t u = f2u(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+RC_HD float rc_ordered_to_float(uint32_t u) { return u2f((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u); }

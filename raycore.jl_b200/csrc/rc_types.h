@@ -1,0 +1,69 @@
+// rc_types.h — device-resident data layouts of libraycore_cuda (host + device).
+//
+// Everything the traversal kernels fetch is 16-byte aligned and sized in 16-byte quanta so it
+// moves as LDG.128: wide nodes 64 B (2 sectors), triangles 48 B, instance records 64 B.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/raycore_cuda.h"
+
+#define RC_INVALID 0xFFFFFFFFu       // INVALID_NODE, src/instanced-bvh.jl:65
+#define RC_SENTINEL 0xFFFFFFFEu      // TOP_LEVEL_SENTINEL, src/instanced-bvh.jl:1733
+#define RC_LEAF_BIT 0x80000000u      // wide-node child reference: leaf flag
+#define RC_LEAF_COUNT_SHIFT 28       // bits 30..28: triangle count - 1
+#define RC_LEAF_START_MASK 0x0FFFFFFFu
+#define RC_BLAS_LEAF_MAX 4           // triangles per wide-BVH leaf (<= 8)
+
+// BVH2 node in the reference's field order (BVHNode2, src/instanced-bvh.jl:50-63) padded 60 -> 64 B.
+// Child / parent / primitive indices keep the reference's 1-based values.
+struct __attribute__((aligned(16))) RcNode2 {
+    float aabb0_min[3], aabb0_max[3], aabb1_min[3], aabb1_max[3];
+    uint32_t child0, child1, parent, pad;
+};
+
+// Wide (4-ary) node with child boxes quantised to 8 bits per plane against the node's own frame.
+//   origin o, per-axis scale 2^(e-127);  child k plane = o + q * scale,  lo rounded down, hi rounded up.
+//   qlo*/qhi*: byte k = child k.   child[k]: RC_INVALID = empty; RC_LEAF_BIT|count-1|start = leaf
+//   (BLAS: start = first Morton-sorted triangle, TLAS: start = instance index); else wide-node index.
+struct __attribute__((aligned(16))) RcNode4 {
+    float ox, oy, oz;
+    uint32_t exp;  // ex | ey << 8 | ez << 16 (biased IEEE exponents)
+    uint32_t qlox, qloy, qloz, qhix;
+    uint32_t qhiy, qhiz, child0, child1;
+    uint32_t child2, child3, src_node, pad;
+};
+
+// One triangle = 3 x float4 in Morton-sorted order:  (v0, primitive_id), (v1, metadata), (v2, face_index)
+//   primitive_id = position in the degenerate-filtered input list, face_index = position in the submitted soup
+struct __attribute__((aligned(16))) RcTri {
+    float v0[3]; uint32_t prim_id;
+    float v1[3]; uint32_t metadata;
+    float v2[3]; uint32_t face_index;
+};
+
+// Per-instance traversal record (64 B): world->local transform + the BLAS arrays it enters.
+struct __attribute__((aligned(16))) RcInstanceRec {
+    float inv[12];           // Mat3x4f rows, src/instanced-bvh.jl:94
+    const RcNode4 *nodes4;   // BLAS wide nodes (root = index 1)
+    const RcTri *tris;
+};
+
+// Cold per-instance data (hit write-back and the reference-order path)
+struct RcInstanceAux {
+    const RcNode2 *nodes2;   // BLAS BVH2 (root = index 1, stored at [0])
+    uint32_t n_prims;
+    uint32_t custom_index;   // InstanceDescriptor.instance_id
+};
+
+struct RcCounters {  // instrumented build only
+    unsigned long long rays, nodes, box_tests, tri_tests, inst_entries, max_stack;
+};
+
+// Everything a trace kernel needs (passed by value)
+struct RcScene {
+    const RcNode4 *tlas4;   // root = index 1
+    const RcNode2 *tlas2;   // root = index 1 (stored at [0])
+    const RcInstanceRec *inst;
+    const RcInstanceAux *aux;
+    uint32_t n_instances;
+};

@@ -1,0 +1,445 @@
+"""Host-side mirror of the reference's accel API for the ray-query path, over the C ABI.
+
+Names, argument meaning and error behaviour follow src/instanced-bvh.jl so the parity tests read like
+the reference's own tests (Julia `f!(x, ...)` becomes the method `x.f(...)`; Julia's 1-based instance
+index in closest_hit's tuple is kept).  Meshes are triangle soups: float32 (n_faces, 9) arrays, i.e.
+what `decompose` yields in build_and_append_blas! (:581-608) — meshing itself stays with the caller.
+
+This is what a Julia shim (`julia/RaycoreCUDA.jl`) does with ccall; the Julia toolchain
+is absent from this image, so the mirror is Python + ctypes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import namedtuple
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+from ._lib import HIT_DTYPE, INSTANCE_DTYPE, NODE2_DTYPE, RAY_DTYPE, RaycoreError
+
+TLASHandle = namedtuple("TLASHandle", ["id"])  # src/instanced-bvh.jl:180-185
+INVALID_HANDLE = TLASHandle(0)
+Triangle = namedtuple("Triangle", ["vertices", "metadata"])  # the part of Triangle{UInt32} the path touches
+Ray = namedtuple("Ray", ["o", "d", "t_min", "t_max"], defaults=(0.0, float("inf")))  # src/ray.jl:1-7
+Bounds3 = namedtuple("Bounds3", ["p_min", "p_max"])  # src/bounds.jl:6-9
+RayHit = namedtuple("RayHit", ["hit", "point", "metadata"])  # src/kernels.jl:1-5
+
+IDENTITY3x4 = np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], np.float32)
+
+
+def mat4_to_mat3x4(m) -> np.ndarray:
+    """Mat4f (indexed m[i][j], Julia's m[i,j]) -> Mat3x4f rows (src/instanced-bvh.jl:1663-1669)."""
+    m = np.asarray(m, np.float32)
+    if m.shape == (4, 4):
+        return np.ascontiguousarray(m[:3, :]).reshape(12)
+    if m.size == 12:
+        return np.ascontiguousarray(m, np.float32).reshape(12)
+    raise ValueError("transform must be a 4x4 Mat4f or a 12-float Mat3x4f")
+
+
+def empty_triangle() -> Triangle:
+    """Zero sentinel returned on a miss (src/triangle_mesh.jl:49-57)."""
+    return Triangle(np.zeros((3, 3), np.float32), np.uint32(0))
+
+
+def _as_rays(rays) -> np.ndarray:
+    if isinstance(rays, np.ndarray) and rays.dtype == RAY_DTYPE:
+        return np.ascontiguousarray(rays)
+    out = np.zeros(len(rays), RAY_DTYPE)
+    for i, r in enumerate(rays):
+        out[i] = (tuple(r.o), r.t_min, tuple(r.d), r.t_max)
+    return out
+
+
+class StaticTLAS:
+    """Adapted (immutable) form, `AbstractAdaptedAccel` (src/Raycore.jl:14-49, src/instanced-bvh.jl:155-168).
+
+    Owned by `TLAS.sync`: the same object is kept across refits and replaced on rebuilds, like
+    `tlas.static_tlas` in the reference (test/test_mesh_update.jl:184-227)."""
+
+    def __init__(self, owner: "TLAS", generation: int):
+        self._owner = owner
+        self._generation = generation
+
+    def _check(self):
+        if self._owner._static is not self:
+            raise RaycoreError(L.RC_ERR_NOT_SYNCED, "stale StaticTLAS: the TLAS was rebuilt; re-adapt per dispatch (src/instanced-bvh.jl:221-226)")
+
+    # queries ---------------------------------------------------------------------------------
+    def trace_closest(self, rays, reference_order=False, counters=False) -> np.ndarray:
+        self._check()
+        return self._owner._trace(rays, any_hit=False, reference_order=reference_order, counters=counters)
+
+    def trace_any(self, rays, reference_order=False, counters=False) -> np.ndarray:
+        self._check()
+        return self._owner._trace(rays, any_hit=True, reference_order=reference_order, counters=counters)
+
+    def closest_hit(self, ray: Ray, **kw):
+        """(hit, Triangle, t, bary(w,u,v), instance_idx 1-based) — src/instanced-bvh.jl:1902-2024."""
+        h = self.trace_closest(_as_rays([ray]), **kw)[0]
+        return self._owner._tuple_from_hit(h, any_hit=False)
+
+    def any_hit(self, ray: Ray, **kw):
+        h = self.trace_any(_as_rays([ray]), **kw)[0]
+        return self._owner._tuple_from_hit(h, any_hit=True)
+
+    # introspection ---------------------------------------------------------------------------
+    @property
+    def n_instances(self) -> int:
+        return self._owner._synced_instances
+
+    @property
+    def n_geometries(self) -> int:
+        return self._owner._synced_geometries
+
+    @property
+    def root_aabb(self) -> Bounds3:
+        return self._owner.world_bound()
+
+
+class TLAS:
+    """Mutable top-level acceleration structure, `AbstractAccel` (src/instanced-bvh.jl:261-358)."""
+
+    def __init__(self, device: Optional[int] = None):
+        self._lib = L.load()
+        ctx = C.c_void_p()
+        rc = self._lib.rc_create(-1 if device is None else int(device), C.byref(ctx))
+        if rc != L.RC_OK:
+            raise RaycoreError(rc, self._lib.rc_last_error(None).decode())
+        self._ctx = ctx
+        self._meshes = {}  # handle id -> (verts, face_meta) kept to materialise Triangle results
+        self._static: Optional[StaticTLAS] = None
+        self._generation = 0
+        self._synced_instances = 0
+        self._synced_geometries = 0
+        self._inst_handles = np.zeros(0, np.uint32)
+        self._face_cache = {}
+        self.last_sync_action = L.RC_SYNC_NONE
+
+    # -- plumbing -----------------------------------------------------------------------------
+    def _ck(self, rc):
+        if rc != L.RC_OK:
+            raise RaycoreError(rc, self._lib.rc_last_error(self._ctx).decode())
+
+    def free(self):
+        """free!(tlas) — src/instanced-bvh.jl:383-399."""
+        if getattr(self, "_ctx", None):
+            self._lib.rc_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):  # finalizer(free!, tlas), :355
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    # -- mutation -----------------------------------------------------------------------------
+    @staticmethod
+    def _verts(verts):
+        v = np.ascontiguousarray(np.asarray(verts, np.float32).reshape(-1, 9))
+        return v
+
+    def push(self, mesh, transform=None, *, instance_id: int = 0, instance_ids: Optional[Sequence[int]] = None, face_meta=None,
+             inv_transform=None) -> TLASHandle:
+        """push!(tlas, mesh, transform; instance_id) / push!(tlas, mesh, transforms; instance_ids) — :639-676.
+
+        `transform`: Mat4f (4x4), Mat3x4f (12 floats), or a list/array of them for instancing."""
+        v = self._verts(mesh)
+        if transform is None:
+            xf = IDENTITY3x4.reshape(1, 12).copy()
+            multi = False
+        else:
+            t = np.asarray(transform, np.float32)
+            multi = not (t.shape == (4, 4) or t.shape == (12,))
+            xf = np.stack([mat4_to_mat3x4(x) for x in transform]) if multi else mat4_to_mat3x4(t).reshape(1, 12)
+        m = len(xf)
+        if multi:
+            if instance_ids is not None and len(instance_ids) != m:
+                raise ValueError(f"instance_ids length {len(instance_ids)} != transforms length {m}")  # ArgumentError, :664-666
+            ids = None if instance_ids is None else np.ascontiguousarray(instance_ids, np.uint32)
+        else:
+            ids = np.array([instance_id], np.uint32)
+        fm = None if face_meta is None else np.ascontiguousarray(face_meta, np.uint32)
+        if fm is not None and len(fm) != len(v):
+            raise ValueError("face_meta length != number of faces")
+        inv = None if inv_transform is None else np.ascontiguousarray(np.asarray(inv_transform, np.float32).reshape(-1, 12))
+        xf = np.ascontiguousarray(xf, np.float32)
+        h = C.c_uint32()
+        self._ck(
+            self._lib.rc_push(
+                self._ctx, v.ctypes.data, len(v), None if fm is None else fm.ctypes.data, xf.ctypes.data, None if inv is None else inv.ctypes.data,
+                None if ids is None else ids.ctypes.data, m, 0, C.byref(h),
+            )
+        )
+        self._meshes[h.value] = (v, fm)
+        return TLASHandle(h.value)
+
+    def delete(self, handle: TLASHandle) -> bool:
+        """delete!(tlas, handle)::Bool — :690-699."""
+        d = C.c_int32()
+        self._ck(self._lib.rc_delete(self._ctx, handle.id, C.byref(d)))
+        return bool(d.value)
+
+    def update_transform(self, handle: TLASHandle, transform):
+        """update_transform! — :755-770 (single-instance handles only)."""
+        n = self._lib.rc_n_instances_of(self._ctx, handle.id)
+        if self.is_valid(handle) and n != 1:
+            raise RaycoreError(L.RC_ERR_INVALID_ARGUMENT, f"Handle has {n} instances, use update_transforms! for multiple")
+        self.update_transforms(handle, [transform])
+
+    def update_transforms(self, handle: TLASHandle, transforms):
+        """update_transforms! — :784-797."""
+        xf = np.ascontiguousarray(np.stack([mat4_to_mat3x4(x) for x in transforms]), np.float32)
+        self._ck(self._lib.rc_update_transforms(self._ctx, handle.id, xf.ctypes.data, None, len(xf)))
+
+    def update(self, handle: TLASHandle, mesh, face_meta=None):
+        """update!(tlas, handle, new_geometry) — :808-857."""
+        v = self._verts(mesh)
+        fm = None if face_meta is None else np.ascontiguousarray(face_meta, np.uint32)
+        self._ck(self._lib.rc_update_geometry(self._ctx, handle.id, v.ctypes.data, len(v), None if fm is None else fm.ctypes.data, 0))
+        self._meshes[handle.id] = (v, fm)
+
+    def sync(self) -> "TLAS":
+        """sync!(tlas) — :894-921."""
+        a = C.c_int32()
+        self._ck(self._lib.rc_sync(self._ctx, C.byref(a)))
+        self.last_sync_action = a.value
+        if a.value == L.RC_SYNC_REBUILD or self._static is None:
+            self._generation += 1
+            self._static = StaticTLAS(self, self._generation)  # rebuild_static_tlas!, :930-959
+            self._face_cache.clear()
+            n = self._lib.rc_n_total_instances(self._ctx)
+            self._inst_handles = np.zeros(n, np.uint32)
+            if n:
+                self._ck(self._lib.rc_get_instance_handles(self._ctx, self._inst_handles.ctypes.data, n))
+            for hid in [k for k in self._meshes if not self._lib.rc_is_valid(self._ctx, k)]:
+                del self._meshes[hid]
+        if a.value != L.RC_SYNC_NONE:
+            self._synced_instances = self._lib.rc_n_total_instances(self._ctx)
+            self._synced_geometries = self._lib.rc_n_geometries(self._ctx)
+        return self
+
+    @property
+    def static_tlas(self) -> Optional[StaticTLAS]:
+        return self._static
+
+    def adapt(self) -> StaticTLAS:
+        """Adapt.adapt(backend, tlas): sync! then return tlas.static_tlas — :1085-1102."""
+        self.sync()
+        return self._static
+
+    # -- introspection ------------------------------------------------------------------------
+    def is_valid(self, handle: TLASHandle) -> bool:
+        return bool(self._lib.rc_is_valid(self._ctx, handle.id))
+
+    def n_instances(self, handle: Optional[TLASHandle] = None) -> int:
+        if handle is None:
+            return self._lib.rc_n_instances(self._ctx)
+        return self._lib.rc_n_instances_of(self._ctx, handle.id)
+
+    def n_total_instances(self) -> int:
+        return self._lib.rc_n_total_instances(self._ctx)
+
+    def n_geometries(self) -> int:
+        return self._lib.rc_n_geometries(self._ctx)
+
+    @property
+    def dirty(self) -> bool:
+        d, t = C.c_int32(), C.c_int32()
+        self._lib.rc_is_dirty(self._ctx, C.byref(d), C.byref(t))
+        return bool(d.value)
+
+    @property
+    def transforms_dirty(self) -> bool:
+        d, t = C.c_int32(), C.c_int32()
+        self._lib.rc_is_dirty(self._ctx, C.byref(d), C.byref(t))
+        return bool(t.value)
+
+    def get_instances(self, handle: TLASHandle) -> np.ndarray:
+        """get_instances — :732-738 (raises for invalid / deleted handles)."""
+        n = max(1, self._lib.rc_n_instances_of(self._ctx, handle.id))
+        out = np.zeros(n, INSTANCE_DTYPE)
+        self._ck(self._lib.rc_get_instances(self._ctx, handle.id, out.ctypes.data))
+        return out
+
+    def get_instance(self, handle: TLASHandle, instance_idx: int = 1):
+        """get_instance — :714-723 (1-based instance_idx)."""
+        inst = self.get_instances(handle)
+        if not (1 <= instance_idx <= len(inst)):
+            raise RaycoreError(L.RC_ERR_INVALID_ARGUMENT, f"Instance index {instance_idx} out of range 1:{len(inst)}")
+        return inst[instance_idx - 1]
+
+    def world_bound(self) -> Bounds3:
+        b = np.zeros(6, np.float32)
+        self._ck(self._lib.rc_world_bound(self._ctx, b.ctypes.data))
+        return Bounds3(b[:3].copy(), b[3:].copy())
+
+    def wait_for_gpu(self) -> "TLAS":
+        """wait_for_gpu!(accel) === accel — :2418-2421."""
+        self._ck(self._lib.rc_wait(self._ctx))
+        return self
+
+    def sizes(self):
+        a, b, c, d = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+        self._ck(self._lib.rc_sizes(self._ctx, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return {"tlas_nodes": a.value, "blas_nodes": b.value, "blas_prims": c.value, "pending_deletes": d.value}
+
+    def read_tlas_nodes(self) -> np.ndarray:
+        n = self.sizes()["tlas_nodes"]
+        out = np.zeros(n, NODE2_DTYPE)
+        if n:
+            self._ck(self._lib.rc_read_tlas_nodes(self._ctx, out.ctypes.data, n))
+        return out
+
+    def read_blas_nodes(self, blas_index: int) -> np.ndarray:
+        n = self._lib.rc_blas_n_prims(self._ctx, blas_index)
+        out = np.zeros(max(0, 2 * n - 1), NODE2_DTYPE)
+        self._ck(self._lib.rc_read_blas_nodes(self._ctx, blas_index, out.ctypes.data, len(out)))
+        return out
+
+    def read_blas_order(self, blas_index: int) -> np.ndarray:
+        n = self._lib.rc_blas_n_prims(self._ctx, blas_index)
+        out = np.zeros(n, np.uint32)
+        self._ck(self._lib.rc_read_blas_order(self._ctx, blas_index, out.ctypes.data, n))
+        return out
+
+    def read_blas_faces(self, blas_index: int) -> np.ndarray:
+        n = self._lib.rc_blas_n_prims(self._ctx, blas_index)
+        out = np.zeros(n, np.uint32)
+        self._ck(self._lib.rc_read_blas_faces(self._ctx, blas_index, out.ctypes.data, n))
+        return out
+
+    def flat_metadata(self) -> np.ndarray:
+        n = self.sizes()["blas_prims"]
+        out = np.zeros(n, np.uint32)
+        if n:
+            self._ck(self._lib.rc_read_flat_metadata(self._ctx, out.ctypes.data, n))
+        return out
+
+    # -- queries --------------------------------------------------------------------------------
+    def _trace(self, rays, any_hit, reference_order=False, counters=False) -> np.ndarray:
+        rays = _as_rays(rays)
+        hits = np.zeros(len(rays), HIT_DTYPE)
+        flags = (L.RC_MODE_REFERENCE_ORDER if reference_order else 0) | (L.RC_COUNTERS if counters else 0)
+        fn = self._lib.rc_trace_any if any_hit else self._lib.rc_trace_closest
+        if len(rays):
+            self._ck(fn(self._ctx, rays.ctypes.data, hits.ctypes.data, len(rays), flags))
+        return hits
+
+    def trace_closest(self, rays, **kw) -> np.ndarray:
+        return self.adapt().trace_closest(rays, **kw)
+
+    def trace_any(self, rays, **kw) -> np.ndarray:
+        return self.adapt().trace_any(rays, **kw)
+
+    def closest_hit(self, ray: Ray, **kw):
+        return self.adapt().closest_hit(ray, **kw)
+
+    def any_hit(self, ray: Ray, **kw):
+        return self.adapt().any_hit(ray, **kw)
+
+    def counters(self, reset=True) -> dict:
+        out = (C.c_uint64 * 6)()
+        self._ck(self._lib.rc_get_counters(self._ctx, out, 1 if reset else 0))
+        keys = ["rays", "nodes", "box_tests", "tri_tests", "inst_entries", "max_stack"]
+        return dict(zip(keys, [int(x) for x in out]))
+
+    def last_kernel_ms(self) -> float:
+        return float(self._lib.rc_last_kernel_ms(self._ctx))
+
+    def triangle_of(self, hit) -> Triangle:
+        """Materialise the reference's `Triangle` for a hit from the caller-side copy of the mesh."""
+        inst_pos = int(hit["instance_id"])
+        hid = int(self._inst_handles[inst_pos])
+        verts, _ = self._meshes[hid]
+        blas_index = int(self.get_instances(TLASHandle(hid))[0]["blas_index"])
+        faces = self._face_cache.get(blas_index)
+        if faces is None:
+            faces = self._face_cache[blas_index] = self.read_blas_faces(blas_index)
+        face = int(faces[int(hit["primitive_id"])])
+        return Triangle(verts[face].reshape(3, 3).copy(), np.uint32(hit["meta"]))
+
+    def _tuple_from_hit(self, h, any_hit: bool):
+        if h["hit"]:
+            u, v = np.float32(h["bary_u"]), np.float32(h["bary_v"])
+            w = np.float32(1.0) - u - v  # :2015
+            return True, self.triangle_of(h), np.float32(h["t"]), np.array([w, u, v], np.float32), np.uint32(h["instance_id"] + 1)
+        return False, empty_triangle(), np.float32(0), np.zeros(3, np.float32), np.uint32(0)
+
+    # -- analysis (src/kernels.jl) --------------------------------------------------------------
+    def hits_from_grid(self, viewdir, grid_size: int = 32):
+        """hits_from_grid — :58-72: (hits[grid*grid], points[grid*grid,3]) in Julia column-major cell order."""
+        self.sync()
+        d = np.ascontiguousarray(viewdir, np.float32)
+        n = grid_size * grid_size
+        hits = np.zeros(n, HIT_DTYPE)
+        pts = np.zeros((n, 3), np.float32)
+        self._ck(self._lib.rc_hits_from_grid(self._ctx, d.ctypes.data, grid_size, hits.ctypes.data, pts.ctypes.data))
+        return hits, pts
+
+    def get_centroid(self, viewdir, grid_size: int = 32):
+        """get_centroid — :106-110: (surface_points, mean)."""
+        self.sync()
+        d = np.ascontiguousarray(viewdir, np.float32)
+        c = np.zeros(3, np.float32)
+        n = C.c_uint32()
+        pts = np.zeros((grid_size * grid_size, 3), np.float32)
+        self._ck(self._lib.rc_get_centroid(self._ctx, d.ctypes.data, grid_size, c.ctypes.data, C.byref(n), pts.ctypes.data))
+        return pts[: n.value].copy(), c
+
+    def get_illumination(self, viewdir, grid_size: int = 1000) -> np.ndarray:
+        """get_illumination — :112-124: Float32 hit count per metadata 1..n_prims."""
+        self.sync()
+        d = np.ascontiguousarray(viewdir, np.float32)
+        n = self.sizes()["blas_prims"]
+        out = np.zeros(n, np.float32)
+        if n:
+            self._ck(self._lib.rc_get_illumination(self._ctx, d.ctypes.data, grid_size, out.ctypes.data, n))
+        return out
+
+    def view_factors(self, rays_per_triangle: int = 10000, seed: int = 0, row_base: int = 0, n_rows: Optional[int] = None) -> np.ndarray:
+        """view_factors — :74-104.  Returns result[src, hit] (UInt32, indexable like Julia's result[src_meta, hit_meta]
+        with 0-based numpy indices = metadata - 1); `row_base`/`n_rows` select a block of source rows."""
+        self.sync()
+        n = self.sizes()["blas_prims"]
+        n_rows = n - row_base if n_rows is None else n_rows
+        out = np.zeros((n_rows, n), np.uint32)
+        sk = C.c_uint64()
+        if n and n_rows:
+            self._ck(self._lib.rc_view_factors(self._ctx, rays_per_triangle, seed, out.ctypes.data, row_base, n_rows, 0, C.byref(sk)))
+        self.last_vf_skipped = sk.value
+        return out
+
+    def view_factor_rays(self, rays_per_triangle: int, seed: int = 0, row_base: int = 0, n_rows: Optional[int] = None) -> np.ndarray:
+        self.sync()
+        n = self.sizes()["blas_prims"]
+        n_rows = n - row_base if n_rows is None else n_rows
+        out = np.zeros(n_rows * rays_per_triangle, RAY_DTYPE)
+        if len(out):
+            self._ck(self._lib.rc_view_factor_rays(self._ctx, rays_per_triangle, seed, row_base, n_rows, out.ctypes.data))
+        return out
+
+
+def build_static_tlas(meshes, metadata_fn=None, device: Optional[int] = None) -> StaticTLAS:
+    """TLAS(meshes, metadata_fn) — src/instanced-bvh.jl:2276-2324: one BLAS + identity instance per mesh,
+    instance_id = mesh index (1-based), metadata = metadata_fn(mesh_idx, face_idx) (both 1-based)."""
+    tlas = TLAS(device)
+    for mi, mesh in enumerate(meshes, start=1):
+        v = TLAS._verts(mesh)
+        fm = None
+        if metadata_fn is not None:
+            fm = np.array([metadata_fn(mi, fi) for fi in range(1, len(v) + 1)], np.uint32)
+        tlas.push(v, None, instance_id=mi, face_meta=fm)
+    return tlas.adapt()
+
+
+def tlas_from_meshes(meshes, device: Optional[int] = None):
+    """TLAS(meshes) -> (tlas, handles) — src/instanced-bvh.jl:2361-2378."""
+    if len(meshes) == 0:
+        raise RaycoreError(L.RC_ERR_INVALID_ARGUMENT, "Cannot create TLAS from empty mesh list")
+    tlas = TLAS(device)
+    handles = [tlas.push(m) for m in meshes]
+    tlas.sync()
+    return tlas, handles

@@ -1,0 +1,106 @@
+"""ctypes wrapper of tests/hostsim (CPU instantiation of the library's RC_HD device code).  Test infrastructure only."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from raycore_b200._lib import HIT_DTYPE, INSTANCE_DTYPE, NODE2_DTYPE, RAY_DTYPE
+
+_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        subprocess.check_call(["make", "-C", _DIR, "libhostsim.so"], stdout=subprocess.DEVNULL)
+        L = C.CDLL(os.path.join(_DIR, "libhostsim.so"))
+        vp = C.c_void_p
+        L.hs_blas_build.restype = vp
+        L.hs_blas_build.argtypes = [vp, C.c_uint32, vp]
+        L.hs_blas_n.restype = C.c_uint32
+        L.hs_blas_n.argtypes = [vp]
+        for f in ("hs_blas_nodes2", "hs_blas_root", "hs_blas_order"):
+            getattr(L, f).restype = None
+            getattr(L, f).argtypes = [vp, vp]
+        L.hs_blas_free.argtypes = [vp]
+        L.hs_mat3x4_inverse.argtypes = [vp, vp]
+        L.hs_scene_build.restype = vp
+        L.hs_scene_build.argtypes = [vp, C.c_uint32, vp, C.c_uint32]
+        L.hs_scene_tlas_nodes2.restype = C.c_uint32
+        L.hs_scene_tlas_nodes2.argtypes = [vp, vp]
+        L.hs_scene_root.argtypes = [vp, vp]
+        L.hs_scene_free.argtypes = [vp]
+        L.hs_trace.restype = C.c_uint32
+        L.hs_trace.argtypes = [vp, vp, vp, C.c_uint64, C.c_int, C.c_int, vp]
+        L.hs_check_wide.restype = C.c_uint32
+        L.hs_check_wide.argtypes = [vp]
+        _lib = L
+    return _lib
+
+
+class HsBlas:
+    def __init__(self, verts, face_meta=None):
+        v = np.ascontiguousarray(np.asarray(verts, np.float32).reshape(-1, 9))
+        fm = None if face_meta is None else np.ascontiguousarray(face_meta, np.uint32)
+        self.p = lib().hs_blas_build(v.ctypes.data, len(v), None if fm is None else fm.ctypes.data)
+        if not self.p:
+            raise ValueError("Geometry has no valid triangles")
+        self.n = lib().hs_blas_n(self.p)
+
+    def nodes2(self):
+        out = np.zeros(2 * self.n - 1, NODE2_DTYPE)
+        lib().hs_blas_nodes2(self.p, out.ctypes.data)
+        return out
+
+    def root(self):
+        out = np.zeros(6, np.float32)
+        lib().hs_blas_root(self.p, out.ctypes.data)
+        return out
+
+    def order(self):
+        out = np.zeros(self.n, np.uint32)
+        lib().hs_blas_order(self.p, out.ctypes.data)
+        return out
+
+    def check_wide(self):
+        return lib().hs_check_wide(self.p)
+
+
+def mat3x4_inverse(m):
+    a = np.ascontiguousarray(m, np.float32)
+    out = np.zeros(12, np.float32)
+    lib().hs_mat3x4_inverse(a.ctypes.data, out.ctypes.data)
+    return out
+
+
+class HsScene:
+    def __init__(self, blas_list, instances):
+        self.blas_list = list(blas_list)
+        inst = np.ascontiguousarray(instances, INSTANCE_DTYPE)
+        arr = (C.c_void_p * max(1, len(self.blas_list)))(*[b.p for b in self.blas_list])
+        self.p = lib().hs_scene_build(arr, len(self.blas_list), inst.ctypes.data, len(inst))
+        self.n = len(inst)
+
+    def tlas_nodes2(self):
+        n = lib().hs_scene_tlas_nodes2(self.p, None)
+        out = np.zeros(n, NODE2_DTYPE)
+        if n:
+            lib().hs_scene_tlas_nodes2(self.p, out.ctypes.data)
+        return out
+
+    def root(self):
+        out = np.zeros(6, np.float32)
+        lib().hs_scene_root(self.p, out.ctypes.data)
+        return out
+
+    def trace(self, rays, any_hit=False, wide=True, counters=False):
+        rays = np.ascontiguousarray(rays, RAY_DTYPE)
+        hits = np.zeros(len(rays), HIT_DTYPE)
+        cnt = (C.c_uint64 * 5)()
+        ov = lib().hs_trace(self.p, rays.ctypes.data, hits.ctypes.data, len(rays), int(any_hit), int(wide), cnt)
+        assert ov == 0, f"{ov} traversal stack overflows"
+        if counters:
+            return hits, dict(zip(["nodes", "box_tests", "tri_tests", "inst_entries", "max_stack"], [int(x) for x in cnt]))
+        return hits
