@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py — closest_hit Mrays/s (incoherent) on the 1M-triangle config of BASELINE.json (configs[1]).
+
+    python bench.py --gpus 1 --steps K --warmup W              our arm (CUDA library through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...     the reference's CPU algorithm (oracle port, OpenMP)
+
+A step = one pass of batched closest_hit over this rank's ray batch (2^24 rays: 2^23 diffuse-bounce rays leaving
+the surface + 2^23 rays from interior points, uniform directions — both incoherent).  `value` is timed with rays
+and hit buffers resident in HBM; `e2e` is the same call with pinned HOST ray/hit buffers (H2D + D2H inside the
+timed region).  One process per GPU; the BVH is replicated, rays are sharded (weak scaling: every rank traces its own
+batch); each step ends with the NCCL gather of the hit records to rank 0 when N > 1.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+TESS = 709            # bumpy_sphere(709): 1,002,528 faces
+RAYS_PER_RANK = 1 << 24
+PRIMARY_RES = 3072    # primary rays used to seed the bounce rays
+CPU_SAMPLE = 1 << 21  # rays per CPU-baseline step (bounded sample of the same ray set)
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), float(p.get("sm_max_mhz", 1965.0)), "measured"
+    except Exception:
+        return 6650.0, 1965.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_rays(tlas_trace, verts, faces_of_prim, n, seed):
+    """2^23 diffuse-bounce rays from primary hits + 2^23 interior rays, interleaved in blocks so both kinds are in every chunk."""
+    from raycore_b200 import workloads as W
+
+    half = n // 2
+    prim = W.pinhole_rays(PRIMARY_RES, PRIMARY_RES, camera_pos=(0.0, 0.0, -3.0))
+    ph = tlas_trace(prim)
+    normals = W.geometric_normals(verts)
+    nrm = normals[faces_of_prim[ph["primitive_id"]]]
+    b = W.bounce_rays(half, prim, ph, nrm, seed=0x5EED + seed)
+    c = W.interior_rays(n - half, seed=77 + seed, radius=0.8)
+    rays = np.empty(n, W.RAY_DTYPE)
+    rays[0::2] = b
+    rays[1::2] = c
+    return rays, float(ph["hit"].mean())
+
+
+def run_reference(args):
+    """The reference's CPU algorithm (C restatement, OpenMP over rays as Threads.@threads does) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    from raycore_b200 import workloads as W
+
+    verts = W.bumpy_sphere(TESS)
+    t0 = time.time()
+    blas = orc.OracleBLAS.from_verts(verts)
+    inst = orc.make_instances(1, [orc.identity3x4()], [1])
+    tlas = orc.OracleTLAS([blas], inst)
+    build_s = time.time() - t0
+    cores = orc.max_threads()
+    n = CPU_SAMPLE
+    # the sample = the first CPU_SAMPLE rays of the benchmark's own ray set; the oracle traces the primaries itself
+    prim = W.pinhole_rays(1024, 1024, camera_pos=(0.0, 0.0, -3.0))
+    ph = tlas.closest_hit(prim)
+    normals = W.geometric_normals(verts)
+    order = blas.prims["input_index"]
+    tris_in = orc.filter_triangles(verts)
+    face_of_prim = (tris_in["metadata"] - 1).astype(np.int64)  # metadata = 1-based face index
+    nrm = normals[face_of_prim[ph["primitive_id"]]]
+    rays = np.empty(n, W.RAY_DTYPE)
+    rays[0::2] = W.bounce_rays(n // 2, prim, ph, nrm, seed=0x5EED)
+    rays[1::2] = W.interior_rays(n - n // 2, seed=77, radius=0.8)
+    for _ in range(args.warmup):
+        tlas.closest_hit(rays)
+    t0 = time.time()
+    for _ in range(args.steps):
+        tlas.closest_hit(rays)
+    dt = time.time() - t0
+    v = n * args.steps / dt / 1e6
+    line = {
+        "impl": "reference", "metric": "closest_hit Mrays/s (incoherent)", "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": f"C2 bumpy_sphere({TESS}) 1,002,528 faces, 1 instance; bounded sample of {n} rays/step (bounce+interior interleaved)"},
+        "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": f"{n} rays/step x {args.steps} steps; oracle/oracle.c (C restatement of the reference BVH2 path; Julia absent)", "build_s": build_s},
+        "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--rays", type=int, default=RAYS_PER_RANK)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--counters", action="store_true", help="extra instrumented pass (per-ray node/triangle counts) after the timed region")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import raycore_b200 as rc
+    from raycore_b200 import workloads as W
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.rays
+    L = rc._lib
+
+    # ---- scene: every rank builds the same BVH (replicated, deterministic builder) --------------------------
+    verts = W.bumpy_sphere(TESS)
+    tlas = rc.TLAS(local)
+    lib, ctx = tlas._lib, tlas._ctx
+    t0 = time.time()
+    h = tlas.push(verts, None, instance_id=1)
+    tlas.sync()
+    build_wall_ms = 1e3 * (time.time() - t0)
+    # device-side build time with the vertices already resident (what the reference's published build numbers measure)
+    d_verts = torch.from_numpy(verts).to(dev)
+    xf = W.identity3x4()
+    hh = C.c_uint32()
+    torch.cuda.synchronize()
+    build_ms = []
+    for _ in range(3):
+        t0 = time.time()
+        assert lib.rc_push(ctx, d_verts.data_ptr(), len(verts), None, xf.ctypes.data, None, None, 1, L.RC_VERTS_ON_DEVICE, C.byref(hh)) == 0
+        build_ms.append(1e3 * (time.time() - t0))
+        dd = C.c_int32()
+        lib.rc_delete(ctx, hh.value, C.byref(dd))
+    tlas.sync()
+    n_tris = tlas.sizes()["blas_prims"]
+    faces = tlas.read_blas_faces(1).astype(np.int64)
+
+    rays, primary_hit_rate = build_rays(lambda r: tlas.trace_closest(r), verts, faces, n, seed=rank)
+    d_rays = torch.from_numpy(rays.view(np.uint8).reshape(-1)).to(dev)
+    d_hits = torch.empty(n * 32, dtype=torch.uint8, device=dev)
+    gather_buf = [torch.empty_like(d_hits) for _ in range(world)] if (world > 1 and rank == 0) else None
+    # all library work on torch's current stream so torch.cuda.Event brackets it
+    stream = torch.cuda.current_stream(dev)
+    assert lib.rc_set_stream(ctx, C.c_void_p(stream.cuda_stream)) == 0
+    flags = L.RC_RAYS_ON_DEVICE | L.RC_HITS_ON_DEVICE | L.RC_NO_SYNC
+
+    def step():
+        rc_ = lib.rc_trace_closest(ctx, d_rays.data_ptr(), d_hits.data_ptr(), n, flags)
+        assert rc_ == 0, lib.rc_last_error(ctx)
+        if world > 1:
+            dist.gather(d_hits, gather_buf, dst=0)  # results gathered by NCCL over NVLink
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kern_ms = []
+    with ClockSampler(local) as clk:
+        barrier()
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step()
+        ev1.record(stream)
+        barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    assert lib.rc_wait(ctx) == 0
+    ms_step = ms_total / args.steps
+    value = world * n * args.steps / (ms_total * 1e-3) / 1e6
+
+    # per-launch kernel time (CUDA events inside the library, on the launching stream), for the roofline
+    for _ in range(3):
+        assert lib.rc_trace_closest(ctx, d_rays.data_ptr(), d_hits.data_ptr(), n, L.RC_RAYS_ON_DEVICE | L.RC_HITS_ON_DEVICE) == 0
+        kern_ms.append(lib.rc_last_kernel_ms(ctx))
+    k_ms = float(np.mean(kern_ms))
+    hits_np = d_hits.cpu().numpy().view(L.HIT_DTYPE)
+    hit_rate = float(hits_np["hit"].mean())
+
+    # ---- e2e: same call, pinned host buffers, H2D + D2H inside the timed region ------------------------------
+    e2e = None
+    if not args.no_e2e:
+        assert lib.rc_set_stream(ctx, None) == 0
+        h_rays = torch.from_numpy(rays.view(np.uint8).reshape(-1)).pin_memory()
+        h_hits = torch.empty(n * 32, dtype=torch.uint8).pin_memory()
+        for _ in range(2):
+            assert lib.rc_trace_closest(ctx, h_rays.data_ptr(), h_hits.data_ptr(), n, 0) == 0
+        barrier()
+        t0 = time.perf_counter()
+        e_steps = max(3, min(args.steps, 10))
+        for _ in range(e_steps):
+            assert lib.rc_trace_closest(ctx, h_rays.data_ptr(), h_hits.data_ptr(), n, 0) == 0
+        barrier()
+        e_s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([e_s], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e_s = float(t.item())
+        assert h_hits.numpy().view(L.HIT_DTYPE)["hit"].mean() == hits_np["hit"].mean()
+        e2e = {"value": world * n * e_steps / e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": n * 32, "steps": e_steps}
+
+    # ---- instrumented pass: per-ray work of the shipped kernel ---------------------------------
+    counters = None
+    if rank == 0:
+        m = min(n, 1 << 20)
+        lib.rc_get_counters(ctx, (C.c_uint64 * 6)(), 1)
+        assert lib.rc_trace_closest(ctx, d_rays.data_ptr(), d_hits.data_ptr(), m, L.RC_RAYS_ON_DEVICE | L.RC_HITS_ON_DEVICE | L.RC_COUNTERS) == 0
+        c = tlas.counters()
+        counters = {k: c[k] / m for k in ("nodes", "box_tests", "tri_tests", "inst_entries")} | {"max_stack": c["max_stack"]}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm_peak, sm_max, which = peaks()
+    rays_per_s = n / (k_ms * 1e-3)
+    alg_hbm_bytes = 64.0  # 32 B RTRay in + 32 B RTHitResult out per ray
+    roofline = {
+        "bound": "hbm", "achieved": rays_per_s * alg_hbm_bytes / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": rays_per_s * alg_hbm_bytes / 1e9 / hbm_peak,
+        "traffic": None, "peak_source": which, "kernel": "k_trace<wide,closest>", "kernel_ms": k_ms, "rays_per_launch": n,
+        "note": "HBM carries only the ray/hit streams (64 B/ray); the BVH working set is L2-resident, so the binding limits are L2->SM traffic and FP32/ALU issue (see l2/fp32 below)",
+    }
+    if counters:
+        node_b, tri_b = 64.0, 48.0
+        l2_bytes = counters["nodes"] * node_b + counters["tri_tests"] * tri_b + counters["inst_entries"] * 64.0
+        flops = counters["box_tests"] * 25 + counters["tri_tests"] * 58 + counters["inst_entries"] * 42
+        fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+        roofline["l2"] = {"bytes_per_ray": l2_bytes, "achieved_gbs": rays_per_s * l2_bytes / 1e9, "peak_gbs": 6300 * sm_max * 1e6 / 1e9, "peak_source": "6300 B/clk x sm_max_mhz (B300_MICROARCH LTS cap)"}
+        roofline["fp32"] = {"flop_per_ray": flops, "achieved_tflops": rays_per_s * flops / 1e12, "peak_tflops": fp32_peak}
+        roofline["per_ray"] = counters
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import oracle as orc
+
+        t0 = time.time()
+        ob = orc.OracleBLAS.from_verts(verts)
+        ot = orc.OracleTLAS([ob], orc.make_instances(1, [orc.identity3x4()], [1]))
+        cpu_build = time.time() - t0
+        sample = rays[:CPU_SAMPLE]
+        ot.closest_hit(sample[: 1 << 16])
+        t0 = time.time()
+        oh, oc = ot.closest_hit(sample, counters=True)
+        dt = time.time() - t0
+        # parity on the sample while we are here (ids bit-exact outside the documented classes)
+        import parity
+
+        cls = parity.classify(hits_np[: len(sample)], oh, None)
+        cpu = {"value": len(sample) / dt / 1e6, "unit": "Mrays/s", "cores": orc.max_threads(), "kind": "port",
+               "sample": f"first {len(sample)} rays of the benchmark ray set, 1 pass; oracle/oracle.c (C restatement of the reference BVH2 path, OpenMP over rays; Julia absent)",
+               "build_s": cpu_build, "bvh2_per_ray": {k: oc[k] / len(sample) for k in ("nodes", "box_tests", "tri_tests")},
+               "parity_on_sample": {k: int(len(v)) for k, v in cls.items()}}
+
+    line = {
+        "metric": "closest_hit Mrays/s (incoherent)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": f"C2: bumpy_sphere({TESS}) {len(verts)} faces -> {n_tris} triangles, 1 instance TLAS; per rank 2^{int(np.log2(n))} rays = diffuse-bounce (hemisphere about the geometric normal, from {PRIMARY_RES}^2 primary hits) interleaved with interior-origin uniform-direction rays",
+            "rays_per_rank": n, "hit_rate": hit_rate, "primary_hit_rate": primary_hit_rate, "l2_policy": "inputs larger than L2 (512 MiB rays + 512 MiB hits per step)",
+            "gather": "dist.gather of hit records to rank 0 (NCCL) inside every step" if world > 1 else "none (1 GPU)", "parallelism": f"bvh replicated, rays sharded x{world}",
+        },
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps * 1, "clocks": clk.summary(),
+        "build": {"blas_build_ms_device_input": min(build_ms), "push_sync_ms_host_input": build_wall_ms, "triangles": n_tris},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

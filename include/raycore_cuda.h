@@ -103,6 +103,9 @@ const char *rc_last_error(const rc_context *ctx); /* ctx may be NULL: last creat
 int32_t rc_abi_version(void);
 /* the context's CUDA stream (cudaStream_t) — all work of this context is ordered on it */
 void *rc_stream(rc_context *ctx);
+/* adopt a caller-owned cudaStream_t (e.g. the host framework's current stream) for all subsequent work of this
+ * context; NULL restores a private stream.  Lets callers bracket calls with their own CUDA events. */
+int32_t rc_set_stream(rc_context *ctx, void *stream);
 
 /* ---- mutation (handle API) ----------------------------------------------------------- */
 /* push!(tlas, mesh, transform; instance_id) / push!(tlas, mesh, transforms; instance_ids)

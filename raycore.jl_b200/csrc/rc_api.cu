@@ -27,6 +27,7 @@ std::string g_create_error;
 struct rc_context {
     int device = 0;
     cudaStream_t stream = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    bool owns_stream = true;
     std::string last_error;
     std::vector<RcDeviceBlas> blas;           // blas_index b+1 <-> blas[b]
     std::vector<rc_instance_desc> instances;  // host mirror of tlas.instances
@@ -151,12 +152,26 @@ int32_t rc_destroy(rc_context *ctx) {
     if (ctx->d_hits) cudaFree(ctx->d_hits);
     for (int i = 0; i < rc_context::NEV; i++) { cudaEventDestroy(ctx->ev_h2d[i]); cudaEventDestroy(ctx->ev_k[i]); }
     cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1);
-    cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->s_h2d); cudaStreamDestroy(ctx->s_d2h);
+    if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->s_h2d); cudaStreamDestroy(ctx->s_d2h);
     delete ctx;
     return RC_OK;
 }
 
 void *rc_stream(rc_context *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int32_t rc_set_stream(rc_context *ctx, void *stream) {
+    if (!ctx) return RC_ERR_INVALID_ARGUMENT;
+    use_device(ctx);
+    RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->owns_stream) { cudaStreamDestroy(ctx->stream); ctx->owns_stream = false; }
+    if (stream) ctx->stream = (cudaStream_t)stream;
+    else {
+        RC_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->owns_stream = true;
+    }
+    return RC_OK;
+}
 
 // ------------------------------------------------------------------------------------------------ mutation
 static int32_t build_blas_from(rc_context *ctx, const float *verts, uint32_t n_faces, const uint32_t *face_meta, uint32_t flags, RcDeviceBlas *out) {

@@ -1,0 +1,135 @@
+"""Parity tests proper: the CUDA library through the C ABI against the CPU oracle (bit-exact ids; DESIGN.md classes)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from raycore_b200 import workloads as W
+import raycore_b200 as rc
+import engines
+import kat
+import parity
+
+pytestmark = pytest.mark.gpu
+
+
+def _scene_instanced(n_inst=300, tess=16, seed=11):
+    xf = W.random_trs(n_inst, seed, extent=10.0)
+    return [(W.bumpy_sphere(tess), None, xf, np.arange(1, n_inst + 1, dtype=np.uint32)), (W.box_mesh(), None, W.random_trs(17, seed + 1, extent=10.0), None)]
+
+
+def _rays(n, seed, half=12.0):
+    return np.concatenate([W.box_rays(n // 2, seed, half=half), W.interior_rays(n - n // 2, seed + 5, radius=half * 0.9)])
+
+
+def test_reference_kats_cuda_wide():
+    kat.check_all(lambda p: engines.GpuEngine(p))
+
+
+def test_reference_kats_cuda_reference_order():
+    kat.check_all(lambda p: engines.GpuEngine(p, reference_order=True))
+
+
+def test_builder_bit_exact_vs_oracle():
+    for verts in (kat.TRI, W.quad_mesh(), W.box_mesh(), W.uv_sphere(9), W.bumpy_sphere(40), W.bumpy_sphere(150)):
+        ob = orc.OracleBLAS.from_verts(verts)
+        g = engines.GpuEngine([(verts, None, [kat.I34], None)])
+        assert g.tlas.read_blas_order(1).tolist() == ob.prims["input_index"].tolist()
+        assert g.tlas.read_blas_nodes(1).tobytes() == ob.nodes.tobytes(), "GPU BVH2 differs from the reference restatement"
+        g.tlas.free()
+
+
+def test_tlas_bit_exact_vs_oracle():
+    pushes = _scene_instanced()
+    o, g = engines.OracleEngine(pushes), engines.GpuEngine(pushes)
+    for k, h in enumerate(g.handles):
+        gi = g.tlas.get_instances(h)
+        oi = o.instances[o.instances["blas_index"] == k + 1]
+        assert gi.tobytes() == oi.tobytes(), "instance descriptors (incl. mat3x4_inverse) differ"
+    assert g.tlas.read_tlas_nodes().tobytes() == o.tlas.nodes.tobytes()
+    assert np.array_equal(g.world_bound(), o.tlas.root_aabb)
+    s = g.tlas.sizes()
+    assert s["tlas_nodes"] == 2 * 317 - 1 and s["blas_prims"] == o.tlas.c.n_blas_prims and s["blas_nodes"] == o.tlas.c.n_blas_nodes
+
+
+@pytest.mark.parametrize("any_hit", [False, True])
+def test_reference_order_traversal_bit_exact(any_hit):
+    pushes = _scene_instanced()
+    o, g = engines.OracleEngine(pushes), engines.GpuEngine(pushes, reference_order=True)
+    rays = _rays(200000, 3)
+    a, b = g.trace(rays, any_hit=any_hit), o.trace(rays, any_hit=any_hit)
+    assert a.tobytes() == b.tobytes()
+
+
+def test_wide_traversal_parity_closest():
+    pushes = _scene_instanced()
+    o, g = engines.OracleEngine(pushes), engines.GpuEngine(pushes)
+    rays = _rays(400000, 9)
+    a, b = g.trace(rays), o.trace(rays)
+    cls = parity.classify(a, b, parity.make_graze_verifier(orc, rays, a, o.instances, o.tris))
+    s = parity.assert_parity(cls, len(rays), label="cuda wide closest")
+    assert s["exact"] >= 0.995 * len(rays), s
+    # t / barycentrics within 1e-5 relative wherever ids agree (they are bit-identical: same expression, same space)
+    same = (a["hit"] == 1) & (a["primitive_id"] == b["primitive_id"]) & (a["instance_id"] == b["instance_id"]) & (b["hit"] == 1) & ~np.isnan(b["t"])
+    assert np.all(np.abs(a["t"][same] - b["t"][same]) <= 1e-5 * np.abs(b["t"][same]))
+    assert np.all(np.abs(a["bary_u"][same] - b["bary_u"][same]) <= 1e-5) and np.all(np.abs(a["bary_v"][same] - b["bary_v"][same]) <= 1e-5)
+
+
+def test_wide_traversal_parity_any():
+    pushes = _scene_instanced()
+    o, g = engines.OracleEngine(pushes), engines.GpuEngine(pushes)
+    rays = _rays(400000, 10)
+    a, b = g.trace(rays, any_hit=True), o.trace(rays, any_hit=True)
+    mism = np.nonzero(a["hit"] != b["hit"])[0]
+    assert len(mism) <= 4, (len(mism), mism[:5])
+    ver = parity.make_graze_verifier(orc, rays, a, o.instances, o.tris)
+    idx = np.nonzero(a["hit"] == 1)[0][:4000]
+    assert ver(idx).all(), "any_hit reported a triangle the exact test does not accept"
+
+
+def test_bumpy_sphere_250k_interior_and_primary():
+    verts = W.bumpy_sphere(355)  # ~250k triangles
+    pushes = [(verts, None, [kat.I34], None)]
+    o, g = engines.OracleEngine(pushes), engines.GpuEngine(pushes)
+    assert g.tlas.read_blas_nodes(1).tobytes() == o.blas[0].nodes.tobytes()
+    for rays, label in ((W.interior_rays(1 << 20, 21), "interior"), (W.pinhole_rays(1024, 1024), "primary")):
+        a, b = g.trace(rays), o.trace(rays)
+        cls = parity.classify(a, b, parity.make_graze_verifier(orc, rays, a, o.instances, o.tris))
+        s = parity.assert_parity(cls, len(rays), label=label)
+        assert s["exact"] >= 0.999 * len(rays), s
+    # the reference-order path is bit-identical on the same rays
+    gr = engines.GpuEngine(pushes, reference_order=True)
+    rays = W.interior_rays(1 << 18, 22)
+    assert gr.trace(rays).tobytes() == o.trace(rays).tobytes()
+
+
+def test_readme_sphere_c1():
+    # BASELINE config 0: README sphere, single-instance TLAS, 1024x1024 primary rays (reference CPU path = oracle)
+    verts = W.uv_sphere(24, (0, 0, 2), 1.0)
+    pushes = [(verts, None, [kat.I34], [1])]
+    o, g = engines.OracleEngine(pushes), engines.GpuEngine(pushes)
+    rays = W.pinhole_rays(1024, 1024, camera_pos=(0, 0, 0))
+    a, b = g.trace(rays), o.trace(rays)
+    cls = parity.classify(a, b, parity.make_graze_verifier(orc, rays, a, o.instances, o.tris))
+    s = parity.assert_parity(cls, len(rays), label="README sphere")
+    assert 0.1 < b["hit"].mean() < 0.9 and s["exact"] >= 0.999 * len(rays)
+
+
+def test_device_resident_buffers_and_counters():
+    import ctypes as C
+
+    pushes = _scene_instanced(50, 10)
+    g = engines.GpuEngine(pushes)
+    rays = _rays(100000, 4)
+    ref = g.trace(rays)
+    L, ctx = g.tlas._lib, g.tlas._ctx
+    d_r, d_h = C.c_void_p(), C.c_void_p()
+    assert L.rc_device_alloc(ctx, rays.nbytes, C.byref(d_r)) == 0 and L.rc_device_alloc(ctx, ref.nbytes, C.byref(d_h)) == 0
+    assert L.rc_memcpy_h2d(ctx, d_r, rays.ctypes.data, rays.nbytes) == 0
+    assert L.rc_trace_closest(ctx, d_r, d_h, len(rays), rc._lib.RC_RAYS_ON_DEVICE | rc._lib.RC_HITS_ON_DEVICE | rc._lib.RC_COUNTERS) == 0
+    out = np.zeros_like(ref)
+    assert L.rc_memcpy_d2h(ctx, out.ctypes.data, d_h, out.nbytes) == 0
+    assert out.tobytes() == ref.tobytes()
+    c = g.tlas.counters()
+    assert c["rays"] == len(rays) and c["nodes"] > len(rays) and c["tri_tests"] > 0 and 0 < c["max_stack"] < 64
+    assert g.tlas.last_kernel_ms() > 0
+    L.rc_device_free(ctx, d_r), L.rc_device_free(ctx, d_h)
