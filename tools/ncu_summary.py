@@ -1,0 +1,62 @@
+#!/usr/bin/env python
+"""Summarise an .ncu-rep (one line per captured launch + stall/pipe breakdown).  usage: ncu_summary.py file.ncu-rep [out.md]"""
+import csv
+import io
+import subprocess
+import sys
+
+KEYS = [
+    ("gpu__time_duration.sum", "time"),
+    ("launch__registers_per_thread", "regs"),
+    ("launch__grid_size", "grid"),
+    ("launch__block_size", "block"),
+    ("sm__warps_active.avg.pct_of_peak_sustained_active", "occupancy%"),
+    ("smsp__thread_inst_executed_per_inst_executed.ratio", "threads/warp-inst"),
+    ("smsp__inst_executed.sum", "warp-insts"),
+    ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue-active%"),
+    ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "xu%"),
+    ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "alu%"),
+    ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "fma%"),
+    ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "lsu%"),
+    ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "lsu-wavefronts%"),
+    ("l1tex__t_sector_hit_rate.pct", "L1 hit%"),
+    ("lts__t_sector_hit_rate.pct", "L2 hit%"),
+    ("lts__t_bytes.sum", "L2 bytes"),
+    ("dram__bytes_read.sum", "dram rd"),
+    ("dram__bytes_write.sum", "dram wr"),
+    ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram%"),
+    ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 tput%"),
+    ("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "L1 tput%"),
+    ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM tput%"),
+]
+
+
+def main():
+    rep = sys.argv[1]
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    col = {h: i for i, h in enumerate(hdr)}
+    out = []
+    for d in data:
+        out.append(f"## {d[col['Kernel Name']][:110]}")
+        for k, label in KEYS:
+            if k in col:
+                out.append(f"- {label}: {d[col[k]]} {units[col[k]]}  (`{k}`)")
+        st = []
+        for h, i in col.items():
+            if h.startswith("smsp__pcsamp_warps_issue_stalled_") and not h.endswith("_not_issued"):
+                try:
+                    st.append((float(d[i]), h.replace("smsp__pcsamp_warps_issue_stalled_", "")))
+                except ValueError:
+                    pass
+        tot = sum(v for v, _ in st) or 1
+        out.append("- warp-state samples: " + ", ".join(f"{n} {100 * v / tot:.1f}%" for v, n in sorted(st, reverse=True)[:9]))
+    text = "\n".join(out)
+    print(text)
+    if len(sys.argv) > 2:
+        open(sys.argv[2], "w").write(text + "\n")
+
+
+if __name__ == "__main__":
+    main()
