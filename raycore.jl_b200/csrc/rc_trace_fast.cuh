@@ -1,18 +1,22 @@
 // rc_trace_fast.cuh — the default traversal kernel: persistent lanes over the quantised BVH4 with a
 // warp-level step scheduler.
 //
-// Every lane owns one ray at a time and is, at any moment, ready for a NODE step (its next reference is a wide
-// node), ready for a TRIANGLE step (it has a leaf parked), both, or neither (finished, waiting for a new ray).
-// Each iteration the warp votes (two ballots) and executes the step kind with more ready lanes, so a freshly
-// fetched ray that needs ten box steps to reach its first leaf never stalls 31 lanes that are waiting to test
-// triangles, and vice versa (profiles/r1_v2: the plain while-while loop ran the box code at 9.4/32 lanes).
-// Finished lanes are refilled together (one warp-aggregated atomic on the global work counter) once enough of
-// them have retired, so the refill code also runs with many lanes.
+// Every lane owns one ray at a time and is, at any moment, ready for one or two of four step kinds:
+//   N  node step      its next reference is a wide node (4 quantised child boxes)
+//   T  triangle step  it has a leaf parked (one triangle per step)
+//   X  level step     it must enter an instance (TLAS leaf) or leave one (sentinel popped)
+//   F  refill         its ray is finished (or it has none yet)
+// Each iteration the warp counts the ready lanes per kind with ONE packed REDUX.SUM vote and executes the kind with the
+// most ready lanes, so a freshly fetched ray that needs ten box steps to reach its first leaf never stalls 31 lanes that
+// wait to test triangles, and vice versa (profiles/r1_v2: a plain while-while loop ran the box code at 9.4/32 lanes,
+// this scheduler at 18.6/32 in r1_v3).  Refills are warp-cooperative (one atomic on the global work counter per refill)
+// and deferred until RC_FETCH_MIN lanes are idle, so the refill / retire code also runs with many lanes.
 //
-// Arithmetic: child planes are decoded with PRMT + FADD (no I2F: XU pipe saturated in profiles/r1_v1); the slab test
-// is 24 FMAs against per-node (scale * inv_d, (origin - o) * inv_d) plus an explicit rounding bound (conservative);
+// Arithmetic: child planes are decoded with PRMT + FADD (no I2F: the XU pipe saturated in profiles/r1_v1); the slab
+// test is 24 FMAs against per-node (scale * inv_d, (origin - o) * inv_d) plus an explicit rounding bound (conservative);
 // the triangle test is the exact, FMA-free Moeller-Trumbore of rc_device.cuh, so t/u/v are bit-identical to the
-// reference evaluation whenever the same triangle wins.
+// reference evaluation whenever the same triangle wins.  The traversal stack lives in shared memory ([depth][thread],
+// conflict-free) with a local-memory overflow area, so pushes / pops never touch the L1 tag stage.
 #pragma once
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -36,7 +40,10 @@ __device__ __forceinline__ void rc_store_hit(rc_hit *hits, unsigned long long i,
     __stcs(p + 1, make_float4(h.bary_u, h.bary_v, __uint_as_float(h.instance_id), __uint_as_float(h.metadata)));
 }
 
-#define RC_FETCH_MIN 12  // refill when at least this many lanes of the warp are idle (or nothing else can run)
+#define RC_FETCH_MIN 12    // refill when at least this many lanes of the warp are idle (or nothing else can run)
+#define RC_SSTACK 24       // stack entries per lane kept in shared memory
+#define RC_LSTACK 104      // overflow entries per lane in local memory (total depth 128)
+#define RC_DEADLANE 0xFFFFFFFDu
 
 #define RC_CE(ta, ra, tb, rb)                    \
     {                                            \
@@ -48,18 +55,24 @@ __device__ __forceinline__ void rc_store_hit(rc_hit *hits, unsigned long long i,
         ta = tl_; tb = th_; ra = rl_; rb = rh_;  \
     }
 
-__device__ __forceinline__ float rc_fast_inv(float d) {  // safe_invdir's clamp; correctly rounded reciprocal without the IEEE-division slow path
+// safe_invdir's clamp (src/instanced-bvh.jl:1742-1748) with MUFU.RCP (<= 1 ulp); only the conservative box test uses it,
+// and RC_BOX_EPS_FAST covers the extra ulp.
+__device__ __forceinline__ float rc_fast_inv(float d) {
     const float ooeps = 1.0e-5f;
-    return __frcp_rn(fabsf(d) > ooeps ? d : copysignf(ooeps, d));
+    float x = fabsf(d) > ooeps ? d : copysignf(ooeps, d), r;
+    asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
+#define RC_BOX_EPS_FAST 4.8e-7f  // 2^-21
 
 template <bool ANY, bool COUNT>
 __global__ void __launch_bounds__(RC_TRACE_THREADS) k_trace_wide(RcScene sc, const rc_ray *__restrict__ rays, rc_hit *__restrict__ hits, unsigned long long n,
                                                                  unsigned long long *__restrict__ work, RcCounters *__restrict__ counters,
                                                                  uint32_t *__restrict__ overflow) {
+    __shared__ uint32_t sstack[RC_SSTACK * RC_TRACE_THREADS];
+    uint32_t lstack[RC_LSTACK];
     const uint32_t FULL = 0xFFFFFFFFu;
-    const uint32_t lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
-    uint32_t stack[RC_STACK_WIDE];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, lt_mask = (1u << lane) - 1u;
     RcLocalCounters lc = {0, 0, 0, 0, 0};
     unsigned long long traced = 0, idx = 0;
     f3 wo = mk3(0, 0, 0), wd = mk3(0, 0, 0), o = wo, d = wd, inv = wo;
@@ -69,22 +82,102 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS) k_trace_wide(RcScene sc, con
     const RcTri *tris = nullptr;
     const RcNode4 *nodes = sc.tlas4;
     uint32_t cur = RC_INVALID, leaf = 0, leaf_k = 0;
-    bool dead = false, have = false, ovf = false;
+    bool have = false, ovf = false;
+
+#define RC_PUSH(v)                                                         \
+    {                                                                      \
+        if (sp < RC_SSTACK) sstack[sp * RC_TRACE_THREADS + tid] = (v);     \
+        else if (sp < RC_SSTACK + RC_LSTACK) lstack[sp - RC_SSTACK] = (v); \
+        else ovf = true;                                                   \
+        sp++;                                                              \
+    }
+#define RC_TOP() ((sp - 1) < RC_SSTACK ? sstack[(sp - 1) * RC_TRACE_THREADS + tid] : ((sp - 1) < RC_SSTACK + RC_LSTACK ? lstack[sp - 1 - RC_SSTACK] : RC_INVALID))
 
     for (;;) {
-        // ---- cheap per-lane transitions (park a leaf, leave / enter an instance) ------------------------------------
-        if (have) {
-            if (cur == RC_SENTINEL && leaf == 0) {  // back to the TLAS: restore the world ray (src/instanced-bvh.jl:1996-2006)
-                cur_inst = -1;
-                nodes = sc.tlas4;
-                o = wo; d = wd;
-                inv = mk3(rc_fast_inv(d.x), rc_fast_inv(d.y), rc_fast_inv(d.z));
-                cur = stack[--sp];
+        // park a leaf (cheap, every iteration): a BLAS leaf reference with no leaf parked yet
+        if (cur_inst >= 0 && (cur & RC_LEAF_BIT) && cur < RC_DEADLANE && leaf == 0) {
+            leaf = cur;
+            leaf_k = 0;
+            cur = RC_TOP();
+            sp--;
+        }
+        const bool wantN = !(cur & RC_LEAF_BIT);
+        const bool wantT = leaf != 0;
+        const bool wantX = (cur_inst < 0 && (cur & RC_LEAF_BIT) && cur < RC_DEADLANE) || (cur == RC_SENTINEL && leaf == 0);
+        const bool wantF = cur == RC_INVALID && leaf == 0;
+        const uint32_t votes = __reduce_add_sync(FULL, (uint32_t)wantN | ((uint32_t)wantT << 8) | ((uint32_t)wantX << 16) | ((uint32_t)wantF << 24));
+        if (votes == 0) break;  // every lane is dead
+        const uint32_t nN = votes & 0xFFu, nT = (votes >> 8) & 0xFFu, nX = (votes >> 16) & 0xFFu, nF = votes >> 24;
+
+        if (nF > 0 && (nF >= RC_FETCH_MIN || (votes & 0x00FFFFFFu) == 0)) {
+            // ---- F: retire + refill (warp-cooperative) -----------------------------------------------------------------
+            if (wantF && have) {
+                rc_hit h;
+                if (best_inst >= 0) {
+                    h.hit = 1; h.t = t_max; h.primitive_id = best_prim; h.instance_custom_index = sc.aux[best_inst].custom_index;
+                    h.bary_u = hit_u; h.bary_v = hit_v; h.instance_id = (uint32_t)best_inst; h.metadata = best_meta;
+                } else {
+                    rc_write_miss(h);
+                }
+                rc_store_hit(hits, idx, h);
+                if (ovf) atomicAdd(overflow, 1u);
+                traced++;
+                have = false;
             }
-            if (cur != RC_INVALID && cur != RC_SENTINEL && (cur & RC_LEAF_BIT)) {
-                if (cur_inst < 0) {
-                    // TLAS leaf: enter the instance (:1961-1977); ray transformed with the reference's exact arithmetic
-                    cur_inst = (int)(cur & RC_LEAF_START_MASK);
+            const uint32_t mNeed = __ballot_sync(FULL, wantF);
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(work, (unsigned long long)__popc(mNeed));
+            base = __shfl_sync(FULL, base, 0);
+            if (wantF) {
+                idx = base + (unsigned long long)__popc(mNeed & lt_mask);
+                if (idx >= n) {
+                    cur = RC_DEADLANE;
+                } else {
+                    rc_ray r = rc_load_ray(rays, idx);
+                    RcRayIn w = rc_prepare_ray(r, ANY);
+                    wo = w.o; wd = w.d; o = wo; d = wd;
+                    t_min = w.t_min; t_max = w.t_max;
+                    inv = mk3(rc_fast_inv(d.x), rc_fast_inv(d.y), rc_fast_inv(d.z));
+                    cur_inst = -1; best_inst = -1; ovf = false;
+                    nodes = sc.tlas4;
+                    sstack[tid] = RC_INVALID;
+                    sp = 1;
+                    cur = 1;
+                    have = true;
+                }
+            }
+        } else if (nT >= nN && nT >= nX) {
+            // ---- T: one triangle of the parked leaf per lane -------------------------------------------------------------
+            if (wantT) {
+                const uint32_t start = leaf & RC_LEAF_START_MASK, count = ((leaf >> RC_LEAF_COUNT_SHIFT) & 7u) + 1u;
+                const float4 *tp = reinterpret_cast<const float4 *>(tris + start + leaf_k);
+                const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+                float t, u, v;
+                if (COUNT) lc.tri_tests++;
+                if (x_intersect_triangle(o, d, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), t_min, t_max, t, u, v) && t == t) {
+                    t_max = t;
+                    best_inst = cur_inst;
+                    best_prim = __float_as_uint(a.w);
+                    best_meta = __float_as_uint(b.w);
+                    hit_u = u; hit_v = v;
+                    if (ANY) { cur = RC_INVALID; sp = 0; leaf_k = count; }
+                }
+                if (++leaf_k >= count) leaf = 0;
+            }
+        } else if (nX > nN) {
+            // ---- X: enter an instance (TLAS leaf) or return to the TLAS (sentinel) -------------------------------------------
+            if (wantX) {
+                if (cur == RC_SENTINEL) {
+                    cur_inst = -1;  // src/instanced-bvh.jl:1996-2006
+                    nodes = sc.tlas4;
+                    cur = RC_TOP();
+                    sp--;
+                    if (cur != RC_INVALID) {  // more TLAS work: restore the world ray (skipped when the ray is finished)
+                        o = wo; d = wd;
+                        inv = mk3(rc_fast_inv(d.x), rc_fast_inv(d.y), rc_fast_inv(d.z));
+                    }
+                } else {
+                    cur_inst = (int)(cur & RC_LEAF_START_MASK);  // :1961-1977; ray transformed with the reference's exact arithmetic
                     const char *ip = reinterpret_cast<const char *>(sc.inst + cur_inst);
                     float m[12];
 #pragma unroll
@@ -98,88 +191,13 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS) k_trace_wide(RcScene sc, con
                     o = x_transform_point(m, wo);
                     d = x_transform_direction(m, wd);
                     inv = mk3(rc_fast_inv(d.x), rc_fast_inv(d.y), rc_fast_inv(d.z));
-                    if (sp >= RC_STACK_WIDE) { ovf = true; sp = 1; cur = RC_INVALID; leaf = 0; }
-                    else {
-                        stack[sp++] = RC_SENTINEL;
-                        if (COUNT) { lc.inst_entries++; if ((uint32_t)sp > lc.max_stack) lc.max_stack = (uint32_t)sp; }
-                        cur = 1;
-                    }
-                } else if (leaf == 0) {
-                    leaf = cur;  // park the leaf, keep descending
-                    leaf_k = 0;
-                    cur = stack[--sp];
-                }
-            }
-        }
-        const bool wantN = have && !(cur & RC_LEAF_BIT);
-        const bool wantT = have && leaf != 0;
-        const bool idle = !have && !dead;
-        const bool fin = have && leaf == 0 && cur == RC_INVALID;
-        const uint32_t mN = __ballot_sync(FULL, wantN), mT = __ballot_sync(FULL, wantT), mF = __ballot_sync(FULL, fin || idle);
-        const int nN = __popc(mN), nT = __popc(mT), nF = __popc(mF);
-
-        if (nF > 0 && (nF >= RC_FETCH_MIN || (nN == 0 && nT == 0))) {
-            // ---- retire + refill (warp-cooperative) ---------------------------------------------------------------
-            if (fin) {
-                rc_hit h;
-                if (best_inst >= 0) {
-                    h.hit = 1; h.t = t_max; h.primitive_id = best_prim; h.instance_custom_index = sc.aux[best_inst].custom_index;
-                    h.bary_u = hit_u; h.bary_v = hit_v; h.instance_id = (uint32_t)best_inst; h.metadata = best_meta;
-                } else {
-                    rc_write_miss(h);
-                }
-                rc_store_hit(hits, idx, h);
-                if (ovf) atomicAdd(overflow, 1u);
-                traced++;
-                have = false;
-            }
-            const uint32_t mNeed = __ballot_sync(FULL, !have && !dead);
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(work, (unsigned long long)__popc(mNeed));
-            base = __shfl_sync(FULL, base, 0);
-            if (!have && !dead) {
-                idx = base + (unsigned long long)__popc(mNeed & lt_mask);
-                if (idx >= n) {
-                    dead = true;
-                } else {
-                    rc_ray r = rc_load_ray(rays, idx);
-                    RcRayIn w = rc_prepare_ray(r, ANY);
-                    wo = w.o; wd = w.d; o = wo; d = wd;
-                    t_min = w.t_min; t_max = w.t_max;
-                    inv = mk3(rc_fast_inv(d.x), rc_fast_inv(d.y), rc_fast_inv(d.z));
-                    cur_inst = -1; best_inst = -1; ovf = false;
-                    nodes = sc.tlas4;
-                    stack[0] = RC_INVALID;
-                    sp = 1;
+                    RC_PUSH(RC_SENTINEL)
+                    if (COUNT) { lc.inst_entries++; if ((uint32_t)sp > lc.max_stack) lc.max_stack = (uint32_t)sp; }
                     cur = 1;
-                    leaf = 0;
-                    have = true;
                 }
-            }
-            if (__all_sync(FULL, dead)) break;
-            continue;
-        }
-
-        if (nT >= nN) {
-            // ---- triangle step: one triangle of the parked leaf per lane --------------------------------------------
-            if (wantT) {
-                const uint32_t start = leaf & RC_LEAF_START_MASK, count = ((leaf >> RC_LEAF_COUNT_SHIFT) & 7u) + 1u;
-                const float4 *tp = reinterpret_cast<const float4 *>(tris + start + leaf_k);
-                const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
-                float t, u, v;
-                if (COUNT) lc.tri_tests++;
-                if (x_intersect_triangle(o, d, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), t_min, t_max, t, u, v) && t == t) {
-                    t_max = t;
-                    best_inst = cur_inst;
-                    best_prim = __float_as_uint(a.w);
-                    best_meta = __float_as_uint(b.w);
-                    hit_u = u; hit_v = v;
-                    if (ANY) { cur = RC_INVALID; sp = 1; leaf_k = count; }
-                }
-                if (++leaf_k >= count) leaf = 0;
             }
         } else {
-            // ---- node step: test the 4 quantised child boxes, descend into the nearest, push the rest far -> near --
+            // ---- N: test the 4 quantised child boxes, descend into the nearest, push the rest far -> near -----------------
             if (wantN) {
                 const float4 *np = reinterpret_cast<const float4 *>(nodes + cur);
                 const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
@@ -188,7 +206,7 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS) k_trace_wide(RcScene sc, con
                 const float ax = __uint_as_float((e & 0xFFu) << 23) * inv.x, ay = __uint_as_float(((e >> 8) & 0xFFu) << 23) * inv.y,
                             az = __uint_as_float(((e >> 16) & 0xFFu) << 23) * inv.z;
                 const float bx = (n0.x - o.x) * inv.x, by = (n0.y - o.y) * inv.y, bz = (n0.z - o.z) * inv.z;
-                const float slack = RC_BOX_EPS * fmaxf(fmaxf(fmaf(255.0f, fabsf(ax), fabsf(bx)), fmaf(255.0f, fabsf(ay), fabsf(by))), fmaf(255.0f, fabsf(az), fabsf(bz)));
+                const float slack = RC_BOX_EPS_FAST * fmaxf(fmaxf(fmaf(255.0f, fabsf(ax), fabsf(bx)), fmaf(255.0f, fabsf(ay), fabsf(by))), fmaf(255.0f, fabsf(az), fabsf(bz)));
                 const uint32_t qlox = __float_as_uint(n1.x), qloy = __float_as_uint(n1.y), qloz = __float_as_uint(n1.z), qhix = __float_as_uint(n1.w);
                 const uint32_t qhiy = __float_as_uint(n2.x), qhiz = __float_as_uint(n2.y);
                 uint32_t r0 = __float_as_uint(n2.z), r1 = __float_as_uint(n2.w), r2 = __float_as_uint(n3.x), r3 = __float_as_uint(n3.y);
@@ -206,20 +224,22 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS) k_trace_wide(RcScene sc, con
                 // empty slots carry an inverted box (qlo = 255, qhi = 0) and could only pass through the slack: mask them
                 float t0 = r0 == RC_INVALID ? CUDART_INF_F : tn[0], t1 = r1 == RC_INVALID ? CUDART_INF_F : tn[1];
                 float t2 = r2 == RC_INVALID ? CUDART_INF_F : tn[2], t3 = r3 == RC_INVALID ? CUDART_INF_F : tn[3];
-                const int nh = (t0 < CUDART_INF_F) + (t1 < CUDART_INF_F) + (t2 < CUDART_INF_F) + (t3 < CUDART_INF_F);
                 RC_CE(t0, r0, t1, r1) RC_CE(t2, r2, t3, r3) RC_CE(t0, r0, t2, r2) RC_CE(t1, r1, t3, r3) RC_CE(t1, r1, t2, r2)
-                if (sp + 3 > RC_STACK_WIDE) {
-                    ovf = true; sp = 1; cur = RC_INVALID; leaf = 0;
-                } else {
-                    if (nh > 3) stack[sp++] = r3;
-                    if (nh > 2) stack[sp++] = r2;
-                    if (nh > 1) stack[sp++] = r1;
-                    if (COUNT && (uint32_t)sp > lc.max_stack) lc.max_stack = (uint32_t)sp;
-                    cur = nh > 0 ? r0 : stack[--sp];
-                }
+                // sorted near -> far, misses (+inf) last: push far -> near, continue with the nearest (or pop)
+                if (t3 < CUDART_INF_F) RC_PUSH(r3)
+                if (t2 < CUDART_INF_F) RC_PUSH(r2)
+                if (t1 < CUDART_INF_F) RC_PUSH(r1)
+                if (COUNT && (uint32_t)sp > lc.max_stack) lc.max_stack = (uint32_t)sp;
+                const uint32_t top = RC_TOP();
+                const bool hit0 = t0 < CUDART_INF_F;
+                cur = hit0 ? r0 : top;
+                sp -= hit0 ? 0 : 1;
+                if (ovf) { cur = RC_INVALID; leaf = 0; sp = 0; }
             }
         }
     }
+#undef RC_PUSH
+#undef RC_TOP
     if (COUNT) {
         atomicAdd(&counters->rays, traced);
         atomicAdd(&counters->nodes, (unsigned long long)lc.nodes);
