@@ -122,9 +122,9 @@ int32_t rc_create(int32_t device, rc_context **out) {
     CREATE_CK(cudaEventCreate(&ctx->ev_t1));
     CREATE_CK(cudaMalloc(&ctx->d_work, sizeof(unsigned long long)));
     CREATE_CK(cudaMalloc(&ctx->d_counters, sizeof(RcCounters)));
-    CREATE_CK(cudaMalloc(&ctx->d_overflow, sizeof(uint32_t)));
+    CREATE_CK(cudaMalloc(&ctx->d_overflow, 2 * sizeof(uint32_t)));
     CREATE_CK(cudaMemset(ctx->d_counters, 0, sizeof(RcCounters)));
-    CREATE_CK(cudaMemset(ctx->d_overflow, 0, sizeof(uint32_t)));
+    CREATE_CK(cudaMemset(ctx->d_overflow, 0, 2 * sizeof(uint32_t)));
     // keep freed blocks cached in the stream-ordered pool: rebuild-per-frame workloads reuse them
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -501,10 +501,10 @@ static int32_t ensure_capacity(rc_context *ctx, void **buf, size_t *cap, size_t 
 
 static int32_t check_overflow(rc_context *ctx) {
     uint32_t ov = 0;
-    RC_CUDA(ctx, cudaMemcpyAsync(&ov, ctx->d_overflow, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    RC_CUDA(ctx, cudaMemcpyAsync(&ov, ctx->d_overflow + 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
     RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (ov) {
-        cudaMemsetAsync(ctx->d_overflow, 0, 4, ctx->stream);
+        cudaMemsetAsync(ctx->d_overflow + 1, 0, 4, ctx->stream);
         RC_FAIL(ctx, RC_ERR_STACK_OVERFLOW, "traversal stack overflow for " + std::to_string(ov) + " ray(s)");
     }
     return RC_OK;
@@ -623,7 +623,7 @@ static int32_t grid_common(rc_context *ctx, const float viewdir[3], uint32_t gri
         RC_CUDA(ctx, cudaMallocAsync(&d_cent, 4 * sizeof(double), ctx->stream));
         RC_CUDA(ctx, cudaMemsetAsync(d_cent, 0, 4 * sizeof(double), ctx->stream));
     }
-    rc_launch_grid_trace(ctx->stream, make_scene(ctx), f, d_hits, d_points, d_illum, n_illum, d_cent, ctx->d_overflow, ctx->max_blocks);
+    rc_launch_grid_trace(ctx->stream, make_scene(ctx), f, d_hits, d_points, d_illum, n_illum, d_cent, ctx->d_overflow + 1, ctx->max_blocks);
     ctx->last_launches = 1;
     if (hits) RC_CUDA(ctx, cudaMemcpyAsync(hits, d_hits, n * sizeof(rc_hit), cudaMemcpyDeviceToHost, ctx->stream));
     if (points) RC_CUDA(ctx, cudaMemcpyAsync(points, d_points, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
@@ -683,7 +683,7 @@ int32_t rc_view_factors(rc_context *ctx, uint32_t rays_per_triangle, uint64_t se
     RC_CUDA(ctx, cudaMemsetAsync(d_skipped, 0, 8, ctx->stream));
     cudaEventRecord(ctx->ev_t0, ctx->stream);
     rc_launch_view_factors(ctx->stream, make_scene(ctx), ctx->d_flat, ctx->n_flat_blas, ctx->n_flat_prims, rays_per_triangle, seed, row_base, n_rows, n_cols, d_out,
-                           nullptr, d_skipped, ctx->d_overflow, ctx->max_blocks);
+                           nullptr, d_skipped, ctx->d_overflow + 1, ctx->max_blocks);
     cudaEventRecord(ctx->ev_t1, ctx->stream);
     ctx->last_launches = 1;
     unsigned long long sk = 0;
@@ -711,7 +711,7 @@ int32_t rc_view_factor_rays(rc_context *ctx, uint32_t rays_per_triangle, uint64_
     RC_CUDA(ctx, cudaMallocAsync(&d_rays, n * sizeof(rc_ray), ctx->stream));
     RC_CUDA(ctx, cudaMemsetAsync(d_rays, 0, n * sizeof(rc_ray), ctx->stream));
     rc_launch_view_factors(ctx->stream, make_scene(ctx), ctx->d_flat, ctx->n_flat_blas, ctx->n_flat_prims, rays_per_triangle, seed, row_base, n_rows, ctx->n_flat_prims,
-                           nullptr, d_rays, nullptr, ctx->d_overflow, ctx->max_blocks);
+                           nullptr, d_rays, nullptr, ctx->d_overflow + 1, ctx->max_blocks);
     RC_CUDA(ctx, cudaMemcpyAsync(out, d_rays, n * sizeof(rc_ray), cudaMemcpyDeviceToHost, ctx->stream));
     cudaFreeAsync(d_rays, ctx->stream);
     RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS) k_trace(RcScene sc, const rc
         if (i >= n) break;
         rc_ray r = rc_load_ray(rays, i);
         rc_hit h;
-        if (!rc_trace_reference_order<ANY, COUNT>(sc, r, h, &lc)) atomicAdd(overflow, 1u);
+        if (!rc_trace_reference_order<ANY, COUNT>(sc, r, h, &lc)) atomicAdd(overflow + 1, 1u);
         rc_store_hit(hits, i, h);
         traced++;
     }
@@ -34,6 +34,21 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS) k_trace(RcScene sc, const rc
         atomicAdd(&counters->tri_tests, (unsigned long long)lc.tri_tests);
         atomicAdd(&counters->inst_entries, (unsigned long long)lc.inst_entries);
         atomicMax(&counters->max_stack, (unsigned long long)lc.max_stack);
+    }
+}
+
+// Re-trace the rays whose short (shared-memory) stack overflowed in k_trace_wide with the deep-stack generic body.
+// overflow[0] = rays flagged by the fast kernel (exit immediately when 0), overflow[1] = rays no stack could hold (error).
+template <bool ANY>
+__global__ void __launch_bounds__(RC_TRACE_THREADS) k_trace_fixup(RcScene sc, const rc_ray *__restrict__ rays, rc_hit *__restrict__ hits, unsigned long long n,
+                                                                  uint32_t *__restrict__ overflow) {
+    if (*reinterpret_cast<volatile uint32_t *>(overflow) == 0) return;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        if (hits[i].hit != RC_OVERFLOW_MARK) continue;
+        rc_ray r = rc_load_ray(rays, i);
+        rc_hit h;
+        if (!rc_trace_wide<ANY, false>(sc, r, h, nullptr)) atomicAdd(overflow + 1, 1u);
+        rc_store_hit(hits, i, h);
     }
 }
 
@@ -51,6 +66,7 @@ bool rc_launch_trace(cudaStream_t st, const RcTraceLaunch &L, std::string &err) 
         k_fill_miss<<<(unsigned)((L.n + 255) / 256), 256, 0, st>>>(L.hits, L.n);
     } else {
         cudaMemsetAsync(L.work, 0, sizeof(unsigned long long), st);
+        cudaMemsetAsync(L.overflow, 0, sizeof(uint32_t), st);
         unsigned long long want = (L.n + RC_TRACE_THREADS - 1) / RC_TRACE_THREADS;
         int blocks = (int)(want < (unsigned long long)L.max_blocks ? want : (unsigned long long)L.max_blocks);
         if (blocks < 1) blocks = 1;
@@ -63,6 +79,10 @@ bool rc_launch_trace(cudaStream_t st, const RcTraceLaunch &L, std::string &err) 
             else { if (L.count) k_trace<false, true><<<blocks, RC_TRACE_THREADS, 0, st>>>(RC_ARGS); else k_trace<false, false><<<blocks, RC_TRACE_THREADS, 0, st>>>(RC_ARGS); }
         }
 #undef RC_ARGS
+        if (L.wide) {
+            if (L.any) k_trace_fixup<true><<<blocks, RC_TRACE_THREADS, 0, st>>>(L.scene, L.rays, L.hits, L.n, L.overflow);
+            else k_trace_fixup<false><<<blocks, RC_TRACE_THREADS, 0, st>>>(L.scene, L.rays, L.hits, L.n, L.overflow);
+        }
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { err = std::string("trace launch: ") + cudaGetErrorString(e); return false; }

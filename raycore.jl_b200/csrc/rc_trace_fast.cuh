@@ -41,8 +41,8 @@ __device__ __forceinline__ void rc_store_hit(rc_hit *hits, unsigned long long i,
 }
 
 #define RC_FETCH_MIN 12    // refill when at least this many lanes of the warp are idle (or nothing else can run)
-#define RC_SSTACK 24       // stack entries per lane kept in shared memory
-#define RC_LSTACK 104      // overflow entries per lane in local memory (total depth 128)
+#define RC_SSTACK 32       // stack entries per lane (shared memory, [depth][thread])
+#define RC_OVERFLOW_MARK 0xFFFFFFFFu  // rc_hit.hit of a ray whose short stack overflowed (re-traced by k_trace_fixup)
 #define RC_DEADLANE 0xFFFFFFFDu
 
 #define RC_CE(ta, ra, tb, rb)                    \
@@ -70,7 +70,6 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS) k_trace_wide(RcScene sc, con
                                                                  unsigned long long *__restrict__ work, RcCounters *__restrict__ counters,
                                                                  uint32_t *__restrict__ overflow) {
     __shared__ uint32_t sstack[RC_SSTACK * RC_TRACE_THREADS];
-    uint32_t lstack[RC_LSTACK];
     const uint32_t FULL = 0xFFFFFFFFu;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, lt_mask = (1u << lane) - 1u;
     RcLocalCounters lc = {0, 0, 0, 0, 0};
@@ -84,22 +83,25 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS) k_trace_wide(RcScene sc, con
     uint32_t cur = RC_INVALID, leaf = 0, leaf_k = 0;
     bool have = false, ovf = false;
 
-#define RC_PUSH(v)                                                         \
-    {                                                                      \
-        if (sp < RC_SSTACK) sstack[sp * RC_TRACE_THREADS + tid] = (v);     \
-        else if (sp < RC_SSTACK + RC_LSTACK) lstack[sp - RC_SSTACK] = (v); \
-        else ovf = true;                                                   \
-        sp++;                                                              \
+    // The stack holds RC_SSTACK entries per lane.  A push beyond that is dropped and flags the ray; flagged rays are
+    // re-traced by k_trace_fixup with the deep-stack generic body, so results never depend on the short stack.
+#define RC_PUSH(v)                                                     \
+    {                                                                  \
+        if (sp < RC_SSTACK) sstack[sp * RC_TRACE_THREADS + tid] = (v); \
+        ovf |= sp >= RC_SSTACK;                                        \
+        sp++;                                                          \
     }
-#define RC_TOP() ((sp - 1) < RC_SSTACK ? sstack[(sp - 1) * RC_TRACE_THREADS + tid] : ((sp - 1) < RC_SSTACK + RC_LSTACK ? lstack[sp - 1 - RC_SSTACK] : RC_INVALID))
+#define RC_TOP() (sstack[min(max(sp - 1, 0), RC_SSTACK - 1) * RC_TRACE_THREADS + tid])
 
     for (;;) {
         // park a leaf (cheap, every iteration): a BLAS leaf reference with no leaf parked yet
-        if (cur_inst >= 0 && (cur & RC_LEAF_BIT) && cur < RC_DEADLANE && leaf == 0) {
-            leaf = cur;
-            leaf_k = 0;
-            cur = RC_TOP();
-            sp--;
+        {
+            const bool park = cur_inst >= 0 && (cur & RC_LEAF_BIT) && cur < RC_DEADLANE && leaf == 0;
+            const uint32_t top = RC_TOP();
+            leaf = park ? cur : leaf;
+            leaf_k = park ? 0u : leaf_k;
+            cur = park ? top : cur;
+            sp -= park ? 1 : 0;
         }
         const bool wantN = !(cur & RC_LEAF_BIT);
         const bool wantT = leaf != 0;
@@ -119,8 +121,8 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS) k_trace_wide(RcScene sc, con
                 } else {
                     rc_write_miss(h);
                 }
+                if (ovf) { rc_write_miss(h); h.hit = RC_OVERFLOW_MARK; atomicAdd(overflow, 1u); }
                 rc_store_hit(hits, idx, h);
-                if (ovf) atomicAdd(overflow, 1u);
                 traced++;
                 have = false;
             }
@@ -194,6 +196,7 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS) k_trace_wide(RcScene sc, con
                     RC_PUSH(RC_SENTINEL)
                     if (COUNT) { lc.inst_entries++; if ((uint32_t)sp > lc.max_stack) lc.max_stack = (uint32_t)sp; }
                     cur = 1;
+                    if (ovf) { cur = RC_INVALID; leaf = 0; sp = 0; }
                 }
             }
         } else {
@@ -224,16 +227,19 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS) k_trace_wide(RcScene sc, con
                 // empty slots carry an inverted box (qlo = 255, qhi = 0) and could only pass through the slack: mask them
                 float t0 = r0 == RC_INVALID ? CUDART_INF_F : tn[0], t1 = r1 == RC_INVALID ? CUDART_INF_F : tn[1];
                 float t2 = r2 == RC_INVALID ? CUDART_INF_F : tn[2], t3 = r3 == RC_INVALID ? CUDART_INF_F : tn[3];
-                RC_CE(t0, r0, t1, r1) RC_CE(t2, r2, t3, r3) RC_CE(t0, r0, t2, r2) RC_CE(t1, r1, t3, r3) RC_CE(t1, r1, t2, r2)
-                // sorted near -> far, misses (+inf) last: push far -> near, continue with the nearest (or pop)
-                if (t3 < CUDART_INF_F) RC_PUSH(r3)
-                if (t2 < CUDART_INF_F) RC_PUSH(r2)
-                if (t1 < CUDART_INF_F) RC_PUSH(r1)
+                // the nearest hit child is entered next (exact argmin); the other hit children are pushed in slot order
+                const float tm = fminf(fminf(t0, t1), fminf(t2, t3));
+                const bool any_hit = tm < CUDART_INF_F;
+                const bool e0 = t0 == tm, e1 = !e0 && t1 == tm, e2 = !e0 && !e1 && t2 == tm, e3 = !e0 && !e1 && !e2;
+                if (t3 < CUDART_INF_F && !e3) RC_PUSH(r3)
+                if (t2 < CUDART_INF_F && !e2) RC_PUSH(r2)
+                if (t1 < CUDART_INF_F && !e1) RC_PUSH(r1)
+                if (t0 < CUDART_INF_F && !e0) RC_PUSH(r0)
                 if (COUNT && (uint32_t)sp > lc.max_stack) lc.max_stack = (uint32_t)sp;
                 const uint32_t top = RC_TOP();
-                const bool hit0 = t0 < CUDART_INF_F;
-                cur = hit0 ? r0 : top;
-                sp -= hit0 ? 0 : 1;
+                const uint32_t rn = e0 ? r0 : (e1 ? r1 : (e2 ? r2 : r3));
+                cur = any_hit ? rn : top;
+                sp -= any_hit ? 0 : 1;
                 if (ovf) { cur = RC_INVALID; leaf = 0; sp = 0; }
             }
         }
