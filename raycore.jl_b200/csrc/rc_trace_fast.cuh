@@ -6,18 +6,24 @@
 //   T  triangle step  it has a leaf parked (one triangle per step)
 //   X  level step     it must enter an instance (TLAS leaf) or leave one (sentinel popped)
 //   F  refill         its ray is finished (or it has none yet)
-// Each iteration the warp counts the ready lanes per kind with ONE packed REDUX.SUM vote and executes the kind with the
-// most ready lanes, so a freshly fetched ray that needs ten box steps to reach its first leaf never stalls 31 lanes that
-// wait to test triangles, and vice versa (profiles/r1_v2: a plain while-while loop ran the box code at 9.4/32 lanes,
-// this scheduler at 18.6/32 in r1_v3).  Refills are warp-cooperative (one atomic on the global work counter per refill)
-// and deferred until RC_FETCH_MIN lanes are idle, so the refill / retire code also runs with many lanes.
+// Each lane keeps its readiness as a packed vote word (one byte per kind); every iteration the warp sums the votes
+// with ONE REDUX.SUM and executes the kind with the most ready lanes, so a freshly fetched ray that needs ten box steps
+// to reach its first leaf never stalls 31 lanes that wait to test triangles, and vice versa (profiles/r1_v2: a plain
+// while-while loop ran the box code at 9.4/32 lanes, this scheduler at 18.5/32).  The vote word is recomputed only by
+// the lanes that just executed a step ("settle"), which also parks a freshly reached leaf so the lane can keep descending.
+// Refills are warp-cooperative (one atomic on the global work counter per refill) and deferred until RC_FETCH_MIN
+// lanes are idle, so the refill / retire code also runs with many lanes.
 //
-// Arithmetic: child planes are decoded with PRMT + FADD (no I2F: the XU pipe saturated in profiles/r1_v1); the slab
-// test is 24 FMAs against per-node (scale * inv_d, (origin - o) * inv_d) plus an explicit rounding bound (conservative);
-// the triangle test is the exact, FMA-free Moeller-Trumbore of rc_device.cuh, so t/u/v are bit-identical to the
-// reference evaluation whenever the same triangle wins.  The traversal stack lives in shared memory ([depth][thread],
-// conflict-free) with a local-memory overflow area, so pushes / pops never touch the L1 tag stage.
+// Arithmetic: two child planes are decoded per PRMT into a half2 (0x6400 | q = 1024 + q exactly), widened with
+// HADD2.F32 on the FMA pipe (no I2F: the XU pipe saturated in profiles/r1_v1; the ALU pipe is the limiter since v4),
+// and fed to one FMA against per-node (scale * inv_d, (origin - o) * inv_d - 1024 * scale * inv_d); an explicit
+// rounding bound keeps the slab test conservative.  The triangle test is the exact, FMA-free Moeller-Trumbore of
+// rc_device.cuh, so t/u/v are bit-identical to the reference evaluation whenever the same triangle wins.
+// The traversal stack lives in shared memory ([depth][thread], conflict-free); pushes are branch-free (a rejected
+// child is written to a dummy row); rays that would need more than RC_SSTACK entries are flagged and re-traced by
+// k_trace_fixup with the deep-stack generic body.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
@@ -41,35 +47,37 @@ __device__ __forceinline__ void rc_store_hit(rc_hit *hits, unsigned long long i,
 }
 
 #define RC_FETCH_MIN 12    // refill when at least this many lanes of the warp are idle (or nothing else can run)
-#define RC_SSTACK 32       // stack entries per lane (shared memory, [depth][thread])
+#define RC_SSTACK 32       // stack entries per lane (shared memory, [depth][thread]); row RC_SSTACK is the dummy row
 #define RC_OVERFLOW_MARK 0xFFFFFFFFu  // rc_hit.hit of a ray whose short stack overflowed (re-traced by k_trace_fixup)
 #define RC_DEADLANE 0xFFFFFFFDu
 
-#define RC_CE(ta, ra, tb, rb)                    \
-    {                                            \
-        bool sw_ = (tb) < (ta);                  \
-        float tl_ = sw_ ? (tb) : (ta);           \
-        float th_ = sw_ ? (ta) : (tb);           \
-        uint32_t rl_ = sw_ ? (rb) : (ra);        \
-        uint32_t rh_ = sw_ ? (ra) : (rb);        \
-        ta = tl_; tb = th_; ra = rl_; rb = rh_;  \
-    }
+#define RC_VOTE_N 0x00000001u
+#define RC_VOTE_T 0x00000100u
+#define RC_VOTE_X 0x00010000u
+#define RC_VOTE_F 0x01000000u
 
-// safe_invdir's clamp (src/instanced-bvh.jl:1742-1748) with MUFU.RCP (<= 1 ulp); only the conservative box test uses it,
-// and RC_BOX_EPS_FAST covers the extra ulp.
+// safe_invdir's clamp (src/instanced-bvh.jl:1742-1748) with MUFU.RCP (<= 1 ulp); only the conservative box test uses it
 __device__ __forceinline__ float rc_fast_inv(float d) {
     const float ooeps = 1.0e-5f;
     float x = fabsf(d) > ooeps ? d : copysignf(ooeps, d), r;
     asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-#define RC_BOX_EPS_FAST 4.8e-7f  // 2^-21
+// bound on the relative error of the slab evaluation: reciprocal (1 ulp), two roundings of (origin - o) * inv,
+// the 1024 * a bias folded into b (2^-14 of a cell), one FMA
+#define RC_BOX_EPS_FAST 7.2e-7f
+
+// bytes (2j, 2j+1) of w -> two floats 1024 + q (exact)
+__device__ __forceinline__ float2 rc_q2f_pair(uint32_t w, int j) {
+    const uint32_t h = __byte_perm(w, 0x64646464u, j == 0 ? 0x4140u : 0x4342u);
+    return __half22float2(*reinterpret_cast<const __half2 *>(&h));
+}
 
 template <bool ANY, bool COUNT>
 __global__ void __launch_bounds__(RC_TRACE_THREADS) k_trace_wide(RcScene sc, const rc_ray *__restrict__ rays, rc_hit *__restrict__ hits, unsigned long long n,
                                                                  unsigned long long *__restrict__ work, RcCounters *__restrict__ counters,
                                                                  uint32_t *__restrict__ overflow) {
-    __shared__ uint32_t sstack[RC_SSTACK * RC_TRACE_THREADS];
+    __shared__ uint32_t sstack[(RC_SSTACK + 1) * RC_TRACE_THREADS];
     const uint32_t FULL = 0xFFFFFFFFu;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, lt_mask = (1u << lane) - 1u;
     RcLocalCounters lc = {0, 0, 0, 0, 0};
@@ -80,39 +88,41 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS) k_trace_wide(RcScene sc, con
     uint32_t best_prim = 0, best_meta = 0;
     const RcTri *tris = nullptr;
     const RcNode4 *nodes = sc.tlas4;
-    uint32_t cur = RC_INVALID, leaf = 0, leaf_k = 0;
+    uint32_t cur = RC_INVALID, leaf = 0, leaf_k = 0, vote = RC_VOTE_F;
     bool have = false, ovf = false;
 
-    // The stack holds RC_SSTACK entries per lane.  A push beyond that is dropped and flags the ray; flagged rays are
-    // re-traced by k_trace_fixup with the deep-stack generic body, so results never depend on the short stack.
-#define RC_PUSH(v)                                                     \
-    {                                                                  \
-        if (sp < RC_SSTACK) sstack[sp * RC_TRACE_THREADS + tid] = (v); \
-        ovf |= sp >= RC_SSTACK;                                        \
-        sp++;                                                          \
+    // branch-free conditional push: a rejected (or overflowing) entry lands in the dummy row
+#define RC_PUSH_IF(cond, v)                                                             \
+    {                                                                                   \
+        const int row_ = (cond) ? min(sp, RC_SSTACK) : RC_SSTACK;                       \
+        sstack[row_ * RC_TRACE_THREADS + tid] = (v);                                    \
+        sp += (cond) ? 1 : 0;                                                           \
     }
-#define RC_TOP() (sstack[min(max(sp - 1, 0), RC_SSTACK - 1) * RC_TRACE_THREADS + tid])
+#define RC_TOP() (sstack[min(max(sp - 1, 0), RC_SSTACK) * RC_TRACE_THREADS + tid])
+    // after a step: park a freshly reached BLAS leaf (so the lane can keep descending) and recompute the lane's vote
+#define RC_SETTLE()                                                                                                       \
+    {                                                                                                                     \
+        if (sp > RC_SSTACK) { ovf = true; cur = RC_INVALID; leaf = 0; sp = 0; }                                           \
+        const bool park_ = cur_inst >= 0 && (cur & RC_LEAF_BIT) && cur < RC_DEADLANE && leaf == 0;                        \
+        const uint32_t top_ = RC_TOP();                                                                                   \
+        leaf = park_ ? cur : leaf;                                                                                        \
+        leaf_k = park_ ? 0u : leaf_k;                                                                                     \
+        cur = park_ ? top_ : cur;                                                                                         \
+        sp -= park_ ? 1 : 0;                                                                                              \
+        vote = (cur & RC_LEAF_BIT) ? 0u : RC_VOTE_N;                                                                      \
+        if (leaf) vote |= RC_VOTE_T;                                                                                      \
+        else if (cur == RC_INVALID) vote |= RC_VOTE_F;                                                                    \
+        if ((cur_inst < 0 && (cur & RC_LEAF_BIT) && cur < RC_DEADLANE) || (cur == RC_SENTINEL && leaf == 0)) vote |= RC_VOTE_X; \
+    }
 
     for (;;) {
-        // park a leaf (cheap, every iteration): a BLAS leaf reference with no leaf parked yet
-        {
-            const bool park = cur_inst >= 0 && (cur & RC_LEAF_BIT) && cur < RC_DEADLANE && leaf == 0;
-            const uint32_t top = RC_TOP();
-            leaf = park ? cur : leaf;
-            leaf_k = park ? 0u : leaf_k;
-            cur = park ? top : cur;
-            sp -= park ? 1 : 0;
-        }
-        const bool wantN = !(cur & RC_LEAF_BIT);
-        const bool wantT = leaf != 0;
-        const bool wantX = (cur_inst < 0 && (cur & RC_LEAF_BIT) && cur < RC_DEADLANE) || (cur == RC_SENTINEL && leaf == 0);
-        const bool wantF = cur == RC_INVALID && leaf == 0;
-        const uint32_t votes = __reduce_add_sync(FULL, (uint32_t)wantN | ((uint32_t)wantT << 8) | ((uint32_t)wantX << 16) | ((uint32_t)wantF << 24));
+        const uint32_t votes = __reduce_add_sync(FULL, vote);
         if (votes == 0) break;  // every lane is dead
         const uint32_t nN = votes & 0xFFu, nT = (votes >> 8) & 0xFFu, nX = (votes >> 16) & 0xFFu, nF = votes >> 24;
 
         if (nF > 0 && (nF >= RC_FETCH_MIN || (votes & 0x00FFFFFFu) == 0)) {
             // ---- F: retire + refill (warp-cooperative) -----------------------------------------------------------------
+            const bool wantF = vote & RC_VOTE_F;
             if (wantF && have) {
                 rc_hit h;
                 if (best_inst >= 0) {
@@ -134,6 +144,7 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS) k_trace_wide(RcScene sc, con
                 idx = base + (unsigned long long)__popc(mNeed & lt_mask);
                 if (idx >= n) {
                     cur = RC_DEADLANE;
+                    vote = 0;
                 } else {
                     rc_ray r = rc_load_ray(rays, idx);
                     RcRayIn w = rc_prepare_ray(r, ANY);
@@ -145,12 +156,14 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS) k_trace_wide(RcScene sc, con
                     sstack[tid] = RC_INVALID;
                     sp = 1;
                     cur = 1;
+                    leaf = 0;
+                    vote = RC_VOTE_N;
                     have = true;
                 }
             }
         } else if (nT >= nN && nT >= nX) {
             // ---- T: one triangle of the parked leaf per lane -------------------------------------------------------------
-            if (wantT) {
+            if (vote & RC_VOTE_T) {
                 const uint32_t start = leaf & RC_LEAF_START_MASK, count = ((leaf >> RC_LEAF_COUNT_SHIFT) & 7u) + 1u;
                 const float4 *tp = reinterpret_cast<const float4 *>(tris + start + leaf_k);
                 const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
@@ -165,10 +178,11 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS) k_trace_wide(RcScene sc, con
                     if (ANY) { cur = RC_INVALID; sp = 0; leaf_k = count; }
                 }
                 if (++leaf_k >= count) leaf = 0;
+                RC_SETTLE()
             }
         } else if (nX > nN) {
             // ---- X: enter an instance (TLAS leaf) or return to the TLAS (sentinel) -------------------------------------------
-            if (wantX) {
+            if (vote & RC_VOTE_X) {
                 if (cur == RC_SENTINEL) {
                     cur_inst = -1;  // src/instanced-bvh.jl:1996-2006
                     nodes = sc.tlas4;
@@ -193,59 +207,66 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS) k_trace_wide(RcScene sc, con
                     o = x_transform_point(m, wo);
                     d = x_transform_direction(m, wd);
                     inv = mk3(rc_fast_inv(d.x), rc_fast_inv(d.y), rc_fast_inv(d.z));
-                    RC_PUSH(RC_SENTINEL)
+                    RC_PUSH_IF(true, RC_SENTINEL)
                     if (COUNT) { lc.inst_entries++; if ((uint32_t)sp > lc.max_stack) lc.max_stack = (uint32_t)sp; }
                     cur = 1;
-                    if (ovf) { cur = RC_INVALID; leaf = 0; sp = 0; }
                 }
+                RC_SETTLE()
             }
         } else {
-            // ---- N: test the 4 quantised child boxes, descend into the nearest, push the rest far -> near -----------------
-            if (wantN) {
+            // ---- N: test the 4 quantised child boxes, descend into the nearest, push the other hit children -----------------
+            if (vote & RC_VOTE_N) {
                 const float4 *np = reinterpret_cast<const float4 *>(nodes + cur);
                 const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
                 if (COUNT) { lc.nodes++; lc.box_tests += 4; }
                 const uint32_t e = __float_as_uint(n0.w);
                 const float ax = __uint_as_float((e & 0xFFu) << 23) * inv.x, ay = __uint_as_float(((e >> 8) & 0xFFu) << 23) * inv.y,
                             az = __uint_as_float(((e >> 16) & 0xFFu) << 23) * inv.z;
-                const float bx = (n0.x - o.x) * inv.x, by = (n0.y - o.y) * inv.y, bz = (n0.z - o.z) * inv.z;
-                const float slack = RC_BOX_EPS_FAST * fmaxf(fmaxf(fmaf(255.0f, fabsf(ax), fabsf(bx)), fmaf(255.0f, fabsf(ay), fabsf(by))), fmaf(255.0f, fabsf(az), fabsf(bz)));
+                const float b0x = (n0.x - o.x) * inv.x, b0y = (n0.y - o.y) * inv.y, b0z = (n0.z - o.z) * inv.z;
+                const float slack = RC_BOX_EPS_FAST * fmaxf(fmaxf(fmaf(255.0f, fabsf(ax), fabsf(b0x)), fmaf(255.0f, fabsf(ay), fabsf(b0y))), fmaf(255.0f, fabsf(az), fabsf(b0z)));
+                const float bx = fmaf(-1024.0f, ax, b0x), by = fmaf(-1024.0f, ay, b0y), bz = fmaf(-1024.0f, az, b0z);  // decoded planes carry +1024
                 const uint32_t qlox = __float_as_uint(n1.x), qloy = __float_as_uint(n1.y), qloz = __float_as_uint(n1.z), qhix = __float_as_uint(n1.w);
                 const uint32_t qhiy = __float_as_uint(n2.x), qhiz = __float_as_uint(n2.y);
-                uint32_t r0 = __float_as_uint(n2.z), r1 = __float_as_uint(n2.w), r2 = __float_as_uint(n3.x), r3 = __float_as_uint(n3.y);
+                const uint32_t r0 = __float_as_uint(n2.z), r1 = __float_as_uint(n2.w), r2 = __float_as_uint(n3.x), r3 = __float_as_uint(n3.y);
                 const uint32_t nx = inv.x >= 0.0f ? qlox : qhix, fx = inv.x >= 0.0f ? qhix : qlox;
                 const uint32_t ny = inv.y >= 0.0f ? qloy : qhiy, fy = inv.y >= 0.0f ? qhiy : qloy;
                 const uint32_t nz = inv.z >= 0.0f ? qloz : qhiz, fz = inv.z >= 0.0f ? qhiz : qloz;
                 const float t_hi = t_max + slack;
                 float tn[4];
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    float lo = fmaxf(fmaxf(fmaf(rc_q2f(nx, k), ax, bx), fmaf(rc_q2f(ny, k), ay, by)), fmaxf(fmaf(rc_q2f(nz, k), az, bz), t_min));
-                    float hi = fminf(fminf(fmaf(rc_q2f(fx, k), ax, bx), fmaf(rc_q2f(fy, k), ay, by)), fmaf(rc_q2f(fz, k), az, bz));
-                    tn[k] = (lo <= fminf(hi + slack, t_hi)) ? lo : CUDART_INF_F;
+                for (int j = 0; j < 2; j++) {
+                    const float2 pnx = rc_q2f_pair(nx, j), pny = rc_q2f_pair(ny, j), pnz = rc_q2f_pair(nz, j);
+                    const float2 pfx = rc_q2f_pair(fx, j), pfy = rc_q2f_pair(fy, j), pfz = rc_q2f_pair(fz, j);
+                    const float lo0 = fmaxf(fmaxf(fmaf(pnx.x, ax, bx), fmaf(pny.x, ay, by)), fmaxf(fmaf(pnz.x, az, bz), t_min));
+                    const float hi0 = fminf(fminf(fmaf(pfx.x, ax, bx), fmaf(pfy.x, ay, by)), fmaf(pfz.x, az, bz));
+                    const float lo1 = fmaxf(fmaxf(fmaf(pnx.y, ax, bx), fmaf(pny.y, ay, by)), fmaxf(fmaf(pnz.y, az, bz), t_min));
+                    const float hi1 = fminf(fminf(fmaf(pfx.y, ax, bx), fmaf(pfy.y, ay, by)), fmaf(pfz.y, az, bz));
+                    tn[2 * j] = (lo0 <= fminf(hi0 + slack, t_hi)) ? lo0 : CUDART_INF_F;
+                    tn[2 * j + 1] = (lo1 <= fminf(hi1 + slack, t_hi)) ? lo1 : CUDART_INF_F;
                 }
                 // empty slots carry an inverted box (qlo = 255, qhi = 0) and could only pass through the slack: mask them
-                float t0 = r0 == RC_INVALID ? CUDART_INF_F : tn[0], t1 = r1 == RC_INVALID ? CUDART_INF_F : tn[1];
-                float t2 = r2 == RC_INVALID ? CUDART_INF_F : tn[2], t3 = r3 == RC_INVALID ? CUDART_INF_F : tn[3];
+                const float t0 = r0 == RC_INVALID ? CUDART_INF_F : tn[0], t1 = r1 == RC_INVALID ? CUDART_INF_F : tn[1];
+                const float t2 = r2 == RC_INVALID ? CUDART_INF_F : tn[2], t3 = r3 == RC_INVALID ? CUDART_INF_F : tn[3];
                 // the nearest hit child is entered next (exact argmin); the other hit children are pushed in slot order
                 const float tm = fminf(fminf(t0, t1), fminf(t2, t3));
                 const bool any_hit = tm < CUDART_INF_F;
                 const bool e0 = t0 == tm, e1 = !e0 && t1 == tm, e2 = !e0 && !e1 && t2 == tm, e3 = !e0 && !e1 && !e2;
-                if (t3 < CUDART_INF_F && !e3) RC_PUSH(r3)
-                if (t2 < CUDART_INF_F && !e2) RC_PUSH(r2)
-                if (t1 < CUDART_INF_F && !e1) RC_PUSH(r1)
-                if (t0 < CUDART_INF_F && !e0) RC_PUSH(r0)
+                RC_PUSH_IF(t3 < CUDART_INF_F && !e3, r3)
+                RC_PUSH_IF(t2 < CUDART_INF_F && !e2, r2)
+                RC_PUSH_IF(t1 < CUDART_INF_F && !e1, r1)
+                RC_PUSH_IF(t0 < CUDART_INF_F && !e0, r0)
                 if (COUNT && (uint32_t)sp > lc.max_stack) lc.max_stack = (uint32_t)sp;
                 const uint32_t top = RC_TOP();
                 const uint32_t rn = e0 ? r0 : (e1 ? r1 : (e2 ? r2 : r3));
                 cur = any_hit ? rn : top;
                 sp -= any_hit ? 0 : 1;
-                if (ovf) { cur = RC_INVALID; leaf = 0; sp = 0; }
+                RC_SETTLE()
             }
         }
     }
-#undef RC_PUSH
+#undef RC_PUSH_IF
 #undef RC_TOP
+#undef RC_SETTLE
     if (COUNT) {
         atomicAdd(&counters->rays, traced);
         atomicAdd(&counters->nodes, (unsigned long long)lc.nodes);
