@@ -1,0 +1,189 @@
+# RaycoreCUDA.jl — Julia shim binding libraycore_cuda.so (include/raycore_cuda.h) behind Raycore's own accel API.
+#
+# NOT EXECUTED IN THIS REPO'S CI: neither the build container nor the B200 boxes have Julia.  The shim is kept
+# deliberately thin (every method is one ccall plus bookkeeping that mirrors src/instanced-bvh.jl) so it can be
+# checked by inspection; every behaviour it relies on is exercised through the same C ABI by the Python mirror
+# (raycore.jl_b200/tlas.py) in tests/.  See INTEGRATION.md.
+#
+#   CuTLAS        <: Raycore.AbstractAccel          (src/Raycore.jl:14-49)   replaces Raycore.TLAS   (src/instanced-bvh.jl:261)
+#   CuStaticTLAS  <: Raycore.AbstractAdaptedAccel                            replaces Raycore.StaticTLAS (:155)
+module RaycoreCUDA
+
+using Raycore, GeometryBasics, StaticArrays, Adapt
+import Raycore: Mat3x4f, mat4_to_mat3x4, mat3x4_inverse, TLASHandle, RTRay, RTHitResult, Triangle, Bounds3,
+                closest_hit, any_hit, sync!, world_bound, n_instances, n_geometries, wait_for_gpu!, is_valid,
+                get_instance, get_instances, update_transform!, update_transforms!, update!, free!
+
+const lib = get(ENV, "RAYCORE_CUDA_LIB", "libraycore_cuda")
+
+const RC_RAYS_ON_DEVICE = UInt32(0x1); const RC_HITS_ON_DEVICE = UInt32(0x2); const RC_MODE_REFERENCE_ORDER = UInt32(0x4)
+
+struct RcError <: Exception; code::Int32; msg::String; end
+function check(ctx, rc::Int32)
+    rc == 0 && return nothing
+    msg = unsafe_string(ccall((:rc_last_error, lib), Cstring, (Ptr{Cvoid},), ctx))
+    # the reference raises ErrorException via error(...) for handle misuse (src/instanced-bvh.jl:715-718,756-759)
+    rc in (1, 2, 3, 4) ? error(msg) : throw(RcError(rc, msg))
+end
+
+mutable struct CuStaticTLAS{T} <: Raycore.AbstractAdaptedAccel
+    owner::Any          # the CuTLAS; identity of this object is kept across refits, replaced on rebuilds
+    generation::Int
+end
+
+mutable struct CuTLAS <: Raycore.AbstractAccel
+    ctx::Ptr{Cvoid}
+    meshes::Dict{UInt32, Vector}           # handle id => filtered-order Vector{Triangle} source (input order)
+    prim_to_face::Dict{UInt32, Vector{UInt32}}
+    static_tlas::Union{Nothing, CuStaticTLAS}
+    generation::Int
+    function CuTLAS(device::Integer = -1)
+        ref = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = ccall((:rc_create, lib), Int32, (Int32, Ref{Ptr{Cvoid}}), device, ref)
+        rc == 0 || error(unsafe_string(ccall((:rc_last_error, lib), Cstring, (Ptr{Cvoid},), C_NULL)))
+        t = new(ref[], Dict(), Dict(), nothing, 0)
+        finalizer(free!, t)                                    # finalizer(free!, tlas), src/instanced-bvh.jl:355
+        t
+    end
+end
+
+function free!(t::CuTLAS)
+    t.ctx == C_NULL && return nothing
+    ccall((:rc_destroy, lib), Int32, (Ptr{Cvoid},), t.ctx); t.ctx = C_NULL; nothing
+end
+
+# ---- decomposition identical to build_and_append_blas! (src/instanced-bvh.jl:581-600), minus the filter (done on the GPU)
+function soup(mesh::GeometryBasics.Mesh)
+    nmesh = GeometryBasics.expand_faceviews(mesh)
+    fs = decompose(TriangleFace{UInt32}, nmesh); verts = decompose(Point3f, nmesh)
+    v = Matrix{Float32}(undef, 9, length(fs))
+    for (i, f) in enumerate(fs), k in 1:3, c in 1:3
+        v[3 * (k - 1) + c, i] = verts[f[k]][c]
+    end
+    meta = hasproperty(nmesh, :face_meta) ? UInt32[nmesh.face_meta[f[1]] for f in fs] : nothing
+    return v, meta, nmesh
+end
+
+function Base.push!(t::CuTLAS, mesh::GeometryBasics.Mesh, transforms::AbstractVector{Mat4f};
+                    instance_ids::Union{Nothing, AbstractVector{<:Integer}} = nothing, sbt_offset::UInt32 = UInt32(0))
+    instance_ids !== nothing && length(instance_ids) != length(transforms) &&
+        throw(ArgumentError("instance_ids length $(length(instance_ids)) != transforms length $(length(transforms))"))
+    v, meta, nmesh = soup(mesh)
+    xf = [mat4_to_mat3x4(m) for m in transforms]
+    inv = [mat3x4_inverse(m) for m in xf]          # computed with Raycore's own code => bit-identical descriptors
+    ids = instance_ids === nothing ? C_NULL : UInt32.(instance_ids)
+    h = Ref{UInt32}(0)
+    check(t.ctx, ccall((:rc_push, lib), Int32,
+        (Ptr{Cvoid}, Ptr{Float32}, UInt32, Ptr{UInt32}, Ptr{Float32}, Ptr{Float32}, Ptr{UInt32}, UInt32, UInt32, Ref{UInt32}),
+        t.ctx, v, size(v, 2), meta === nothing ? C_NULL : meta, reinterpret(Float32, xf), reinterpret(Float32, inv), ids,
+        length(xf), 0, h))
+    t.meshes[h[]] = [nmesh]
+    return TLASHandle(h[])
+end
+Base.push!(t::CuTLAS, mesh::GeometryBasics.Mesh, transform::Mat4f = Mat4f(I); instance_id::UInt32 = UInt32(0), sbt_offset::UInt32 = UInt32(0)) =
+    push!(t, mesh, [transform]; instance_ids = [instance_id])
+
+function Base.delete!(t::CuTLAS, h::TLASHandle)::Bool
+    d = Ref{Int32}(0); check(t.ctx, ccall((:rc_delete, lib), Int32, (Ptr{Cvoid}, UInt32, Ref{Int32}), t.ctx, h.id, d)); d[] != 0
+end
+
+function update_transforms!(t::CuTLAS, h::TLASHandle, transforms::AbstractVector{Mat3x4f})
+    inv = [mat3x4_inverse(m) for m in transforms]
+    check(t.ctx, ccall((:rc_update_transforms, lib), Int32, (Ptr{Cvoid}, UInt32, Ptr{Float32}, Ptr{Float32}, UInt32),
+        t.ctx, h.id, reinterpret(Float32, collect(transforms)), reinterpret(Float32, inv), length(transforms)))
+end
+update_transforms!(t::CuTLAS, h::TLASHandle, ts::AbstractVector{Mat4f}) = update_transforms!(t, h, map(mat4_to_mat3x4, ts))
+function update_transform!(t::CuTLAS, h::TLASHandle, m::Union{Mat4f, Mat3x4f})
+    n = ccall((:rc_n_instances_of, lib), UInt32, (Ptr{Cvoid}, UInt32), t.ctx, h.id)
+    is_valid(t, h) && n != 1 && error("Handle has $n instances, use update_transforms! for multiple")
+    update_transforms!(t, h, [m isa Mat4f ? mat4_to_mat3x4(m) : m])
+end
+function update!(t::CuTLAS, h::TLASHandle, mesh)
+    v, meta, nmesh = soup(mesh)
+    check(t.ctx, ccall((:rc_update_geometry, lib), Int32, (Ptr{Cvoid}, UInt32, Ptr{Float32}, UInt32, Ptr{UInt32}, UInt32),
+        t.ctx, h.id, v, size(v, 2), meta === nothing ? C_NULL : meta, 0))
+    t.meshes[h.id] = [nmesh]; nothing
+end
+
+function sync!(t::CuTLAS)
+    a = Ref{Int32}(0); check(t.ctx, ccall((:rc_sync, lib), Int32, (Ptr{Cvoid}, Ref{Int32}), t.ctx, a))
+    if a[] == 2 || t.static_tlas === nothing           # rebuild => new adapted object; refit keeps identity (test_mesh_update.jl:214)
+        t.generation += 1; t.static_tlas = CuStaticTLAS{Triangle{UInt32}}(t, t.generation); empty!(t.prim_to_face)
+    end
+    return t
+end
+Adapt.adapt_structure(to, t::CuTLAS) = (sync!(t); t.static_tlas)          # src/instanced-bvh.jl:1085-1102
+
+is_valid(t::CuTLAS, h::TLASHandle) = ccall((:rc_is_valid, lib), Int32, (Ptr{Cvoid}, UInt32), t.ctx, h.id) != 0
+n_instances(t::CuTLAS) = Int(ccall((:rc_n_instances, lib), UInt32, (Ptr{Cvoid},), t.ctx))
+n_instances(t::CuTLAS, h::TLASHandle) = Int(ccall((:rc_n_instances_of, lib), UInt32, (Ptr{Cvoid}, UInt32), t.ctx, h.id))
+n_geometries(t::CuTLAS) = Int(ccall((:rc_n_geometries, lib), UInt32, (Ptr{Cvoid},), t.ctx))
+function world_bound(t::CuTLAS)
+    b = Vector{Float32}(undef, 6); check(t.ctx, ccall((:rc_world_bound, lib), Int32, (Ptr{Cvoid}, Ptr{Float32}), t.ctx, b))
+    Bounds3(Point3f(b[1:3]...), Point3f(b[4:6]...))
+end
+wait_for_gpu!(t::CuTLAS) = (check(t.ctx, ccall((:rc_wait, lib), Int32, (Ptr{Cvoid},), t.ctx)); t)
+function get_instances(t::CuTLAS, h::TLASHandle)
+    out = Vector{Raycore.InstanceDescriptor}(undef, max(1, n_instances(t, h)))
+    check(t.ctx, ccall((:rc_get_instances, lib), Int32, (Ptr{Cvoid}, UInt32, Ptr{Cvoid}), t.ctx, h.id, out)); out
+end
+get_instance(t::CuTLAS, h::TLASHandle, i::Integer = 1) = get_instances(t, h)[i]
+
+# ---- queries -------------------------------------------------------------------------------------------------------
+"Batched entry, same shape as Lava.trace_closest_hits!(hits, rays, accel, n) (docs/src/hw_acceleration.md:143-146)."
+function trace_closest_hits!(hits::Vector{RTHitResult}, rays::Vector{RTRay}, s::CuStaticTLAS, n::Integer = length(rays); any = false, flags = UInt32(0))
+    s.owner.static_tlas === s || error("stale CuStaticTLAS: re-adapt per dispatch (src/instanced-bvh.jl:221-226)")
+    f = any ? :rc_trace_any : :rc_trace_closest
+    check(s.owner.ctx, ccall((f, lib), Int32, (Ptr{Cvoid}, Ptr{RTRay}, Ptr{RTHitResult}, UInt64, UInt32), s.owner.ctx, rays, hits, n, flags))
+    hits
+end
+Raycore.trace_rays(s::CuStaticTLAS, rays::AbstractVector{<:Raycore.AbstractRay}) =
+    trace_closest_hits!(Vector{RTHitResult}(undef, length(rays)), [RTRay(r.o..., r.t_min, r.d..., r.t_max) for r in rays], s)
+
+function hit_tuple(s::CuStaticTLAS, h::RTHitResult, tri_of)
+    h.hit == 0 && return (false, Raycore.empty_triangle(Triangle{UInt32}), 0f0, SVector{3, Float32}(0, 0, 0), UInt32(0))   # :2019-2022
+    w = 1f0 - h.bary_u - h.bary_v
+    (true, tri_of(h), h.t, SVector{3, Float32}(w, h.bary_u, h.bary_v), h.instance_id + UInt32(1))                              # :2010-2017
+end
+# Per-ray methods: host-side convenience (n = 1 batch).  Device-side per-ray calls from user KA kernels are replaced by the
+# batched entry above — the library owns traversal; see INTEGRATION.md "What changes for callers".
+closest_hit(s::CuStaticTLAS, ray::Raycore.AbstractRay) =
+    hit_tuple(s, trace_closest_hits!([RTHitResult(0, 0, 0, 0, 0, 0, 0, 0)], [RTRay(ray.o..., ray.t_min, ray.d..., ray.t_max)], s)[1], h -> triangle_of(s.owner, h))
+any_hit(s::CuStaticTLAS, ray::Raycore.AbstractRay) =
+    hit_tuple(s, trace_closest_hits!([RTHitResult(0, 0, 0, 0, 0, 0, 0, 0)], [RTRay(ray.o..., 0f0, ray.d..., ray.t_max)], s; any = true)[1], h -> triangle_of(s.owner, h))
+
+"Materialise Raycore's Triangle (vertices, normals, uv, metadata) for a hit from the caller-side copy of the mesh (rc_read_blas_faces)."
+function triangle_of(t::CuTLAS, h::RTHitResult)
+    handles = Vector{UInt32}(undef, ccall((:rc_n_total_instances, lib), UInt32, (Ptr{Cvoid},), t.ctx))
+    ccall((:rc_get_instance_handles, lib), Int32, (Ptr{Cvoid}, Ptr{UInt32}, UInt32), t.ctx, handles, length(handles))
+    hid = handles[h.instance_id + 1]
+    nmesh = t.meshes[hid][1]
+    blas = get_instances(t, TLASHandle(hid))[1].blas_index
+    faces = get!(t.prim_to_face, blas) do
+        n = ccall((:rc_blas_n_prims, lib), UInt32, (Ptr{Cvoid}, UInt32), t.ctx, blas); out = Vector{UInt32}(undef, n)
+        ccall((:rc_read_blas_faces, lib), Int32, (Ptr{Cvoid}, UInt32, Ptr{UInt32}, UInt32), t.ctx, blas, out, n); out
+    end
+    face = faces[h.primitive_id + 1] + 1
+    fs = decompose(TriangleFace{UInt32}, nmesh); verts = decompose(Point3f, nmesh); norms = Raycore.Normal3f.(decompose_normals(nmesh))
+    uvs_raw = GeometryBasics.decompose_uv(nmesh); uvs = isnothing(uvs_raw) ? Point2f[] : Point2f.(uvs_raw)
+    Raycore.build_triangle(verts, norms, uvs, collect(reinterpret(UInt32, fs)), face, h._pad2)      # _pad2 carries Triangle.metadata
+end
+
+# ---- analysis (src/kernels.jl) -----------------------------------------------------------------------------------------
+function Raycore.get_illumination(t::CuTLAS, viewdir; grid_size = 1000)
+    sync!(t); n = Ref{UInt32}(0); ccall((:rc_sizes, lib), Int32, (Ptr{Cvoid}, Ptr{UInt32}, Ptr{UInt32}, Ref{UInt32}, Ptr{UInt32}), t.ctx, C_NULL, C_NULL, n, C_NULL)
+    out = zeros(Float32, n[]); check(t.ctx, ccall((:rc_get_illumination, lib), Int32, (Ptr{Cvoid}, Ptr{Float32}, UInt32, Ptr{Float32}, UInt32), t.ctx, Float32[viewdir...], grid_size, out, n[])); out
+end
+function Raycore.get_centroid(t::CuTLAS, viewdir; grid_size = 32)
+    sync!(t); c = zeros(Float32, 3); nh = Ref{UInt32}(0); pts = Matrix{Float32}(undef, 3, grid_size^2)
+    check(t.ctx, ccall((:rc_get_centroid, lib), Int32, (Ptr{Cvoid}, Ptr{Float32}, UInt32, Ptr{Float32}, Ref{UInt32}, Ptr{Float32}), t.ctx, Float32[viewdir...], grid_size, c, nh, pts))
+    [Point3f(pts[:, i]...) for i in 1:nh[]], Point3f(c...)
+end
+function Raycore.view_factors(t::CuTLAS; rays_per_triangle = 10000, seed = 0)
+    sync!(t); n = Ref{UInt32}(0); ccall((:rc_sizes, lib), Int32, (Ptr{Cvoid}, Ptr{UInt32}, Ptr{UInt32}, Ref{UInt32}, Ptr{UInt32}), t.ctx, C_NULL, C_NULL, n, C_NULL)
+    out = zeros(UInt32, n[], n[]); sk = Ref{UInt64}(0)   # C side is row-major [src][hit] = Julia's transpose
+    check(t.ctx, ccall((:rc_view_factors, lib), Int32, (Ptr{Cvoid}, UInt32, UInt64, Ptr{UInt32}, UInt32, UInt32, UInt32, Ref{UInt64}), t.ctx, rays_per_triangle, seed, out, 0, n[], 0, sk))
+    permutedims(out)                                       # result[src_meta, hit_meta]
+end
+
+end # module
