@@ -1,0 +1,67 @@
+"""Multi-GPU plumbing: one process per GPU, BVH replicated, rays / view-factor rows sharded, results
+gathered with torch.distributed (NCCL over NVLink on GPUs; gloo in the CPU tests).  The data path itself needs no
+collective — every rank traces its own contiguous block."""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous block [lo, hi) of `n` units owned by `rank`: [r*n/G, (r+1)*n/G)."""
+    return (rank * n) // world, ((rank + 1) * n) // world
+
+
+def shard_sizes(n: int, world: int) -> List[int]:
+    return [shard_range(n, r, world)[1] - shard_range(n, r, world)[0] for r in range(world)]
+
+
+def gather_records(local: torch.Tensor, total_units: int, unit_bytes: int, dst: int = 0) -> Optional[torch.Tensor]:
+    """Gather per-rank blocks of fixed-size records (uint8 tensors of shard_size*unit_bytes) to `dst`, in rank order.
+    Uneven shards are padded to the largest block for the collective and trimmed on arrival."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    sizes = shard_sizes(total_units, world)
+    assert local.dtype == torch.uint8 and local.numel() == sizes[rank] * unit_bytes
+    mx = max(sizes) * unit_bytes
+    buf = local
+    if local.numel() != mx:
+        buf = torch.zeros(mx, dtype=torch.uint8, device=local.device)
+        buf[: local.numel()] = local
+    out = [torch.empty(mx, dtype=torch.uint8, device=local.device) for _ in range(world)] if rank == dst else None
+    dist.gather(buf, out, dst=dst)
+    if rank != dst:
+        return None
+    return torch.cat([o[: s * unit_bytes] for o, s in zip(out, sizes)])
+
+
+def trace_sharded(trace_fn, rays: np.ndarray, record_dtype: np.dtype, device: Optional[torch.device] = None, dst: int = 0):
+    """Every rank holds the same `rays`; rank r traces rays[lo:hi] with `trace_fn` and the hit records are gathered to dst.
+    Returns the full hit array on dst, None elsewhere."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    lo, hi = shard_range(len(rays), rank, world)
+    hits = np.ascontiguousarray(trace_fn(rays[lo:hi]))
+    t = torch.from_numpy(hits.view(np.uint8).reshape(-1).copy())
+    if device is not None:
+        t = t.to(device)
+    full = gather_records(t, len(rays), record_dtype.itemsize, dst)
+    if full is None:
+        return None
+    return full.cpu().numpy().view(record_dtype)
+
+
+def view_factor_rows_sharded(vf_fn, n_prims: int, device: Optional[torch.device] = None, dst: int = 0):
+    """Rank r computes the row block [lo, hi) of the view-factor matrix with vf_fn(row_base, n_rows) -> uint32[n_rows, n_prims];
+    blocks are gathered to dst (rows in order)."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    lo, hi = shard_range(n_prims, rank, world)
+    block = np.ascontiguousarray(vf_fn(lo, hi - lo), dtype=np.uint32)
+    t = torch.from_numpy(block.view(np.uint8).reshape(-1).copy())
+    if device is not None:
+        t = t.to(device)
+    full = gather_records(t, n_prims, 4 * n_prims, dst)
+    if full is None:
+        return None
+    return full.cpu().numpy().view(np.uint32).reshape(n_prims, n_prims)
