@@ -148,6 +148,7 @@ def main():
     ap.add_argument("--rays", type=int, default=RAYS_PER_RANK)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"], help="N > 1: how hit records reach rank 0")
     ap.add_argument("--counters", action="store_true", help="extra instrumented pass (per-ray node/triangle counts) after the timed region")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -198,7 +199,34 @@ def main():
     rays, primary_hit_rate = build_rays(lambda r: tlas.trace_closest(r), verts, faces, n, seed=rank)
     d_rays = torch.from_numpy(rays.view(np.uint8).reshape(-1)).to(dev)
     d_hits = torch.empty(n * 32, dtype=torch.uint8, device=dev)
-    gather_buf = [torch.empty_like(d_hits) for _ in range(world)] if (world > 1 and rank == 0) else None
+    # ---- result gather for N > 1 --------------------------------------------------------------------------------
+    # fused (default): rank 0 owns one world*n*32-byte buffer, exports it over CUDA IPC, and every rank's traversal kernel
+    # stores its hit records straight into its slice of that buffer through the NVLink peer mapping — the "gather" is the
+    # kernel's own epilogue, there is no separate collective.  nccl (fallback / --gather nccl): dist.gather after the trace.
+    gather_mode, gather_buf, hits_ptr, g_base = "none (1 GPU)", None, d_hits.data_ptr(), C.c_void_p()
+    if world > 1:
+        gather_mode = "nccl"
+        if args.gather == "fused":
+            try:
+                handle = (C.c_uint8 * 64)()
+                if rank == 0:
+                    assert lib.rc_device_alloc(ctx, world * n * 32, C.byref(g_base)) == 0
+                    assert lib.rc_ipc_export(ctx, g_base, handle) == 0
+                obj = [bytes(handle)]
+                dist.broadcast_object_list(obj, src=0)
+                ok = 1
+                if rank != 0:
+                    hb = (C.c_uint8 * 64).from_buffer_copy(obj[0])
+                    ok = int(lib.rc_ipc_open(ctx, hb, C.byref(g_base)) == 0)
+                t = torch.tensor([ok], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                if int(t.item()) == 1:
+                    gather_mode = "fused"
+                    hits_ptr = g_base.value + rank * n * 32
+            except Exception as e:  # pragma: no cover
+                print(f"[rank {rank}] fused gather unavailable ({e}); falling back to NCCL gather", file=sys.stderr)
+        if gather_mode == "nccl" and rank == 0:
+            gather_buf = [torch.empty_like(d_hits) for _ in range(world)]
     # all library work on torch's current stream so torch.cuda.Event brackets it
     stream = torch.cuda.Stream(dev)  # a real (non-default) stream: handle 0 would mean "private stream" to rc_set_stream
     torch.cuda.set_stream(stream)
@@ -206,9 +234,9 @@ def main():
     flags = L.RC_RAYS_ON_DEVICE | L.RC_HITS_ON_DEVICE | L.RC_NO_SYNC
 
     def step():
-        rc_ = lib.rc_trace_closest(ctx, d_rays.data_ptr(), d_hits.data_ptr(), n, flags)
+        rc_ = lib.rc_trace_closest(ctx, d_rays.data_ptr(), hits_ptr, n, flags)
         assert rc_ == 0, lib.rc_last_error(ctx)
-        if world > 1:
+        if gather_mode == "nccl":
             dist.gather(d_hits, gather_buf, dst=0)  # results gathered by NCCL over NVLink
 
     def barrier():
@@ -234,6 +262,20 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     assert lib.rc_wait(ctx) == 0
+    if world > 1:
+        # check what rank 0 received: per-rank hit counts of the gathered blocks == the counts each rank measures locally
+        assert lib.rc_trace_closest(ctx, d_rays.data_ptr(), d_hits.data_ptr(), n, L.RC_RAYS_ON_DEVICE | L.RC_HITS_ON_DEVICE) == 0
+        local_hits = int(d_hits.view(torch.int32).view(-1, 8)[:, 0].sum().item())
+        counts = [None] * world
+        dist.all_gather_object(counts, local_hits)
+        if rank == 0:
+            if gather_mode == "fused":
+                host = np.empty(world * n * 32, np.uint8)
+                assert lib.rc_memcpy_d2h(ctx, host.ctypes.data, g_base, host.nbytes) == 0
+                got = [int(host.view(np.uint32).reshape(-1, 8)[r * n:(r + 1) * n, 0].sum()) for r in range(world)]
+            else:
+                got = [int(b.view(torch.int32).view(-1, 8)[:, 0].sum().item()) for b in gather_buf]
+            assert got == counts, (got, counts)
     ms_step = ms_total / args.steps
     value = world * n * args.steps / (ms_total * 1e-3) / 1e6
 
@@ -326,7 +368,7 @@ def main():
         "config": {
             "workload": f"C2: bumpy_sphere({TESS}) {len(verts)} faces -> {n_tris} triangles, 1 instance TLAS; per rank 2^{int(np.log2(n))} rays = diffuse-bounce (hemisphere about the geometric normal, from {PRIMARY_RES}^2 primary hits) interleaved with interior-origin uniform-direction rays",
             "rays_per_rank": n, "hit_rate": hit_rate, "primary_hit_rate": primary_hit_rate, "l2_policy": "inputs larger than L2 (512 MiB rays + 512 MiB hits per step)",
-            "gather": "dist.gather of hit records to rank 0 (NCCL) inside every step" if world > 1 else "none (1 GPU)", "parallelism": f"bvh replicated, rays sharded x{world}",
+            "gather": {"fused": "fused: each rank's traversal kernel stores its hit records straight into rank 0's buffer through CUDA-IPC peer pointers over NVLink (no separate collective)", "nccl": "dist.gather of hit records to rank 0 (NCCL) after every trace"}.get(gather_mode, gather_mode), "parallelism": f"bvh replicated, rays sharded x{world}",
         },
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps * 1, "clocks": clk.summary(),
         "build": {"blas_build_ms_device_input": min(build_ms), "push_sync_ms_host_input": build_wall_ms, "triangles": n_tris},
