@@ -170,6 +170,8 @@ int32_t rc_get_counters(rc_context *ctx, uint64_t out[6], int32_t reset);
 /* milliseconds of the last trace's kernel(s), measured with CUDA events on the context stream */
 float rc_last_kernel_ms(const rc_context *ctx);
 uint32_t rc_last_kernel_launches(const rc_context *ctx);
+/* milliseconds of the last BLAS build (rc_push / rc_update_geometry), CUDA events on the context stream, upload excluded */
+float rc_last_build_ms(const rc_context *ctx);
 
 /* ---- analysis (src/kernels.jl) --------------------------------------------------------- */
 /* hits_from_grid(tlas, viewdir; grid_size) — :58-72 with generate_ray_grid :10-56.

@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libraycore_cuda.so")
+LIB_PATH = os.environ.get("RAYCORE_CUDA_LIB") or os.path.join(_HERE, "libraycore_cuda.so")
 
 RC_OK = 0
 RC_ERR_INVALID_ARGUMENT = 1
@@ -68,7 +68,7 @@ EXPORTS = [
     "rc_is_valid", "rc_n_instances", "rc_n_instances_of", "rc_n_total_instances", "rc_n_geometries", "rc_is_dirty",
     "rc_get_instances", "rc_world_bound", "rc_wait", "rc_sizes", "rc_read_tlas_nodes", "rc_read_blas_nodes",
     "rc_read_blas_order", "rc_blas_n_prims", "rc_read_blas_faces", "rc_get_instance_handles",
-    "rc_trace_closest", "rc_trace_any", "rc_get_counters", "rc_last_kernel_ms", "rc_last_kernel_launches",
+    "rc_trace_closest", "rc_trace_any", "rc_get_counters", "rc_last_kernel_ms", "rc_last_kernel_launches", "rc_last_build_ms",
     "rc_hits_from_grid", "rc_get_illumination", "rc_get_centroid", "rc_view_factors", "rc_view_factor_rays", "rc_read_flat_metadata",
     "rc_device_alloc", "rc_device_free", "rc_host_alloc", "rc_host_free", "rc_memcpy_h2d", "rc_memcpy_d2h",
     "rc_ipc_export", "rc_ipc_open", "rc_ipc_close",
@@ -132,6 +132,7 @@ def load():
         "rc_get_counters": (i32, [vp, vp, i32]),
         "rc_last_kernel_ms": (C.c_float, [vp]),
         "rc_last_kernel_launches": (u32, [vp]),
+        "rc_last_build_ms": (C.c_float, [vp]),
         "rc_hits_from_grid": (i32, [vp, vp, u32, vp, vp]),
         "rc_get_illumination": (i32, [vp, vp, u32, vp, u32]),
         "rc_get_centroid": (i32, [vp, vp, u32, vp, pu32, vp]),

@@ -46,7 +46,7 @@ struct rc_context {
     size_t cap_rays = 0, cap_hits = 0;
     static const int NEV = 8;
     cudaEvent_t ev_h2d[NEV], ev_k[NEV], ev_t0 = nullptr, ev_t1 = nullptr;
-    float last_ms = 0.f;
+    float last_ms = 0.f, last_build_ms = 0.f;
     uint32_t last_launches = 0;
     int max_blocks = 148;
 };
@@ -191,7 +191,10 @@ static int32_t build_blas_from(rc_context *ctx, const float *verts, uint32_t n_f
         }
     }
     std::string err;
+    cudaEventRecord(ctx->ev_t0, ctx->stream);
     bool ok = rc_build_blas(ctx->stream, d_verts, d_meta, n_faces, out, err);
+    cudaEventRecord(ctx->ev_t1, ctx->stream);
+    if (ok && cudaEventSynchronize(ctx->ev_t1) == cudaSuccess) cudaEventElapsedTime(&ctx->last_build_ms, ctx->ev_t0, ctx->ev_t1);
     if (tmp_v) cudaFreeAsync(tmp_v, ctx->stream);
     if (tmp_m) cudaFreeAsync(tmp_m, ctx->stream);
     if (!ok) {
@@ -594,6 +597,7 @@ int32_t rc_get_counters(rc_context *ctx, uint64_t out[6], int32_t reset) {
     return RC_OK;
 }
 float rc_last_kernel_ms(const rc_context *ctx) { return ctx ? ctx->last_ms : 0.f; }
+float rc_last_build_ms(const rc_context *ctx) { return ctx ? ctx->last_build_ms : 0.f; }
 uint32_t rc_last_kernel_launches(const rc_context *ctx) { return ctx ? ctx->last_launches : 0; }
 
 // ------------------------------------------------------------------------------------------------ analysis

@@ -194,6 +194,38 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const uint32_t *__
     }
 }
 
+// Exclusive scan of the digit-major table hist[256][tiles] in place (one block, 32 warps; warp w owns digits w, w+32, ...):
+// coalesced row scans with a carried prefix, then the 256 row totals are scanned and added back.
+__global__ void __launch_bounds__(1024) k_scan_hist(uint32_t *__restrict__ hist, uint32_t tiles) {
+    __shared__ uint32_t tot[256];
+    __shared__ uint32_t sm[33];
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint32_t d = wid; d < 256; d += 32) {
+        uint32_t *row = hist + (size_t)d * tiles;
+        uint32_t carry = 0;
+        for (uint32_t i0 = 0; i0 < tiles; i0 += 32) {
+            uint32_t i = i0 + lane;
+            uint32_t v = i < tiles ? row[i] : 0;
+            uint32_t inc = warp_incl_scan(v);
+            if (i < tiles) row[i] = carry + inc - v;
+            carry += __shfl_sync(0xFFFFFFFFu, inc, 31);
+        }
+        if (lane == 0) tot[d] = carry;
+    }
+    __syncthreads();
+    uint32_t total;
+    uint32_t mine = threadIdx.x < 256 ? tot[threadIdx.x] : 0;
+    uint32_t base = block_excl_scan(mine, sm, total);
+    if (threadIdx.x < 256) tot[threadIdx.x] = base;
+    __syncthreads();
+    for (uint32_t d = wid; d < 256; d += 32) {
+        uint32_t *row = hist + (size_t)d * tiles;
+        const uint32_t b = tot[d];
+        if (b)
+            for (uint32_t i = lane; i < tiles; i += 32) row[i] += b;
+    }
+}
+
 // sorts in place: on return keys/vals hold the sorted pairs (4 passes ping-pong through tmp buffers)
 static void radix_sort_pairs(cudaStream_t st, uint32_t *keys, uint32_t *vals, uint32_t *keys_tmp, uint32_t *vals_tmp, uint32_t n, uint32_t *hist /* 256*tiles */) {
     uint32_t tiles = cdiv(n, RS_TILE);
@@ -201,7 +233,7 @@ static void radix_sort_pairs(cudaStream_t st, uint32_t *keys, uint32_t *vals, ui
     for (int pass = 0; pass < 4; pass++) {
         int shift = pass * 8;
         k_radix_hist<<<tiles, RS_THREADS, 0, st>>>(ki, n, shift, tiles, hist);
-        k_scan_single<<<1, 1024, 0, st>>>(hist, 256u * tiles, nullptr);
+        k_scan_hist<<<1, 1024, 0, st>>>(hist, tiles);
         k_radix_scatter<<<tiles, RS_THREADS, 0, st>>>(ki, vi, ko, vo, n, shift, tiles, hist);
         std::swap(ki, ko);
         std::swap(vi, vo);
@@ -221,15 +253,27 @@ __global__ void k_face_flags(const float *__restrict__ verts, uint32_t n_faces, 
 }
 
 __device__ __forceinline__ void bounds_atomic(uint32_t *bounds, f3 lo, f3 hi) {
-    // warp reduce in ordered-uint space, one atomic per warp per component
+    // warp reduce (REDUX) then block reduce in ordered-uint space: 6 atomics per block (per-warp atomics on one 32-B sector
+    // serialised in L2: 134 us for 1 M triangles in profiles/r1_launches_v6)
+    __shared__ uint32_t part[6][32];
     uint32_t v[6] = {rc_float_to_ordered(lo.x), rc_float_to_ordered(lo.y), rc_float_to_ordered(lo.z),
                      rc_float_to_ordered(hi.x), rc_float_to_ordered(hi.y), rc_float_to_ordered(hi.z)};
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
 #pragma unroll
     for (int c = 0; c < 6; c++) {
         uint32_t r = c < 3 ? __reduce_min_sync(0xFFFFFFFFu, v[c]) : __reduce_max_sync(0xFFFFFFFFu, v[c]);
-        if ((threadIdx.x & 31) == 0) {
-            if (c < 3) atomicMin(&bounds[c], r);
-            else atomicMax(&bounds[c], r);
+        if (lane == 0) part[c][wid] = r;
+    }
+    __syncthreads();
+    if (wid == 0) {
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+            uint32_t x = lane < nw ? part[c][lane] : (c < 3 ? 0xFFFFFFFFu : 0u);
+            uint32_t r = c < 3 ? __reduce_min_sync(0xFFFFFFFFu, x) : __reduce_max_sync(0xFFFFFFFFu, x);
+            if (lane == 0) {
+                if (c < 3) atomicMin(&bounds[c], r);
+                else atomicMax(&bounds[c], r);
+            }
         }
     }
 }

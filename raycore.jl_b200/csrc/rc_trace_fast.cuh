@@ -67,6 +67,14 @@ __device__ __forceinline__ float rc_fast_inv(float d) {
 // the 1024 * a bias folded into b (2^-14 of a cell), one FMA
 #define RC_BOX_EPS_FAST 7.2e-7f
 
+// 32-byte read-only load (LDG.E.256.CONSTANT on sm_100a): a 64-B wide node is two of these instead of four LDG.128,
+// halving the L1 wavefronts per node step (LSU wavefronts were 70 % of peak in profiles/r1_v6)
+__device__ __forceinline__ void rc_ldg256(const void *p, float4 &a, float4 &b) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
+}
+
 // bytes (2j, 2j+1) of w -> two floats 1024 + q (exact)
 __device__ __forceinline__ float2 rc_q2f_pair(uint32_t w, int j) {
     const uint32_t h = __byte_perm(w, 0x64646464u, j == 0 ? 0x4140u : 0x4342u);
@@ -216,8 +224,10 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS) k_trace_wide(RcScene sc, con
         } else {
             // ---- N: test the 4 quantised child boxes, descend into the nearest, push the other hit children -----------------
             if (vote & RC_VOTE_N) {
-                const float4 *np = reinterpret_cast<const float4 *>(nodes + cur);
-                const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
+                const char *np = reinterpret_cast<const char *>(nodes + cur);
+                float4 n0, n1, n2, n3;
+                rc_ldg256(np, n0, n1);
+                rc_ldg256(np + 32, n2, n3);
                 if (COUNT) { lc.nodes++; lc.box_tests += 4; }
                 const uint32_t e = __float_as_uint(n0.w);
                 const float ax = __uint_as_float((e & 0xFFu) << 23) * inv.x, ay = __uint_as_float(((e >> 8) & 0xFFu) << 23) * inv.y,

@@ -12,7 +12,9 @@
 #define RC_LEAF_BIT 0x80000000u      // wide-node child reference: leaf flag
 #define RC_LEAF_COUNT_SHIFT 28       // bits 30..28: triangle count - 1
 #define RC_LEAF_START_MASK 0x0FFFFFFFu
-#define RC_BLAS_LEAF_MAX 4           // triangles per wide-BVH leaf (<= 8)
+#ifndef RC_BLAS_LEAF_MAX
+#define RC_BLAS_LEAF_MAX 2           // triangles per wide-BVH leaf (<= 8); 2 measured best on C2 (profiles/r1_leafmax.md)
+#endif
 
 // BVH2 node in the reference's field order (BVHNode2, src/instanced-bvh.jl:50-63) padded 60 -> 64 B.
 // Child / parent / primitive indices keep the reference's 1-based values.
