@@ -6,7 +6,9 @@
 
 #include "rc_types.h"
 
+#ifndef RC_TRACE_THREADS
 #define RC_TRACE_THREADS 128
+#endif
 
 struct RcTraceLaunch {
     RcScene scene;

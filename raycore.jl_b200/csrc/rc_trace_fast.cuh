@@ -46,7 +46,12 @@ __device__ __forceinline__ void rc_store_hit(rc_hit *hits, unsigned long long i,
     __stcs(p + 1, make_float4(h.bary_u, h.bary_v, __uint_as_float(h.instance_id), __uint_as_float(h.metadata)));
 }
 
-#define RC_FETCH_MIN 12    // refill when at least this many lanes of the warp are idle (or nothing else can run)
+#ifndef RC_FETCH_MIN
+#define RC_FETCH_MIN 16    // refill when at least this many lanes of the warp are idle (or nothing else can run); 8..24 swept in r1
+#endif
+#ifndef RC_MIN_BLOCKS
+#define RC_MIN_BLOCKS 8     // 64 registers -> 32 resident warps per SM (swept 6..10 in r1: 8 is best, 9+ spills)
+#endif
 #define RC_SSTACK 32       // stack entries per lane (shared memory, [depth][thread]); row RC_SSTACK is the dummy row
 #define RC_OVERFLOW_MARK 0xFFFFFFFFu  // rc_hit.hit of a ray whose short stack overflowed (re-traced by k_trace_fixup)
 #define RC_DEADLANE 0xFFFFFFFDu
@@ -82,7 +87,7 @@ __device__ __forceinline__ float2 rc_q2f_pair(uint32_t w, int j) {
 }
 
 template <bool ANY, bool COUNT>
-__global__ void __launch_bounds__(RC_TRACE_THREADS) k_trace_wide(RcScene sc, const rc_ray *__restrict__ rays, rc_hit *__restrict__ hits, unsigned long long n,
+__global__ void __launch_bounds__(RC_TRACE_THREADS, RC_MIN_BLOCKS) k_trace_wide(RcScene sc, const rc_ray *__restrict__ rays, rc_hit *__restrict__ hits, unsigned long long n,
                                                                  unsigned long long *__restrict__ work, RcCounters *__restrict__ counters,
                                                                  uint32_t *__restrict__ overflow) {
     __shared__ uint32_t sstack[(RC_SSTACK + 1) * RC_TRACE_THREADS];
