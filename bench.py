@@ -40,42 +40,66 @@ def peaks():
         return 6650.0, 1965.0, "fallback"
 
 
+def ncu_traffic(rays_per_launch):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed ncu --set full
+    capture of this same command (profiles/r1_traffic.json, written by tools/ncu_summary.py); None if the capture is for
+    another launch size."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        return float(t["dram_bytes"]) if int(t["rays_per_launch"]) == int(rays_per_launch) else None
+    except Exception:
+        return None
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe): one `nvidia-smi -lms 20`
+    process is read continuously; only samples stamped between mark_start() and mark_end() are summarised."""
 
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.index, self.rows, self.t0, self.t1, self.proc = index, [], None, None, None
         self.t = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
-        while not self.stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([x.strip() for x in out.strip().split(",")])
-            except Exception:
-                pass
-            self.stop.wait(0.2)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append((time.time(), [x.strip() for x in line.strip().split(",")]))
+        except Exception:
+            pass
 
     def __enter__(self):
         self.t.start()
+        time.sleep(0.15)  # let the first samples arrive before the timed region starts
         return self
 
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def __exit__(self, *a):
-        self.stop.set()
-        self.t.join(timeout=6)
+        time.sleep(0.05)
+        if self.proc is not None:
+            self.proc.terminate()
+        self.t.join(timeout=3)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        inside = [r for ts, r in self.rows if len(r) >= 7 and self.t0 is not None and self.t0 - 0.02 <= ts <= (self.t1 or ts) + 0.02]
+        rows = inside if inside else [r for _, r in self.rows if len(r) >= 7]
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        pw = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
-            if len(r) >= 7:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "power_w_max": max(pw) if pw else None,
+                "reasons": sorted(reasons), "samples": len(sm), "samples_in_timed_region": len(inside)}
 
 
 def build_rays(tlas_trace, verts, faces_of_prim, n, seed):
@@ -142,12 +166,13 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--rays", type=int, default=RAYS_PER_RANK)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the view_factors (C4) measurement")
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"], help="N > 1: how hit records reach rank 0")
     ap.add_argument("--counters", action="store_true", help="extra instrumented pass (per-ray node/triangle counts) after the timed region")
     args = ap.parse_args()
@@ -193,7 +218,7 @@ def main():
         build_dev_ms.append(float(lib.rc_last_build_ms(ctx)))
         dd = C.c_int32()
         lib.rc_delete(ctx, hh.value, C.byref(dd))
-    tlas.sync()
+        tlas.sync()  # frees the deleted BLAS so the next build reuses the pooled blocks (steady-state rebuild cost)
     n_tris = tlas.sizes()["blas_prims"]
     faces = tlas.read_blas_faces(1).astype(np.int64)
 
@@ -252,11 +277,13 @@ def main():
     kern_ms = []
     with ClockSampler(local) as clk:
         barrier()
+        clk.mark_start()
         ev0.record(stream)
         for _ in range(args.steps):
             step()
         ev1.record(stream)
         barrier()
+        clk.mark_end()
     ms_total = ev0.elapsed_time(ev1)
     if world > 1:
         t = torch.tensor([ms_total], device=dev)
@@ -329,7 +356,7 @@ def main():
     alg_hbm_bytes = 64.0  # 32 B RTRay in + 32 B RTHitResult out per ray
     roofline = {
         "bound": "hbm", "achieved": rays_per_s * alg_hbm_bytes / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": rays_per_s * alg_hbm_bytes / 1e9 / hbm_peak,
-        "traffic": None, "peak_source": which, "kernel": "k_trace<wide,closest>", "kernel_ms": k_ms, "rays_per_launch": n,
+        "traffic": ncu_traffic(n), "peak_source": which, "kernel": "k_trace_wide<closest>", "kernel_ms": k_ms, "rays_per_launch": n,
         "note": "HBM carries only the ray/hit streams (64 B/ray); the BVH working set is L2-resident, so the binding limits are L2->SM traffic and FP32/ALU issue (see l2/fp32 below)",
     }
     if counters:
@@ -340,6 +367,32 @@ def main():
         roofline["l2"] = {"bytes_per_ray": l2_bytes, "achieved_gbs": rays_per_s * l2_bytes / 1e9, "peak_gbs": 6300 * sm_max * 1e6 / 1e9, "peak_source": "6300 B/clk x sm_max_mhz (B300_MICROARCH LTS cap)"}
         roofline["fp32"] = {"flop_per_ray": flops, "achieved_tflops": rays_per_s * flops / 1e12, "peak_tflops": fp32_peak}
         roofline["per_ray"] = counters
+
+    # ---- the other two numbers of BASELINE.json's metric: BVH build ms (above) and view_factors s (C4) ------------------------
+    extras = None
+    if not args.no_extras:
+        from oracle import oracle as orc0
+
+        vt = rc.TLAS(local)
+        base = 0
+        for msh in W.viewfactor_scene(72):
+            keep = ~np.array([orc0.is_degenerate(v) for v in msh])
+            meta = np.zeros(len(msh), np.uint32)
+            meta[keep] = base + 1 + np.arange(keep.sum())
+            base += int(keep.sum())
+            vt.push(msh, None, face_meta=meta)
+        vt.sync()
+        npr = vt.sizes()["blas_prims"]
+        d_vf = torch.empty(npr * npr, dtype=torch.int32, device=dev)
+        sk = C.c_uint64()
+        vms = []
+        for _ in range(3):
+            assert vt._lib.rc_view_factors(vt._ctx, 1000, 11, d_vf.data_ptr(), 0, npr, L.RC_HITS_ON_DEVICE, C.byref(sk)) == 0
+            vms.append(float(vt._lib.rc_last_kernel_ms(vt._ctx)))
+        extras = {"view_factors_s": min(vms) * 1e-3, "view_factors_config": f"C4: 5 x bumpy_sphere(72) = {npr} triangles, rays_per_triangle=1000 ({npr * 1000} rays), UInt32 {npr}x{npr} matrix resident in HBM, 1 GPU",
+                  "view_factors_total_hits": int(d_vf.sum().item()), "blas_build_ms_1M_triangles": min(build_dev_ms)}
+        del d_vf
+        vt.free()
 
     cpu = None
     if not args.no_cpu_baseline:
@@ -371,7 +424,7 @@ def main():
             "rays_per_rank": n, "hit_rate": hit_rate, "primary_hit_rate": primary_hit_rate, "l2_policy": "inputs larger than L2 (512 MiB rays + 512 MiB hits per step)",
             "gather": {"fused": "fused: each rank's traversal kernel stores its hit records straight into rank 0's buffer through CUDA-IPC peer pointers over NVLink (no separate collective)", "nccl": "dist.gather of hit records to rank 0 (NCCL) after every trace"}.get(gather_mode, gather_mode), "parallelism": f"bvh replicated, rays sharded x{world}",
         },
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps * 1, "clocks": clk.summary(),
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps * 2, "clocks": clk.summary(), "extras": extras,
         "build": {"blas_build_ms_cuda_events": min(build_dev_ms), "blas_build_ms_wall_device_input": min(build_ms), "push_sync_ms_host_input": build_wall_ms, "triangles": n_tris},
     }
     print(json.dumps(line))

@@ -52,6 +52,15 @@ def main():
                     pass
         tot = sum(v for v, _ in st) or 1
         out.append("- warp-state samples: " + ", ".join(f"{n} {100 * v / tot:.1f}%" for v, n in sorted(st, reverse=True)[:9]))
+    if len(sys.argv) > 3:  # ncu_summary.py rep out.md traffic.json rays_per_launch
+        d = data[-1]
+        def num(k):
+            v, u = float(d[col[k]].replace(",", "")), units[col[k]].lower()
+            return v * {"gbyte": 1e9, "mbyte": 1e6, "kbyte": 1e3, "byte": 1.0}.get(u, 1.0)
+        import json
+        json.dump({"kernel": d[col["Kernel Name"]][:80], "dram_bytes": num("dram__bytes_read.sum") + num("dram__bytes_write.sum"),
+                   "dram_read_bytes": num("dram__bytes_read.sum"), "dram_write_bytes": num("dram__bytes_write.sum"),
+                   "rays_per_launch": int(sys.argv[4]), "source": rep}, open(sys.argv[3], "w"))
     text = "\n".join(out)
     print(text)
     if len(sys.argv) > 2:
