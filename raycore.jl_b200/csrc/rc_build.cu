@@ -382,13 +382,13 @@ __global__ void k_fit(const RcTri *__restrict__ tris, const RcBox *__restrict__ 
         f3 v0 = mk3(a.x, a.y, a.z), v1 = mk3(b.x, b.y, b.z), v2 = mk3(c.x, c.y, c.z);
         lo = jl_min3(jl_min3(v0, v1), v2);  // get_node_aabb leaf branch, :1148-1158
         hi = jl_max3(jl_max3(v0, v1), v2);
-        st_node2(nodes2 + (leaf - 1), v0, v1, v2, mk3(0, 0, 0), RC_INVALID, p + 1, par);
+        if (nodes2) st_node2(nodes2 + (leaf - 1), v0, v1, v2, mk3(0, 0, 0), RC_INVALID, p + 1, par);
     } else {
         uint32_t inst = leaf_map[p];
         RcBox b = inst_boxes[inst];
         lo = mk3(b.lo[0], b.lo[1], b.lo[2]);
         hi = mk3(b.hi[0], b.hi[1], b.hi[2]);
-        st_node2(nodes2 + (leaf - 1), lo, hi, mk3(0, 0, 0), mk3(0, 0, 0), RC_INVALID, inst, par);
+        if (nodes2) st_node2(nodes2 + (leaf - 1), lo, hi, mk3(0, 0, 0), mk3(0, 0, 0), RC_INVALID, inst, par);
     }
     st_box(boxes + (leaf - 1), lo, hi);
     uint32_t node = par;
@@ -401,7 +401,7 @@ __global__ void k_fit(const RcTri *__restrict__ tris, const RcBox *__restrict__ 
         f3 l0 = mk3(b0.lo[0], b0.lo[1], b0.lo[2]), h0 = mk3(b0.hi[0], b0.hi[1], b0.hi[2]);
         f3 l1 = mk3(b1.lo[0], b1.lo[1], b1.lo[2]), h1 = mk3(b1.hi[0], b1.hi[1], b1.hi[2]);
         uint32_t up = parent[node - 1];
-        st_node2(nodes2 + (node - 1), l0, h0, l1, h1, tp.child0, tp.child1, up);
+        if (nodes2) st_node2(nodes2 + (node - 1), l0, h0, l1, h1, tp.child0, tp.child1, up);
         st_box(boxes + (node - 1), jl_min3(l0, l1), jl_max3(h0, h1));  // get_node_aabb interior branch, :1142-1147
         node = up;
     }
@@ -418,6 +418,34 @@ __global__ void k_collapse(const RcBox *__restrict__ boxes, const RcTopo *__rest
     d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3];
 }
 
+// RC_HULL_BOXES subtree boxes that together cover the BLAS: open the largest-area internal node until the budget is used.
+// One warp, lane 0 does the (tiny) serial selection.
+__global__ void k_blas_hull(const RcBox *__restrict__ boxes, const RcTopo *__restrict__ topo, uint32_t n, RcBox *__restrict__ hull) {
+    if (threadIdx.x != 0) return;
+    uint32_t ids[RC_HULL_BOXES];
+    int cnt = 1;
+    ids[0] = 1;
+    while (cnt < RC_HULL_BOXES) {
+        int best = -1;
+        float best_area = -1.0f;
+        for (int k = 0; k < cnt; k++)
+            if (ids[k] < n) {
+                float a = rc_half_area(boxes[ids[k] - 1]);
+                if (a > best_area) { best_area = a; best = k; }
+            }
+        if (best < 0) break;
+        RcTopo tp = topo[ids[best] - 1];
+        ids[best] = tp.child0;
+        ids[cnt++] = tp.child1;
+    }
+    for (int k = 0; k < RC_HULL_BOXES; k++) {
+        RcBox b;
+        if (k < cnt) b = boxes[ids[k] - 1];
+        else { b.lo[0] = b.lo[1] = b.lo[2] = INFINITY; b.hi[0] = b.hi[1] = b.hi[2] = -INFINITY; b.pad0 = b.pad1 = 0; }
+        hull[k] = b;
+    }
+}
+
 __global__ void k_read_root(const RcBox *__restrict__ boxes, float *__restrict__ out6) {
     if (threadIdx.x < 3) out6[threadIdx.x] = boxes[0].lo[threadIdx.x];
     else if (threadIdx.x < 6) out6[threadIdx.x] = boxes[0].hi[threadIdx.x - 3];
@@ -425,7 +453,8 @@ __global__ void k_read_root(const RcBox *__restrict__ boxes, float *__restrict__
 
 // codes (sorted) -> topology, fit, BVH2, BVH4
 static void build_tree(cudaStream_t st, const uint32_t *codes_sorted, uint32_t n, const RcTri *tris, const RcBox *inst_boxes, const uint32_t *leaf_map,
-                       uint32_t leaf_max, RcTopo *topo, uint32_t *parent, uint32_t *flags, RcBox *boxes, RcNode2 *nodes2, RcNode4 *nodes4) {
+                       uint32_t leaf_max, RcTopo *topo, uint32_t *parent, uint32_t *flags, RcBox *boxes, RcNode2 *nodes2, RcNode4 *nodes4,
+                       const RcBox *inst_boxes_tight = nullptr, RcBox *boxes_tight = nullptr) {
     const int T = 256;
     if (n > 1) {
         k_topology<<<cdiv(n - 1, T), T, 0, st>>>(codes_sorted, n, topo, parent);
@@ -434,16 +463,24 @@ static void build_tree(cudaStream_t st, const uint32_t *codes_sorted, uint32_t n
         cudaMemsetAsync(parent, 0xFF, sizeof(uint32_t), st);  // single leaf: parent = INVALID
     }
     k_fit<<<cdiv(n, T), T, 0, st>>>(tris, inst_boxes, leaf_map, n, topo, parent, flags, boxes, nodes2);
+    if (inst_boxes_tight) {  // wide TLAS from the tighter instance bounds (same topology, second fit without BVH2 output)
+        if (n > 1) cudaMemsetAsync(flags, 0, sizeof(uint32_t) * (n - 1), st);
+        k_fit<<<cdiv(n, T), T, 0, st>>>(nullptr, inst_boxes_tight, leaf_map, n, topo, parent, flags, boxes_tight, nullptr);
+        boxes = boxes_tight;
+    }
     k_collapse<<<cdiv(n > 1 ? n - 1 : 1, T), T, 0, st>>>(boxes, topo, n, leaf_max, leaf_map, nodes4);
 }
 
 // refit only (topology kept): recompute boxes, BVH2 and BVH4
 static void refit_tree(cudaStream_t st, uint32_t n, const RcBox *inst_boxes, const uint32_t *leaf_map, uint32_t leaf_max, const RcTopo *topo,
-                       const uint32_t *parent, uint32_t *flags, RcBox *boxes, RcNode2 *nodes2, RcNode4 *nodes4) {
+                       const uint32_t *parent, uint32_t *flags, RcBox *boxes, RcNode2 *nodes2, RcNode4 *nodes4, const RcBox *inst_boxes_tight,
+                       RcBox *boxes_tight) {
     const int T = 256;
     if (n > 1) cudaMemsetAsync(flags, 0, sizeof(uint32_t) * (n - 1), st);
     k_fit<<<cdiv(n, T), T, 0, st>>>(nullptr, inst_boxes, leaf_map, n, topo, parent, flags, boxes, nodes2);
-    k_collapse<<<cdiv(n > 1 ? n - 1 : 1, T), T, 0, st>>>(boxes, topo, n, leaf_max, leaf_map, nodes4);
+    if (n > 1) cudaMemsetAsync(flags, 0, sizeof(uint32_t) * (n - 1), st);
+    k_fit<<<cdiv(n, T), T, 0, st>>>(nullptr, inst_boxes_tight, leaf_map, n, topo, parent, flags, boxes_tight, nullptr);
+    k_collapse<<<cdiv(n > 1 ? n - 1 : 1, T), T, 0, st>>>(boxes_tight, topo, n, leaf_max, leaf_map, nodes4);
 }
 
 // =================================================================================================
@@ -454,7 +491,8 @@ void rc_free_blas(RcDeviceBlas *b, cudaStream_t st) {
     if (b->nodes2) cudaFreeAsync(b->nodes2, st);
     if (b->nodes4) cudaFreeAsync(b->nodes4, st);
     if (b->tris) cudaFreeAsync(b->tris, st);
-    b->nodes2 = nullptr; b->nodes4 = nullptr; b->tris = nullptr; b->n = 0;
+    if (b->hull) cudaFreeAsync(b->hull, st);
+    b->nodes2 = nullptr; b->nodes4 = nullptr; b->tris = nullptr; b->hull = nullptr; b->n = 0;
 }
 
 bool rc_build_blas(cudaStream_t st, const float *d_verts, const uint32_t *d_face_meta, uint32_t n_faces, RcDeviceBlas *out, std::string &err) {
@@ -498,6 +536,7 @@ bool rc_build_blas(cudaStream_t st, const float *d_verts, const uint32_t *d_face
     CK(cudaMallocAsync(&out->nodes2, sizeof(RcNode2) * (2 * n - 1), st));
     CK(cudaMallocAsync(&out->nodes4, sizeof(RcNode4) * (n + 1), st));
     CK(cudaMallocAsync(&out->tris, sizeof(RcTri) * n, st));
+    CK(cudaMallocAsync(&out->hull, sizeof(RcBox) * RC_HULL_BOXES, st));
     out->n = n;
     out->n_faces_in = n_faces;
 
@@ -507,6 +546,7 @@ bool rc_build_blas(cudaStream_t st, const float *d_verts, const uint32_t *d_face
     radix_sort_pairs(st, d_codes, d_idx, d_codes2, d_idx2, n, d_hist);
     k_gather_tris<<<cdiv(n, T), T, 0, st>>>(d_tris_in, d_idx, n, out->tris);
     build_tree(st, d_codes, n, out->tris, nullptr, nullptr, RC_BLAS_LEAF_MAX, d_topo, d_parent, d_fl, d_boxes, out->nodes2, out->nodes4);
+    k_blas_hull<<<1, 32, 0, st>>>(d_boxes, d_topo, n, out->hull);
     k_read_root<<<1, 32, 0, st>>>(d_boxes, reinterpret_cast<float *>(d_small + 10));
     CK(cudaMemcpyAsync(out->root_aabb, d_small + 10, 24, cudaMemcpyDeviceToHost, st));
     for (void *p : {(void *)d_flags, (void *)d_pos, (void *)d_tile, (void *)d_tris_in, (void *)d_tri_boxes, (void *)d_codes, (void *)d_idx, (void *)d_codes2,
@@ -521,13 +561,31 @@ bool rc_build_blas(cudaStream_t st, const float *d_verts, const uint32_t *d_face
 // ---------------------------------------------------------------------------------------------- TLAS
 // instance world boxes + scene bounds (compute_instance_aabbs_kernel!, kernels.jl:65-78; host reduction :1499-1512)
 __global__ void k_instance_boxes(const rc_instance_desc *__restrict__ inst, const float *__restrict__ blas_roots /* 6 per BLAS */, uint32_t n,
-                                 RcBox *__restrict__ inst_boxes, uint32_t *__restrict__ bounds) {
+                                 RcBox *__restrict__ inst_boxes, uint32_t *__restrict__ bounds, const RcBlasPtrs *__restrict__ blas,
+                                 RcBox *__restrict__ tight_boxes) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     f3 lo = mk3(INFINITY, INFINITY, INFINITY), hi = mk3(-INFINITY, -INFINITY, -INFINITY);
     if (i < n) {
         const rc_instance_desc *d = inst + i;
         rc_instance_world_aabb(d->transform, blas_roots + 6 * (d->blas_index - 1), lo, hi);
         st_box(inst_boxes + i, lo, hi);
+        // tighter conservative bound for the wide TLAS: union of the transformed BLAS hull boxes (a rotated root box is up to
+        // sqrt(3) wider per axis than the geometry it holds)
+        const RcBox *hull = blas[d->blas_index - 1].hull;
+        f3 tl = mk3(INFINITY, INFINITY, INFINITY), th = mk3(-INFINITY, -INFINITY, -INFINITY);
+        for (int k = 0; k < RC_HULL_BOXES; k++) {
+            RcBox hb = hull[k];
+            if (!(hb.lo[0] <= hb.hi[0])) continue;
+            float loc[6] = {hb.lo[0], hb.lo[1], hb.lo[2], hb.hi[0], hb.hi[1], hb.hi[2]};
+            f3 a, b;
+            rc_instance_world_aabb(d->transform, loc, a, b);
+            tl = mk3(fminf(tl.x, a.x), fminf(tl.y, a.y), fminf(tl.z, a.z));
+            th = mk3(fmaxf(th.x, b.x), fmaxf(th.y, b.y), fmaxf(th.z, b.z));
+        }
+        // never larger than the reference box
+        tl = mk3(fmaxf(tl.x, lo.x), fmaxf(tl.y, lo.y), fmaxf(tl.z, lo.z));
+        th = mk3(fminf(th.x, hi.x), fminf(th.y, hi.y), fminf(th.z, hi.z));
+        st_box(tight_boxes + i, tl, th);
     }
     if (bounds) bounds_atomic(bounds, lo, hi);
 }
@@ -570,7 +628,7 @@ __global__ void k_instance_records(const rc_instance_desc *__restrict__ inst, co
 void rc_free_tlas(RcDeviceTlas *t, cudaStream_t st) {
     if (!t) return;
     for (void *p : {(void *)t->nodes2, (void *)t->nodes4, (void *)t->rec, (void *)t->aux, (void *)t->d_inst, (void *)t->d_blas_roots, (void *)t->d_blas_ptrs,
-                    (void *)t->inst_boxes, (void *)t->leaf_map, (void *)t->topo, (void *)t->parent, (void *)t->flags, (void *)t->boxes, (void *)t->d_small})
+                    (void *)t->inst_boxes, (void *)t->inst_boxes_tight, (void *)t->boxes_tight, (void *)t->leaf_map, (void *)t->topo, (void *)t->parent, (void *)t->flags, (void *)t->boxes, (void *)t->d_small})
         if (p) cudaFreeAsync(p, st);
     *t = RcDeviceTlas();
 }
@@ -598,6 +656,8 @@ bool rc_build_tlas(cudaStream_t st, const rc_instance_desc *h_inst, uint32_t n, 
     CK(cudaMallocAsync(&t->rec, sizeof(RcInstanceRec) * n, st));
     CK(cudaMallocAsync(&t->aux, sizeof(RcInstanceAux) * n, st));
     CK(cudaMallocAsync(&t->inst_boxes, sizeof(RcBox) * n, st));
+    CK(cudaMallocAsync(&t->inst_boxes_tight, sizeof(RcBox) * n, st));
+    CK(cudaMallocAsync(&t->boxes_tight, sizeof(RcBox) * (2 * n - 1), st));
     CK(cudaMallocAsync(&t->leaf_map, sizeof(uint32_t) * n, st));
     CK(cudaMallocAsync(&t->topo, sizeof(RcTopo) * std::max(1u, n - 1), st));
     CK(cudaMallocAsync(&t->parent, sizeof(uint32_t) * (2 * n - 1), st));
@@ -615,10 +675,11 @@ bool rc_build_tlas(cudaStream_t st, const rc_instance_desc *h_inst, uint32_t n, 
     if (!upload_instances(st, t, h_inst, n, err)) return false;
     uint32_t *d_bounds = t->d_small + 4;
     k_init_bounds<<<1, 32, 0, st>>>(d_bounds);
-    k_instance_boxes<<<cdiv(n, T), T, 0, st>>>(t->d_inst, t->d_blas_roots, n, t->inst_boxes, d_bounds);
+    k_instance_boxes<<<cdiv(n, T), T, 0, st>>>(t->d_inst, t->d_blas_roots, n, t->inst_boxes, d_bounds, t->d_blas_ptrs, t->inst_boxes_tight);
     k_morton_instances<<<cdiv(n, T), T, 0, st>>>(t->d_inst, t->d_blas_roots, n, d_bounds, d_codes, t->leaf_map);
     radix_sort_pairs(st, d_codes, t->leaf_map, d_codes2, d_idx2, n, d_hist);  // leaf_map = sorted position -> instance index
-    build_tree(st, d_codes, n, nullptr, t->inst_boxes, t->leaf_map, 1, t->topo, t->parent, t->flags, t->boxes, t->nodes2, t->nodes4);
+    build_tree(st, d_codes, n, nullptr, t->inst_boxes, t->leaf_map, 1, t->topo, t->parent, t->flags, t->boxes, t->nodes2, t->nodes4, t->inst_boxes_tight,
+               t->boxes_tight);
     k_read_root<<<1, 32, 0, st>>>(t->boxes, reinterpret_cast<float *>(t->d_small + 10));
     CK(cudaMemcpyAsync(t->root_aabb, t->d_small + 10, 24, cudaMemcpyDeviceToHost, st));
     for (void *p : {(void *)d_codes, (void *)d_codes2, (void *)d_idx2, (void *)d_hist}) cudaFreeAsync(p, st);
@@ -632,8 +693,8 @@ bool rc_refit_tlas(cudaStream_t st, const rc_instance_desc *h_inst, uint32_t n, 
     if (n != t->n) { err = "refit: instance count changed"; return false; }
     if (!upload_instances(st, t, h_inst, n, err)) return false;
     // update_tlas_leaf_aabbs_kernel! (kernels.jl:487-519) + refit_tlas_aabbs_kernel! (:381-428), then re-quantise the wide nodes
-    k_instance_boxes<<<cdiv(n, 256), 256, 0, st>>>(t->d_inst, t->d_blas_roots, n, t->inst_boxes, nullptr);
-    refit_tree(st, n, t->inst_boxes, t->leaf_map, 1, t->topo, t->parent, t->flags, t->boxes, t->nodes2, t->nodes4);
+    k_instance_boxes<<<cdiv(n, 256), 256, 0, st>>>(t->d_inst, t->d_blas_roots, n, t->inst_boxes, nullptr, t->d_blas_ptrs, t->inst_boxes_tight);
+    refit_tree(st, n, t->inst_boxes, t->leaf_map, 1, t->topo, t->parent, t->flags, t->boxes, t->nodes2, t->nodes4, t->inst_boxes_tight, t->boxes_tight);
     k_read_root<<<1, 32, 0, st>>>(t->boxes, reinterpret_cast<float *>(t->d_small + 10));
     CK(cudaMemcpyAsync(t->root_aabb, t->d_small + 10, 24, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));

@@ -16,13 +16,17 @@ struct RcDeviceBlas {
     RcNode2 *nodes2 = nullptr;  // 2n-1, reference layout, node k at [k-1]
     RcNode4 *nodes4 = nullptr;  // n+1 slots, indexed by BVH2 internal node number, root = [1]
     RcTri *tris = nullptr;      // n, Morton-sorted
+    RcBox *hull = nullptr;      // RC_HULL_BOXES boxes of BVH2 subtrees covering the whole BLAS (tight instance bounds for the wide TLAS)
     float root_aabb[6] = {0, 0, 0, 0, 0, 0};
 };
+
+#define RC_HULL_BOXES 16
 
 struct RcBlasPtrs {  // device-visible BLAS table entry
     const RcNode2 *nodes2;
     const RcNode4 *nodes4;
     const RcTri *tris;
+    const RcBox *hull;  // RC_HULL_BOXES entries (unused ones are empty boxes)
     uint32_t n, pad;
 };
 
@@ -35,7 +39,9 @@ struct RcDeviceTlas {
     rc_instance_desc *d_inst = nullptr;
     float *d_blas_roots = nullptr;
     RcBlasPtrs *d_blas_ptrs = nullptr;
-    RcBox *inst_boxes = nullptr;
+    RcBox *inst_boxes = nullptr;        // reference-identical world boxes (8 corners of the BLAS root box) -> BVH2
+    RcBox *inst_boxes_tight = nullptr;  // union over the BLAS hull boxes -> wide TLAS only (conservative, tighter)
+    RcBox *boxes_tight = nullptr;       // per-node boxes of the tight fit
     uint32_t *leaf_map = nullptr;  // sorted position -> instance index
     RcTopo *topo = nullptr;
     uint32_t *parent = nullptr;
