@@ -170,3 +170,34 @@ def test_deep_trees_short_stack_fixup():
     a2 = gq.trace(rays)
     assert a2.tobytes() == a.tobytes()
     assert np.array_equal(gq.trace(rays, any_hit=True)["hit"], o.trace(rays, any_hit=True)["hit"])
+
+
+def test_edge_case_rays_and_geometry():
+    """Edge cases the domain has: zero / negative-zero direction components, axis-parallel rays lying in box faces, t_min / t_max
+    windows, non-finite rays (must terminate and miss, never hang or crash), empty batches, coincident duplicate triangles (exact
+    ties: the winner is traversal-order dependent in the reference, so only t is compared), rays starting on a triangle."""
+    verts = np.concatenate([W.box_mesh(), W.box_mesh(), W.quad_mesh(2.0, 3.0)])  # the box twice: every box hit is an exact tie
+    pushes = [(verts, None, [kat.I34, W.translation3x4((4, 0, 0))], [5, 6])]
+    o, g, gr = engines.OracleEngine(pushes), engines.GpuEngine(pushes), engines.GpuEngine(pushes, reference_order=True)
+    org = np.array([[0.1, 0.2, 5], [0.1, 0.2, 5], [0.5, 0.5, 5], [0.0, 0.0, 0.0], [0.1, 0.2, 0.5], [10, 10, 10], [4.1, 0.1, -5], [0.1, 0.2, 5], [0.1, 0.2, 5]], np.float32)
+    d = np.array([[0, 0, -1], [-0.0, -0.0, -1], [0, 0, -1], [1, 0, 0], [0, 0, 1], [0, 0, -1], [0, 0, 1], [0, 0, -1], [0, 0, -1]], np.float32)
+    rays = W.make_rays(org, d)
+    rays["t_min"][7], rays["t_max"][8] = 4.7, 2.0  # window beyond the first two surfaces / before the first
+    a, r, b = g.trace(rays), gr.trace(rays), o.trace(rays)
+    assert r.tobytes() == b.tobytes()
+    assert np.array_equal(a["hit"], b["hit"])
+    ok = b["hit"] == 1
+    assert np.array_equal(a["t"][ok], b["t"][ok]) or np.allclose(a["t"][ok], b["t"][ok], rtol=1e-6)
+    assert b["hit"][5] == 0 and b["hit"][0] == 1 and b["hit"][8] == 0
+    # non-finite rays
+    bad = W.make_rays([[np.nan, 0, 0], [0, 0, 5], [np.inf, 0, 0], [0, 0, 5], [0, 0, 5]], [[0, 0, -1], [np.nan, 0, -1], [0, 0, -1], [np.inf, 0, -1], [0, 0, 0]])
+    for eng in (g, gr):
+        h = eng.trace(bad)
+        assert (h["hit"] <= 1).all() and h["hit"][:4].sum() == 0
+        assert (eng.trace(bad, any_hit=True)["hit"] <= 1).all()
+    # empty batch
+    assert len(g.trace(rays[:0])) == 0
+    # large counts of identical rays (all lanes retire together) and a batch that is not a multiple of anything
+    many = np.repeat(rays[:1], 100003)
+    h = g.trace(many)
+    assert (h["hit"] == 1).all() and (h["t"] == h["t"][0]).all()
