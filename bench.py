@@ -234,21 +234,12 @@ def main():
         gather_mode = "nccl"
         if args.gather == "fused":
             try:
-                handle = (C.c_uint8 * 64)()
-                if rank == 0:
-                    assert lib.rc_device_alloc(ctx, world * n * 32, C.byref(g_base)) == 0
-                    assert lib.rc_ipc_export(ctx, g_base, handle) == 0
-                obj = [bytes(handle)]
-                dist.broadcast_object_list(obj, src=0)
-                ok = 1
-                if rank != 0:
-                    hb = (C.c_uint8 * 64).from_buffer_copy(obj[0])
-                    ok = int(lib.rc_ipc_open(ctx, hb, C.byref(g_base)) == 0)
-                t = torch.tensor([ok], device=dev)
-                dist.all_reduce(t, op=dist.ReduceOp.MIN)
-                if int(t.item()) == 1:
-                    gather_mode = "fused"
-                    hits_ptr = g_base.value + rank * n * 32
+                from raycore_b200.sharding import PeerResultBuffer
+
+                peer = PeerResultBuffer(tlas, world * n * 32)
+                g_base = peer.base
+                gather_mode = "fused"
+                hits_ptr = peer.ptr(rank * n * 32)
             except Exception as e:  # pragma: no cover
                 print(f"[rank {rank}] fused gather unavailable ({e}); falling back to NCCL gather", file=sys.stderr)
         if gather_mode == "nccl" and rank == 0:

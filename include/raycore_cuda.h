@@ -201,6 +201,19 @@ int32_t rc_view_factor_rays(rc_context *ctx, uint32_t rays_per_triangle, uint64_
 /* metadata of the flat primitive array (position -> metadata), n_prims entries */
 int32_t rc_read_flat_metadata(rc_context *ctx, uint32_t *out, uint32_t capacity);
 
+/* ---- collision broad phase (src/collision.jl) ---------------------------- */
+/* ContactPair, 8 bytes — src/collision.jl:25-28 (1-based instance indices, instance_a < instance_b) */
+typedef struct rc_contact_pair {
+    uint32_t instance_a, instance_b;
+} rc_contact_pair;
+/* collide_instances(tlas) — src/collision.jl:189-233: every pair of instances whose world AABBs overlap, in the reference's
+ * output order.  Two-call protocol: contacts == NULL (or capacity too small) only reports *n_contacts.  Host pointers. */
+int32_t rc_collide_instances(rc_context *ctx, rc_contact_pair *contacts, uint64_t capacity, uint64_t *n_contacts);
+/* collide_instances_any(tlas, handle_a, handle_b) — src/collision.jl:241-261: do any two instances of the two handles overlap
+ * (world AABBs)?  Each instance's own TLAS leaf box is used (the reference indexes the Morton-sorted leaves with the instance
+ * index, which is only correct when the sort is the identity — see DESIGN.md). */
+int32_t rc_collide_instances_any(rc_context *ctx, uint32_t handle_a, uint32_t handle_b, int32_t *overlap);
+
 /* ---- device memory helpers for callers that keep rays/hits resident -------------------- */
 int32_t rc_device_alloc(rc_context *ctx, size_t bytes, void **out);
 int32_t rc_device_free(rc_context *ctx, void *ptr);

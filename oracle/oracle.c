@@ -825,3 +825,82 @@ void orc_view_factors_from_rays(const orc_tlas *t, const orc_ray *rays, uint32_t
         }
     }
 }
+
+/* ------------------------------------------------------------------ collision, src/collision.jl */
+static inline int aabb_overlaps(const float amin[3], const float amax[3], const float bmin[3], const float bmax[3]) { /* :49-51 */
+    return amax[0] >= bmin[0] && amax[1] >= bmin[1] && amax[2] >= bmin[2] && amin[0] <= bmax[0] && amin[1] <= bmax[1] && amin[2] <= bmax[2];
+}
+
+/* one pass of collide_instances_kernel! (:81-156) for leaf position i (1-based); contacts == NULL: count only */
+static uint32_t collide_leaf(const orc_tlas *t, uint32_t i, const uint32_t *incl_counts, orc_contact *contacts) {
+    uint32_t n = t->n_instances;
+    const orc_node2 *nodes = t->nodes;
+    const orc_node2 *leaf = &nodes[(n - 1 + i) - 1];
+    const float *a_min = leaf->aabb0_min, *a_max = leaf->aabb0_max;
+    uint32_t instance_a = leaf->child1, count = 0;
+    uint32_t stack[256];
+    int sp = 0;
+    uint32_t node_index = 1;
+    for (;;) {
+        const orc_node2 *nd = &nodes[node_index - 1];
+        if (nd->child0 != ORC_INVALID_NODE) {
+            int o0 = aabb_overlaps(a_min, a_max, nd->aabb0_min, nd->aabb0_max);
+            int o1 = aabb_overlaps(a_min, a_max, nd->aabb1_min, nd->aabb1_max);
+            if (o0 && o1) {
+                if (sp >= 256) { fprintf(stderr, "oracle: collision stack overflow\n"); abort(); }
+                stack[sp++] = nd->child1;
+                node_index = nd->child0;
+                continue;
+            } else if (o0) { node_index = nd->child0; continue; }
+            else if (o1) { node_index = nd->child1; continue; }
+        } else {
+            uint32_t instance_b = nd->child1;
+            if (instance_b > instance_a && aabb_overlaps(a_min, a_max, nd->aabb0_min, nd->aabb0_max)) {
+                count++;
+                if (contacts) {
+                    uint32_t write_idx = incl_counts[i - 1] - count + 1; /* :138 */
+                    contacts[write_idx - 1].instance_a = instance_a + 1;
+                    contacts[write_idx - 1].instance_b = instance_b + 1;
+                }
+            }
+        }
+        if (sp > 0) node_index = stack[--sp];
+        else break;
+    }
+    return count;
+}
+
+/* collide_instances (:189-233).  counts (n entries, nullable) receives the inclusive prefix sums the reference keeps as its
+ * cache; contacts (nullable) must hold the returned total.  Returns the number of contacts. */
+uint64_t orc_collide_instances(const orc_tlas *t, uint32_t *counts, orc_contact *contacts) {
+    uint32_t n = t->n_instances;
+    if (n == 0) return 0;
+    uint32_t *c = counts ? counts : (uint32_t *)malloc(sizeof(uint32_t) * n);
+    for (uint32_t i = 1; i <= n; i++) c[i - 1] = collide_leaf(t, i, NULL, NULL);
+    for (uint32_t i = 1; i < n; i++) c[i] += c[i - 1]; /* AK.accumulate!(+) :215 */
+    uint64_t total = c[n - 1];
+    if (contacts && total)
+        for (uint32_t i = 1; i <= n; i++) collide_leaf(t, i, c, contacts);
+    if (!counts) free(c);
+    return total;
+}
+
+/* collide_instances_any (:241-261).  literal != 0 reproduces the reference verbatim: it indexes the Morton-sorted leaf array
+ * with the *instance* index (nodes[n-1+ia]), which is only right when the sort is the identity; literal == 0 looks each
+ * instance's own leaf up (the evident intent). */
+int orc_collide_instances_any(const orc_tlas *t, uint32_t a_start, uint32_t a_count, uint32_t b_start, uint32_t b_count, int literal) {
+    uint32_t n = t->n_instances;
+    uint32_t *leaf_of = (uint32_t *)malloc(sizeof(uint32_t) * (n ? n : 1));
+    for (uint32_t p = 1; p <= n; p++) {
+        const orc_node2 *lf = &t->nodes[(n - 1 + p) - 1];
+        leaf_of[literal ? p - 1 : lf->child1] = p;
+    }
+    int hit = 0;
+    for (uint32_t ia = a_start; ia < a_start + a_count && !hit; ia++)
+        for (uint32_t ib = b_start; ib < b_start + b_count && !hit; ib++) {
+            const orc_node2 *la = &t->nodes[(n - 1 + leaf_of[ia]) - 1], *lb = &t->nodes[(n - 1 + leaf_of[ib]) - 1];
+            hit = aabb_overlaps(la->aabb0_min, la->aabb0_max, lb->aabb0_min, lb->aabb0_max);
+        }
+    free(leaf_of);
+    return hit;
+}

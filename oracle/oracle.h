@@ -169,6 +169,12 @@ void orc_view_factors(const orc_tlas *t, uint32_t rays_per_triangle, uint64_t se
 /* accumulate caller-supplied rays (e.g. the CUDA library's own generated rays) laid out as above */
 void orc_view_factors_from_rays(const orc_tlas *t, const orc_ray *rays, uint32_t rays_per_triangle, uint32_t row_base,
                                 uint32_t n_rows, uint32_t *result, int threads);
+/* ---- collision (src/collision.jl) ---- */
+typedef struct { uint32_t instance_a, instance_b; } orc_contact; /* ContactPair :25-28, 1-based instance indices, a < b */
+uint64_t orc_collide_instances(const orc_tlas *t, uint32_t *counts, orc_contact *contacts);  /* :189-233 */
+/* ranges are 0-based [start, start+count) positions in instances[] */
+int orc_collide_instances_any(const orc_tlas *t, uint32_t a_start, uint32_t a_count, uint32_t b_start, uint32_t b_count, int literal); /* :241-261 */
+
 /* the RNG itself, exposed so tests can pin GPU == oracle on the uniform stream */
 float orc_rng_uniform(uint64_t seed, uint64_t index, uint32_t dim);
 

@@ -141,6 +141,10 @@ def lib():
         L.orc_view_factors.argtypes = [C.POINTER(_Tlas), C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, vp, vp, C.c_int]
         L.orc_view_factors_from_rays.restype = None
         L.orc_view_factors_from_rays.argtypes = [C.POINTER(_Tlas), vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, C.c_int]
+        L.orc_collide_instances.restype = C.c_uint64
+        L.orc_collide_instances.argtypes = [C.POINTER(_Tlas), vp, vp]
+        L.orc_collide_instances_any.restype = C.c_int
+        L.orc_collide_instances_any.argtypes = [C.POINTER(_Tlas), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
         L.orc_rng_uniform.restype = C.c_float
         L.orc_rng_uniform.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32]
         _lib = L
@@ -409,6 +413,19 @@ class OracleTLAS:
         res = np.zeros((n_rows, n), np.uint32)
         lib().orc_view_factors_from_rays(self._p, rays.ctypes.data, rays_per_triangle, row_base, n_rows, res.ctypes.data, threads)
         return res
+
+    def collide_instances(self):
+        """collide_instances (src/collision.jl:189-233): (pairs[total, 2] 1-based, inclusive count cache)."""
+        n = self.n_instances
+        counts = np.zeros(max(n, 1), np.uint32)
+        total = lib().orc_collide_instances(self._p, counts.ctypes.data, None)
+        pairs = np.zeros((total, 2), np.uint32)
+        if total:
+            lib().orc_collide_instances(self._p, counts.ctypes.data, pairs.ctypes.data)
+        return pairs, counts[:n]
+
+    def collide_instances_any(self, a_range, b_range, literal=False):
+        return bool(lib().orc_collide_instances_any(self._p, a_range[0], a_range[1], b_range[0], b_range[1], int(literal)))
 
     def __del__(self):
         if getattr(self, "_p", None):

@@ -70,6 +70,7 @@ EXPORTS = [
     "rc_read_blas_order", "rc_blas_n_prims", "rc_read_blas_faces", "rc_get_instance_handles",
     "rc_trace_closest", "rc_trace_any", "rc_get_counters", "rc_last_kernel_ms", "rc_last_kernel_launches", "rc_last_build_ms",
     "rc_hits_from_grid", "rc_get_illumination", "rc_get_centroid", "rc_view_factors", "rc_view_factor_rays", "rc_read_flat_metadata",
+    "rc_collide_instances", "rc_collide_instances_any",
     "rc_device_alloc", "rc_device_free", "rc_host_alloc", "rc_host_free", "rc_memcpy_h2d", "rc_memcpy_d2h",
     "rc_ipc_export", "rc_ipc_open", "rc_ipc_close",
 ]  # fmt: skip
@@ -139,6 +140,8 @@ def load():
         "rc_view_factors": (i32, [vp, u32, u64, vp, u32, u32, u32, C.POINTER(u64)]),
         "rc_view_factor_rays": (i32, [vp, u32, u64, u32, u32, vp]),
         "rc_read_flat_metadata": (i32, [vp, vp, u32]),
+        "rc_collide_instances": (i32, [vp, vp, u64, C.POINTER(u64)]),
+        "rc_collide_instances_any": (i32, [vp, u32, u32, pi32]),
         "rc_device_alloc": (i32, [vp, C.c_size_t, C.POINTER(vp)]),
         "rc_device_free": (i32, [vp, vp]),
         "rc_host_alloc": (i32, [vp, C.c_size_t, C.POINTER(vp)]),

@@ -738,6 +738,60 @@ int32_t rc_read_flat_metadata(rc_context *ctx, uint32_t *out, uint32_t capacity)
     return RC_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ collision (§8f row 1)
+int32_t rc_collide_instances(rc_context *ctx, rc_contact_pair *contacts, uint64_t capacity, uint64_t *n_contacts) {
+    if (!ctx || !n_contacts) return RC_ERR_INVALID_ARGUMENT;
+    use_device(ctx);
+    int32_t rc = require_synced(ctx);
+    if (rc != RC_OK) return rc;
+    *n_contacts = 0;
+    uint32_t n = ctx->tlas.n;
+    if (n == 0) return RC_OK;
+    uint32_t *d_counts = nullptr, *d_excl = nullptr, *d_tile = nullptr, *d_total = nullptr;
+    RC_CUDA(ctx, cudaMallocAsync(&d_counts, sizeof(uint32_t) * n, ctx->stream));
+    RC_CUDA(ctx, cudaMallocAsync(&d_excl, sizeof(uint32_t) * n, ctx->stream));
+    RC_CUDA(ctx, cudaMallocAsync(&d_tile, sizeof(uint32_t) * ((n + 2047) / 2048), ctx->stream));
+    RC_CUDA(ctx, cudaMallocAsync(&d_total, sizeof(uint32_t), ctx->stream));
+    rc_collide_count(ctx->stream, ctx->tlas, d_counts, ctx->d_overflow + 1);
+    rc_exclusive_scan_u32(ctx->stream, d_counts, d_excl, n, d_tile, d_total);
+    uint32_t total = 0;
+    RC_CUDA(ctx, cudaMemcpyAsync(&total, d_total, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *n_contacts = total;
+    if (contacts && capacity >= total && total > 0) {
+        rc_contact_pair *d_c = nullptr;
+        RC_CUDA(ctx, cudaMallocAsync(&d_c, sizeof(rc_contact_pair) * (size_t)total, ctx->stream));
+        rc_collide_write(ctx->stream, ctx->tlas, d_counts, d_excl, d_c, ctx->d_overflow + 1);
+        RC_CUDA(ctx, cudaMemcpyAsync(contacts, d_c, sizeof(rc_contact_pair) * (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
+        cudaFreeAsync(d_c, ctx->stream);
+    }
+    for (void *p : {(void *)d_counts, (void *)d_excl, (void *)d_tile, (void *)d_total}) cudaFreeAsync(p, ctx->stream);
+    RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return check_overflow(ctx);
+}
+
+int32_t rc_collide_instances_any(rc_context *ctx, uint32_t handle_a, uint32_t handle_b, int32_t *overlap) {
+    if (!ctx || !overlap) return RC_ERR_INVALID_ARGUMENT;
+    use_device(ctx);
+    *overlap = 0;
+    int32_t rc = require_synced(ctx);
+    if (rc != RC_OK) return rc;
+    HandleInfo *ha = nullptr, *hb = nullptr;
+    if ((rc = find_handle(ctx, handle_a, &ha)) != RC_OK) return rc;
+    if ((rc = find_handle(ctx, handle_b, &hb)) != RC_OK) return rc;
+    uint32_t n = ctx->tlas.n;
+    if (n == 0) return RC_OK;
+    std::vector<float> boxes(8 * (size_t)n);  // RcBox = 8 floats; reference-identical world boxes, indexed by instance position
+    RC_CUDA(ctx, cudaMemcpyAsync(boxes.data(), ctx->tlas.inst_boxes, sizeof(float) * 8 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (uint32_t ia = ha->start; ia < ha->start + ha->count; ia++)
+        for (uint32_t ib = hb->start; ib < hb->start + hb->count; ib++) {
+            const float *a = &boxes[8 * (size_t)ia], *b = &boxes[8 * (size_t)ib];
+            if (a[4] >= b[0] && a[5] >= b[1] && a[6] >= b[2] && a[0] <= b[4] && a[1] <= b[5] && a[2] <= b[6]) { *overlap = 1; return RC_OK; }
+        }
+    return RC_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ memory helpers
 int32_t rc_device_alloc(rc_context *ctx, size_t bytes, void **out) {
     if (!ctx || !out) return RC_ERR_INVALID_ARGUMENT;

@@ -118,6 +118,10 @@ static void exclusive_scan_u32(cudaStream_t st, const uint32_t *in, uint32_t *ou
     k_scan_apply<<<tiles, SCAN_THREADS, 0, st>>>(in, n, tile_tmp, out);
 }
 
+void rc_exclusive_scan_u32(cudaStream_t st, const uint32_t *in, uint32_t *out, uint32_t n, uint32_t *tile_tmp, uint32_t *d_total) {
+    exclusive_scan_u32(st, in, out, n, tile_tmp, d_total);
+}
+
 // =================================================================================================
 // Stable LSD radix sort of (u32 key, u32 value) pairs, 8 bits per pass.
 //   per pass:  k_radix_hist   per-tile digit histogram            -> hist[digit * tiles + tile]

@@ -57,3 +57,9 @@ bool rc_build_tlas(cudaStream_t st, const rc_instance_desc *h_inst, uint32_t n, 
                    RcDeviceTlas *t, std::string &err);
 bool rc_refit_tlas(cudaStream_t st, const rc_instance_desc *h_inst, uint32_t n, RcDeviceTlas *t, std::string &err);
 void rc_free_tlas(RcDeviceTlas *t, cudaStream_t st);
+
+// generic device exclusive scan (rc_build.cu): out[i] = sum(in[0..i)), *d_total = sum of all; tile_tmp >= ceil(n / 2048) words
+void rc_exclusive_scan_u32(cudaStream_t st, const uint32_t *in, uint32_t *out, uint32_t n, uint32_t *tile_tmp, uint32_t *d_total);
+// collision broad phase (rc_collide.cu)
+bool rc_collide_count(cudaStream_t st, const RcDeviceTlas &t, uint32_t *d_counts, uint32_t *d_overflow);
+bool rc_collide_write(cudaStream_t st, const RcDeviceTlas &t, uint32_t *d_counts, const uint32_t *d_excl, rc_contact_pair *d_contacts, uint32_t *d_overflow);

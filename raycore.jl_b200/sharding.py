@@ -65,3 +65,55 @@ def view_factor_rows_sharded(vf_fn, n_prims: int, device: Optional[torch.device]
     if full is None:
         return None
     return full.cpu().numpy().view(np.uint32).reshape(n_prims, n_prims)
+
+
+class PeerResultBuffer:
+    """A device buffer owned by rank `dst` and mapped into every other rank through CUDA IPC (rc_ipc_export / rc_ipc_open), so
+    each rank's traversal kernel can store its hit records straight into its slice over NVLink: the gather is the kernel's
+    epilogue, no separate collective runs.  Call `fence()` (stream sync + barrier) before the owner reads.
+
+    Raises RuntimeError on every rank if any rank cannot map the buffer (callers then fall back to `gather_records`)."""
+
+    def __init__(self, tlas, nbytes: int, dst: int = 0):
+        import ctypes as C
+
+        self._C, self._lib, self._ctx = C, tlas._lib, tlas._ctx
+        self.rank, self.world, self.dst, self.nbytes = dist.get_rank(), dist.get_world_size(), dst, nbytes
+        self.base = C.c_void_p()
+        handle = (C.c_uint8 * 64)()
+        ok = 1
+        if self.rank == dst:
+            ok = int(self._lib.rc_device_alloc(self._ctx, nbytes, C.byref(self.base)) == 0 and self._lib.rc_ipc_export(self._ctx, self.base, handle) == 0)
+        obj = [bytes(handle)]
+        dist.broadcast_object_list(obj, src=dst)
+        if self.rank != dst:
+            hb = (C.c_uint8 * 64).from_buffer_copy(obj[0])
+            ok = int(self._lib.rc_ipc_open(self._ctx, hb, C.byref(self.base)) == 0)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        t = torch.tensor([ok], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        self.ok = int(t.item()) == 1
+        if not self.ok:
+            self.close()
+            raise RuntimeError("CUDA IPC peer mapping unavailable")
+
+    def ptr(self, offset_bytes: int = 0) -> int:
+        return self.base.value + offset_bytes
+
+    def fence(self):
+        torch.cuda.synchronize()
+        dist.barrier()
+
+    def read(self) -> np.ndarray:
+        assert self.rank == self.dst
+        host = np.empty(self.nbytes, np.uint8)
+        assert self._lib.rc_memcpy_d2h(self._ctx, host.ctypes.data, self.base, self.nbytes) == 0
+        return host
+
+    def close(self):
+        if getattr(self, "base", None) is not None and self.base.value:
+            if self.rank == self.dst:
+                self._lib.rc_device_free(self._ctx, self.base)
+            else:
+                self._lib.rc_ipc_close(self._ctx, self.base)
+            self.base = self._C.c_void_p()

@@ -368,6 +368,24 @@ class TLAS:
             return True, self.triangle_of(h), np.float32(h["t"]), np.array([w, u, v], np.float32), np.uint32(h["instance_id"] + 1)
         return False, empty_triangle(), np.float32(0), np.zeros(3, np.float32), np.uint32(0)
 
+    # -- collision broad phase (src/collision.jl) --------------------------------------------------
+    def collide_instances(self) -> np.ndarray:
+        """collide_instances(tlas) — src/collision.jl:189-233: uint32[total, 2] of 1-based (instance_a, instance_b), a < b."""
+        self.sync()
+        n = C.c_uint64()
+        self._ck(self._lib.rc_collide_instances(self._ctx, None, 0, C.byref(n)))
+        out = np.zeros((n.value, 2), np.uint32)
+        if n.value:
+            self._ck(self._lib.rc_collide_instances(self._ctx, out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+    def collide_instances_any(self, handle_a: TLASHandle, handle_b: TLASHandle) -> bool:
+        """collide_instances_any — src/collision.jl:241-261."""
+        self.sync()
+        o = C.c_int32()
+        self._ck(self._lib.rc_collide_instances_any(self._ctx, handle_a.id, handle_b.id, C.byref(o)))
+        return bool(o.value)
+
     # -- analysis (src/kernels.jl) --------------------------------------------------------------
     def hits_from_grid(self, viewdir, grid_size: int = 32):
         """hits_from_grid — :58-72: (hits[grid*grid], points[grid*grid,3]) in Julia column-major cell order."""

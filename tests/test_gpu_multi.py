@@ -28,10 +28,22 @@ def _worker(rank, world, port, out_path):
     tlas.sync()
     rays = np.concatenate([W.box_rays(100001, 1, half=8.0), W.interior_rays(100000, 2, radius=7.0)])
     full = sharding.trace_sharded(lambda r: tlas.trace_closest(r), rays, rc.HIT_DTYPE, device=torch.device("cuda", rank))
-    n = tlas.sizes()["blas_prims"]
+    # fused gather: every rank's kernel stores its slice of the hit records directly into rank 0's buffer (CUDA IPC peer pointer)
+    import ctypes as C
+
+    lo, hi = sharding.shard_range(len(rays), rank, world)
+    buf = sharding.PeerResultBuffer(tlas, len(rays) * 32)
+    d_rays = torch.from_numpy(rays[lo:hi].view(np.uint8).reshape(-1).copy()).cuda()
+    L = rc._lib
+    assert tlas._lib.rc_trace_closest(tlas._ctx, d_rays.data_ptr(), C.c_void_p(buf.ptr(lo * 32)), hi - lo, L.RC_RAYS_ON_DEVICE | L.RC_HITS_ON_DEVICE) == 0
+    buf.fence()
     if rank == 0:
         ref = tlas.trace_closest(rays)
-        open(out_path, "w").write("ok" if full.tobytes() == ref.tobytes() else "mismatch")
+        fused = buf.read().view(rc.HIT_DTYPE)
+        ok = full.tobytes() == ref.tobytes() and fused.tobytes() == ref.tobytes()
+        open(out_path, "w").write("ok" if ok else "mismatch")
+    dist.barrier()
+    buf.close()
     dist.barrier()
     dist.destroy_process_group()
 
