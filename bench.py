@@ -173,7 +173,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the view_factors (C4) measurement")
-    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"], help="N > 1: how hit records reach rank 0")
+    ap.add_argument("--gather", default="auto", choices=["auto", "fused", "peer-copy", "nccl"], help="N > 1: how hit records reach rank 0")
     ap.add_argument("--counters", action="store_true", help="extra instrumented pass (per-ray node/triangle counts) after the timed region")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -188,6 +188,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gather == "auto":
+        # measured on the 8 x B200 box (profiles/r1_scaling.md): in-kernel remote stores are free up to 4 ranks; at 8 ranks the 32-byte
+        # stores of 7 senders saturate rank 0's NVLink ingress, so the copy engines push whole buffers while the next step traces
+        args.gather = "fused" if world <= 4 else "peer-copy"
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
@@ -232,14 +236,17 @@ def main():
     gather_mode, gather_buf, hits_ptr, g_base = "none (1 GPU)", None, d_hits.data_ptr(), C.c_void_p()
     if world > 1:
         gather_mode = "nccl"
-        if args.gather == "fused":
+        if args.gather in ("fused", "peer-copy"):
             try:
                 from raycore_b200.sharding import PeerResultBuffer
 
                 peer = PeerResultBuffer(tlas, world * n * 32)
                 g_base = peer.base
-                gather_mode = "fused"
-                hits_ptr = peer.ptr(rank * n * 32)
+                gather_mode = args.gather
+                if gather_mode == "fused":
+                    hits_ptr = peer.ptr(rank * n * 32)
+                else:  # double-buffered local hit buffers, pushed to rank 0 by the copy engine while the next step traces
+                    d_hits2 = [d_hits, torch.empty_like(d_hits)]
             except Exception as e:  # pragma: no cover
                 print(f"[rank {rank}] fused gather unavailable ({e}); falling back to NCCL gather", file=sys.stderr)
         if gather_mode == "nccl" and rank == 0:
@@ -250,13 +257,24 @@ def main():
     assert stream.cuda_stream != 0 and lib.rc_set_stream(ctx, C.c_void_p(stream.cuda_stream)) == 0
     flags = L.RC_RAYS_ON_DEVICE | L.RC_HITS_ON_DEVICE | L.RC_NO_SYNC
 
+    step_no = [0]
+
     def step():
+        if gather_mode == "peer-copy":
+            b = step_no[0] & 1
+            step_no[0] += 1
+            assert lib.rc_stream_wait_copy(ctx, b) == 0
+            assert lib.rc_trace_closest(ctx, d_rays.data_ptr(), d_hits2[b].data_ptr(), n, flags) == 0, lib.rc_last_error(ctx)
+            assert lib.rc_peer_copy_async(ctx, C.c_void_p(peer.ptr(rank * n * 32)), d_hits2[b].data_ptr(), n * 32, b) == 0
+            return
         rc_ = lib.rc_trace_closest(ctx, d_rays.data_ptr(), hits_ptr, n, flags)
         assert rc_ == 0, lib.rc_last_error(ctx)
         if gather_mode == "nccl":
             dist.gather(d_hits, gather_buf, dst=0)  # results gathered by NCCL over NVLink
 
     def barrier():
+        if gather_mode == "peer-copy":
+            assert lib.rc_wait(ctx) == 0  # drains the copy stream too
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -288,7 +306,7 @@ def main():
         counts = [None] * world
         dist.all_gather_object(counts, local_hits)
         if rank == 0:
-            if gather_mode == "fused":
+            if gather_mode in ("fused", "peer-copy"):
                 host = np.empty(world * n * 32, np.uint8)
                 assert lib.rc_memcpy_d2h(ctx, host.ctypes.data, g_base, host.nbytes) == 0
                 got = [int(host.view(np.uint32).reshape(-1, 8)[r * n:(r + 1) * n, 0].sum()) for r in range(world)]
@@ -413,7 +431,7 @@ def main():
         "config": {
             "workload": f"C2: bumpy_sphere({TESS}) {len(verts)} faces -> {n_tris} triangles, 1 instance TLAS; per rank 2^{int(np.log2(n))} rays = diffuse-bounce (hemisphere about the geometric normal, from {PRIMARY_RES}^2 primary hits) interleaved with interior-origin uniform-direction rays",
             "rays_per_rank": n, "hit_rate": hit_rate, "primary_hit_rate": primary_hit_rate, "l2_policy": "inputs larger than L2 (512 MiB rays + 512 MiB hits per step)",
-            "gather": {"fused": "fused: each rank's traversal kernel stores its hit records straight into rank 0's buffer through CUDA-IPC peer pointers over NVLink (no separate collective)", "nccl": "dist.gather of hit records to rank 0 (NCCL) after every trace"}.get(gather_mode, gather_mode), "parallelism": f"bvh replicated, rays sharded x{world}",
+            "gather": {"fused": "fused: each rank's traversal kernel stores its hit records straight into rank 0's buffer through CUDA-IPC peer pointers over NVLink (no separate collective)", "peer-copy": "each rank traces into double-buffered local hit buffers; the copy engine pushes a finished buffer into rank 0's CUDA-IPC-mapped gather buffer over NVLink while the next step traces", "nccl": "dist.gather of hit records to rank 0 (NCCL) after every trace"}.get(gather_mode, gather_mode), "parallelism": f"bvh replicated, rays sharded x{world}",
         },
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps * 2, "clocks": clk.summary(), "extras": extras,
         "build": {"blas_build_ms_cuda_events": min(build_dev_ms), "blas_build_ms_wall_device_input": min(build_ms), "push_sync_ms_host_input": build_wall_ms, "triangles": n_tris},

@@ -226,6 +226,12 @@ int32_t rc_memcpy_d2h(rc_context *ctx, void *dst, const void *src, size_t bytes)
 int32_t rc_ipc_export(rc_context *ctx, void *ptr, uint8_t handle_out[64]);
 int32_t rc_ipc_open(rc_context *ctx, const uint8_t handle[64], void **out);
 int32_t rc_ipc_close(rc_context *ctx, void *ptr);
+/* copy-engine gather: enqueue a device-to-device copy (dst may be a peer pointer from rc_ipc_open) on the context's copy stream,
+ * ordered after the work already enqueued on the context stream; it overlaps with later traces.  slot (0/1) names the completion
+ * event; rc_stream_wait_copy(slot) makes the context stream wait for it (call before tracing into that source buffer again).
+ * rc_wait() drains the copy stream. */
+int32_t rc_peer_copy_async(rc_context *ctx, void *dst, const void *src, size_t bytes, uint32_t slot);
+int32_t rc_stream_wait_copy(rc_context *ctx, uint32_t slot);
 
 #ifdef __cplusplus
 }

@@ -72,7 +72,7 @@ EXPORTS = [
     "rc_hits_from_grid", "rc_get_illumination", "rc_get_centroid", "rc_view_factors", "rc_view_factor_rays", "rc_read_flat_metadata",
     "rc_collide_instances", "rc_collide_instances_any",
     "rc_device_alloc", "rc_device_free", "rc_host_alloc", "rc_host_free", "rc_memcpy_h2d", "rc_memcpy_d2h",
-    "rc_ipc_export", "rc_ipc_open", "rc_ipc_close",
+    "rc_ipc_export", "rc_ipc_open", "rc_ipc_close", "rc_peer_copy_async", "rc_stream_wait_copy",
 ]  # fmt: skip
 
 
@@ -151,6 +151,8 @@ def load():
         "rc_ipc_export": (i32, [vp, vp, vp]),
         "rc_ipc_open": (i32, [vp, vp, C.POINTER(vp)]),
         "rc_ipc_close": (i32, [vp, vp]),
+        "rc_peer_copy_async": (i32, [vp, vp, vp, C.c_size_t, u32]),
+        "rc_stream_wait_copy": (i32, [vp, u32]),
     }
     assert set(sig) == set(EXPORTS)
     for name, (res, args) in sig.items():

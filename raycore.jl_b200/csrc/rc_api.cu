@@ -47,6 +47,7 @@ struct rc_context {
     static const int NEV = 8;
     cudaEvent_t ev_h2d[NEV], ev_k[NEV], ev_t0 = nullptr, ev_t1 = nullptr;
     float last_ms = 0.f, last_build_ms = 0.f;
+    bool copy_pending[2] = {false, false};
     uint32_t last_launches = 0;
     int max_blocks = 148;
 };
@@ -847,6 +848,26 @@ int32_t rc_ipc_open(rc_context *ctx, const uint8_t handle[64], void **out) {
     RC_CUDA(ctx, cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
     return RC_OK;
 }
+// Copy-engine gather for N > 4 GPUs: push a finished hit buffer into (a slice of) a peer-mapped buffer on the copy stream,
+// ordered after everything already enqueued on the context stream, while the next trace runs.  slot selects one of two
+// completion events so a double-buffering caller can make the context stream wait before it overwrites that buffer again.
+int32_t rc_peer_copy_async(rc_context *ctx, void *dst, const void *src, size_t bytes, uint32_t slot) {
+    if (!ctx || !dst || !src || slot > 1) return RC_ERR_INVALID_ARGUMENT;
+    use_device(ctx);
+    RC_CUDA(ctx, cudaEventRecord(ctx->ev_k[slot], ctx->stream));
+    RC_CUDA(ctx, cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_k[slot], 0));
+    RC_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->s_d2h));
+    RC_CUDA(ctx, cudaEventRecord(ctx->ev_h2d[slot], ctx->s_d2h));
+    ctx->copy_pending[slot] = true;
+    return RC_OK;
+}
+int32_t rc_stream_wait_copy(rc_context *ctx, uint32_t slot) {
+    if (!ctx || slot > 1) return RC_ERR_INVALID_ARGUMENT;
+    use_device(ctx);
+    if (ctx->copy_pending[slot]) RC_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[slot], 0));
+    return RC_OK;
+}
+
 int32_t rc_ipc_close(rc_context *ctx, void *ptr) {
     if (!ctx) return RC_ERR_INVALID_ARGUMENT;
     use_device(ctx);
