@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -556,7 +557,7 @@ static int32_t trace_common(rc_context *ctx, const rc_ray *rays, rc_hit *hits, u
         if (rc != RC_OK) return rc;
         d_hits = ctx->d_hits;
     }
-    const uint64_t chunk = 1ull << 20;
+    static const uint64_t chunk = [] { const char *e = getenv("RC_HOST_CHUNK_RAYS"); uint64_t v = e ? strtoull(e, nullptr, 10) : 0; return v ? v : (1ull << 20); }();
     cudaEventRecord(ctx->ev_t0, ctx->stream);
     int c = 0;
     for (uint64_t off = 0; off < n; off += chunk, c++) {

@@ -499,47 +499,64 @@ void rc_free_blas(RcDeviceBlas *b, cudaStream_t st) {
     b->nodes2 = nullptr; b->nodes4 = nullptr; b->tris = nullptr; b->hull = nullptr; b->n = 0;
 }
 
+// Stream-ordered temporaries that are returned to the pool when the builder leaves scope (also on every error path).
+struct RcTemps {
+    cudaStream_t st;
+    std::vector<void *> ptrs;
+    explicit RcTemps(cudaStream_t s) : st(s) {}
+    ~RcTemps() {
+        for (void *p : ptrs) cudaFreeAsync(p, st);
+    }
+    template <class T>
+    bool get(T **out, size_t count, std::string &err) {
+        void *p = nullptr;
+        cudaError_t e = cudaMallocAsync(&p, sizeof(T) * (count ? count : 1), st);
+        if (e != cudaSuccess) { err = std::string("cudaMallocAsync: ") + cudaGetErrorString(e); return false; }
+        ptrs.push_back(p);
+        *out = static_cast<T *>(p);
+        return true;
+    }
+};
+#define TMP(ptr, count) \
+    if (!tmp.get(&(ptr), (count), err)) return false
+
 bool rc_build_blas(cudaStream_t st, const float *d_verts, const uint32_t *d_face_meta, uint32_t n_faces, RcDeviceBlas *out, std::string &err) {
     *out = RcDeviceBlas();
     if (n_faces == 0) { err = "Geometry has no valid triangles"; return false; }
     const int T = 256;
+    RcTemps tmp(st);
     uint32_t *d_flags = nullptr, *d_pos = nullptr, *d_tile = nullptr, *d_small = nullptr;
-    uint32_t tiles = cdiv(n_faces, SCAN_TILE);
-    CK(cudaMallocAsync(&d_flags, sizeof(uint32_t) * n_faces, st));
-    CK(cudaMallocAsync(&d_pos, sizeof(uint32_t) * n_faces, st));
-    CK(cudaMallocAsync(&d_tile, sizeof(uint32_t) * tiles, st));
-    CK(cudaMallocAsync(&d_small, sizeof(uint32_t) * 16, st));  // [0]=count, [4..9]=bounds(ordered), [10..15]=root box
+    TMP(d_flags, n_faces);
+    TMP(d_pos, n_faces);
+    TMP(d_tile, cdiv(n_faces, SCAN_TILE));
+    TMP(d_small, 16);  // [0] = valid count, [4..9] = scene bounds (ordered uints), [10..15] = root box
     k_face_flags<<<cdiv(n_faces, T), T, 0, st>>>(d_verts, n_faces, d_flags);
     exclusive_scan_u32(st, d_flags, d_pos, n_faces, d_tile, d_small);
     uint32_t n = 0;
     CK(cudaMemcpyAsync(&n, d_small, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    if (n == 0) {
-        cudaFreeAsync(d_flags, st); cudaFreeAsync(d_pos, st); cudaFreeAsync(d_tile, st); cudaFreeAsync(d_small, st);
-        err = "Geometry has no valid triangles";
-        return false;
-    }
+    if (n == 0) { err = "Geometry has no valid triangles"; return false; }  // src/instanced-bvh.jl:601
     if (n > RC_LEAF_START_MASK - 16u) { err = "BLAS too large (max 2^28 triangles)"; return false; }
     uint32_t *d_bounds = d_small + 4;
     RcTri *d_tris_in = nullptr;
     RcBox *d_tri_boxes = nullptr, *d_boxes = nullptr;
     uint32_t *d_codes = nullptr, *d_idx = nullptr, *d_codes2 = nullptr, *d_idx2 = nullptr, *d_hist = nullptr, *d_parent = nullptr, *d_fl = nullptr;
     RcTopo *d_topo = nullptr;
-    uint32_t rs_tiles = cdiv(n, RS_TILE);
-    CK(cudaMallocAsync(&d_tris_in, sizeof(RcTri) * n, st));
-    CK(cudaMallocAsync(&d_tri_boxes, sizeof(RcBox) * n, st));
-    CK(cudaMallocAsync(&d_codes, sizeof(uint32_t) * n, st));
-    CK(cudaMallocAsync(&d_idx, sizeof(uint32_t) * n, st));
-    CK(cudaMallocAsync(&d_codes2, sizeof(uint32_t) * n, st));
-    CK(cudaMallocAsync(&d_idx2, sizeof(uint32_t) * n, st));
-    CK(cudaMallocAsync(&d_hist, sizeof(uint32_t) * 256 * rs_tiles, st));
-    CK(cudaMallocAsync(&d_topo, sizeof(RcTopo) * std::max(1u, n - 1), st));
-    CK(cudaMallocAsync(&d_parent, sizeof(uint32_t) * (2 * n - 1), st));
-    CK(cudaMallocAsync(&d_fl, sizeof(uint32_t) * std::max(1u, n - 1), st));
-    CK(cudaMallocAsync(&d_boxes, sizeof(RcBox) * (2 * n - 1), st));
-    CK(cudaMallocAsync(&out->nodes2, sizeof(RcNode2) * (2 * n - 1), st));
-    CK(cudaMallocAsync(&out->nodes4, sizeof(RcNode4) * (n + 1), st));
-    CK(cudaMallocAsync(&out->tris, sizeof(RcTri) * n, st));
+    TMP(d_tris_in, n);
+    TMP(d_tri_boxes, n);
+    TMP(d_codes, n);
+    TMP(d_idx, n);
+    TMP(d_codes2, n);
+    TMP(d_idx2, n);
+    TMP(d_hist, 256 * (size_t)cdiv(n, RS_TILE));
+    TMP(d_topo, n - 1);
+    TMP(d_parent, 2 * (size_t)n - 1);
+    TMP(d_fl, n - 1);
+    TMP(d_boxes, 2 * (size_t)n - 1);
+    // the results outlive this call; on failure the caller releases them with rc_free_blas
+    CK(cudaMallocAsync(&out->nodes2, sizeof(RcNode2) * (2 * (size_t)n - 1), st));
+    CK(cudaMallocAsync(&out->nodes4, sizeof(RcNode4) * ((size_t)n + 1), st));
+    CK(cudaMallocAsync(&out->tris, sizeof(RcTri) * (size_t)n, st));
     CK(cudaMallocAsync(&out->hull, sizeof(RcBox) * RC_HULL_BOXES, st));
     out->n = n;
     out->n_faces_in = n_faces;
@@ -553,11 +570,7 @@ bool rc_build_blas(cudaStream_t st, const float *d_verts, const uint32_t *d_face
     k_blas_hull<<<1, 32, 0, st>>>(d_boxes, d_topo, n, out->hull);
     k_read_root<<<1, 32, 0, st>>>(d_boxes, reinterpret_cast<float *>(d_small + 10));
     CK(cudaMemcpyAsync(out->root_aabb, d_small + 10, 24, cudaMemcpyDeviceToHost, st));
-    for (void *p : {(void *)d_flags, (void *)d_pos, (void *)d_tile, (void *)d_tris_in, (void *)d_tri_boxes, (void *)d_codes, (void *)d_idx, (void *)d_codes2,
-                    (void *)d_idx2, (void *)d_hist, (void *)d_topo, (void *)d_parent, (void *)d_fl, (void *)d_boxes})
-        cudaFreeAsync(p, st);
     CK(cudaStreamSynchronize(st));
-    cudaFreeAsync(d_small, st);
     CK(cudaGetLastError());
     return true;
 }
@@ -654,6 +667,7 @@ bool rc_build_tlas(cudaStream_t st, const rc_instance_desc *h_inst, uint32_t n, 
     uint32_t nb = (uint32_t)blas.size();
     uint32_t rs_tiles = cdiv(n, RS_TILE);
     uint32_t *d_codes = nullptr, *d_codes2 = nullptr, *d_idx2 = nullptr, *d_hist = nullptr;
+    RcTemps tmp(st);
     CK(cudaMallocAsync(&t->d_inst, sizeof(rc_instance_desc) * n, st));
     CK(cudaMallocAsync(&t->d_blas_roots, sizeof(float) * 6 * nb, st));
     CK(cudaMallocAsync(&t->d_blas_ptrs, sizeof(RcBlasPtrs) * nb, st));
@@ -670,10 +684,10 @@ bool rc_build_tlas(cudaStream_t st, const rc_instance_desc *h_inst, uint32_t n, 
     CK(cudaMallocAsync(&t->nodes2, sizeof(RcNode2) * (2 * n - 1), st));
     CK(cudaMallocAsync(&t->nodes4, sizeof(RcNode4) * (n + 1), st));
     CK(cudaMallocAsync(&t->d_small, sizeof(uint32_t) * 16, st));
-    CK(cudaMallocAsync(&d_codes, sizeof(uint32_t) * n, st));
-    CK(cudaMallocAsync(&d_codes2, sizeof(uint32_t) * n, st));
-    CK(cudaMallocAsync(&d_idx2, sizeof(uint32_t) * n, st));
-    CK(cudaMallocAsync(&d_hist, sizeof(uint32_t) * 256 * rs_tiles, st));
+    TMP(d_codes, n);
+    TMP(d_codes2, n);
+    TMP(d_idx2, n);
+    TMP(d_hist, 256 * (size_t)rs_tiles);
     CK(cudaMemcpyAsync(t->d_blas_roots, blas_roots.data(), sizeof(float) * 6 * nb, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(t->d_blas_ptrs, blas.data(), sizeof(RcBlasPtrs) * nb, cudaMemcpyHostToDevice, st));
     if (!upload_instances(st, t, h_inst, n, err)) return false;
@@ -686,7 +700,6 @@ bool rc_build_tlas(cudaStream_t st, const rc_instance_desc *h_inst, uint32_t n, 
                t->boxes_tight);
     k_read_root<<<1, 32, 0, st>>>(t->boxes, reinterpret_cast<float *>(t->d_small + 10));
     CK(cudaMemcpyAsync(t->root_aabb, t->d_small + 10, 24, cudaMemcpyDeviceToHost, st));
-    for (void *p : {(void *)d_codes, (void *)d_codes2, (void *)d_idx2, (void *)d_hist}) cudaFreeAsync(p, st);
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     return true;
