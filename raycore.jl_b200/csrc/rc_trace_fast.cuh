@@ -14,10 +14,10 @@
 // Refills are warp-cooperative (one atomic on the global work counter per refill) and deferred until RC_FETCH_MIN
 // lanes are idle, so the refill / retire code also runs with many lanes.
 //
-// Arithmetic: two child planes are decoded per PRMT into a half2 (0x6400 | q = 1024 + q exactly), widened with
+// Arithmetic: two child planes are decoded per PRMT into a half2 of subnormals (0x00qq = q * 2^-24 exactly), widened with
 // HADD2.F32 on the FMA pipe (no I2F: the XU pipe saturated in profiles/r1_v1; the ALU pipe is the limiter since v4),
-// and fed to one FMA against per-node (scale * inv_d, (origin - o) * inv_d - 1024 * scale * inv_d); an explicit
-// rounding bound keeps the slab test conservative.  The triangle test is the exact, FMA-free Moeller-Trumbore of
+// and fed to one FMA against per-node (2^24 * scale * inv_d, (origin - o) * inv_d); an explicit rounding bound keeps the
+// slab test conservative.  The triangle test is the exact, FMA-free Moeller-Trumbore of
 // rc_device.cuh, so t/u/v are bit-identical to the reference evaluation whenever the same triangle wins.
 // The traversal stack lives in shared memory ([depth][thread], conflict-free); pushes are branch-free (a rejected
 // child is written to a dummy row); rays that would need more than RC_SSTACK entries are flagged and re-traced by
@@ -70,9 +70,9 @@ __device__ __forceinline__ float rc_fast_inv(float d) {
     asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-// bound on the relative error of the slab evaluation: reciprocal (1 ulp), two roundings of (origin - o) * inv,
-// the 1024 * a bias folded into b (2^-14 of a cell), one FMA
-#define RC_BOX_EPS_FAST 7.2e-7f
+// bound on the relative error of the slab evaluation: reciprocal (1 ulp), two roundings of (origin - o) * inv, one rounding of
+// the scale product, one FMA
+#define RC_BOX_EPS_FAST 4.8e-7f  // 2^-21
 
 // 32-byte read-only load (LDG.E.256.CONSTANT on sm_100a): a 64-B wide node is two of these instead of four LDG.128,
 // halving the L1 wavefronts per node step (LSU wavefronts were 70 % of peak in profiles/r1_v6)
@@ -82,9 +82,11 @@ __device__ __forceinline__ void rc_ldg256(const void *p, float4 &a, float4 &b) {
                  : "l"(p));
 }
 
-// bytes (2j, 2j+1) of w -> two floats 1024 + q (exact)
+// bytes (2j, 2j+1) of w -> two floats q * 2^-24 (exact): each byte becomes the mantissa of a subnormal fp16 (0x00qq), which
+// HADD2.F32 widens exactly; the 2^24 factor is folded into the per-node slab scale.  One PRMT with immediate selector and RZ per
+// pair — no magic-constant register (the 0x6400 bias form cost an extra register move per PRMT, profiles/r1_v7).
 __device__ __forceinline__ float2 rc_q2f_pair(uint32_t w, int j) {
-    const uint32_t h = __byte_perm(w, 0x64646464u, j == 0 ? 0x4140u : 0x4342u);
+    const uint32_t h = __byte_perm(w, 0u, j == 0 ? 0x4140u : 0x4342u);
     return __half22float2(*reinterpret_cast<const __half2 *>(&h));
 }
 
@@ -237,11 +239,12 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, RC_MIN_BLOCKS) k_trace_wide(
                 rc_ldg256(np + 32, n2, n3);
                 if (COUNT) { lc.nodes++; lc.box_tests += 4; }
                 const uint32_t e = __float_as_uint(n0.w);
-                const float ax = __uint_as_float((e & 0xFFu) << 23) * inv.x, ay = __uint_as_float(((e >> 8) & 0xFFu) << 23) * inv.y,
-                            az = __uint_as_float(((e >> 16) & 0xFFu) << 23) * inv.z;
-                const float b0x = (n0.x - o.x) * inv.x, b0y = (n0.y - o.y) * inv.y, b0z = (n0.z - o.z) * inv.z;
-                const float slack = RC_BOX_EPS_FAST * fmaxf(fmaxf(fmaf(255.0f, fabsf(ax), fabsf(b0x)), fmaf(255.0f, fabsf(ay), fabsf(b0y))), fmaf(255.0f, fabsf(az), fabsf(b0z)));
-                const float bx = fmaf(-1024.0f, ax, b0x), by = fmaf(-1024.0f, ay, b0y), bz = fmaf(-1024.0f, az, b0z);  // decoded planes carry +1024
+                // a = 2^24 * scale * inv_d (decoded planes carry 2^-24), b = (origin - o) * inv_d
+                const float ax = __uint_as_float((e & 0xFFu) << 23) * (inv.x * 16777216.0f), ay = __uint_as_float(((e >> 8) & 0xFFu) << 23) * (inv.y * 16777216.0f),
+                            az = __uint_as_float(((e >> 16) & 0xFFu) << 23) * (inv.z * 16777216.0f);
+                const float bx = (n0.x - o.x) * inv.x, by = (n0.y - o.y) * inv.y, bz = (n0.z - o.z) * inv.z;
+                const float kq = 255.0f / 16777216.0f;
+                const float slack = RC_BOX_EPS_FAST * fmaxf(fmaxf(fmaf(kq, fabsf(ax), fabsf(bx)), fmaf(kq, fabsf(ay), fabsf(by))), fmaf(kq, fabsf(az), fabsf(bz)));
                 const uint32_t qlox = __float_as_uint(n1.x), qloy = __float_as_uint(n1.y), qloz = __float_as_uint(n1.z), qhix = __float_as_uint(n1.w);
                 const uint32_t qhiy = __float_as_uint(n2.x), qhiz = __float_as_uint(n2.y);
                 const uint32_t r0 = __float_as_uint(n2.z), r1 = __float_as_uint(n2.w), r2 = __float_as_uint(n3.x), r3 = __float_as_uint(n3.y);
