@@ -141,7 +141,7 @@ RC_HD RcNode4 rc_collapse_node(uint32_t idx, const RcBox *boxes, const RcTopo *t
         uint32_t cnt = count_of(c);
         if (c >= n) {
             uint32_t pos = c - n;  // 0-based sorted position
-            ch[k] = RC_LEAF_BIT | (leaf_map ? leaf_map[pos] : pos);
+            ch[k] = leaf_map ? (RC_TLAS_LEAF_TAG | leaf_map[pos]) : (RC_LEAF_BIT | pos);
         } else if (cnt <= leaf_max) {
             uint32_t pos = topo[c - 1].span_lo - 1u;
             ch[k] = RC_LEAF_BIT | ((cnt - 1u) << RC_LEAF_COUNT_SHIFT) | (leaf_map ? leaf_map[pos] : pos);

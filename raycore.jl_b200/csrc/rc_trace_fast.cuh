@@ -56,7 +56,7 @@ __device__ __forceinline__ void rc_store_hit(rc_hit *hits, unsigned long long i,
 #define RC_SSTACK 32       // stack entries per lane (shared memory, [depth][thread]); row RC_SSTACK is the dummy row
 #endif
 #define RC_OVERFLOW_MARK 0xFFFFFFFFu  // rc_hit.hit of a ray whose short stack overflowed (re-traced by k_trace_fixup)
-#define RC_DEADLANE 0xFFFFFFFDu
+#define RC_DEADLANE 0xFFFFFFFEu
 
 #define RC_VOTE_N 0x00000001u
 #define RC_VOTE_T 0x00000100u
@@ -94,7 +94,8 @@ template <bool ANY, bool COUNT>
 __global__ void __launch_bounds__(RC_TRACE_THREADS, RC_MIN_BLOCKS) k_trace_wide(RcScene sc, const rc_ray *__restrict__ rays, rc_hit *__restrict__ hits, unsigned long long n,
                                                                  unsigned long long *__restrict__ work, RcCounters *__restrict__ counters,
                                                                  uint32_t *__restrict__ overflow) {
-    __shared__ uint32_t sstack[(RC_SSTACK + 1) * RC_TRACE_THREADS];
+    // rows: 0 guard (always RC_INVALID), 1..RC_SSTACK live entries, +3 overflow scratch, last = dummy row for rejected pushes
+    __shared__ uint32_t sstack[(RC_SSTACK + 5) * RC_TRACE_THREADS];
     const uint32_t FULL = 0xFFFFFFFFu;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, lt_mask = (1u << lane) - 1u;
     RcLocalCounters lc = {0, 0, 0, 0, 0};
@@ -108,28 +109,29 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, RC_MIN_BLOCKS) k_trace_wide(
     uint32_t cur = RC_INVALID, leaf = 0, leaf_k = 0, vote = RC_VOTE_F;
     bool have = false, ovf = false;
 
-    // branch-free conditional push: a rejected (or overflowing) entry lands in the dummy row
-#define RC_PUSH_IF(cond, v)                                                             \
-    {                                                                                   \
-        const int row_ = (cond) ? min(sp, RC_SSTACK) : RC_SSTACK;                       \
-        sstack[row_ * RC_TRACE_THREADS + tid] = (v);                                    \
-        sp += (cond) ? 1 : 0;                                                           \
+    // branch-free conditional push: a rejected entry lands in the dummy row.  Row sp holds the top of the stack; the guard row 0
+    // makes the speculative read of an empty stack harmless, so neither push nor pop needs a clamp.
+#define RC_PUSH_IF(cond, v)                                                  \
+    {                                                                        \
+        const int row_ = (cond) ? sp + 1 : RC_SSTACK + 4;                    \
+        sstack[row_ * RC_TRACE_THREADS + tid] = (v);                         \
+        sp += (cond) ? 1 : 0;                                                \
     }
-#define RC_TOP() (sstack[min(max(sp - 1, 0), RC_SSTACK) * RC_TRACE_THREADS + tid])
+#define RC_TOP() (sstack[sp * RC_TRACE_THREADS + tid])
     // after a step: park a freshly reached BLAS leaf (so the lane can keep descending) and recompute the lane's vote
-#define RC_SETTLE()                                                                                                       \
-    {                                                                                                                     \
-        if (sp > RC_SSTACK) { ovf = true; cur = RC_INVALID; leaf = 0; sp = 0; }                                           \
-        const bool park_ = cur_inst >= 0 && (cur & RC_LEAF_BIT) && cur < RC_DEADLANE && leaf == 0;                        \
-        const uint32_t top_ = RC_TOP();                                                                                   \
-        leaf = park_ ? cur : leaf;                                                                                        \
-        leaf_k = park_ ? 0u : leaf_k;                                                                                     \
-        cur = park_ ? top_ : cur;                                                                                         \
-        sp -= park_ ? 1 : 0;                                                                                              \
-        vote = (cur & RC_LEAF_BIT) ? 0u : RC_VOTE_N;                                                                      \
-        if (leaf) vote |= RC_VOTE_T;                                                                                      \
-        else if (cur == RC_INVALID) vote |= RC_VOTE_F;                                                                    \
-        if ((cur_inst < 0 && (cur & RC_LEAF_BIT) && cur < RC_DEADLANE) || (cur == RC_SENTINEL && leaf == 0)) vote |= RC_VOTE_X; \
+#define RC_SETTLE()                                                                                                \
+    {                                                                                                              \
+        if (sp > RC_SSTACK) { ovf = true; cur = RC_INVALID; leaf = 0; sp = 0; }                                    \
+        const bool park_ = ((cur ^ RC_LEAF_BIT) < 0x40000000u) && leaf == 0; /* BLAS leaf reference */              \
+        const uint32_t top_ = RC_TOP();                                                                            \
+        leaf = park_ ? cur : leaf;                                                                                 \
+        leaf_k = park_ ? 0u : leaf_k;                                                                              \
+        cur = park_ ? top_ : cur;                                                                                  \
+        sp -= park_ ? 1 : 0;                                                                                       \
+        vote = ((int)cur >= 0) ? RC_VOTE_N : 0u;                                                                   \
+        vote |= leaf ? RC_VOTE_T : ((cur == RC_INVALID) ? RC_VOTE_F : 0u);                                         \
+        /* level change: instance leaf or sentinel = [0xC0000000, 0xF0000000); the sentinel waits for the parked leaf */ \
+        vote |= (((cur + 0x40000000u) < 0x30000000u) && !(cur == RC_SENTINEL && leaf != 0)) ? RC_VOTE_X : 0u;      \
     }
 
     for (;;) {
@@ -170,7 +172,8 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, RC_MIN_BLOCKS) k_trace_wide(
                     inv = mk3(rc_fast_inv(d.x), rc_fast_inv(d.y), rc_fast_inv(d.z));
                     cur_inst = -1; best_inst = -1; ovf = false;
                     nodes = sc.tlas4;
-                    sstack[tid] = RC_INVALID;
+                    sstack[tid] = RC_INVALID;                     // guard row
+                    sstack[RC_TRACE_THREADS + tid] = RC_INVALID;  // stack bottom: popping it ends the ray
                     sp = 1;
                     cur = 1;
                     leaf = 0;

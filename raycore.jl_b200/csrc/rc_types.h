@@ -8,8 +8,10 @@
 #include "../../include/raycore_cuda.h"
 
 #define RC_INVALID 0xFFFFFFFFu       // INVALID_NODE, src/instanced-bvh.jl:65
-#define RC_SENTINEL 0xFFFFFFFEu      // TOP_LEVEL_SENTINEL, src/instanced-bvh.jl:1733
+#define RC_SENTINEL 0xEFFFFFFFu      // TOP_LEVEL_SENTINEL (src/instanced-bvh.jl:1733 uses 0xFFFFFFFE; the value is internal to the stack)
 #define RC_LEAF_BIT 0x80000000u      // wide-node child reference: leaf flag
+#define RC_TLAS_LEAF_TAG 0xC0000000u // TLAS leaves carry bit 30 too, so a reference alone tells "triangles" [0x8..,0xC..) from
+                                     // "change level" [0xC.., 0xF..) (instance leaf or RC_SENTINEL) without consulting the traversal level
 #define RC_LEAF_COUNT_SHIFT 28       // bits 30..28: triangle count - 1
 #define RC_LEAF_START_MASK 0x0FFFFFFFu
 #ifndef RC_BLAS_LEAF_MAX
