@@ -197,8 +197,10 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, RC_MIN_BLOCKS) k_trace_wide(
                     hit_u = u; hit_v = v;
                     if (ANY) { cur = RC_INVALID; sp = 0; leaf_k = count; }
                 }
-                if (++leaf_k >= count) leaf = 0;
-                RC_SETTLE()
+                if (++leaf_k >= count) {
+                    leaf = 0;
+                    RC_SETTLE()  // the vote can only change when the parked leaf is exhausted
+                }
             }
         } else if (nX > nN) {
             // ---- X: enter an instance (TLAS leaf) or return to the TLAS (sentinel) -------------------------------------------
