@@ -7,6 +7,7 @@
 
 #include "rc_trace.h"
 #include "rc_trace_core.cuh"
+#include "rc_trace_fast.cuh"
 
 // ------------------------------------------------------------------------------------------------ grid
 // Host-side restatement of generate_ray_grid's frame (src/kernels.jl:10-47).  Float32 arithmetic in the
@@ -120,7 +121,7 @@ void rc_launch_grid_trace(cudaStream_t st, const RcScene &sc, const RcGridFrame 
 // One ray of view_factors! (src/kernels.jl:84-92) for source triangle `tri`: random_triangle_point (math.jl:158-174),
 // origin offset 0.01*normal (:91), random_hemisphere_uniform (math.jl:125-141), frame from get_orthogonal_basis (:143-156).
 // Randomness: counter RNG keyed by (seed, ray_index, dim) since Julia's task-local rand() is not reproducible.
-__device__ __forceinline__ rc_ray vf_make_ray(const RcTri *tri, unsigned long long seed, unsigned long long ray_index) {
+__device__ __noinline__ rc_ray vf_make_ray(const RcTri *tri, unsigned long long seed, unsigned long long ray_index) {
     f3 p1 = mk3(tri->v0[0], tri->v0[1], tri->v0[2]), p2 = mk3(tri->v1[0], tri->v1[1], tri->v1[2]), p3 = mk3(tri->v2[0], tri->v2[1], tri->v2[2]);
     f3 normal = x_normalize(x_cross(x_sub3(p2, p1), x_sub3(p3, p1)));  // GB.orthogonal_vector ∝ (v2-v1)x(v3-v1)
     f3 n = x_normalize(normal);
@@ -162,37 +163,70 @@ __device__ __forceinline__ const RcTri *flat_tri(const RcFlatBlas *flat, uint32_
     return flat[b].tris + (pos - flat[b].offset);
 }
 
-__global__ void __launch_bounds__(RC_TRACE_THREADS) k_view_factors(RcScene sc, const RcFlatBlas *__restrict__ flat, uint32_t n_blas, uint32_t n_prims, uint32_t rpt,
-                                                                   unsigned long long seed, uint32_t row_base, uint32_t n_rows, uint32_t n_cols, uint32_t *__restrict__ out,
-                                                                   rc_ray *__restrict__ rays_out, unsigned long long *__restrict__ skipped, uint32_t *__restrict__ overflow) {
+// Ray source / hit sink that turns the scheduler kernel into view_factors! (src/kernels.jl:80-104): "ray" g is ray g % rpt of the
+// flat primitive g / rpt; it is generated on the fly in the refill step, and its result is one atomicAdd into the matrix block.
+struct RcIoViewFactors {
+    RcScene sc;
+    const RcFlatBlas *flat;
+    uint32_t n_blas, rpt, row_base, n_rows, n_cols;
+    unsigned long long seed;
+    uint32_t *out;
+    unsigned long long *skipped;
+    uint32_t *overflow;
+    __device__ __forceinline__ rc_ray load(unsigned long long g) const {
+        const uint32_t pos = (uint32_t)(g / rpt), i = (uint32_t)(g % rpt);
+        const RcTri *tri = flat_tri(flat, n_blas, pos);
+        const uint32_t meta = tri->metadata;
+        const uint32_t row = meta - 1u;
+        if (meta < 1u || meta > n_cols || row < row_base || row >= row_base + n_rows) {
+            if (i == 0 && skipped && row_base == 0 && (meta < 1u || meta > n_cols)) atomicAdd(skipped, 1ull);  // reference: unchecked index (:85,95-97)
+            rc_ray r;  // a ray no box can accept: retires after the TLAS root
+            r.origin[0] = r.origin[1] = r.origin[2] = 0.f; r.dir[0] = 1.f; r.dir[1] = r.dir[2] = 0.f; r.tmin = 1.f; r.tmax = -1.f;
+            return r;
+        }
+        return vf_make_ray(tri, seed, (unsigned long long)row * rpt + i);
+    }
+    __device__ __forceinline__ void store(unsigned long long g, rc_hit h) const {
+        const uint32_t pos = (uint32_t)(g / rpt);
+        const RcTri *tri = flat_tri(flat, n_blas, pos);
+        const uint32_t meta = tri->metadata, row = meta - 1u;
+        if (meta < 1u || meta > n_cols || row < row_base || row >= row_base + n_rows) return;
+        if (h.hit == RC_OVERFLOW_MARK) {  // short stack overflowed: redo this ray with the deep-stack generic body
+            rc_ray r = vf_make_ray(tri, seed, (unsigned long long)row * rpt + (uint32_t)(g % rpt));
+            if (!rc_trace_wide<false, false>(sc, r, h, nullptr)) atomicAdd(overflow, 1u);
+        }
+        if (h.hit && h.metadata != meta && h.metadata >= 1u && h.metadata <= n_cols) atomicAdd(&out[(size_t)(row - row_base) * n_cols + (h.metadata - 1u)], 1u);
+    }
+};
+
+// the generated rays themselves (tests: the oracle traces exactly these)
+__global__ void k_view_factor_rays(const RcFlatBlas *__restrict__ flat, uint32_t n_blas, uint32_t n_prims, uint32_t rpt, unsigned long long seed, uint32_t row_base,
+                                   uint32_t n_rows, uint32_t n_cols, rc_ray *__restrict__ rays_out) {
     unsigned long long total = (unsigned long long)n_prims * rpt;
     for (unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (unsigned long long)gridDim.x * blockDim.x) {
-        uint32_t pos = (uint32_t)(g / rpt), i = (uint32_t)(g % rpt);
+        const uint32_t pos = (uint32_t)(g / rpt), i = (uint32_t)(g % rpt);
         const RcTri *tri = flat_tri(flat, n_blas, pos);
-        uint32_t meta = tri->metadata;
-        if (meta < 1 || meta > n_cols) {  // the reference indexes result[meta, ...] unchecked (:85,95-97)
-            if (i == 0 && skipped && row_base == 0) atomicAdd(skipped, 1ull);
-            continue;
-        }
-        uint32_t row = meta - 1;
-        if (row < row_base || row >= row_base + n_rows) continue;
-        rc_ray r = vf_make_ray(tri, seed, (unsigned long long)row * rpt + i);
-        if (rays_out) { rays_out[(size_t)(row - row_base) * rpt + i] = r; continue; }
-        rc_hit h;
-        if (!rc_trace_wide<false, false>(sc, r, h, nullptr)) atomicAdd(overflow, 1u);
-        if (h.hit && h.metadata != meta && h.metadata >= 1 && h.metadata <= n_cols)
-            atomicAdd(&out[(size_t)(row - row_base) * n_cols + (h.metadata - 1)], 1u);
+        const uint32_t meta = tri->metadata, row = meta - 1u;
+        if (meta < 1u || meta > n_cols || row < row_base || row >= row_base + n_rows) continue;
+        rays_out[(size_t)(row - row_base) * rpt + i] = vf_make_ray(tri, seed, (unsigned long long)row * rpt + i);
     }
 }
 
 void rc_launch_view_factors(cudaStream_t st, const RcScene &sc, const RcFlatBlas *d_flat, uint32_t n_blas, uint32_t n_prims, uint32_t rpt, unsigned long long seed,
                             uint32_t row_base, uint32_t n_rows, uint32_t n_cols, uint32_t *out, rc_ray *rays_out, unsigned long long *skipped,
-                            uint32_t *overflow, int max_blocks) {
+                            uint32_t *overflow, int max_blocks, unsigned long long *work) {
     unsigned long long total = (unsigned long long)n_prims * rpt;
     if (total == 0) return;
     unsigned long long want = (total + RC_TRACE_THREADS - 1) / RC_TRACE_THREADS;
     int blocks = (int)(want < (unsigned long long)max_blocks ? want : (unsigned long long)max_blocks);
-    k_view_factors<<<blocks, RC_TRACE_THREADS, 0, st>>>(sc, d_flat, n_blas, n_prims, rpt, seed, row_base, n_rows, n_cols, out, rays_out, skipped, overflow);
+    if (rays_out) {
+        k_view_factor_rays<<<blocks, RC_TRACE_THREADS, 0, st>>>(d_flat, n_blas, n_prims, rpt, seed, row_base, n_rows, n_cols, rays_out);
+        return;
+    }
+    if (sc.n_instances == 0) return;  // nothing to hit: the zeroed matrix is the answer
+    RcIoViewFactors io{sc, d_flat, n_blas, rpt, row_base, n_rows, n_cols, seed, out, skipped, overflow};
+    cudaMemsetAsync(work, 0, sizeof(unsigned long long), st);
+    k_trace_wide<false, false, RcIoViewFactors><<<blocks, RC_TRACE_THREADS, 0, st>>>(sc, io, total, work, nullptr, overflow + 1);
 }
 
 __global__ void k_flat_metadata(const RcFlatBlas *__restrict__ flat, uint32_t n_blas, uint32_t n_prims, uint32_t *__restrict__ out) {

@@ -689,7 +689,7 @@ int32_t rc_view_factors(rc_context *ctx, uint32_t rays_per_triangle, uint64_t se
     RC_CUDA(ctx, cudaMemsetAsync(d_skipped, 0, 8, ctx->stream));
     cudaEventRecord(ctx->ev_t0, ctx->stream);
     rc_launch_view_factors(ctx->stream, make_scene(ctx), ctx->d_flat, ctx->n_flat_blas, ctx->n_flat_prims, rays_per_triangle, seed, row_base, n_rows, n_cols, d_out,
-                           nullptr, d_skipped, ctx->d_overflow + 1, ctx->max_blocks);
+                           nullptr, d_skipped, ctx->d_overflow + 1, ctx->max_blocks, ctx->d_work);
     cudaEventRecord(ctx->ev_t1, ctx->stream);
     ctx->last_launches = 1;
     unsigned long long sk = 0;
@@ -717,7 +717,7 @@ int32_t rc_view_factor_rays(rc_context *ctx, uint32_t rays_per_triangle, uint64_
     RC_CUDA(ctx, cudaMallocAsync(&d_rays, n * sizeof(rc_ray), ctx->stream));
     RC_CUDA(ctx, cudaMemsetAsync(d_rays, 0, n * sizeof(rc_ray), ctx->stream));
     rc_launch_view_factors(ctx->stream, make_scene(ctx), ctx->d_flat, ctx->n_flat_blas, ctx->n_flat_prims, rays_per_triangle, seed, row_base, n_rows, ctx->n_flat_prims,
-                           nullptr, d_rays, nullptr, ctx->d_overflow + 1, ctx->max_blocks);
+                           nullptr, d_rays, nullptr, ctx->d_overflow + 1, ctx->max_blocks, ctx->d_work);
     RC_CUDA(ctx, cudaMemcpyAsync(out, d_rays, n * sizeof(rc_ray), cudaMemcpyDeviceToHost, ctx->stream));
     cudaFreeAsync(d_rays, ctx->stream);
     RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

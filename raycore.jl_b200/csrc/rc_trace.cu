@@ -71,14 +71,16 @@ bool rc_launch_trace(cudaStream_t st, const RcTraceLaunch &L, std::string &err) 
         int blocks = (int)(want < (unsigned long long)L.max_blocks ? want : (unsigned long long)L.max_blocks);
         if (blocks < 1) blocks = 1;
 #define RC_ARGS L.scene, L.rays, L.hits, L.n, L.work, L.counters, L.overflow
+#define RC_WARGS L.scene, RcIoArrays{L.rays, L.hits}, L.n, L.work, L.counters, L.overflow
         if (L.wide) {
-            if (L.any) { if (L.count) k_trace_wide<true, true><<<blocks, RC_TRACE_THREADS, 0, st>>>(RC_ARGS); else k_trace_wide<true, false><<<blocks, RC_TRACE_THREADS, 0, st>>>(RC_ARGS); }
-            else { if (L.count) k_trace_wide<false, true><<<blocks, RC_TRACE_THREADS, 0, st>>>(RC_ARGS); else k_trace_wide<false, false><<<blocks, RC_TRACE_THREADS, 0, st>>>(RC_ARGS); }
+            if (L.any) { if (L.count) k_trace_wide<true, true, RcIoArrays><<<blocks, RC_TRACE_THREADS, 0, st>>>(RC_WARGS); else k_trace_wide<true, false, RcIoArrays><<<blocks, RC_TRACE_THREADS, 0, st>>>(RC_WARGS); }
+            else { if (L.count) k_trace_wide<false, true, RcIoArrays><<<blocks, RC_TRACE_THREADS, 0, st>>>(RC_WARGS); else k_trace_wide<false, false, RcIoArrays><<<blocks, RC_TRACE_THREADS, 0, st>>>(RC_WARGS); }
         } else {
             if (L.any) { if (L.count) k_trace<true, true><<<blocks, RC_TRACE_THREADS, 0, st>>>(RC_ARGS); else k_trace<true, false><<<blocks, RC_TRACE_THREADS, 0, st>>>(RC_ARGS); }
             else { if (L.count) k_trace<false, true><<<blocks, RC_TRACE_THREADS, 0, st>>>(RC_ARGS); else k_trace<false, false><<<blocks, RC_TRACE_THREADS, 0, st>>>(RC_ARGS); }
         }
 #undef RC_ARGS
+#undef RC_WARGS
         if (L.wide) {
             if (L.any) k_trace_fixup<true><<<blocks, RC_TRACE_THREADS, 0, st>>>(L.scene, L.rays, L.hits, L.n, L.overflow);
             else k_trace_fixup<false><<<blocks, RC_TRACE_THREADS, 0, st>>>(L.scene, L.rays, L.hits, L.n, L.overflow);
@@ -92,7 +94,7 @@ bool rc_launch_trace(cudaStream_t st, const RcTraceLaunch &L, std::string &err) 
 int rc_trace_max_blocks(int device) {
     int sms = 148, per_sm = 1;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace_wide<false, false>, RC_TRACE_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace_wide<false, false, RcIoArrays>, RC_TRACE_THREADS, 0);
     if (per_sm < 1) per_sm = 1;
     return sms * per_sm;
 }

@@ -90,8 +90,18 @@ __device__ __forceinline__ float2 rc_q2f_pair(uint32_t w, int j) {
     return __half22float2(*reinterpret_cast<const __half2 *>(&h));
 }
 
-template <bool ANY, bool COUNT>
-__global__ void __launch_bounds__(RC_TRACE_THREADS, RC_MIN_BLOCKS) k_trace_wide(RcScene sc, const rc_ray *__restrict__ rays, rc_hit *__restrict__ hits, unsigned long long n,
+// Ray source / hit sink of the batched entry points: RTRay array in, RTHitResult array out.
+struct RcIoArrays {
+    const rc_ray *rays;
+    rc_hit *hits;
+    __device__ __forceinline__ rc_ray load(unsigned long long i) const { return rc_load_ray(rays, i); }
+    __device__ __forceinline__ void store(unsigned long long i, const rc_hit &h) const { rc_store_hit(hits, i, h); }
+};
+
+// IO: where ray i comes from and where its result goes (RcIoArrays for rc_trace_*; rc_analysis.cu plugs in an on-the-fly
+// view-factor ray generator + matrix accumulator, so the analysis kernels run on the same scheduler).
+template <bool ANY, bool COUNT, class IO>
+__global__ void __launch_bounds__(RC_TRACE_THREADS, RC_MIN_BLOCKS) k_trace_wide(RcScene sc, IO io, unsigned long long n,
                                                                  unsigned long long *__restrict__ work, RcCounters *__restrict__ counters,
                                                                  uint32_t *__restrict__ overflow) {
     // rows: 0 guard (always RC_INVALID), 1..RC_SSTACK live entries, +3 overflow scratch, last = dummy row for rejected pushes
@@ -151,7 +161,7 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, RC_MIN_BLOCKS) k_trace_wide(
                     rc_write_miss(h);
                 }
                 if (ovf) { rc_write_miss(h); h.hit = RC_OVERFLOW_MARK; atomicAdd(overflow, 1u); }
-                rc_store_hit(hits, idx, h);
+                io.store(idx, h);
                 traced++;
                 have = false;
             }
@@ -165,7 +175,7 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, RC_MIN_BLOCKS) k_trace_wide(
                     cur = RC_DEADLANE;
                     vote = 0;
                 } else {
-                    rc_ray r = rc_load_ray(rays, idx);
+                    rc_ray r = io.load(idx);
                     RcRayIn w = rc_prepare_ray(r, ANY);
                     wo = w.o; wd = w.d; o = wo; d = wd;
                     t_min = w.t_min; t_max = w.t_max;
