@@ -214,6 +214,38 @@ int32_t rc_collide_instances(rc_context *ctx, rc_contact_pair *contacts, uint64_
  * index, which is only correct when the sort is the identity — see DESIGN.md). */
 int32_t rc_collide_instances_any(rc_context *ctx, uint32_t handle_a, uint32_t handle_b, int32_t *overlap);
 
+/* ---- wavefront stages either side of the trace (docs/src/wavefront-renderer.jl) ----
+ * The reference's renderer keeps SoA work queues on the device and runs one kernel per stage; these entry points are those stages
+ * on DEVICE-RESIDENT queues (every rays / hits / visible pointer below is device memory, e.g. from rc_device_alloc), so closest_hit
+ * and any_hit are fed without a host round trip.  The queue fields the reference carries beside the ray (pixel_x, pixel_y,
+ * sample_idx, hit_idx, light_idx) are pure functions of the queue index and are not stored.  RC_NO_SYNC applies. */
+#define RC_WAVE_NO_JITTER 0x40u /* primary rays through pixel centres instead of a jittered sample */
+#define RC_MAX_LIGHTS 16
+/* Triangle.normals (src/triangle_mesh.jl:3,20) of a handle's geometry: 9 floats (n0, n1, n2) per SUBMITTED face, in rc_push
+ * order (degenerate faces are dropped by the library).  Optional: a geometry without normals shades with its geometric normal
+ * (the reference always has vertex normals, src/instanced-bvh.jl:2291-2298).  rc_update_geometry drops them.  RC_VERTS_ON_DEVICE applies. */
+int32_t rc_set_normals(rc_context *ctx, uint32_t handle, const float *normals, uint32_t n_faces, uint32_t flags);
+/* generate_primary_rays! — docs/src/wavefront-renderer.jl:185-213: pinhole camera at camera_pos looking down +z;
+ * ray ((y-1)*width + (x-1))*n_samples + (s-1) for 1-based pixel (x, y), sample s.  The reference's rand(Vec2f) jitter is the
+ * counter RNG of DESIGN.md (seed, ray index, dims 0/1).  rays: width*height*n_samples records. */
+int32_t rc_generate_primary_rays(rc_context *ctx, uint32_t width, uint32_t height, uint32_t n_samples, const float camera_pos[3], float focal_length, float aspect,
+                                 uint64_t seed, rc_ray *rays, uint32_t flags);
+/* generate_primary_rays_lookat! — :219-253 */
+int32_t rc_generate_primary_rays_lookat(rc_context *ctx, uint32_t width, uint32_t height, uint32_t n_samples, const float camera_pos[3], const float right[3],
+                                        const float up[3], const float forward[3], float half_width, float half_height, uint64_t seed, rc_ray *rays, uint32_t flags);
+/* generate_shadow_rays! — :277-330: shadow ray k*n_lights + l from primary hit k towards light l (origin = hit point +
+ * shadow_bias * interpolated normal, t_max = distance to the light; the reference hard-codes shadow_bias = 0.01); a missed
+ * primary ray yields the dummy ray (t_max = 0).  lights: n_lights*3 floats, HOST memory, n_lights <= RC_MAX_LIGHTS.
+ * hits must come from rc_trace_closest on the same, still synced, TLAS.  shadow_rays: n*n_lights records. */
+int32_t rc_generate_shadow_rays(rc_context *ctx, const rc_ray *rays, const rc_hit *hits, uint64_t n, const float *lights, uint32_t n_lights, float shadow_bias,
+                                rc_ray *shadow_rays, uint32_t flags);
+/* test_shadow_rays! — :337-362: visible[i] = shadow_rays[i].t_max > 0 ? !any_hit(shadow_rays[i]) : 0 (one byte per ray) */
+int32_t rc_test_shadow_rays(rc_context *ctx, const rc_ray *shadow_rays, uint64_t n, uint8_t *visible, uint32_t flags);
+/* stages 3 + 4 in one kernel: same result as rc_generate_shadow_rays followed by rc_test_shadow_rays, but each shadow ray is
+ * generated inside the traversal kernel when a lane picks it up, so the shadow-ray queue is never written to memory. */
+int32_t rc_shadow_visibility(rc_context *ctx, const rc_ray *rays, const rc_hit *hits, uint64_t n, const float *lights, uint32_t n_lights, float shadow_bias,
+                             uint8_t *visible, uint32_t flags);
+
 /* ---- device memory helpers for callers that keep rays/hits resident -------------------- */
 int32_t rc_device_alloc(rc_context *ctx, size_t bytes, void **out);
 int32_t rc_device_free(rc_context *ctx, void *ptr);

@@ -904,3 +904,105 @@ int orc_collide_instances_any(const orc_tlas *t, uint32_t a_start, uint32_t a_co
     free(leaf_of);
     return hit;
 }
+
+/* ------------------------------------------------------------------ wavefront stages (docs/src/wavefront-renderer.jl) */
+static void primary_uv(uint32_t width, uint32_t height, uint32_t n_samples, uint64_t seed, int jitter, uint64_t ray_idx, float *u, float *v) {
+    uint64_t pixel = ray_idx / n_samples;
+    float x = (float)(uint32_t)(pixel % width + 1), y = (float)(uint32_t)(pixel / width + 1);
+    float j1 = jitter ? orc_rng_uniform(seed, ray_idx, 0) : 0.5f, j2 = jitter ? orc_rng_uniform(seed, ray_idx, 1) : 0.5f;
+    *u = 2.0f * (x - 0.5f + j1) / (float)width - 1.0f;   /* :202 / :238 */
+    *v = 1.0f - 2.0f * (y - 0.5f + j2) / (float)height;  /* :203 / :239 */
+}
+
+void orc_generate_primary_rays(uint32_t width, uint32_t height, uint32_t n_samples, const float camera_pos[3], float focal_length,
+                               float aspect, uint64_t seed, int jitter, orc_ray *rays) { /* :185-213 */
+    uint64_t total = (uint64_t)width * height * n_samples;
+    for (uint64_t i = 0; i < total; i++) {
+        float u, v;
+        primary_uv(width, height, n_samples, seed, jitter, i, &u, &v);
+        float d[3] = {u * aspect, v, focal_length}, dn[3];
+        v_normalize(d, dn);
+        orc_ray r = {{camera_pos[0], camera_pos[1], camera_pos[2]}, 0.0f, {dn[0], dn[1], dn[2]}, INFINITY};
+        rays[i] = r;
+    }
+}
+
+void orc_generate_primary_rays_lookat(uint32_t width, uint32_t height, uint32_t n_samples, const float camera_pos[3], const float right[3],
+                                      const float up[3], const float forward[3], float half_width, float half_height, uint64_t seed,
+                                      int jitter, orc_ray *rays) { /* :219-253 */
+    uint64_t total = (uint64_t)width * height * n_samples;
+    for (uint64_t i = 0; i < total; i++) {
+        float u, v;
+        primary_uv(width, height, n_samples, seed, jitter, i, &u, &v);
+        float a = u * half_width, b = v * half_height, d[3], dn[3];
+        for (int k = 0; k < 3; k++) d[k] = (forward[k] + right[k] * a) + up[k] * b; /* :242-246 */
+        v_normalize(d, dn);
+        orc_ray r = {{camera_pos[0], camera_pos[1], camera_pos[2]}, 0.0f, {dn[0], dn[1], dn[2]}, INFINITY};
+        rays[i] = r;
+    }
+}
+
+void orc_generate_shadow_rays(const orc_tlas *t, const orc_ray *rays, const orc_hit *hits, uint64_t n, const float *const *blas_normals,
+                              const float *lights, uint32_t n_lights, float shadow_bias, orc_ray *shadow_rays) { /* :277-330 */
+    /* primitive_id -> sorted position, per BLAS (only needed for the geometric-normal fallback) */
+    uint32_t **inv = (uint32_t **)calloc(t->n_blas ? t->n_blas : 1, sizeof(uint32_t *));
+    for (uint64_t k = 0; k < n; k++) {
+        const orc_hit *h = &hits[k];
+        orc_ray *out = shadow_rays + k * n_lights;
+        if (!h->hit) {
+            orc_ray dummy = {{0, 0, 0}, 0.0f, {0, 0, 1}, 0.0f}; /* :319 */
+            for (uint32_t l = 0; l < n_lights; l++) out[l] = dummy;
+            continue;
+        }
+        const orc_instance *inst = &t->instances[h->instance_id];
+        uint32_t b = inst->blas_index - 1;
+        float n9[9];
+        if (blas_normals && blas_normals[b]) {
+            memcpy(n9, blas_normals[b] + (size_t)h->primitive_id * 9, 36);
+        } else {
+            uint32_t cnt = (b + 1 < t->n_blas ? t->descs[b + 1].primitives_offset : t->n_blas_prims) - t->descs[b].primitives_offset;
+            const orc_tri *prims = t->all_blas_prims + t->descs[b].primitives_offset;
+            if (!inv[b]) {
+                inv[b] = (uint32_t *)malloc(sizeof(uint32_t) * (cnt ? cnt : 1));
+                for (uint32_t p = 0; p < cnt; p++) inv[b][prims[p].input_index] = p;
+            }
+            const orc_tri *tri = &prims[inv[b][h->primitive_id]];
+            float e1[3], e2[3], c[3], g[3];
+            v_sub(tri->v + 3, tri->v, e1); v_sub(tri->v + 6, tri->v, e2);
+            v_cross(e1, e2, c);
+            v_normalize(c, g);
+            for (int q = 0; q < 3; q++) memcpy(n9 + 3 * q, g, 12);
+        }
+        const orc_ray *ray = &rays[k];
+        float w0 = 1.0f - h->bary_u - h->bary_v, w1 = h->bary_u, w2 = h->bary_v; /* bary = (1-u-v, u, v), :2015-2016 */
+        float nl[3], nw[3], nn[3], so[3];
+        for (int c = 0; c < 3; c++) nl[c] = (n9[c] * w0 + n9[3 + c] * w1) + n9[6 + c] * w2; /* :292 */
+        const float *m = inst->inv_transform;
+        for (int c = 0; c < 3; c++) nw[c] = (m[c] * nl[0] + m[4 + c] * nl[1]) + m[8 + c] * nl[2];
+        v_normalize(nw, nn);
+        for (int c = 0; c < 3; c++) so[c] = (ray->o[c] + ray->d[c] * h->t) + nn[c] * shadow_bias; /* :289, :306 */
+        for (uint32_t l = 0; l < n_lights; l++) {
+            float lv[3], sd[3];
+            v_sub(lights + 3 * l, so, lv);
+            v_normalize(lv, sd);
+            orc_ray r = {{so[0], so[1], so[2]}, 0.0f, {sd[0], sd[1], sd[2]}, sqrtf(lv[0] * lv[0] + lv[1] * lv[1] + lv[2] * lv[2])};
+            out[l] = r;
+        }
+    }
+    for (uint32_t b = 0; b < t->n_blas; b++) free(inv[b]);
+    free(inv);
+}
+
+void orc_test_shadow_rays(const orc_tlas *t, const orc_ray *shadow_rays, uint64_t n, uint8_t *visible, int threads) { /* :337-362 */
+    if (threads <= 0) threads = orc_max_threads();
+#pragma omp parallel for num_threads(threads) schedule(dynamic, 1024)
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+        if (shadow_rays[i].t_max > 0.0f) {
+            orc_hit h;
+            traverse(t, &shadow_rays[i], 1, &h, NULL, NULL);
+            visible[i] = h.hit ? 0 : 1;
+        } else {
+            visible[i] = 0; /* dummy ray of a sky hit */
+        }
+    }
+}

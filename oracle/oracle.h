@@ -175,6 +175,23 @@ uint64_t orc_collide_instances(const orc_tlas *t, uint32_t *counts, orc_contact 
 /* ranges are 0-based [start, start+count) positions in instances[] */
 int orc_collide_instances_any(const orc_tlas *t, uint32_t a_start, uint32_t a_count, uint32_t b_start, uint32_t b_count, int literal); /* :241-261 */
 
+/* ---- wavefront stages (docs/src/wavefront-renderer.jl) ---- */
+/* generate_primary_rays! :185-213 — ray ((y-1)*width + (x-1))*n_samples + (s-1); jitter != 0: rand(Vec2f) restated with the
+ * counter RNG (seed, ray index, dims 0/1), jitter == 0: pixel centres (0.5, 0.5) */
+void orc_generate_primary_rays(uint32_t width, uint32_t height, uint32_t n_samples, const float camera_pos[3], float focal_length,
+                               float aspect, uint64_t seed, int jitter, orc_ray *rays);
+/* generate_primary_rays_lookat! :219-253 */
+void orc_generate_primary_rays_lookat(uint32_t width, uint32_t height, uint32_t n_samples, const float camera_pos[3], const float right[3],
+                                      const float up[3], const float forward[3], float half_width, float half_height, uint64_t seed,
+                                      int jitter, orc_ray *rays);
+/* generate_shadow_rays! :277-330.  blas_normals[b] (nullable table / nullable entries): 9 floats per primitive of BLAS b+1 indexed
+ * by hit.primitive_id (= orc_tri.input_index); NULL => the triangle's geometric normal at all three vertices.  The interpolated
+ * normal is carried through the instance's inverse-transpose (identity for the reference renderer's identity instances). */
+void orc_generate_shadow_rays(const orc_tlas *t, const orc_ray *rays, const orc_hit *hits, uint64_t n, const float *const *blas_normals,
+                              const float *lights, uint32_t n_lights, float shadow_bias, orc_ray *shadow_rays);
+/* test_shadow_rays! :337-362 */
+void orc_test_shadow_rays(const orc_tlas *t, const orc_ray *shadow_rays, uint64_t n, uint8_t *visible, int threads);
+
 /* the RNG itself, exposed so tests can pin GPU == oracle on the uniform stream */
 float orc_rng_uniform(uint64_t seed, uint64_t index, uint32_t dim);
 

@@ -145,6 +145,14 @@ def lib():
         L.orc_collide_instances.argtypes = [C.POINTER(_Tlas), vp, vp]
         L.orc_collide_instances_any.restype = C.c_int
         L.orc_collide_instances_any.argtypes = [C.POINTER(_Tlas), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
+        L.orc_generate_primary_rays.restype = None
+        L.orc_generate_primary_rays.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, fp, C.c_float, C.c_float, C.c_uint64, C.c_int, vp]
+        L.orc_generate_primary_rays_lookat.restype = None
+        L.orc_generate_primary_rays_lookat.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, fp, fp, fp, fp, C.c_float, C.c_float, C.c_uint64, C.c_int, vp]
+        L.orc_generate_shadow_rays.restype = None
+        L.orc_generate_shadow_rays.argtypes = [C.POINTER(_Tlas), vp, vp, C.c_uint64, vp, vp, C.c_uint32, C.c_float, vp]
+        L.orc_test_shadow_rays.restype = None
+        L.orc_test_shadow_rays.argtypes = [C.POINTER(_Tlas), vp, C.c_uint64, vp, C.c_int]
         L.orc_rng_uniform.restype = C.c_float
         L.orc_rng_uniform.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32]
         _lib = L
@@ -427,6 +435,32 @@ class OracleTLAS:
     def collide_instances_any(self, a_range, b_range, literal=False):
         return bool(lib().orc_collide_instances_any(self._p, a_range[0], a_range[1], b_range[0], b_range[1], int(literal)))
 
+    # wavefront stages (docs/src/wavefront-renderer.jl:277-362)
+    def generate_shadow_rays(self, rays, hits, lights, shadow_bias=0.01, blas_normals=None):
+        """blas_normals: None or a list (one entry per BLAS) of None / float32 (n_prims, 9) arrays indexed by primitive_id."""
+        rays = np.ascontiguousarray(rays, RAY_DTYPE)
+        hits = np.ascontiguousarray(hits, HIT_DTYPE)
+        lights = np.ascontiguousarray(lights, np.float32).reshape(-1, 3)
+        out = np.zeros(len(rays) * len(lights), RAY_DTYPE)
+        table = None
+        keep = []
+        if blas_normals is not None:
+            table = (C.c_void_p * max(1, len(blas_normals)))()
+            for b, a in enumerate(blas_normals):
+                if a is not None:
+                    a = np.ascontiguousarray(a, np.float32)
+                    keep.append(a)
+                    table[b] = a.ctypes.data
+        lib().orc_generate_shadow_rays(self._p, rays.ctypes.data, hits.ctypes.data, len(rays), table, lights.ctypes.data, len(lights),
+                                       shadow_bias, out.ctypes.data)
+        return out
+
+    def test_shadow_rays(self, shadow_rays, threads=0):
+        shadow_rays = np.ascontiguousarray(shadow_rays, RAY_DTYPE)
+        vis = np.zeros(len(shadow_rays), np.uint8)
+        lib().orc_test_shadow_rays(self._p, shadow_rays.ctypes.data, len(shadow_rays), vis.ctypes.data, threads)
+        return vis
+
     def __del__(self):
         if getattr(self, "_p", None):
             lib().orc_free_tlas(self._p)
@@ -435,3 +469,20 @@ class OracleTLAS:
 
 def max_threads():
     return lib().orc_max_threads()
+
+
+def generate_primary_rays(width, height, n_samples, camera_pos, focal_length, aspect, seed=0, jitter=True):
+    """generate_primary_rays! (docs/src/wavefront-renderer.jl:185-213)"""
+    out = np.zeros(width * height * n_samples, RAY_DTYPE)
+    cp = _f(camera_pos, 3)
+    lib().orc_generate_primary_rays(width, height, n_samples, _fp(cp), focal_length, aspect, seed, int(jitter), out.ctypes.data)
+    return out
+
+
+def generate_primary_rays_lookat(width, height, n_samples, camera_pos, right, up, forward, half_width, half_height, seed=0, jitter=True):
+    """generate_primary_rays_lookat! (docs/src/wavefront-renderer.jl:219-253)"""
+    out = np.zeros(width * height * n_samples, RAY_DTYPE)
+    cp, r, u, f = _f(camera_pos, 3), _f(right, 3), _f(up, 3), _f(forward, 3)
+    lib().orc_generate_primary_rays_lookat(width, height, n_samples, _fp(cp), _fp(r), _fp(u), _fp(f), half_width, half_height, seed, int(jitter),
+                                           out.ctypes.data)
+    return out

@@ -30,6 +30,8 @@ RC_MODE_REFERENCE_ORDER = 0x4
 RC_COUNTERS = 0x8
 RC_VERTS_ON_DEVICE = 0x10
 RC_NO_SYNC = 0x20
+RC_WAVE_NO_JITTER = 0x40
+RC_MAX_LIGHTS = 16
 
 RC_SYNC_NONE, RC_SYNC_REFIT, RC_SYNC_REBUILD = 0, 1, 2
 
@@ -71,6 +73,8 @@ EXPORTS = [
     "rc_trace_closest", "rc_trace_any", "rc_get_counters", "rc_last_kernel_ms", "rc_last_kernel_launches", "rc_last_build_ms",
     "rc_hits_from_grid", "rc_get_illumination", "rc_get_centroid", "rc_view_factors", "rc_view_factor_rays", "rc_read_flat_metadata",
     "rc_collide_instances", "rc_collide_instances_any",
+    "rc_set_normals", "rc_generate_primary_rays", "rc_generate_primary_rays_lookat", "rc_generate_shadow_rays", "rc_test_shadow_rays",
+    "rc_shadow_visibility",
     "rc_device_alloc", "rc_device_free", "rc_host_alloc", "rc_host_free", "rc_memcpy_h2d", "rc_memcpy_d2h",
     "rc_ipc_export", "rc_ipc_open", "rc_ipc_close", "rc_peer_copy_async", "rc_stream_wait_copy",
 ]  # fmt: skip
@@ -142,6 +146,12 @@ def load():
         "rc_read_flat_metadata": (i32, [vp, vp, u32]),
         "rc_collide_instances": (i32, [vp, vp, u64, C.POINTER(u64)]),
         "rc_collide_instances_any": (i32, [vp, u32, u32, pi32]),
+        "rc_set_normals": (i32, [vp, u32, vp, u32, u32]),
+        "rc_generate_primary_rays": (i32, [vp, u32, u32, u32, vp, C.c_float, C.c_float, u64, vp, u32]),
+        "rc_generate_primary_rays_lookat": (i32, [vp, u32, u32, u32, vp, vp, vp, vp, C.c_float, C.c_float, u64, vp, u32]),
+        "rc_generate_shadow_rays": (i32, [vp, vp, vp, u64, vp, u32, C.c_float, vp, u32]),
+        "rc_test_shadow_rays": (i32, [vp, vp, u64, vp, u32]),
+        "rc_shadow_visibility": (i32, [vp, vp, vp, u64, vp, u32, C.c_float, vp, u32]),
         "rc_device_alloc": (i32, [vp, C.c_size_t, C.POINTER(vp)]),
         "rc_device_free": (i32, [vp, vp]),
         "rc_host_alloc": (i32, [vp, C.c_size_t, C.POINTER(vp)]),

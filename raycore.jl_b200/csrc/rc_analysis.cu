@@ -226,7 +226,7 @@ void rc_launch_view_factors(cudaStream_t st, const RcScene &sc, const RcFlatBlas
     if (sc.n_instances == 0) return;  // nothing to hit: the zeroed matrix is the answer
     RcIoViewFactors io{sc, d_flat, n_blas, rpt, row_base, n_rows, n_cols, seed, out, skipped, overflow};
     cudaMemsetAsync(work, 0, sizeof(unsigned long long), st);
-    k_trace_wide<false, false, RcIoViewFactors><<<blocks, RC_TRACE_THREADS, 0, st>>>(sc, io, total, work, nullptr, overflow + 1);
+    k_trace_wide<false, false, RcIoViewFactors><<<blocks, RC_TRACE_THREADS, 0, st>>>(sc, io, total, work, nullptr, overflow + 1);  // overflow = &d_overflow[1]; [2] is the flagged-ray scratch
 }
 
 __global__ void k_flat_metadata(const RcFlatBlas *__restrict__ flat, uint32_t n_blas, uint32_t n_prims, uint32_t *__restrict__ out) {

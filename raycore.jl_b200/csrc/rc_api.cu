@@ -13,6 +13,8 @@
 #include "rc_build.h"
 #include "rc_device.cuh"
 #include "rc_trace.h"
+#include "rc_wave.h"
+#include "rc_wave_core.cuh"
 
 namespace {
 
@@ -51,6 +53,9 @@ struct rc_context {
     bool copy_pending[2] = {false, false};
     uint32_t last_launches = 0;
     int max_blocks = 148;
+    // wavefront stages: device table of per-BLAS normal arrays, re-uploaded when normals_version moves
+    const float **d_normal_ptrs = nullptr;
+    std::vector<const float *> normal_ptrs;  // what d_normal_ptrs currently holds
 };
 
 #define RC_FAIL(ctx, code, msg)        \
@@ -124,9 +129,9 @@ int32_t rc_create(int32_t device, rc_context **out) {
     CREATE_CK(cudaEventCreate(&ctx->ev_t1));
     CREATE_CK(cudaMalloc(&ctx->d_work, sizeof(unsigned long long)));
     CREATE_CK(cudaMalloc(&ctx->d_counters, sizeof(RcCounters)));
-    CREATE_CK(cudaMalloc(&ctx->d_overflow, 2 * sizeof(uint32_t)));
+    CREATE_CK(cudaMalloc(&ctx->d_overflow, 4 * sizeof(uint32_t)));  // [0] rays flagged for k_trace_fixup, [1] hard errors, [2] flagged-ray scratch of the inline re-trace policies
     CREATE_CK(cudaMemset(ctx->d_counters, 0, sizeof(RcCounters)));
-    CREATE_CK(cudaMemset(ctx->d_overflow, 0, 2 * sizeof(uint32_t)));
+    CREATE_CK(cudaMemset(ctx->d_overflow, 0, 4 * sizeof(uint32_t)));
     // keep freed blocks cached in the stream-ordered pool: rebuild-per-frame workloads reuse them
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -152,6 +157,7 @@ int32_t rc_destroy(rc_context *ctx) {
     cudaFree(ctx->d_work); cudaFree(ctx->d_counters); cudaFree(ctx->d_overflow);
     if (ctx->d_rays) cudaFree(ctx->d_rays);
     if (ctx->d_hits) cudaFree(ctx->d_hits);
+    if (ctx->d_normal_ptrs) cudaFree(ctx->d_normal_ptrs);
     for (int i = 0; i < rc_context::NEV; i++) { cudaEventDestroy(ctx->ev_h2d[i]); cudaEventDestroy(ctx->ev_k[i]); }
     cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1);
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
@@ -793,6 +799,173 @@ int32_t rc_collide_instances_any(rc_context *ctx, uint32_t handle_a, uint32_t ha
         }
     return RC_OK;
 }
+
+// ---- wavefront stages around the trace (docs/src/wavefront-renderer.jl:185-362) --------------------------------------------
+int32_t rc_set_normals(rc_context *ctx, uint32_t handle, const float *normals, uint32_t n_faces, uint32_t flags) {
+    if (!ctx) return RC_ERR_INVALID_ARGUMENT;
+    use_device(ctx);
+    HandleInfo *hi = nullptr;
+    int32_t rc = find_handle(ctx, handle, &hi);
+    if (rc != RC_OK) return rc;
+    if (hi->count == 0) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "Handle has no instances");
+    RcDeviceBlas &B = ctx->blas[ctx->instances[hi->start].blas_index - 1];
+    if (!normals || n_faces != B.n_faces_in) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "rc_set_normals: need 9 floats for each of the " + std::to_string(B.n_faces_in) + " submitted faces");
+    const float *d_in = normals;
+    float *tmp = nullptr;
+    const size_t bytes = sizeof(float) * 9 * (size_t)n_faces;
+    if (!(flags & RC_VERTS_ON_DEVICE)) {
+        RC_CUDA(ctx, cudaMallocAsync(&tmp, bytes, ctx->stream));
+        RC_CUDA(ctx, cudaMemcpyAsync(tmp, normals, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        d_in = tmp;
+    }
+    if (!B.normals) RC_CUDA(ctx, cudaMallocAsync(&B.normals, sizeof(float) * 9 * (size_t)B.n, ctx->stream));
+    rc_launch_gather_normals(ctx->stream, B.tris, B.n, d_in, B.normals);
+    if (tmp) cudaFreeAsync(tmp, ctx->stream);
+    RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the caller may reuse `normals` on return
+    return RC_OK;
+}
+
+// every BLAS gets a normal array (geometric normals where the caller set none) and the device pointer table follows ctx->blas
+static int32_t ensure_normals(rc_context *ctx) {
+    std::vector<const float *> want(ctx->blas.size());
+    for (size_t b = 0; b < ctx->blas.size(); b++) {
+        RcDeviceBlas &B = ctx->blas[b];
+        if (!B.normals && B.n) {
+            RC_CUDA(ctx, cudaMallocAsync(&B.normals, sizeof(float) * 9 * (size_t)B.n, ctx->stream));
+            rc_launch_gather_normals(ctx->stream, B.tris, B.n, nullptr, B.normals);
+        }
+        want[b] = B.normals;
+    }
+    if (want != ctx->normal_ptrs || !ctx->d_normal_ptrs) {
+        if (want.size() > ctx->normal_ptrs.capacity() || !ctx->d_normal_ptrs) {
+            RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (ctx->d_normal_ptrs) cudaFree(ctx->d_normal_ptrs);
+            ctx->d_normal_ptrs = nullptr;
+            ctx->normal_ptrs.reserve(want.size() * 2 + 8);
+            RC_CUDA(ctx, cudaMalloc(&ctx->d_normal_ptrs, sizeof(float *) * ctx->normal_ptrs.capacity()));
+        }
+        ctx->normal_ptrs.assign(want.begin(), want.end());
+        RC_CUDA(ctx, cudaMemcpyAsync(ctx->d_normal_ptrs, ctx->normal_ptrs.data(), sizeof(float *) * want.size(), cudaMemcpyHostToDevice, ctx->stream));
+        RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host vector may be reassigned by the next call
+    }
+    return RC_OK;
+}
+
+static int32_t finish_stage(rc_context *ctx, uint32_t flags, uint32_t launches, bool traced) {
+    cudaEventRecord(ctx->ev_t1, ctx->stream);
+    ctx->last_launches = launches;
+    RC_CUDA(ctx, cudaGetLastError());
+    if (flags & RC_NO_SYNC) return RC_OK;
+    RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->last_ms, ctx->ev_t0, ctx->ev_t1);
+    return traced ? check_overflow(ctx) : RC_OK;
+}
+
+static int32_t primary_common(rc_context *ctx, const RcCamera &cam, uint32_t width, uint32_t height, uint32_t n_samples, uint64_t seed, rc_ray *d_rays, uint32_t flags) {
+    use_device(ctx);
+    if (width == 0 || height == 0 || n_samples == 0) return RC_OK;
+    if (!d_rays) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "rays is NULL");
+    cudaEventRecord(ctx->ev_t0, ctx->stream);
+    rc_launch_primary_rays(ctx->stream, cam, width, height, n_samples, seed, d_rays);
+    return finish_stage(ctx, flags, 1, false);
+}
+
+int32_t rc_generate_primary_rays(rc_context *ctx, uint32_t width, uint32_t height, uint32_t n_samples, const float camera_pos[3], float focal_length, float aspect,
+                                 uint64_t seed, rc_ray *rays, uint32_t flags) {
+    if (!ctx) return RC_ERR_INVALID_ARGUMENT;
+    if (!camera_pos) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "camera_pos is NULL");
+    RcCamera cam;
+    memset(&cam, 0, sizeof(cam));
+    memcpy(cam.pos, camera_pos, 12);
+    cam.forward[2] = focal_length;
+    cam.half_width = aspect;
+    cam.half_height = 1.0f;
+    cam.lookat = 0;
+    cam.jitter = (flags & RC_WAVE_NO_JITTER) ? 0 : 1;
+    return primary_common(ctx, cam, width, height, n_samples, seed, rays, flags);
+}
+
+int32_t rc_generate_primary_rays_lookat(rc_context *ctx, uint32_t width, uint32_t height, uint32_t n_samples, const float camera_pos[3], const float right[3],
+                                        const float up[3], const float forward[3], float half_width, float half_height, uint64_t seed, rc_ray *rays, uint32_t flags) {
+    if (!ctx) return RC_ERR_INVALID_ARGUMENT;
+    if (!camera_pos || !right || !up || !forward) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "camera vectors are NULL");
+    RcCamera cam;
+    memcpy(cam.pos, camera_pos, 12);
+    memcpy(cam.right, right, 12);
+    memcpy(cam.up, up, 12);
+    memcpy(cam.forward, forward, 12);
+    cam.half_width = half_width;
+    cam.half_height = half_height;
+    cam.lookat = 1;
+    cam.jitter = (flags & RC_WAVE_NO_JITTER) ? 0 : 1;
+    return primary_common(ctx, cam, width, height, n_samples, seed, rays, flags);
+}
+
+static int32_t make_lights(rc_context *ctx, const float *lights, uint32_t n_lights, float bias, RcLights *out) {
+    if (!lights || n_lights == 0 || n_lights > RC_MAX_LIGHTS) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "need 1.." + std::to_string(RC_MAX_LIGHTS) + " lights");
+    memset(out, 0, sizeof(*out));
+    memcpy(out->pos, lights, 12 * (size_t)n_lights);
+    out->n = n_lights;
+    out->bias = bias;
+    return RC_OK;
+}
+
+static int32_t shadow_source(rc_context *ctx, const rc_ray *rays, const rc_hit *hits, RcShadowSource *out) {
+    if (!rays || !hits) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "rays / hits is NULL");
+    int32_t rc = require_synced(ctx);
+    if (rc != RC_OK) return rc;
+    rc = ensure_normals(ctx);
+    if (rc != RC_OK) return rc;
+    *out = RcShadowSource{rays, hits, ctx->tlas.d_inst, ctx->d_normal_ptrs};
+    return RC_OK;
+}
+
+int32_t rc_generate_shadow_rays(rc_context *ctx, const rc_ray *rays, const rc_hit *hits, uint64_t n, const float *lights, uint32_t n_lights, float shadow_bias,
+                                rc_ray *shadow_rays, uint32_t flags) {
+    if (!ctx) return RC_ERR_INVALID_ARGUMENT;
+    use_device(ctx);
+    if (n == 0) return RC_OK;
+    RcLights L;
+    RcShadowSource src;
+    int32_t rc = make_lights(ctx, lights, n_lights, shadow_bias, &L);
+    if (rc != RC_OK) return rc;
+    if (!shadow_rays) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "shadow_rays is NULL");
+    rc = shadow_source(ctx, rays, hits, &src);
+    if (rc != RC_OK) return rc;
+    cudaEventRecord(ctx->ev_t0, ctx->stream);
+    rc_launch_shadow_rays(ctx->stream, src, L, n, shadow_rays);
+    return finish_stage(ctx, flags, 1, false);
+}
+
+int32_t rc_test_shadow_rays(rc_context *ctx, const rc_ray *shadow_rays, uint64_t n, uint8_t *visible, uint32_t flags) {
+    if (!ctx) return RC_ERR_INVALID_ARGUMENT;
+    use_device(ctx);
+    if (n == 0) return RC_OK;
+    if (!shadow_rays || !visible) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "shadow_rays / visible is NULL");
+    int32_t rc = require_synced(ctx);
+    if (rc != RC_OK) return rc;
+    cudaEventRecord(ctx->ev_t0, ctx->stream);
+    rc_launch_test_shadow_rays(ctx->stream, make_scene(ctx), shadow_rays, n, visible, ctx->d_overflow, ctx->max_blocks, ctx->d_work);
+    return finish_stage(ctx, flags, 2, true);
+}
+
+int32_t rc_shadow_visibility(rc_context *ctx, const rc_ray *rays, const rc_hit *hits, uint64_t n, const float *lights, uint32_t n_lights, float shadow_bias,
+                             uint8_t *visible, uint32_t flags) {
+    if (!ctx) return RC_ERR_INVALID_ARGUMENT;
+    use_device(ctx);
+    if (n == 0) return RC_OK;
+    RcLights L;
+    RcShadowSource src;
+    int32_t rc = make_lights(ctx, lights, n_lights, shadow_bias, &L);
+    if (rc != RC_OK) return rc;
+    if (!visible) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "visible is NULL");
+    rc = shadow_source(ctx, rays, hits, &src);
+    if (rc != RC_OK) return rc;
+    cudaEventRecord(ctx->ev_t0, ctx->stream);
+    rc_launch_shadow_visibility(ctx->stream, make_scene(ctx), src, L, n, visible, ctx->d_overflow, ctx->max_blocks, ctx->d_work);
+    return finish_stage(ctx, flags, 2, true);
+}
+
 
 // ------------------------------------------------------------------------------------------------ memory helpers
 int32_t rc_device_alloc(rc_context *ctx, size_t bytes, void **out) {

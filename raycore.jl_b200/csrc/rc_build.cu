@@ -496,6 +496,8 @@ void rc_free_blas(RcDeviceBlas *b, cudaStream_t st) {
     if (b->nodes4) cudaFreeAsync(b->nodes4, st);
     if (b->tris) cudaFreeAsync(b->tris, st);
     if (b->hull) cudaFreeAsync(b->hull, st);
+    if (b->normals) cudaFreeAsync(b->normals, st);
+    b->normals = nullptr;
     b->nodes2 = nullptr; b->nodes4 = nullptr; b->tris = nullptr; b->hull = nullptr; b->n = 0;
 }
 

@@ -17,6 +17,7 @@ struct RcDeviceBlas {
     RcNode4 *nodes4 = nullptr;  // n+1 slots, indexed by BVH2 internal node number, root = [1]
     RcTri *tris = nullptr;      // n, Morton-sorted
     RcBox *hull = nullptr;      // RC_HULL_BOXES boxes of BVH2 subtrees covering the whole BLAS (tight instance bounds for the wide TLAS)
+    float *normals = nullptr;   // optional, 9 floats per primitive indexed by primitive_id (rc_set_normals; shading-side data of the wavefront stages)
     float root_aabb[6] = {0, 0, 0, 0, 0, 0};
 };
 

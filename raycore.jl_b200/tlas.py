@@ -53,6 +53,44 @@ def _as_rays(rays) -> np.ndarray:
     return out
 
 
+class DeviceQueue:
+    """A device-resident work queue (the reference's SoA queues on the backend, docs/src/wavefront-renderer.jl:127-180):
+    `count` records of numpy dtype `dtype` in memory owned by the TLAS's context."""
+
+    def __init__(self, owner: "TLAS", dtype, count: int):
+        self._owner = owner
+        self.dtype = np.dtype(dtype)
+        self.count = int(count)
+        p = C.c_void_p()
+        owner._ck(owner._lib.rc_device_alloc(owner._ctx, max(1, self.count * self.dtype.itemsize), C.byref(p)))
+        self.ptr = p.value
+
+    def upload(self, host) -> "DeviceQueue":
+        a = np.ascontiguousarray(host, self.dtype)
+        if len(a) != self.count:
+            raise ValueError(f"queue holds {self.count} records, got {len(a)}")
+        if self.count:
+            self._owner._ck(self._owner._lib.rc_memcpy_h2d(self._owner._ctx, self.ptr, a.ctypes.data, a.nbytes))
+        return self
+
+    def download(self) -> np.ndarray:
+        out = np.zeros(self.count, self.dtype)
+        if self.count:
+            self._owner._ck(self._owner._lib.rc_memcpy_d2h(self._owner._ctx, out.ctypes.data, self.ptr, out.nbytes))
+        return out
+
+    def free(self):
+        if getattr(self, "ptr", None) and self._owner._ctx:
+            self._owner._lib.rc_device_free(self._owner._ctx, self.ptr)
+        self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 class StaticTLAS:
     """Adapted (immutable) form, `AbstractAdaptedAccel` (src/Raycore.jl:14-49, src/instanced-bvh.jl:155-168).
 
@@ -438,6 +476,66 @@ class TLAS:
         if len(out):
             self._ck(self._lib.rc_view_factor_rays(self._ctx, rays_per_triangle, seed, row_base, n_rows, out.ctypes.data))
         return out
+
+
+    # -- wavefront stages on device-resident queues (docs/src/wavefront-renderer.jl:185-362) -------------
+    def queue(self, dtype, count: int) -> DeviceQueue:
+        return DeviceQueue(self, dtype, count)
+
+    def set_normals(self, handle: TLASHandle, normals):
+        """Triangle.normals of the handle's geometry: float32 (n_faces, 9) = (n0, n1, n2) per submitted face."""
+        n = np.ascontiguousarray(np.asarray(normals, np.float32).reshape(-1, 9))
+        self._ck(self._lib.rc_set_normals(self._ctx, handle.id, n.ctypes.data, len(n), 0))
+
+    def generate_primary_rays(self, width: int, height: int, camera_pos, focal_length: float, aspect: float, n_samples: int = 1, seed: int = 0,
+                              jitter: bool = True, out: Optional[DeviceQueue] = None) -> DeviceQueue:
+        """generate_primary_rays! — :185-213."""
+        q = out or DeviceQueue(self, RAY_DTYPE, width * height * n_samples)
+        cp = np.ascontiguousarray(camera_pos, np.float32)
+        self._ck(self._lib.rc_generate_primary_rays(self._ctx, width, height, n_samples, cp.ctypes.data, focal_length, aspect, seed, q.ptr,
+                                                    0 if jitter else L.RC_WAVE_NO_JITTER))
+        return q
+
+    def generate_primary_rays_lookat(self, width: int, height: int, camera_pos, right, up, forward, half_width: float, half_height: float,
+                                     n_samples: int = 1, seed: int = 0, jitter: bool = True, out: Optional[DeviceQueue] = None) -> DeviceQueue:
+        """generate_primary_rays_lookat! — :219-253."""
+        q = out or DeviceQueue(self, RAY_DTYPE, width * height * n_samples)
+        v = [np.ascontiguousarray(x, np.float32) for x in (camera_pos, right, up, forward)]
+        self._ck(self._lib.rc_generate_primary_rays_lookat(self._ctx, width, height, n_samples, v[0].ctypes.data, v[1].ctypes.data, v[2].ctypes.data,
+                                                           v[3].ctypes.data, half_width, half_height, seed, q.ptr, 0 if jitter else L.RC_WAVE_NO_JITTER))
+        return q
+
+    def intersect_rays(self, rays: DeviceQueue, any_hit: bool = False, out: Optional[DeviceQueue] = None) -> DeviceQueue:
+        """intersect_primary_rays! — :260-275: closest_hit over a device ray queue into a device hit queue."""
+        self.sync()
+        q = out or DeviceQueue(self, HIT_DTYPE, rays.count)
+        fn = self._lib.rc_trace_any if any_hit else self._lib.rc_trace_closest
+        if rays.count:
+            self._ck(fn(self._ctx, rays.ptr, q.ptr, rays.count, L.RC_RAYS_ON_DEVICE | L.RC_HITS_ON_DEVICE))
+        return q
+
+    def generate_shadow_rays(self, rays: DeviceQueue, hits: DeviceQueue, lights, shadow_bias: float = 0.01, out: Optional[DeviceQueue] = None) -> DeviceQueue:
+        """generate_shadow_rays! — :277-330: queue of rays.count * n_lights shadow rays."""
+        self.sync()
+        lt = np.ascontiguousarray(np.asarray(lights, np.float32).reshape(-1, 3))
+        q = out or DeviceQueue(self, RAY_DTYPE, rays.count * len(lt))
+        self._ck(self._lib.rc_generate_shadow_rays(self._ctx, rays.ptr, hits.ptr, rays.count, lt.ctypes.data, len(lt), shadow_bias, q.ptr, 0))
+        return q
+
+    def test_shadow_rays(self, shadow_rays: DeviceQueue, out: Optional[DeviceQueue] = None) -> DeviceQueue:
+        """test_shadow_rays! — :337-362: one visibility byte per shadow ray."""
+        self.sync()
+        q = out or DeviceQueue(self, np.uint8, shadow_rays.count)
+        self._ck(self._lib.rc_test_shadow_rays(self._ctx, shadow_rays.ptr, shadow_rays.count, q.ptr, 0))
+        return q
+
+    def shadow_visibility(self, rays: DeviceQueue, hits: DeviceQueue, lights, shadow_bias: float = 0.01, out: Optional[DeviceQueue] = None) -> DeviceQueue:
+        """generate_shadow_rays! + test_shadow_rays! in one kernel (no shadow-ray queue in memory)."""
+        self.sync()
+        lt = np.ascontiguousarray(np.asarray(lights, np.float32).reshape(-1, 3))
+        q = out or DeviceQueue(self, np.uint8, rays.count * len(lt))
+        self._ck(self._lib.rc_shadow_visibility(self._ctx, rays.ptr, hits.ptr, rays.count, lt.ctypes.data, len(lt), shadow_bias, q.ptr, 0))
+        return q
 
 
 def build_static_tlas(meshes, metadata_fn=None, device: Optional[int] = None) -> StaticTLAS:

@@ -13,6 +13,7 @@
 
 #include "../../raycore.jl_b200/csrc/rc_build_core.cuh"
 #include "../../raycore.jl_b200/csrc/rc_trace_core.cuh"
+#include "../../raycore.jl_b200/csrc/rc_wave_core.cuh"
 
 namespace {
 
@@ -295,6 +296,49 @@ uint32_t hs_check_wide(void *b) {
         }
     }
     return bad;
+}
+
+// ---- wavefront stage bodies (rc_wave_core.cuh); loops stand in for k_primary_rays / k_geometric_normals / k_shadow_rays
+void hs_primary_rays(const float *camera_pos, const float *right, const float *up, const float *forward, float half_width, float half_height, int lookat, int jitter,
+                     uint32_t width, uint32_t height, uint32_t n_samples, uint64_t seed, rc_ray *out) {
+    RcCamera cam;
+    memset(&cam, 0, sizeof cam);
+    memcpy(cam.pos, camera_pos, 12);
+    if (right) memcpy(cam.right, right, 12);
+    if (up) memcpy(cam.up, up, 12);
+    memcpy(cam.forward, forward, 12);
+    cam.half_width = half_width; cam.half_height = half_height;
+    cam.lookat = (uint32_t)lookat; cam.jitter = (uint32_t)jitter;
+    uint64_t total = (uint64_t)width * height * n_samples;
+    for (uint64_t i = 0; i < total; i++) out[i] = rc_primary_ray(cam, width, height, n_samples, seed, i);
+}
+
+// blas_normals: table with one entry per BLAS (NULL entry => geometric normals), 9 floats per primitive indexed by primitive_id
+void hs_shadow_rays(void *s, const rc_ray *rays, const rc_hit *hits, uint64_t n, const float *const *blas_normals, const float *lights, uint32_t n_lights,
+                    float bias, rc_ray *out) {
+    HsScene *S = (HsScene *)s;
+    std::vector<std::vector<float>> geo(S->blas.size());
+    for (uint64_t k = 0; k < n; k++) {
+        for (uint32_t l = 0; l < n_lights; l++) {
+            if (!hits[k].hit) { out[k * n_lights + l] = rc_dummy_shadow_ray(); continue; }
+            const rc_instance_desc &inst = S->inst[hits[k].instance_id];
+            uint32_t b = inst.blas_index - 1;
+            const float *nrm = blas_normals ? blas_normals[b] : nullptr;
+            if (!nrm) {
+                if (geo[b].empty()) {
+                    HsBlas *B = S->blas[b];
+                    geo[b].resize(9 * (size_t)B->tree.n);
+                    for (uint32_t p = 0; p < B->tree.n; p++) {
+                        f3 g = rc_geometric_normal(B->tris[p]);
+                        float *o = geo[b].data() + 9 * (size_t)B->tris[p].prim_id;
+                        for (int q = 0; q < 3; q++) { o[3 * q] = g.x; o[3 * q + 1] = g.y; o[3 * q + 2] = g.z; }
+                    }
+                }
+                nrm = geo[b].data();
+            }
+            out[k * n_lights + l] = rc_shadow_ray(rays[k], hits[k], nrm + 9 * (size_t)hits[k].primitive_id, inst.inv_transform, lights + 3 * l, bias);
+        }
+    }
 }
 
 }  // extern "C"

@@ -34,6 +34,10 @@ def lib():
         L.hs_scene_free.argtypes = [vp]
         L.hs_trace.restype = C.c_uint32
         L.hs_trace.argtypes = [vp, vp, vp, C.c_uint64, C.c_int, C.c_int, vp]
+        L.hs_primary_rays.restype = None
+        L.hs_primary_rays.argtypes = [vp, vp, vp, vp, C.c_float, C.c_float, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, vp]
+        L.hs_shadow_rays.restype = None
+        L.hs_shadow_rays.argtypes = [vp, vp, vp, C.c_uint64, vp, vp, C.c_uint32, C.c_float, vp]
         L.hs_check_wide.restype = C.c_uint32
         L.hs_check_wide.argtypes = [vp]
         _lib = L
@@ -95,6 +99,21 @@ class HsScene:
         lib().hs_scene_root(self.p, out.ctypes.data)
         return out
 
+    def shadow_rays(self, rays, hits, lights, shadow_bias=0.01, blas_normals=None):
+        rays = np.ascontiguousarray(rays, RAY_DTYPE)
+        hits = np.ascontiguousarray(hits, HIT_DTYPE)
+        lights = np.ascontiguousarray(lights, np.float32).reshape(-1, 3)
+        out = np.zeros(len(rays) * len(lights), RAY_DTYPE)
+        table, keep = None, []
+        if blas_normals is not None:
+            table = (C.c_void_p * max(1, len(blas_normals)))()
+            for b, a in enumerate(blas_normals):
+                if a is not None:
+                    keep.append(np.ascontiguousarray(a, np.float32))
+                    table[b] = keep[-1].ctypes.data
+        lib().hs_shadow_rays(self.p, rays.ctypes.data, hits.ctypes.data, len(rays), table, lights.ctypes.data, len(lights), shadow_bias, out.ctypes.data)
+        return out
+
     def trace(self, rays, any_hit=False, wide=True, counters=False):
         rays = np.ascontiguousarray(rays, RAY_DTYPE)
         hits = np.zeros(len(rays), HIT_DTYPE)
@@ -104,3 +123,17 @@ class HsScene:
         if counters:
             return hits, dict(zip(["nodes", "box_tests", "tri_tests", "inst_entries", "max_stack"], [int(x) for x in cnt]))
         return hits
+
+
+def primary_rays(width, height, n_samples, camera_pos, focal_length=None, aspect=None, lookat=None, seed=0, jitter=True):
+    """lookat = (right, up, forward, half_width, half_height) for generate_primary_rays_lookat!, else the pinhole form."""
+    out = np.zeros(width * height * n_samples, RAY_DTYPE)
+    cp = np.ascontiguousarray(camera_pos, np.float32)
+    if lookat is None:
+        fw = np.array([0, 0, focal_length], np.float32)
+        lib().hs_primary_rays(cp.ctypes.data, None, None, fw.ctypes.data, aspect, 1.0, 0, int(jitter), width, height, n_samples, seed, out.ctypes.data)
+    else:
+        r, u, f = (np.ascontiguousarray(x, np.float32) for x in lookat[:3])
+        lib().hs_primary_rays(cp.ctypes.data, r.ctypes.data, u.ctypes.data, f.ctypes.data, lookat[3], lookat[4], 1, int(jitter), width, height, n_samples, seed,
+                              out.ctypes.data)
+    return out
