@@ -172,7 +172,8 @@ struct RcIoViewFactors {
     unsigned long long seed;
     uint32_t *out;
     unsigned long long *skipped;
-    uint32_t *overflow;
+    uint32_t *overflow;       // hard errors (no stack could hold the ray)
+    uint32_t *retrace_bits;   // one bit per ray: short stack overflowed
     __device__ __forceinline__ rc_ray load(unsigned long long g) const {
         const uint32_t pos = (uint32_t)(g / rpt), i = (uint32_t)(g % rpt);
         const RcTri *tri = flat_tri(flat, n_blas, pos);
@@ -187,17 +188,38 @@ struct RcIoViewFactors {
         return vf_make_ray(tri, seed, (unsigned long long)row * rpt + i);
     }
     __device__ __forceinline__ void store(unsigned long long g, rc_hit h) const {
+        if (h.hit == RC_OVERFLOW_MARK) {  // short stack overflowed: k_view_factor_fixup redoes this ray with the deep-stack generic body
+            atomicOr(&retrace_bits[g >> 5], 1u << (uint32_t)(g & 31u));
+            return;
+        }
+        if (!h.hit) return;
+        accumulate(g, h);
+    }
+    __device__ __forceinline__ void accumulate(unsigned long long g, const rc_hit &h) const {
         const uint32_t pos = (uint32_t)(g / rpt);
         const RcTri *tri = flat_tri(flat, n_blas, pos);
         const uint32_t meta = tri->metadata, row = meta - 1u;
         if (meta < 1u || meta > n_cols || row < row_base || row >= row_base + n_rows) return;
-        if (h.hit == RC_OVERFLOW_MARK) {  // short stack overflowed: redo this ray with the deep-stack generic body
-            rc_ray r = vf_make_ray(tri, seed, (unsigned long long)row * rpt + (uint32_t)(g % rpt));
-            if (!rc_trace_wide<false, false>(sc, r, h, nullptr)) atomicAdd(overflow, 1u);
-        }
         if (h.hit && h.metadata != meta && h.metadata >= 1u && h.metadata <= n_cols) atomicAdd(&out[(size_t)(row - row_base) * n_cols + (h.metadata - 1u)], 1u);
     }
 };
+
+// Deep-stack pass over the rays the scheduler kernel flagged (one bit per ray); exits at once when none was.
+__global__ void __launch_bounds__(RC_TRACE_THREADS) k_view_factor_fixup(RcIoViewFactors io, unsigned long long total, const uint32_t *__restrict__ flagged) {
+    if (*reinterpret_cast<const volatile uint32_t *>(flagged) == 0) return;
+    const unsigned long long words = (total + 31) / 32;
+    for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < words; w += (unsigned long long)gridDim.x * blockDim.x) {
+        uint32_t m = io.retrace_bits[w];
+        while (m) {
+            const unsigned long long g = w * 32 + (unsigned long long)(__ffs((int)m) - 1);
+            m &= m - 1;
+            rc_ray r = io.load(g);
+            rc_hit h;
+            if (!rc_trace_wide<false, false>(io.sc, r, h, nullptr)) atomicAdd(io.overflow, 1u);
+            io.accumulate(g, h);
+        }
+    }
+}
 
 // the generated rays themselves (tests: the oracle traces exactly these)
 __global__ void k_view_factor_rays(const RcFlatBlas *__restrict__ flat, uint32_t n_blas, uint32_t n_prims, uint32_t rpt, unsigned long long seed, uint32_t row_base,
@@ -224,9 +246,16 @@ void rc_launch_view_factors(cudaStream_t st, const RcScene &sc, const RcFlatBlas
         return;
     }
     if (sc.n_instances == 0) return;  // nothing to hit: the zeroed matrix is the answer
-    RcIoViewFactors io{sc, d_flat, n_blas, rpt, row_base, n_rows, n_cols, seed, out, skipped, overflow};
+    uint32_t *bits = nullptr;
+    const size_t bit_bytes = (size_t)((total + 31) / 32) * sizeof(uint32_t);
+    cudaMallocAsync(&bits, bit_bytes, st);
+    cudaMemsetAsync(bits, 0, bit_bytes, st);
+    RcIoViewFactors io{sc, d_flat, n_blas, rpt, row_base, n_rows, n_cols, seed, out, skipped, overflow, bits};
     cudaMemsetAsync(work, 0, sizeof(unsigned long long), st);
-    k_trace_wide<false, false, RcIoViewFactors><<<blocks, RC_TRACE_THREADS, 0, st>>>(sc, io, total, work, nullptr, overflow + 1);  // overflow = &d_overflow[1]; [2] is the flagged-ray scratch
+    cudaMemsetAsync(overflow + 1, 0, sizeof(uint32_t), st);  // overflow = &d_overflow[1]; [2] counts the rays flagged for the fix-up pass
+    k_trace_wide<false, false, RcIoViewFactors><<<blocks, RC_TRACE_THREADS, 0, st>>>(sc, io, total, work, nullptr, overflow + 1);
+    k_view_factor_fixup<<<blocks, RC_TRACE_THREADS, 0, st>>>(io, total, overflow + 1);
+    cudaFreeAsync(bits, st);
 }
 
 __global__ void k_flat_metadata(const RcFlatBlas *__restrict__ flat, uint32_t n_blas, uint32_t n_prims, uint32_t *__restrict__ out) {

@@ -697,7 +697,7 @@ int32_t rc_view_factors(rc_context *ctx, uint32_t rays_per_triangle, uint64_t se
     rc_launch_view_factors(ctx->stream, make_scene(ctx), ctx->d_flat, ctx->n_flat_blas, ctx->n_flat_prims, rays_per_triangle, seed, row_base, n_rows, n_cols, d_out,
                            nullptr, d_skipped, ctx->d_overflow + 1, ctx->max_blocks, ctx->d_work);
     cudaEventRecord(ctx->ev_t1, ctx->stream);
-    ctx->last_launches = 1;
+    ctx->last_launches = 2;
     unsigned long long sk = 0;
     RC_CUDA(ctx, cudaMemcpyAsync(&sk, d_skipped, 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (!(flags & RC_HITS_ON_DEVICE)) {

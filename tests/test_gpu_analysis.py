@@ -7,6 +7,7 @@ from raycore_b200 import workloads as W
 import raycore_b200 as rc
 import engines
 import kat
+import parity
 
 pytestmark = pytest.mark.gpu
 
@@ -66,3 +67,34 @@ def test_view_factors_same_rays_exact_and_statistics():
     assert np.array_equal(np.vstack([a, b]), vf_g)
     # uniform stream itself is identical on both sides
     assert np.array_equal(rays["o"].shape, (n_prims * rpt, 3))
+
+
+def test_view_factors_deep_trees_fixup():
+    """view_factors! on exponentially nested geometry: some of the generated rays need more than the 32-entry short stack; the
+    scheduler kernel flags them in a bitmap and k_view_factor_fixup redoes them with the deep-stack body.  The matrix must
+    still equal the oracle's on identical rays."""
+    from test_gpu_parity import _deep_scene
+
+    blas = _deep_scene(20)
+    g14 = [2.0 ** -i for i in range(14)]
+    xf = np.stack([W.trs3x4((4 * a, 4 * b, 4 * g14[(i + j) % 14]), (1, 0, 0, 0), 1.0) for i, a in enumerate(g14) for j, b in enumerate(g14)])
+    pushes = [(blas, None, xf, None)]
+    o, g = engines.OracleEngine(pushes), engines.GpuEngine(pushes)
+    rpt = 2
+    rays = g.tlas.view_factor_rays(rpt, seed=3)
+    hits = g.tlas.adapt().trace_closest(rays, counters=True)
+    deep = g.tlas.counters()["max_stack"]
+    assert deep > 32, f"scene no longer exercises the fix-up pass (max stack {deep})"
+    vf_g = g.tlas.view_factors(rpt, seed=3)
+    # the nested copies produce many exact ties, so the matrix is compared with the one accumulated from the library's own
+    # closest hits of the same rays (same tie resolution), and those hits with the oracle under the usual parity classes
+    n = vf_g.shape[0]
+    src = np.arange(len(rays)) // rpt + 1
+    ok = (hits["hit"] == 1) & (hits["meta"] != src) & (hits["meta"] >= 1) & (hits["meta"] <= n)
+    want = np.zeros_like(vf_g)
+    np.add.at(want, (src[ok] - 1, hits["meta"][ok] - 1), 1)
+    assert np.array_equal(vf_g, want)
+    assert vf_g.sum() > 0
+    b = o.trace(rays)
+    cls = parity.classify(hits, b, parity.make_graze_verifier(orc, rays, hits, o.instances, o.tris))
+    parity.assert_parity(cls, len(rays), max_tie_frac=0.05, label="deep view-factor rays")

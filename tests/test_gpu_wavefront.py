@@ -119,3 +119,36 @@ def test_shadow_large_mesh_sample():
     rays_q = tl.queue(RAY_DTYPE, n).upload(W.interior_rays(n, seed=2))
     hits, sh, vis = _pipeline(tl, oe, rays_q, np.array([[0.1, 0.2, 0.0]], F))
     assert hits["hit"].all() and (sh["t_max"] > 0).all()
+
+
+def test_shadow_deep_trees_fixup():
+    """Occlusion rays through exponentially nested geometry overflow the 32-entry short stack: the scheduler kernel marks them
+    and k_shadow_fixup redoes them (queue and fused sources) — results must still match the oracle."""
+    from test_gpu_parity import _deep_scene
+
+    blas = _deep_scene(20)
+    g = [2.0 ** -i for i in range(14)]
+    xf = np.stack([W.trs3x4((4 * a, 4 * b, 4 * g[(i + j) % 14]), (1, 0, 0, 0), 1.0) for i, a in enumerate(g) for j, b in enumerate(g)])
+    pushes = [(blas, None, xf, None)]
+    ge, oe = GpuEngine(pushes), OracleEngine(pushes)
+    tl = ge.tlas
+    rs = np.random.RandomState(0)
+    n = 4096
+    d = (np.array([1, 1, 1], F) + rs.uniform(-0.9, 0.9, (n, 3))).astype(F)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = W.make_rays(np.full((n, 3), 1e-9, F), d)
+    tl.adapt().trace_closest(rays, counters=True)
+    assert tl.counters()["max_stack"] > 32
+    rays["t_max"] = rs.uniform(0.0, 6.0, n).astype(F)
+    rays["t_max"][::7] = 0  # dummy rays
+    q = tl.queue(RAY_DTYPE, n).upload(rays)
+    vis = tl.test_shadow_rays(q).download()
+    vo = oe.tlas.test_shadow_rays(rays)
+    diff = np.nonzero(vis != vo)[0]
+    assert len(diff) <= 2 and (vis[diff] == 0).all()  # graze class only
+    assert (vis[::7] == 0).all() and 0 < vis.sum() < n
+    # fused source on the same scene: primary rays from far outside towards the nest, lights inside it
+    org = (np.array([6, 6, 6], F) + rs.uniform(-1, 1, (n, 3))).astype(F)
+    prim = W.make_rays(org, (-org / np.linalg.norm(org, axis=1, keepdims=True)).astype(F))
+    pq = tl.queue(RAY_DTYPE, n).upload(prim)
+    _pipeline(tl, oe, pq, np.array([[1.3e-3, 0.9e-3, 1.1e-3], [4.3, 4.6, 4.45]], F))  # off the 2^-k lattice the geometry sits on
