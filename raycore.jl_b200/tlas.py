@@ -559,3 +559,61 @@ def tlas_from_meshes(meshes, device: Optional[int] = None):
     handles = [tlas.push(m) for m in meshes]
     tlas.sync()
     return tlas, handles
+
+
+class BLAS4:
+    """BLAS4 / build_blas4 / closest_hit4 / any_hit4 — src/bvh4.jl:154-163, 511-522, 606-766.
+
+    The reference collapses its LBVH into 128-byte 4-wide nodes on the host; the library's own quantised 4-wide BVH (the one
+    every TLAS query already uses) backs the same API: a BLAS4 is one geometry under an identity instance, and the `*4` queries
+    are rc_trace_closest / rc_trace_any on it.  As in the reference, closest_hit4 / any_hit4 ignore ray.t_min
+    (`ray_mint = 0`, src/bvh4.jl:610, :700) and return (hit, Triangle, t, bary) without an instance index."""
+
+    def __init__(self, primitives, face_meta=None, device: Optional[int] = None):
+        v = np.ascontiguousarray(np.asarray(primitives, np.float32).reshape(-1, 9))
+        if len(v) == 0:
+            raise RaycoreError(L.RC_ERR_NO_VALID_TRIANGLES, "Cannot build BLAS4 from empty primitive list")  # src/bvh4.jl:513
+        self._tlas = TLAS(device)
+        self._handle = self._tlas.push(v, None, face_meta=face_meta)
+        self._tlas.sync()
+
+    @property
+    def root_aabb(self) -> Bounds3:
+        return self._tlas.world_bound()
+
+    @property
+    def n_primitives(self) -> int:
+        return self._tlas.sizes()["blas_prims"]
+
+    def _rays(self, rays):
+        r = _as_rays(rays).copy()
+        r["t_min"] = 0.0
+        return r
+
+    def trace_closest4(self, rays) -> np.ndarray:
+        return self._tlas._trace(self._rays(rays), any_hit=False)
+
+    def trace_any4(self, rays) -> np.ndarray:
+        return self._tlas._trace(self._rays(rays), any_hit=True)
+
+    def closest_hit4(self, ray: Ray):
+        return self._tlas._tuple_from_hit(self.trace_closest4([ray])[0], any_hit=False)[:4]
+
+    def any_hit4(self, ray: Ray):
+        return self._tlas._tuple_from_hit(self.trace_any4([ray])[0], any_hit=True)[:4]
+
+    def free(self):
+        self._tlas.free()
+
+
+def build_blas4(primitives, face_meta=None, device: Optional[int] = None) -> BLAS4:
+    """build_blas4(primitives) -> BLAS4 — src/bvh4.jl:511-522"""
+    return BLAS4(primitives, face_meta, device)
+
+
+def closest_hit4(blas: BLAS4, ray: Ray):
+    return blas.closest_hit4(ray)
+
+
+def any_hit4(blas: BLAS4, ray: Ray):
+    return blas.any_hit4(ray)

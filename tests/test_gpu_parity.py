@@ -201,3 +201,31 @@ def test_edge_case_rays_and_geometry():
     many = np.repeat(rays[:1], 100003)
     h = g.trace(many)
     assert (h["hit"] == 1).all() and (h["t"] == h["t"][0]).all()
+
+
+def test_blas4_api():
+    """BLAS4 / build_blas4 / closest_hit4 / any_hit4 (src/bvh4.jl:511-766): one geometry, no instance index in
+    the result, ray.t_min ignored (`ray_mint = 0`, :610)."""
+    import raycore_b200 as rc
+
+    verts = W.uv_sphere(32, (0, 0, 2), 1.0)
+    blas = rc.build_blas4(verts)
+    o = engines.OracleEngine([(verts, None, [kat.I34], None)])
+    rays = W.pinhole_rays(128, 128, camera_pos=(0, 0, 0))
+    rays["t_min"] = 1.5  # beyond the front surface for the central rays: closest_hit4 must still report the front hit
+    a = blas.trace_closest4(rays)
+    r0 = rays.copy()
+    r0["t_min"] = 0
+    b = o.trace(r0)
+    cls = parity.classify(a, b, parity.make_graze_verifier(orc, r0, a, o.instances, o.tris))
+    parity.assert_parity(cls, len(rays), label="closest_hit4")
+    assert np.array_equal(blas.trace_any4(rays)["hit"], o.trace(r0, any_hit=True)["hit"])
+    hit, tri, t, bary = rc.closest_hit4(blas, rc.Ray((0, 0, 0), (0, 0, 1), 1.5))
+    assert hit and abs(float(t) - 1.0) < 1e-3 and len(bary) == 3 and abs(float(bary.sum()) - 1) < 1e-6
+    assert tri.vertices.shape == (3, 3)
+    hit, _, t, _ = rc.any_hit4(blas, rc.Ray((0, 0, 0), (0, 1, 0)))
+    assert not hit and t == 0
+    assert blas.n_primitives == len(o.tris[1])
+    with pytest.raises(rc.RaycoreError):
+        rc.build_blas4(np.zeros((0, 9), np.float32))
+    blas.free()
