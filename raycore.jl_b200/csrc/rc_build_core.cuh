@@ -64,9 +64,9 @@ RC_HD uint32_t rc_quant_exponent(float extent) {
     uint32_t e = (bits >> 23) & 0xFFu;
     if (bits & 0x7FFFFFu) e += 1;
     if (e < 1u) e = 1u;
-    if (e > 254u) e = 254u;
+    if (e > RC_QUANT_EXP_MAX) e = RC_QUANT_EXP_MAX;
     // guard the rounding of extent/255: make sure 255 * scale really covers the extent
-    while (e < 254u && u2f(e << 23) * 255.0f < extent) e += 1;
+    while (e < RC_QUANT_EXP_MAX && u2f(e << 23) * 255.0f < extent) e += 1;
     return e;
 }
 
@@ -121,13 +121,12 @@ RC_HD RcNode4 rc_collapse_node(uint32_t idx, const RcBox *boxes, const RcTopo *t
     uint32_t ex = rc_quant_exponent(own.hi[0] - own.lo[0]);
     uint32_t ey = rc_quant_exponent(own.hi[1] - own.lo[1]);
     uint32_t ez = rc_quant_exponent(own.hi[2] - own.lo[2]);
-    nd.exp = ex | (ey << 8) | (ez << 16);
+    nd.sx = u2f((ex + 24u) << 23); nd.sy = u2f((ey + 24u) << 23); nd.sz = u2f((ez + 24u) << 23);
     float sx = u2f(ex << 23), sy = u2f(ey << 23), sz = u2f(ez << 23);
     uint32_t qlo[3] = {0, 0, 0}, qhi[3] = {0, 0, 0}, ch[4];
     for (int k = 0; k < 4; k++) {
-        if (k >= ns) {
-            ch[k] = RC_INVALID;
-            for (int a = 0; a < 3; a++) { qlo[a] |= 255u << (8 * k); }  // inverted box: never hit
+        if (k >= ns) {  // unused slot: inverted box + child 0's reference (filled in below)
+            for (int a = 0; a < 3; a++) { qlo[a] |= 255u << (8 * k); }
             continue;
         }
         uint32_t c = slots[k];
@@ -151,9 +150,8 @@ RC_HD RcNode4 rc_collapse_node(uint32_t idx, const RcBox *boxes, const RcTopo *t
     }
     nd.qlox = qlo[0]; nd.qloy = qlo[1]; nd.qloz = qlo[2];
     nd.qhix = qhi[0]; nd.qhiy = qhi[1]; nd.qhiz = qhi[2];
+    for (int k = ns; k < 4; k++) ch[k] = ch[0];
     nd.child0 = ch[0]; nd.child1 = ch[1]; nd.child2 = ch[2]; nd.child3 = ch[3];
-    nd.src_node = idx;
-    nd.pad = (uint32_t)ns;
     return nd;
 }
 

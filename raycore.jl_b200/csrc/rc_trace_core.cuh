@@ -170,14 +170,14 @@ struct RcWideHit {
 // Test the 4 quantised child boxes of `nd` against the ray (o, inv) over [t_lo, t_hi]; returns the hit
 // children sorted near -> far.
 RC_HD void rc_wide_node_test(const rc_f4 &n0, const rc_f4 &n1, const rc_f4 &n2, const rc_f4 &n3, f3 o, f3 inv, float t_lo, float t_hi, RcWideHit &h) {
-    uint32_t e = n0.w;
-    float ax = u2f((e & 0xFFu) << 23) * inv.x, ay = u2f(((e >> 8) & 0xFFu) << 23) * inv.y, az = u2f(((e >> 16) & 0xFFu) << 23) * inv.z;
+    const float k24 = 5.9604644775390625e-8f;  // 2^-24: the node stores its scales pre-multiplied by 2^24 (exact rescale)
+    float ax = (u2f(n0.w) * k24) * inv.x, ay = (n3.z * k24) * inv.y, az = (u2f(n3.w) * k24) * inv.z;
     float bx = (n0.x - o.x) * inv.x, by = (n0.y - o.y) * inv.y, bz = (n0.z - o.z) * inv.z;
     // error bound of fmaf(q, a, b) over q in [0,255] (both products rounded once, b rounded twice)
     float slack = RC_BOX_EPS * fmaxf(fmaxf(fmaf(255.0f, fabsf(ax), fabsf(bx)), fmaf(255.0f, fabsf(ay), fabsf(by))), fmaf(255.0f, fabsf(az), fabsf(bz)));
     uint32_t qlox = f2u(n1.x), qloy = f2u(n1.y), qloz = f2u(n1.z), qhix = n1.w;
     uint32_t qhiy = f2u(n2.x), qhiz = f2u(n2.y);
-    uint32_t ch[4] = {f2u(n2.z), n2.w, f2u(n3.x), f2u(n3.y)};
+    uint32_t ch[4] = {f2u(n2.z), n2.w, f2u(n3.x), f2u(n3.y)};  // unused slots repeat child 0 under an inverted box
     // choose near/far planes per axis by the sign of the direction
     uint32_t nx = inv.x >= 0.0f ? qlox : qhix, fx = inv.x >= 0.0f ? qhix : qlox;
     uint32_t ny = inv.y >= 0.0f ? qloy : qhiy, fy = inv.y >= 0.0f ? qhiy : qloy;
@@ -190,7 +190,7 @@ RC_HD void rc_wide_node_test(const rc_f4 &n0, const rc_f4 &n1, const rc_f4 &n2, 
         float tnz = fmaf(rc_q2f(nz, k), az, bz), tfz = fmaf(rc_q2f(fz, k), az, bz);
         float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, t_lo));
         float tf = fminf(fminf(tfx, tfy), fminf(tfz, t_hi));
-        bool hit = (tn <= tf + slack) && (ch[k] != RC_INVALID);
+        bool hit = tn <= tf + slack;
         if (hit) {
             // insertion sort by tn (<= 4 elements)
             int j = h.n++;

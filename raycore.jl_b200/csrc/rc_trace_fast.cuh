@@ -104,7 +104,7 @@ template <bool ANY, bool COUNT, class IO>
 __global__ void __launch_bounds__(RC_TRACE_THREADS, RC_MIN_BLOCKS) k_trace_wide(RcScene sc, IO io, unsigned long long n,
                                                                  unsigned long long *__restrict__ work, RcCounters *__restrict__ counters,
                                                                  uint32_t *__restrict__ overflow) {
-    // rows: 0 guard (always RC_INVALID), 1..RC_SSTACK live entries, +3 overflow scratch, last = dummy row for rejected pushes
+    // rows: 0 guard (always RC_INVALID), 1..RC_SSTACK live entries, +4 scratch (<= 3 pushes past the limit before the overflow check, + 1 rejected store)
     __shared__ uint32_t sstack[(RC_SSTACK + 5) * RC_TRACE_THREADS];
     const uint32_t FULL = 0xFFFFFFFFu;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, lt_mask = (1u << lane) - 1u;
@@ -112,32 +112,37 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, RC_MIN_BLOCKS) k_trace_wide(
     unsigned long long traced = 0, idx = 0;
     f3 wo = mk3(0, 0, 0), wd = mk3(0, 0, 0), o = wo, d = wd, inv = wo;
     float t_min = 0.f, t_max = 0.f, hit_u = 0.f, hit_v = 0.f;
-    int cur_inst = -1, best_inst = -1, sp = 0;
+    int cur_inst = -1, best_inst = -1;
+    uint32_t *const sbase = sstack + tid;  // row 0 of this lane's column (the guard row)
+    uint32_t *spa = sbase;                 // top of the stack
     uint32_t best_prim = 0, best_meta = 0;
     const RcTri *tris = nullptr;
     const RcNode4 *nodes = sc.tlas4;
     uint32_t cur = RC_INVALID, leaf = 0, leaf_k = 0, vote = RC_VOTE_F;
     bool have = false, ovf = false;
 
-    // branch-free conditional push: a rejected entry lands in the dummy row.  Row sp holds the top of the stack; the guard row 0
-    // makes the speculative read of an empty stack harmless, so neither push nor pop needs a clamp.
-#define RC_PUSH_IF(cond, v)                                                  \
-    {                                                                        \
-        const int row_ = (cond) ? sp + 1 : RC_SSTACK + 4;                    \
-        sstack[row_ * RC_TRACE_THREADS + tid] = (v);                         \
-        sp += (cond) ? 1 : 0;                                                \
+    // Branch-free conditional push: the value is always stored one row above the top and the top pointer only advances when the
+    // push is accepted, so a rejected value is simply overwritten by the next push (rows above the top are don't-care).  Row 0 is
+    // a guard row that always holds RC_INVALID, so the speculative read of an empty stack is harmless and neither push nor pop
+    // needs a clamp.
+#define RC_ROW RC_TRACE_THREADS
+#define RC_PUSH_IF(cond, v)              \
+    {                                    \
+        spa[RC_ROW] = (v);               \
+        spa += (cond) ? RC_ROW : 0;      \
     }
-#define RC_TOP() (sstack[sp * RC_TRACE_THREADS + tid])
+#define RC_TOP() (*spa)
+#define RC_DEPTH() ((uint32_t)(spa - sbase) / RC_ROW)
     // after a step: park a freshly reached BLAS leaf (so the lane can keep descending) and recompute the lane's vote
 #define RC_SETTLE()                                                                                                \
     {                                                                                                              \
-        if (sp > RC_SSTACK) { ovf = true; cur = RC_INVALID; leaf = 0; sp = 0; }                                    \
+        if (spa > sbase + RC_SSTACK * RC_ROW) { ovf = true; cur = RC_INVALID; leaf = 0; spa = sbase; }               \
         const bool park_ = ((cur ^ RC_LEAF_BIT) < 0x40000000u) && leaf == 0; /* BLAS leaf reference */              \
         const uint32_t top_ = RC_TOP();                                                                            \
         leaf = park_ ? cur : leaf;                                                                                 \
         leaf_k = park_ ? 0u : leaf_k;                                                                              \
         cur = park_ ? top_ : cur;                                                                                  \
-        sp -= park_ ? 1 : 0;                                                                                       \
+        spa -= park_ ? RC_ROW : 0;                                                                                 \
         vote = ((int)cur >= 0) ? RC_VOTE_N : 0u;                                                                   \
         vote |= leaf ? RC_VOTE_T : ((cur == RC_INVALID) ? RC_VOTE_F : 0u);                                         \
         /* level change: instance leaf or sentinel = [0xC0000000, 0xF0000000); the sentinel waits for the parked leaf */ \
@@ -182,9 +187,9 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, RC_MIN_BLOCKS) k_trace_wide(
                     inv = mk3(rc_fast_inv(d.x), rc_fast_inv(d.y), rc_fast_inv(d.z));
                     cur_inst = -1; best_inst = -1; ovf = false;
                     nodes = sc.tlas4;
-                    sstack[tid] = RC_INVALID;                     // guard row
-                    sstack[RC_TRACE_THREADS + tid] = RC_INVALID;  // stack bottom: popping it ends the ray
-                    sp = 1;
+                    sbase[0] = RC_INVALID;       // guard row
+                    sbase[RC_ROW] = RC_INVALID;  // stack bottom: popping it ends the ray
+                    spa = sbase + RC_ROW;
                     cur = 1;
                     leaf = 0;
                     vote = RC_VOTE_N;
@@ -205,7 +210,7 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, RC_MIN_BLOCKS) k_trace_wide(
                     best_prim = __float_as_uint(a.w);
                     best_meta = __float_as_uint(b.w);
                     hit_u = u; hit_v = v;
-                    if (ANY) { cur = RC_INVALID; sp = 0; leaf_k = count; }
+                    if (ANY) { cur = RC_INVALID; spa = sbase; leaf_k = count; }
                 }
                 if (++leaf_k >= count) {
                     leaf = 0;
@@ -219,7 +224,7 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, RC_MIN_BLOCKS) k_trace_wide(
                     cur_inst = -1;  // src/instanced-bvh.jl:1996-2006
                     nodes = sc.tlas4;
                     cur = RC_TOP();
-                    sp--;
+                    spa -= RC_ROW;
                     if (cur != RC_INVALID) {  // more TLAS work: restore the world ray (skipped when the ray is finished)
                         o = wo; d = wd;
                         inv = mk3(rc_fast_inv(d.x), rc_fast_inv(d.y), rc_fast_inv(d.z));
@@ -240,7 +245,7 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, RC_MIN_BLOCKS) k_trace_wide(
                     d = x_transform_direction(m, wd);
                     inv = mk3(rc_fast_inv(d.x), rc_fast_inv(d.y), rc_fast_inv(d.z));
                     RC_PUSH_IF(true, RC_SENTINEL)
-                    if (COUNT) { lc.inst_entries++; if ((uint32_t)sp > lc.max_stack) lc.max_stack = (uint32_t)sp; }
+                    if (COUNT) { lc.inst_entries++; if (RC_DEPTH() > lc.max_stack) lc.max_stack = RC_DEPTH(); }
                     cur = 1;
                 }
                 RC_SETTLE()
@@ -253,10 +258,8 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, RC_MIN_BLOCKS) k_trace_wide(
                 rc_ldg256(np, n0, n1);
                 rc_ldg256(np + 32, n2, n3);
                 if (COUNT) { lc.nodes++; lc.box_tests += 4; }
-                const uint32_t e = __float_as_uint(n0.w);
-                // a = 2^24 * scale * inv_d (decoded planes carry 2^-24), b = (origin - o) * inv_d
-                const float ax = __uint_as_float((e & 0xFFu) << 23) * (inv.x * 16777216.0f), ay = __uint_as_float(((e >> 8) & 0xFFu) << 23) * (inv.y * 16777216.0f),
-                            az = __uint_as_float(((e >> 16) & 0xFFu) << 23) * (inv.z * 16777216.0f);
+                // a = (2^24 * scale) * inv_d (decoded planes carry 2^-24; the node stores the scaled value), b = (origin - o) * inv_d
+                const float ax = n0.w * inv.x, ay = n3.z * inv.y, az = n3.w * inv.z;
                 const float bx = (n0.x - o.x) * inv.x, by = (n0.y - o.y) * inv.y, bz = (n0.z - o.z) * inv.z;
                 const float kq = 255.0f / 16777216.0f;
                 const float slack = RC_BOX_EPS_FAST * fmaxf(fmaxf(fmaf(kq, fabsf(ax), fabsf(bx)), fmaf(kq, fabsf(ay), fabsf(by))), fmaf(kq, fabsf(az), fabsf(bz)));
@@ -279,9 +282,8 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, RC_MIN_BLOCKS) k_trace_wide(
                     tn[2 * j] = (lo0 <= fminf(hi0 + slack, t_hi)) ? lo0 : CUDART_INF_F;
                     tn[2 * j + 1] = (lo1 <= fminf(hi1 + slack, t_hi)) ? lo1 : CUDART_INF_F;
                 }
-                // empty slots carry an inverted box (qlo = 255, qhi = 0) and could only pass through the slack: mask them
-                const float t0 = r0 == RC_INVALID ? CUDART_INF_F : tn[0], t1 = r1 == RC_INVALID ? CUDART_INF_F : tn[1];
-                const float t2 = r2 == RC_INVALID ? CUDART_INF_F : tn[2], t3 = r3 == RC_INVALID ? CUDART_INF_F : tn[3];
+                // unused slots carry an inverted box and child 0's reference: no validity test needed (rc_types.h)
+                const float t0 = tn[0], t1 = tn[1], t2 = tn[2], t3 = tn[3];
                 // the nearest hit child is entered next (exact argmin); the other hit children are pushed in slot order
                 const float tm = fminf(fminf(t0, t1), fminf(t2, t3));
                 const bool any_hit = tm < CUDART_INF_F;
@@ -290,17 +292,19 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, RC_MIN_BLOCKS) k_trace_wide(
                 RC_PUSH_IF(t2 < CUDART_INF_F && !e2, r2)
                 RC_PUSH_IF(t1 < CUDART_INF_F && !e1, r1)
                 RC_PUSH_IF(t0 < CUDART_INF_F && !e0, r0)
-                if (COUNT && (uint32_t)sp > lc.max_stack) lc.max_stack = (uint32_t)sp;
+                if (COUNT && RC_DEPTH() > lc.max_stack) lc.max_stack = RC_DEPTH();
                 const uint32_t top = RC_TOP();
                 const uint32_t rn = e0 ? r0 : (e1 ? r1 : (e2 ? r2 : r3));
                 cur = any_hit ? rn : top;
-                sp -= any_hit ? 0 : 1;
+                spa -= any_hit ? 0 : RC_ROW;
                 RC_SETTLE()
             }
         }
     }
 #undef RC_PUSH_IF
 #undef RC_TOP
+#undef RC_DEPTH
+#undef RC_ROW
 #undef RC_SETTLE
     if (COUNT) {
         atomicAdd(&counters->rays, traced);

@@ -27,15 +27,20 @@ struct __attribute__((aligned(16))) RcNode2 {
 
 // Wide (4-ary) node with child boxes quantised to 8 bits per plane against the node's own frame.
 //   origin o, per-axis scale 2^(e-127);  child k plane = o + q * scale,  lo rounded down, hi rounded up.
-//   qlo*/qhi*: byte k = child k.   child[k]: RC_INVALID = empty; RC_LEAF_BIT|count-1|start = leaf
-//   (BLAS: start = first Morton-sorted triangle, TLAS: start = instance index); else wide-node index.
+//   sx/sy/sz hold the scale pre-multiplied by 2^24 (the traversal kernel's plane decode yields q * 2^-24), e <= RC_QUANT_EXP_MAX.
+//   qlo*/qhi*: byte k = child k.   child[k]: RC_LEAF_BIT|count-1|start = leaf (BLAS: start = first Morton-sorted triangle,
+//   TLAS: RC_TLAS_LEAF_TAG | instance index); else wide-node index.  An unused slot repeats child 0's reference under an
+//   inverted box (qlo = 255, qhi = 0): it fails the slab test, and if rounding slack ever lets it through, the traversal
+//   merely revisits child 0 — so the kernels need no per-slot validity test.
 struct __attribute__((aligned(16))) RcNode4 {
     float ox, oy, oz;
-    uint32_t exp;  // ex | ey << 8 | ez << 16 (biased IEEE exponents)
+    float sx;
     uint32_t qlox, qloy, qloz, qhix;
     uint32_t qhiy, qhiz, child0, child1;
-    uint32_t child2, child3, src_node, pad;
+    uint32_t child2, child3;
+    float sy, sz;
 };
+#define RC_QUANT_EXP_MAX 230u  // 2^(e-127+24) must stay finite; extents beyond 255 * 2^103 overflow the reference's own Moeller-Trumbore
 
 // One triangle = 3 x float4 in Morton-sorted order:  (v0, primitive_id), (v1, metadata), (v2, face_index)
 //   primitive_id = position in the degenerate-filtered input list, face_index = position in the submitted soup

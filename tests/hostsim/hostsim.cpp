@@ -268,12 +268,14 @@ uint32_t hs_check_wide(void *b) {
         uint32_t k = todo.back();
         todo.pop_back();
         const RcNode4 &nd = t.nodes4[k];
-        float sc[3] = {u2f((nd.exp & 0xFF) << 23), u2f(((nd.exp >> 8) & 0xFF) << 23), u2f(((nd.exp >> 16) & 0xFF) << 23)};
+        const float k24 = 5.9604644775390625e-8f;
+        float sc[3] = {nd.sx * k24, nd.sy * k24, nd.sz * k24};
         float org[3] = {nd.ox, nd.oy, nd.oz};
         uint32_t ql[3] = {nd.qlox, nd.qloy, nd.qloz}, qh[3] = {nd.qhix, nd.qhiy, nd.qhiz};
         uint32_t ch[4] = {nd.child0, nd.child1, nd.child2, nd.child3};
         for (int c = 0; c < 4; c++) {
-            if (ch[c] == RC_INVALID) continue;
+            if (c > 0 && ch[c] == ch[0] && ((ql[0] >> (8 * c)) & 0xFF) == 255 && ((qh[0] >> (8 * c)) & 0xFF) == 0) continue;  // unused slot
+            if (ch[c] == RC_INVALID) { bad++; continue; }
             float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
             if (ch[c] & RC_LEAF_BIT) {
                 uint32_t start = ch[c] & RC_LEAF_START_MASK, cnt = ((ch[c] >> RC_LEAF_COUNT_SHIFT) & 7) + 1;
