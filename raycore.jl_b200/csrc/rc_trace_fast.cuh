@@ -120,6 +120,9 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, RC_MIN_BLOCKS) k_trace_wide(
     const RcNode4 *nodes = sc.tlas4;
     uint32_t cur = RC_INVALID, leaf = 0, leaf_k = 0, vote = RC_VOTE_F;
     bool have = false, ovf = false;
+    // A TLAS with a single instance needs no top-level traversal: the ray starts at that instance's leaf reference and, with no
+    // sentinel under the BLAS entries, finishes when the stack bottom is popped (saves one node step and one level change per ray).
+    const bool single = sc.n_instances == 1u;
 
     // Branch-free conditional push: the value is always stored one row above the top and the top pointer only advances when the
     // push is accepted, so a rejected value is simply overwritten by the next push (rows above the top are don't-care).  Row 0 is
@@ -190,9 +193,9 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, RC_MIN_BLOCKS) k_trace_wide(
                     sbase[0] = RC_INVALID;       // guard row
                     sbase[RC_ROW] = RC_INVALID;  // stack bottom: popping it ends the ray
                     spa = sbase + RC_ROW;
-                    cur = 1;
+                    cur = single ? RC_TLAS_LEAF_TAG : 1u;
                     leaf = 0;
-                    vote = RC_VOTE_N;
+                    vote = single ? RC_VOTE_X : RC_VOTE_N;
                     have = true;
                 }
             }
@@ -244,7 +247,7 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, RC_MIN_BLOCKS) k_trace_wide(
                     o = x_transform_point(m, wo);
                     d = x_transform_direction(m, wd);
                     inv = mk3(rc_fast_inv(d.x), rc_fast_inv(d.y), rc_fast_inv(d.z));
-                    RC_PUSH_IF(true, RC_SENTINEL)
+                    RC_PUSH_IF(!single, RC_SENTINEL)
                     if (COUNT) { lc.inst_entries++; if (RC_DEPTH() > lc.max_stack) lc.max_stack = RC_DEPTH(); }
                     cur = 1;
                 }
