@@ -120,8 +120,8 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, RC_MIN_BLOCKS) k_trace_wide(
     const RcNode4 *nodes = sc.tlas4;
     uint32_t cur = RC_INVALID, leaf = 0, leaf_k = 0, vote = RC_VOTE_F;
     bool have = false, ovf = false;
-    // A TLAS with a single instance needs no top-level traversal: the ray starts at that instance's leaf reference and, with no
-    // sentinel under the BLAS entries, finishes when the stack bottom is popped (saves one node step and one level change per ray).
+    // A TLAS with a single instance needs no top-level traversal: the refill step enters that instance directly and, with no
+    // sentinel under the BLAS entries, the ray finishes when the stack bottom is popped (saves a node step and two level changes).
     const bool single = sc.n_instances == 1u;
 
     // Branch-free conditional push: the value is always stored one row above the top and the top pointer only advances when the
@@ -150,6 +150,24 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, RC_MIN_BLOCKS) k_trace_wide(
         vote |= leaf ? RC_VOTE_T : ((cur == RC_INVALID) ? RC_VOTE_F : 0u);                                         \
         /* level change: instance leaf or sentinel = [0xC0000000, 0xF0000000); the sentinel waits for the parked leaf */ \
         vote |= (((cur + 0x40000000u) < 0x30000000u) && !(cur == RC_SENTINEL && leaf != 0)) ? RC_VOTE_X : 0u;      \
+    }
+
+    // enter instance `index`: its world->local transform applied with the reference's exact arithmetic (:1961-1977)
+#define RC_ENTER_INSTANCE(index)                                                          \
+    {                                                                                     \
+        cur_inst = (index);                                                               \
+        const char *ip_ = reinterpret_cast<const char *>(sc.inst + cur_inst);             \
+        float m_[12];                                                                     \
+        _Pragma("unroll") for (int k_ = 0; k_ < 3; k_++) {                                \
+            float4 r_ = __ldg(reinterpret_cast<const float4 *>(ip_) + k_);                \
+            m_[4 * k_] = r_.x; m_[4 * k_ + 1] = r_.y; m_[4 * k_ + 2] = r_.z; m_[4 * k_ + 3] = r_.w; \
+        }                                                                                 \
+        const ulonglong2 pp_ = __ldg(reinterpret_cast<const ulonglong2 *>(ip_ + 48));     \
+        nodes = reinterpret_cast<const RcNode4 *>(pp_.x);                                 \
+        tris = reinterpret_cast<const RcTri *>(pp_.y);                                    \
+        o = x_transform_point(m_, wo);                                                    \
+        d = x_transform_direction(m_, wd);                                                \
+        inv = mk3(rc_fast_inv(d.x), rc_fast_inv(d.y), rc_fast_inv(d.z));                  \
     }
 
     for (;;) {
@@ -185,17 +203,24 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, RC_MIN_BLOCKS) k_trace_wide(
                 } else {
                     rc_ray r = io.load(idx);
                     RcRayIn w = rc_prepare_ray(r, ANY);
-                    wo = w.o; wd = w.d; o = wo; d = wd;
+                    wo = w.o; wd = w.d;
                     t_min = w.t_min; t_max = w.t_max;
-                    inv = mk3(rc_fast_inv(d.x), rc_fast_inv(d.y), rc_fast_inv(d.z));
-                    cur_inst = -1; best_inst = -1; ovf = false;
-                    nodes = sc.tlas4;
+                    best_inst = -1; ovf = false;
                     sbase[0] = RC_INVALID;       // guard row
                     sbase[RC_ROW] = RC_INVALID;  // stack bottom: popping it ends the ray
                     spa = sbase + RC_ROW;
-                    cur = single ? RC_TLAS_LEAF_TAG : 1u;
+                    if (single) {  // straight into the only instance: no top-level node step, no sentinel, no return step
+                        RC_ENTER_INSTANCE(0)
+                        if (COUNT) lc.inst_entries++;
+                    } else {
+                        o = wo; d = wd;
+                        inv = mk3(rc_fast_inv(d.x), rc_fast_inv(d.y), rc_fast_inv(d.z));
+                        cur_inst = -1;
+                        nodes = sc.tlas4;
+                    }
+                    cur = 1;
                     leaf = 0;
-                    vote = single ? RC_VOTE_X : RC_VOTE_N;
+                    vote = RC_VOTE_N;
                     have = true;
                 }
             }
@@ -233,21 +258,8 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, RC_MIN_BLOCKS) k_trace_wide(
                         inv = mk3(rc_fast_inv(d.x), rc_fast_inv(d.y), rc_fast_inv(d.z));
                     }
                 } else {
-                    cur_inst = (int)(cur & RC_LEAF_START_MASK);  // :1961-1977; ray transformed with the reference's exact arithmetic
-                    const char *ip = reinterpret_cast<const char *>(sc.inst + cur_inst);
-                    float m[12];
-#pragma unroll
-                    for (int k = 0; k < 3; k++) {
-                        float4 r = __ldg(reinterpret_cast<const float4 *>(ip) + k);
-                        m[4 * k] = r.x; m[4 * k + 1] = r.y; m[4 * k + 2] = r.z; m[4 * k + 3] = r.w;
-                    }
-                    const ulonglong2 pp = __ldg(reinterpret_cast<const ulonglong2 *>(ip + 48));
-                    nodes = reinterpret_cast<const RcNode4 *>(pp.x);
-                    tris = reinterpret_cast<const RcTri *>(pp.y);
-                    o = x_transform_point(m, wo);
-                    d = x_transform_direction(m, wd);
-                    inv = mk3(rc_fast_inv(d.x), rc_fast_inv(d.y), rc_fast_inv(d.z));
-                    RC_PUSH_IF(!single, RC_SENTINEL)
+                    RC_ENTER_INSTANCE((int)(cur & RC_LEAF_START_MASK))
+                    RC_PUSH_IF(true, RC_SENTINEL)
                     if (COUNT) { lc.inst_entries++; if (RC_DEPTH() > lc.max_stack) lc.max_stack = RC_DEPTH(); }
                     cur = 1;
                 }
@@ -309,6 +321,7 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, RC_MIN_BLOCKS) k_trace_wide(
 #undef RC_DEPTH
 #undef RC_ROW
 #undef RC_SETTLE
+#undef RC_ENTER_INSTANCE
     if (COUNT) {
         atomicAdd(&counters->rays, traced);
         atomicAdd(&counters->nodes, (unsigned long long)lc.nodes);

@@ -229,3 +229,28 @@ def test_blas4_api():
     with pytest.raises(rc.RaycoreError):
         rc.build_blas4(np.zeros((0, 9), np.float32))
     blas.free()
+
+
+@pytest.mark.parametrize("any_hit", [False, True])
+def test_single_instance_shortcut_with_transform(any_hit):
+    """A TLAS with exactly one instance skips the top-level traversal in the scheduler kernel (the refill step enters the
+    instance directly): rotated / scaled / translated instance, rays that miss its world box, custom instance id."""
+    verts = W.uv_sphere(48)
+    xf = W.random_trs(1, seed=21, extent=3.0, smin=0.4, smax=2.5)
+    pushes = [(verts, None, xf, np.array([77], np.uint32))]
+    o, g = engines.OracleEngine(pushes), engines.GpuEngine(pushes)
+    c = xf[0].reshape(3, 4)[:, 3]
+    n = 60000
+    rays = W.box_rays(n, seed=4, half=6.0)
+    rays["o"] += c  # around the instance
+    far = W.make_rays(np.full((100, 3), 50.0, np.float32) + c, np.tile(np.array([[0, 1, 0]], np.float32), (100, 1)))  # miss the world box
+    rays = np.concatenate([rays, far])
+    a, b = g.trace(rays, any_hit=any_hit), o.trace(rays, any_hit=any_hit)
+    if any_hit:
+        assert np.array_equal(a["hit"], b["hit"])
+    else:
+        cls = parity.classify(a, b, parity.make_graze_verifier(orc, rays, a, o.instances, o.tris))
+        s = parity.assert_parity(cls, len(rays), label="single instance")
+        assert s["exact"] > 0.99 * len(rays)
+    assert 0.02 < a["hit"].mean() < 0.98 and a["hit"][-100:].sum() == 0
+    assert (a["instance_custom_index"][a["hit"] == 1] == 77).all() and (a["instance_id"][a["hit"] == 1] == 0).all()
