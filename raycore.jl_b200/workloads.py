@@ -67,6 +67,17 @@ def bumpy_sphere(n: int, center=(0.0, 0.0, 0.0), r0: float = 1.0) -> np.ndarray:
     return _grid_sphere(n, center, lambda T, P: r0 * (1.0 + 0.15 * np.sin(7 * T) * np.sin(5 * P)))
 
 
+def is_degenerate(tris: np.ndarray) -> np.ndarray:
+    """is_degenerate (src/triangle_mesh.jl:14-17) for a float32 (n, 9) soup, evaluated in Float32 like the reference:
+    c = (v3 - v1) x (v2 - v1), degenerate iff dot(c, c) == 0 (`≈ 0f0` on Float32 is an exact test)."""
+    v = np.asarray(tris, np.float32).reshape(-1, 3, 3)
+    a, b = v[:, 2] - v[:, 0], v[:, 1] - v[:, 0]
+    cx = a[:, 1] * b[:, 2] - a[:, 2] * b[:, 1]
+    cy = a[:, 2] * b[:, 0] - a[:, 0] * b[:, 2]
+    cz = a[:, 0] * b[:, 1] - a[:, 1] * b[:, 0]
+    return ((cx * cx + cy * cy) + cz * cz) == 0
+
+
 def box_mesh(lo=(-0.5, -0.5, -0.5), hi=(0.5, 0.5, 0.5)) -> np.ndarray:
     """12-triangle axis-aligned box (stress_box analogue, test/test_tlas_stress.jl:40), outward winding."""
     x0, y0, z0 = lo

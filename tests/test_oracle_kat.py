@@ -139,3 +139,21 @@ def test_analysis_oracle_sanity():
     assert min(u) >= 0 and max(u) < 1 and len(set(u)) > 190
     un = np.array([W.rng_uniform(7, np.arange(50, dtype=np.uint64), d) for d in range(4)]).T.reshape(-1)
     assert np.array_equal(np.array(u, np.float32), un)
+
+
+def test_workloads_degenerate_filter_matches_oracle():
+    """raycore_b200.workloads.is_degenerate (numpy, used by bench.py to number view-factor metadata) == the oracle's restatement of
+    is_degenerate (src/triangle_mesh.jl:14-17) on pole faces, exact duplicates, collinear and tiny-but-valid triangles."""
+    from raycore_b200 import workloads as W
+
+    soup = np.concatenate([W.uv_sphere(24), W.bumpy_sphere(40, (1, 2, 3), 0.5), W.box_mesh()])
+    rng = np.random.default_rng(0)
+    extra = rng.normal(size=(200, 9)).astype(np.float32)
+    extra[:50, 3:6] = extra[:50, 0:3]  # repeated vertex
+    extra[50:100, 6:9] = extra[50:100, 0:3] + 2 * (extra[50:100, 3:6] - extra[50:100, 0:3])  # collinear (up to rounding)
+    extra[100:150] *= 1e-18  # cross product underflows towards zero
+    soup = np.concatenate([soup, extra])
+    want = np.array([bool(orc.is_degenerate(v)) for v in soup])
+    got = W.is_degenerate(soup)
+    assert np.array_equal(got, want)
+    assert 0 < got.sum() < len(soup)

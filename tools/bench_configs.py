@@ -146,7 +146,7 @@ def main():
     tl = rc.TLAS()
     base = 0
     for msh in meshes:
-        keep = ~np.array([orc.is_degenerate(v) for v in msh])
+        keep = ~W.is_degenerate(msh)
         meta = np.zeros(len(msh), np.uint32)
         meta[keep] = base + 1 + np.arange(keep.sum())
         base += int(keep.sum())
