@@ -1,7 +1,7 @@
 #!/usr/bin/env python
-"""Measure every BASELINE.json config (C1..C5) on one GPU and print one JSON object.
+"""(test infrastructure: compares against oracle/) Measure every BASELINE.json config (C1..C5) on one GPU and print one JSON object.
 Complements bench.py (which carries the headline C2 metric and the driver contract).  Usage:
-    python tools/bench_configs.py [--quick] > gpurun_out/configs.json
+    python tests/bench_configs.py [--quick] > gpurun_out/configs.json
 """
 import argparse
 import ctypes as C
