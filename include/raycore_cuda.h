@@ -114,7 +114,9 @@ int32_t rc_set_stream(rc_context *ctx, void *stream);
  *   verts: n_faces*9 floats; face_meta: NULL => metadata = 1-based face index before filtering.
  *   transforms: m*12 floats; inv_transforms: NULL => mat3x4_inverse (:1675-1687) is evaluated by the
  *   library, else used verbatim (lets the Julia shim pass its own results for bit identity);
- *   instance_ids: NULL => 0 ("inherit", :656-657).  m must be >= 1. */
+ *   instance_ids: NULL => 0 ("inherit", :656-657).  m must be >= 1.
+ * Geometry (or, at rc_sync, a scene) whose extent exceeds 255 * 2^103 is refused with RC_ERR_INVALID_ARGUMENT: the wide
+ * nodes' quantisation frame cannot cover it (and the reference's own single-precision triangle test overflows long before). */
 int32_t rc_push(rc_context *ctx, const float *verts, uint32_t n_faces, const uint32_t *face_meta, const float *transforms,
                 const float *inv_transforms, const uint32_t *instance_ids, uint32_t m, uint32_t flags, uint32_t *handle_out);
 /* delete!(tlas, handle)::Bool — src/instanced-bvh.jl:690-699.  *deleted = 0 for unknown / already deleted. */

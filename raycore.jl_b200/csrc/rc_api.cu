@@ -74,6 +74,7 @@ struct rc_context {
     } while (0)
 
 static inline void use_device(const rc_context *ctx) { cudaSetDevice(ctx->device); }
+static int32_t builder_error_code(const std::string &err) { return err.find("supported range") != std::string::npos ? RC_ERR_INVALID_ARGUMENT : RC_ERR_CUDA; }
 
 static RcScene make_scene(const rc_context *ctx) {
     RcScene sc;
@@ -208,7 +209,7 @@ static int32_t build_blas_from(rc_context *ctx, const float *verts, uint32_t n_f
     if (!ok) {
         rc_free_blas(out, ctx->stream);
         if (err == "Geometry has no valid triangles") RC_FAIL(ctx, RC_ERR_NO_VALID_TRIANGLES, err);
-        RC_FAIL(ctx, RC_ERR_CUDA, err);
+        RC_FAIL(ctx, builder_error_code(err), err);
     }
     return RC_OK;
 }
@@ -345,7 +346,7 @@ static int32_t rebuild(rc_context *ctx) {  // rebuild_bvh! :962-993 + build_flat
     }
     uint32_t n = (uint32_t)ctx->instances.size();
     std::string err;
-    if (!rc_build_tlas(ctx->stream, ctx->instances.data(), n, ptrs, roots, &ctx->tlas, err)) RC_FAIL(ctx, RC_ERR_CUDA, err);
+    if (!rc_build_tlas(ctx->stream, ctx->instances.data(), n, ptrs, roots, &ctx->tlas, err)) RC_FAIL(ctx, builder_error_code(err), err);
     if (ctx->d_flat) { cudaFreeAsync(ctx->d_flat, ctx->stream); ctx->d_flat = nullptr; }
     // the reference drains the flat arrays when no instance is left (:969-978) but keeps every BLAS otherwise
     ctx->n_flat_blas = n == 0 && ctx->blas.empty() ? 0 : (uint32_t)flat.size();
@@ -374,7 +375,7 @@ int32_t rc_sync(rc_context *ctx, int32_t *action) {  // sync!, :894-921
         if (action) *action = RC_SYNC_REBUILD;
     } else {
         std::string err;  // refit_tlas!, :2197-2222
-        if (!rc_refit_tlas(ctx->stream, ctx->instances.data(), (uint32_t)ctx->instances.size(), &ctx->tlas, err)) RC_FAIL(ctx, RC_ERR_CUDA, err);
+        if (!rc_refit_tlas(ctx->stream, ctx->instances.data(), (uint32_t)ctx->instances.size(), &ctx->tlas, err)) RC_FAIL(ctx, builder_error_code(err), err);
         ctx->transforms_dirty = false;
         if (action) *action = RC_SYNC_REFIT;
     }

@@ -522,6 +522,17 @@ struct RcTemps {
 #define TMP(ptr, count) \
     if (!tmp.get(&(ptr), (count), err)) return false
 
+// The wide nodes quantise against 2^(e-127) with e <= RC_QUANT_EXP_MAX: extents beyond 255 * 2^103 (where the reference's own
+// Moeller-Trumbore already overflows) are refused instead of being traversed with boxes that do not cover them.
+static bool extent_supported(const float aabb[6], std::string &err) {
+    const float limit = 255.0f * 1.0141204801825835e31f;  // 255 * 2^103
+    for (int k = 0; k < 3; k++) {
+        const float e = aabb[3 + k] - aabb[k];
+        if (e > limit) { err = "geometry extent exceeds the supported range (255 * 2^103)"; return false; }
+    }
+    return true;
+}
+
 bool rc_build_blas(cudaStream_t st, const float *d_verts, const uint32_t *d_face_meta, uint32_t n_faces, RcDeviceBlas *out, std::string &err) {
     *out = RcDeviceBlas();
     if (n_faces == 0) { err = "Geometry has no valid triangles"; return false; }
@@ -574,8 +585,9 @@ bool rc_build_blas(cudaStream_t st, const float *d_verts, const uint32_t *d_face
     CK(cudaMemcpyAsync(out->root_aabb, d_small + 10, 24, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
-    return true;
+    return extent_supported(out->root_aabb, err);
 }
+
 
 // ---------------------------------------------------------------------------------------------- TLAS
 // instance world boxes + scene bounds (compute_instance_aabbs_kernel!, kernels.jl:65-78; host reduction :1499-1512)
@@ -704,7 +716,7 @@ bool rc_build_tlas(cudaStream_t st, const rc_instance_desc *h_inst, uint32_t n, 
     CK(cudaMemcpyAsync(t->root_aabb, t->d_small + 10, 24, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
-    return true;
+    return extent_supported(t->root_aabb, err);
 }
 
 bool rc_refit_tlas(cudaStream_t st, const rc_instance_desc *h_inst, uint32_t n, RcDeviceTlas *t, std::string &err) {
@@ -718,5 +730,5 @@ bool rc_refit_tlas(cudaStream_t st, const rc_instance_desc *h_inst, uint32_t n, 
     CK(cudaMemcpyAsync(t->root_aabb, t->d_small + 10, 24, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
-    return true;
+    return extent_supported(t->root_aabb, err);
 }

@@ -201,3 +201,27 @@ def test_churn_invariants():
             assert not tlas.dirty and not tlas.transforms_dirty
             for h, m in live.items():
                 assert tlas.n_instances(h) == m
+
+
+def test_extent_beyond_quantisation_range_is_refused():
+    """Wide nodes quantise against 2^(e-127), e <= 230: geometry whose extent exceeds 255 * 2^103 is refused at push / sync
+    (the reference's own triangle test overflows there) instead of being traversed with boxes that do not cover it."""
+    import raycore_b200 as rc
+    from raycore_b200 import workloads as W
+
+    tl = rc.TLAS()
+    big = (W.box_mesh() * np.float32(1e34)).astype(np.float32)
+    with pytest.raises(rc.RaycoreError):
+        tl.push(big, None)
+    # still usable afterwards; a large but supported scene works
+    ok = (W.box_mesh() * np.float32(1e8)).astype(np.float32)
+    tl.push(ok, None)
+    tl.sync()
+    h = tl.trace_closest(W.make_rays([[1e6, 2e6, -1e9]], [[0, 0, 1]]))
+    assert h["hit"][0] == 1 and np.isclose(h["t"][0], 1e9 - 0.5e8, rtol=1e-5)
+    # instances flung apart beyond the range: refused at sync
+    far = W.translation3x4((3e34, 0, 0))
+    tl.push(W.box_mesh(), far)
+    with pytest.raises(rc.RaycoreError):
+        tl.sync()
+    tl.free()
