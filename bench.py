@@ -68,6 +68,13 @@ def ncu_traffic(rays_per_launch):
         return None
 
 
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe): one `nvidia-smi -lms 20`
     process is read continuously; only samples stamped between mark_start() and mark_end() are summarised."""
@@ -89,7 +96,9 @@ class ClockSampler:
 
     def __enter__(self):
         self.t.start()
-        time.sleep(0.15)  # let the first samples arrive before the timed region starts
+        deadline = time.time() + 10.0  # nvidia-smi needs a second or more to initialise on an 8-GPU box: wait for its first sample
+        while not self.rows and time.time() < deadline:
+            time.sleep(0.02)
         return self
 
     def mark_start(self):
@@ -150,11 +159,11 @@ def run_reference(args):
     inst = orc.make_instances(1, [orc.identity3x4()], [1])
     tlas = orc.OracleTLAS([blas], inst)
     build_s = time.time() - t0
-    cores = orc.max_threads()
+    cores = host_threads()  # all the cores this process may run on (torchrun exports OMP_NUM_THREADS=1: ask for them explicitly)
     n = CPU_SAMPLE
     # the sample = the first CPU_SAMPLE rays of the benchmark's own ray set; the oracle traces the primaries itself
     prim = W.pinhole_rays(1024, 1024, camera_pos=(0.0, 0.0, -3.0))
-    ph = tlas.closest_hit(prim)
+    ph = tlas.closest_hit(prim, threads=cores)
     normals = W.geometric_normals(verts)
     order = blas.prims["input_index"]
     tris_in = orc.filter_triangles(verts)
@@ -164,10 +173,10 @@ def run_reference(args):
     rays[0::2] = W.bounce_rays(n // 2, prim, ph, nrm, seed=0x5EED)
     rays[1::2] = W.interior_rays(n - n // 2, seed=77, radius=0.8)
     for _ in range(args.warmup):
-        tlas.closest_hit(rays)
+        tlas.closest_hit(rays, threads=cores)
     t0 = time.time()
     for _ in range(args.steps):
-        tlas.closest_hit(rays)
+        tlas.closest_hit(rays, threads=cores)
     dt = time.time() - t0
     v = n * args.steps / dt / 1e6
     line = {
@@ -429,7 +438,7 @@ def main():
         vt.free()
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # the CPU baseline is an N = 1 figure (torchrun also pins OMP_NUM_THREADS=1)
         from oracle import oracle as orc
 
         t0 = time.time()
@@ -437,15 +446,16 @@ def main():
         ot = orc.OracleTLAS([ob], orc.make_instances(1, [orc.identity3x4()], [1]))
         cpu_build = time.time() - t0
         sample = rays[:CPU_SAMPLE]
-        ot.closest_hit(sample[: 1 << 16])
+        cores = host_threads()
+        ot.closest_hit(sample[: 1 << 16], threads=cores)
         t0 = time.time()
-        oh, oc = ot.closest_hit(sample, counters=True)
+        oh, oc = ot.closest_hit(sample, threads=cores, counters=True)
         dt = time.time() - t0
         # parity on the sample while we are here (ids bit-exact outside the documented classes)
         import parity
 
         cls = parity.classify(hits_np[: len(sample)], oh, None)
-        cpu = {"value": len(sample) / dt / 1e6, "unit": "Mrays/s", "cores": orc.max_threads(), "kind": "port",
+        cpu = {"value": len(sample) / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
                "sample": f"first {len(sample)} rays of the benchmark ray set, 1 pass; oracle/oracle.c (C restatement of the reference BVH2 path, OpenMP over rays; Julia absent)",
                "build_s": cpu_build, "bvh2_per_ray": {k: oc[k] / len(sample) for k in ("nodes", "box_tests", "tri_tests")},
                "parity_on_sample": {k: int(len(v)) for k, v in cls.items()}}
