@@ -148,8 +148,10 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const uint32_t *__res
 }
 
 __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in, uint32_t *__restrict__ keys_out,
-                                                             uint32_t *__restrict__ vals_out, uint32_t n, int shift, uint32_t tiles, const uint32_t *__restrict__ offs) {
+                                                             uint32_t *__restrict__ vals_out, uint32_t n, int shift, uint32_t tiles, const uint32_t *__restrict__ offs,
+                                                             const uint32_t *__restrict__ totals) {
     __shared__ uint32_t wh[RS_WARPS][256];
+    __shared__ uint32_t sm[33];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&wh[0][0])[i] = 0;
     __syncthreads();
@@ -176,10 +178,11 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const uint32_t *__
         rank[i] = prev + __popc(peers & lt_mask);
         __syncwarp();
     }
-    __syncthreads();
+    uint32_t total_;
+    const uint32_t digit_base = block_excl_scan(totals[threadIdx.x], sm, total_);  // keys with a smaller digit (includes a __syncthreads)
     {   // thread d: turn per-warp counts of digit d into exclusive prefixes starting at the global offset
         uint32_t d = threadIdx.x;
-        uint32_t off = offs[d * tiles + blockIdx.x];
+        uint32_t off = digit_base + offs[d * tiles + blockIdx.x];
 #pragma unroll
         for (int w = 0; w < RS_WARPS; w++) {
             uint32_t c = wh[w][d];
@@ -198,47 +201,36 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const uint32_t *__
     }
 }
 
-// Exclusive scan of the digit-major table hist[256][tiles] in place (one block, 32 warps; warp w owns digits w, w+32, ...):
-// coalesced row scans with a carried prefix, then the 256 row totals are scanned and added back.
-__global__ void __launch_bounds__(1024) k_scan_hist(uint32_t *__restrict__ hist, uint32_t tiles) {
-    __shared__ uint32_t tot[256];
-    __shared__ uint32_t sm[33];
-    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (uint32_t d = wid; d < 256; d += 32) {
-        uint32_t *row = hist + (size_t)d * tiles;
-        uint32_t carry = 0;
-        for (uint32_t i0 = 0; i0 < tiles; i0 += 32) {
-            uint32_t i = i0 + lane;
-            uint32_t v = i < tiles ? row[i] : 0;
-            uint32_t inc = warp_incl_scan(v);
-            if (i < tiles) row[i] = carry + inc - v;
-            carry += __shfl_sync(0xFFFFFFFFu, inc, 31);
-        }
-        if (lane == 0) tot[d] = carry;
+// Row-wise exclusive scan of the digit-major table hist[256][tiles] in place, one warp per digit row (256 warps in 32 blocks):
+// each lane sums a contiguous segment (independent loads), one warp scan orders the segments, the lane rewrites its segment.
+// The row totals go to totals[256]; k_radix_scatter turns them into the per-digit bases itself (a 256-entry block scan), so no
+// single-block pass over the whole table is needed (the one-block version was 30 us per pass at 1 M keys, a third of the build).
+__global__ void __launch_bounds__(256) k_scan_rows(uint32_t *__restrict__ hist, uint32_t tiles, uint32_t *__restrict__ totals) {
+    const uint32_t lane = threadIdx.x & 31, d = blockIdx.x * 8 + (threadIdx.x >> 5);
+    uint32_t *row = hist + (size_t)d * tiles;
+    const uint32_t seg = (tiles + 31) / 32, lo = min(lane * seg, tiles), hi = min(lo + seg, tiles);
+    uint32_t sum = 0;
+    for (uint32_t i = lo; i < hi; i++) sum += row[i];
+    const uint32_t inc = warp_incl_scan(sum);
+    uint32_t run = inc - sum;
+    for (uint32_t i = lo; i < hi; i++) {
+        const uint32_t v = row[i];
+        row[i] = run;
+        run += v;
     }
-    __syncthreads();
-    uint32_t total;
-    uint32_t mine = threadIdx.x < 256 ? tot[threadIdx.x] : 0;
-    uint32_t base = block_excl_scan(mine, sm, total);
-    if (threadIdx.x < 256) tot[threadIdx.x] = base;
-    __syncthreads();
-    for (uint32_t d = wid; d < 256; d += 32) {
-        uint32_t *row = hist + (size_t)d * tiles;
-        const uint32_t b = tot[d];
-        if (b)
-            for (uint32_t i = lane; i < tiles; i += 32) row[i] += b;
-    }
+    if (lane == 31) totals[d] = inc;
 }
 
 // sorts in place: on return keys/vals hold the sorted pairs (4 passes ping-pong through tmp buffers)
-static void radix_sort_pairs(cudaStream_t st, uint32_t *keys, uint32_t *vals, uint32_t *keys_tmp, uint32_t *vals_tmp, uint32_t n, uint32_t *hist /* 256*tiles */) {
+static void radix_sort_pairs(cudaStream_t st, uint32_t *keys, uint32_t *vals, uint32_t *keys_tmp, uint32_t *vals_tmp, uint32_t n, uint32_t *hist /* 256*tiles + 256 */) {
     uint32_t tiles = cdiv(n, RS_TILE);
     uint32_t *ki = keys, *vi = vals, *ko = keys_tmp, *vo = vals_tmp;
     for (int pass = 0; pass < 4; pass++) {
         int shift = pass * 8;
         k_radix_hist<<<tiles, RS_THREADS, 0, st>>>(ki, n, shift, tiles, hist);
-        k_scan_hist<<<1, 1024, 0, st>>>(hist, tiles);
-        k_radix_scatter<<<tiles, RS_THREADS, 0, st>>>(ki, vi, ko, vo, n, shift, tiles, hist);
+        uint32_t *totals = hist + (size_t)256 * tiles;
+        k_scan_rows<<<32, 256, 0, st>>>(hist, tiles, totals);
+        k_radix_scatter<<<tiles, RS_THREADS, 0, st>>>(ki, vi, ko, vo, n, shift, tiles, hist, totals);
         std::swap(ki, ko);
         std::swap(vi, vo);
     }
@@ -561,7 +553,7 @@ bool rc_build_blas(cudaStream_t st, const float *d_verts, const uint32_t *d_face
     TMP(d_idx, n);
     TMP(d_codes2, n);
     TMP(d_idx2, n);
-    TMP(d_hist, 256 * (size_t)cdiv(n, RS_TILE));
+    TMP(d_hist, 256 * (size_t)cdiv(n, RS_TILE) + 256);
     TMP(d_topo, n - 1);
     TMP(d_parent, 2 * (size_t)n - 1);
     TMP(d_fl, n - 1);
@@ -701,7 +693,7 @@ bool rc_build_tlas(cudaStream_t st, const rc_instance_desc *h_inst, uint32_t n, 
     TMP(d_codes, n);
     TMP(d_codes2, n);
     TMP(d_idx2, n);
-    TMP(d_hist, 256 * (size_t)rs_tiles);
+    TMP(d_hist, 256 * (size_t)rs_tiles + 256);
     CK(cudaMemcpyAsync(t->d_blas_roots, blas_roots.data(), sizeof(float) * 6 * nb, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(t->d_blas_ptrs, blas.data(), sizeof(RcBlasPtrs) * nb, cudaMemcpyHostToDevice, st));
     if (!upload_instances(st, t, h_inst, n, err)) return false;
