@@ -57,6 +57,46 @@ def measure_l2_gbs(torch, dev):
     return 2.0 * a.numel() * iters / (e0.elapsed_time(e1) * 1e-3) / 1e9
 
 
+def measure_view_factors(rc, W, L, torch, dev, local, world, rank, dist):
+    """C4: view_factors of 5 bumpy spheres (49,704 triangles) x 1000 rays per triangle into a UInt32 matrix resident in HBM.
+    N > 1: every rank holds the (replicated) scene and computes its own block of source rows, no exchange (SURVEY 8e);
+    the time is the max over ranks of the library's CUDA-event kernel time."""
+    from raycore_b200.sharding import shard_range
+
+    vt = rc.TLAS(local)
+    base = 0
+    for msh in W.viewfactor_scene(72):
+        keep = ~W.is_degenerate(msh)
+        meta = np.zeros(len(msh), np.uint32)
+        meta[keep] = base + 1 + np.arange(keep.sum())
+        base += int(keep.sum())
+        vt.push(msh, None, face_meta=meta)
+    vt.sync()
+    npr = vt.sizes()["blas_prims"]
+    row0, row1 = shard_range(npr, rank, world)
+    d_vf = torch.empty((row1 - row0) * npr, dtype=torch.int32, device=dev)
+    sk = C.c_uint64()
+    vms = []
+    for _ in range(3):
+        if dist is not None:
+            dist.barrier()
+        assert vt._lib.rc_view_factors(vt._ctx, 1000, 11, d_vf.data_ptr(), row0, row1 - row0, L.RC_HITS_ON_DEVICE, C.byref(sk)) == 0
+        vms.append(float(vt._lib.rc_last_kernel_ms(vt._ctx)))
+    ms, hits = min(vms), int(d_vf.sum().item())
+    if dist is not None:
+        t = torch.tensor([ms, float(hits)], device=dev, dtype=torch.float64)
+        mx = t.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ms, hits = float(mx[0].item()), int(t[1].item())
+    del d_vf
+    vt.free()
+    return {"view_factors_s": ms * 1e-3,
+            "view_factors_config": f"C4: 5 x bumpy_sphere(72) = {npr} triangles, rays_per_triangle=1000 ({npr * 1000} rays), UInt32 {npr}x{npr} matrix resident in HBM, "
+                                   f"{world} GPU(s): source rows sharded, no exchange",
+            "view_factors_total_hits": hits}
+
+
 def ncu_traffic(rays_per_launch):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed ncu --set full
     capture of this same command (profiles/r1_traffic.json, written by tools/ncu_summary.py); None if the capture is for
@@ -381,6 +421,8 @@ def main():
         c = tlas.counters()
         counters = {k: c[k] / m for k in ("nodes", "box_tests", "tri_tests", "inst_entries")} | {"max_stack": c["max_stack"]}
 
+    vf = None if args.no_extras else measure_view_factors(rc, W, L, torch, dev, local, world, rank, dist if world > 1 else None)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -413,29 +455,10 @@ def main():
         "per_ray": counters,
     }
 
-    # ---- the other two numbers of BASELINE.json's metric: BVH build ms (above) and view_factors s (C4) ------------------------
+    # ---- the other two numbers of BASELINE.json's metric: BVH build ms (above) and view_factors s (C4, measured before the ranks part)
     extras = None
-    if not args.no_extras:
-        vt = rc.TLAS(local)
-        base = 0
-        for msh in W.viewfactor_scene(72):
-            keep = ~W.is_degenerate(msh)
-            meta = np.zeros(len(msh), np.uint32)
-            meta[keep] = base + 1 + np.arange(keep.sum())
-            base += int(keep.sum())
-            vt.push(msh, None, face_meta=meta)
-        vt.sync()
-        npr = vt.sizes()["blas_prims"]
-        d_vf = torch.empty(npr * npr, dtype=torch.int32, device=dev)
-        sk = C.c_uint64()
-        vms = []
-        for _ in range(3):
-            assert vt._lib.rc_view_factors(vt._ctx, 1000, 11, d_vf.data_ptr(), 0, npr, L.RC_HITS_ON_DEVICE, C.byref(sk)) == 0
-            vms.append(float(vt._lib.rc_last_kernel_ms(vt._ctx)))
-        extras = {"view_factors_s": min(vms) * 1e-3, "view_factors_config": f"C4: 5 x bumpy_sphere(72) = {npr} triangles, rays_per_triangle=1000 ({npr * 1000} rays), UInt32 {npr}x{npr} matrix resident in HBM, 1 GPU",
-                  "view_factors_total_hits": int(d_vf.sum().item()), "blas_build_ms_1M_triangles": min(build_dev_ms)}
-        del d_vf
-        vt.free()
+    if vf is not None:
+        extras = dict(vf, blas_build_ms_1M_triangles=min(build_dev_ms))
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:  # the CPU baseline is an N = 1 figure (torchrun also pins OMP_NUM_THREADS=1)
