@@ -203,21 +203,23 @@ end
 # Each function replaces one `kernel!(backend)(...; ndrange)` launch of the reference renderer; queues are CuArray{RTRay},
 # CuArray{RTHitResult} and CuArray{UInt8} (CuPtr arguments), lights a host Vector{Point3f}.
 const RC_ON_DEVICE = RC_RAYS_ON_DEVICE | RC_HITS_ON_DEVICE
+# device arrays come from CUDA.jl (pointer(::CuArray) is a CuPtr); the C ABI takes plain addresses
+devptr(a) = reinterpret(Ptr{Cvoid}, pointer(a))
 set_normals!(t::CuTLAS, h::TLASHandle, normals9::Matrix{Float32}) =       # 9 x n_faces: Triangle.normals per submitted face
     check(t.ctx, ccall((:rc_set_normals, lib), Int32, (Ptr{Cvoid}, UInt32, Ptr{Float32}, UInt32, UInt32), t.ctx, h.id, normals9, size(normals9, 2), 0))
 generate_primary_rays!(t::CuTLAS, rays, width, height, camera_pos, focal_length, aspect; nsamples = 1, seed = 0) =
     check(t.ctx, ccall((:rc_generate_primary_rays, lib), Int32, (Ptr{Cvoid}, UInt32, UInt32, UInt32, Ptr{Float32}, Float32, Float32, UInt64, Ptr{Cvoid}, UInt32),
-                       t.ctx, width, height, nsamples, Float32[camera_pos...], focal_length, aspect, seed, pointer(rays), 0))
+                       t.ctx, width, height, nsamples, Float32[camera_pos...], focal_length, aspect, seed, devptr(rays), 0))
 intersect_primary_rays!(t::CuTLAS, rays, hits) =
-    check(t.ctx, ccall((:rc_trace_closest, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, UInt64, UInt32), t.ctx, pointer(rays), pointer(hits), length(rays), RC_ON_DEVICE))
+    check(t.ctx, ccall((:rc_trace_closest, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, UInt64, UInt32), t.ctx, devptr(rays), devptr(hits), length(rays), RC_ON_DEVICE))
 generate_shadow_rays!(t::CuTLAS, rays, hits, lights::Vector{Point3f}, shadow_rays; shadow_bias = 0.01f0) =
     check(t.ctx, ccall((:rc_generate_shadow_rays, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, UInt64, Ptr{Float32}, UInt32, Float32, Ptr{Cvoid}, UInt32),
-                       t.ctx, pointer(rays), pointer(hits), length(rays), reinterpret(Float32, lights), length(lights), shadow_bias, pointer(shadow_rays), 0))
+                       t.ctx, devptr(rays), devptr(hits), length(rays), reinterpret(Float32, lights), length(lights), shadow_bias, devptr(shadow_rays), 0))
 test_shadow_rays!(t::CuTLAS, shadow_rays, visible) =
-    check(t.ctx, ccall((:rc_test_shadow_rays, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, UInt64, Ptr{Cvoid}, UInt32), t.ctx, pointer(shadow_rays), length(shadow_rays), pointer(visible), 0))
+    check(t.ctx, ccall((:rc_test_shadow_rays, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, UInt64, Ptr{Cvoid}, UInt32), t.ctx, devptr(shadow_rays), length(shadow_rays), devptr(visible), 0))
 "stages 3 + 4 in one kernel: no shadow-ray queue"
 shadow_visibility!(t::CuTLAS, rays, hits, lights::Vector{Point3f}, visible; shadow_bias = 0.01f0) =
     check(t.ctx, ccall((:rc_shadow_visibility, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, UInt64, Ptr{Float32}, UInt32, Float32, Ptr{Cvoid}, UInt32),
-                       t.ctx, pointer(rays), pointer(hits), length(rays), reinterpret(Float32, lights), length(lights), shadow_bias, pointer(visible), 0))
+                       t.ctx, devptr(rays), devptr(hits), length(rays), reinterpret(Float32, lights), length(lights), shadow_bias, devptr(visible), 0))
 
 end # module
