@@ -183,7 +183,9 @@ RC_HD void rc_wide_node_test(const rc_f4 &n0, const rc_f4 &n1, const rc_f4 &n2, 
     uint32_t ny = inv.y >= 0.0f ? qloy : qhiy, fy = inv.y >= 0.0f ? qhiy : qloy;
     uint32_t nz = inv.z >= 0.0f ? qloz : qhiz, fz = inv.z >= 0.0f ? qhiz : qloz;
     h.n = 0;
+#ifdef __CUDA_ARCH__
 #pragma unroll
+#endif
     for (int k = 0; k < 4; k++) {
         float tnx = fmaf(rc_q2f(nx, k), ax, bx), tfx = fmaf(rc_q2f(fx, k), ax, bx);
         float tny = fmaf(rc_q2f(ny, k), ay, by), tfy = fmaf(rc_q2f(fy, k), ay, by);
