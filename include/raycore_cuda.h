@@ -124,6 +124,9 @@ int32_t rc_delete(rc_context *ctx, uint32_t handle, int32_t *deleted);
 /* update_transform!/update_transforms! — src/instanced-bvh.jl:755-797 (+ kernels.jl:434-476).
  * m must equal the handle's instance count. */
 int32_t rc_update_transforms(rc_context *ctx, uint32_t handle, const float *transforms, const float *inv_transforms, uint32_t m);
+/* the same with DEVICE-resident transform arrays (the `instance_buffer` use case of src/Raycore.jl:118-130: transforms written by
+ * a caller's kernel); ordered after the work already enqueued on the context stream. */
+int32_t rc_update_transforms_device(rc_context *ctx, uint32_t handle, const float *d_transforms, const float *d_inv_transforms, uint32_t m);
 /* update!(tlas, handle, new_geometry) — src/instanced-bvh.jl:808-857: rebuild the handle's BLAS in place. */
 int32_t rc_update_geometry(rc_context *ctx, uint32_t handle, const float *verts, uint32_t n_faces, const uint32_t *face_meta, uint32_t flags);
 /* sync!(tlas) — src/instanced-bvh.jl:894-921: no-op when clean, refit when only transforms changed,

@@ -279,6 +279,21 @@ int32_t rc_update_transforms(rc_context *ctx, uint32_t handle, const float *tran
     return RC_OK;
 }
 
+// Transforms produced on the device (a simulation kernel's output): staged through the host mirror, which stays the single
+// source of truth for the instance list (refit uploads it, compaction reorders it), so this costs one 48 B/instance read-back.
+int32_t rc_update_transforms_device(rc_context *ctx, uint32_t handle, const float *d_transforms, const float *d_inv_transforms, uint32_t m) {
+    if (!ctx) return RC_ERR_INVALID_ARGUMENT;
+    use_device(ctx);
+    if (!d_transforms) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "rc_update_transforms_device: transforms is NULL");
+    std::vector<float> xf(12 * (size_t)m), inv(d_inv_transforms ? 12 * (size_t)m : 0);
+    if (m) {
+        RC_CUDA(ctx, cudaMemcpyAsync(xf.data(), d_transforms, xf.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        if (d_inv_transforms) RC_CUDA(ctx, cudaMemcpyAsync(inv.data(), d_inv_transforms, inv.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return rc_update_transforms(ctx, handle, xf.data(), d_inv_transforms ? inv.data() : nullptr, m);
+}
+
 int32_t rc_update_geometry(rc_context *ctx, uint32_t handle, const float *verts, uint32_t n_faces, const uint32_t *face_meta, uint32_t flags) {  // :808-857
     if (!ctx) return RC_ERR_INVALID_ARGUMENT;
     use_device(ctx);

@@ -232,6 +232,13 @@ class TLAS:
         xf = np.ascontiguousarray(np.stack([mat4_to_mat3x4(x) for x in transforms]), np.float32)
         self._ck(self._lib.rc_update_transforms(self._ctx, handle.id, xf.ctypes.data, None, len(xf)))
 
+    def update_transforms_device(self, handle: TLASHandle, transforms: "DeviceQueue"):
+        """update_transforms! with the Mat3x4f array resident on the device (float32, 12 per instance), e.g. written by a
+        caller's kernel — the `instance_buffer` use case (src/Raycore.jl:118-130)."""
+        if transforms.dtype != np.float32 or transforms.count % 12:
+            raise ValueError("device transforms must be float32 with 12 values per instance")
+        self._ck(self._lib.rc_update_transforms_device(self._ctx, handle.id, transforms.ptr, None, transforms.count // 12))
+
     def update(self, handle: TLASHandle, mesh, face_meta=None):
         """update!(tlas, handle, new_geometry) — :808-857."""
         v = self._verts(mesh)

@@ -225,3 +225,27 @@ def test_extent_beyond_quantisation_range_is_refused():
     with pytest.raises(rc.RaycoreError):
         tl.sync()
     tl.free()
+
+
+def test_update_transforms_from_device_array():
+    """update_transforms! fed from a device-resident Mat3x4f array (the instance_buffer use case): same refit, same hits as the
+    host-array path; arity errors as in :788."""
+    mesh = W.uv_sphere(16)
+    xf0 = W.random_trs(50, seed=1, extent=10.0)
+    xf1 = W.random_trs(50, seed=2, extent=10.0)
+    a, b = TLAS(), TLAS()
+    ha, hb = a.push(mesh, list(xf0)), b.push(mesh, list(xf0))
+    a.sync(); b.sync()
+    rays = W.box_rays(20000, seed=3, half=12.0)
+    sa = a.static_tlas
+    a.update_transforms(ha, list(xf1))
+    q = b.queue(np.float32, 50 * 12).upload(xf1.reshape(-1))
+    b.update_transforms_device(hb, q)
+    assert b.transforms_dirty
+    a.sync(); b.sync()
+    assert a.static_tlas is sa  # refit keeps the adapted object
+    assert a.trace_closest(rays).tobytes() == b.trace_closest(rays).tobytes()
+    assert np.array_equal(a.get_instances(ha)["inv_transform"], b.get_instances(hb)["inv_transform"])
+    with pytest.raises(RaycoreError):
+        b.update_transforms_device(hb, b.queue(np.float32, 49 * 12))
+    a.free(); b.free()
