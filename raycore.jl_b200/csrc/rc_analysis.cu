@@ -174,13 +174,29 @@ struct RcIoViewFactors {
     unsigned long long *skipped;
     uint32_t *overflow;       // hard errors (no stack could hold the ray)
     uint32_t *retrace_bits;   // one bit per ray: short stack overflowed
-    __device__ __forceinline__ rc_ray load(unsigned long long g) const {
-        const uint32_t pos = (uint32_t)(g / rpt), i = (uint32_t)(g % rpt);
-        const RcTri *tri = flat_tri(flat, n_blas, pos);
+    const uint32_t *row_pos;  // nullable: row -> flat primitive (dense metadata)
+    // work item g -> (source triangle, its row).  With the row map (dense metadata: every row has exactly one triangle) the items are
+    // the rays of the owned rows only; without it every flat primitive is visited and rows outside the block yield a dead ray.
+    __device__ __forceinline__ const RcTri *locate(unsigned long long g, uint32_t &row, uint32_t &i) const {
+        i = (uint32_t)(g % rpt);
+        if (row_pos) {
+            row = row_base + (uint32_t)(g / rpt);
+            const uint32_t pos = __ldg(row_pos + row);
+            return pos == RC_INVALID ? nullptr : flat_tri(flat, n_blas, pos);
+        }
+        const RcTri *tri = flat_tri(flat, n_blas, (uint32_t)(g / rpt));
         const uint32_t meta = tri->metadata;
-        const uint32_t row = meta - 1u;
-        if (meta < 1u || meta > n_cols || row < row_base || row >= row_base + n_rows) {
-            if (i == 0 && skipped && row_base == 0 && (meta < 1u || meta > n_cols)) atomicAdd(skipped, 1ull);  // reference: unchecked index (:85,95-97)
+        row = meta - 1u;
+        if (meta < 1u || meta > n_cols) {
+            if (i == 0 && skipped && row_base == 0) atomicAdd(skipped, 1ull);  // reference: unchecked index (:85,95-97)
+            return nullptr;
+        }
+        return (row < row_base || row >= row_base + n_rows) ? nullptr : tri;
+    }
+    __device__ __forceinline__ rc_ray load(unsigned long long g) const {
+        uint32_t row, i;
+        const RcTri *tri = locate(g, row, i);
+        if (!tri) {
             rc_ray r;  // a ray no box can accept: retires after the TLAS root
             r.origin[0] = r.origin[1] = r.origin[2] = 0.f; r.dir[0] = 1.f; r.dir[1] = r.dir[2] = 0.f; r.tmin = 1.f; r.tmax = -1.f;
             return r;
@@ -196,13 +212,36 @@ struct RcIoViewFactors {
         accumulate(g, h);
     }
     __device__ __forceinline__ void accumulate(unsigned long long g, const rc_hit &h) const {
-        const uint32_t pos = (uint32_t)(g / rpt);
-        const RcTri *tri = flat_tri(flat, n_blas, pos);
-        const uint32_t meta = tri->metadata, row = meta - 1u;
-        if (meta < 1u || meta > n_cols || row < row_base || row >= row_base + n_rows) return;
+        uint32_t row, i;
+        if (row_pos) {
+            row = row_base + (uint32_t)(g / rpt);
+        } else {
+            const RcTri *tri = flat_tri(flat, n_blas, (uint32_t)(g / rpt));
+            const uint32_t meta = tri->metadata;
+            row = meta - 1u;
+            if (meta < 1u || meta > n_cols || row < row_base || row >= row_base + n_rows) return;
+        }
+        (void)i;
+        const uint32_t meta = row + 1u;
         if (h.hit && h.metadata != meta && h.metadata >= 1u && h.metadata <= n_cols) atomicAdd(&out[(size_t)(row - row_base) * n_cols + (h.metadata - 1u)], 1u);
     }
 };
+
+// Row map for view_factors: row_pos[meta-1] = flat position of the triangle carrying that metadata.  info[0] counts duplicates
+// (two triangles with one metadata value: the map cannot be used), info[1] the triangles whose metadata is outside 1..n_cols.
+__global__ void k_vf_row_map(const RcFlatBlas *__restrict__ flat, uint32_t n_blas, uint32_t n_prims, uint32_t n_cols, uint32_t *__restrict__ row_pos,
+                             uint32_t *__restrict__ info) {
+    uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= n_prims) return;
+    const uint32_t meta = flat_tri(flat, n_blas, pos)->metadata;
+    if (meta < 1u || meta > n_cols) { atomicAdd(&info[1], 1u); return; }
+    if (atomicCAS(&row_pos[meta - 1u], RC_INVALID, pos) != RC_INVALID) atomicAdd(&info[0], 1u);
+}
+void rc_launch_vf_row_map(cudaStream_t st, const RcFlatBlas *d_flat, uint32_t n_blas, uint32_t n_prims, uint32_t n_cols, uint32_t *row_pos, uint32_t *info) {
+    cudaMemsetAsync(row_pos, 0xFF, sizeof(uint32_t) * (size_t)n_cols, st);
+    cudaMemsetAsync(info, 0, 2 * sizeof(uint32_t), st);
+    if (n_prims) k_vf_row_map<<<(n_prims + 255) / 256, 256, 0, st>>>(d_flat, n_blas, n_prims, n_cols, row_pos, info);
+}
 
 // Deep-stack pass over the rays the scheduler kernel flagged (one bit per ray); exits at once when none was.
 __global__ void __launch_bounds__(RC_TRACE_THREADS) k_view_factor_fixup(RcIoViewFactors io, unsigned long long total, const uint32_t *__restrict__ flagged) {
@@ -236,8 +275,8 @@ __global__ void k_view_factor_rays(const RcFlatBlas *__restrict__ flat, uint32_t
 
 void rc_launch_view_factors(cudaStream_t st, const RcScene &sc, const RcFlatBlas *d_flat, uint32_t n_blas, uint32_t n_prims, uint32_t rpt, unsigned long long seed,
                             uint32_t row_base, uint32_t n_rows, uint32_t n_cols, uint32_t *out, rc_ray *rays_out, unsigned long long *skipped,
-                            uint32_t *overflow, int max_blocks, unsigned long long *work) {
-    unsigned long long total = (unsigned long long)n_prims * rpt;
+                            uint32_t *overflow, int max_blocks, unsigned long long *work, const uint32_t *row_pos) {
+    unsigned long long total = (unsigned long long)(row_pos && !rays_out ? n_rows : n_prims) * rpt;
     if (total == 0) return;
     unsigned long long want = (total + RC_TRACE_THREADS - 1) / RC_TRACE_THREADS;
     int blocks = (int)(want < (unsigned long long)max_blocks ? want : (unsigned long long)max_blocks);
@@ -250,7 +289,7 @@ void rc_launch_view_factors(cudaStream_t st, const RcScene &sc, const RcFlatBlas
     const size_t bit_bytes = (size_t)((total + 31) / 32) * sizeof(uint32_t);
     cudaMallocAsync(&bits, bit_bytes, st);
     cudaMemsetAsync(bits, 0, bit_bytes, st);
-    RcIoViewFactors io{sc, d_flat, n_blas, rpt, row_base, n_rows, n_cols, seed, out, skipped, overflow, bits};
+    RcIoViewFactors io{sc, d_flat, n_blas, rpt, row_base, n_rows, n_cols, seed, out, skipped, overflow, bits, row_pos};
     cudaMemsetAsync(work, 0, sizeof(unsigned long long), st);
     cudaMemsetAsync(overflow + 1, 0, sizeof(uint32_t), st);  // overflow = &d_overflow[1]; [2] counts the rays flagged for the fix-up pass
     k_trace_wide<false, false, RcIoViewFactors><<<blocks, RC_TRACE_THREADS, 0, st>>>(sc, io, total, work, nullptr, overflow + 1);

@@ -56,6 +56,10 @@ struct rc_context {
     // wavefront stages: device table of per-BLAS normal arrays, re-uploaded when normals_version moves
     const float **d_normal_ptrs = nullptr;
     std::vector<const float *> normal_ptrs;  // what d_normal_ptrs currently holds
+    // view_factors: row -> flat primitive map of the synced scene (usable when every metadata value occurs at most once)
+    uint32_t *d_vf_row_pos = nullptr;
+    bool vf_map_built = false, vf_map_usable = false;
+    uint32_t vf_out_of_range = 0;
 };
 
 #define RC_FAIL(ctx, code, msg)        \
@@ -159,6 +163,7 @@ int32_t rc_destroy(rc_context *ctx) {
     if (ctx->d_rays) cudaFree(ctx->d_rays);
     if (ctx->d_hits) cudaFree(ctx->d_hits);
     if (ctx->d_normal_ptrs) cudaFree(ctx->d_normal_ptrs);
+    if (ctx->d_vf_row_pos) cudaFree(ctx->d_vf_row_pos);
     for (int i = 0; i < rc_context::NEV; i++) { cudaEventDestroy(ctx->ev_h2d[i]); cudaEventDestroy(ctx->ev_k[i]); }
     cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1);
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
@@ -376,6 +381,7 @@ static int32_t rebuild(rc_context *ctx) {  // rebuild_bvh! :962-993 + build_flat
     ctx->dirty = false;
     ctx->transforms_dirty = false;
     ctx->built = true;
+    ctx->vf_map_built = false;
     return RC_OK;
 }
 
@@ -702,16 +708,29 @@ int32_t rc_view_factors(rc_context *ctx, uint32_t rays_per_triangle, uint64_t se
     uint32_t n_cols = ctx->n_flat_prims;
     if (skipped) *skipped = 0;
     if (n_cols == 0 || n_rows == 0) return RC_OK;
+    if (row_base > n_cols || n_rows > n_cols - row_base) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "view_factors: row block exceeds the matrix");
     size_t bytes = (size_t)n_rows * n_cols * sizeof(uint32_t);
     uint32_t *d_out = out;
     if (!(flags & RC_HITS_ON_DEVICE)) RC_CUDA(ctx, cudaMallocAsync(&d_out, bytes, ctx->stream));
     RC_CUDA(ctx, cudaMemsetAsync(d_out, 0, bytes, ctx->stream));
+    if (!ctx->vf_map_built) {  // once per synced scene: which flat primitive carries row r's metadata
+        if (ctx->d_vf_row_pos) { cudaFree(ctx->d_vf_row_pos); ctx->d_vf_row_pos = nullptr; }
+        RC_CUDA(ctx, cudaMalloc(&ctx->d_vf_row_pos, sizeof(uint32_t) * ((size_t)n_cols + 2)));
+        uint32_t *info = ctx->d_vf_row_pos + n_cols, h_info[2] = {0, 0};
+        rc_launch_vf_row_map(ctx->stream, ctx->d_flat, ctx->n_flat_blas, ctx->n_flat_prims, n_cols, ctx->d_vf_row_pos, info);
+        RC_CUDA(ctx, cudaMemcpyAsync(h_info, info, sizeof(h_info), cudaMemcpyDeviceToHost, ctx->stream));
+        RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->vf_map_built = true;
+        ctx->vf_map_usable = h_info[0] == 0;  // duplicated metadata values: several triangles feed one row, fall back to the scan
+        ctx->vf_out_of_range = h_info[1];
+    }
+    const uint32_t *row_pos = ctx->vf_map_usable ? ctx->d_vf_row_pos : nullptr;
     unsigned long long *d_skipped = nullptr;
     RC_CUDA(ctx, cudaMallocAsync(&d_skipped, 8, ctx->stream));
     RC_CUDA(ctx, cudaMemsetAsync(d_skipped, 0, 8, ctx->stream));
     cudaEventRecord(ctx->ev_t0, ctx->stream);
     rc_launch_view_factors(ctx->stream, make_scene(ctx), ctx->d_flat, ctx->n_flat_blas, ctx->n_flat_prims, rays_per_triangle, seed, row_base, n_rows, n_cols, d_out,
-                           nullptr, d_skipped, ctx->d_overflow + 1, ctx->max_blocks, ctx->d_work);
+                           nullptr, d_skipped, ctx->d_overflow + 1, ctx->max_blocks, ctx->d_work, row_pos);
     cudaEventRecord(ctx->ev_t1, ctx->stream);
     ctx->last_launches = 2;
     unsigned long long sk = 0;
@@ -724,6 +743,7 @@ int32_t rc_view_factors(rc_context *ctx, uint32_t rays_per_triangle, uint64_t se
     if (flags & RC_NO_SYNC) return RC_OK;
     RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaEventElapsedTime(&ctx->last_ms, ctx->ev_t0, ctx->ev_t1);
+    if (row_pos && row_base == 0) sk = ctx->vf_out_of_range;  // the map never visits them; the scan counts them itself
     if (skipped) *skipped = sk;
     return check_overflow(ctx);
 }
@@ -739,7 +759,7 @@ int32_t rc_view_factor_rays(rc_context *ctx, uint32_t rays_per_triangle, uint64_
     RC_CUDA(ctx, cudaMallocAsync(&d_rays, n * sizeof(rc_ray), ctx->stream));
     RC_CUDA(ctx, cudaMemsetAsync(d_rays, 0, n * sizeof(rc_ray), ctx->stream));
     rc_launch_view_factors(ctx->stream, make_scene(ctx), ctx->d_flat, ctx->n_flat_blas, ctx->n_flat_prims, rays_per_triangle, seed, row_base, n_rows, ctx->n_flat_prims,
-                           nullptr, d_rays, nullptr, ctx->d_overflow + 1, ctx->max_blocks, ctx->d_work);
+                           nullptr, d_rays, nullptr, ctx->d_overflow + 1, ctx->max_blocks, ctx->d_work, nullptr);
     RC_CUDA(ctx, cudaMemcpyAsync(out, d_rays, n * sizeof(rc_ray), cudaMemcpyDeviceToHost, ctx->stream));
     cudaFreeAsync(d_rays, ctx->stream);
     RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

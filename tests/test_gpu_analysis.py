@@ -98,3 +98,34 @@ def test_view_factors_deep_trees_fixup():
     b = o.trace(rays)
     cls = parity.classify(hits, b, parity.make_graze_verifier(orc, rays, hits, o.instances, o.tris))
     parity.assert_parity(cls, len(rays), max_tie_frac=0.05, label="deep view-factor rays")
+
+
+def test_view_factors_metadata_not_a_permutation():
+    """Duplicated and out-of-range metadata (the reference indexes result[src_meta, hit_meta] unchecked, src/kernels.jl:85,95-97):
+    rows fed by two triangles fall back to the scan over all primitives (no row map), out-of-range sources are skipped and
+    counted, row blocks still tile the full matrix."""
+    near = W.quad_mesh(z=0.0, half=1.0)  # normal +z
+    far = W.quad_mesh(z=1.0, half=1.0)[:, [6, 7, 8, 3, 4, 5, 0, 1, 2]]  # flipped: normal -z, faces the first quad
+    verts = np.concatenate([near, far])
+    meta = np.array([1, 1, 2, 9], np.uint32)
+    tl = rc.TLAS()
+    tl.push(verts, None, face_meta=meta)
+    tl.sync()
+    rpt = 200
+    vf = tl.view_factors(rpt, seed=1)
+    assert vf.shape == (4, 4) and tl.last_vf_skipped == 1
+    assert vf[2:].sum() == 0 and vf[:, 2:].sum() == 0 and vf[0, 0] == 0 and vf[1, 1] == 0
+    assert 0 < vf[0, 1] <= 2 * rpt and 0 < vf[1, 0] <= rpt  # row 0 is fed by two triangles
+    blocks = np.vstack([tl.view_factors(rpt, seed=1, row_base=0, n_rows=1), tl.view_factors(rpt, seed=1, row_base=1, n_rows=3)])
+    assert np.array_equal(blocks, vf)
+    with pytest.raises(rc.RaycoreError):
+        tl.view_factors(rpt, row_base=3, n_rows=2)
+    # the same geometry with permutation metadata takes the row-map path; out-of-range only
+    tl2 = rc.TLAS()
+    tl2.push(verts, None, face_meta=np.array([2, 1, 3, 9], np.uint32))
+    tl2.sync()
+    vf2 = tl2.view_factors(rpt, seed=1)
+    assert tl2.last_vf_skipped == 1 and vf2[3].sum() == 0 and vf2[:, 3].sum() == 0
+    assert vf2[:2, 2].sum() > 0 and vf2[2, :2].sum() > 0 and vf2[:2, :2].sum() == 0
+    assert np.array_equal(np.vstack([tl2.view_factors(rpt, seed=1, row_base=0, n_rows=2), tl2.view_factors(rpt, seed=1, row_base=2, n_rows=2)]), vf2)
+    tl.free(); tl2.free()
