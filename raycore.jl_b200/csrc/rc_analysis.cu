@@ -279,7 +279,8 @@ void rc_launch_view_factors(cudaStream_t st, const RcScene &sc, const RcFlatBlas
     unsigned long long total = (unsigned long long)(row_pos && !rays_out ? n_rows : n_prims) * rpt;
     if (total == 0) return;
     unsigned long long want = (total + RC_TRACE_THREADS - 1) / RC_TRACE_THREADS;
-    int blocks = (int)(want < (unsigned long long)max_blocks ? want : (unsigned long long)max_blocks);
+    const unsigned long long cap = (sc.n_instances == 1u && !rays_out) ? (unsigned long long)max_blocks * RC_MIN_BLOCKS_SINGLE / RC_MIN_BLOCKS : (unsigned long long)max_blocks;
+    int blocks = (int)(want < cap ? want : cap);
     if (rays_out) {
         k_view_factor_rays<<<blocks, RC_TRACE_THREADS, 0, st>>>(d_flat, n_blas, n_prims, rpt, seed, row_base, n_rows, n_cols, rays_out);
         return;
@@ -292,7 +293,8 @@ void rc_launch_view_factors(cudaStream_t st, const RcScene &sc, const RcFlatBlas
     RcIoViewFactors io{sc, d_flat, n_blas, rpt, row_base, n_rows, n_cols, seed, out, skipped, overflow, bits, row_pos};
     cudaMemsetAsync(work, 0, sizeof(unsigned long long), st);
     cudaMemsetAsync(overflow + 1, 0, sizeof(uint32_t), st);  // overflow = &d_overflow[1]; [2] counts the rays flagged for the fix-up pass
-    k_trace_wide<false, false, RcIoViewFactors><<<blocks, RC_TRACE_THREADS, 0, st>>>(sc, io, total, work, nullptr, overflow + 1);
+    if (sc.n_instances == 1u) k_trace_wide<false, false, RcIoViewFactors, true><<<blocks, RC_TRACE_THREADS, 0, st>>>(sc, io, total, work, nullptr, overflow + 1);
+    else k_trace_wide<false, false, RcIoViewFactors, false><<<blocks, RC_TRACE_THREADS, 0, st>>>(sc, io, total, work, nullptr, overflow + 1);
     k_view_factor_fixup<<<blocks, RC_TRACE_THREADS, 0, st>>>(io, total, overflow + 1);
     cudaFreeAsync(bits, st);
 }

@@ -68,13 +68,21 @@ bool rc_launch_trace(cudaStream_t st, const RcTraceLaunch &L, std::string &err) 
         cudaMemsetAsync(L.work, 0, sizeof(unsigned long long), st);
         cudaMemsetAsync(L.overflow, 0, sizeof(uint32_t), st);
         unsigned long long want = (L.n + RC_TRACE_THREADS - 1) / RC_TRACE_THREADS;
-        int blocks = (int)(want < (unsigned long long)L.max_blocks ? want : (unsigned long long)L.max_blocks);
+        // the single-instance variant is compiled for RC_MIN_BLOCKS_SINGLE resident CTAs per SM (fewer registers: no world-ray copy)
+        const unsigned long long cap = (L.wide && L.scene.n_instances == 1u) ? (unsigned long long)L.max_blocks * RC_MIN_BLOCKS_SINGLE / RC_MIN_BLOCKS : (unsigned long long)L.max_blocks;
+        int blocks = (int)(want < cap ? want : cap);
         if (blocks < 1) blocks = 1;
 #define RC_ARGS L.scene, L.rays, L.hits, L.n, L.work, L.counters, L.overflow
 #define RC_WARGS L.scene, RcIoArrays{L.rays, L.hits}, L.n, L.work, L.counters, L.overflow
         if (L.wide) {
-            if (L.any) { if (L.count) k_trace_wide<true, true, RcIoArrays><<<blocks, RC_TRACE_THREADS, 0, st>>>(RC_WARGS); else k_trace_wide<true, false, RcIoArrays><<<blocks, RC_TRACE_THREADS, 0, st>>>(RC_WARGS); }
-            else { if (L.count) k_trace_wide<false, true, RcIoArrays><<<blocks, RC_TRACE_THREADS, 0, st>>>(RC_WARGS); else k_trace_wide<false, false, RcIoArrays><<<blocks, RC_TRACE_THREADS, 0, st>>>(RC_WARGS); }
+#define RC_LAUNCH_WIDE(A, C)                                                                                                  \
+    {                                                                                                                         \
+        if (L.scene.n_instances == 1u) k_trace_wide<A, C, RcIoArrays, true><<<blocks, RC_TRACE_THREADS, 0, st>>>(RC_WARGS);   \
+        else k_trace_wide<A, C, RcIoArrays, false><<<blocks, RC_TRACE_THREADS, 0, st>>>(RC_WARGS);                            \
+    }
+            if (L.any) { if (L.count) RC_LAUNCH_WIDE(true, true) else RC_LAUNCH_WIDE(true, false) }
+            else { if (L.count) RC_LAUNCH_WIDE(false, true) else RC_LAUNCH_WIDE(false, false) }
+#undef RC_LAUNCH_WIDE
         } else {
             if (L.any) { if (L.count) k_trace<true, true><<<blocks, RC_TRACE_THREADS, 0, st>>>(RC_ARGS); else k_trace<true, false><<<blocks, RC_TRACE_THREADS, 0, st>>>(RC_ARGS); }
             else { if (L.count) k_trace<false, true><<<blocks, RC_TRACE_THREADS, 0, st>>>(RC_ARGS); else k_trace<false, false><<<blocks, RC_TRACE_THREADS, 0, st>>>(RC_ARGS); }

@@ -53,6 +53,9 @@ __device__ __forceinline__ void rc_store_hit(rc_hit *hits, unsigned long long i,
 #define RC_MIN_BLOCKS 8     // 64 registers -> 32 resident warps per SM (swept 6..10 in r1: 8 is best, 9+ spills)
 #endif
 #ifndef RC_SSTACK
+#ifndef RC_MIN_BLOCKS_SINGLE
+#define RC_MIN_BLOCKS_SINGLE 9
+#endif
 #define RC_SSTACK 32       // stack entries per lane (shared memory, [depth][thread]); row RC_SSTACK is the dummy row
 #endif
 #define RC_OVERFLOW_MARK 0xFFFFFFFFu  // rc_hit.hit of a ray whose short stack overflowed (re-traced by k_trace_fixup)
@@ -100,8 +103,8 @@ struct RcIoArrays {
 
 // IO: where ray i comes from and where its result goes (RcIoArrays for rc_trace_*; rc_analysis.cu plugs in an on-the-fly
 // view-factor ray generator + matrix accumulator, so the analysis kernels run on the same scheduler).
-template <bool ANY, bool COUNT, class IO>
-__global__ void __launch_bounds__(RC_TRACE_THREADS, RC_MIN_BLOCKS) k_trace_wide(RcScene sc, IO io, unsigned long long n,
+template <bool ANY, bool COUNT, class IO, bool SINGLE = false>
+__global__ void __launch_bounds__(RC_TRACE_THREADS, SINGLE ? RC_MIN_BLOCKS_SINGLE : RC_MIN_BLOCKS) k_trace_wide(RcScene sc, IO io, unsigned long long n,
                                                                  unsigned long long *__restrict__ work, RcCounters *__restrict__ counters,
                                                                  uint32_t *__restrict__ overflow) {
     // rows: 0 guard (always RC_INVALID), 1..RC_SSTACK live entries, +4 scratch (<= 3 pushes past the limit before the overflow check, + 1 rejected store)
@@ -122,7 +125,9 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, RC_MIN_BLOCKS) k_trace_wide(
     bool have = false, ovf = false;
     // A TLAS with a single instance needs no top-level traversal: the refill step enters that instance directly and, with no
     // sentinel under the BLAS entries, the ray finishes when the stack bottom is popped (saves a node step and two level changes).
-    const bool single = sc.n_instances == 1u;
+    // SINGLE is a compile-time variant (chosen by the launcher when n_instances == 1): the world-space ray copy, the sentinel and the
+    // whole level-change step drop out of the kernel.
+    constexpr bool single = SINGLE;
 
     // Branch-free conditional push: the value is always stored one row above the top and the top pointer only advances when the
     // push is accepted, so a rejected value is simply overwritten by the next push (rows above the top are don't-care).  Row 0 is
@@ -149,7 +154,7 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, RC_MIN_BLOCKS) k_trace_wide(
         vote = ((int)cur >= 0) ? RC_VOTE_N : 0u;                                                                   \
         vote |= leaf ? RC_VOTE_T : ((cur == RC_INVALID) ? RC_VOTE_F : 0u);                                         \
         /* level change: instance leaf or sentinel = [0xC0000000, 0xF0000000); the sentinel waits for the parked leaf */ \
-        vote |= (((cur + 0x40000000u) < 0x30000000u) && !(cur == RC_SENTINEL && leaf != 0)) ? RC_VOTE_X : 0u;      \
+        if (!SINGLE) vote |= (((cur + 0x40000000u) < 0x30000000u) && !(cur == RC_SENTINEL && leaf != 0)) ? RC_VOTE_X : 0u; \
     }
 
     // enter instance `index`: its world->local transform applied with the reference's exact arithmetic (:1961-1977)
@@ -245,7 +250,7 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, RC_MIN_BLOCKS) k_trace_wide(
                     RC_SETTLE()  // the vote can only change when the parked leaf is exhausted
                 }
             }
-        } else if (nX > nN) {
+        } else if (!SINGLE && nX > nN) {
             // ---- X: enter an instance (TLAS leaf) or return to the TLAS (sentinel) -------------------------------------------
             if (vote & RC_VOTE_X) {
                 if (cur == RC_SENTINEL) {

@@ -142,11 +142,13 @@ template <class SRC>
 static void launch_shadow(cudaStream_t st, const RcScene &sc, const SRC &source, unsigned long long total, uint8_t *d_visible, uint32_t *overflow, int max_blocks,
                           unsigned long long *work) {
     unsigned long long want = (total + RC_TRACE_THREADS - 1) / RC_TRACE_THREADS;
-    int blocks = (int)(want < (unsigned long long)max_blocks ? want : (unsigned long long)max_blocks);
+    const unsigned long long cap = sc.n_instances == 1u ? (unsigned long long)max_blocks * RC_MIN_BLOCKS_SINGLE / RC_MIN_BLOCKS : (unsigned long long)max_blocks;
+    int blocks = (int)(want < cap ? want : cap);
     cudaMemsetAsync(work, 0, sizeof(unsigned long long), st);
     cudaMemsetAsync(overflow + 2, 0, sizeof(uint32_t), st);
     RcIoShadow<SRC> io{source, d_visible};
-    k_trace_wide<true, false, RcIoShadow<SRC>><<<blocks, RC_TRACE_THREADS, 0, st>>>(sc, io, total, work, nullptr, overflow + 2);
+    if (sc.n_instances == 1u) k_trace_wide<true, false, RcIoShadow<SRC>, true><<<blocks, RC_TRACE_THREADS, 0, st>>>(sc, io, total, work, nullptr, overflow + 2);
+    else k_trace_wide<true, false, RcIoShadow<SRC>, false><<<blocks, RC_TRACE_THREADS, 0, st>>>(sc, io, total, work, nullptr, overflow + 2);
     k_shadow_fixup<SRC><<<blocks, RC_TRACE_THREADS, 0, st>>>(sc, source, total, d_visible, overflow);
 }
 
