@@ -52,11 +52,11 @@ __device__ __forceinline__ void rc_store_hit(rc_hit *hits, unsigned long long i,
 #ifndef RC_MIN_BLOCKS
 #define RC_MIN_BLOCKS 8     // 64 registers -> 32 resident warps per SM (swept 6..10 in r1: 8 is best, 9+ spills)
 #endif
-#ifndef RC_SSTACK
 #ifndef RC_MIN_BLOCKS_SINGLE
-#define RC_MIN_BLOCKS_SINGLE 9
+#define RC_MIN_BLOCKS_SINGLE 9  // the single-instance variant needs 56 registers (no world-ray copy): 36 resident warps (10 spills, -5 %)
 #endif
-#define RC_SSTACK 32       // stack entries per lane (shared memory, [depth][thread]); row RC_SSTACK is the dummy row
+#ifndef RC_SSTACK
+#define RC_SSTACK 32       // stack entries per lane (shared memory, [depth][thread]); deeper rays go through the fix-up pass
 #endif
 #define RC_OVERFLOW_MARK 0xFFFFFFFFu  // rc_hit.hit of a ray whose short stack overflowed (re-traced by k_trace_fixup)
 #define RC_DEADLANE 0xFFFFFFFEu
