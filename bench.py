@@ -59,10 +59,8 @@ def measure_l2_gbs(torch, dev):
 
 def measure_view_factors(rc, W, L, torch, dev, local, world, rank, dist):
     """C4: view_factors of 5 bumpy spheres (49,704 triangles) x 1000 rays per triangle into a UInt32 matrix resident in HBM.
-    N > 1: every rank holds the (replicated) scene and computes its own block of source rows, no exchange (SURVEY 8e);
+    N > 1: every rank holds the (replicated) scene and computes its own interleaved share of the source rows, no exchange (SURVEY 8e);
     the time is the max over ranks of the library's CUDA-event kernel time."""
-    from raycore_b200.sharding import shard_range
-
     vt = rc.TLAS(local)
     base = 0
     for msh in W.viewfactor_scene(72):
@@ -73,14 +71,14 @@ def measure_view_factors(rc, W, L, torch, dev, local, world, rank, dist):
         vt.push(msh, None, face_meta=meta)
     vt.sync()
     npr = vt.sizes()["blas_prims"]
-    row0, row1 = shard_range(npr, rank, world)
-    d_vf = torch.empty((row1 - row0) * npr, dtype=torch.int32, device=dev)
+    n_mine = len(range(rank, npr, world))  # interleaved share: rows rank, rank + world, ... (equally expensive shares)
+    d_vf = torch.empty(n_mine * npr, dtype=torch.int32, device=dev)
     sk = C.c_uint64()
     vms = []
     for _ in range(3):
         if dist is not None:
             dist.barrier()
-        assert vt._lib.rc_view_factors(vt._ctx, 1000, 11, d_vf.data_ptr(), row0, row1 - row0, L.RC_HITS_ON_DEVICE, C.byref(sk)) == 0
+        assert vt._lib.rc_view_factors_strided(vt._ctx, 1000, 11, d_vf.data_ptr(), rank, world, n_mine, L.RC_HITS_ON_DEVICE, C.byref(sk)) == 0
         vms.append(float(vt._lib.rc_last_kernel_ms(vt._ctx)))
     ms, hits = min(vms), int(d_vf.sum().item())
     if dist is not None:
@@ -93,7 +91,7 @@ def measure_view_factors(rc, W, L, torch, dev, local, world, rank, dist):
     vt.free()
     return {"view_factors_s": ms * 1e-3,
             "view_factors_config": f"C4: 5 x bumpy_sphere(72) = {npr} triangles, rays_per_triangle=1000 ({npr * 1000} rays), UInt32 {npr}x{npr} matrix resident in HBM, "
-                                   f"{world} GPU(s): source rows sharded, no exchange",
+                                   f"{world} GPU(s): source rows interleaved over the ranks, no exchange",
             "view_factors_total_hits": hits}
 
 

@@ -200,6 +200,10 @@ int32_t rc_get_centroid(rc_context *ctx, const float viewdir[3], uint32_t grid, 
  * out is zeroed first.  RC_HITS_ON_DEVICE => out is a device pointer. */
 int32_t rc_view_factors(rc_context *ctx, uint32_t rays_per_triangle, uint64_t seed, uint32_t *out, uint32_t row_base, uint32_t n_rows,
                         uint32_t flags, uint64_t *skipped);
+/* the same for the interleaved row set {row_first + k * row_stride, k < n_rows} (out row k): with row_first = rank and
+ * row_stride = world size every GPU gets an equally expensive share of the rows. */
+int32_t rc_view_factors_strided(rc_context *ctx, uint32_t rays_per_triangle, uint64_t seed, uint32_t *out, uint32_t row_first, uint32_t row_stride, uint32_t n_rows,
+                                uint32_t flags, uint64_t *skipped);
 /* the rays rc_view_factors generates for that row block: host buffer of n_rows*rays_per_triangle records,
  * ray (meta_src-1-row_base)*rays_per_triangle + i (rows without a source stay zero) */
 int32_t rc_view_factor_rays(rc_context *ctx, uint32_t rays_per_triangle, uint64_t seed, uint32_t row_base, uint32_t n_rows, rc_ray *out);

@@ -71,7 +71,7 @@ EXPORTS = [
     "rc_get_instances", "rc_world_bound", "rc_wait", "rc_sizes", "rc_read_tlas_nodes", "rc_read_blas_nodes",
     "rc_read_blas_order", "rc_blas_n_prims", "rc_read_blas_faces", "rc_get_instance_handles",
     "rc_trace_closest", "rc_trace_any", "rc_get_counters", "rc_last_kernel_ms", "rc_last_kernel_launches", "rc_last_build_ms",
-    "rc_hits_from_grid", "rc_get_illumination", "rc_get_centroid", "rc_view_factors", "rc_view_factor_rays", "rc_read_flat_metadata",
+    "rc_hits_from_grid", "rc_get_illumination", "rc_get_centroid", "rc_view_factors", "rc_view_factors_strided", "rc_view_factor_rays", "rc_read_flat_metadata",
     "rc_collide_instances", "rc_collide_instances_any",
     "rc_set_normals", "rc_generate_primary_rays", "rc_generate_primary_rays_lookat", "rc_generate_shadow_rays", "rc_test_shadow_rays",
     "rc_shadow_visibility",
@@ -143,6 +143,7 @@ def load():
         "rc_get_illumination": (i32, [vp, vp, u32, vp, u32]),
         "rc_get_centroid": (i32, [vp, vp, u32, vp, pu32, vp]),
         "rc_view_factors": (i32, [vp, u32, u64, vp, u32, u32, u32, C.POINTER(u64)]),
+        "rc_view_factors_strided": (i32, [vp, u32, u64, vp, u32, u32, u32, u32, C.POINTER(u64)]),
         "rc_view_factor_rays": (i32, [vp, u32, u64, u32, u32, vp]),
         "rc_read_flat_metadata": (i32, [vp, vp, u32]),
         "rc_collide_instances": (i32, [vp, vp, u64, C.POINTER(u64)]),

@@ -168,19 +168,25 @@ __device__ __forceinline__ const RcTri *flat_tri(const RcFlatBlas *flat, uint32_
 struct RcIoViewFactors {
     RcScene sc;
     const RcFlatBlas *flat;
-    uint32_t n_blas, rpt, row_base, n_rows, n_cols;
+    uint32_t n_blas, rpt, row_base, n_rows, n_cols;  // owned rows: row_base + k * row_stride, k < n_rows (output row k)
     unsigned long long seed;
     uint32_t *out;
     unsigned long long *skipped;
     uint32_t *overflow;       // hard errors (no stack could hold the ray)
     uint32_t *retrace_bits;   // one bit per ray: short stack overflowed
     const uint32_t *row_pos;  // nullable: row -> flat primitive (dense metadata)
+    uint32_t row_stride;
+    __device__ __forceinline__ bool owned(uint32_t row, uint32_t &local) const {
+        const uint32_t d = row - row_base;
+        local = d / row_stride;
+        return row >= row_base && d % row_stride == 0u && local < n_rows;
+    }
     // work item g -> (source triangle, its row).  With the row map (dense metadata: every row has exactly one triangle) the items are
     // the rays of the owned rows only; without it every flat primitive is visited and rows outside the block yield a dead ray.
     __device__ __forceinline__ const RcTri *locate(unsigned long long g, uint32_t &row, uint32_t &i) const {
         i = (uint32_t)(g % rpt);
         if (row_pos) {
-            row = row_base + (uint32_t)(g / rpt);
+            row = row_base + (uint32_t)(g / rpt) * row_stride;
             const uint32_t pos = __ldg(row_pos + row);
             return pos == RC_INVALID ? nullptr : flat_tri(flat, n_blas, pos);
         }
@@ -191,7 +197,8 @@ struct RcIoViewFactors {
             if (i == 0 && skipped && row_base == 0) atomicAdd(skipped, 1ull);  // reference: unchecked index (:85,95-97)
             return nullptr;
         }
-        return (row < row_base || row >= row_base + n_rows) ? nullptr : tri;
+        uint32_t local;
+        return owned(row, local) ? tri : nullptr;
     }
     __device__ __forceinline__ rc_ray load(unsigned long long g) const {
         uint32_t row, i;
@@ -212,18 +219,18 @@ struct RcIoViewFactors {
         accumulate(g, h);
     }
     __device__ __forceinline__ void accumulate(unsigned long long g, const rc_hit &h) const {
-        uint32_t row, i;
+        uint32_t row, local;
         if (row_pos) {
-            row = row_base + (uint32_t)(g / rpt);
+            local = (uint32_t)(g / rpt);
+            row = row_base + local * row_stride;
         } else {
             const RcTri *tri = flat_tri(flat, n_blas, (uint32_t)(g / rpt));
             const uint32_t meta = tri->metadata;
             row = meta - 1u;
-            if (meta < 1u || meta > n_cols || row < row_base || row >= row_base + n_rows) return;
+            if (meta < 1u || meta > n_cols || !owned(row, local)) return;
         }
-        (void)i;
         const uint32_t meta = row + 1u;
-        if (h.hit && h.metadata != meta && h.metadata >= 1u && h.metadata <= n_cols) atomicAdd(&out[(size_t)(row - row_base) * n_cols + (h.metadata - 1u)], 1u);
+        if (h.hit && h.metadata != meta && h.metadata >= 1u && h.metadata <= n_cols) atomicAdd(&out[(size_t)local * n_cols + (h.metadata - 1u)], 1u);
     }
 };
 
@@ -275,7 +282,7 @@ __global__ void k_view_factor_rays(const RcFlatBlas *__restrict__ flat, uint32_t
 
 void rc_launch_view_factors(cudaStream_t st, const RcScene &sc, const RcFlatBlas *d_flat, uint32_t n_blas, uint32_t n_prims, uint32_t rpt, unsigned long long seed,
                             uint32_t row_base, uint32_t n_rows, uint32_t n_cols, uint32_t *out, rc_ray *rays_out, unsigned long long *skipped,
-                            uint32_t *overflow, int max_blocks, unsigned long long *work, const uint32_t *row_pos) {
+                            uint32_t *overflow, int max_blocks, unsigned long long *work, const uint32_t *row_pos, uint32_t row_stride) {
     unsigned long long total = (unsigned long long)(row_pos && !rays_out ? n_rows : n_prims) * rpt;
     if (total == 0) return;
     unsigned long long want = (total + RC_TRACE_THREADS - 1) / RC_TRACE_THREADS;
@@ -290,7 +297,7 @@ void rc_launch_view_factors(cudaStream_t st, const RcScene &sc, const RcFlatBlas
     const size_t bit_bytes = (size_t)((total + 31) / 32) * sizeof(uint32_t);
     cudaMallocAsync(&bits, bit_bytes, st);
     cudaMemsetAsync(bits, 0, bit_bytes, st);
-    RcIoViewFactors io{sc, d_flat, n_blas, rpt, row_base, n_rows, n_cols, seed, out, skipped, overflow, bits, row_pos};
+    RcIoViewFactors io{sc, d_flat, n_blas, rpt, row_base, n_rows, n_cols, seed, out, skipped, overflow, bits, row_pos, row_stride ? row_stride : 1u};
     cudaMemsetAsync(work, 0, sizeof(unsigned long long), st);
     cudaMemsetAsync(overflow + 1, 0, sizeof(uint32_t), st);  // overflow = &d_overflow[1]; [2] counts the rays flagged for the fix-up pass
     if (sc.n_instances == 1u) k_trace_wide<false, false, RcIoViewFactors, true><<<blocks, RC_TRACE_THREADS, 0, st>>>(sc, io, total, work, nullptr, overflow + 1);

@@ -701,6 +701,11 @@ int32_t rc_get_centroid(rc_context *ctx, const float viewdir[3], uint32_t grid, 
 
 int32_t rc_view_factors(rc_context *ctx, uint32_t rays_per_triangle, uint64_t seed, uint32_t *out, uint32_t row_base, uint32_t n_rows, uint32_t flags,
                         uint64_t *skipped) {
+    return rc_view_factors_strided(ctx, rays_per_triangle, seed, out, row_base, 1, n_rows, flags, skipped);
+}
+
+int32_t rc_view_factors_strided(rc_context *ctx, uint32_t rays_per_triangle, uint64_t seed, uint32_t *out, uint32_t row_base, uint32_t row_stride, uint32_t n_rows,
+                                uint32_t flags, uint64_t *skipped) {
     if (!ctx || !out) return RC_ERR_INVALID_ARGUMENT;
     use_device(ctx);
     int32_t rc = require_synced(ctx);
@@ -708,7 +713,8 @@ int32_t rc_view_factors(rc_context *ctx, uint32_t rays_per_triangle, uint64_t se
     uint32_t n_cols = ctx->n_flat_prims;
     if (skipped) *skipped = 0;
     if (n_cols == 0 || n_rows == 0) return RC_OK;
-    if (row_base > n_cols || n_rows > n_cols - row_base) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "view_factors: row block exceeds the matrix");
+    if (row_stride == 0 || row_base >= n_cols || (uint64_t)row_base + (uint64_t)(n_rows - 1) * row_stride >= n_cols)
+        RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "view_factors: row block exceeds the matrix");
     size_t bytes = (size_t)n_rows * n_cols * sizeof(uint32_t);
     uint32_t *d_out = out;
     if (!(flags & RC_HITS_ON_DEVICE)) RC_CUDA(ctx, cudaMallocAsync(&d_out, bytes, ctx->stream));
@@ -730,7 +736,7 @@ int32_t rc_view_factors(rc_context *ctx, uint32_t rays_per_triangle, uint64_t se
     RC_CUDA(ctx, cudaMemsetAsync(d_skipped, 0, 8, ctx->stream));
     cudaEventRecord(ctx->ev_t0, ctx->stream);
     rc_launch_view_factors(ctx->stream, make_scene(ctx), ctx->d_flat, ctx->n_flat_blas, ctx->n_flat_prims, rays_per_triangle, seed, row_base, n_rows, n_cols, d_out,
-                           nullptr, d_skipped, ctx->d_overflow + 1, ctx->max_blocks, ctx->d_work, row_pos);
+                           nullptr, d_skipped, ctx->d_overflow + 1, ctx->max_blocks, ctx->d_work, row_pos, row_stride);
     cudaEventRecord(ctx->ev_t1, ctx->stream);
     ctx->last_launches = 2;
     unsigned long long sk = 0;
@@ -759,7 +765,7 @@ int32_t rc_view_factor_rays(rc_context *ctx, uint32_t rays_per_triangle, uint64_
     RC_CUDA(ctx, cudaMallocAsync(&d_rays, n * sizeof(rc_ray), ctx->stream));
     RC_CUDA(ctx, cudaMemsetAsync(d_rays, 0, n * sizeof(rc_ray), ctx->stream));
     rc_launch_view_factors(ctx->stream, make_scene(ctx), ctx->d_flat, ctx->n_flat_blas, ctx->n_flat_prims, rays_per_triangle, seed, row_base, n_rows, ctx->n_flat_prims,
-                           nullptr, d_rays, nullptr, ctx->d_overflow + 1, ctx->max_blocks, ctx->d_work, nullptr);
+                           nullptr, d_rays, nullptr, ctx->d_overflow + 1, ctx->max_blocks, ctx->d_work, nullptr, 1);
     RC_CUDA(ctx, cudaMemcpyAsync(out, d_rays, n * sizeof(rc_ray), cudaMemcpyDeviceToHost, ctx->stream));
     cudaFreeAsync(d_rays, ctx->stream);
     RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

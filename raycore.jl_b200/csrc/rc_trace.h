@@ -48,7 +48,8 @@ struct RcFlatBlas {  // flat primitive array view: BLAS b covers flat positions 
 // (ray (meta_src-1-row_base)*rpt + i).
 void rc_launch_view_factors(cudaStream_t st, const RcScene &sc, const RcFlatBlas *d_flat, uint32_t n_blas, uint32_t n_prims, uint32_t rpt, unsigned long long seed,
                             uint32_t row_base, uint32_t n_rows, uint32_t n_cols, uint32_t *out, rc_ray *rays_out, unsigned long long *skipped,
-                            uint32_t *overflow, int max_blocks, unsigned long long *work, const uint32_t *row_pos /* nullable, see rc_launch_vf_row_map */);
+                            uint32_t *overflow, int max_blocks, unsigned long long *work, const uint32_t *row_pos /* nullable, see rc_launch_vf_row_map */,
+                            uint32_t row_stride /* owned rows: row_base + k * row_stride, k < n_rows */);
 // row_pos[n_cols], info[2] = {duplicate metadata values, out-of-range metadata values}
 void rc_launch_vf_row_map(cudaStream_t st, const RcFlatBlas *d_flat, uint32_t n_blas, uint32_t n_prims, uint32_t n_cols, uint32_t *row_pos, uint32_t *info);
 void rc_launch_flat_metadata(cudaStream_t st, const RcFlatBlas *d_flat, uint32_t n_blas, uint32_t n_prims, uint32_t *out);

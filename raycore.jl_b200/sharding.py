@@ -52,19 +52,41 @@ def trace_sharded(trace_fn, rays: np.ndarray, record_dtype: np.dtype, device: Op
     return full.cpu().numpy().view(record_dtype)
 
 
-def view_factor_rows_sharded(vf_fn, n_prims: int, device: Optional[torch.device] = None, dst: int = 0):
-    """Rank r computes the row block [lo, hi) of the view-factor matrix with vf_fn(row_base, n_rows) -> uint32[n_rows, n_prims];
-    blocks are gathered to dst (rows in order)."""
+def view_factor_rows_sharded(vf_fn, n_prims: int, device: Optional[torch.device] = None, dst: int = 0, interleaved: bool = False):
+    """Rank r computes its share of the view-factor matrix's source rows and the shares are gathered to dst (rows in order).
+    contiguous (default): vf_fn(row_base, n_rows) -> uint32[n_rows, n_prims] for the block [lo, hi);
+    interleaved: vf_fn(row_first, n_rows, row_stride) for the rows r, r + world, ... — equally expensive shares when the cost of a
+    row varies along the matrix."""
     world, rank = dist.get_world_size(), dist.get_rank()
-    lo, hi = shard_range(n_prims, rank, world)
-    block = np.ascontiguousarray(vf_fn(lo, hi - lo), dtype=np.uint32)
+    if interleaved:
+        counts = [len(range(r, n_prims, world)) for r in range(world)]
+        block = np.ascontiguousarray(vf_fn(rank, counts[rank], world), dtype=np.uint32)
+    else:
+        lo, hi = shard_range(n_prims, rank, world)
+        block = np.ascontiguousarray(vf_fn(lo, hi - lo), dtype=np.uint32)
     t = torch.from_numpy(block.view(np.uint8).reshape(-1).copy())
     if device is not None:
         t = t.to(device)
-    full = gather_records(t, n_prims, 4 * n_prims, dst)
-    if full is None:
-        return None
-    return full.cpu().numpy().view(np.uint32).reshape(n_prims, n_prims)
+    if not interleaved:
+        full = gather_records(t, n_prims, 4 * n_prims, dst)
+        return None if full is None else full.cpu().numpy().view(np.uint32).reshape(n_prims, n_prims)
+    sizes = [c * 4 * n_prims for c in counts]
+    bufs = [torch.empty(sz, dtype=torch.uint8, device=t.device) for sz in sizes] if rank == dst else None
+    if world == 1:
+        bufs = [t]
+    else:
+        # ragged gather: pad to the largest share
+        pad = torch.zeros(max(sizes), dtype=torch.uint8, device=t.device)
+        pad[: t.numel()] = t
+        recv = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+        dist.gather(pad, recv, dst=dst)
+        if rank != dst:
+            return None
+        bufs = [recv[r][: sizes[r]] for r in range(world)]
+    full = np.zeros((n_prims, n_prims), np.uint32)
+    for r in range(world):
+        full[r::world] = bufs[r].cpu().numpy().view(np.uint32).reshape(counts[r], n_prims)
+    return full
 
 
 class PeerResultBuffer:

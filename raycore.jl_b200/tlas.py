@@ -462,16 +462,18 @@ class TLAS:
             self._ck(self._lib.rc_get_illumination(self._ctx, d.ctypes.data, grid_size, out.ctypes.data, n))
         return out
 
-    def view_factors(self, rays_per_triangle: int = 10000, seed: int = 0, row_base: int = 0, n_rows: Optional[int] = None) -> np.ndarray:
+    def view_factors(self, rays_per_triangle: int = 10000, seed: int = 0, row_base: int = 0, n_rows: Optional[int] = None, row_stride: int = 1) -> np.ndarray:
         """view_factors — :74-104.  Returns result[src, hit] (UInt32, indexable like Julia's result[src_meta, hit_meta]
-        with 0-based numpy indices = metadata - 1); `row_base`/`n_rows` select a block of source rows."""
+        with 0-based numpy indices = metadata - 1); `row_base` / `row_stride` / `n_rows` select the source rows
+        row_base + k * row_stride, k < n_rows (a contiguous block with stride 1, an interleaved share with stride = world size)."""
         self.sync()
         n = self.sizes()["blas_prims"]
-        n_rows = n - row_base if n_rows is None else n_rows
+        if n_rows is None:
+            n_rows = max(0, -(-(n - row_base) // row_stride))
         out = np.zeros((n_rows, n), np.uint32)
         sk = C.c_uint64()
         if n and n_rows:
-            self._ck(self._lib.rc_view_factors(self._ctx, rays_per_triangle, seed, out.ctypes.data, row_base, n_rows, 0, C.byref(sk)))
+            self._ck(self._lib.rc_view_factors_strided(self._ctx, rays_per_triangle, seed, out.ctypes.data, row_base, row_stride, n_rows, 0, C.byref(sk)))
         self.last_vf_skipped = sk.value
         return out
 

@@ -65,6 +65,11 @@ def test_view_factors_same_rays_exact_and_statistics():
     a = g.tlas.view_factors(rpt, seed=5, row_base=0, n_rows=n_prims // 2)
     b = g.tlas.view_factors(rpt, seed=5, row_base=n_prims // 2)
     assert np.array_equal(np.vstack([a, b]), vf_g)
+    # interleaved shares (row r of rank k in a world of 3 = row k + 3 r)
+    for k in range(3):
+        assert np.array_equal(g.tlas.view_factors(rpt, seed=5, row_base=k, row_stride=3), vf_g[k::3])
+    with pytest.raises(rc.RaycoreError):
+        g.tlas.view_factors(rpt, seed=5, row_base=1, row_stride=3, n_rows=(n_prims + 2) // 3 + 1)
     # uniform stream itself is identical on both sides
     assert np.array_equal(rays["o"].shape, (n_prims * rpt, 3))
 
@@ -118,6 +123,8 @@ def test_view_factors_metadata_not_a_permutation():
     assert 0 < vf[0, 1] <= 2 * rpt and 0 < vf[1, 0] <= rpt  # row 0 is fed by two triangles
     blocks = np.vstack([tl.view_factors(rpt, seed=1, row_base=0, n_rows=1), tl.view_factors(rpt, seed=1, row_base=1, n_rows=3)])
     assert np.array_equal(blocks, vf)
+    assert np.array_equal(tl.view_factors(rpt, seed=1, row_base=0, row_stride=2), vf[0::2])  # strided rows through the scan fallback
+    assert np.array_equal(tl.view_factors(rpt, seed=1, row_base=1, row_stride=2), vf[1::2])
     with pytest.raises(rc.RaycoreError):
         tl.view_factors(rpt, row_base=3, n_rows=2)
     # the same geometry with permutation metadata takes the row-map path; out-of-range only

@@ -33,10 +33,13 @@ def _worker(rank, world, port, out_path):
          (W.quad_mesh(2.5, 0.5), np.array([5, 6], np.uint32), [kat.I34], None)]
     ev = engines.OracleEngine(q)
     vf = sharding.view_factor_rows_sharded(lambda lo, n: ev.tlas.view_factors(50, seed=9, row_base=lo, n_rows=n), 6)
+    # interleaved shares (rows rank, rank + world, ...): ragged gather + re-interleave
+    whole = ev.tlas.view_factors(50, seed=9)
+    vf_i = sharding.view_factor_rows_sharded(lambda first, n, stride: whole[first::stride][:n], 6, interleaved=True)
     if rank == 0:
         ref = e.trace(rays)
         ref_vf = ev.tlas.view_factors(50, seed=9)
-        ok = full.tobytes() == ref.tobytes() and np.array_equal(vf, ref_vf) and vf.sum() > 0
+        ok = full.tobytes() == ref.tobytes() and np.array_equal(vf, ref_vf) and vf.sum() > 0 and np.array_equal(vf_i, ref_vf)
         open(out_path, "w").write("ok" if ok else "mismatch")
     assert sharding.shard_sizes(5001, 2) == [2500, 2501] and sharding.shard_range(10, 1, 4) == (2, 5)
     dist.barrier()
