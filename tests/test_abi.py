@@ -44,3 +44,15 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".jl")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "oracle.h" not in txt and "liboracle" not in txt, f
+
+
+def test_header_is_plain_c_and_cxx(tmp_path):
+    """include/raycore_cuda.h is the drop-in boundary: it must compile as C99 and as C++11 on its own (plain pointers and sizes)."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "raycore_cuda.h"\nint main(void) { rc_ray r; rc_hit h; (void)r; (void)h; return RC_ABI_VERSION ? 0 : 1; }\n')
+    inc = os.path.join(root, "include")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, str(src)])
+    subprocess.check_call(["g++", "-std=c++11", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, "-x", "c++", str(src)])
