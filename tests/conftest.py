@@ -11,6 +11,12 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
+    # a fresh checkout has no built artefacts (they are git-ignored): build the library once, as __graft_entry__.build() does
+    lib = os.path.join(ROOT, "raycore.jl_b200", "libraycore_cuda.so")
+    if not os.path.exists(lib) and os.environ.get("RAYCORE_CUDA_LIB") is None:
+        import subprocess
+
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "raycore.jl_b200", "csrc"), "-j4", "../libraycore_cuda.so"], stdout=subprocess.DEVNULL)
 
 
 def _have_gpu():
