@@ -133,6 +133,18 @@ int32_t rc_update_geometry(rc_context *ctx, uint32_t handle, const float *verts,
  * else compact + rebuild; returns with the stream idle.  *action: RC_SYNC_*. */
 int32_t rc_sync(rc_context *ctx, int32_t *action);
 
+/* ---- serialised geometry -------------------------------------------
+ * to_gpu(ArrayType, blas::BLAS) — src/kernel-abstractions.jl:31-36: a BLAS that was built earlier is moved to the device
+ * instead of being rebuilt.  rc_export_geometry writes a handle's built geometry (reference-layout BVH2, wide nodes, sorted
+ * triangles, hull boxes, normals if present) into a host blob; rc_push_exported restores byte-identical device arrays from it
+ * (no builder kernels run) and appends instances exactly like rc_push, so traces of the restored geometry are bit-identical.
+ * Two-call protocol: blob == NULL only reports *size.  Blobs carry a layout version and a payload hash; a blob from an
+ * incompatible build, a truncated or damaged one, or one whose references leave its arrays is refused with
+ * RC_ERR_INVALID_ARGUMENT (the hash is an integrity check, not authentication: import blobs you wrote). */
+int32_t rc_export_geometry(rc_context *ctx, uint32_t handle, void *blob, uint64_t capacity, uint64_t *size);
+int32_t rc_push_exported(rc_context *ctx, const void *blob, uint64_t size, const float *transforms, const float *inv_transforms,
+                         const uint32_t *instance_ids, uint32_t m, uint32_t *handle_out);
+
 /* ---- introspection ------------------------------------------------------------------- */
 int32_t rc_is_valid(const rc_context *ctx, uint32_t handle);                 /* :524-526 */
 uint32_t rc_n_instances(const rc_context *ctx);                              /* live, :2391-2398 */

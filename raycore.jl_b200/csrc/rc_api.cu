@@ -219,14 +219,9 @@ static int32_t build_blas_from(rc_context *ctx, const float *verts, uint32_t n_f
     return RC_OK;
 }
 
-int32_t rc_push(rc_context *ctx, const float *verts, uint32_t n_faces, const uint32_t *face_meta, const float *transforms, const float *inv_transforms,
-                const uint32_t *instance_ids, uint32_t m, uint32_t flags, uint32_t *handle_out) {
-    if (!ctx) return RC_ERR_INVALID_ARGUMENT;
-    use_device(ctx);
-    if (!transforms || m == 0 || !handle_out) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "rc_push: transforms, m >= 1 and handle_out are required");
-    RcDeviceBlas b;
-    int32_t rc = build_blas_from(ctx, verts, n_faces, face_meta, flags, &b);
-    if (rc != RC_OK) return rc;
+// append_instances_with_handle!, :612-623: the BLAS joins the table, m descriptors join the instance list under a fresh handle
+static uint32_t append_blas_with_instances(rc_context *ctx, const RcDeviceBlas &b, const float *transforms, const float *inv_transforms,
+                                           const uint32_t *instance_ids, uint32_t m) {
     ctx->blas.push_back(b);
     uint32_t blas_idx = (uint32_t)ctx->blas.size();  // :607
     uint32_t start = (uint32_t)ctx->instances.size();
@@ -240,10 +235,21 @@ int32_t rc_push(rc_context *ctx, const float *verts, uint32_t n_faces, const uin
         d.flags = 0;
         ctx->instances.push_back(d);
     }
-    uint32_t h = ctx->next_handle++;  // append_instances_with_handle!, :612-623
+    uint32_t h = ctx->next_handle++;
     ctx->handles[h] = HandleInfo{start, m, false};
     ctx->dirty = true;
-    *handle_out = h;
+    return h;
+}
+
+int32_t rc_push(rc_context *ctx, const float *verts, uint32_t n_faces, const uint32_t *face_meta, const float *transforms, const float *inv_transforms,
+                const uint32_t *instance_ids, uint32_t m, uint32_t flags, uint32_t *handle_out) {
+    if (!ctx) return RC_ERR_INVALID_ARGUMENT;
+    use_device(ctx);
+    if (!transforms || m == 0 || !handle_out) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "rc_push: transforms, m >= 1 and handle_out are required");
+    RcDeviceBlas b;
+    int32_t rc = build_blas_from(ctx, verts, n_faces, face_meta, flags, &b);
+    if (rc != RC_OK) return rc;
+    *handle_out = append_blas_with_instances(ctx, b, transforms, inv_transforms, instance_ids, m);
     return RC_OK;
 }
 
@@ -316,6 +322,43 @@ int32_t rc_update_geometry(rc_context *ctx, uint32_t handle, const float *verts,
     rc_free_blas(&ctx->blas[blas_idx - 1], ctx->stream);
     ctx->blas[blas_idx - 1] = nb;
     ctx->dirty = true;
+    return RC_OK;
+}
+
+// ---- serialised geometry (rc_build.cu, "Serialised BLAS") ----
+int32_t rc_export_geometry(rc_context *ctx, uint32_t handle, void *blob, uint64_t capacity, uint64_t *size) {
+    if (!ctx) return RC_ERR_INVALID_ARGUMENT;
+    use_device(ctx);
+    HandleInfo *hi = nullptr;
+    int32_t rc = find_handle(ctx, handle, &hi);
+    if (rc != RC_OK) return rc;
+    if (hi->count == 0) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "Handle has no instances");
+    const RcDeviceBlas &B = ctx->blas[ctx->instances[hi->start].blas_index - 1];
+    const uint64_t need = rc_blas_blob_bytes(B);
+    if (size) *size = need;
+    if (!blob) {
+        if (!size) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "rc_export_geometry: blob and size are both NULL");
+        return RC_OK;  // size query
+    }
+    if (capacity < need) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "rc_export_geometry: capacity " + std::to_string(capacity) + " < " + std::to_string(need) + " bytes");
+    std::string err;
+    if (!rc_blas_export(ctx->stream, B, blob, capacity, err)) RC_FAIL(ctx, RC_ERR_CUDA, err);
+    return RC_OK;
+}
+
+int32_t rc_push_exported(rc_context *ctx, const void *blob, uint64_t size, const float *transforms, const float *inv_transforms, const uint32_t *instance_ids,
+                         uint32_t m, uint32_t *handle_out) {
+    if (!ctx) return RC_ERR_INVALID_ARGUMENT;
+    use_device(ctx);
+    if (!blob || !transforms || m == 0 || !handle_out) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "rc_push_exported: blob, transforms, m >= 1 and handle_out are required");
+    RcDeviceBlas b;
+    std::string err;
+    if (!rc_blas_import(ctx->stream, blob, size, &b, err)) {
+        rc_free_blas(&b, ctx->stream);
+        const bool cuda = err.find("cuda") == 0;  // CK() messages start with the failing call
+        RC_FAIL(ctx, cuda ? (err.find("out of memory") != std::string::npos ? RC_ERR_OUT_OF_MEMORY : RC_ERR_CUDA) : RC_ERR_INVALID_ARGUMENT, err);
+    }
+    *handle_out = append_blas_with_instances(ctx, b, transforms, inv_transforms, instance_ids, m);
     return RC_OK;
 }
 

@@ -724,3 +724,146 @@ bool rc_refit_tlas(cudaStream_t st, const rc_instance_desc *h_inst, uint32_t n, 
     CK(cudaGetLastError());
     return extent_supported(t->root_aabb, err);
 }
+
+// =================================================================================================
+// Serialised BLAS: the built structure moved host <-> device as one blob, the role of
+// to_gpu(ArrayType, blas::BLAS) (src/kernel-abstractions.jl:31-36: a BLAS built elsewhere is uploaded, not rebuilt).
+//   [RcBlobHeader 128 B][nodes2 64·(2n-1)][nodes4 64·(n+1)][tris 48·n][hull 32·RC_HULL_BOXES][normals 36·n, optional]
+// every section starts on a 64-byte boundary.  An import restores byte-identical device arrays, so traces of an imported
+// geometry are bit-identical to traces of the original.
+// =================================================================================================
+static_assert(sizeof(RcBox) == 32, "blob layout");
+static_assert(sizeof(RcNode2) == 64 && sizeof(RcNode4) == 64 && sizeof(RcTri) == 48, "blob layout");
+
+struct RcBlobHeader {
+    char magic[8];  // "RCBLAS\0\1"
+    uint32_t abi_version, leaf_max, hull_boxes, n, n_faces_in, has_normals;
+    float root_aabb[6];
+    uint64_t total_bytes, payload_hash;
+    uint64_t off_nodes2, off_nodes4, off_tris, off_hull, off_normals;  // from the blob start
+    uint8_t pad[16];
+};
+static_assert(sizeof(RcBlobHeader) == 128, "blob header is 128 bytes");
+static const char RC_BLOB_MAGIC[8] = {'R', 'C', 'B', 'L', 'A', 'S', 0, 1};
+
+static inline uint64_t up64(uint64_t x) { return (x + 63u) & ~(uint64_t)63u; }
+
+static void blob_layout(uint32_t n, bool normals, RcBlobHeader *h) {
+    uint64_t o = sizeof(RcBlobHeader);
+    h->off_nodes2 = o; o = up64(o + sizeof(RcNode2) * (2 * (uint64_t)n - 1));
+    h->off_nodes4 = o; o = up64(o + sizeof(RcNode4) * ((uint64_t)n + 1));
+    h->off_tris = o;   o = up64(o + sizeof(RcTri) * (uint64_t)n);
+    h->off_hull = o;   o = up64(o + sizeof(RcBox) * RC_HULL_BOXES);
+    h->off_normals = normals ? o : 0;
+    if (normals) o = up64(o + sizeof(float) * 9 * (uint64_t)n);
+    h->total_bytes = o;
+}
+
+// word-wise multiply-xorshift hash of the payload (everything after the header); detects truncation and bit rot, not an adversary
+static uint64_t blob_hash(const uint8_t *p, uint64_t bytes) {
+    uint64_t h = 0x9E3779B97F4A7C15ull ^ bytes;
+    const uint64_t nw = bytes / 8;
+    for (uint64_t i = 0; i < nw; i++) {
+        uint64_t w;
+        memcpy(&w, p + 8 * i, 8);
+        h = (h ^ w) * 0xD6E8FEB86659FD93ull;
+        h ^= h >> 32;
+    }
+    for (uint64_t i = 8 * nw; i < bytes; i++) h = (h ^ p[i]) * 0x100000001B3ull;
+    return h;
+}
+
+uint64_t rc_blas_blob_bytes(const RcDeviceBlas &b) {
+    RcBlobHeader h;
+    blob_layout(b.n, b.normals != nullptr, &h);
+    return h.total_bytes;
+}
+
+bool rc_blas_export(cudaStream_t st, const RcDeviceBlas &b, void *blob, uint64_t capacity, std::string &err) {
+    if (b.n == 0 || !b.nodes2 || !b.nodes4 || !b.tris || !b.hull) { err = "export: geometry is not built"; return false; }
+    RcBlobHeader h;
+    memset(&h, 0, sizeof h);
+    memcpy(h.magic, RC_BLOB_MAGIC, 8);
+    h.abi_version = RC_ABI_VERSION;
+    h.leaf_max = RC_BLAS_LEAF_MAX;
+    h.hull_boxes = RC_HULL_BOXES;
+    h.n = b.n;
+    h.n_faces_in = b.n_faces_in;
+    h.has_normals = b.normals ? 1u : 0u;
+    memcpy(h.root_aabb, b.root_aabb, 24);
+    blob_layout(b.n, b.normals != nullptr, &h);
+    if (capacity < h.total_bytes) { err = "export: capacity too small"; return false; }
+    uint8_t *p = static_cast<uint8_t *>(blob);
+    memset(p + sizeof h, 0, h.total_bytes - sizeof h);  // alignment gaps are part of the hashed payload
+    const uint64_t n = b.n;
+    CK(cudaMemcpyAsync(p + h.off_nodes2, b.nodes2, sizeof(RcNode2) * (2 * n - 1), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(p + h.off_nodes4, b.nodes4, sizeof(RcNode4) * (n + 1), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(p + h.off_tris, b.tris, sizeof(RcTri) * n, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(p + h.off_hull, b.hull, sizeof(RcBox) * RC_HULL_BOXES, cudaMemcpyDeviceToHost, st));
+    if (b.normals) CK(cudaMemcpyAsync(p + h.off_normals, b.normals, sizeof(float) * 9 * n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    // wide-node slots no kernel writes (slot 0; slot n when there are internal nodes) are zeroed so equal geometry gives equal blobs
+    memset(p + h.off_nodes4, 0, sizeof(RcNode4));
+    if (n > 1) memset(p + h.off_nodes4 + sizeof(RcNode4) * n, 0, sizeof(RcNode4));
+    h.payload_hash = blob_hash(p + sizeof h, h.total_bytes - sizeof h);
+    memcpy(p, &h, sizeof h);
+    return true;
+}
+
+// structural check of an uploaded blob (rc_validate_blas_elem, rc_build_core.cuh): every reference stays inside the arrays,
+// so a damaged blob cannot send a traversal out of bounds
+__global__ void k_validate_blas(const RcNode2 *__restrict__ nodes2, const RcNode4 *__restrict__ nodes4, const RcTri *__restrict__ tris, uint32_t n,
+                                uint32_t *__restrict__ bad) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t errs = rc_validate_blas_elem(i, nodes2, nodes4, tris, n, RC_BLAS_LEAF_MAX);
+    if (errs) atomicAdd(bad, errs);
+}
+
+bool rc_blas_import(cudaStream_t st, const void *blob, uint64_t size, RcDeviceBlas *out, std::string &err) {
+    *out = RcDeviceBlas();
+    if (!blob || size < sizeof(RcBlobHeader)) { err = "import: blob too small"; return false; }
+    RcBlobHeader h;
+    memcpy(&h, blob, sizeof h);
+    if (memcmp(h.magic, RC_BLOB_MAGIC, 8) != 0) { err = "import: not a raycore BLAS blob"; return false; }
+    if (h.abi_version != RC_ABI_VERSION || h.leaf_max != RC_BLAS_LEAF_MAX || h.hull_boxes != RC_HULL_BOXES) {
+        err = "import: blob was written by an incompatible library build";
+        return false;
+    }
+    if (h.n == 0 || h.n > RC_LEAF_START_MASK - 16u || h.n_faces_in < h.n) { err = "import: bad triangle count"; return false; }
+    RcBlobHeader want = h;
+    blob_layout(h.n, h.has_normals != 0, &want);
+    if (want.total_bytes != h.total_bytes || want.off_nodes2 != h.off_nodes2 || want.off_nodes4 != h.off_nodes4 || want.off_tris != h.off_tris ||
+        want.off_hull != h.off_hull || want.off_normals != h.off_normals) {
+        err = "import: section table does not match the triangle count";
+        return false;
+    }
+    if (size < h.total_bytes) { err = "import: blob is truncated"; return false; }
+    const uint8_t *p = static_cast<const uint8_t *>(blob);
+    if (blob_hash(p + sizeof h, h.total_bytes - sizeof h) != h.payload_hash) { err = "import: payload hash mismatch (corrupted blob)"; return false; }
+    if (!extent_supported(h.root_aabb, err)) return false;
+    const uint64_t n = h.n;
+    uint32_t *d_bad = nullptr;
+    RcTemps tmp(st);
+    TMP(d_bad, 1);
+    CK(cudaMallocAsync(&out->nodes2, sizeof(RcNode2) * (2 * n - 1), st));
+    CK(cudaMallocAsync(&out->nodes4, sizeof(RcNode4) * (n + 1), st));
+    CK(cudaMallocAsync(&out->tris, sizeof(RcTri) * n, st));
+    CK(cudaMallocAsync(&out->hull, sizeof(RcBox) * RC_HULL_BOXES, st));
+    if (h.has_normals) CK(cudaMallocAsync(&out->normals, sizeof(float) * 9 * n, st));
+    out->n = h.n;
+    out->n_faces_in = h.n_faces_in;
+    memcpy(out->root_aabb, h.root_aabb, 24);
+    CK(cudaMemcpyAsync(out->nodes2, p + h.off_nodes2, sizeof(RcNode2) * (2 * n - 1), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(out->nodes4, p + h.off_nodes4, sizeof(RcNode4) * (n + 1), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(out->tris, p + h.off_tris, sizeof(RcTri) * n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(out->hull, p + h.off_hull, sizeof(RcBox) * RC_HULL_BOXES, cudaMemcpyHostToDevice, st));
+    if (h.has_normals) CK(cudaMemcpyAsync(out->normals, p + h.off_normals, sizeof(float) * 9 * n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(d_bad, 0, 4, st));
+    k_validate_blas<<<cdiv((uint32_t)(2 * n), 256), 256, 0, st>>>(out->nodes2, out->nodes4, out->tris, h.n, d_bad);
+    uint32_t bad = 0;
+    CK(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));  // the caller may release the blob on return
+    CK(cudaGetLastError());
+    if (bad) { err = "import: blob fails the structural check (" + std::to_string(bad) + " bad references)"; return false; }
+    return true;
+}

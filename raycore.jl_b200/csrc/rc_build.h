@@ -54,6 +54,10 @@ struct RcDeviceTlas {
 
 bool rc_build_blas(cudaStream_t st, const float *d_verts, const uint32_t *d_face_meta, uint32_t n_faces, RcDeviceBlas *out, std::string &err);
 void rc_free_blas(RcDeviceBlas *b, cudaStream_t st);
+// serialised BLAS (host blob <-> device arrays, byte-identical restore; layout in rc_build.cu)
+uint64_t rc_blas_blob_bytes(const RcDeviceBlas &b);
+bool rc_blas_export(cudaStream_t st, const RcDeviceBlas &b, void *blob, uint64_t capacity, std::string &err);
+bool rc_blas_import(cudaStream_t st, const void *blob, uint64_t size, RcDeviceBlas *out, std::string &err);
 bool rc_build_tlas(cudaStream_t st, const rc_instance_desc *h_inst, uint32_t n, const std::vector<RcBlasPtrs> &blas, const std::vector<float> &blas_roots,
                    RcDeviceTlas *t, std::string &err);
 bool rc_refit_tlas(cudaStream_t st, const rc_instance_desc *h_inst, uint32_t n, RcDeviceTlas *t, std::string &err);

@@ -155,6 +155,37 @@ RC_HD RcNode4 rc_collapse_node(uint32_t idx, const RcBox *boxes, const RcTopo *t
     return nd;
 }
 
+// Structural check of one element of a BLAS (used on imported blobs): element i covers BVH2 node i+1, wide node i and triangle i.
+// Returns the number of references that leave the arrays: BVH2 internal nodes are 1..n-1 and leaves n..2n-1
+// (src/instanced-bvh.jl:1293-1295, leaf: child0 == INVALID_NODE, child1 = 1-based primitive); wide nodes in use are 1..max(1, n-1).
+RC_HD uint32_t rc_validate_blas_elem(uint32_t i, const RcNode2 *nodes2, const RcNode4 *nodes4, const RcTri *tris, uint32_t n, uint32_t leaf_max) {
+    uint32_t errs = 0;
+    const uint32_t n_nodes2 = 2u * n - 1u;
+    if (i < n_nodes2) {
+        const RcNode2 &nd = nodes2[i];
+        if (i + 1u < n) {
+            if (nd.child0 < 1u || nd.child0 > n_nodes2 || nd.child1 < 1u || nd.child1 > n_nodes2) errs++;
+        } else if (nd.child0 != RC_INVALID || nd.child1 < 1u || nd.child1 > n) {
+            errs++;
+        }
+    }
+    const uint32_t last = n > 1u ? n - 1u : 1u;
+    if (i >= 1u && i <= last) {
+        const RcNode4 &w = nodes4[i];
+        const uint32_t c[4] = {w.child0, w.child1, w.child2, w.child3};
+        for (int k = 0; k < 4; k++) {
+            if (c[k] & RC_LEAF_BIT) {
+                const uint32_t count = ((c[k] >> RC_LEAF_COUNT_SHIFT) & 7u) + 1u, start = c[k] & RC_LEAF_START_MASK;
+                if ((c[k] & RC_TLAS_LEAF_TAG) == RC_TLAS_LEAF_TAG || count > leaf_max || start >= n || count > n - start) errs++;
+            } else if (n == 1u || c[k] < 1u || c[k] > last) {
+                errs++;
+            }
+        }
+    }
+    if (i < n && tris[i].prim_id >= n) errs++;
+    return errs;
+}
+
 // world AABB of an instance: bounds of the 8 transformed corners of the BLAS root box
 // (compute_instance_world_aabb, kernels.jl:38-62; corner order bounds.jl:53-59)
 RC_HD void rc_instance_world_aabb(const float *xf, const float *local, f3 &mn, f3 &mx) {

@@ -83,6 +83,29 @@ end
 Base.push!(t::CuTLAS, mesh::GeometryBasics.Mesh, transform::Mat4f = Mat4f(I); instance_id::UInt32 = UInt32(0), sbt_offset::UInt32 = UInt32(0)) =
     push!(t, mesh, [transform]; instance_ids = [instance_id])
 
+# ---- serialised geometry (to_gpu(ArrayType, blas::BLAS), src/kernel-abstractions.jl:31-36: upload a built BLAS instead of rebuilding) ----
+"Bytes of the handle's built geometry (BVH2 in BVHNode2 order, wide nodes, sorted triangles, hull, normals): write them to disk, restore with `push_exported!`."
+function export_geometry(t::CuTLAS, h::TLASHandle)
+    n = Ref{UInt64}(0)
+    check(t.ctx, ccall((:rc_export_geometry, lib), Int32, (Ptr{Cvoid}, UInt32, Ptr{Cvoid}, UInt64, Ref{UInt64}), t.ctx, h.id, C_NULL, 0, n))
+    blob = Vector{UInt8}(undef, n[])
+    check(t.ctx, ccall((:rc_export_geometry, lib), Int32, (Ptr{Cvoid}, UInt32, Ptr{Cvoid}, UInt64, Ref{UInt64}), t.ctx, h.id, blob, length(blob), n))
+    return blob
+end
+"push! of a geometry restored from `export_geometry` bytes (no builder kernel runs).  `mesh` is the caller's copy used to materialise Triangles."
+function push_exported!(t::CuTLAS, blob::Vector{UInt8}, mesh::GeometryBasics.Mesh, transforms::AbstractVector{Mat4f};
+                        instance_ids::Union{Nothing, AbstractVector{<:Integer}} = nothing)
+    instance_ids !== nothing && length(instance_ids) != length(transforms) &&
+        throw(ArgumentError("instance_ids length $(length(instance_ids)) != transforms length $(length(transforms))"))
+    xf = [mat4_to_mat3x4(m) for m in transforms]; inv = [mat3x4_inverse(m) for m in xf]
+    ids = instance_ids === nothing ? C_NULL : UInt32.(instance_ids)
+    h = Ref{UInt32}(0)
+    check(t.ctx, ccall((:rc_push_exported, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, UInt64, Ptr{Float32}, Ptr{Float32}, Ptr{UInt32}, UInt32, Ref{UInt32}),
+        t.ctx, blob, length(blob), reinterpret(Float32, xf), reinterpret(Float32, inv), ids, length(xf), h))
+    t.meshes[h[]] = [GeometryBasics.expand_faceviews(mesh)]
+    return TLASHandle(h[])
+end
+
 function Base.delete!(t::CuTLAS, h::TLASHandle)::Bool
     d = Ref{Int32}(0); check(t.ctx, ccall((:rc_delete, lib), Int32, (Ptr{Cvoid}, UInt32, Ref{Int32}), t.ctx, h.id, d)); d[] != 0
 end

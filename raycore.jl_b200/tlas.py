@@ -53,6 +53,36 @@ def _as_rays(rays) -> np.ndarray:
     return out
 
 
+BLOB_HEADER_DTYPE = np.dtype(
+    [
+        ("magic", "S8"), ("abi_version", "<u4"), ("leaf_max", "<u4"), ("hull_boxes", "<u4"), ("n", "<u4"), ("n_faces_in", "<u4"), ("has_normals", "<u4"),
+        ("root_aabb", "<f4", 6), ("total_bytes", "<u8"), ("payload_hash", "<u8"),
+        ("off_nodes2", "<u8"), ("off_nodes4", "<u8"), ("off_tris", "<u8"), ("off_hull", "<u8"), ("off_normals", "<u8"), ("pad", "u1", 16),
+    ]
+)  # RcBlobHeader, csrc/rc_build.cu
+assert BLOB_HEADER_DTYPE.itemsize == 128
+BLOB_TRI_DTYPE = np.dtype([("v0", "<f4", 3), ("prim_id", "<u4"), ("v1", "<f4", 3), ("metadata", "<u4"), ("v2", "<f4", 3), ("face_index", "<u4")])  # RcTri
+
+
+def blob_header(blob) -> np.void:
+    """Header record of an `export_geometry` blob."""
+    return np.frombuffer(memoryview(blob)[:128], BLOB_HEADER_DTYPE)[0]
+
+
+def blob_triangles(blob) -> np.ndarray:
+    """Morton-sorted triangle records of an `export_geometry` blob."""
+    h = blob_header(blob)
+    return np.frombuffer(memoryview(blob), BLOB_TRI_DTYPE, count=int(h["n"]), offset=int(h["off_tris"]))
+
+
+def blob_faces(blob) -> np.ndarray:
+    """n_faces_in x 9 vertex soup in submission order (faces the degenerate filter dropped are zero)."""
+    h, t = blob_header(blob), blob_triangles(blob)
+    out = np.zeros((int(h["n_faces_in"]), 9), np.float32)
+    out[t["face_index"]] = np.concatenate([t["v0"], t["v1"], t["v2"]], axis=1)
+    return out
+
+
 class DeviceQueue:
     """A device-resident work queue (the reference's SoA queues on the backend, docs/src/wavefront-renderer.jl:127-180):
     `count` records of numpy dtype `dtype` in memory owned by the TLAS's context."""
@@ -185,6 +215,23 @@ class TLAS:
 
         `transform`: Mat4f (4x4), Mat3x4f (12 floats), or a list/array of them for instancing."""
         v = self._verts(mesh)
+        xf, inv, ids, m = self._instance_args(transform, instance_id, instance_ids, inv_transform)
+        fm = None if face_meta is None else np.ascontiguousarray(face_meta, np.uint32)
+        if fm is not None and len(fm) != len(v):
+            raise ValueError("face_meta length != number of faces")
+        h = C.c_uint32()
+        self._ck(
+            self._lib.rc_push(
+                self._ctx, v.ctypes.data, len(v), None if fm is None else fm.ctypes.data, xf.ctypes.data, None if inv is None else inv.ctypes.data,
+                None if ids is None else ids.ctypes.data, m, 0, C.byref(h),
+            )
+        )
+        self._meshes[h.value] = (v, fm)
+        return TLASHandle(h.value)
+
+    @staticmethod
+    def _instance_args(transform, instance_id, instance_ids, inv_transform):
+        """(transforms m x 12, inverse transforms or None, instance ids or None, m) of a push — the argument rules of :639-676."""
         if transform is None:
             xf = IDENTITY3x4.reshape(1, 12).copy()
             multi = False
@@ -199,19 +246,30 @@ class TLAS:
             ids = None if instance_ids is None else np.ascontiguousarray(instance_ids, np.uint32)
         else:
             ids = np.array([instance_id], np.uint32)
-        fm = None if face_meta is None else np.ascontiguousarray(face_meta, np.uint32)
-        if fm is not None and len(fm) != len(v):
-            raise ValueError("face_meta length != number of faces")
         inv = None if inv_transform is None else np.ascontiguousarray(np.asarray(inv_transform, np.float32).reshape(-1, 12))
-        xf = np.ascontiguousarray(xf, np.float32)
+        return np.ascontiguousarray(xf, np.float32), inv, ids, m
+
+    # -- serialised geometry (to_gpu(ArrayType, blas::BLAS), src/kernel-abstractions.jl:31-36) ----
+    def export_geometry(self, handle: TLASHandle) -> np.ndarray:
+        """The handle's built geometry (BVH2, wide nodes, sorted triangles, hull, normals) as one byte blob."""
+        size = C.c_uint64()
+        self._ck(self._lib.rc_export_geometry(self._ctx, handle.id, None, 0, C.byref(size)))
+        blob = np.empty(size.value, np.uint8)
+        self._ck(self._lib.rc_export_geometry(self._ctx, handle.id, blob.ctypes.data, blob.nbytes, C.byref(size)))
+        return blob
+
+    def push_exported(self, blob, transform=None, *, instance_id: int = 0, instance_ids: Optional[Sequence[int]] = None, inv_transform=None) -> TLASHandle:
+        """push! of a geometry restored from `export_geometry` bytes: no builder kernel runs, the device arrays are byte-identical."""
+        blob = np.ascontiguousarray(np.frombuffer(blob, np.uint8) if not isinstance(blob, np.ndarray) else blob.view(np.uint8).reshape(-1))
+        xf, inv, ids, m = self._instance_args(transform, instance_id, instance_ids, inv_transform)
         h = C.c_uint32()
         self._ck(
-            self._lib.rc_push(
-                self._ctx, v.ctypes.data, len(v), None if fm is None else fm.ctypes.data, xf.ctypes.data, None if inv is None else inv.ctypes.data,
-                None if ids is None else ids.ctypes.data, m, 0, C.byref(h),
+            self._lib.rc_push_exported(
+                self._ctx, blob.ctypes.data, blob.nbytes, xf.ctypes.data, None if inv is None else inv.ctypes.data,
+                None if ids is None else ids.ctypes.data, m, C.byref(h),
             )
         )
-        self._meshes[h.value] = (v, fm)
+        self._meshes[h.value] = (blob_faces(blob), None)  # the submitted soup as far as the blob keeps it (dropped faces are zero)
         return TLASHandle(h.value)
 
     def delete(self, handle: TLASHandle) -> bool:

@@ -3,6 +3,7 @@
  * a transform update (refit) and an any-hit query.  Exit code 0 = all checks passed. */
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "raycore_cuda.h"
@@ -53,6 +54,25 @@ int main(void) {
     CHECK(rc_sync(ctx, &action) == RC_OK && action == RC_SYNC_REFIT);
     CHECK(rc_trace_closest(ctx, rays, hits, 3, 0) == RC_OK);
     CHECK(hits[2].hit == 1 && hits[2].instance_id == 1 && fabsf(hits[2].t - 1.0f) < 1e-6f && hits[1].hit == 0);
+
+    /* serialised geometry: export the built quad, restore it in a second context, same answers (two-call size protocol) */
+    {
+        uint64_t size = 0;
+        CHECK(rc_export_geometry(ctx, handle, NULL, 0, &size) == RC_OK && size > 128);
+        void *blob = malloc(size);
+        CHECK(blob != NULL && rc_export_geometry(ctx, handle, blob, size, &size) == RC_OK);
+        rc_context *ctx2 = NULL;
+        CHECK(rc_create(-1, &ctx2) == RC_OK);
+        uint32_t h2 = 0;
+        rc_hit hits2[3];
+        int same = rc_push_exported(ctx2, blob, size, xf2, NULL, ids, 2, &h2) == RC_OK && rc_sync(ctx2, &action) == RC_OK &&
+                   rc_trace_closest(ctx2, rays, hits2, 3, 0) == RC_OK && memcmp(hits, hits2, sizeof hits) == 0;
+        ((unsigned char *)blob)[200] ^= 1; /* a damaged blob is refused */
+        int refused = rc_push_exported(ctx2, blob, size, xf2, NULL, ids, 2, &h2) == RC_ERR_INVALID_ARGUMENT;
+        free(blob);
+        CHECK(rc_destroy(ctx2) == RC_OK);
+        CHECK(same && refused);
+    }
 
     /* error behaviour of the handle API (src/instanced-bvh.jl:715-718) */
     CHECK(rc_update_transforms(ctx, handle + 100, xf2, NULL, 2) == RC_ERR_INVALID_HANDLE);

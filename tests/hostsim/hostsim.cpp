@@ -300,6 +300,31 @@ uint32_t hs_check_wide(void *b) {
     return bad;
 }
 
+// structural check used on imported blobs (rc_validate_blas_elem; the loop stands in for k_validate_blas).  corrupt: 0 none,
+// 1 wide-node child index past the last node, 2 leaf range past the triangle array, 3 BVH2 child out of range, 4 BVH2 leaf
+// primitive out of range, 5 triangle prim_id out of range, 6 TLAS-tagged reference inside a BLAS.  `where` picks the element.
+uint32_t hs_validate_blas(void *b, int corrupt, uint32_t where) {
+    HsBlas *B = (HsBlas *)b;
+    HsTree &t = B->tree;
+    const uint32_t n = t.n, last = n > 1 ? n - 1 : 1;
+    std::vector<RcNode2> nodes2 = t.nodes2;
+    std::vector<RcNode4> nodes4 = t.nodes4;
+    std::vector<RcTri> tris = B->tris;
+    const uint32_t w = 1 + where % last;
+    switch (corrupt) {
+        case 1: nodes4[w].child1 = last + 1; break;
+        case 2: nodes4[w].child0 = RC_LEAF_BIT | ((RC_BLAS_LEAF_MAX - 1u) << RC_LEAF_COUNT_SHIFT) | (n - RC_BLAS_LEAF_MAX + 1u); break;
+        case 3: if (n > 1) nodes2[where % (n - 1)].child1 = 2 * n; else nodes2[0].child0 = 1; break;
+        case 4: nodes2[n - 1 + where % n].child1 = n + 1; break;
+        case 5: tris[where % n].prim_id = n; break;
+        case 6: nodes4[w].child2 = RC_TLAS_LEAF_TAG | 0u; break;
+        default: break;
+    }
+    uint32_t bad = 0;
+    for (uint32_t i = 0; i < 2 * n; i++) bad += rc_validate_blas_elem(i, nodes2.data(), nodes4.data(), tris.data(), n, RC_BLAS_LEAF_MAX);
+    return bad;
+}
+
 // ---- wavefront stage bodies (rc_wave_core.cuh); loops stand in for k_primary_rays / k_geometric_normals / k_shadow_rays
 void hs_primary_rays(const float *camera_pos, const float *right, const float *up, const float *forward, float half_width, float half_height, int lookat, int jitter,
                      uint32_t width, uint32_t height, uint32_t n_samples, uint64_t seed, rc_ray *out) {

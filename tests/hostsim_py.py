@@ -40,6 +40,8 @@ def lib():
         L.hs_shadow_rays.argtypes = [vp, vp, vp, C.c_uint64, vp, vp, C.c_uint32, C.c_float, vp]
         L.hs_check_wide.restype = C.c_uint32
         L.hs_check_wide.argtypes = [vp]
+        L.hs_validate_blas.restype = C.c_uint32
+        L.hs_validate_blas.argtypes = [vp, C.c_int, C.c_uint32]
         _lib = L
     return _lib
 
@@ -70,6 +72,10 @@ class HsBlas:
 
     def check_wide(self):
         return lib().hs_check_wide(self.p)
+
+    def validate(self, corrupt=0, where=0):
+        """rc_validate_blas_elem over the whole BLAS (optionally after one injected fault): number of bad references."""
+        return lib().hs_validate_blas(self.p, corrupt, where)
 
 
 def mat3x4_inverse(m):

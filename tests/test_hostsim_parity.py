@@ -99,3 +99,16 @@ def test_single_blas_million_scale_structure():
     cls = parity.classify(a, b, parity.make_graze_verifier(orc, rays, a, o.instances, o.tris))
     s = parity.assert_parity(cls, len(rays), label="bumpy sphere interior")
     assert b["hit"].all() and s["exact"] >= 0.995 * len(rays), s
+
+
+def test_blob_structural_check_accepts_built_trees_and_catches_faults():
+    """The validator run on imported blobs (rc_validate_blas_elem, k_validate_blas): clean for everything the builder produces
+    (single triangle, 2-triangle root leaf, duplicates, large meshes), non-zero for each class of out-of-range reference."""
+    for verts in (kat.TRI, W.quad_mesh(), W.box_mesh(), W.uv_sphere(9), W.bumpy_sphere(23), np.repeat(kat.TRI.reshape(1, 9), 9, axis=0)):
+        hb = hs.HsBlas(verts)
+        assert hb.validate() == 0
+        for where in (0, 1, 7, 1000):
+            for corrupt in (2, 3, 4, 5, 6):
+                assert hb.validate(corrupt, where) >= 1, (hb.n, corrupt, where)
+            if hb.n > 1:
+                assert hb.validate(1, where) >= 1, (hb.n, where)
