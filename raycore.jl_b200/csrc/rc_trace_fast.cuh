@@ -4,7 +4,7 @@
 // Every lane owns one ray at a time and is, at any moment, ready for one or two of four step kinds:
 //   N  node step      its next reference is a wide node (4 quantised child boxes)
 //   T  triangle step  it has a leaf parked (one triangle per step)
-//   X  level step     it must enter an instance (TLAS leaf) or leave one (sentinel popped)
+//   X  level step     it must enter an instance (TLAS leaf); leaving one (sentinel popped) is folded into the settle
 //   F  refill         its ray is finished (or it has none yet)
 // Each lane keeps its readiness as a packed vote word (one byte per kind); every iteration the warp sums the votes
 // with ONE REDUX.SUM and executes the kind with the most ready lanes, so a freshly fetched ray that needs ten box steps
@@ -141,9 +141,22 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, SINGLE ? RC_MIN_BLOCKS_SINGL
     }
 #define RC_TOP() (*spa)
 #define RC_DEPTH() ((uint32_t)(spa - sbase) / RC_ROW)
+    // A lane whose next reference is the level sentinel (and has no leaf parked) returns to the TLAS right here in the settle
+    // instead of voting for a level-change step: the leave is ~10 instructions, a scheduler round for it costs more (+3.2 % on the
+    // instanced scene C3; folding the much longer instance *entry* in the same way gives the gain back — profiles/README.md).
+#define RC_SETTLE_LEAVE()                                                                 \
+    if (!SINGLE && cur == RC_SENTINEL && leaf == 0) {                                     \
+        cur_inst = -1; /* src/instanced-bvh.jl:1996-2006 */                               \
+        nodes = sc.tlas4;                                                                 \
+        cur = RC_TOP();                                                                   \
+        spa -= RC_ROW;                                                                    \
+        o = wo; d = wd;                                                                   \
+        inv = mk3(rc_fast_inv(d.x), rc_fast_inv(d.y), rc_fast_inv(d.z));                  \
+    }
     // after a step: park a freshly reached BLAS leaf (so the lane can keep descending) and recompute the lane's vote
 #define RC_SETTLE()                                                                                                \
     {                                                                                                              \
+        RC_SETTLE_LEAVE()                                                                                          \
         if (spa > sbase + RC_SSTACK * RC_ROW) { ovf = true; cur = RC_INVALID; leaf = 0; spa = sbase; }               \
         const bool park_ = ((cur ^ RC_LEAF_BIT) < 0x40000000u) && leaf == 0; /* BLAS leaf reference */              \
         const uint32_t top_ = RC_TOP();                                                                            \
@@ -153,8 +166,8 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, SINGLE ? RC_MIN_BLOCKS_SINGL
         spa -= park_ ? RC_ROW : 0;                                                                                 \
         vote = ((int)cur >= 0) ? RC_VOTE_N : 0u;                                                                   \
         vote |= leaf ? RC_VOTE_T : ((cur == RC_INVALID) ? RC_VOTE_F : 0u);                                         \
-        /* level change: instance leaf or sentinel = [0xC0000000, 0xF0000000); the sentinel waits for the parked leaf */ \
-        if (!SINGLE) vote |= (((cur + 0x40000000u) < 0x30000000u) && !(cur == RC_SENTINEL && leaf != 0)) ? RC_VOTE_X : 0u; \
+        /* instance leaf = [0xC0000000, RC_SENTINEL); a sentinel still here waits for the parked leaf and is left by the T step's settle */ \
+        if (!SINGLE) vote |= ((cur + 0x40000000u) < 0x2FFFFFFFu) ? RC_VOTE_X : 0u;                                 \
     }
 
     // enter instance `index`: its world->local transform applied with the reference's exact arithmetic (:1961-1977)
@@ -251,23 +264,12 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, SINGLE ? RC_MIN_BLOCKS_SINGL
                 }
             }
         } else if (!SINGLE && nX > nN) {
-            // ---- X: enter an instance (TLAS leaf) or return to the TLAS (sentinel) -------------------------------------------
-            if (vote & RC_VOTE_X) {
-                if (cur == RC_SENTINEL) {
-                    cur_inst = -1;  // src/instanced-bvh.jl:1996-2006
-                    nodes = sc.tlas4;
-                    cur = RC_TOP();
-                    spa -= RC_ROW;
-                    if (cur != RC_INVALID) {  // more TLAS work: restore the world ray (skipped when the ray is finished)
-                        o = wo; d = wd;
-                        inv = mk3(rc_fast_inv(d.x), rc_fast_inv(d.y), rc_fast_inv(d.z));
-                    }
-                } else {
-                    RC_ENTER_INSTANCE((int)(cur & RC_LEAF_START_MASK))
-                    RC_PUSH_IF(true, RC_SENTINEL)
-                    if (COUNT) { lc.inst_entries++; if (RC_DEPTH() > lc.max_stack) lc.max_stack = RC_DEPTH(); }
-                    cur = 1;
-                }
+            // ---- X: enter an instance (TLAS leaf) --------------------------------------------------------------------------
+            if (vote & RC_VOTE_X) {  // (the return to the TLAS happens in RC_SETTLE_LEAVE)
+                RC_ENTER_INSTANCE((int)(cur & RC_LEAF_START_MASK))
+                RC_PUSH_IF(true, RC_SENTINEL)
+                if (COUNT) { lc.inst_entries++; if (RC_DEPTH() > lc.max_stack) lc.max_stack = RC_DEPTH(); }
+                cur = 1;
                 RC_SETTLE()
             }
         } else {
@@ -326,6 +328,7 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, SINGLE ? RC_MIN_BLOCKS_SINGL
 #undef RC_DEPTH
 #undef RC_ROW
 #undef RC_SETTLE
+#undef RC_SETTLE_LEAVE
 #undef RC_ENTER_INSTANCE
     if (COUNT) {
         atomicAdd(&counters->rays, traced);
