@@ -165,7 +165,18 @@ __device__ __forceinline__ const RcTri *flat_tri(const RcFlatBlas *flat, uint32_
 
 // Ray source / hit sink that turns the scheduler kernel into view_factors! (src/kernels.jl:80-104): "ray" g is ray g % rpt of the
 // flat primitive g / rpt; it is generated on the fly in the refill step, and its result is one atomicAdd into the matrix block.
+#ifndef RC_VF_FETCH_MIN
+#define RC_VF_FETCH_MIN 16
+#endif
+#ifndef RC_VF_T_W
+#define RC_VF_T_W 1u
+#endif
+#ifndef RC_VF_X_W
+#define RC_VF_X_W 1u
+#endif
 struct RcIoViewFactors {
+    // scheduler constants (rc_trace_fast.cuh): the refill generates the ray (RNG, point on the triangle, hemisphere direction), so it waits for more lanes
+    static constexpr uint32_t kFetchMinMulti = RC_VF_FETCH_MIN, kTWMulti = RC_VF_T_W, kXWMulti = RC_VF_X_W;
     RcScene sc;
     const RcFlatBlas *flat;
     uint32_t n_blas, rpt, row_base, n_rows, n_cols;  // owned rows: row_base + k * row_stride, k < n_rows (output row k)

@@ -11,7 +11,7 @@
 // to reach its first leaf never stalls 31 lanes that wait to test triangles, and vice versa (profiles/r1_v2: a plain
 // while-while loop ran the box code at 9.4/32 lanes, this scheduler at 18.5/32).  The vote word is recomputed only by
 // the lanes that just executed a step ("settle"), which also parks a freshly reached leaf so the lane can keep descending.
-// Refills are warp-cooperative (one atomic on the global work counter per refill) and deferred until RC_FETCH_MIN
+// Refills are warp-cooperative (one atomic on the global work counter per refill) and deferred until RC_FETCH_MIN_*
 // lanes are idle, so the refill / retire code also runs with many lanes.
 //
 // Arithmetic: two child planes are decoded per PRMT into a half2 of subnormals (0x00qq = q * 2^-24 exactly), widened with
@@ -46,8 +46,26 @@ __device__ __forceinline__ void rc_store_hit(rc_hit *hits, unsigned long long i,
     __stcs(p + 1, make_float4(h.bary_u, h.bary_v, __uint_as_float(h.instance_id), __uint_as_float(h.metadata)));
 }
 
-#ifndef RC_FETCH_MIN
-#define RC_FETCH_MIN 16    // refill when at least this many lanes of the warp are idle (or nothing else can run); 8..24 swept in r1
+// Scheduler constants per kernel variant (swept with tools/exp_variant.py, profiles/README.md).  A refill runs when at least
+// RC_FETCH_MIN lanes of the warp are idle (or nothing else can run); a T step runs when RC_T_W * nT >= nN, an X step when
+// RC_X_W * nX > nN.  One mesh under one instance (SINGLE): plain majority and a late refill are best (8..24 and weights 2..4 are
+// within +-1 % or worse).  With a real TLAS the rays are longer and spread over four step kinds: letting the short steps (instance
+// entry, triangle test, refill) run as soon as a third of the node-step lanes want them keeps those lanes from idling through
+// long runs of node steps (C3: 13.39 -> 10.28 ms).
+#ifndef RC_FETCH_MIN_SINGLE
+#define RC_FETCH_MIN_SINGLE 16
+#endif
+#ifndef RC_FETCH_MIN_MULTI
+#define RC_FETCH_MIN_MULTI 6
+#endif
+#ifndef RC_T_W_SINGLE
+#define RC_T_W_SINGLE 1u
+#endif
+#ifndef RC_T_W_MULTI
+#define RC_T_W_MULTI 3u
+#endif
+#ifndef RC_X_W
+#define RC_X_W 3u
 #endif
 #ifndef RC_MIN_BLOCKS
 #define RC_MIN_BLOCKS 8     // 64 registers -> 32 resident warps per SM (swept 6..10 in r1: 8 is best, 9+ spills)
@@ -95,6 +113,8 @@ __device__ __forceinline__ float2 rc_q2f_pair(uint32_t w, int j) {
 
 // Ray source / hit sink of the batched entry points: RTRay array in, RTHitResult array out.
 struct RcIoArrays {
+    // scheduler constants of the multi-instance variant for this ray source (see above): a cheap refill (one 32-B load) can run early
+    static constexpr uint32_t kFetchMinMulti = RC_FETCH_MIN_MULTI, kTWMulti = RC_T_W_MULTI, kXWMulti = RC_X_W;
     const rc_ray *rays;
     rc_hit *hits;
     __device__ __forceinline__ rc_ray load(unsigned long long i) const { return rc_load_ray(rays, i); }
@@ -128,6 +148,7 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, SINGLE ? RC_MIN_BLOCKS_SINGL
     // SINGLE is a compile-time variant (chosen by the launcher when n_instances == 1): the world-space ray copy, the sentinel and the
     // whole level-change step drop out of the kernel.
     constexpr bool single = SINGLE;
+    constexpr uint32_t FETCH_MIN = SINGLE ? RC_FETCH_MIN_SINGLE : IO::kFetchMinMulti, T_W = SINGLE ? RC_T_W_SINGLE : IO::kTWMulti, X_W = IO::kXWMulti;
 
     // Branch-free conditional push: the value is always stored one row above the top and the top pointer only advances when the
     // push is accepted, so a rejected value is simply overwritten by the next push (rows above the top are don't-care).  Row 0 is
@@ -193,7 +214,7 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, SINGLE ? RC_MIN_BLOCKS_SINGL
         if (votes == 0) break;  // every lane is dead
         const uint32_t nN = votes & 0xFFu, nT = (votes >> 8) & 0xFFu, nX = (votes >> 16) & 0xFFu, nF = votes >> 24;
 
-        if (nF > 0 && (nF >= RC_FETCH_MIN || (votes & 0x00FFFFFFu) == 0)) {
+        if (nF > 0 && (nF >= FETCH_MIN || (votes & 0x00FFFFFFu) == 0)) {
             // ---- F: retire + refill (warp-cooperative) -----------------------------------------------------------------
             const bool wantF = vote & RC_VOTE_F;
             if (wantF && have) {
@@ -242,7 +263,7 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, SINGLE ? RC_MIN_BLOCKS_SINGL
                     have = true;
                 }
             }
-        } else if (nT >= nN && nT >= nX) {
+        } else if (nT * T_W >= nN && nT >= nX) {
             // ---- T: one triangle of the parked leaf per lane -------------------------------------------------------------
             if (vote & RC_VOTE_T) {
                 const uint32_t start = leaf & RC_LEAF_START_MASK, count = ((leaf >> RC_LEAF_COUNT_SHIFT) & 7u) + 1u;
@@ -263,7 +284,7 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, SINGLE ? RC_MIN_BLOCKS_SINGL
                     RC_SETTLE()  // the vote can only change when the parked leaf is exhausted
                 }
             }
-        } else if (!SINGLE && nX > nN) {
+        } else if (!SINGLE && nX * X_W > nN) {
             // ---- X: enter an instance (TLAS leaf) --------------------------------------------------------------------------
             if (vote & RC_VOTE_X) {  // (the return to the TLAS happens in RC_SETTLE_LEAVE)
                 RC_ENTER_INSTANCE((int)(cur & RC_LEAF_START_MASK))

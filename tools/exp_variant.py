@@ -33,6 +33,26 @@ def dev_trace(tlas, d_r, n, any_hit=False, reps=7):
 def main():
     out = {"lib": os.environ.get("RAYCORE_CUDA_LIB", "default")}
     n = 1 << 24
+    if "--vf" in sys.argv:  # C4: view_factors of 5 bumpy spheres x 1000 rays per triangle (bench.py extras)
+        import ctypes as C
+
+        vt, base = rc.TLAS(), 0
+        for msh in W.viewfactor_scene(72):
+            keep = ~W.is_degenerate(msh)
+            meta = np.zeros(len(msh), np.uint32)
+            meta[keep] = base + 1 + np.arange(keep.sum())
+            base += int(keep.sum())
+            vt.push(msh, None, face_meta=meta)
+        vt.sync()
+        npr = vt.sizes()["blas_prims"]
+        d_vf = torch.empty(npr * npr, dtype=torch.int32, device="cuda")
+        sk, ms = C.c_uint64(), []
+        for _ in range(4):
+            assert vt._lib.rc_view_factors_strided(vt._ctx, 1000, 11, d_vf.data_ptr(), 0, 1, npr, L.RC_HITS_ON_DEVICE, C.byref(sk)) == 0
+            ms.append(float(vt._lib.rc_last_kernel_ms(vt._ctx)))
+        out.update(scene="C4 view_factors", vf_ms=min(ms[1:]), total_hits=int(d_vf.sum().item()))
+        print(json.dumps(out))
+        return
     if "--c2" in sys.argv:
         tl = rc.TLAS()
         tl.push(W.bumpy_sphere(709))
