@@ -84,11 +84,26 @@ __device__ __forceinline__ void rc_store_hit(rc_hit *hits, unsigned long long i,
 #define RC_VOTE_X 0x00010000u
 #define RC_VOTE_F 0x01000000u
 
-// safe_invdir's clamp (src/instanced-bvh.jl:1742-1748) with MUFU.RCP (<= 1 ulp); only the conservative box test uses it
-__device__ __forceinline__ float rc_fast_inv(float d) {
+// safe_invdir's clamp (src/instanced-bvh.jl:1742-1748) with MUFU.RCP (<= 1 ulp); only the conservative box test uses it.
+// rcp.approx.f32 without .ftz expands to ~8 instructions (operand rescaling for subnormal inputs / results); the clamp rules out
+// subnormal inputs, so the single-instruction .ftz form gives the same bits unless a component exceeds 2^126 (subnormal result),
+// which takes the full form behind one warp-rarely-taken branch.  (The three reciprocals of a level change were 14 % of the
+// instanced kernel's warp instructions at 4/32 lanes, profiles/r1_trace_c3_v20.)
+__device__ __forceinline__ f3 rc_fast_inv3(f3 d) {
     const float ooeps = 1.0e-5f;
-    float x = fabsf(d) > ooeps ? d : copysignf(ooeps, d), r;
-    asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    const float x = fabsf(d.x) > ooeps ? d.x : copysignf(ooeps, d.x);
+    const float y = fabsf(d.y) > ooeps ? d.y : copysignf(ooeps, d.y);
+    const float z = fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z);
+    f3 r;
+    if (fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z)) > 8.5070591730234616e37f) {  // 2^126: 1/x would be subnormal
+        asm("rcp.approx.f32 %0, %1;" : "=f"(r.x) : "f"(x));
+        asm("rcp.approx.f32 %0, %1;" : "=f"(r.y) : "f"(y));
+        asm("rcp.approx.f32 %0, %1;" : "=f"(r.z) : "f"(z));
+    } else {
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(x));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(y));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.z) : "f"(z));
+    }
     return r;
 }
 // bound on the relative error of the slab evaluation: reciprocal (1 ulp), two roundings of (origin - o) * inv, one rounding of
@@ -172,7 +187,7 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, SINGLE ? RC_MIN_BLOCKS_SINGL
         cur = RC_TOP();                                                                   \
         spa -= RC_ROW;                                                                    \
         o = wo; d = wd;                                                                   \
-        inv = mk3(rc_fast_inv(d.x), rc_fast_inv(d.y), rc_fast_inv(d.z));                  \
+        inv = rc_fast_inv3(d);                  \
     }
     // after a step: park a freshly reached BLAS leaf (so the lane can keep descending) and recompute the lane's vote
 #define RC_SETTLE()                                                                                                \
@@ -206,7 +221,7 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, SINGLE ? RC_MIN_BLOCKS_SINGL
         tris = reinterpret_cast<const RcTri *>(pp_.y);                                    \
         o = x_transform_point(m_, wo);                                                    \
         d = x_transform_direction(m_, wd);                                                \
-        inv = mk3(rc_fast_inv(d.x), rc_fast_inv(d.y), rc_fast_inv(d.z));                  \
+        inv = rc_fast_inv3(d);                  \
     }
 
     for (;;) {
@@ -253,7 +268,7 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, SINGLE ? RC_MIN_BLOCKS_SINGL
                         if (COUNT) lc.inst_entries++;
                     } else {
                         o = wo; d = wd;
-                        inv = mk3(rc_fast_inv(d.x), rc_fast_inv(d.y), rc_fast_inv(d.z));
+                        inv = rc_fast_inv3(d);
                         cur_inst = -1;
                         nodes = sc.tlas4;
                     }
