@@ -23,11 +23,18 @@
 // child is written to a dummy row); rays that would need more than RC_SSTACK entries are flagged and re-traced by
 // k_trace_fixup with the deep-stack generic body.
 #pragma once
+#ifdef RC_WARPSIM
+// tests/hostsim compiles this very kernel for the CPU — one fibre per lane, the warp intrinsics as lock-step exchanges — so the
+// scheduler, the stack handling and the level changes are parity-tested without a GPU.  Test infrastructure only: the shim comes
+// from tests/hostsim/warpsim.h, never from the library build.
+#include "warpsim.h"
+#else
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
 #include "rc_trace.h"
+#endif
 #include "rc_trace_core.cuh"
 
 __device__ __forceinline__ rc_ray rc_load_ray(const rc_ray *rays, unsigned long long i) {
@@ -95,6 +102,9 @@ __device__ __forceinline__ f3 rc_fast_inv3(f3 d) {
     const float y = fabsf(d.y) > ooeps ? d.y : copysignf(ooeps, d.y);
     const float z = fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z);
     f3 r;
+#ifdef RC_WARPSIM
+    r.x = 1.0f / x; r.y = 1.0f / y; r.z = 1.0f / z;  // host stand-in for MUFU.RCP (<= 1 ulp apart; only the conservative box test sees it)
+#else
     if (fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z)) > 8.5070591730234616e37f) {  // 2^126: 1/x would be subnormal
         asm("rcp.approx.f32 %0, %1;" : "=f"(r.x) : "f"(x));
         asm("rcp.approx.f32 %0, %1;" : "=f"(r.y) : "f"(y));
@@ -104,6 +114,7 @@ __device__ __forceinline__ f3 rc_fast_inv3(f3 d) {
         asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(y));
         asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.z) : "f"(z));
     }
+#endif
     return r;
 }
 // bound on the relative error of the slab evaluation: reciprocal (1 ulp), two roundings of (origin - o) * inv, one rounding of
@@ -113,9 +124,14 @@ __device__ __forceinline__ f3 rc_fast_inv3(f3 d) {
 // 32-byte read-only load (LDG.E.256.CONSTANT on sm_100a): a 64-B wide node is two of these instead of four LDG.128,
 // halving the L1 wavefronts per node step (LSU wavefronts were 70 % of peak in profiles/r1_v6)
 __device__ __forceinline__ void rc_ldg256(const void *p, float4 &a, float4 &b) {
+#ifdef RC_WARPSIM
+    a = static_cast<const float4 *>(p)[0];
+    b = static_cast<const float4 *>(p)[1];
+#else
     asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
                  : "l"(p));
+#endif
 }
 
 // bytes (2j, 2j+1) of w -> two floats q * 2^-24 (exact): each byte becomes the mantissa of a subnormal fp16 (0x00qq), which

@@ -60,6 +60,19 @@ class HostsimEngine:
         return self.scene.root()
 
 
+class WarpsimEngine(HostsimEngine):
+    """The shipped traversal kernel (k_trace_wide, rc_trace_fast.cuh) compiled for the CPU: 32 fibres per warp, lock step at the warp
+    intrinsics (tests/hostsim/warpsim.h).  Same scene construction as HostsimEngine."""
+
+    def __init__(self, pushes, n_warps=3):
+        super().__init__(pushes, wide=True)
+        self.name = "warpsim"
+        self.n_warps = n_warps
+
+    def trace(self, rays, any_hit=False, **kw):
+        return self.scene.trace_warpsim(rays, any_hit=any_hit, n_warps=self.n_warps)
+
+
 class GpuEngine:
     def __init__(self, pushes, reference_order=False):
         import raycore_b200 as rc

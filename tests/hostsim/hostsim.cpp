@@ -14,6 +14,9 @@
 #include "../../raycore.jl_b200/csrc/rc_build_core.cuh"
 #include "../../raycore.jl_b200/csrc/rc_trace_core.cuh"
 #include "../../raycore.jl_b200/csrc/rc_wave_core.cuh"
+// the shipped traversal kernel itself, compiled for the CPU (one fibre per lane; see warpsim.h)
+#define RC_WARPSIM 1
+#include "../../raycore.jl_b200/csrc/rc_trace_fast.cuh"
 
 namespace {
 
@@ -368,4 +371,101 @@ void hs_shadow_rays(void *s, const rc_ray *rays, const rc_hit *hits, uint64_t n,
     }
 }
 
+}  // extern "C"
+
+// ---- k_trace_wide (rc_trace_fast.cuh) on the CPU: n_warps persistent warps of 32 fibres share one work counter, as the CTAs of the
+// real launch do.  Rays whose short stack overflowed are re-traced by the deep-stack generic body, as k_trace_fixup does.
+namespace warpsim {
+Warp *g_warp = nullptr;
+int g_lane = 0;
+Tid g_tid = {0};
+ucontext_t g_sched;
+uint64_t g_exchanges = 0;
+struct Launch {
+    RcScene sc;
+    RcIoArrays io;
+    unsigned long long n;
+    unsigned long long *work;
+    RcCounters *counters;
+    uint32_t *overflow;
+    int any, count;
+};
+static Launch g_launch;
+static void lane_main() {
+    const Launch &L = g_launch;
+    const bool single = L.sc.n_instances == 1u;  // the launcher's choice of variant (rc_trace.cu)
+#define WS_RUN(A, C)                                                                                      \
+    {                                                                                                     \
+        if (single) k_trace_wide<A, C, RcIoArrays, true>(L.sc, L.io, L.n, L.work, L.counters, L.overflow);  \
+        else k_trace_wide<A, C, RcIoArrays, false>(L.sc, L.io, L.n, L.work, L.counters, L.overflow);        \
+    }
+    if (L.any) { if (L.count) WS_RUN(true, true) else WS_RUN(true, false) }
+    else { if (L.count) WS_RUN(false, true) else WS_RUN(false, false) }
+#undef WS_RUN
+    g_warp->lane[g_lane].done = true;
+    swapcontext(&g_warp->lane[g_lane].ctx, &g_sched);
+}
+// returns 0, or 1 when the lanes of a warp did not leave the kernel together (a divergence bug around a warp intrinsic)
+static int run(std::vector<Warp> &warps) {
+    const size_t stack_bytes = 512 * 1024;
+    for (size_t w = 0; w < warps.size(); w++) {
+        warps[w].first_tid = 32u * (unsigned)(w % (RC_TRACE_THREADS / 32));
+        for (int l = 0; l < 32; l++) {
+            Lane &ln = warps[w].lane[l];
+            ln.stack.resize(stack_bytes);
+            getcontext(&ln.ctx);
+            ln.ctx.uc_stack.ss_sp = ln.stack.data();
+            ln.ctx.uc_stack.ss_size = stack_bytes;
+            ln.ctx.uc_link = &g_sched;
+            makecontext(&ln.ctx, lane_main, 0);
+        }
+    }
+    for (;;) {
+        size_t live = 0;
+        for (auto &w : warps) {
+            int done = 0;
+            for (int l = 0; l < 32; l++) done += w.lane[l].done ? 1 : 0;
+            if (done == 32) continue;
+            if (done != 0) return 1;
+            live++;
+            for (int l = 0; l < 32; l++) {
+                g_warp = &w;
+                g_lane = l;
+                g_tid.x = w.first_tid + (unsigned)l;
+                swapcontext(&g_sched, &w.lane[l].ctx);
+            }
+        }
+        if (!live) return 0;
+    }
+}
+}  // namespace warpsim
+
+extern "C" {
+// out_info (nullable, 4): rays flagged by the short stack, rays no stack could hold, warp exchanges executed, lock-step violation
+uint32_t hs_trace_warpsim(void *s, const rc_ray *rays, rc_hit *hits, uint64_t n, int any, uint32_t n_warps, uint64_t *counters /* nullable, 6 */,
+                          uint64_t *out_info) {
+    HsScene *S = (HsScene *)s;
+    if (out_info) out_info[0] = out_info[1] = out_info[2] = out_info[3] = 0;
+    if (S->scene.n_instances == 0) {  // rc_launch_trace: an empty TLAS never reaches the kernel
+        for (uint64_t i = 0; i < n; i++) rc_write_miss(hits[i]);
+        return 0;
+    }
+    unsigned long long work = 0;
+    RcCounters cnt;
+    memset(&cnt, 0, sizeof cnt);
+    uint32_t overflow[4] = {0, 0, 0, 0};
+    warpsim::g_launch = warpsim::Launch{S->scene, RcIoArrays{rays, hits}, n, &work, &cnt, overflow, any, counters != nullptr};
+    warpsim::g_exchanges = 0;
+    std::vector<warpsim::Warp> warps(n_warps ? n_warps : 1);
+    const int bad = warpsim::run(warps);
+    uint32_t hard = 0;
+    for (uint64_t i = 0; i < n && !bad; i++) {  // k_trace_fixup
+        if (hits[i].hit != RC_OVERFLOW_MARK) continue;
+        bool ok = any ? rc_trace_wide<true, false>(S->scene, rays[i], hits[i], nullptr) : rc_trace_wide<false, false>(S->scene, rays[i], hits[i], nullptr);
+        if (!ok) hard++;
+    }
+    if (counters) { counters[0] = cnt.rays; counters[1] = cnt.nodes; counters[2] = cnt.box_tests; counters[3] = cnt.tri_tests; counters[4] = cnt.inst_entries; counters[5] = cnt.max_stack; }
+    if (out_info) { out_info[0] = overflow[0]; out_info[1] = hard; out_info[2] = warpsim::g_exchanges; out_info[3] = (uint64_t)bad; }
+    return bad ? 0xFFFFFFFFu : hard;
+}
 }  // extern "C"

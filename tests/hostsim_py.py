@@ -40,6 +40,8 @@ def lib():
         L.hs_shadow_rays.argtypes = [vp, vp, vp, C.c_uint64, vp, vp, C.c_uint32, C.c_float, vp]
         L.hs_check_wide.restype = C.c_uint32
         L.hs_check_wide.argtypes = [vp]
+        L.hs_trace_warpsim.restype = C.c_uint32
+        L.hs_trace_warpsim.argtypes = [vp, vp, vp, C.c_uint64, C.c_int, C.c_uint32, vp, vp]
         L.hs_validate_blas.restype = C.c_uint32
         L.hs_validate_blas.argtypes = [vp, C.c_int, C.c_uint32]
         _lib = L
@@ -128,6 +130,21 @@ class HsScene:
         assert ov == 0, f"{ov} traversal stack overflows"
         if counters:
             return hits, dict(zip(["nodes", "box_tests", "tri_tests", "inst_entries", "max_stack"], [int(x) for x in cnt]))
+        return hits
+
+    def trace_warpsim(self, rays, any_hit=False, n_warps=3, counters=False):
+        """The shipped kernel k_trace_wide (rc_trace_fast.cuh) on the CPU: n_warps warps of 32 fibres, lock step at the warp intrinsics.
+        Returns hits (and, with counters, the kernel's work counters plus the run's info)."""
+        rays = np.ascontiguousarray(rays, RAY_DTYPE)
+        hits = np.full(len(rays), 0xAB, np.uint8).repeat(HIT_DTYPE.itemsize).view(HIT_DTYPE).copy()  # every record must be written
+        cnt, info = (C.c_uint64 * 6)(), (C.c_uint64 * 4)()
+        rc = lib().hs_trace_warpsim(self.p, rays.ctypes.data, hits.ctypes.data, len(rays), int(any_hit), n_warps, cnt if counters else None, info)
+        assert info[3] == 0, "lanes of a warp left the kernel at different times (divergence around a warp intrinsic)"
+        assert rc == 0, f"{rc} rays overflowed the deep stack"
+        if counters:
+            d = dict(zip(["rays", "nodes", "box_tests", "tri_tests", "inst_entries", "max_stack"], [int(x) for x in cnt]))
+            d.update(short_stack_overflows=int(info[0]), exchanges=int(info[2]))
+            return hits, d
         return hits
 
 
