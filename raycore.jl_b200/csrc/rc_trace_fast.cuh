@@ -37,6 +37,12 @@
 #endif
 #include "rc_trace_core.cuh"
 
+// RC_SIM_STEP(kind, active): step statistics of the CPU warp simulator (iterations and active lanes per step kind); nothing on the GPU
+#ifndef RC_SIM_STEP
+#define RC_SIM_STEP(kind, active)
+#define RC_SIM_ITER()
+#endif
+
 __device__ __forceinline__ rc_ray rc_load_ray(const rc_ray *rays, unsigned long long i) {
     const float4 *p = reinterpret_cast<const float4 *>(rays + i);
     float4 a = __ldcs(p), b = __ldcs(p + 1);  // streamed once: evict-first keeps the BVH resident in L2
@@ -242,12 +248,14 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, SINGLE ? RC_MIN_BLOCKS_SINGL
 
     for (;;) {
         const uint32_t votes = __reduce_add_sync(FULL, vote);
+        RC_SIM_ITER()
         if (votes == 0) break;  // every lane is dead
         const uint32_t nN = votes & 0xFFu, nT = (votes >> 8) & 0xFFu, nX = (votes >> 16) & 0xFFu, nF = votes >> 24;
 
         if (nF > 0 && (nF >= FETCH_MIN || (votes & 0x00FFFFFFu) == 0)) {
             // ---- F: retire + refill (warp-cooperative) -----------------------------------------------------------------
             const bool wantF = vote & RC_VOTE_F;
+            RC_SIM_STEP(3, wantF)
             if (wantF && have) {
                 rc_hit h;
                 if (best_inst >= 0) {
@@ -296,6 +304,7 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, SINGLE ? RC_MIN_BLOCKS_SINGL
             }
         } else if (nT * T_W >= nN && nT >= nX) {
             // ---- T: one triangle of the parked leaf per lane -------------------------------------------------------------
+            RC_SIM_STEP(1, vote & RC_VOTE_T)
             if (vote & RC_VOTE_T) {
                 const uint32_t start = leaf & RC_LEAF_START_MASK, count = ((leaf >> RC_LEAF_COUNT_SHIFT) & 7u) + 1u;
                 const float4 *tp = reinterpret_cast<const float4 *>(tris + start + leaf_k);
@@ -317,6 +326,7 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, SINGLE ? RC_MIN_BLOCKS_SINGL
             }
         } else if (!SINGLE && nX * X_W > nN) {
             // ---- X: enter an instance (TLAS leaf) --------------------------------------------------------------------------
+            RC_SIM_STEP(2, vote & RC_VOTE_X)
             if (vote & RC_VOTE_X) {  // (the return to the TLAS happens in RC_SETTLE_LEAVE)
                 RC_ENTER_INSTANCE((int)(cur & RC_LEAF_START_MASK))
                 RC_PUSH_IF(true, RC_SENTINEL)
@@ -326,6 +336,7 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, SINGLE ? RC_MIN_BLOCKS_SINGL
             }
         } else {
             // ---- N: test the 4 quantised child boxes, descend into the nearest, push the other hit children -----------------
+            RC_SIM_STEP(0, vote & RC_VOTE_N)
             if (vote & RC_VOTE_N) {
                 const char *np = reinterpret_cast<const char *>(nodes + cur);
                 float4 n0, n1, n2, n3;

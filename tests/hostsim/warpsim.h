@@ -69,6 +69,7 @@ struct Warp {
     Lane lane[32];
     uint64_t slot[2][32];
     unsigned first_tid = 0;
+    uint64_t iter = 0, last_iter[4] = {~0ull, ~0ull, ~0ull, ~0ull};  // step statistics: scheduler iteration number, last iteration each step kind ran in
 };
 struct Tid { unsigned x; };
 extern Warp *g_warp;     // the warp and lane the scheduler is running right now
@@ -76,6 +77,7 @@ extern int g_lane;
 extern Tid g_tid;
 extern ucontext_t g_sched;
 extern uint64_t g_exchanges;
+extern uint64_t g_step_iters[4], g_step_lanes[4];  // per step kind (N, T, X, F): warp iterations, active lanes summed
 // every lane contributes v; returns the 32 operands of this exchange
 static inline const uint64_t *exchange(uint64_t v) {
     Warp *w = g_warp;
@@ -88,6 +90,16 @@ static inline const uint64_t *exchange(uint64_t v) {
 }
 }  // namespace warpsim
 #define threadIdx (warpsim::g_tid)
+// step statistics: a step kind counts one iteration when at least one lane of the warp executes its body
+#define RC_SIM_ITER() { if (warpsim::g_lane == 0) warpsim::g_warp->iter++; }
+#define RC_SIM_STEP(kind, active)                                                                     \
+    {                                                                                                 \
+        if (active) {                                                                                 \
+            warpsim::Warp *w_ = warpsim::g_warp;                                                      \
+            if (w_->last_iter[kind] != w_->iter) { w_->last_iter[kind] = w_->iter; warpsim::g_step_iters[kind]++; } \
+            warpsim::g_step_lanes[kind]++;                                                            \
+        }                                                                                             \
+    }
 
 static inline uint32_t __reduce_add_sync(uint32_t, uint32_t v) {
     const uint64_t *s = warpsim::exchange(v);

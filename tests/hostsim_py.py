@@ -15,7 +15,7 @@ def lib():
     global _lib
     if _lib is None:
         subprocess.check_call(["make", "-C", _DIR, "libhostsim.so"], stdout=subprocess.DEVNULL)
-        L = C.CDLL(os.path.join(_DIR, "libhostsim.so"))
+        L = C.CDLL(os.environ.get("RC_HOSTSIM_LIB") or os.path.join(_DIR, "libhostsim.so"))  # the override loads an experiment build (other -D flags)
         vp = C.c_void_p
         L.hs_blas_build.restype = vp
         L.hs_blas_build.argtypes = [vp, C.c_uint32, vp]
@@ -137,13 +137,15 @@ class HsScene:
         Returns hits (and, with counters, the kernel's work counters plus the run's info)."""
         rays = np.ascontiguousarray(rays, RAY_DTYPE)
         hits = np.full(len(rays), 0xAB, np.uint8).repeat(HIT_DTYPE.itemsize).view(HIT_DTYPE).copy()  # every record must be written
-        cnt, info = (C.c_uint64 * 6)(), (C.c_uint64 * 4)()
+        cnt, info = (C.c_uint64 * 6)(), (C.c_uint64 * 12)()
         rc = lib().hs_trace_warpsim(self.p, rays.ctypes.data, hits.ctypes.data, len(rays), int(any_hit), n_warps, cnt if counters else None, info)
         assert info[3] == 0, "lanes of a warp left the kernel at different times (divergence around a warp intrinsic)"
         assert rc == 0, f"{rc} rays overflowed the deep stack"
         if counters:
             d = dict(zip(["rays", "nodes", "box_tests", "tri_tests", "inst_entries", "max_stack"], [int(x) for x in cnt]))
             d.update(short_stack_overflows=int(info[0]), exchanges=int(info[2]))
+            d["step_iterations"] = dict(zip("NTXF", [int(x) for x in info[4:8]]))  # warp iterations per step kind
+            d["step_lanes"] = dict(zip("NTXF", [int(x) for x in info[8:12]]))  # active lanes summed over those iterations
             return hits, d
         return hits
 
