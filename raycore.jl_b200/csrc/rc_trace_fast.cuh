@@ -41,6 +41,7 @@
 #ifndef RC_SIM_STEP
 #define RC_SIM_STEP(kind, active)
 #define RC_SIM_ITER()
+#define RC_SIM_IDLE(vote_word, cur_ref, leaf_ref)
 #endif
 
 __device__ __forceinline__ rc_ray rc_load_ray(const rc_ray *rays, unsigned long long i) {
@@ -337,6 +338,7 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, SINGLE ? RC_MIN_BLOCKS_SINGL
         } else {
             // ---- N: test the 4 quantised child boxes, descend into the nearest, push the other hit children -----------------
             RC_SIM_STEP(0, vote & RC_VOTE_N)
+            RC_SIM_IDLE(vote, cur, leaf)
             if (vote & RC_VOTE_N) {
                 const char *np = reinterpret_cast<const char *>(nodes + cur);
                 float4 n0, n1, n2, n3;

@@ -382,6 +382,7 @@ Tid g_tid = {0};
 ucontext_t g_sched;
 uint64_t g_exchanges = 0;
 uint64_t g_step_iters[4] = {0, 0, 0, 0}, g_step_lanes[4] = {0, 0, 0, 0};
+uint64_t g_idle[6] = {0, 0, 0, 0, 0, 0};
 struct Launch {
     RcScene sc;
     RcIoArrays io;
@@ -442,12 +443,13 @@ static int run(std::vector<Warp> &warps) {
 }  // namespace warpsim
 
 extern "C" {
-// out_info (nullable, 12): rays flagged by the short stack, rays no stack could hold, warp exchanges executed, lock-step violation,
-// then per step kind (N, T, X, F) the warp iterations [4..7] and the active lanes summed over them [8..11]
+// out_info (nullable, 18): rays flagged by the short stack, rays no stack could hold, warp exchanges executed, lock-step violation,
+// then per step kind (N, T, X, F) the warp iterations [4..7] and the active lanes summed over them [8..11], then the lanes that sat
+// out node steps by reason [12..17] (see g_idle)
 uint32_t hs_trace_warpsim(void *s, const rc_ray *rays, rc_hit *hits, uint64_t n, int any, uint32_t n_warps, uint64_t *counters /* nullable, 6 */,
                           uint64_t *out_info) {
     HsScene *S = (HsScene *)s;
-    if (out_info) memset(out_info, 0, 12 * sizeof(uint64_t));
+    if (out_info) memset(out_info, 0, 18 * sizeof(uint64_t));
     if (S->scene.n_instances == 0) {  // rc_launch_trace: an empty TLAS never reaches the kernel
         for (uint64_t i = 0; i < n; i++) rc_write_miss(hits[i]);
         return 0;
@@ -459,6 +461,7 @@ uint32_t hs_trace_warpsim(void *s, const rc_ray *rays, rc_hit *hits, uint64_t n,
     warpsim::g_launch = warpsim::Launch{S->scene, RcIoArrays{rays, hits}, n, &work, &cnt, overflow, any, counters != nullptr};
     warpsim::g_exchanges = 0;
     for (int k = 0; k < 4; k++) warpsim::g_step_iters[k] = warpsim::g_step_lanes[k] = 0;
+    for (int k = 0; k < 6; k++) warpsim::g_idle[k] = 0;
     std::vector<warpsim::Warp> warps(n_warps ? n_warps : 1);
     const int bad = warpsim::run(warps);
     uint32_t hard = 0;
@@ -471,6 +474,7 @@ uint32_t hs_trace_warpsim(void *s, const rc_ray *rays, rc_hit *hits, uint64_t n,
     if (out_info) {
         out_info[0] = overflow[0]; out_info[1] = hard; out_info[2] = warpsim::g_exchanges; out_info[3] = (uint64_t)bad;
         for (int k = 0; k < 4; k++) { out_info[4 + k] = warpsim::g_step_iters[k]; out_info[8 + k] = warpsim::g_step_lanes[k]; }
+        for (int k = 0; k < 6; k++) out_info[12 + k] = warpsim::g_idle[k];
     }
     return bad ? 0xFFFFFFFFu : hard;
 }

@@ -77,6 +77,7 @@ extern int g_lane;
 extern Tid g_tid;
 extern ucontext_t g_sched;
 extern uint64_t g_exchanges;
+extern uint64_t g_idle[6];  // lanes sitting out a node step, by what they wait for: T with a second leaf reached, T at the level sentinel, T with an empty stack, X, F, dead
 extern uint64_t g_step_iters[4], g_step_lanes[4];  // per step kind (N, T, X, F): warp iterations, active lanes summed
 // every lane contributes v; returns the 32 operands of this exchange
 static inline const uint64_t *exchange(uint64_t v) {
@@ -99,6 +100,17 @@ static inline const uint64_t *exchange(uint64_t v) {
             if (w_->last_iter[kind] != w_->iter) { w_->last_iter[kind] = w_->iter; warpsim::g_step_iters[kind]++; } \
             warpsim::g_step_lanes[kind]++;                                                            \
         }                                                                                             \
+    }
+
+#define RC_SIM_IDLE(vote_word, cur_ref, leaf_ref)                                                          \
+    {                                                                                                       \
+        if (!((vote_word) & RC_VOTE_N)) {                                                                   \
+            int k_ = 5;                                                                                     \
+            if ((vote_word) & RC_VOTE_T) k_ = ((cur_ref) == RC_SENTINEL) ? 1 : ((cur_ref) == RC_INVALID ? 2 : 0); \
+            else if ((vote_word) & RC_VOTE_X) k_ = 3;                                                       \
+            else if ((vote_word) & RC_VOTE_F) k_ = 4;                                                       \
+            warpsim::g_idle[k_]++;                                                                          \
+        }                                                                                                   \
     }
 
 static inline uint32_t __reduce_add_sync(uint32_t, uint32_t v) {

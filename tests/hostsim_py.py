@@ -137,7 +137,7 @@ class HsScene:
         Returns hits (and, with counters, the kernel's work counters plus the run's info)."""
         rays = np.ascontiguousarray(rays, RAY_DTYPE)
         hits = np.full(len(rays), 0xAB, np.uint8).repeat(HIT_DTYPE.itemsize).view(HIT_DTYPE).copy()  # every record must be written
-        cnt, info = (C.c_uint64 * 6)(), (C.c_uint64 * 12)()
+        cnt, info = (C.c_uint64 * 6)(), (C.c_uint64 * 18)()
         rc = lib().hs_trace_warpsim(self.p, rays.ctypes.data, hits.ctypes.data, len(rays), int(any_hit), n_warps, cnt if counters else None, info)
         assert info[3] == 0, "lanes of a warp left the kernel at different times (divergence around a warp intrinsic)"
         assert rc == 0, f"{rc} rays overflowed the deep stack"
@@ -146,6 +146,7 @@ class HsScene:
             d.update(short_stack_overflows=int(info[0]), exchanges=int(info[2]))
             d["step_iterations"] = dict(zip("NTXF", [int(x) for x in info[4:8]]))  # warp iterations per step kind
             d["step_lanes"] = dict(zip("NTXF", [int(x) for x in info[8:12]]))  # active lanes summed over those iterations
+            d["idle_in_node_steps"] = dict(zip(["T_second_leaf", "T_at_sentinel", "T_stack_empty", "X", "F", "dead"], [int(x) for x in info[12:18]]))
             return hits, d
         return hits
 

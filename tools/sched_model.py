@@ -32,6 +32,7 @@ def main():
         "per_ray": {k: c[k] / n_rays for k in ("nodes", "tri_tests", "inst_entries")},
         "iterations_per_32_rays": {k: 32.0 * it[k] / n_rays for k in "NTXF"},
         "lanes_per_iteration": {k: ln[k] / max(1, it[k]) for k in "NTXF"},
+        "idle_lanes_per_node_step": {k: v / max(1, it["N"]) for k, v in c["idle_in_node_steps"].items()},
         "model_warp_instructions_per_ray": sum(it[k] * (BODY[k] + OVERHEAD) for k in "NTXF") / n_rays,
     }
     print(json.dumps(out))
