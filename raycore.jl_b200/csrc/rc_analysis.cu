@@ -177,6 +177,7 @@ __device__ __forceinline__ const RcTri *flat_tri(const RcFlatBlas *flat, uint32_
 struct RcIoViewFactors {
     // scheduler constants (rc_trace_fast.cuh): the refill generates the ray (RNG, point on the triangle, hemisphere direction), so it waits for more lanes
     static constexpr uint32_t kFetchMinMulti = RC_VF_FETCH_MIN, kTWMulti = RC_VF_T_W, kXWMulti = RC_VF_X_W;
+    static constexpr uint32_t kFetchMinSingle = RC_VF_FETCH_MIN, kTWSingle = RC_VF_T_W;
     RcScene sc;
     const RcFlatBlas *flat;
     uint32_t n_blas, rpt, row_base, n_rows, n_cols;  // owned rows: row_base + k * row_stride, k < n_rows (output row k)

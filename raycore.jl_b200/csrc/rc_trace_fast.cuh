@@ -60,20 +60,21 @@ __device__ __forceinline__ void rc_store_hit(rc_hit *hits, unsigned long long i,
     __stcs(p + 1, make_float4(h.bary_u, h.bary_v, __uint_as_float(h.instance_id), __uint_as_float(h.metadata)));
 }
 
-// Scheduler constants per kernel variant (swept with tools/exp_variant.py, profiles/README.md).  A refill runs when at least
-// RC_FETCH_MIN lanes of the warp are idle (or nothing else can run); a T step runs when RC_T_W * nT >= nN, an X step when
-// RC_X_W * nX > nN.  One mesh under one instance (SINGLE): plain majority and a late refill are best (8..24 and weights 2..4 are
-// within +-1 % or worse).  With a real TLAS the rays are longer and spread over four step kinds: letting the short steps (instance
-// entry, triangle test, refill) run as soon as a third of the node-step lanes want them keeps those lanes from idling through
-// long runs of node steps (C3: 13.39 -> 10.28 ms).
+// Scheduler constants per kernel variant (swept with tools/exp_variant.py on the B200 and screened with tools/sched_model.py in the
+// CPU warp simulator, profiles/README.md).  A refill runs when at least RC_FETCH_MIN lanes of the warp are idle (or nothing else can
+// run); a T step runs when RC_T_W * nT >= nN, an X step when RC_X_W * nX > nN.  Letting the short steps (triangle test, instance entry,
+// refill) run before they have a majority keeps their lanes from idling through long runs of node steps; the weight and the refill
+// threshold only pay off together (each alone is within +-1 % on C2).  One mesh under one instance (SINGLE): weight 2, refill at 8
+// (C2 interior rays 2.54 -> 2.36 ms per 2^23; weight 3 / refill 6: 2.39).  With a real TLAS the rays are longer and spread over four
+// step kinds: weight 3, refill at 6 (C3: 13.39 -> 10.28 ms).
 #ifndef RC_FETCH_MIN_SINGLE
-#define RC_FETCH_MIN_SINGLE 16
+#define RC_FETCH_MIN_SINGLE 8
 #endif
 #ifndef RC_FETCH_MIN_MULTI
 #define RC_FETCH_MIN_MULTI 6
 #endif
 #ifndef RC_T_W_SINGLE
-#define RC_T_W_SINGLE 1u
+#define RC_T_W_SINGLE 2u
 #endif
 #ifndef RC_T_W_MULTI
 #define RC_T_W_MULTI 3u
@@ -153,6 +154,7 @@ __device__ __forceinline__ float2 rc_q2f_pair(uint32_t w, int j) {
 struct RcIoArrays {
     // scheduler constants of the multi-instance variant for this ray source (see above): a cheap refill (one 32-B load) can run early
     static constexpr uint32_t kFetchMinMulti = RC_FETCH_MIN_MULTI, kTWMulti = RC_T_W_MULTI, kXWMulti = RC_X_W;
+    static constexpr uint32_t kFetchMinSingle = RC_FETCH_MIN_SINGLE, kTWSingle = RC_T_W_SINGLE;
     const rc_ray *rays;
     rc_hit *hits;
     __device__ __forceinline__ rc_ray load(unsigned long long i) const { return rc_load_ray(rays, i); }
@@ -186,7 +188,7 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, SINGLE ? RC_MIN_BLOCKS_SINGL
     // SINGLE is a compile-time variant (chosen by the launcher when n_instances == 1): the world-space ray copy, the sentinel and the
     // whole level-change step drop out of the kernel.
     constexpr bool single = SINGLE;
-    constexpr uint32_t FETCH_MIN = SINGLE ? RC_FETCH_MIN_SINGLE : IO::kFetchMinMulti, T_W = SINGLE ? RC_T_W_SINGLE : IO::kTWMulti, X_W = IO::kXWMulti;
+    constexpr uint32_t FETCH_MIN = SINGLE ? IO::kFetchMinSingle : IO::kFetchMinMulti, T_W = SINGLE ? IO::kTWSingle : IO::kTWMulti, X_W = IO::kXWMulti;
 
     // Branch-free conditional push: the value is always stored one row above the top and the top pointer only advances when the
     // push is accepted, so a rejected value is simply overwritten by the next push (rows above the top are don't-care).  Row 0 is

@@ -113,6 +113,7 @@ struct RcShadowFusedSource {
 template <class SRC>
 struct RcIoShadow {
     static constexpr uint32_t kFetchMinMulti = RC_FETCH_MIN_MULTI, kTWMulti = RC_T_W_MULTI, kXWMulti = RC_X_W;  // scheduler constants, rc_trace_fast.cuh
+    static constexpr uint32_t kFetchMinSingle = RC_FETCH_MIN_SINGLE, kTWSingle = RC_T_W_SINGLE;
     SRC source;
     uint8_t *visible;
     __device__ __forceinline__ rc_ray load(unsigned long long g) const {

@@ -32,7 +32,7 @@ def dev_trace(tlas, d_r, n, any_hit=False, reps=7):
 
 def main():
     out = {"lib": os.environ.get("RAYCORE_CUDA_LIB", "default")}
-    n = 1 << 24
+    n = 1 << (int(sys.argv[sys.argv.index('--log2rays') + 1]) if '--log2rays' in sys.argv else 24)
     if "--vf" in sys.argv:  # C4: view_factors of 5 bumpy spheres x 1000 rays per triangle (bench.py extras)
         import ctypes as C
 
