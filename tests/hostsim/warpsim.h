@@ -60,6 +60,7 @@ template <class T> static inline T atomicMax(T *p, T v) { T o = *p; if (v > o) *
 
 namespace warpsim {
 struct Lane {
+    Lane() { memset(&ctx, 0, sizeof ctx); }
     ucontext_t ctx;
     std::vector<char> stack;
     bool done = false;
