@@ -415,7 +415,10 @@ static int run(std::vector<Warp> &warps) {
         for (int l = 0; l < 32; l++) {
             Lane &ln = warps[w].lane[l];
             ln.stack.resize(stack_bytes);
+#pragma GCC diagnostic push
+#pragma GCC diagnostic ignored "-Wmaybe-uninitialized"  // getcontext *writes* the context; gcc 13 flags the argument as read
             getcontext(&ln.ctx);
+#pragma GCC diagnostic pop
             ln.ctx.uc_stack.ss_sp = ln.stack.data();
             ln.ctx.uc_stack.ss_size = stack_bytes;
             ln.ctx.uc_link = &g_sched;
