@@ -9,8 +9,6 @@ import parity
 from oracle import oracle as orc
 from raycore_b200 import workloads as W
 
-pytestmark = pytest.mark.gpu
-
 
 def _random_mesh(rs):
     kind = rs.randint(5)
@@ -30,8 +28,8 @@ def _random_mesh(rs):
     return np.ascontiguousarray(m, np.float32)
 
 
-@pytest.mark.parametrize("seed", range(12))
-def test_random_scene_parity(seed):
+def random_scene(seed, n=20000):
+    """(pushes, rays) of fuzz case `seed` (shared with the CPU run of the shipped kernel, tests/test_warpsim_parity.py)."""
     rs = np.random.RandomState(1000 + seed)
     n_inst_total = [1, 1, 2, 3, 5, 8, 13, 21, 40, 4, 1, 17][seed]
     n_blas = min(n_inst_total, int(rs.randint(1, 4)))
@@ -42,12 +40,19 @@ def test_random_scene_parity(seed):
         xf = W.random_trs(int(counts[b]), seed=seed * 10 + b, extent=3.0, smin=0.3, smax=2.0)
         ids = rs.randint(0, 1000, int(counts[b])).astype(np.uint32) if rs.rand() < 0.5 else None
         pushes.append((_random_mesh(rs), None, xf, ids))
-    o, g, gr = engines.OracleEngine(pushes), engines.GpuEngine(pushes), engines.GpuEngine(pushes, reference_order=True)
-    n = 20000
     rays = W.box_rays(n, seed=seed, half=5.0)
     win = rs.rand(n) < 0.3
     rays["t_min"][win] = rs.uniform(0, 3, win.sum()).astype(np.float32)
     rays["t_max"][win] = rays["t_min"][win] + rs.uniform(0, 6, win.sum()).astype(np.float32)
+    return pushes, rays
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(12))
+def test_random_scene_parity(seed):
+    pushes, rays = random_scene(seed)
+    n = len(rays)
+    o, g, gr = engines.OracleEngine(pushes), engines.GpuEngine(pushes), engines.GpuEngine(pushes, reference_order=True)
     a, r, b = g.trace(rays), gr.trace(rays), o.trace(rays)
     assert r.tobytes() == b.tobytes(), "reference-order mode differs from the oracle"
     cls = parity.classify(a, b, parity.make_graze_verifier(orc, rays, a, o.instances, o.tris))

@@ -124,3 +124,16 @@ def test_empty_tlas_misses():
     w = engines.WarpsimEngine([])
     h = w.trace(W.box_rays(10, 1))
     assert not h["hit"].any() and not h["t"].any()
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_scenes(seed):
+    """The fuzz cases of tests/test_gpu_fuzz.py (1..40 instances, mixed BLASes, degenerate faces, t windows) through the shipped kernel on the CPU."""
+    from test_gpu_fuzz import random_scene
+
+    pushes, rays = random_scene(seed, n=6000)
+    o, w = engines.OracleEngine(pushes), engines.WarpsimEngine(pushes, n_warps=2)
+    a, b, _ = _parity(w, o, rays, f"warpsim fuzz {seed}", max_tie_frac=0.02)
+    aa, ba = w.trace(rays, any_hit=True), o.trace(rays, any_hit=True)
+    d = np.nonzero(aa["hit"] != ba["hit"])[0]
+    assert len(d) <= 2 and (aa["hit"][d] == 1).all() and b["hit"].sum() > 0
