@@ -60,7 +60,7 @@ __device__ __forceinline__ void rc_store_hit(rc_hit *hits, unsigned long long i,
     __stcs(p + 1, make_float4(h.bary_u, h.bary_v, __uint_as_float(h.instance_id), __uint_as_float(h.metadata)));
 }
 
-// Scheduler constants per kernel variant (swept with tools/exp_variant.py on the B200 and screened with tools/sched_model.py in the
+// Scheduler constants per kernel variant (swept with tools/exp_variant.py on the B200 and screened with tests/sched_model.py in the
 // CPU warp simulator, profiles/README.md).  A refill runs when at least RC_FETCH_MIN lanes of the warp are idle (or nothing else can
 // run); a T step runs when RC_T_W * nT >= nN, an X step when RC_X_W * nX > nN.  Letting the short steps (triangle test, instance entry,
 // refill) run before they have a majority keeps their lanes from idling through long runs of node steps; the weight and the refill

@@ -3,8 +3,8 @@
 iterations and active lanes per step kind (N node, T triangle, X instance entry, F retire + refill) on the instanced scene C3, and a
 cost model  sum_k iterations_k * (body_k + overhead)  in warp instructions (body lengths from the SASS: N 180, T 110, X 60, F 150,
 scheduler overhead 20).  The model tracks the B200 within 6 % over the policies measured there (profiles/README.md), so a policy
-can be screened here before it costs GPU time:  RC_HOSTSIM_LIB=<experiment build of tests/hostsim> python tools/sched_model.py
-usage: python tools/sched_model.py [n_instances=10000] [n_rays=40000]"""
+can be screened here before it costs GPU time:  RC_HOSTSIM_LIB=<experiment build of tests/hostsim> python tests/sched_model.py
+usage: python tests/sched_model.py [n_instances=10000] [n_rays=40000]"""
 import json
 import os
 import sys

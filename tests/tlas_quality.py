@@ -3,7 +3,7 @@
 box a ray crosses (no early termination) for the shipped LBVH topology, a PLOC (windowed agglomerative) topology and a full-sweep
 SAH topology, all collapsed to 4-wide nodes by the same greedy rule.  Result (10,000 instances, 3,000 box rays): LBVH 36.4, PLOC r=8
 35.7, PLOC r=32 37.1, SAH 33.9 node visits per ray: at most 7 % of the TLAS part, ~3 % of a ray, so the LBVH stays.
-usage: python tools/tlas_quality.py [n_instances]"""
+usage: python tests/tlas_quality.py [n_instances]"""
 import sys, time
 import os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
