@@ -16,9 +16,12 @@
  *     library with the reference's exact rule (src/triangle_mesh.jl:14-17).
  *   - Indices returned in RTHitResult are 0-based (src/rt_transport.jl:26-31); the Julia shim
  *     adds 1 where closest_hit's tuple is 1-based (src/instanced-bvh.jl:2011).
- *   - Not thread-safe per context for mutation; trace calls on a synced context are re-entrant
- *     only when issued on the same stream (reference: single-threaded mutation, concurrent pure
- *     reads, src/kernels.jl:64).
+ *   - Threading: every entry point that touches the GPU holds a per-context lock for the duration of the
+ *     call, so queries on a synced context may be issued from several host threads (the reference calls
+ *     closest_hit under Threads.@threads, src/kernels.jl:64,82) — they execute one after the other on the
+ *     context's stream.  Mutation keeps the reference's contract: one mutating thread, no query in flight
+ *     (the lock keeps the library's own state consistent, it does not make push!/sync! + trace a transaction).
+ *     rc_last_error() returns the context's last message and is not per thread.
  */
 #ifndef RAYCORE_CUDA_H
 #define RAYCORE_CUDA_H

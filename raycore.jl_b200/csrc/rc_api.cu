@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -28,6 +29,9 @@ std::string g_create_error;
 }  // namespace
 
 struct rc_context {
+    // queries on a synced TLAS may come from several host threads at once (the reference calls them under Threads.@threads,
+    // src/kernels.jl:64,82); entry points that touch the GPU or the shared launch resources serialise on this lock (RC_ENTER)
+    std::recursive_mutex mu;
     int device = 0;
     cudaStream_t stream = nullptr, s_h2d = nullptr, s_d2h = nullptr;
     bool owns_stream = true;
@@ -78,6 +82,10 @@ struct rc_context {
     } while (0)
 
 static inline void use_device(const rc_context *ctx) { cudaSetDevice(ctx->device); }
+// select the context's device and hold its lock for the rest of the calling function
+#define RC_ENTER(ctx)  \
+    use_device(ctx);   \
+    std::lock_guard<std::recursive_mutex> rc_guard_((ctx)->mu)
 static int32_t builder_error_code(const std::string &err) { return err.find("supported range") != std::string::npos ? RC_ERR_INVALID_ARGUMENT : RC_ERR_CUDA; }
 
 static RcScene make_scene(const rc_context *ctx) {
@@ -176,7 +184,7 @@ void *rc_stream(rc_context *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
 int32_t rc_set_stream(rc_context *ctx, void *stream) {
     if (!ctx) return RC_ERR_INVALID_ARGUMENT;
-    use_device(ctx);
+    RC_ENTER(ctx);
     RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->owns_stream) { cudaStreamDestroy(ctx->stream); ctx->owns_stream = false; }
     if (stream) ctx->stream = (cudaStream_t)stream;
@@ -244,7 +252,7 @@ static uint32_t append_blas_with_instances(rc_context *ctx, const RcDeviceBlas &
 int32_t rc_push(rc_context *ctx, const float *verts, uint32_t n_faces, const uint32_t *face_meta, const float *transforms, const float *inv_transforms,
                 const uint32_t *instance_ids, uint32_t m, uint32_t flags, uint32_t *handle_out) {
     if (!ctx) return RC_ERR_INVALID_ARGUMENT;
-    use_device(ctx);
+    RC_ENTER(ctx);
     if (!transforms || m == 0 || !handle_out) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "rc_push: transforms, m >= 1 and handle_out are required");
     RcDeviceBlas b;
     int32_t rc = build_blas_from(ctx, verts, n_faces, face_meta, flags, &b);
@@ -294,7 +302,7 @@ int32_t rc_update_transforms(rc_context *ctx, uint32_t handle, const float *tran
 // source of truth for the instance list (refit uploads it, compaction reorders it), so this costs one 48 B/instance read-back.
 int32_t rc_update_transforms_device(rc_context *ctx, uint32_t handle, const float *d_transforms, const float *d_inv_transforms, uint32_t m) {
     if (!ctx) return RC_ERR_INVALID_ARGUMENT;
-    use_device(ctx);
+    RC_ENTER(ctx);
     if (!d_transforms) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "rc_update_transforms_device: transforms is NULL");
     std::vector<float> xf(12 * (size_t)m), inv(d_inv_transforms ? 12 * (size_t)m : 0);
     if (m) {
@@ -307,7 +315,7 @@ int32_t rc_update_transforms_device(rc_context *ctx, uint32_t handle, const floa
 
 int32_t rc_update_geometry(rc_context *ctx, uint32_t handle, const float *verts, uint32_t n_faces, const uint32_t *face_meta, uint32_t flags) {  // :808-857
     if (!ctx) return RC_ERR_INVALID_ARGUMENT;
-    use_device(ctx);
+    RC_ENTER(ctx);
     HandleInfo *hi = nullptr;
     int32_t rc = find_handle(ctx, handle, &hi);
     if (rc != RC_OK) return rc;
@@ -328,7 +336,7 @@ int32_t rc_update_geometry(rc_context *ctx, uint32_t handle, const float *verts,
 // ---- serialised geometry (rc_build.cu, "Serialised BLAS") ----
 int32_t rc_export_geometry(rc_context *ctx, uint32_t handle, void *blob, uint64_t capacity, uint64_t *size) {
     if (!ctx) return RC_ERR_INVALID_ARGUMENT;
-    use_device(ctx);
+    RC_ENTER(ctx);
     HandleInfo *hi = nullptr;
     int32_t rc = find_handle(ctx, handle, &hi);
     if (rc != RC_OK) return rc;
@@ -349,7 +357,7 @@ int32_t rc_export_geometry(rc_context *ctx, uint32_t handle, void *blob, uint64_
 int32_t rc_push_exported(rc_context *ctx, const void *blob, uint64_t size, const float *transforms, const float *inv_transforms, const uint32_t *instance_ids,
                          uint32_t m, uint32_t *handle_out) {
     if (!ctx) return RC_ERR_INVALID_ARGUMENT;
-    use_device(ctx);
+    RC_ENTER(ctx);
     if (!blob || !transforms || m == 0 || !handle_out) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "rc_push_exported: blob, transforms, m >= 1 and handle_out are required");
     RcDeviceBlas b;
     std::string err;
@@ -432,7 +440,7 @@ int32_t rc_sync(rc_context *ctx, int32_t *action) {  // sync!, :894-921
     if (!ctx) return RC_ERR_INVALID_ARGUMENT;
     if (action) *action = RC_SYNC_NONE;
     if (!ctx->dirty && !ctx->transforms_dirty && ctx->built) return RC_OK;  // clean fast path: no GPU work, no sync (:898-900)
-    use_device(ctx);
+    RC_ENTER(ctx);
     if (ctx->dirty || !ctx->built) {
         int32_t rc = rebuild(ctx);
         if (rc != RC_OK) return rc;
@@ -489,7 +497,7 @@ int32_t rc_world_bound(const rc_context *ctx, float out[6]) {
 }
 int32_t rc_wait(rc_context *ctx) {
     if (!ctx) return RC_ERR_INVALID_ARGUMENT;
-    use_device(ctx);
+    RC_ENTER(ctx);
     RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     RC_CUDA(ctx, cudaStreamSynchronize(ctx->s_h2d));
     RC_CUDA(ctx, cudaStreamSynchronize(ctx->s_d2h));
@@ -519,20 +527,20 @@ static int32_t read_nodes2(rc_context *ctx, const RcNode2 *d_nodes, uint32_t cou
 }
 int32_t rc_read_tlas_nodes(rc_context *ctx, rc_bvh_node2 *out, uint32_t capacity) {
     if (!ctx || !out) return RC_ERR_INVALID_ARGUMENT;
-    use_device(ctx);
+    RC_ENTER(ctx);
     if (!ctx->built || ctx->dirty) RC_FAIL(ctx, RC_ERR_NOT_SYNCED, "call rc_sync first");
     return read_nodes2(ctx, ctx->tlas.nodes2, ctx->synced_tlas_nodes, out, capacity);
 }
 int32_t rc_read_blas_nodes(rc_context *ctx, uint32_t blas_index, rc_bvh_node2 *out, uint32_t capacity) {
     if (!ctx || !out) return RC_ERR_INVALID_ARGUMENT;
-    use_device(ctx);
+    RC_ENTER(ctx);
     if (blas_index < 1 || blas_index > ctx->blas.size()) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "blas_index out of range");
     const RcDeviceBlas &B = ctx->blas[blas_index - 1];
     return read_nodes2(ctx, B.nodes2, 2 * B.n - 1, out, capacity);
 }
 int32_t rc_read_blas_order(rc_context *ctx, uint32_t blas_index, uint32_t *out, uint32_t capacity) {
     if (!ctx || !out) return RC_ERR_INVALID_ARGUMENT;
-    use_device(ctx);
+    RC_ENTER(ctx);
     if (blas_index < 1 || blas_index > ctx->blas.size()) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "blas_index out of range");
     const RcDeviceBlas &B = ctx->blas[blas_index - 1];
     if (capacity < B.n) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "capacity too small");
@@ -544,7 +552,7 @@ int32_t rc_read_blas_order(rc_context *ctx, uint32_t blas_index, uint32_t *out, 
 }
 int32_t rc_read_blas_faces(rc_context *ctx, uint32_t blas_index, uint32_t *out, uint32_t capacity) {
     if (!ctx || !out) return RC_ERR_INVALID_ARGUMENT;
-    use_device(ctx);
+    RC_ENTER(ctx);
     if (blas_index < 1 || blas_index > ctx->blas.size()) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "blas_index out of range");
     const RcDeviceBlas &B = ctx->blas[blas_index - 1];
     if (capacity < B.n) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "capacity too small");
@@ -588,7 +596,7 @@ static int32_t check_overflow(rc_context *ctx) {
 
 static int32_t trace_common(rc_context *ctx, const rc_ray *rays, rc_hit *hits, uint64_t n, uint32_t flags, bool any) {
     if (!ctx) return RC_ERR_INVALID_ARGUMENT;
-    use_device(ctx);
+    RC_ENTER(ctx);
     if (n == 0) return RC_OK;
     if (!rays || !hits) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "rays / hits is NULL");
     if (!ctx->built || ctx->dirty || ctx->transforms_dirty) RC_FAIL(ctx, RC_ERR_NOT_SYNCED, "TLAS has pending mutations: call rc_sync before tracing");
@@ -661,7 +669,7 @@ int32_t rc_trace_any(rc_context *ctx, const rc_ray *rays, rc_hit *hits, uint64_t
 
 int32_t rc_get_counters(rc_context *ctx, uint64_t out[6], int32_t reset) {
     if (!ctx || !out) return RC_ERR_INVALID_ARGUMENT;
-    use_device(ctx);
+    RC_ENTER(ctx);
     RcCounters c;
     RC_CUDA(ctx, cudaMemcpyAsync(&c, ctx->d_counters, sizeof c, cudaMemcpyDeviceToHost, ctx->stream));
     if (reset) RC_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof c, ctx->stream));
@@ -680,7 +688,7 @@ static int32_t require_synced(rc_context *ctx) {
 }
 
 static int32_t grid_common(rc_context *ctx, const float viewdir[3], uint32_t grid, rc_hit *hits, float *points, float *illum, uint32_t n_illum, double *centroid4) {
-    use_device(ctx);
+    RC_ENTER(ctx);
     int32_t rc = require_synced(ctx);
     if (rc != RC_OK) return rc;
     if (!viewdir || grid == 0) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "viewdir / grid");
@@ -750,7 +758,7 @@ int32_t rc_view_factors(rc_context *ctx, uint32_t rays_per_triangle, uint64_t se
 int32_t rc_view_factors_strided(rc_context *ctx, uint32_t rays_per_triangle, uint64_t seed, uint32_t *out, uint32_t row_base, uint32_t row_stride, uint32_t n_rows,
                                 uint32_t flags, uint64_t *skipped) {
     if (!ctx || !out) return RC_ERR_INVALID_ARGUMENT;
-    use_device(ctx);
+    RC_ENTER(ctx);
     int32_t rc = require_synced(ctx);
     if (rc != RC_OK) return rc;
     uint32_t n_cols = ctx->n_flat_prims;
@@ -799,7 +807,7 @@ int32_t rc_view_factors_strided(rc_context *ctx, uint32_t rays_per_triangle, uin
 
 int32_t rc_view_factor_rays(rc_context *ctx, uint32_t rays_per_triangle, uint64_t seed, uint32_t row_base, uint32_t n_rows, rc_ray *out) {
     if (!ctx || !out) return RC_ERR_INVALID_ARGUMENT;
-    use_device(ctx);
+    RC_ENTER(ctx);
     int32_t rc = require_synced(ctx);
     if (rc != RC_OK) return rc;
     size_t n = (size_t)n_rows * rays_per_triangle;
@@ -817,7 +825,7 @@ int32_t rc_view_factor_rays(rc_context *ctx, uint32_t rays_per_triangle, uint64_
 
 int32_t rc_read_flat_metadata(rc_context *ctx, uint32_t *out, uint32_t capacity) {
     if (!ctx || !out) return RC_ERR_INVALID_ARGUMENT;
-    use_device(ctx);
+    RC_ENTER(ctx);
     int32_t rc = require_synced(ctx);
     if (rc != RC_OK) return rc;
     if (capacity < ctx->n_flat_prims) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "capacity too small");
@@ -834,7 +842,7 @@ int32_t rc_read_flat_metadata(rc_context *ctx, uint32_t *out, uint32_t capacity)
 // ------------------------------------------------------------------------------------------------ collision (§8f row 1)
 int32_t rc_collide_instances(rc_context *ctx, rc_contact_pair *contacts, uint64_t capacity, uint64_t *n_contacts) {
     if (!ctx || !n_contacts) return RC_ERR_INVALID_ARGUMENT;
-    use_device(ctx);
+    RC_ENTER(ctx);
     int32_t rc = require_synced(ctx);
     if (rc != RC_OK) return rc;
     *n_contacts = 0;
@@ -865,7 +873,7 @@ int32_t rc_collide_instances(rc_context *ctx, rc_contact_pair *contacts, uint64_
 
 int32_t rc_collide_instances_any(rc_context *ctx, uint32_t handle_a, uint32_t handle_b, int32_t *overlap) {
     if (!ctx || !overlap) return RC_ERR_INVALID_ARGUMENT;
-    use_device(ctx);
+    RC_ENTER(ctx);
     *overlap = 0;
     int32_t rc = require_synced(ctx);
     if (rc != RC_OK) return rc;
@@ -888,7 +896,7 @@ int32_t rc_collide_instances_any(rc_context *ctx, uint32_t handle_a, uint32_t ha
 // ---- wavefront stages around the trace (docs/src/wavefront-renderer.jl:185-362) --------------------------------------------
 int32_t rc_set_normals(rc_context *ctx, uint32_t handle, const float *normals, uint32_t n_faces, uint32_t flags) {
     if (!ctx) return RC_ERR_INVALID_ARGUMENT;
-    use_device(ctx);
+    RC_ENTER(ctx);
     HandleInfo *hi = nullptr;
     int32_t rc = find_handle(ctx, handle, &hi);
     if (rc != RC_OK) return rc;
@@ -947,7 +955,7 @@ static int32_t finish_stage(rc_context *ctx, uint32_t flags, uint32_t launches, 
 }
 
 static int32_t primary_common(rc_context *ctx, const RcCamera &cam, uint32_t width, uint32_t height, uint32_t n_samples, uint64_t seed, rc_ray *d_rays, uint32_t flags) {
-    use_device(ctx);
+    RC_ENTER(ctx);
     if (width == 0 || height == 0 || n_samples == 0) return RC_OK;
     if (!d_rays) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "rays is NULL");
     cudaEventRecord(ctx->ev_t0, ctx->stream);
@@ -1008,7 +1016,7 @@ static int32_t shadow_source(rc_context *ctx, const rc_ray *rays, const rc_hit *
 int32_t rc_generate_shadow_rays(rc_context *ctx, const rc_ray *rays, const rc_hit *hits, uint64_t n, const float *lights, uint32_t n_lights, float shadow_bias,
                                 rc_ray *shadow_rays, uint32_t flags) {
     if (!ctx) return RC_ERR_INVALID_ARGUMENT;
-    use_device(ctx);
+    RC_ENTER(ctx);
     if (n == 0) return RC_OK;
     RcLights L;
     RcShadowSource src;
@@ -1024,7 +1032,7 @@ int32_t rc_generate_shadow_rays(rc_context *ctx, const rc_ray *rays, const rc_hi
 
 int32_t rc_test_shadow_rays(rc_context *ctx, const rc_ray *shadow_rays, uint64_t n, uint8_t *visible, uint32_t flags) {
     if (!ctx) return RC_ERR_INVALID_ARGUMENT;
-    use_device(ctx);
+    RC_ENTER(ctx);
     if (n == 0) return RC_OK;
     if (!shadow_rays || !visible) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "shadow_rays / visible is NULL");
     int32_t rc = require_synced(ctx);
@@ -1037,7 +1045,7 @@ int32_t rc_test_shadow_rays(rc_context *ctx, const rc_ray *shadow_rays, uint64_t
 int32_t rc_shadow_visibility(rc_context *ctx, const rc_ray *rays, const rc_hit *hits, uint64_t n, const float *lights, uint32_t n_lights, float shadow_bias,
                              uint8_t *visible, uint32_t flags) {
     if (!ctx) return RC_ERR_INVALID_ARGUMENT;
-    use_device(ctx);
+    RC_ENTER(ctx);
     if (n == 0) return RC_OK;
     RcLights L;
     RcShadowSource src;
@@ -1055,19 +1063,19 @@ int32_t rc_shadow_visibility(rc_context *ctx, const rc_ray *rays, const rc_hit *
 // ------------------------------------------------------------------------------------------------ memory helpers
 int32_t rc_device_alloc(rc_context *ctx, size_t bytes, void **out) {
     if (!ctx || !out) return RC_ERR_INVALID_ARGUMENT;
-    use_device(ctx);
+    RC_ENTER(ctx);
     RC_CUDA(ctx, cudaMalloc(out, bytes));
     return RC_OK;
 }
 int32_t rc_device_free(rc_context *ctx, void *ptr) {
     if (!ctx) return RC_ERR_INVALID_ARGUMENT;
-    use_device(ctx);
+    RC_ENTER(ctx);
     RC_CUDA(ctx, cudaFree(ptr));
     return RC_OK;
 }
 int32_t rc_host_alloc(rc_context *ctx, size_t bytes, void **out) {
     if (!ctx || !out) return RC_ERR_INVALID_ARGUMENT;
-    use_device(ctx);
+    RC_ENTER(ctx);
     RC_CUDA(ctx, cudaHostAlloc(out, bytes, cudaHostAllocDefault));
     return RC_OK;
 }
@@ -1078,21 +1086,21 @@ int32_t rc_host_free(rc_context *ctx, void *ptr) {
 }
 int32_t rc_memcpy_h2d(rc_context *ctx, void *dst, const void *src, size_t bytes) {
     if (!ctx) return RC_ERR_INVALID_ARGUMENT;
-    use_device(ctx);
+    RC_ENTER(ctx);
     RC_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return RC_OK;
 }
 int32_t rc_memcpy_d2h(rc_context *ctx, void *dst, const void *src, size_t bytes) {
     if (!ctx) return RC_ERR_INVALID_ARGUMENT;
-    use_device(ctx);
+    RC_ENTER(ctx);
     RC_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return RC_OK;
 }
 int32_t rc_ipc_export(rc_context *ctx, void *ptr, uint8_t handle_out[64]) {
     if (!ctx || !ptr || !handle_out) return RC_ERR_INVALID_ARGUMENT;
-    use_device(ctx);
+    RC_ENTER(ctx);
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     cudaIpcMemHandle_t h;
     RC_CUDA(ctx, cudaIpcGetMemHandle(&h, ptr));
@@ -1101,7 +1109,7 @@ int32_t rc_ipc_export(rc_context *ctx, void *ptr, uint8_t handle_out[64]) {
 }
 int32_t rc_ipc_open(rc_context *ctx, const uint8_t handle[64], void **out) {
     if (!ctx || !handle || !out) return RC_ERR_INVALID_ARGUMENT;
-    use_device(ctx);
+    RC_ENTER(ctx);
     cudaIpcMemHandle_t h;
     memcpy(&h, handle, 64);
     RC_CUDA(ctx, cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
@@ -1112,7 +1120,7 @@ int32_t rc_ipc_open(rc_context *ctx, const uint8_t handle[64], void **out) {
 // completion events so a double-buffering caller can make the context stream wait before it overwrites that buffer again.
 int32_t rc_peer_copy_async(rc_context *ctx, void *dst, const void *src, size_t bytes, uint32_t slot) {
     if (!ctx || !dst || !src || slot > 1) return RC_ERR_INVALID_ARGUMENT;
-    use_device(ctx);
+    RC_ENTER(ctx);
     RC_CUDA(ctx, cudaEventRecord(ctx->ev_k[slot], ctx->stream));
     RC_CUDA(ctx, cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_k[slot], 0));
     RC_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->s_d2h));
@@ -1122,14 +1130,14 @@ int32_t rc_peer_copy_async(rc_context *ctx, void *dst, const void *src, size_t b
 }
 int32_t rc_stream_wait_copy(rc_context *ctx, uint32_t slot) {
     if (!ctx || slot > 1) return RC_ERR_INVALID_ARGUMENT;
-    use_device(ctx);
+    RC_ENTER(ctx);
     if (ctx->copy_pending[slot]) RC_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[slot], 0));
     return RC_OK;
 }
 
 int32_t rc_ipc_close(rc_context *ctx, void *ptr) {
     if (!ctx) return RC_ERR_INVALID_ARGUMENT;
-    use_device(ctx);
+    RC_ENTER(ctx);
     RC_CUDA(ctx, cudaIpcCloseMemHandle(ptr));
     return RC_OK;
 }
