@@ -249,3 +249,40 @@ def test_update_transforms_from_device_array():
     with pytest.raises(RaycoreError):
         b.update_transforms_device(hb, b.queue(np.float32, 49 * 12))
     a.free(); b.free()
+
+
+def test_queries_from_several_host_threads():
+    """The reference's callers issue closest_hit under Threads.@threads (src/kernels.jl:64,82).  Calls on one context serialise on the
+    context lock: concurrent batched traces from host buffers (which share the context's staging buffers and work counter) and per-ray
+    calls give exactly the single-threaded results."""
+    import threading
+
+    tlas = TLAS()
+    tlas.push(W.bumpy_sphere(40), list(W.random_trs(20, 3, extent=5.0)))
+    tlas.sync()
+    batches = [np.concatenate([W.box_rays(30000 + 1000 * k, 10 + k, half=7.0), W.interior_rays(5000, 20 + k, radius=6.0)]) for k in range(4)]
+    want_c = [tlas.trace_closest(b) for b in batches]
+    want_a = [tlas.trace_any(b) for b in batches]
+    errors = []
+
+    def worker(k):
+        try:
+            for it in range(6):
+                got = tlas.trace_any(batches[k]) if it % 2 else tlas.trace_closest(batches[k])
+                ref = want_a[k] if it % 2 else want_c[k]
+                if got.tobytes() != ref.tobytes():
+                    errors.append((k, it, "batch differs"))
+            r = batches[k][0]
+            h = tlas.closest_hit(Ray(tuple(r["o"]), tuple(r["d"])))
+            if bool(h[0]) != bool(want_c[k][0]["hit"]):
+                errors.append((k, "per-ray call differs"))
+        except Exception as e:  # noqa: BLE001
+            errors.append((k, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    tlas.free()
