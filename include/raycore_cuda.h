@@ -147,6 +147,9 @@ int32_t rc_sync(rc_context *ctx, int32_t *action);
 int32_t rc_export_geometry(rc_context *ctx, uint32_t handle, void *blob, uint64_t capacity, uint64_t *size);
 int32_t rc_push_exported(rc_context *ctx, const void *blob, uint64_t size, const float *transforms, const float *inv_transforms,
                          const uint32_t *instance_ids, uint32_t m, uint32_t *handle_out);
+/* The host-side part of those checks alone (magic, layout version, section table, size, payload hash, supported extent): needs neither a
+ * context nor a GPU, e.g. to vet a file before a device is claimed.  Outputs are nullable; a refusal's message is rc_last_error(NULL). */
+int32_t rc_check_exported(const void *blob, uint64_t size, uint32_t *n_triangles, uint32_t *n_faces, uint32_t *has_normals);
 
 /* ---- introspection ------------------------------------------------------------------- */
 int32_t rc_is_valid(const rc_context *ctx, uint32_t handle);                 /* :524-526 */

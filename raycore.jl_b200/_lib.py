@@ -67,7 +67,7 @@ NODE2_DTYPE = np.dtype(
 EXPORTS = [
     "rc_abi_version", "rc_create", "rc_destroy", "rc_last_error", "rc_stream", "rc_set_stream",
     "rc_push", "rc_delete", "rc_update_transforms", "rc_update_transforms_device", "rc_update_geometry", "rc_sync",
-    "rc_export_geometry", "rc_push_exported",
+    "rc_export_geometry", "rc_push_exported", "rc_check_exported",
     "rc_is_valid", "rc_n_instances", "rc_n_instances_of", "rc_n_total_instances", "rc_n_geometries", "rc_is_dirty",
     "rc_get_instances", "rc_world_bound", "rc_wait", "rc_sizes", "rc_read_tlas_nodes", "rc_read_blas_nodes",
     "rc_read_blas_order", "rc_blas_n_prims", "rc_read_blas_faces", "rc_get_instance_handles",
@@ -120,6 +120,7 @@ def load():
         "rc_sync": (i32, [vp, pi32]),
         "rc_export_geometry": (i32, [vp, u32, vp, u64, C.POINTER(u64)]),
         "rc_push_exported": (i32, [vp, vp, u64, vp, vp, vp, u32, pu32]),
+        "rc_check_exported": (i32, [vp, u64, pu32, pu32, pu32]),
         "rc_is_valid": (i32, [vp, u32]),
         "rc_n_instances": (u32, [vp]),
         "rc_n_instances_of": (u32, [vp, u32]),

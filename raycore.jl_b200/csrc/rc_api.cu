@@ -354,6 +354,14 @@ int32_t rc_export_geometry(rc_context *ctx, uint32_t handle, void *blob, uint64_
     return RC_OK;
 }
 
+// host-only: would rc_push_exported accept these bytes as far as header, size and payload hash go?  Needs neither a context nor a GPU;
+// the message of a refusal is returned by rc_last_error(NULL).
+int32_t rc_check_exported(const void *blob, uint64_t size, uint32_t *n_triangles, uint32_t *n_faces, uint32_t *has_normals) {
+    std::string err;
+    if (!rc_blas_blob_check(blob, size, n_triangles, n_faces, has_normals, err)) { g_create_error = err; return RC_ERR_INVALID_ARGUMENT; }
+    return RC_OK;
+}
+
 int32_t rc_push_exported(rc_context *ctx, const void *blob, uint64_t size, const float *transforms, const float *inv_transforms, const uint32_t *instance_ids,
                          uint32_t m, uint32_t *handle_out) {
     if (!ctx) return RC_ERR_INVALID_ARGUMENT;

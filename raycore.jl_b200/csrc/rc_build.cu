@@ -819,10 +819,9 @@ __global__ void k_validate_blas(const RcNode2 *__restrict__ nodes2, const RcNode
     if (errs) atomicAdd(bad, errs);
 }
 
-bool rc_blas_import(cudaStream_t st, const void *blob, uint64_t size, RcDeviceBlas *out, std::string &err) {
-    *out = RcDeviceBlas();
+// host-side checks of a blob (no GPU involved): magic, layout version, section table, size, payload hash, supported extent
+static bool blob_check(const void *blob, uint64_t size, RcBlobHeader &h, std::string &err) {
     if (!blob || size < sizeof(RcBlobHeader)) { err = "import: blob too small"; return false; }
-    RcBlobHeader h;
     memcpy(&h, blob, sizeof h);
     if (memcmp(h.magic, RC_BLOB_MAGIC, 8) != 0) { err = "import: not a raycore BLAS blob"; return false; }
     if (h.abi_version != RC_ABI_VERSION || h.leaf_max != RC_BLAS_LEAF_MAX || h.hull_boxes != RC_HULL_BOXES) {
@@ -840,7 +839,23 @@ bool rc_blas_import(cudaStream_t st, const void *blob, uint64_t size, RcDeviceBl
     if (size < h.total_bytes) { err = "import: blob is truncated"; return false; }
     const uint8_t *p = static_cast<const uint8_t *>(blob);
     if (blob_hash(p + sizeof h, h.total_bytes - sizeof h) != h.payload_hash) { err = "import: payload hash mismatch (corrupted blob)"; return false; }
-    if (!extent_supported(h.root_aabb, err)) return false;
+    return extent_supported(h.root_aabb, err);
+}
+
+bool rc_blas_blob_check(const void *blob, uint64_t size, uint32_t *n_triangles, uint32_t *n_faces_in, uint32_t *has_normals, std::string &err) {
+    RcBlobHeader h;
+    if (!blob_check(blob, size, h, err)) return false;
+    if (n_triangles) *n_triangles = h.n;
+    if (n_faces_in) *n_faces_in = h.n_faces_in;
+    if (has_normals) *has_normals = h.has_normals;
+    return true;
+}
+
+bool rc_blas_import(cudaStream_t st, const void *blob, uint64_t size, RcDeviceBlas *out, std::string &err) {
+    *out = RcDeviceBlas();
+    RcBlobHeader h;
+    if (!blob_check(blob, size, h, err)) return false;
+    const uint8_t *p = static_cast<const uint8_t *>(blob);
     const uint64_t n = h.n;
     uint32_t *d_bad = nullptr;
     RcTemps tmp(st);

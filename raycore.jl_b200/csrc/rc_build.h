@@ -58,6 +58,8 @@ void rc_free_blas(RcDeviceBlas *b, cudaStream_t st);
 uint64_t rc_blas_blob_bytes(const RcDeviceBlas &b);
 bool rc_blas_export(cudaStream_t st, const RcDeviceBlas &b, void *blob, uint64_t capacity, std::string &err);
 bool rc_blas_import(cudaStream_t st, const void *blob, uint64_t size, RcDeviceBlas *out, std::string &err);
+// the host-side part of the import checks alone (header, section table, size, payload hash): no GPU needed
+bool rc_blas_blob_check(const void *blob, uint64_t size, uint32_t *n_triangles, uint32_t *n_faces_in, uint32_t *has_normals, std::string &err);
 bool rc_build_tlas(cudaStream_t st, const rc_instance_desc *h_inst, uint32_t n, const std::vector<RcBlasPtrs> &blas, const std::vector<float> &blas_roots,
                    RcDeviceTlas *t, std::string &err);
 bool rc_refit_tlas(cudaStream_t st, const rc_instance_desc *h_inst, uint32_t n, RcDeviceTlas *t, std::string &err);

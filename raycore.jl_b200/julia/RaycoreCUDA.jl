@@ -92,6 +92,13 @@ function export_geometry(t::CuTLAS, h::TLASHandle)
     check(t.ctx, ccall((:rc_export_geometry, lib), Int32, (Ptr{Cvoid}, UInt32, Ptr{Cvoid}, UInt64, Ref{UInt64}), t.ctx, h.id, blob, length(blob), n))
     return blob
 end
+"Host-side vetting of `export_geometry` bytes (header, layout version, size, payload hash) without a context or a GPU; errors like the import would."
+function check_exported(blob::Vector{UInt8})
+    n = Ref{UInt32}(0); f = Ref{UInt32}(0); hn = Ref{UInt32}(0)
+    rc = ccall((:rc_check_exported, lib), Int32, (Ptr{Cvoid}, UInt64, Ref{UInt32}, Ref{UInt32}, Ref{UInt32}), blob, length(blob), n, f, hn)
+    rc == 0 || error(unsafe_string(ccall((:rc_last_error, lib), Cstring, (Ptr{Cvoid},), C_NULL)))
+    return (n_triangles = Int(n[]), n_faces = Int(f[]), has_normals = hn[] != 0)
+end
 "push! of a geometry restored from `export_geometry` bytes (no builder kernel runs).  `mesh` is the caller's copy used to materialise Triangles."
 function push_exported!(t::CuTLAS, blob::Vector{UInt8}, mesh::GeometryBasics.Mesh, transforms::AbstractVector{Mat4f};
                         instance_ids::Union{Nothing, AbstractVector{<:Integer}} = nothing)

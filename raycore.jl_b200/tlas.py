@@ -75,6 +75,32 @@ def blob_triangles(blob) -> np.ndarray:
     return np.frombuffer(memoryview(blob), BLOB_TRI_DTYPE, count=int(h["n"]), offset=int(h["off_tris"]))
 
 
+def blob_hash(payload) -> int:
+    """Payload hash of an `export_geometry` blob (blob_hash, csrc/rc_build.cu): word-wise multiply-xorshift over everything after the header."""
+    b = bytes(payload)
+    m64 = (1 << 64) - 1
+    h = 0x9E3779B97F4A7C15 ^ len(b)
+    nw = len(b) // 8
+    for w in np.frombuffer(b, "<u8", count=nw).tolist():
+        h = ((h ^ w) * 0xD6E8FEB86659FD93) & m64
+        h ^= h >> 32
+    for x in b[8 * nw:]:
+        h = ((h ^ x) * 0x100000001B3) & m64
+    return h
+
+
+def check_exported(blob):
+    """rc_check_exported: the host-side import checks (header, section table, size, payload hash) without a context or a GPU.
+    Returns (n_triangles, n_faces, has_normals); raises RaycoreError with the library's message on refusal."""
+    lib = L.load()
+    b = np.ascontiguousarray(np.frombuffer(blob, np.uint8) if not isinstance(blob, np.ndarray) else blob.view(np.uint8).reshape(-1))
+    n, f, hn = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    rc = lib.rc_check_exported(b.ctypes.data if b.size else None, b.nbytes, C.byref(n), C.byref(f), C.byref(hn))
+    if rc != L.RC_OK:
+        raise RaycoreError(rc, lib.rc_last_error(None).decode())
+    return n.value, f.value, bool(hn.value)
+
+
 def blob_faces(blob) -> np.ndarray:
     """n_faces_in x 9 vertex soup in submission order (faces the degenerate filter dropped are zero)."""
     h, t = blob_header(blob), blob_triangles(blob)
