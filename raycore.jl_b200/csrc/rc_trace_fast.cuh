@@ -7,12 +7,14 @@
 //   X  level step     it must enter an instance (TLAS leaf); leaving one (sentinel popped) is folded into the settle
 //   F  refill         its ray is finished (or it has none yet)
 // Each lane keeps its readiness as a packed vote word (one byte per kind); every iteration the warp sums the votes
-// with ONE REDUX.SUM and executes the kind with the most ready lanes, so a freshly fetched ray that needs ten box steps
-// to reach its first leaf never stalls 31 lanes that wait to test triangles, and vice versa (profiles/r1_v2: a plain
-// while-while loop ran the box code at 9.4/32 lanes, this scheduler at 18.5/32).  The vote word is recomputed only by
-// the lanes that just executed a step ("settle"), which also parks a freshly reached leaf so the lane can keep descending.
+// with ONE REDUX.SUM and executes one kind for the lanes that are ready for it (node steps by default; a short step as soon as
+// it has a policy-defined share of the node-step lanes, see the scheduler constants below), so a freshly fetched ray that needs
+// ten box steps to reach its first leaf never stalls 31 lanes that wait to test triangles, and vice versa (profiles/r1_v2: a plain
+// while-while loop ran the box code at 9.4/32 lanes; the shipped policies run node steps at 23-25/32 lanes in the warp simulator).
+// The vote word is recomputed only by the lanes that just executed a step ("settle"), which also returns a lane to the TLAS when
+// it popped the level sentinel and parks a freshly reached leaf so the lane can keep descending.
 // Refills are warp-cooperative (one atomic on the global work counter per refill) and deferred until RC_FETCH_MIN_*
-// lanes are idle, so the refill / retire code also runs with many lanes.
+// lanes are idle, so the refill / retire code also runs with several lanes.
 //
 // Arithmetic: two child planes are decoded per PRMT into a half2 of subnormals (0x00qq = q * 2^-24 exactly), widened with
 // HADD2.F32 on the FMA pipe (no I2F: the XU pipe saturated in profiles/r1_v1; the ALU pipe is the limiter since v4),
