@@ -37,6 +37,25 @@ def gather_records(local: torch.Tensor, total_units: int, unit_bytes: int, dst: 
     return torch.cat([o[: s * unit_bytes] for o, s in zip(out, sizes)])
 
 
+def broadcast_blob(blob: Optional[np.ndarray], src: int = 0, device: Optional[torch.device] = None) -> np.ndarray:
+    """Replicate a byte blob (e.g. `TLAS.export_geometry` bytes) from `src` to every rank: the other way to replicate the BVH
+    (SURVEY.md §8e: "rank 0 builds and broadcasts the arrays") when only one rank holds the meshes.  Ranks other than `src` pass None;
+    every rank returns the bytes, ready for `TLAS.push_exported`.  Two collectives: the size, then the payload."""
+    rank = dist.get_rank()
+    n = torch.tensor([0 if blob is None else int(np.asarray(blob).nbytes)], dtype=torch.int64)
+    if device is not None:
+        n = n.to(device)
+    dist.broadcast(n, src=src)
+    if rank == src:
+        t = torch.from_numpy(np.ascontiguousarray(blob).view(np.uint8).reshape(-1).copy())
+    else:
+        t = torch.empty(int(n.item()), dtype=torch.uint8)
+    if device is not None:
+        t = t.to(device)
+    dist.broadcast(t, src=src)
+    return t.cpu().numpy()
+
+
 def trace_sharded(trace_fn, rays: np.ndarray, record_dtype: np.dtype, device: Optional[torch.device] = None, dst: int = 0):
     """Every rank holds the same `rays`; rank r traces rays[lo:hi] with `trace_fn` and the hit records are gathered to dst.
     Returns the full hit array on dst, None elsewhere."""

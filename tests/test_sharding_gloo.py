@@ -36,10 +36,19 @@ def _worker(rank, world, port, out_path):
     # interleaved shares (rows rank, rank + world, ...): ragged gather + re-interleave
     whole = ev.tlas.view_factors(50, seed=9)
     vf_i = sharding.view_factor_rows_sharded(lambda first, n, stride: whole[first::stride][:n], 6, interleaved=True)
+    # a serialised geometry built on rank 0 only reaches every rank intact (the host-side import checks run without a GPU)
+    from raycore_b200 import tlas as T
+    from test_blob_format import make_blob
+
+    mine = make_blob(W.bumpy_sphere(9)) if rank == 0 else None
+    got = sharding.broadcast_blob(mine)
+    blob_ok = T.check_exported(got) == (len(W.bumpy_sphere(9)) - int(W.is_degenerate(W.bumpy_sphere(9)).sum()), len(W.bumpy_sphere(9)), False)
+    flags = [None] * world
+    dist.all_gather_object(flags, bool(blob_ok) and (rank != 0 or got.tobytes() == mine.tobytes()))
     if rank == 0:
         ref = e.trace(rays)
         ref_vf = ev.tlas.view_factors(50, seed=9)
-        ok = full.tobytes() == ref.tobytes() and np.array_equal(vf, ref_vf) and vf.sum() > 0 and np.array_equal(vf_i, ref_vf)
+        ok = full.tobytes() == ref.tobytes() and np.array_equal(vf, ref_vf) and vf.sum() > 0 and np.array_equal(vf_i, ref_vf) and all(flags)
         open(out_path, "w").write("ok" if ok else "mismatch")
     assert sharding.shard_sizes(5001, 2) == [2500, 2501] and sharding.shard_range(10, 1, 4) == (2, 5)
     dist.barrier()
