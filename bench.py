@@ -57,6 +57,29 @@ def measure_l2_gbs(torch, dev):
     return 2.0 * a.numel() * iters / (e0.elapsed_time(e1) * 1e-3) / 1e9
 
 
+def measure_instanced(rc, W, L, torch, dev, local):
+    """C3 (BASELINE configs[2], on one GPU): 10,000 instances of bumpy_sphere(72) under random T*R*S transforms, 2^23 incoherent rays through
+    the scene box, device-resident closest_hit and any_hit; best of 5 launches after one warm-up (the library's CUDA-event kernel time)."""
+    tl = rc.TLAS(local)
+    tl.push(W.bumpy_sphere(72), list(W.random_trs(10000, 2026, extent=40.0)))
+    tl.sync()
+    n = 1 << 23
+    rays = W.box_rays(n, 7, half=44.0)
+    d_r = torch.from_numpy(rays.view(np.uint8).reshape(-1)).to(dev)
+    d_h = torch.empty(n * 32, dtype=torch.uint8, device=dev)
+    out = {"instanced_config": f"C3: 10000 instances x {tl.sizes()['blas_prims']} triangles, {n} rays with origins uniform in the scene box and uniform directions, rays and hits resident in HBM"}
+    for name, fn in (("closest", tl._lib.rc_trace_closest), ("any", tl._lib.rc_trace_any)):
+        ms = []
+        for _ in range(6):
+            assert fn(tl._ctx, d_r.data_ptr(), d_h.data_ptr(), n, L.RC_RAYS_ON_DEVICE | L.RC_HITS_ON_DEVICE) == 0, tl._lib.rc_last_error(tl._ctx)
+            ms.append(float(tl._lib.rc_last_kernel_ms(tl._ctx)))
+        out[f"instanced_{name}_hit_Mrays_s"] = n / (min(ms[1:]) * 1e-3) / 1e6
+    out["instanced_hit_rate"] = float((d_h.view(torch.int32)[::8] == 1).float().mean().item())
+    del d_r, d_h
+    tl.free()
+    return out
+
+
 def measure_view_factors(rc, W, L, torch, dev, local, world, rank, dist):
     """C4: view_factors of 5 bumpy spheres (49,704 triangles) x 1000 rays per triangle into a UInt32 matrix resident in HBM.
     N > 1: every rank holds the (replicated) scene and computes its own interleaved share of the source rows, no exchange (SURVEY 8e);
@@ -457,6 +480,11 @@ def main():
     extras = None
     if vf is not None:
         extras = dict(vf, blas_build_ms_1M_triangles=min(build_dev_ms))
+        if world == 1:  # the instanced scene of BASELINE's target (a reported extra: it must never take the headline line down with it)
+            try:
+                extras.update(measure_instanced(rc, W, L, torch, dev, local))
+            except Exception as e:  # noqa: BLE001
+                extras["instanced_error"] = repr(e)
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:  # the CPU baseline is an N = 1 figure (torchrun also pins OMP_NUM_THREADS=1)
