@@ -53,6 +53,7 @@ struct rc_context {
     size_t cap_rays = 0, cap_hits = 0;
     static const int NEV = 8;
     cudaEvent_t ev_h2d[NEV], ev_k[NEV], ev_t0 = nullptr, ev_t1 = nullptr;
+    cudaEvent_t ev_pc_src[2] = {nullptr, nullptr}, ev_pc_done[2] = {nullptr, nullptr};  // rc_peer_copy_async's own pair (host-staged traces re-record ev_k / ev_h2d)
     float last_ms = 0.f, last_build_ms = 0.f;
     bool copy_pending[2] = {false, false};
     uint32_t last_launches = 0;
@@ -86,7 +87,28 @@ static inline void use_device(const rc_context *ctx) { cudaSetDevice(ctx->device
 #define RC_ENTER(ctx)  \
     use_device(ctx);   \
     std::lock_guard<std::recursive_mutex> rc_guard_((ctx)->mu)
+// host-state-only entry points (no GPU work): the lock alone.  Every entry point that reads or writes context state takes one of the two,
+// so a query thread interleaving with the (single) mutating thread never sees a half-updated handle table or a reallocating vector.
+#define RC_LOCK(ctx) std::lock_guard<std::recursive_mutex> rc_guard_(const_cast<rc_context *>(ctx)->mu)
 static int32_t builder_error_code(const std::string &err) { return err.find("supported range") != std::string::npos ? RC_ERR_INVALID_ARGUMENT : RC_ERR_CUDA; }
+
+// Stream-ordered temporaries of one entry point: returned to the pool when the call leaves scope, on every path (an RC_CUDA early
+// return included — the pool's release threshold is unbounded, so a leaked block would stay allocated for good).
+struct ApiTemps {
+    cudaStream_t st;
+    std::vector<void *> ptrs;
+    explicit ApiTemps(cudaStream_t s) : st(s) {}
+    ~ApiTemps() {
+        for (void *p : ptrs) cudaFreeAsync(p, st);
+    }
+    template <class T>
+    cudaError_t get(T **out, size_t bytes) {
+        void *p = nullptr;
+        cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 1, st);
+        if (e == cudaSuccess) { ptrs.push_back(p); *out = static_cast<T *>(p); }
+        return e;
+    }
+};
 
 static RcScene make_scene(const rc_context *ctx) {
     RcScene sc;
@@ -138,6 +160,10 @@ int32_t rc_create(int32_t device, rc_context **out) {
         CREATE_CK(cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
         CREATE_CK(cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming));
     }
+    for (int i = 0; i < 2; i++) {
+        CREATE_CK(cudaEventCreateWithFlags(&ctx->ev_pc_src[i], cudaEventDisableTiming));
+        CREATE_CK(cudaEventCreateWithFlags(&ctx->ev_pc_done[i], cudaEventDisableTiming));
+    }
     CREATE_CK(cudaEventCreate(&ctx->ev_t0));
     CREATE_CK(cudaEventCreate(&ctx->ev_t1));
     CREATE_CK(cudaMalloc(&ctx->d_work, sizeof(unsigned long long)));
@@ -173,6 +199,7 @@ int32_t rc_destroy(rc_context *ctx) {
     if (ctx->d_normal_ptrs) cudaFree(ctx->d_normal_ptrs);
     if (ctx->d_vf_row_pos) cudaFree(ctx->d_vf_row_pos);
     for (int i = 0; i < rc_context::NEV; i++) { cudaEventDestroy(ctx->ev_h2d[i]); cudaEventDestroy(ctx->ev_k[i]); }
+    for (int i = 0; i < 2; i++) { cudaEventDestroy(ctx->ev_pc_src[i]); cudaEventDestroy(ctx->ev_pc_done[i]); }
     cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1);
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->s_h2d); cudaStreamDestroy(ctx->s_d2h);
@@ -202,12 +229,13 @@ static int32_t build_blas_from(rc_context *ctx, const float *verts, uint32_t n_f
     const uint32_t *d_meta = face_meta;
     float *tmp_v = nullptr;
     uint32_t *tmp_m = nullptr;
+    ApiTemps tmp(ctx->stream);
     if (!(flags & RC_VERTS_ON_DEVICE)) {
-        RC_CUDA(ctx, cudaMallocAsync(&tmp_v, sizeof(float) * 9 * (size_t)n_faces, ctx->stream));
+        RC_CUDA(ctx, tmp.get(&tmp_v, sizeof(float) * 9 * (size_t)n_faces));
         RC_CUDA(ctx, cudaMemcpyAsync(tmp_v, verts, sizeof(float) * 9 * (size_t)n_faces, cudaMemcpyHostToDevice, ctx->stream));
         d_verts = tmp_v;
         if (face_meta) {
-            RC_CUDA(ctx, cudaMallocAsync(&tmp_m, sizeof(uint32_t) * (size_t)n_faces, ctx->stream));
+            RC_CUDA(ctx, tmp.get(&tmp_m, sizeof(uint32_t) * (size_t)n_faces));
             RC_CUDA(ctx, cudaMemcpyAsync(tmp_m, face_meta, sizeof(uint32_t) * (size_t)n_faces, cudaMemcpyHostToDevice, ctx->stream));
             d_meta = tmp_m;
         }
@@ -217,8 +245,6 @@ static int32_t build_blas_from(rc_context *ctx, const float *verts, uint32_t n_f
     bool ok = rc_build_blas(ctx->stream, d_verts, d_meta, n_faces, out, err);
     cudaEventRecord(ctx->ev_t1, ctx->stream);
     if (ok && cudaEventSynchronize(ctx->ev_t1) == cudaSuccess) cudaEventElapsedTime(&ctx->last_build_ms, ctx->ev_t0, ctx->ev_t1);
-    if (tmp_v) cudaFreeAsync(tmp_v, ctx->stream);
-    if (tmp_m) cudaFreeAsync(tmp_m, ctx->stream);
     if (!ok) {
         rc_free_blas(out, ctx->stream);
         if (err == "Geometry has no valid triangles") RC_FAIL(ctx, RC_ERR_NO_VALID_TRIANGLES, err);
@@ -271,6 +297,7 @@ static int32_t find_handle(rc_context *ctx, uint32_t handle, HandleInfo **out) {
 
 int32_t rc_delete(rc_context *ctx, uint32_t handle, int32_t *deleted) {  // :690-699
     if (!ctx) return RC_ERR_INVALID_ARGUMENT;
+    RC_LOCK(ctx);
     if (deleted) *deleted = 0;
     auto it = ctx->handles.find(handle);
     if (it == ctx->handles.end() || it->second.deleted) return RC_OK;
@@ -282,6 +309,7 @@ int32_t rc_delete(rc_context *ctx, uint32_t handle, int32_t *deleted) {  // :690
 
 int32_t rc_update_transforms(rc_context *ctx, uint32_t handle, const float *transforms, const float *inv_transforms, uint32_t m) {  // :755-797
     if (!ctx) return RC_ERR_INVALID_ARGUMENT;
+    RC_LOCK(ctx);
     HandleInfo *hi = nullptr;
     int32_t rc = find_handle(ctx, handle, &hi);
     if (rc != RC_OK) return rc;
@@ -447,8 +475,8 @@ static int32_t rebuild(rc_context *ctx) {  // rebuild_bvh! :962-993 + build_flat
 int32_t rc_sync(rc_context *ctx, int32_t *action) {  // sync!, :894-921
     if (!ctx) return RC_ERR_INVALID_ARGUMENT;
     if (action) *action = RC_SYNC_NONE;
-    if (!ctx->dirty && !ctx->transforms_dirty && ctx->built) return RC_OK;  // clean fast path: no GPU work, no sync (:898-900)
     RC_ENTER(ctx);
+    if (!ctx->dirty && !ctx->transforms_dirty && ctx->built) return RC_OK;  // clean fast path: no GPU work, no sync (:898-900)
     if (ctx->dirty || !ctx->built) {
         int32_t rc = rebuild(ctx);
         if (rc != RC_OK) return rc;
@@ -466,12 +494,18 @@ int32_t rc_sync(rc_context *ctx, int32_t *action) {  // sync!, :894-921
 // ------------------------------------------------------------------------------------------------ introspection
 int32_t rc_is_valid(const rc_context *ctx, uint32_t handle) {
     if (!ctx) return 0;
+    RC_LOCK(ctx);
     auto it = ctx->handles.find(handle);
     return it != ctx->handles.end() && !it->second.deleted;
 }
-uint32_t rc_n_total_instances(const rc_context *ctx) { return ctx ? (uint32_t)ctx->instances.size() : 0; }
+uint32_t rc_n_total_instances(const rc_context *ctx) {
+    if (!ctx) return 0;
+    RC_LOCK(ctx);
+    return (uint32_t)ctx->instances.size();
+}
 uint32_t rc_n_instances(const rc_context *ctx) {  // :2391-2398
     if (!ctx) return 0;
+    RC_LOCK(ctx);
     uint32_t pending = 0;
     for (auto &kv : ctx->handles)
         if (kv.second.deleted) pending += kv.second.count;
@@ -479,12 +513,18 @@ uint32_t rc_n_instances(const rc_context *ctx) {  // :2391-2398
 }
 uint32_t rc_n_instances_of(const rc_context *ctx, uint32_t handle) {
     if (!ctx) return 0;
+    RC_LOCK(ctx);
     auto it = ctx->handles.find(handle);
     return (it == ctx->handles.end() || it->second.deleted) ? 0 : it->second.count;
 }
-uint32_t rc_n_geometries(const rc_context *ctx) { return ctx ? (uint32_t)ctx->blas.size() : 0; }
+uint32_t rc_n_geometries(const rc_context *ctx) {
+    if (!ctx) return 0;
+    RC_LOCK(ctx);
+    return (uint32_t)ctx->blas.size();
+}
 int32_t rc_is_dirty(const rc_context *ctx, int32_t *dirty, int32_t *transforms_dirty) {
     if (!ctx) return RC_ERR_INVALID_ARGUMENT;
+    RC_LOCK(ctx);
     if (dirty) *dirty = ctx->dirty;
     if (transforms_dirty) *transforms_dirty = ctx->transforms_dirty;
     return RC_OK;
@@ -492,6 +532,7 @@ int32_t rc_is_dirty(const rc_context *ctx, int32_t *dirty, int32_t *transforms_d
 int32_t rc_get_instances(const rc_context *cctx, uint32_t handle, rc_instance_desc *out) {
     rc_context *ctx = const_cast<rc_context *>(cctx);
     if (!ctx || !out) return RC_ERR_INVALID_ARGUMENT;
+    RC_LOCK(ctx);
     HandleInfo *hi = nullptr;
     int32_t rc = find_handle(ctx, handle, &hi);
     if (rc != RC_OK) return rc;
@@ -500,6 +541,7 @@ int32_t rc_get_instances(const rc_context *cctx, uint32_t handle, rc_instance_de
 }
 int32_t rc_world_bound(const rc_context *ctx, float out[6]) {
     if (!ctx || !out) return RC_ERR_INVALID_ARGUMENT;
+    RC_LOCK(ctx);
     memcpy(out, ctx->tlas.root_aabb, 24);
     return RC_OK;
 }
@@ -513,6 +555,7 @@ int32_t rc_wait(rc_context *ctx) {
 }
 int32_t rc_sizes(const rc_context *ctx, uint32_t *tlas_nodes, uint32_t *blas_nodes, uint32_t *blas_prims, uint32_t *pending_deletes) {
     if (!ctx) return RC_ERR_INVALID_ARGUMENT;
+    RC_LOCK(ctx);
     if (tlas_nodes) *tlas_nodes = ctx->synced_tlas_nodes;
     if (blas_nodes) *blas_nodes = ctx->synced_blas_nodes;
     if (blas_prims) *blas_prims = ctx->n_flat_prims;
@@ -572,13 +615,16 @@ int32_t rc_read_blas_faces(rc_context *ctx, uint32_t blas_index, uint32_t *out, 
 }
 int32_t rc_get_instance_handles(const rc_context *ctx, uint32_t *out, uint32_t capacity) {
     if (!ctx || !out) return RC_ERR_INVALID_ARGUMENT;
+    RC_LOCK(ctx);
     if (capacity < ctx->instances.size()) return RC_ERR_INVALID_ARGUMENT;
     for (auto &kv : ctx->handles)
         for (uint32_t i = 0; i < kv.second.count; i++) out[kv.second.start + i] = kv.first;
     return RC_OK;
 }
 uint32_t rc_blas_n_prims(const rc_context *ctx, uint32_t blas_index) {
-    if (!ctx || blas_index < 1 || blas_index > ctx->blas.size()) return 0;
+    if (!ctx) return 0;
+    RC_LOCK(ctx);
+    if (blas_index < 1 || blas_index > ctx->blas.size()) return 0;
     return ctx->blas[blas_index - 1].n;
 }
 
@@ -700,20 +746,22 @@ static int32_t grid_common(rc_context *ctx, const float viewdir[3], uint32_t gri
     int32_t rc = require_synced(ctx);
     if (rc != RC_OK) return rc;
     if (!viewdir || grid == 0) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "viewdir / grid");
+    if (grid > 65535u) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "grid_size must be <= 65535 (grid^2 cells are indexed with 32 bits)");
     size_t n = (size_t)grid * grid;
     RcGridFrame f;
     rc_grid_frame(ctx->tlas.root_aabb, viewdir, grid, &f);
     rc_hit *d_hits = nullptr;
     float *d_points = nullptr, *d_illum = nullptr;
     double *d_cent = nullptr;
-    if (hits) RC_CUDA(ctx, cudaMallocAsync(&d_hits, n * sizeof(rc_hit), ctx->stream));
-    if (points) RC_CUDA(ctx, cudaMallocAsync(&d_points, n * 3 * sizeof(float), ctx->stream));
+    ApiTemps tmp(ctx->stream);
+    if (hits) RC_CUDA(ctx, tmp.get(&d_hits, n * sizeof(rc_hit)));
+    if (points) RC_CUDA(ctx, tmp.get(&d_points, n * 3 * sizeof(float)));
     if (illum) {
-        RC_CUDA(ctx, cudaMallocAsync(&d_illum, (size_t)n_illum * sizeof(float), ctx->stream));
+        RC_CUDA(ctx, tmp.get(&d_illum, (size_t)n_illum * sizeof(float)));
         RC_CUDA(ctx, cudaMemsetAsync(d_illum, 0, (size_t)n_illum * sizeof(float), ctx->stream));
     }
     if (centroid4) {
-        RC_CUDA(ctx, cudaMallocAsync(&d_cent, 4 * sizeof(double), ctx->stream));
+        RC_CUDA(ctx, tmp.get(&d_cent, 4 * sizeof(double)));
         RC_CUDA(ctx, cudaMemsetAsync(d_cent, 0, 4 * sizeof(double), ctx->stream));
     }
     rc_launch_grid_trace(ctx->stream, make_scene(ctx), f, d_hits, d_points, d_illum, n_illum, d_cent, ctx->d_overflow + 1, ctx->max_blocks);
@@ -722,8 +770,6 @@ static int32_t grid_common(rc_context *ctx, const float viewdir[3], uint32_t gri
     if (points) RC_CUDA(ctx, cudaMemcpyAsync(points, d_points, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     if (illum) RC_CUDA(ctx, cudaMemcpyAsync(illum, d_illum, (size_t)n_illum * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     if (centroid4) RC_CUDA(ctx, cudaMemcpyAsync(centroid4, d_cent, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    for (void *p : {(void *)d_hits, (void *)d_points, (void *)d_illum, (void *)d_cent})
-        if (p) cudaFreeAsync(p, ctx->stream);
     RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return check_overflow(ctx);
 }
@@ -776,8 +822,8 @@ int32_t rc_view_factors_strided(rc_context *ctx, uint32_t rays_per_triangle, uin
         RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "view_factors: row block exceeds the matrix");
     size_t bytes = (size_t)n_rows * n_cols * sizeof(uint32_t);
     uint32_t *d_out = out;
-    if (!(flags & RC_HITS_ON_DEVICE)) RC_CUDA(ctx, cudaMallocAsync(&d_out, bytes, ctx->stream));
-    RC_CUDA(ctx, cudaMemsetAsync(d_out, 0, bytes, ctx->stream));
+    ApiTemps tmp(ctx->stream);
+    if (!(flags & RC_HITS_ON_DEVICE)) RC_CUDA(ctx, tmp.get(&d_out, bytes));
     if (!ctx->vf_map_built) {  // once per synced scene: which flat primitive carries row r's metadata
         if (ctx->d_vf_row_pos) { cudaFree(ctx->d_vf_row_pos); ctx->d_vf_row_pos = nullptr; }
         RC_CUDA(ctx, cudaMalloc(&ctx->d_vf_row_pos, sizeof(uint32_t) * ((size_t)n_cols + 2)));
@@ -791,20 +837,19 @@ int32_t rc_view_factors_strided(rc_context *ctx, uint32_t rays_per_triangle, uin
     }
     const uint32_t *row_pos = ctx->vf_map_usable ? ctx->d_vf_row_pos : nullptr;
     unsigned long long *d_skipped = nullptr;
-    RC_CUDA(ctx, cudaMallocAsync(&d_skipped, 8, ctx->stream));
+    RC_CUDA(ctx, tmp.get(&d_skipped, 8));
     RC_CUDA(ctx, cudaMemsetAsync(d_skipped, 0, 8, ctx->stream));
+    // the timed region starts before the matrix is zeroed: view_factors allocates-and-zeros its result (src/kernels.jl:74-78), and
+    // clearing 9.9 GB (C4) is part of the job
     cudaEventRecord(ctx->ev_t0, ctx->stream);
+    RC_CUDA(ctx, cudaMemsetAsync(d_out, 0, bytes, ctx->stream));
     rc_launch_view_factors(ctx->stream, make_scene(ctx), ctx->d_flat, ctx->n_flat_blas, ctx->n_flat_prims, rays_per_triangle, seed, row_base, n_rows, n_cols, d_out,
                            nullptr, d_skipped, ctx->d_overflow + 1, ctx->max_blocks, ctx->d_work, row_pos, row_stride);
     cudaEventRecord(ctx->ev_t1, ctx->stream);
     ctx->last_launches = 2;
     unsigned long long sk = 0;
     RC_CUDA(ctx, cudaMemcpyAsync(&sk, d_skipped, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    if (!(flags & RC_HITS_ON_DEVICE)) {
-        RC_CUDA(ctx, cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-        cudaFreeAsync(d_out, ctx->stream);
-    }
-    cudaFreeAsync(d_skipped, ctx->stream);
+    if (!(flags & RC_HITS_ON_DEVICE)) RC_CUDA(ctx, cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     if (flags & RC_NO_SYNC) return RC_OK;
     RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaEventElapsedTime(&ctx->last_ms, ctx->ev_t0, ctx->ev_t1);
@@ -821,12 +866,12 @@ int32_t rc_view_factor_rays(rc_context *ctx, uint32_t rays_per_triangle, uint64_
     size_t n = (size_t)n_rows * rays_per_triangle;
     if (n == 0) return RC_OK;
     rc_ray *d_rays = nullptr;
-    RC_CUDA(ctx, cudaMallocAsync(&d_rays, n * sizeof(rc_ray), ctx->stream));
+    ApiTemps tmp(ctx->stream);
+    RC_CUDA(ctx, tmp.get(&d_rays, n * sizeof(rc_ray)));
     RC_CUDA(ctx, cudaMemsetAsync(d_rays, 0, n * sizeof(rc_ray), ctx->stream));
     rc_launch_view_factors(ctx->stream, make_scene(ctx), ctx->d_flat, ctx->n_flat_blas, ctx->n_flat_prims, rays_per_triangle, seed, row_base, n_rows, ctx->n_flat_prims,
                            nullptr, d_rays, nullptr, ctx->d_overflow + 1, ctx->max_blocks, ctx->d_work, nullptr, 1);
     RC_CUDA(ctx, cudaMemcpyAsync(out, d_rays, n * sizeof(rc_ray), cudaMemcpyDeviceToHost, ctx->stream));
-    cudaFreeAsync(d_rays, ctx->stream);
     RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return RC_OK;
 }
@@ -839,10 +884,10 @@ int32_t rc_read_flat_metadata(rc_context *ctx, uint32_t *out, uint32_t capacity)
     if (capacity < ctx->n_flat_prims) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "capacity too small");
     if (ctx->n_flat_prims == 0) return RC_OK;
     uint32_t *d = nullptr;
-    RC_CUDA(ctx, cudaMallocAsync(&d, sizeof(uint32_t) * ctx->n_flat_prims, ctx->stream));
+    ApiTemps tmp(ctx->stream);
+    RC_CUDA(ctx, tmp.get(&d, sizeof(uint32_t) * ctx->n_flat_prims));
     rc_launch_flat_metadata(ctx->stream, ctx->d_flat, ctx->n_flat_blas, ctx->n_flat_prims, d);
     RC_CUDA(ctx, cudaMemcpyAsync(out, d, sizeof(uint32_t) * ctx->n_flat_prims, cudaMemcpyDeviceToHost, ctx->stream));
-    cudaFreeAsync(d, ctx->stream);
     RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return RC_OK;
 }
@@ -857,10 +902,11 @@ int32_t rc_collide_instances(rc_context *ctx, rc_contact_pair *contacts, uint64_
     uint32_t n = ctx->tlas.n;
     if (n == 0) return RC_OK;
     uint32_t *d_counts = nullptr, *d_excl = nullptr, *d_tile = nullptr, *d_total = nullptr;
-    RC_CUDA(ctx, cudaMallocAsync(&d_counts, sizeof(uint32_t) * n, ctx->stream));
-    RC_CUDA(ctx, cudaMallocAsync(&d_excl, sizeof(uint32_t) * n, ctx->stream));
-    RC_CUDA(ctx, cudaMallocAsync(&d_tile, sizeof(uint32_t) * ((n + 2047) / 2048), ctx->stream));
-    RC_CUDA(ctx, cudaMallocAsync(&d_total, sizeof(uint32_t), ctx->stream));
+    ApiTemps tmp(ctx->stream);
+    RC_CUDA(ctx, tmp.get(&d_counts, sizeof(uint32_t) * n));
+    RC_CUDA(ctx, tmp.get(&d_excl, sizeof(uint32_t) * n));
+    RC_CUDA(ctx, tmp.get(&d_tile, sizeof(uint32_t) * ((n + 2047) / 2048)));
+    RC_CUDA(ctx, tmp.get(&d_total, sizeof(uint32_t)));
     rc_collide_count(ctx->stream, ctx->tlas, d_counts, ctx->d_overflow + 1);
     rc_exclusive_scan_u32(ctx->stream, d_counts, d_excl, n, d_tile, d_total);
     uint32_t total = 0;
@@ -869,12 +915,10 @@ int32_t rc_collide_instances(rc_context *ctx, rc_contact_pair *contacts, uint64_
     *n_contacts = total;
     if (contacts && capacity >= total && total > 0) {
         rc_contact_pair *d_c = nullptr;
-        RC_CUDA(ctx, cudaMallocAsync(&d_c, sizeof(rc_contact_pair) * (size_t)total, ctx->stream));
+        RC_CUDA(ctx, tmp.get(&d_c, sizeof(rc_contact_pair) * (size_t)total));
         rc_collide_write(ctx->stream, ctx->tlas, d_counts, d_excl, d_c, ctx->d_overflow + 1);
         RC_CUDA(ctx, cudaMemcpyAsync(contacts, d_c, sizeof(rc_contact_pair) * (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
-        cudaFreeAsync(d_c, ctx->stream);
     }
-    for (void *p : {(void *)d_counts, (void *)d_excl, (void *)d_tile, (void *)d_total}) cudaFreeAsync(p, ctx->stream);
     RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return check_overflow(ctx);
 }
@@ -913,15 +957,15 @@ int32_t rc_set_normals(rc_context *ctx, uint32_t handle, const float *normals, u
     if (!normals || n_faces != B.n_faces_in) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "rc_set_normals: need 9 floats for each of the " + std::to_string(B.n_faces_in) + " submitted faces");
     const float *d_in = normals;
     float *tmp = nullptr;
+    ApiTemps temps(ctx->stream);
     const size_t bytes = sizeof(float) * 9 * (size_t)n_faces;
     if (!(flags & RC_VERTS_ON_DEVICE)) {
-        RC_CUDA(ctx, cudaMallocAsync(&tmp, bytes, ctx->stream));
+        RC_CUDA(ctx, temps.get(&tmp, bytes));
         RC_CUDA(ctx, cudaMemcpyAsync(tmp, normals, bytes, cudaMemcpyHostToDevice, ctx->stream));
         d_in = tmp;
     }
     if (!B.normals) RC_CUDA(ctx, cudaMallocAsync(&B.normals, sizeof(float) * 9 * (size_t)B.n, ctx->stream));
     rc_launch_gather_normals(ctx->stream, B.tris, B.n, d_in, B.normals);
-    if (tmp) cudaFreeAsync(tmp, ctx->stream);
     RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the caller may reuse `normals` on return
     return RC_OK;
 }
@@ -1129,17 +1173,17 @@ int32_t rc_ipc_open(rc_context *ctx, const uint8_t handle[64], void **out) {
 int32_t rc_peer_copy_async(rc_context *ctx, void *dst, const void *src, size_t bytes, uint32_t slot) {
     if (!ctx || !dst || !src || slot > 1) return RC_ERR_INVALID_ARGUMENT;
     RC_ENTER(ctx);
-    RC_CUDA(ctx, cudaEventRecord(ctx->ev_k[slot], ctx->stream));
-    RC_CUDA(ctx, cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_k[slot], 0));
+    RC_CUDA(ctx, cudaEventRecord(ctx->ev_pc_src[slot], ctx->stream));
+    RC_CUDA(ctx, cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_pc_src[slot], 0));
     RC_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->s_d2h));
-    RC_CUDA(ctx, cudaEventRecord(ctx->ev_h2d[slot], ctx->s_d2h));
+    RC_CUDA(ctx, cudaEventRecord(ctx->ev_pc_done[slot], ctx->s_d2h));
     ctx->copy_pending[slot] = true;
     return RC_OK;
 }
 int32_t rc_stream_wait_copy(rc_context *ctx, uint32_t slot) {
     if (!ctx || slot > 1) return RC_ERR_INVALID_ARGUMENT;
     RC_ENTER(ctx);
-    if (ctx->copy_pending[slot]) RC_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[slot], 0));
+    if (ctx->copy_pending[slot]) RC_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_pc_done[slot], 0));
     return RC_OK;
 }
 

@@ -810,12 +810,12 @@ bool rc_blas_export(cudaStream_t st, const RcDeviceBlas &b, void *blob, uint64_t
     return true;
 }
 
-// structural check of an uploaded blob (rc_validate_blas_elem, rc_build_core.cuh): every reference stays inside the arrays,
-// so a damaged blob cannot send a traversal out of bounds
+// structural check of an uploaded blob (rc_validate_blas_elem, rc_build_core.cuh): every reference stays inside the arrays and no
+// cycle is reachable from a root, so a damaged blob can neither send a traversal out of bounds nor make it spin
 __global__ void k_validate_blas(const RcNode2 *__restrict__ nodes2, const RcNode4 *__restrict__ nodes4, const RcTri *__restrict__ tris, uint32_t n,
-                                uint32_t *__restrict__ bad) {
+                                uint32_t n_faces_in, uint32_t *__restrict__ bad) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t errs = rc_validate_blas_elem(i, nodes2, nodes4, tris, n, RC_BLAS_LEAF_MAX);
+    const uint32_t errs = rc_validate_blas_elem(i, nodes2, nodes4, tris, n, RC_BLAS_LEAF_MAX, n_faces_in);
     if (errs) atomicAdd(bad, errs);
 }
 
@@ -874,7 +874,7 @@ bool rc_blas_import(cudaStream_t st, const void *blob, uint64_t size, RcDeviceBl
     CK(cudaMemcpyAsync(out->hull, p + h.off_hull, sizeof(RcBox) * RC_HULL_BOXES, cudaMemcpyHostToDevice, st));
     if (h.has_normals) CK(cudaMemcpyAsync(out->normals, p + h.off_normals, sizeof(float) * 9 * n, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(d_bad, 0, 4, st));
-    k_validate_blas<<<cdiv((uint32_t)(2 * n), 256), 256, 0, st>>>(out->nodes2, out->nodes4, out->tris, h.n, d_bad);
+    k_validate_blas<<<cdiv((uint32_t)(2 * n), 256), 256, 0, st>>>(out->nodes2, out->nodes4, out->tris, h.n, h.n_faces_in, d_bad);
     uint32_t bad = 0;
     CK(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));  // the caller may release the blob on return

@@ -156,15 +156,24 @@ RC_HD RcNode4 rc_collapse_node(uint32_t idx, const RcBox *boxes, const RcTopo *t
 }
 
 // Structural check of one element of a BLAS (used on imported blobs): element i covers BVH2 node i+1, wide node i and triangle i.
-// Returns the number of references that leave the arrays: BVH2 internal nodes are 1..n-1 and leaves n..2n-1
-// (src/instanced-bvh.jl:1293-1295, leaf: child0 == INVALID_NODE, child1 = 1-based primitive); wide nodes in use are 1..max(1, n-1).
-RC_HD uint32_t rc_validate_blas_elem(uint32_t i, const RcNode2 *nodes2, const RcNode4 *nodes4, const RcTri *tris, uint32_t n, uint32_t leaf_max) {
+// Returns the number of violations.  Checked: (1) every reference stays inside its array — BVH2 internal nodes are 1..n-1 and leaves
+// n..2n-1 (src/instanced-bvh.jl:1293-1295, leaf: child0 == INVALID_NODE, child1 = 1-based primitive), wide nodes in use are
+// 1..max(1, n-1), leaf ranges lie inside the triangle array, prim_id < n, face_index < n_faces_in (rc_set_normals gathers by it);
+// (2) no cycle can be reached from either root: the two children of a BVH2 internal node are distinct and name it as their parent
+// and the root has none, so the 2n-2 child references reach 2n-2 distinct nodes and everything reachable from node 1 is a tree;
+// a wide node's node-children must be BVH2 descendants of it (the collapse opens at most three levels), so wide edges only go down
+// that tree.  A blob that passes cannot send a traversal out of bounds or into an endless loop.  Not checked (harmless for memory
+// safety and termination): that the boxes bound their subtrees and that prim_id values are distinct — import blobs you wrote.
+RC_HD uint32_t rc_validate_blas_elem(uint32_t i, const RcNode2 *nodes2, const RcNode4 *nodes4, const RcTri *tris, uint32_t n, uint32_t leaf_max,
+                                     uint32_t n_faces_in) {
     uint32_t errs = 0;
     const uint32_t n_nodes2 = 2u * n - 1u;
     if (i < n_nodes2) {
         const RcNode2 &nd = nodes2[i];
+        if (i == 0u && nd.parent != RC_INVALID) errs++;
         if (i + 1u < n) {
-            if (nd.child0 < 1u || nd.child0 > n_nodes2 || nd.child1 < 1u || nd.child1 > n_nodes2) errs++;
+            if (nd.child0 < 1u || nd.child0 > n_nodes2 || nd.child1 < 1u || nd.child1 > n_nodes2 || nd.child0 == nd.child1) errs++;
+            else if (nodes2[nd.child0 - 1u].parent != i + 1u || nodes2[nd.child1 - 1u].parent != i + 1u) errs++;
         } else if (nd.child0 != RC_INVALID || nd.child1 < 1u || nd.child1 > n) {
             errs++;
         }
@@ -179,10 +188,19 @@ RC_HD uint32_t rc_validate_blas_elem(uint32_t i, const RcNode2 *nodes2, const Rc
                 if ((c[k] & RC_TLAS_LEAF_TAG) == RC_TLAS_LEAF_TAG || count > leaf_max || start >= n || count > n - start) errs++;
             } else if (n == 1u || c[k] < 1u || c[k] > last) {
                 errs++;
+            } else {  // must hang below BVH2 node i: at most three parent steps lead from the child to i
+                uint32_t up = c[k];
+                bool below = false;
+                for (int s = 0; s < 3 && !below; s++) {
+                    up = nodes2[up - 1u].parent;
+                    if (up == i) below = true;
+                    else if (up < 1u || up > last) break;
+                }
+                if (!below) errs++;
             }
         }
     }
-    if (i < n && tris[i].prim_id >= n) errs++;
+    if (i < n && (tris[i].prim_id >= n || tris[i].face_index >= n_faces_in)) errs++;
     return errs;
 }
 

@@ -139,10 +139,23 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS) k_shadow_fixup(RcScene sc, S
     }
 }
 
+// Empty TLAS (every handle deleted, then sync!): nothing can occlude, so a ray is visible iff it is a real ray (t_max > 0).  The
+// scheduler kernel must not run here: there are no TLAS nodes to fetch (test/test_tlas_stress.jl:808-831 pins "empty => miss").
+template <class SRC>
+__global__ void k_shadow_empty(SRC source, unsigned long long n, uint8_t *__restrict__ visible) {
+    for (unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += (unsigned long long)gridDim.x * blockDim.x)
+        visible[g] = source.get(g).tmax > 0.0f ? 1 : 0;
+}
+
 // overflow: the context's counter words ([1] hard errors, [2] rays flagged for the fix-up pass)
 template <class SRC>
 static void launch_shadow(cudaStream_t st, const RcScene &sc, const SRC &source, unsigned long long total, uint8_t *d_visible, uint32_t *overflow, int max_blocks,
                           unsigned long long *work) {
+    if (sc.n_instances == 0) {
+        const unsigned long long want0 = (total + 255) / 256;
+        k_shadow_empty<SRC><<<(int)(want0 < 148ull * 16 ? want0 : 148ull * 16), 256, 0, st>>>(source, total, d_visible);
+        return;
+    }
     unsigned long long want = (total + RC_TRACE_THREADS - 1) / RC_TRACE_THREADS;
     const unsigned long long cap = sc.n_instances == 1u ? (unsigned long long)max_blocks * RC_MIN_BLOCKS_SINGLE / RC_MIN_BLOCKS : (unsigned long long)max_blocks;
     int blocks = (int)(want < cap ? want : cap);

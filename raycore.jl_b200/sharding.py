@@ -142,6 +142,9 @@ class PeerResultBuffer:
         return self.base.value + offset_bytes
 
     def fence(self):
+        """Everything this rank enqueued on the library context (trace stream and copy stream, on the context's own device — which need
+        not be torch's current device) has completed, on every rank."""
+        assert self._lib.rc_wait(self._ctx) == 0
         torch.cuda.synchronize()
         dist.barrier()
 
@@ -152,9 +155,17 @@ class PeerResultBuffer:
         return host
 
     def close(self):
-        if getattr(self, "base", None) is not None and self.base.value:
-            if self.rank == self.dst:
-                self._lib.rc_device_free(self._ctx, self.base)
-            else:
-                self._lib.rc_ipc_close(self._ctx, self.base)
+        """Collective: peers drain their work and unmap first, then the owner frees (a peer kernel or copy may still be writing into the
+        mapping until its rank has passed the first barrier)."""
+        if getattr(self, "base", None) is None:
+            return
+        mapped = bool(self.base.value)
+        self._lib.rc_wait(self._ctx)
+        if mapped and self.rank != self.dst:
+            self._lib.rc_ipc_close(self._ctx, self.base)
+            self.base = self._C.c_void_p()
+        if dist.is_initialized():
+            dist.barrier()
+        if mapped and self.rank == self.dst:
+            self._lib.rc_device_free(self._ctx, self.base)
             self.base = self._C.c_void_p()

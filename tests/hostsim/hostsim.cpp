@@ -33,6 +33,7 @@ struct HsTree {
 struct HsBlas {
     HsTree tree;
     std::vector<RcTri> tris;
+    uint32_t n_faces_in = 0;
 };
 
 struct HsScene {
@@ -162,6 +163,7 @@ void *hs_blas_build(const float *verts, uint32_t n_faces, const uint32_t *face_m
     }
     stable_sort_pairs(codes, idx);
     HsBlas *B = new HsBlas();
+    B->n_faces_in = n_faces;
     B->tris.resize(n);
     for (uint32_t j = 0; j < n; j++) B->tris[j] = tris_in[idx[j]];  // k_gather_tris
     build_tree(B->tree, codes, B->tris.data(), nullptr, RC_BLAS_LEAF_MAX);
@@ -305,7 +307,9 @@ uint32_t hs_check_wide(void *b) {
 
 // structural check used on imported blobs (rc_validate_blas_elem; the loop stands in for k_validate_blas).  corrupt: 0 none,
 // 1 wide-node child index past the last node, 2 leaf range past the triangle array, 3 BVH2 child out of range, 4 BVH2 leaf
-// primitive out of range, 5 triangle prim_id out of range, 6 TLAS-tagged reference inside a BLAS.  `where` picks the element.
+// primitive out of range, 5 triangle prim_id out of range, 6 TLAS-tagged reference inside a BLAS, 7 wide node naming itself as a child
+// (a cycle: the traversal would never end), 8 BVH2 node naming itself as a child, 9 triangle face_index past the submitted faces,
+// 10 wide child that is in range but not below its node.  `where` picks the element.
 uint32_t hs_validate_blas(void *b, int corrupt, uint32_t where) {
     HsBlas *B = (HsBlas *)b;
     HsTree &t = B->tree;
@@ -321,10 +325,14 @@ uint32_t hs_validate_blas(void *b, int corrupt, uint32_t where) {
         case 4: nodes2[n - 1 + where % n].child1 = n + 1; break;
         case 5: tris[where % n].prim_id = n; break;
         case 6: nodes4[w].child2 = RC_TLAS_LEAF_TAG | 0u; break;
+        case 7: nodes4[w].child0 = w; break;
+        case 8: if (n > 1) nodes2[where % (n - 1)].child0 = 1 + where % (n - 1); else nodes2[0].child0 = 1; break;
+        case 9: tris[where % n].face_index = B->n_faces_in; break;
+        case 10: nodes4[w].child3 = 1; break;  // the root is below no node
         default: break;
     }
     uint32_t bad = 0;
-    for (uint32_t i = 0; i < 2 * n; i++) bad += rc_validate_blas_elem(i, nodes2.data(), nodes4.data(), tris.data(), n, RC_BLAS_LEAF_MAX);
+    for (uint32_t i = 0; i < 2 * n; i++) bad += rc_validate_blas_elem(i, nodes2.data(), nodes4.data(), tris.data(), n, RC_BLAS_LEAF_MAX, B->n_faces_in);
     return bad;
 }
 

@@ -5,6 +5,7 @@ import pytest
 
 from engines import GpuEngine, OracleEngine
 from oracle import oracle as orc
+import raycore_b200 as rc
 from raycore_b200 import HIT_DTYPE, RAY_DTYPE
 from raycore_b200 import workloads as W
 from test_wavefront import flipped, random_normals, shadow_scene
@@ -152,3 +153,31 @@ def test_shadow_deep_trees_fixup():
     prim = W.make_rays(org, (-org / np.linalg.norm(org, axis=1, keepdims=True)).astype(F))
     pq = tl.queue(RAY_DTYPE, n).upload(prim)
     _pipeline(tl, oe, pq, np.array([[1.3e-3, 0.9e-3, 1.1e-3], [4.3, 4.6, 4.45]], F))  # off the 2^-k lattice the geometry sits on
+
+
+def test_wavefront_on_emptied_tlas():
+    """Every handle deleted, then sync!: closest_hit misses (test/test_tlas_stress.jl:808-831) and the shadow stages must not walk a
+    TLAS that has no nodes — a live shadow ray is visible, a dummy one is not."""
+    tl = rc.TLAS()
+    h = tl.push(W.bumpy_sphere(12), None)
+    tl.sync()
+    tl.delete(h)
+    tl.sync()
+    assert tl.n_instances() == 0
+    rays_q = tl.generate_primary_rays(16, 16, (0, 0, -3), 1.0, 1.0, jitter=False)
+    hits_q = tl.intersect_rays(rays_q)
+    assert (hits_q.download()["hit"] == 0).all()
+    lights = np.array([[0, 0, -1], [6, 0, 4.5]], F)
+    # staged: every primary ray missed, so every shadow ray is the dummy ray
+    sh_q = tl.generate_shadow_rays(rays_q, hits_q, lights)
+    assert (sh_q.download()["t_max"] == 0).all()
+    assert (tl.test_shadow_rays(sh_q).download() == 0).all()
+    assert (tl.shadow_visibility(rays_q, hits_q, lights).download() == 0).all()
+    # caller-made live shadow rays: nothing can occlude them
+    live = W.box_rays(256, 3, half=2.0)
+    live["t_max"] = 5.0
+    live["t_max"][::4] = 0.0
+    q = tl.queue(RAY_DTYPE, len(live)).upload(live)
+    vis = tl.test_shadow_rays(q).download()
+    assert np.array_equal(vis, (live["t_max"] > 0).astype(np.uint8))
+    tl.free()

@@ -108,7 +108,9 @@ def test_blob_structural_check_accepts_built_trees_and_catches_faults():
         hb = hs.HsBlas(verts)
         assert hb.validate() == 0
         for where in (0, 1, 7, 1000):
-            for corrupt in (2, 3, 4, 5, 6):
+            for corrupt in (2, 3, 4, 5, 6, 8, 9):
                 assert hb.validate(corrupt, where) >= 1, (hb.n, corrupt, where)
             if hb.n > 1:
-                assert hb.validate(1, where) >= 1, (hb.n, where)
+                # 1: child index past the last node; 7 / 10: references that stay in range but would make a traversal cycle
+                for corrupt in (1, 7, 10):
+                    assert hb.validate(corrupt, where) >= 1, (hb.n, corrupt, where)
