@@ -31,6 +31,10 @@ KEYS = [
 ]
 
 
+def num_time(v, u):
+    return float(v.replace(",", "")) * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(u.lower().replace("second", "s").replace("usecond", "us"), 1.0)
+
+
 def main():
     rep = sys.argv[1]
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -60,7 +64,11 @@ def main():
         import json
         json.dump({"kernel": d[col["Kernel Name"]][:80], "dram_bytes": num("dram__bytes_read.sum") + num("dram__bytes_write.sum"),
                    "dram_read_bytes": num("dram__bytes_read.sum"), "dram_write_bytes": num("dram__bytes_write.sum"),
-                   "rays_per_launch": int(sys.argv[4]), "source": rep}, open(sys.argv[3], "w"))
+                   "rays_per_launch": int(sys.argv[4]), "source": rep,
+                   "issue_active_pct": float(d[col["smsp__issue_active.avg.pct_of_peak_sustained_active"]].replace(",", "")),
+                   "alu_pct": float(d[col["sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"]].replace(",", "")),
+                   "lanes_per_inst": float(d[col["smsp__thread_inst_executed_per_inst_executed.ratio"]].replace(",", "")),
+                   "kernel_ms_under_ncu": num_time(d[col["gpu__time_duration.sum"]], units[col["gpu__time_duration.sum"]])}, open(sys.argv[3], "w"))
     text = "\n".join(out)
     print(text)
     if len(sys.argv) > 2:
