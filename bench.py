@@ -284,7 +284,7 @@ def measure_c2(rc, W, L, torch, dev, local):
         assert lib.rc_trace_closest(ctx, d_r.data_ptr(), d_h.data_ptr(), n, fl) == 0, lib.rc_last_error(ctx)
         ms.append(float(lib.rc_last_kernel_ms(ctx)))
     k_ms = min(ms[1:])
-    hit_rate = float((d_h.view(torch.int32)[::8] == 1).float().mean().item())
+    hit_rate = int((d_h.view(torch.int32)[::8] == 1).sum().item()) / n
     m = 1 << 20
     lib.rc_get_counters(ctx, (C.c_uint64 * 6)(), 1)
     assert lib.rc_trace_closest(ctx, d_r.data_ptr(), d_h.data_ptr(), m, fl | L.RC_COUNTERS) == 0
@@ -486,7 +486,8 @@ def main():
         assert lib.rc_trace_closest(ctx, d_rays.data_ptr(), d_hits.data_ptr(), n, dev_flags) == 0, lib.rc_last_error(ctx)
         kern_ms.append(float(lib.rc_last_kernel_ms(ctx)))
     k_ms = min(kern_ms[1:])
-    hit_rate = float((d_hits.view(torch.int32)[::8] == 1).float().mean().item())
+    n_hit = int((d_hits.view(torch.int32)[::8] == 1).sum().item())
+    hit_rate = n_hit / n
 
     for _ in range(max(3, args.warmup)):
         step()
@@ -551,7 +552,7 @@ def main():
             t = torch.tensor([e_s, pcie_s], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e_s, pcie_s = float(t[0].item()), float(t[1].item())
-        assert float((h_hits.view(torch.int32)[::8] == 1).float().mean().item()) == hit_rate
+        assert int((h_hits.view(torch.int32)[::8] == 1).sum().item()) == n_hit, "host-buffer trace and device-resident trace disagree"
         e2e = {"value": total * e_steps / e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": total * 32, "d2h_bytes_per_step": total * 32, "steps": e_steps,
                "host_link_roof": {"Mrays_s": total / pcie_s / 1e6, "GBs_each_way": total * 32 / pcie_s / 1e9,
                                   "how": "the same pinned buffers copied H2D and D2H concurrently by every rank with no kernel in between (max over ranks): what the box's host links give at 32 + 32 B per ray"},

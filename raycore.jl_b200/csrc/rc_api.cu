@@ -445,7 +445,7 @@ static int32_t rebuild(rc_context *ctx) {  // rebuild_bvh! :962-993 + build_flat
     uint32_t off = 0, nodes = 0;
     for (size_t b = 0; b < ctx->blas.size(); b++) {
         const RcDeviceBlas &B = ctx->blas[b];
-        ptrs[b] = RcBlasPtrs{B.nodes2, B.nodes4, B.tris, B.hull, B.n, 0};
+        ptrs[b] = RcBlasPtrs{B.nodes2, B.nodes4, B.tris, B.hull, B.n, 0, {B.sphere[0], B.sphere[1], B.sphere[2], B.sphere[3]}};
         memcpy(&roots[6 * b], B.root_aabb, 24);
         flat[b] = RcFlatBlas{B.tris, off, B.n};
         off += B.n;

@@ -318,12 +318,23 @@ __global__ void k_morton_prims(const RcBox *__restrict__ tri_boxes, uint32_t n, 
     idx[i] = i;
 }
 
-__global__ void k_gather_tris(const RcTri *__restrict__ tris_in, const uint32_t *__restrict__ perm, uint32_t n, RcTri *__restrict__ tris) {
+// sorted triangle j = tris_in[perm[j]]; also the bounding-sphere radius^2 about the centre of the scene bounds (bits of a
+// non-negative float order like the float: one atomicMax per warp)
+__global__ void k_gather_tris(const RcTri *__restrict__ tris_in, const uint32_t *__restrict__ perm, uint32_t n, RcTri *__restrict__ tris,
+                              const uint32_t *__restrict__ bounds, uint32_t *__restrict__ r2_bits) {
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    const float4 *s = reinterpret_cast<const float4 *>(tris_in + perm[j]);
-    float4 *d = reinterpret_cast<float4 *>(tris + j);
-    d[0] = s[0]; d[1] = s[1]; d[2] = s[2];
+    float r2 = 0.0f;
+    if (j < n) {
+        const float4 *s = reinterpret_cast<const float4 *>(tris_in + perm[j]);
+        float4 *d = reinterpret_cast<float4 *>(tris + j);
+        const float4 a = s[0], b = s[1], c = s[2];
+        d[0] = a; d[1] = b; d[2] = c;
+        const f3 ctr = mk3(0.5f * (rc_ordered_to_float(bounds[0]) + rc_ordered_to_float(bounds[3])), 0.5f * (rc_ordered_to_float(bounds[1]) + rc_ordered_to_float(bounds[4])),
+                           0.5f * (rc_ordered_to_float(bounds[2]) + rc_ordered_to_float(bounds[5])));
+        r2 = rc_far2(ctr, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z));
+    }
+    const uint32_t m = __reduce_max_sync(0xFFFFFFFFu, r2 == r2 ? __float_as_uint(r2) : 0x7F800000u);  // NaN vertices: infinite radius (no cull)
+    if ((threadIdx.x & 31u) == 0) atomicMax(r2_bits, m);
 }
 
 // =================================================================================================
@@ -442,9 +453,17 @@ __global__ void k_blas_hull(const RcBox *__restrict__ boxes, const RcTopo *__res
     }
 }
 
-__global__ void k_read_root(const RcBox *__restrict__ boxes, float *__restrict__ out6) {
+// out6 = root box; sphere4 (nullable) = (centre of the scene bounds, radius^2 inflated against the rounding of its own evaluation)
+__global__ void k_read_root(const RcBox *__restrict__ boxes, float *__restrict__ out6, const uint32_t *__restrict__ bounds = nullptr,
+                            const uint32_t *__restrict__ r2_bits = nullptr, float *__restrict__ sphere4 = nullptr) {
     if (threadIdx.x < 3) out6[threadIdx.x] = boxes[0].lo[threadIdx.x];
     else if (threadIdx.x < 6) out6[threadIdx.x] = boxes[0].hi[threadIdx.x - 3];
+    else if (sphere4 && threadIdx.x < 9) {
+        const int k = threadIdx.x - 6;
+        sphere4[k] = 0.5f * (rc_ordered_to_float(bounds[k]) + rc_ordered_to_float(bounds[3 + k]));
+    } else if (sphere4 && threadIdx.x == 9) {
+        sphere4[3] = __uint_as_float(*r2_bits) * 1.000002f;
+    }
 }
 
 // codes (sorted) -> topology, fit, BVH2, BVH4
@@ -534,7 +553,7 @@ bool rc_build_blas(cudaStream_t st, const float *d_verts, const uint32_t *d_face
     TMP(d_flags, n_faces);
     TMP(d_pos, n_faces);
     TMP(d_tile, cdiv(n_faces, SCAN_TILE));
-    TMP(d_small, 16);  // [0] = valid count, [4..9] = scene bounds (ordered uints), [10..15] = root box
+    TMP(d_small, 24);  // [0] = valid count, [1] = sphere radius^2 bits, [4..9] = scene bounds (ordered uints), [10..15] = root box, [16..19] = sphere
     k_face_flags<<<cdiv(n_faces, T), T, 0, st>>>(d_verts, n_faces, d_flags);
     exclusive_scan_u32(st, d_flags, d_pos, n_faces, d_tile, d_small);
     uint32_t n = 0;
@@ -570,13 +589,17 @@ bool rc_build_blas(cudaStream_t st, const float *d_verts, const uint32_t *d_face
     k_compact_faces<<<cdiv(n_faces, T), T, 0, st>>>(d_verts, d_face_meta, d_flags, d_pos, n_faces, d_tris_in, d_tri_boxes, d_bounds);
     k_morton_prims<<<cdiv(n, T), T, 0, st>>>(d_tri_boxes, n, d_bounds, d_codes, d_idx);
     radix_sort_pairs(st, d_codes, d_idx, d_codes2, d_idx2, n, d_hist);
-    k_gather_tris<<<cdiv(n, T), T, 0, st>>>(d_tris_in, d_idx, n, out->tris);
+    cudaMemsetAsync(d_small + 1, 0, 4, st);
+    k_gather_tris<<<cdiv(n, T), T, 0, st>>>(d_tris_in, d_idx, n, out->tris, d_bounds, d_small + 1);
     build_tree(st, d_codes, n, out->tris, nullptr, nullptr, RC_BLAS_LEAF_MAX, d_topo, d_parent, d_fl, d_boxes, out->nodes2, out->nodes4);
     k_blas_hull<<<1, 32, 0, st>>>(d_boxes, d_topo, n, out->hull);
-    k_read_root<<<1, 32, 0, st>>>(d_boxes, reinterpret_cast<float *>(d_small + 10));
-    CK(cudaMemcpyAsync(out->root_aabb, d_small + 10, 24, cudaMemcpyDeviceToHost, st));
+    k_read_root<<<1, 32, 0, st>>>(d_boxes, reinterpret_cast<float *>(d_small + 10), d_bounds, d_small + 1, reinterpret_cast<float *>(d_small + 16));
+    float h_out[10];
+    CK(cudaMemcpyAsync(h_out, d_small + 10, 40, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
+    memcpy(out->root_aabb, h_out, 24);
+    memcpy(out->sphere, h_out + 6, 16);
     return extent_supported(out->root_aabb, err);
 }
 
@@ -640,6 +663,7 @@ __global__ void k_instance_records(const rc_instance_desc *__restrict__ inst, co
     for (int k = 0; k < 12; k++) r.inv[k] = d->inv_transform[k];
     r.nodes4 = b.nodes4;
     r.tris = b.tris;
+    for (int k = 0; k < 4; k++) { r.sphere[k] = b.sphere[k]; r.pad[k] = 0.f; }
     rec[i] = r;
     RcInstanceAux a;
     a.nodes2 = b.nodes2;
@@ -741,7 +765,7 @@ struct RcBlobHeader {
     float root_aabb[6];
     uint64_t total_bytes, payload_hash;
     uint64_t off_nodes2, off_nodes4, off_tris, off_hull, off_normals;  // from the blob start
-    uint8_t pad[16];
+    float sphere[4];  // bounding sphere (centre, radius^2) of the instance-entry cull
 };
 static_assert(sizeof(RcBlobHeader) == 128, "blob header is 128 bytes");
 static const char RC_BLOB_MAGIC[8] = {'R', 'C', 'B', 'L', 'A', 'S', 0, 1};
@@ -791,6 +815,7 @@ bool rc_blas_export(cudaStream_t st, const RcDeviceBlas &b, void *blob, uint64_t
     h.n_faces_in = b.n_faces_in;
     h.has_normals = b.normals ? 1u : 0u;
     memcpy(h.root_aabb, b.root_aabb, 24);
+    memcpy(h.sphere, b.sphere, 16);
     blob_layout(b.n, b.normals != nullptr, &h);
     if (capacity < h.total_bytes) { err = "export: capacity too small"; return false; }
     uint8_t *p = static_cast<uint8_t *>(blob);
@@ -868,6 +893,7 @@ bool rc_blas_import(cudaStream_t st, const void *blob, uint64_t size, RcDeviceBl
     out->n = h.n;
     out->n_faces_in = h.n_faces_in;
     memcpy(out->root_aabb, h.root_aabb, 24);
+    memcpy(out->sphere, h.sphere, 16);
     CK(cudaMemcpyAsync(out->nodes2, p + h.off_nodes2, sizeof(RcNode2) * (2 * n - 1), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(out->nodes4, p + h.off_nodes4, sizeof(RcNode4) * (n + 1), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(out->tris, p + h.off_tris, sizeof(RcTri) * n, cudaMemcpyHostToDevice, st));

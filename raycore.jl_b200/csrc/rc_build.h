@@ -1,6 +1,7 @@
 // rc_build.h — library-internal interface of the GPU builder (rc_build.cu)
 #pragma once
 #include <cuda_runtime.h>
+#include <math.h>
 
 #include <string>
 #include <vector>
@@ -19,6 +20,7 @@ struct RcDeviceBlas {
     RcBox *hull = nullptr;      // RC_HULL_BOXES boxes of BVH2 subtrees covering the whole BLAS (tight instance bounds for the wide TLAS)
     float *normals = nullptr;   // optional, 9 floats per primitive indexed by primitive_id (rc_set_normals; shading-side data of the wavefront stages)
     float root_aabb[6] = {0, 0, 0, 0, 0, 0};
+    float sphere[4] = {0, 0, 0, INFINITY};  // bounding sphere in local space: centre = centre of the root box, radius^2 over all vertices (instance-entry cull)
 };
 
 #define RC_HULL_BOXES 16
@@ -29,6 +31,7 @@ struct RcBlasPtrs {  // device-visible BLAS table entry
     const RcTri *tris;
     const RcBox *hull;  // RC_HULL_BOXES entries (unused ones are empty boxes)
     uint32_t n, pad;
+    float sphere[4];
 };
 
 struct RcDeviceTlas {

@@ -56,6 +56,14 @@ RC_HD float rc_half_area(const RcBox &b) {
     return dx * dy + dy * dz + dz * dx;
 }
 
+// squared distance from c to the farthest of three vertices (bounding-sphere radius of the instance-entry cull)
+RC_HD float rc_far2(f3 c, f3 a, f3 b, f3 v) {
+    const float da = (a.x - c.x) * (a.x - c.x) + (a.y - c.y) * (a.y - c.y) + (a.z - c.z) * (a.z - c.z);
+    const float db = (b.x - c.x) * (b.x - c.x) + (b.y - c.y) * (b.y - c.y) + (b.z - c.z) * (b.z - c.z);
+    const float dv = (v.x - c.x) * (v.x - c.x) + (v.y - c.y) * (v.y - c.y) + (v.z - c.z) * (v.z - c.z);
+    return fmaxf(da, fmaxf(db, dv));
+}
+
 // Smallest biased exponent e with 255 * 2^(e-127) >= extent
 RC_HD uint32_t rc_quant_exponent(float extent) {
     if (!(extent > 0.0f)) return 1u;

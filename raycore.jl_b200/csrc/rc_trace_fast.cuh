@@ -84,6 +84,11 @@ __device__ __forceinline__ void rc_store_hit(rc_hit *hits, unsigned long long i,
 #ifndef RC_X_W
 #define RC_X_W 3u
 #endif
+// RC_PARK_INSTANCE: a lane that reaches an instance leaf parks it and keeps walking the TLAS (as it parks a BLAS leaf); the level step
+// enters the parked instance — or drops it when the bounding-sphere test culls the entry, in which case the TLAS walk was never interrupted.
+#ifndef RC_PARK_INSTANCE
+#define RC_PARK_INSTANCE 0
+#endif
 #ifndef RC_MIN_BLOCKS
 #define RC_MIN_BLOCKS 8     // 64 registers -> 32 resident warps per SM (swept 6..10 in r1: 8 is best, 9+ spills)
 #endif
@@ -152,6 +157,47 @@ __device__ __forceinline__ float2 rc_q2f_pair(uint32_t w, int j) {
     return __half22float2(*reinterpret_cast<const __half2 *>(&h));
 }
 
+// Two FMAs per issue slot: fma.rn.f32x2 (FFMA2 on sm_100a) with the scale and offset broadcast from scalar registers
+// (SASS: FFMA2 R8, R8.F32x2.HI_LO, R0.F32, R13.F32).  The node step is issue / ALU bound (profiles/r1_trace_c3_v20: issue slots 80 %,
+// FMA pipe 32 %), so halving the 24 slab FMAs' issue slots is free throughput.  Each component is an IEEE RN fma, same bits as fmaf.
+#ifndef RC_FFMA2
+#define RC_FFMA2 1
+#endif
+__device__ __forceinline__ float2 rc_fma2(float2 q, float a, float b) {
+#if defined(RC_WARPSIM) || !RC_FFMA2
+    return make_float2(fmaf(q.x, a, b), fmaf(q.y, a, b));
+#else
+    unsigned long long qq, aa, bb, r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(qq) : "f"(q.x), "f"(q.y));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(a));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(bb) : "f"(b));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(qq), "l"(aa), "l"(bb));
+    float2 o;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(o.x), "=f"(o.y) : "l"(r));
+    return o;
+#endif
+}
+
+// Instance-entry cull (level step): does the local-space ray (o, d) miss the BLAS's bounding sphere (c, r2)?  Conservative: the
+// closest approach l = oc - (oc.d / d.d) d is evaluated in the cancellation-free form (Haines et al., "Precision improvements for
+// ray / sphere intersection"), its rounding error is bounded by ~4 ulp(|oc|), and the comparison carries 1.1e-6 (r2 + |oc|^2) of slack
+// (2 r delta + delta^2 <= 1e-6 (r2 + oc2) for delta = 1e-6 |oc|).  NaN / Inf anywhere makes every comparison false: no cull.
+#ifndef RC_SPHERE_CULL
+#define RC_SPHERE_CULL 1
+#endif
+__device__ __forceinline__ bool rc_misses_sphere(f3 o, f3 d, float4 sph, float t_max) {
+    const float ocx = o.x - sph.x, ocy = o.y - sph.y, ocz = o.z - sph.z;
+    const float a = fmaf(d.x, d.x, fmaf(d.y, d.y, d.z * d.z));
+    const float b = fmaf(ocx, d.x, fmaf(ocy, d.y, ocz * d.z));
+    const float oc2 = fmaf(ocx, ocx, fmaf(ocy, ocy, ocz * ocz));
+    const float s = __fdividef(b, a);  // ray parameter of the closest approach is -s
+    const float lx = fmaf(-s, d.x, ocx), ly = fmaf(-s, d.y, ocy), lz = fmaf(-s, d.z, ocz);
+    const float l2 = fmaf(lx, lx, fmaf(ly, ly, lz * lz));
+    const float r2s = fmaf(1.1e-6f, sph.w + oc2, sph.w);
+    // the line misses the sphere, or the origin is outside and the closest approach lies behind it (b > 0: moving away)
+    return l2 > r2s || (oc2 > r2s && b > 0.0f);
+}
+
 // Ray source / hit sink of the batched entry points: RTRay array in, RTHitResult array out.
 struct RcIoArrays {
     // scheduler constants of the multi-instance variant for this ray source (see above): a cheap refill (one 32-B load) can run early
@@ -184,6 +230,9 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, SINGLE ? RC_MIN_BLOCKS_SINGL
     const RcTri *tris = nullptr;
     const RcNode4 *nodes = sc.tlas4;
     uint32_t cur = RC_INVALID, leaf = 0, leaf_k = 0, vote = RC_VOTE_F;
+#if RC_PARK_INSTANCE
+    uint32_t pinst = 0;  // parked instance leaf reference (0 = none)
+#endif
     bool have = false, ovf = false;
     // A TLAS with a single instance needs no top-level traversal: the refill step enters that instance directly and, with no
     // sentinel under the BLAS entries, the ray finishes when the stack bottom is popped (saves a node step and two level changes).
@@ -220,35 +269,64 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, SINGLE ? RC_MIN_BLOCKS_SINGL
 #define RC_SETTLE()                                                                                                \
     {                                                                                                              \
         RC_SETTLE_LEAVE()                                                                                          \
-        if (spa > sbase + RC_SSTACK * RC_ROW) { ovf = true; cur = RC_INVALID; leaf = 0; spa = sbase; }               \
+        if (spa > sbase + RC_SSTACK * RC_ROW) { ovf = true; cur = RC_INVALID; leaf = 0; spa = sbase; RC_CLEAR_PINST() } \
         const bool park_ = ((cur ^ RC_LEAF_BIT) < 0x40000000u) && leaf == 0; /* BLAS leaf reference */              \
         const uint32_t top_ = RC_TOP();                                                                            \
         leaf = park_ ? cur : leaf;                                                                                 \
         leaf_k = park_ ? 0u : leaf_k;                                                                              \
         cur = park_ ? top_ : cur;                                                                                  \
         spa -= park_ ? RC_ROW : 0;                                                                                 \
+        RC_SETTLE_VOTE()                                                                                           \
+    }
+    /* instance leaf = [0xC0000000, RC_SENTINEL); a sentinel still here waits for the parked leaf and is left by the T step's settle */
+#if RC_PARK_INSTANCE
+#define RC_CLEAR_PINST() pinst = 0;
+#define RC_SETTLE_VOTE()                                                                                           \
+        if (!SINGLE && cur_inst < 0 && pinst == 0 && (cur + 0x40000000u) < 0x2FFFFFFFu) {                          \
+            pinst = cur; cur = RC_TOP(); spa -= RC_ROW;                                                            \
+        }                                                                                                          \
+        vote = ((int)cur >= 0) ? RC_VOTE_N : 0u;                                                                   \
+        vote |= leaf ? RC_VOTE_T : ((cur == RC_INVALID && (SINGLE || pinst == 0)) ? RC_VOTE_F : 0u);               \
+        if (!SINGLE) vote |= (pinst != 0) ? RC_VOTE_X : 0u;
+#else
+#define RC_CLEAR_PINST()
+#define RC_SETTLE_VOTE()                                                                                           \
         vote = ((int)cur >= 0) ? RC_VOTE_N : 0u;                                                                   \
         vote |= leaf ? RC_VOTE_T : ((cur == RC_INVALID) ? RC_VOTE_F : 0u);                                         \
-        /* instance leaf = [0xC0000000, RC_SENTINEL); a sentinel still here waits for the parked leaf and is left by the T step's settle */ \
-        if (!SINGLE) vote |= ((cur + 0x40000000u) < 0x2FFFFFFFu) ? RC_VOTE_X : 0u;                                 \
-    }
+        if (!SINGLE) vote |= ((cur + 0x40000000u) < 0x2FFFFFFFu) ? RC_VOTE_X : 0u;
+#endif
 
-    // enter instance `index`: its world->local transform applied with the reference's exact arithmetic (:1961-1977)
-#define RC_ENTER_INSTANCE(index)                                                          \
+    // enter instance `index`: its world->local transform applied with the reference's exact arithmetic (:1961-1977).  `entered_` tells
+    // whether the lane really went in: with CULL, a ray whose local copy misses the BLAS's bounding sphere stays at the top level
+    // (o / d / inv / nodes untouched).
+#define RC_ENTER_INSTANCE(index, CULL, entered_)                                          \
     {                                                                                     \
-        cur_inst = (index);                                                               \
-        const char *ip_ = reinterpret_cast<const char *>(sc.inst + cur_inst);             \
+        const int inst_ = (index);                                                        \
+        const char *ip_ = reinterpret_cast<const char *>(sc.inst + inst_);                \
         float m_[12];                                                                     \
-        _Pragma("unroll") for (int k_ = 0; k_ < 3; k_++) {                                \
-            float4 r_ = __ldg(reinterpret_cast<const float4 *>(ip_) + k_);                \
-            m_[4 * k_] = r_.x; m_[4 * k_ + 1] = r_.y; m_[4 * k_ + 2] = r_.z; m_[4 * k_ + 3] = r_.w; \
+        float4 q0_, q1_, q2_, q3_;                                                        \
+        rc_ldg256(ip_, q0_, q1_);                                                         \
+        rc_ldg256(ip_ + 32, q2_, q3_);                                                    \
+        m_[0] = q0_.x; m_[1] = q0_.y; m_[2] = q0_.z; m_[3] = q0_.w;                       \
+        m_[4] = q1_.x; m_[5] = q1_.y; m_[6] = q1_.z; m_[7] = q1_.w;                       \
+        m_[8] = q2_.x; m_[9] = q2_.y; m_[10] = q2_.z; m_[11] = q2_.w;                     \
+        ulonglong2 pp_;                                                                   \
+        pp_.x = ((unsigned long long)__float_as_uint(q3_.y) << 32) | __float_as_uint(q3_.x); \
+        pp_.y = ((unsigned long long)__float_as_uint(q3_.w) << 32) | __float_as_uint(q3_.z); \
+        const f3 lo_ = x_transform_point(m_, wo);                                         \
+        const f3 ld_ = x_transform_direction(m_, wd);                                     \
+        entered_ = true;                                                                  \
+        if (CULL && RC_SPHERE_CULL) {                                                     \
+            const float4 sph_ = __ldg(reinterpret_cast<const float4 *>(ip_ + 64));        \
+            entered_ = !rc_misses_sphere(lo_, ld_, sph_, t_max);                          \
         }                                                                                 \
-        const ulonglong2 pp_ = __ldg(reinterpret_cast<const ulonglong2 *>(ip_ + 48));     \
-        nodes = reinterpret_cast<const RcNode4 *>(pp_.x);                                 \
-        tris = reinterpret_cast<const RcTri *>(pp_.y);                                    \
-        o = x_transform_point(m_, wo);                                                    \
-        d = x_transform_direction(m_, wd);                                                \
-        inv = rc_fast_inv3(d);                  \
+        if (entered_) {                                                                   \
+            cur_inst = inst_;                                                             \
+            nodes = reinterpret_cast<const RcNode4 *>(pp_.x);                             \
+            tris = reinterpret_cast<const RcTri *>(pp_.y);                                \
+            o = lo_; d = ld_;                                                             \
+            inv = rc_fast_inv3(d);                                                        \
+        }                                                                                 \
     }
 
     for (;;) {
@@ -293,7 +371,9 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, SINGLE ? RC_MIN_BLOCKS_SINGL
                     sbase[RC_ROW] = RC_INVALID;  // stack bottom: popping it ends the ray
                     spa = sbase + RC_ROW;
                     if (single) {  // straight into the only instance: no top-level node step, no sentinel, no return step
-                        RC_ENTER_INSTANCE(0)
+                        bool in_;
+                        RC_ENTER_INSTANCE(0, false, in_)
+                        (void)in_;
                         if (COUNT) lc.inst_entries++;
                     } else {
                         o = wo; d = wd;
@@ -303,6 +383,9 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, SINGLE ? RC_MIN_BLOCKS_SINGL
                     }
                     cur = 1;
                     leaf = 0;
+#if RC_PARK_INSTANCE
+                    pinst = 0;
+#endif
                     vote = RC_VOTE_N;
                     have = true;
                 }
@@ -333,10 +416,26 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, SINGLE ? RC_MIN_BLOCKS_SINGL
             // ---- X: enter an instance (TLAS leaf) --------------------------------------------------------------------------
             RC_SIM_STEP(2, vote & RC_VOTE_X)
             if (vote & RC_VOTE_X) {  // (the return to the TLAS happens in RC_SETTLE_LEAVE)
-                RC_ENTER_INSTANCE((int)(cur & RC_LEAF_START_MASK))
-                RC_PUSH_IF(true, RC_SENTINEL)
-                if (COUNT) { lc.inst_entries++; if (RC_DEPTH() > lc.max_stack) lc.max_stack = RC_DEPTH(); }
-                cur = 1;
+                bool in_;
+#if RC_PARK_INSTANCE
+                RC_ENTER_INSTANCE((int)(pinst & RC_LEAF_START_MASK), true, in_)
+                pinst = 0;
+                if (COUNT) { lc.inst_entries += in_ ? 1u : 0u; }
+                // entered: the interrupted TLAS reference and the sentinel go under the BLAS root; culled: the TLAS walk simply goes on
+                RC_PUSH_IF(in_, cur)
+                RC_PUSH_IF(in_, RC_SENTINEL)
+                if (COUNT && RC_DEPTH() > lc.max_stack) lc.max_stack = RC_DEPTH();
+                cur = in_ ? 1u : cur;
+#else
+                RC_ENTER_INSTANCE((int)(cur & RC_LEAF_START_MASK), true, in_)
+                if (COUNT) { lc.inst_entries += in_ ? 1u : 0u; }
+                // entered: the sentinel goes under the BLAS root; culled: the next TLAS reference is popped instead
+                const uint32_t top_x = RC_TOP();
+                RC_PUSH_IF(in_, RC_SENTINEL)
+                if (COUNT && RC_DEPTH() > lc.max_stack) lc.max_stack = RC_DEPTH();
+                cur = in_ ? 1u : top_x;
+                spa -= in_ ? 0 : RC_ROW;
+#endif
                 RC_SETTLE()
             }
         } else {
@@ -364,12 +463,12 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, SINGLE ? RC_MIN_BLOCKS_SINGL
                 float tn[4];
 #pragma unroll
                 for (int j = 0; j < 2; j++) {
-                    const float2 pnx = rc_q2f_pair(nx, j), pny = rc_q2f_pair(ny, j), pnz = rc_q2f_pair(nz, j);
-                    const float2 pfx = rc_q2f_pair(fx, j), pfy = rc_q2f_pair(fy, j), pfz = rc_q2f_pair(fz, j);
-                    const float lo0 = fmaxf(fmaxf(fmaf(pnx.x, ax, bx), fmaf(pny.x, ay, by)), fmaxf(fmaf(pnz.x, az, bz), t_min));
-                    const float hi0 = fminf(fminf(fmaf(pfx.x, ax, bx), fmaf(pfy.x, ay, by)), fmaf(pfz.x, az, bz));
-                    const float lo1 = fmaxf(fmaxf(fmaf(pnx.y, ax, bx), fmaf(pny.y, ay, by)), fmaxf(fmaf(pnz.y, az, bz), t_min));
-                    const float hi1 = fminf(fminf(fmaf(pfx.y, ax, bx), fmaf(pfy.y, ay, by)), fmaf(pfz.y, az, bz));
+                    const float2 tnx = rc_fma2(rc_q2f_pair(nx, j), ax, bx), tny = rc_fma2(rc_q2f_pair(ny, j), ay, by), tnz = rc_fma2(rc_q2f_pair(nz, j), az, bz);
+                    const float2 tfx = rc_fma2(rc_q2f_pair(fx, j), ax, bx), tfy = rc_fma2(rc_q2f_pair(fy, j), ay, by), tfz = rc_fma2(rc_q2f_pair(fz, j), az, bz);
+                    const float lo0 = fmaxf(fmaxf(tnx.x, tny.x), fmaxf(tnz.x, t_min));
+                    const float hi0 = fminf(fminf(tfx.x, tfy.x), tfz.x);
+                    const float lo1 = fmaxf(fmaxf(tnx.y, tny.y), fmaxf(tnz.y, t_min));
+                    const float hi1 = fminf(fminf(tfx.y, tfy.y), tfz.y);
                     tn[2 * j] = (lo0 <= fminf(hi0 + slack, t_hi)) ? lo0 : CUDART_INF_F;
                     tn[2 * j + 1] = (lo1 <= fminf(hi1 + slack, t_hi)) ? lo1 : CUDART_INF_F;
                 }
@@ -397,6 +496,8 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, SINGLE ? RC_MIN_BLOCKS_SINGL
 #undef RC_DEPTH
 #undef RC_ROW
 #undef RC_SETTLE
+#undef RC_SETTLE_VOTE
+#undef RC_CLEAR_PINST
 #undef RC_SETTLE_LEAVE
 #undef RC_ENTER_INSTANCE
     if (COUNT) {

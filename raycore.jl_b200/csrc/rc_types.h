@@ -50,11 +50,16 @@ struct __attribute__((aligned(16))) RcTri {
     float v2[3]; uint32_t face_index;
 };
 
-// Per-instance traversal record (64 B): world->local transform + the BLAS arrays it enters.
-struct __attribute__((aligned(16))) RcInstanceRec {
+// Per-instance traversal record (96 B, 32-B aligned: the transform + pointers move as two LDG.256, the sphere as one LDG.128 —
+// three L1 wavefronts per entering lane instead of five): world->local transform + the BLAS arrays it enters + the BLAS's bounding sphere in its own
+// (local) space.  A ray whose transformed copy misses that sphere cannot hit any triangle of the instance, so the level step culls
+// the entry before the BLAS walk starts (an instance's world AABB is ~2x the cross-section of a round mesh: profiles/README.md r2).
+struct __attribute__((aligned(32))) RcInstanceRec {
     float inv[12];           // Mat3x4f rows, src/instanced-bvh.jl:94
     const RcNode4 *nodes4;   // BLAS wide nodes (root = index 1)
     const RcTri *tris;
+    float sphere[4];         // centre xyz, radius^2 (conservative: every vertex lies inside); radius^2 = +Inf disables the test
+    float pad[4];
 };
 
 // Cold per-instance data (hit write-back and the reference-order path)

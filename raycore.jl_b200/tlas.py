@@ -57,7 +57,7 @@ BLOB_HEADER_DTYPE = np.dtype(
     [
         ("magic", "S8"), ("abi_version", "<u4"), ("leaf_max", "<u4"), ("hull_boxes", "<u4"), ("n", "<u4"), ("n_faces_in", "<u4"), ("has_normals", "<u4"),
         ("root_aabb", "<f4", 6), ("total_bytes", "<u8"), ("payload_hash", "<u8"),
-        ("off_nodes2", "<u8"), ("off_nodes4", "<u8"), ("off_tris", "<u8"), ("off_hull", "<u8"), ("off_normals", "<u8"), ("pad", "u1", 16),
+        ("off_nodes2", "<u8"), ("off_nodes4", "<u8"), ("off_tris", "<u8"), ("off_hull", "<u8"), ("off_normals", "<u8"), ("sphere", "<f4", 4),
     ]
 )  # RcBlobHeader, csrc/rc_build.cu
 assert BLOB_HEADER_DTYPE.itemsize == 128

@@ -34,6 +34,7 @@ struct HsBlas {
     HsTree tree;
     std::vector<RcTri> tris;
     uint32_t n_faces_in = 0;
+    float sphere[4] = {0, 0, 0, INFINITY};
 };
 
 struct HsScene {
@@ -167,6 +168,16 @@ void *hs_blas_build(const float *verts, uint32_t n_faces, const uint32_t *face_m
     B->tris.resize(n);
     for (uint32_t j = 0; j < n; j++) B->tris[j] = tris_in[idx[j]];  // k_gather_tris
     build_tree(B->tree, codes, B->tris.data(), nullptr, RC_BLAS_LEAF_MAX);
+    {   // bounding sphere of the instance-entry cull (k_gather_tris + k_read_root): centre of the scene bounds, farthest vertex
+        f3 ctr = mk3(0.5f * (smin.x + smax.x), 0.5f * (smin.y + smax.y), 0.5f * (smin.z + smax.z));
+        float r2 = 0.0f;
+        for (uint32_t j = 0; j < n; j++) {
+            const RcTri &t = B->tris[j];
+            float f = rc_far2(ctr, mk3(t.v0[0], t.v0[1], t.v0[2]), mk3(t.v1[0], t.v1[1], t.v1[2]), mk3(t.v2[0], t.v2[1], t.v2[2]));
+            r2 = f == f ? std::max(r2, f) : INFINITY;
+        }
+        B->sphere[0] = ctr.x; B->sphere[1] = ctr.y; B->sphere[2] = ctr.z; B->sphere[3] = r2 * 1.000002f;
+    }
     return B;
 }
 
@@ -198,6 +209,7 @@ void *hs_scene_build(void **blas, uint32_t n_blas, const rc_instance_desc *inst,
         memcpy(S->rec[i].inv, inst[i].inv_transform, 48);
         S->rec[i].nodes4 = B->tree.nodes4.data();
         S->rec[i].tris = B->tris.data();
+        memcpy(S->rec[i].sphere, B->sphere, 16);
         S->aux[i].nodes2 = B->tree.nodes2.data();
         S->aux[i].n_prims = B->tree.n;
         S->aux[i].custom_index = inst[i].instance_id;

@@ -28,6 +28,8 @@
 struct float2 { float x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
 struct alignas(16) ulonglong2 { unsigned long long x, y; };
+static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+static inline float __fdividef(float a, float b) { return a / b; }  // host stand-in; only the conservative sphere cull uses it
 static inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 struct __half2 { uint16_t x, y; };
 static inline float ws_half2float(uint16_t h) {  // IEEE binary16 -> binary32, exact (subnormals included)
