@@ -547,12 +547,12 @@ def main():
             assert lib.rc_trace_closest(ctx, h_rays.data_ptr(), h_hits.data_ptr(), n, 0) == 0
         barrier()
         e_s = time.perf_counter() - t0
-        pcie_s = measure_pcie(torch, dev, h_rays, h_hits, n * 32, barrier)
+        assert int((h_hits.view(torch.int32)[::8] == 1).sum().item()) == n_hit, "host-buffer trace and device-resident trace disagree"
+        pcie_s = measure_pcie(torch, dev, h_rays, h_hits, n * 32, barrier)  # (overwrites h_hits)
         if world > 1:
             t = torch.tensor([e_s, pcie_s], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e_s, pcie_s = float(t[0].item()), float(t[1].item())
-        assert int((h_hits.view(torch.int32)[::8] == 1).sum().item()) == n_hit, "host-buffer trace and device-resident trace disagree"
         e2e = {"value": total * e_steps / e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": total * 32, "d2h_bytes_per_step": total * 32, "steps": e_steps,
                "host_link_roof": {"Mrays_s": total / pcie_s / 1e6, "GBs_each_way": total * 32 / pcie_s / 1e9,
                                   "how": "the same pinned buffers copied H2D and D2H concurrently by every rank with no kernel in between (max over ranks): what the box's host links give at 32 + 32 B per ray"},

@@ -93,6 +93,12 @@ typedef struct rc_context rc_context; /* one mutable TLAS (src/instanced-bvh.jl:
 #define RC_COUNTERS 0x8u        /* accumulate per-ray work counters (rc_get_counters) — instrumented build of the same kernel */
 #define RC_VERTS_ON_DEVICE 0x10u /* rc_push / rc_update_geometry: verts (and face_meta) are device pointers */
 #define RC_NO_SYNC 0x20u        /* trace: do not cudaStreamSynchronize before returning (device buffers only) */
+/* build flags (rc_push / rc_update_geometry flags, or per context with rc_set_build_flags) */
+#define RC_BUILD_KEEP_BVH2 0x80u    /* also emit the reference-layout BVH2 (BVHNode2, src/instanced-bvh.jl:50-63) of the geometry: needed by
+                                       RC_MODE_REFERENCE_ORDER and rc_read_blas_nodes; the default build writes only what the fast path reads */
+#define RC_BUILD_ALLOW_REFIT 0x100u /* keep the radix-tree topology so a later vertex update can re-fit instead of rebuilding (24 B / triangle) */
+#define RC_UPDATE_REFIT 0x200u      /* rc_update_geometry: re-fit the kept topology to the new vertex positions when possible (same face
+                                       count, same degenerate faces, built with RC_BUILD_ALLOW_REFIT); otherwise rebuild */
 
 /* sync actions reported by rc_sync */
 enum { RC_SYNC_NONE = 0, RC_SYNC_REFIT = 1, RC_SYNC_REBUILD = 2 };
@@ -130,8 +136,16 @@ int32_t rc_update_transforms(rc_context *ctx, uint32_t handle, const float *tran
 /* the same with DEVICE-resident transform arrays (the `instance_buffer` use case of src/Raycore.jl:118-130: transforms written by
  * a caller's kernel); ordered after the work already enqueued on the context stream. */
 int32_t rc_update_transforms_device(rc_context *ctx, uint32_t handle, const float *d_transforms, const float *d_inv_transforms, uint32_t m);
-/* update!(tlas, handle, new_geometry) — src/instanced-bvh.jl:808-857: rebuild the handle's BLAS in place. */
+/* update!(tlas, handle, new_geometry) — src/instanced-bvh.jl:808-857: rebuild the handle's BLAS in place (the reference always
+ * rebuilds).  With RC_UPDATE_REFIT and a geometry built with RC_BUILD_ALLOW_REFIT the library keeps the radix tree and only re-fits
+ * boxes and wide nodes to the moved vertices (the refit kernel for mesh updates; test/test_mesh_update.jl:96-116 workload) when the face
+ * count and the set of degenerate faces are unchanged — results then equal a fresh build's wherever the hit is unique (the tree is the
+ * old frame's, so its quality degrades with large deformations).  *face_meta is ignored by a refit.  rc_last_update_refitted tells
+ * which path the last call took. */
 int32_t rc_update_geometry(rc_context *ctx, uint32_t handle, const float *verts, uint32_t n_faces, const uint32_t *face_meta, uint32_t flags);
+int32_t rc_last_update_refitted(const rc_context *ctx);
+/* build flags (RC_BUILD_*) OR-ed into every later rc_push / rc_update_geometry of this context */
+int32_t rc_set_build_flags(rc_context *ctx, uint32_t flags);
 /* sync!(tlas) — src/instanced-bvh.jl:894-921: no-op when clean, refit when only transforms changed,
  * else compact + rebuild; returns with the stream idle.  *action: RC_SYNC_*. */
 int32_t rc_sync(rc_context *ctx, int32_t *action);

@@ -31,6 +31,9 @@ RC_COUNTERS = 0x8
 RC_VERTS_ON_DEVICE = 0x10
 RC_NO_SYNC = 0x20
 RC_WAVE_NO_JITTER = 0x40
+RC_BUILD_KEEP_BVH2 = 0x80
+RC_BUILD_ALLOW_REFIT = 0x100
+RC_UPDATE_REFIT = 0x200
 RC_MAX_LIGHTS = 16
 
 RC_SYNC_NONE, RC_SYNC_REFIT, RC_SYNC_REBUILD = 0, 1, 2
@@ -66,7 +69,7 @@ NODE2_DTYPE = np.dtype(
 # every symbol include/raycore_cuda.h declares (tests check the library exports all of them)
 EXPORTS = [
     "rc_abi_version", "rc_create", "rc_destroy", "rc_last_error", "rc_stream", "rc_set_stream",
-    "rc_push", "rc_delete", "rc_update_transforms", "rc_update_transforms_device", "rc_update_geometry", "rc_sync",
+    "rc_push", "rc_delete", "rc_update_transforms", "rc_update_transforms_device", "rc_update_geometry", "rc_last_update_refitted", "rc_set_build_flags", "rc_sync",
     "rc_export_geometry", "rc_push_exported", "rc_check_exported",
     "rc_is_valid", "rc_n_instances", "rc_n_instances_of", "rc_n_total_instances", "rc_n_geometries", "rc_is_dirty",
     "rc_get_instances", "rc_world_bound", "rc_wait", "rc_sizes", "rc_read_tlas_nodes", "rc_read_blas_nodes",
@@ -117,6 +120,8 @@ def load():
         "rc_update_transforms": (i32, [vp, u32, vp, vp, u32]),
         "rc_update_transforms_device": (i32, [vp, u32, vp, vp, u32]),
         "rc_update_geometry": (i32, [vp, u32, vp, u32, vp, u32]),
+        "rc_last_update_refitted": (i32, [vp]),
+        "rc_set_build_flags": (i32, [vp, u32]),
         "rc_sync": (i32, [vp, pi32]),
         "rc_export_geometry": (i32, [vp, u32, vp, u64, C.POINTER(u64)]),
         "rc_push_exported": (i32, [vp, vp, u64, vp, vp, vp, u32, pu32]),

@@ -39,7 +39,8 @@ struct rc_context {
     std::vector<RcDeviceBlas> blas;           // blas_index b+1 <-> blas[b]
     std::vector<rc_instance_desc> instances;  // host mirror of tlas.instances
     std::map<uint32_t, HandleInfo> handles;   // ordered by id (Julia: Dict{TLASHandle,UnitRange})
-    bool dirty = true, transforms_dirty = false, built = false;
+    bool dirty = true, transforms_dirty = false, built = false, last_update_refitted = false;
+    uint32_t build_flags = 0;  // RC_BUILD_* defaults of this context (rc_set_build_flags; initialised from the RC_BUILD_FLAGS environment variable)
     uint32_t next_handle = 1;
     RcDeviceTlas tlas;
     RcFlatBlas *d_flat = nullptr;
@@ -178,6 +179,7 @@ int32_t rc_create(int32_t device, rc_context **out) {
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
     }
     ctx->max_blocks = rc_trace_max_blocks(device);
+    if (const char *e = getenv("RC_BUILD_FLAGS")) ctx->build_flags = (uint32_t)strtoul(e, nullptr, 0) & (RC_BUILD_KEEP_BVH2 | RC_BUILD_ALLOW_REFIT);
 #undef CREATE_CK
     *out = ctx;
     return RC_OK;
@@ -242,7 +244,7 @@ static int32_t build_blas_from(rc_context *ctx, const float *verts, uint32_t n_f
     }
     std::string err;
     cudaEventRecord(ctx->ev_t0, ctx->stream);
-    bool ok = rc_build_blas(ctx->stream, d_verts, d_meta, n_faces, out, err);
+    bool ok = rc_build_blas(ctx->stream, d_verts, d_meta, n_faces, (flags | ctx->build_flags) & (RC_BUILD_KEEP_BVH2 | RC_BUILD_ALLOW_REFIT), out, err);
     cudaEventRecord(ctx->ev_t1, ctx->stream);
     if (ok && cudaEventSynchronize(ctx->ev_t1) == cudaSuccess) cudaEventElapsedTime(&ctx->last_build_ms, ctx->ev_t0, ctx->ev_t1);
     if (!ok) {
@@ -349,8 +351,34 @@ int32_t rc_update_geometry(rc_context *ctx, uint32_t handle, const float *verts,
     if (rc != RC_OK) return rc;
     if (hi->count == 0) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "Handle has no instances");
     uint32_t blas_idx = ctx->instances[hi->start].blas_index;
+    ctx->last_update_refitted = false;
+    RcDeviceBlas &old = ctx->blas[blas_idx - 1];
+    if ((flags & RC_UPDATE_REFIT) && old.topo && verts && n_faces == old.n_faces_in) {
+        // the refit kernel for mesh updates: same faces, moved vertices -> re-fit the kept radix tree (leaf boxes, bottom-up fit, collapse)
+        const float *d_verts = verts;
+        float *tmp_v = nullptr;
+        ApiTemps tmp(ctx->stream);
+        if (!(flags & RC_VERTS_ON_DEVICE)) {
+            RC_CUDA(ctx, tmp.get(&tmp_v, sizeof(float) * 9 * (size_t)n_faces));
+            RC_CUDA(ctx, cudaMemcpyAsync(tmp_v, verts, sizeof(float) * 9 * (size_t)n_faces, cudaMemcpyHostToDevice, ctx->stream));
+            d_verts = tmp_v;
+        }
+        std::string err;
+        bool refitted = false;
+        cudaEventRecord(ctx->ev_t0, ctx->stream);
+        if (!rc_refit_blas(ctx->stream, d_verts, n_faces, &old, &refitted, err)) RC_FAIL(ctx, builder_error_code(err), err);
+        cudaEventRecord(ctx->ev_t1, ctx->stream);
+        if (refitted) {
+            if (cudaEventSynchronize(ctx->ev_t1) == cudaSuccess) cudaEventElapsedTime(&ctx->last_build_ms, ctx->ev_t0, ctx->ev_t1);
+            if (old.normals) { cudaFreeAsync(old.normals, ctx->stream); old.normals = nullptr; }  // rc_update_geometry drops the normals
+            ctx->last_update_refitted = true;
+            ctx->dirty = true;  // the root box moved: the TLAS is rebuilt over the same BLAS table at the next sync (update! marks dirty, :855)
+            return RC_OK;
+        }
+        // not refittable (the degenerate set changed): the triangles were overwritten in place, fall through to a rebuild from the new soup
+    }
     RcDeviceBlas nb;
-    rc = build_blas_from(ctx, verts, n_faces, face_meta, flags, &nb);
+    rc = build_blas_from(ctx, verts, n_faces, face_meta, flags | (old.nodes2 ? RC_BUILD_KEEP_BVH2 : 0u) | (old.topo ? RC_BUILD_ALLOW_REFIT : 0u), &nb);
     if (rc != RC_OK) {
         if (rc == RC_ERR_NO_VALID_TRIANGLES) ctx->last_error = "New geometry has no valid triangles";
         return rc;
@@ -358,6 +386,13 @@ int32_t rc_update_geometry(rc_context *ctx, uint32_t handle, const float *verts,
     rc_free_blas(&ctx->blas[blas_idx - 1], ctx->stream);
     ctx->blas[blas_idx - 1] = nb;
     ctx->dirty = true;
+    return RC_OK;
+}
+int32_t rc_last_update_refitted(const rc_context *ctx) { return ctx && ctx->last_update_refitted ? 1 : 0; }
+int32_t rc_set_build_flags(rc_context *ctx, uint32_t flags) {
+    if (!ctx) return RC_ERR_INVALID_ARGUMENT;
+    RC_LOCK(ctx);
+    ctx->build_flags = flags & (RC_BUILD_KEEP_BVH2 | RC_BUILD_ALLOW_REFIT);
     return RC_OK;
 }
 
@@ -587,6 +622,7 @@ int32_t rc_read_blas_nodes(rc_context *ctx, uint32_t blas_index, rc_bvh_node2 *o
     RC_ENTER(ctx);
     if (blas_index < 1 || blas_index > ctx->blas.size()) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "blas_index out of range");
     const RcDeviceBlas &B = ctx->blas[blas_index - 1];
+    if (!B.nodes2) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "this geometry was built without RC_BUILD_KEEP_BVH2: there is no BVH2 to read back");
     return read_nodes2(ctx, B.nodes2, 2 * B.n - 1, out, capacity);
 }
 int32_t rc_read_blas_order(rc_context *ctx, uint32_t blas_index, uint32_t *out, uint32_t capacity) {
@@ -659,6 +695,9 @@ static int32_t trace_common(rc_context *ctx, const rc_ray *rays, rc_hit *hits, u
     L.scene = make_scene(ctx);
     L.any = any;
     L.wide = !(flags & RC_MODE_REFERENCE_ORDER);
+    if (!L.wide)
+        for (const RcDeviceBlas &B : ctx->blas)
+            if (!B.nodes2) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "RC_MODE_REFERENCE_ORDER needs the reference-layout BVH2: build the geometry with RC_BUILD_KEEP_BVH2");
     L.count = flags & RC_COUNTERS;
     L.work = ctx->d_work;
     L.counters = ctx->d_counters;

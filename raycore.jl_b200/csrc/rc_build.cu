@@ -1,11 +1,12 @@
-// rc_build.cu — GPU LBVH builder for sm_100a: degenerate filter + compaction, scene bounds,
-// 30-bit Morton codes, hand-written stable LSD radix sort, Karras radix tree, atomic bottom-up fit,
-// reference-layout BVH2 emission and collapse to the quantised BVH4 the fast traversal uses.
+// rc_build.cu — GPU LBVH builder for sm_100a: degenerate filter + stable compaction (single pass, decoupled look-back), scene bounds,
+// 30-bit Morton codes, hand-written stable LSD radix sort (3 passes of 10 bits), Karras radix tree, block-local bottom-up fit,
+// collapse to the quantised BVH4 the fast traversal uses, optional reference-layout BVH2 emission.
 //
 // Replaces build_blas (src/instanced-bvh.jl:1376-1443), build_tlas_topology (:1485-1594),
 // refit_tlas! (:2197-2222) and kernels K0-K11 of src/instanced-bvh-kernels.jl.  Everything runs on
-// the caller's stream; the only device->host traffic is 4 B (valid-triangle count) + 24 B (root box)
-// per BLAS and 24 B per TLAS build/refit.
+// the caller's stream.  A BLAS build is 15 dependent launches with NO host round trip in the middle: the number of valid
+// triangles stays on the device (every kernel reads it from the build's control block), and the only device->host traffic is
+// one 44-byte read-back at the end (valid count, root box, bounding sphere).
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -27,8 +28,37 @@
 
 static inline uint32_t cdiv(uint64_t a, uint32_t b) { return (uint32_t)((a + b - 1) / b); }
 
+// Control block of one build (u32 words, zeroed by one memset): the builder's kernels communicate through it.
+//   [CTL_N] valid primitives   [CTL_R2] bits of the bounding-sphere radius^2   [CTL_BOUNDS..+6) scene bounds, encoded so that 0 is the
+//   identity of atomicMax: word k < 3 holds ~ordered(min_k), word 3+k holds ordered(max_k)   [CTL_TILE] tile ticket of k_filter
+//   [CTL_OUT..+10) floats read back by the host: root box (6), sphere (4)
+enum { CTL_N = 0, CTL_R2 = 1, CTL_BOUNDS = 2, CTL_TILE = 8, CTL_OUT = 16, CTL_WORDS = 32 };
+
+__device__ __forceinline__ f3 ctl_bounds_min(const uint32_t *ctl) {
+    return mk3(rc_ordered_to_float(~ctl[CTL_BOUNDS]), rc_ordered_to_float(~ctl[CTL_BOUNDS + 1]), rc_ordered_to_float(~ctl[CTL_BOUNDS + 2]));
+}
+__device__ __forceinline__ f3 ctl_bounds_max(const uint32_t *ctl) {
+    return mk3(rc_ordered_to_float(ctl[CTL_BOUNDS + 3]), rc_ordered_to_float(ctl[CTL_BOUNDS + 4]), rc_ordered_to_float(ctl[CTL_BOUNDS + 5]));
+}
+// the element count of a build: on the device (BLAS: written by k_filter) or a host constant (TLAS)
+__device__ __forceinline__ uint32_t count_of(const uint32_t *n_ptr, uint32_t n_host) { return n_ptr ? *n_ptr : n_host; }
+
+__device__ __forceinline__ uint32_t ld_relaxed(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed(uint32_t *p, uint32_t v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+// release-ordered counter bump: the stores before it are visible to whoever observes the new count (no L1 invalidation on this side,
+// unlike __threadfence(), which costs a CCTL.IVALL per call)
+__device__ __forceinline__ uint32_t atom_add_release(uint32_t *p, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.release.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+
 // =================================================================================================
-// Scan (exclusive, u32) — block tiles of 2048 + single-block scan of the tile sums
+// Scan (exclusive, u32) — block tiles of 2048 + single-block scan of the tile sums (used by the collision broad phase)
 // =================================================================================================
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
@@ -111,49 +141,59 @@ __global__ void k_scan_apply(const uint32_t *__restrict__ in, uint32_t n, const 
 }
 
 // out[i] = sum of in[0..i); *d_total = sum of all.  tile_tmp: >= cdiv(n, SCAN_TILE) words.
-static void exclusive_scan_u32(cudaStream_t st, const uint32_t *in, uint32_t *out, uint32_t n, uint32_t *tile_tmp, uint32_t *d_total) {
+void rc_exclusive_scan_u32(cudaStream_t st, const uint32_t *in, uint32_t *out, uint32_t n, uint32_t *tile_tmp, uint32_t *d_total) {
     uint32_t tiles = cdiv(n, SCAN_TILE);
     k_tile_sums<<<tiles, SCAN_THREADS, 0, st>>>(in, n, tile_tmp);
     k_scan_single<<<1, 1024, 0, st>>>(tile_tmp, tiles, d_total);
     k_scan_apply<<<tiles, SCAN_THREADS, 0, st>>>(in, n, tile_tmp, out);
 }
 
-void rc_exclusive_scan_u32(cudaStream_t st, const uint32_t *in, uint32_t *out, uint32_t n, uint32_t *tile_tmp, uint32_t *d_total) {
-    exclusive_scan_u32(st, in, out, n, tile_tmp, d_total);
-}
-
 // =================================================================================================
-// Stable LSD radix sort of (u32 key, u32 value) pairs, 8 bits per pass.
-//   per pass:  k_radix_hist   per-tile digit histogram            -> hist[digit * tiles + tile]
-//              k_scan_single  exclusive scan of the 256*tiles table (digit-major => global offsets)
-//              k_radix_scatter stable in-tile ranking (warp match_any) + scatter
+// Stable LSD radix sort of (u32 key, u32 value) pairs, 10 bits per pass: a 30-bit Morton code is three passes.
+//   per pass:  k_radix_hist    per-tile digit histogram (pass 0: written by the kernel that produces the keys) -> hist[digit * tiles + tile]
+//              k_scan_rows     row-wise exclusive scan of the digit-major table + row totals
+//              k_radix_scatter stable in-tile ranking (warp match_any) + scatter; the digit bases come from the row totals
+// Stability is what makes the topology equal the reference's (AK.sortperm is a stable merge sort, src/instanced-bvh.jl:1399).
 // =================================================================================================
 constexpr int RS_THREADS = 256;
 constexpr int RS_ITEMS = 8;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
 constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_BITS = 10;
+constexpr int RS_DIGITS = 1 << RS_BITS;
+constexpr int RS_PASSES = 3;
+constexpr int RS_DPT = RS_DIGITS / RS_THREADS;  // digits per thread in the table steps
 
-__global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const uint32_t *__restrict__ keys, uint32_t n, int shift, uint32_t tiles, uint32_t *__restrict__ hist) {
-    __shared__ uint32_t sh[256];
-    sh[threadIdx.x] = 0;
+__global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ n_ptr, uint32_t n_host, int shift, uint32_t tiles,
+                                                          uint32_t *__restrict__ hist) {
+    __shared__ uint32_t sh[RS_DIGITS];
+    const uint32_t n = count_of(n_ptr, n_host);
+#pragma unroll
+    for (int k = 0; k < RS_DPT; k++) sh[threadIdx.x + k * RS_THREADS] = 0;
     __syncthreads();
     uint32_t base = blockIdx.x * RS_TILE;
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; i++) {
         uint32_t idx = base + i * RS_THREADS + threadIdx.x;
-        if (idx < n) atomicAdd(&sh[(keys[idx] >> shift) & 255u], 1u);
+        if (idx < n) atomicAdd(&sh[(keys[idx] >> shift) & (RS_DIGITS - 1u)], 1u);
     }
     __syncthreads();
-    hist[threadIdx.x * tiles + blockIdx.x] = sh[threadIdx.x];
+#pragma unroll
+    for (int k = 0; k < RS_DPT; k++) {
+        const uint32_t d = threadIdx.x + k * RS_THREADS;
+        hist[(size_t)d * tiles + blockIdx.x] = sh[d];
+    }
 }
 
 __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in, uint32_t *__restrict__ keys_out,
-                                                             uint32_t *__restrict__ vals_out, uint32_t n, int shift, uint32_t tiles, const uint32_t *__restrict__ offs,
-                                                             const uint32_t *__restrict__ totals) {
-    __shared__ uint32_t wh[RS_WARPS][256];
+                                                             uint32_t *__restrict__ vals_out, const uint32_t *__restrict__ n_ptr, uint32_t n_host, int shift, uint32_t tiles,
+                                                             const uint32_t *__restrict__ offs, const uint32_t *__restrict__ totals) {
+    __shared__ uint32_t wh[RS_WARPS][RS_DIGITS];
     __shared__ uint32_t sm[33];
+    const uint32_t n = count_of(n_ptr, n_host);
+    if ((uint64_t)blockIdx.x * RS_TILE >= n) return;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&wh[0][0])[i] = 0;
+    for (int i = threadIdx.x; i < RS_WARPS * RS_DIGITS; i += RS_THREADS) (&wh[0][0])[i] = 0;
     __syncthreads();
     // warp w owns the contiguous chunk [w*256, (w+1)*256) of the tile; item i of lane l = chunk + i*32 + l,
     // so (i, l) lexicographic order == memory order and ranks are stable.
@@ -166,7 +206,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const uint32_t *__
         bool ok = idx < n;
         key[i] = ok ? keys_in[idx] : 0xFFFFFFFFu;
         val[i] = ok ? vals_in[idx] : 0u;
-        dig[i] = ok ? ((key[i] >> shift) & 255u) : 256u;  // 256 = padding lane group
+        dig[i] = ok ? ((key[i] >> shift) & (RS_DIGITS - 1u)) : (uint32_t)RS_DIGITS;  // RS_DIGITS = padding lane group
         uint32_t peers = __match_any_sync(0xFFFFFFFFu, dig[i]);
         uint32_t leader = __ffs(peers) - 1;
         uint32_t prev = 0;
@@ -178,11 +218,17 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const uint32_t *__
         rank[i] = prev + __popc(peers & lt_mask);
         __syncwarp();
     }
+    // keys with a smaller digit: exclusive scan of the 1024 row totals, RS_DPT consecutive digits per thread
+    uint32_t tot[RS_DPT], local = 0;
+#pragma unroll
+    for (int k = 0; k < RS_DPT; k++) { tot[k] = totals[threadIdx.x * RS_DPT + k]; local += tot[k]; }
     uint32_t total_;
-    const uint32_t digit_base = block_excl_scan(totals[threadIdx.x], sm, total_);  // keys with a smaller digit (includes a __syncthreads)
-    {   // thread d: turn per-warp counts of digit d into exclusive prefixes starting at the global offset
-        uint32_t d = threadIdx.x;
-        uint32_t off = digit_base + offs[d * tiles + blockIdx.x];
+    uint32_t digit_base = block_excl_scan(local, sm, total_);  // (includes a __syncthreads: the per-warp counts are complete)
+#pragma unroll
+    for (int k = 0; k < RS_DPT; k++) {  // digit d: turn the per-warp counts into exclusive prefixes starting at the global offset
+        const uint32_t d = threadIdx.x * RS_DPT + k;
+        uint32_t off = digit_base + offs[(size_t)d * tiles + blockIdx.x];
+        digit_base += tot[k];
 #pragma unroll
         for (int w = 0; w < RS_WARPS; w++) {
             uint32_t c = wh[w][d];
@@ -193,7 +239,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const uint32_t *__
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; i++) {
-        if (dig[i] < 256u) {
+        if (dig[i] < (uint32_t)RS_DIGITS) {
             uint32_t pos = wh[wid][dig[i]] + rank[i];
             keys_out[pos] = key[i];
             vals_out[pos] = val[i];
@@ -201,10 +247,10 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const uint32_t *__
     }
 }
 
-// Row-wise exclusive scan of the digit-major table hist[256][tiles] in place, one warp per digit row (256 warps in 32 blocks):
+// Row-wise exclusive scan of the digit-major table hist[RS_DIGITS][tiles] in place, one warp per digit row:
 // each lane sums a contiguous segment (independent loads), one warp scan orders the segments, the lane rewrites its segment.
-// The row totals go to totals[256]; k_radix_scatter turns them into the per-digit bases itself (a 256-entry block scan), so no
-// single-block pass over the whole table is needed (the one-block version was 30 us per pass at 1 M keys, a third of the build).
+// The row totals go to totals[RS_DIGITS]; k_radix_scatter turns them into the per-digit bases itself, so no single-block pass
+// over the whole table is needed.
 __global__ void __launch_bounds__(256) k_scan_rows(uint32_t *__restrict__ hist, uint32_t tiles, uint32_t *__restrict__ totals) {
     const uint32_t lane = threadIdx.x & 31, d = blockIdx.x * 8 + (threadIdx.x >> 5);
     uint32_t *row = hist + (size_t)d * tiles;
@@ -221,130 +267,170 @@ __global__ void __launch_bounds__(256) k_scan_rows(uint32_t *__restrict__ hist, 
     if (lane == 31) totals[d] = inc;
 }
 
-// sorts in place: on return keys/vals hold the sorted pairs (4 passes ping-pong through tmp buffers)
-static void radix_sort_pairs(cudaStream_t st, uint32_t *keys, uint32_t *vals, uint32_t *keys_tmp, uint32_t *vals_tmp, uint32_t n, uint32_t *hist /* 256*tiles + 256 */) {
-    uint32_t tiles = cdiv(n, RS_TILE);
+static size_t radix_hist_words(uint32_t n_bound) { return (size_t)RS_DIGITS * cdiv(n_bound, RS_TILE) + RS_DIGITS; }
+
+// Sorts (keys, vals) by the low 30 bits of the keys.  n_bound sizes the grids; the live count is *n_ptr (device) or n_bound itself.
+// pass0_hist_done: the producer of the keys already wrote the pass-0 tile histograms (same tiling).  With three passes the sorted
+// pairs end up in (keys_tmp, vals_tmp): returned through the out pointers.
+static void radix_sort_pairs(cudaStream_t st, uint32_t *keys, uint32_t *vals, uint32_t *keys_tmp, uint32_t *vals_tmp, const uint32_t *n_ptr, uint32_t n_bound, uint32_t *hist,
+                             bool pass0_hist_done, uint32_t **keys_sorted, uint32_t **vals_sorted) {
+    uint32_t tiles = cdiv(n_bound, RS_TILE);
     uint32_t *ki = keys, *vi = vals, *ko = keys_tmp, *vo = vals_tmp;
-    for (int pass = 0; pass < 4; pass++) {
-        int shift = pass * 8;
-        k_radix_hist<<<tiles, RS_THREADS, 0, st>>>(ki, n, shift, tiles, hist);
-        uint32_t *totals = hist + (size_t)256 * tiles;
-        k_scan_rows<<<32, 256, 0, st>>>(hist, tiles, totals);
-        k_radix_scatter<<<tiles, RS_THREADS, 0, st>>>(ki, vi, ko, vo, n, shift, tiles, hist, totals);
+    uint32_t *totals = hist + (size_t)RS_DIGITS * tiles;
+    for (int pass = 0; pass < RS_PASSES; pass++) {
+        int shift = pass * RS_BITS;
+        if (pass > 0 || !pass0_hist_done) k_radix_hist<<<tiles, RS_THREADS, 0, st>>>(ki, n_ptr, n_bound, shift, tiles, hist);
+        k_scan_rows<<<RS_DIGITS / 8, 256, 0, st>>>(hist, tiles, totals);
+        k_radix_scatter<<<tiles, RS_THREADS, 0, st>>>(ki, vi, ko, vo, n_ptr, n_bound, shift, tiles, hist, totals);
         std::swap(ki, ko);
         std::swap(vi, vo);
     }
+    *keys_sorted = ki;
+    *vals_sorted = vi;
 }
 
 // =================================================================================================
-// BLAS front end: filter, compact, bounds, Morton
+// BLAS front end: filter + stable compaction + bounds in one pass, then Morton codes (+ the first radix histogram)
 // =================================================================================================
 __device__ __forceinline__ f3 ld3(const float *p) { return mk3(p[0], p[1], p[2]); }
 
-__global__ void k_face_flags(const float *__restrict__ verts, uint32_t n_faces, uint32_t *__restrict__ flags) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_faces) return;
-    const float *v = verts + (size_t)i * 9;
-    flags[i] = x_is_degenerate(ld3(v), ld3(v + 3), ld3(v + 6)) ? 0u : 1u;  // is_degenerate_face, :573-577
-}
-
-__device__ __forceinline__ void bounds_atomic(uint32_t *bounds, f3 lo, f3 hi) {
-    // warp reduce (REDUX) then block reduce in ordered-uint space: 6 atomics per block (per-warp atomics on one 32-B sector
-    // serialised in L2: 134 us for 1 M triangles in profiles/r1_launches_v6)
+// block-wide min / max of a box into the control block (REDUX per warp, six atomics per block).  Every thread of the block calls it.
+__device__ __forceinline__ void bounds_atomic(uint32_t *ctl, f3 lo, f3 hi) {
     __shared__ uint32_t part[6][32];
-    uint32_t v[6] = {rc_float_to_ordered(lo.x), rc_float_to_ordered(lo.y), rc_float_to_ordered(lo.z),
+    // 0 is the identity of both encodings: ~ordered(+Inf) and ordered(-Inf) are > 0 only for real boxes' complements... (empty lanes pass +Inf / -Inf)
+    uint32_t v[6] = {~rc_float_to_ordered(lo.x), ~rc_float_to_ordered(lo.y), ~rc_float_to_ordered(lo.z),
                      rc_float_to_ordered(hi.x), rc_float_to_ordered(hi.y), rc_float_to_ordered(hi.z)};
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
 #pragma unroll
     for (int c = 0; c < 6; c++) {
-        uint32_t r = c < 3 ? __reduce_min_sync(0xFFFFFFFFu, v[c]) : __reduce_max_sync(0xFFFFFFFFu, v[c]);
+        uint32_t r = __reduce_max_sync(0xFFFFFFFFu, v[c]);
         if (lane == 0) part[c][wid] = r;
     }
     __syncthreads();
     if (wid == 0) {
 #pragma unroll
         for (int c = 0; c < 6; c++) {
-            uint32_t x = lane < nw ? part[c][lane] : (c < 3 ? 0xFFFFFFFFu : 0u);
-            uint32_t r = c < 3 ? __reduce_min_sync(0xFFFFFFFFu, x) : __reduce_max_sync(0xFFFFFFFFu, x);
-            if (lane == 0) {
-                if (c < 3) atomicMin(&bounds[c], r);
-                else atomicMax(&bounds[c], r);
-            }
+            uint32_t x = lane < nw ? part[c][lane] : 0u;
+            uint32_t r = __reduce_max_sync(0xFFFFFFFFu, x);
+            if (lane == 0) atomicMax(&ctl[CTL_BOUNDS + c], r);
         }
     }
 }
 
-__global__ void k_init_bounds(uint32_t *bounds) {
-    if (threadIdx.x < 3) bounds[threadIdx.x] = rc_float_to_ordered(INFINITY);  // Bounds3(): (+Inf, -Inf)
-    else if (threadIdx.x < 6) bounds[threadIdx.x] = rc_float_to_ordered(-INFINITY);
-}
-
-// valid face i -> compacted slot pos[i]: unsorted RcTri (prim_id = slot, metadata), triangle box, scene bounds
-__global__ void k_compact_faces(const float *__restrict__ verts, const uint32_t *__restrict__ face_meta, const uint32_t *__restrict__ flags,
-                                const uint32_t *__restrict__ pos, uint32_t n_faces, RcTri *__restrict__ tris_in, RcBox *__restrict__ tri_boxes,
-                                uint32_t *__restrict__ bounds) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    f3 lo = mk3(INFINITY, INFINITY, INFINITY), hi = mk3(-INFINITY, -INFINITY, -INFINITY);
-    if (i < n_faces && flags[i]) {
+// One pass over the submitted faces (is_degenerate_face :573-577 + the compaction the reference does with filter!, :591-600):
+// exact degenerate test, stable compaction by a decoupled look-back scan over the 1024-face tiles (tile tickets are handed out in
+// arrival order, so a tile only ever waits for tiles that are already running), compacted RcTri records (prim_id = compacted slot),
+// scene bounds.  The last tile publishes the valid count.
+constexpr int FILTER_T = 1024;
+__global__ void __launch_bounds__(FILTER_T) k_filter(const float *__restrict__ verts, const uint32_t *__restrict__ face_meta, uint32_t n_faces, RcTri *__restrict__ tris_in,
+                                                     uint32_t *__restrict__ ctl, uint32_t *__restrict__ tile_state) {
+    __shared__ uint32_t s_tile, s_warp[32], s_prefix, s_total;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(&ctl[CTL_TILE], 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile, i = tile * FILTER_T + tid;
+    bool valid = false;
+    f3 a = mk3(0, 0, 0), b = a, c = a;
+    if (i < n_faces) {
         const float *v = verts + (size_t)i * 9;
-        f3 a = ld3(v), b = ld3(v + 3), c = ld3(v + 6);
-        uint32_t k = pos[i];
-        RcTri t;
-        t.v0[0] = a.x; t.v0[1] = a.y; t.v0[2] = a.z; t.prim_id = k;
-        t.v1[0] = b.x; t.v1[1] = b.y; t.v1[2] = b.z; t.metadata = face_meta ? face_meta[i] : i + 1u;  // :595
-        t.v2[0] = c.x; t.v2[1] = c.y; t.v2[2] = c.z; t.face_index = i;
-        tris_in[k] = t;
+        a = ld3(v); b = ld3(v + 3); c = ld3(v + 6);
+        valid = !x_is_degenerate(a, b, c);
+    }
+    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, valid);
+    if (lane == 0) s_warp[wid] = __popc(bal);
+    __syncthreads();
+    if (wid == 0) {
+        const uint32_t cnt = s_warp[lane], inc = warp_incl_scan(cnt);
+        s_warp[lane] = inc - cnt;
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+        // look back: state word = flag << 30 | count, flag 1 = this tile's own count, 2 = inclusive prefix up to and including the tile
+        uint32_t excl = 0;
+        if (tile > 0) {
+            if (lane == 0) st_relaxed(&tile_state[tile], (1u << 30) | total);
+            int base = (int)tile;
+            for (;;) {
+                const int t = base - 1 - (int)lane;
+                uint32_t st;
+                do { st = t >= 0 ? ld_relaxed(&tile_state[t]) : (2u << 30); } while (__any_sync(0xFFFFFFFFu, (st >> 30) == 0u));
+                const uint32_t incl_mask = __ballot_sync(0xFFFFFFFFu, (st >> 30) == 2u);
+                const uint32_t use = incl_mask ? ((2u << (__ffs(incl_mask) - 1)) - 1u) : 0xFFFFFFFFu;  // lanes up to the nearest inclusive prefix
+                uint32_t v = (use >> lane) & 1u ? (st & 0x3FFFFFFFu) : 0u;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+                excl += v;
+                if (incl_mask) break;
+                base -= 32;
+            }
+        }
+        if (lane == 0) {
+            st_relaxed(&tile_state[tile], (2u << 30) | (excl + total));
+            s_prefix = excl;
+            s_total = total;
+        }
+    }
+    __syncthreads();
+    f3 lo = mk3(INFINITY, INFINITY, INFINITY), hi = mk3(-INFINITY, -INFINITY, -INFINITY);
+    if (valid) {
+        const uint32_t k = s_prefix + s_warp[wid] + __popc(bal & ((1u << lane) - 1u));
+        float4 *d = reinterpret_cast<float4 *>(tris_in + k);
+        d[0] = make_float4(a.x, a.y, a.z, __uint_as_float(k));
+        d[1] = make_float4(b.x, b.y, b.z, __uint_as_float(face_meta ? face_meta[i] : i + 1u));  // :595
+        d[2] = make_float4(c.x, c.y, c.z, __uint_as_float(i));
         lo = jl_min3(jl_min3(a, b), c);  // world_bound(tri), triangle_mesh.jl:37
         hi = jl_max3(jl_max3(a, b), c);
-        RcBox bx;
-        bx.lo[0] = lo.x; bx.lo[1] = lo.y; bx.lo[2] = lo.z; bx.pad0 = 0;
-        bx.hi[0] = hi.x; bx.hi[1] = hi.y; bx.hi[2] = hi.z; bx.pad1 = 0;
-        tri_boxes[k] = bx;
     }
-    bounds_atomic(bounds, lo, hi);
+    bounds_atomic(ctl, lo, hi);
+    if (tid == 0 && tile == gridDim.x - 1) ctl[CTL_N] = s_prefix + s_total;
 }
 
-// calculate_morton_code_for_prim, kernels.jl:88-98 (extent unguarded, :1388)
-__global__ void k_morton_prims(const RcBox *__restrict__ tri_boxes, uint32_t n, const uint32_t *__restrict__ bounds, uint32_t *__restrict__ codes, uint32_t *__restrict__ idx) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    f3 smin = mk3(rc_ordered_to_float(bounds[0]), rc_ordered_to_float(bounds[1]), rc_ordered_to_float(bounds[2]));
-    f3 smax = mk3(rc_ordered_to_float(bounds[3]), rc_ordered_to_float(bounds[4]), rc_ordered_to_float(bounds[5]));
-    f3 ext = x_sub3(smax, smin);
-    RcBox b = tri_boxes[i];
-    f3 c = mk3(x_mul(0.5f, x_add(b.lo[0], b.hi[0])), x_mul(0.5f, x_add(b.lo[1], b.hi[1])), x_mul(0.5f, x_add(b.lo[2], b.hi[2])));
-    f3 nrm = mk3(x_div(x_sub(c.x, smin.x), ext.x), x_div(x_sub(c.y, smin.y), ext.y), x_div(x_sub(c.z, smin.z), ext.z));
-    codes[i] = rc_morton30(nrm);
-    idx[i] = i;
-}
-
-// sorted triangle j = tris_in[perm[j]]; also the bounding-sphere radius^2 about the centre of the scene bounds (bits of a
-// non-negative float order like the float: one atomicMax per warp)
-__global__ void k_gather_tris(const RcTri *__restrict__ tris_in, const uint32_t *__restrict__ perm, uint32_t n, RcTri *__restrict__ tris,
-                              const uint32_t *__restrict__ bounds, uint32_t *__restrict__ r2_bits) {
-    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    float r2 = 0.0f;
-    if (j < n) {
-        const float4 *s = reinterpret_cast<const float4 *>(tris_in + perm[j]);
-        float4 *d = reinterpret_cast<float4 *>(tris + j);
-        const float4 a = s[0], b = s[1], c = s[2];
-        d[0] = a; d[1] = b; d[2] = c;
-        const f3 ctr = mk3(0.5f * (rc_ordered_to_float(bounds[0]) + rc_ordered_to_float(bounds[3])), 0.5f * (rc_ordered_to_float(bounds[1]) + rc_ordered_to_float(bounds[4])),
-                           0.5f * (rc_ordered_to_float(bounds[2]) + rc_ordered_to_float(bounds[5])));
-        r2 = rc_far2(ctr, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z));
+// calculate_morton_code_for_prim, kernels.jl:88-98 (extent unguarded, :1388), one RS_TILE of compacted triangles per block; also the
+// block's digit histogram of the first radix pass.
+__global__ void __launch_bounds__(RS_THREADS) k_morton_prims(const RcTri *__restrict__ tris_in, const uint32_t *__restrict__ ctl, uint32_t *__restrict__ codes,
+                                                            uint32_t *__restrict__ idx, uint32_t tiles, uint32_t *__restrict__ hist) {
+    __shared__ uint32_t sh[RS_DIGITS];
+    const uint32_t n = ctl[CTL_N];
+#pragma unroll
+    for (int k = 0; k < RS_DPT; k++) sh[threadIdx.x + k * RS_THREADS] = 0;
+    __syncthreads();
+    if ((uint64_t)blockIdx.x * RS_TILE < n) {
+        const f3 smin = ctl_bounds_min(ctl), smax = ctl_bounds_max(ctl);
+        const f3 ext = x_sub3(smax, smin);
+#pragma unroll 2
+        for (int it = 0; it < RS_ITEMS; it++) {
+            const uint32_t i = blockIdx.x * RS_TILE + it * RS_THREADS + threadIdx.x;
+            if (i >= n) break;
+            const float4 *t = reinterpret_cast<const float4 *>(tris_in + i);
+            const float4 p = t[0], q = t[1], r = t[2];
+            const f3 a = mk3(p.x, p.y, p.z), b = mk3(q.x, q.y, q.z), c3 = mk3(r.x, r.y, r.z);
+            const f3 lo = jl_min3(jl_min3(a, b), c3), hi = jl_max3(jl_max3(a, b), c3);
+            const f3 c = mk3(x_mul(0.5f, x_add(lo.x, hi.x)), x_mul(0.5f, x_add(lo.y, hi.y)), x_mul(0.5f, x_add(lo.z, hi.z)));
+            const f3 nrm = mk3(x_div(x_sub(c.x, smin.x), ext.x), x_div(x_sub(c.y, smin.y), ext.y), x_div(x_sub(c.z, smin.z), ext.z));
+            const uint32_t code = rc_morton30(nrm);
+            codes[i] = code;
+            idx[i] = i;
+            atomicAdd(&sh[code & (RS_DIGITS - 1u)], 1u);
+        }
     }
-    const uint32_t m = __reduce_max_sync(0xFFFFFFFFu, r2 == r2 ? __float_as_uint(r2) : 0x7F800000u);  // NaN vertices: infinite radius (no cull)
-    if ((threadIdx.x & 31u) == 0) atomicMax(r2_bits, m);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < RS_DPT; k++) {
+        const uint32_t d = threadIdx.x + k * RS_THREADS;
+        hist[(size_t)d * tiles + blockIdx.x] = sh[d];
+    }
 }
 
 // =================================================================================================
 // Topology, fit, BVH2 emission, collapse (shared by BLAS and TLAS)
 // =================================================================================================
-__global__ void k_topology(const uint32_t *__restrict__ codes, uint32_t n, RcTopo *__restrict__ topo, uint32_t *__restrict__ parent) {
+__global__ void k_topology(const uint32_t *__restrict__ codes, const uint32_t *__restrict__ n_ptr, uint32_t n_host, RcTopo *__restrict__ topo, uint32_t *__restrict__ parent,
+                           uint32_t *__restrict__ flags) {
+    const uint32_t n = count_of(n_ptr, n_host);
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // internal node i+1
+    if (n == 1 && i == 0) parent[0] = RC_INVALID;  // single leaf: no internal node, the leaf's parent is INVALID
     if (i + 1 >= n) return;
     RcTopo t = rc_topology_for_node((int)(i + 1), codes, (int)n);
     topo[i] = t;
+    flags[i] = 0;  // arrival counter of the fit
     parent[t.child0 - 1] = i + 1;  // set_parents_for_node, kernels.jl:159-180
     parent[t.child1 - 1] = i + 1;
     if (i == 0) parent[0] = RC_INVALID;
@@ -371,119 +457,202 @@ __device__ __forceinline__ void st_node2(RcNode2 *p, f3 a0n, f3 a0x, f3 a1n, f3 
     q[3] = make_float4(__uint_as_float(c0), __uint_as_float(c1), __uint_as_float(par), 0.f);
 }
 
-// One thread per leaf: write the leaf's own box + reference-layout leaf node, then climb; the second
-// arriver at an internal node computes it (refit_aabbs_kernel!, kernels.jl:239-286 / :381-428).
-//   BLAS (tris != null): leaf box = bounds of the sorted triangle, leaf node = (v0,v1,v2,0 | INVALID, p, parent)
-//   TLAS (tris == null): leaf box = inst_boxes[leaf_map[p-1]],     leaf node = (lo,hi,0,0 | INVALID, inst, parent)
-__global__ void k_fit(const RcTri *__restrict__ tris, const RcBox *__restrict__ inst_boxes, const uint32_t *__restrict__ leaf_map, uint32_t n,
-                      const RcTopo *__restrict__ topo, const uint32_t *__restrict__ parent, uint32_t *__restrict__ flags, RcBox *__restrict__ boxes,
-                      RcNode2 *__restrict__ nodes2) {
-    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;  // sorted primitive p+1
-    if (p >= n) return;
-    uint32_t leaf = n - 1 + (p + 1);
-    uint32_t par = parent[leaf - 1];
-    f3 lo, hi;
-    if (tris) {
-        const float4 *t = reinterpret_cast<const float4 *>(tris + p);
-        float4 a = t[0], b = t[1], c = t[2];
-        f3 v0 = mk3(a.x, a.y, a.z), v1 = mk3(b.x, b.y, b.z), v2 = mk3(c.x, c.y, c.z);
-        lo = jl_min3(jl_min3(v0, v1), v2);  // get_node_aabb leaf branch, :1148-1158
-        hi = jl_max3(jl_max3(v0, v1), v2);
-        if (nodes2) st_node2(nodes2 + (leaf - 1), v0, v1, v2, mk3(0, 0, 0), RC_INVALID, p + 1, par);
-    } else {
-        uint32_t inst = leaf_map[p];
-        RcBox b = inst_boxes[inst];
-        lo = mk3(b.lo[0], b.lo[1], b.lo[2]);
-        hi = mk3(b.hi[0], b.hi[1], b.hi[2]);
-        if (nodes2) st_node2(nodes2 + (leaf - 1), lo, hi, mk3(0, 0, 0), mk3(0, 0, 0), RC_INVALID, inst, par);
+// Bottom-up fit (refit_aabbs_kernel!, kernels.jl:239-286 / :381-428): one thread per leaf writes the leaf's box and climbs; the
+// second arriver at an internal node computes it.  A block owns FIT_T consecutive leaves, and every internal node whose span lies
+// inside that range (all but ~2 n / FIT_T of them) is fitted through shared memory — arrival counters, boxes, topology and parent
+// links of the range are staged there, so a level of the climb costs shared-memory latency instead of an L2 round trip and a
+// device-scope fence.  Only the nodes spanning several blocks use the global protocol (box in global memory, release-ordered
+// counter bump, children read back with ld.cg).  1 M triangles: 154 us -> see profiles/README.md r2.
+//   BLAS build (tris_in != null): sorted triangle p = tris_in[perm[p]] is gathered here and written to tris; leaf box = its bounds;
+//                                 leaf node = (v0,v1,v2,0 | INVALID, p+1, parent); the bounding-sphere radius is reduced on the way
+//   BLAS refit (tris_in == null, tris != null): the triangles are already in place
+//   TLAS (tris == null): leaf box = inst_boxes[leaf_map[p]], leaf node = (lo,hi,0,0 | INVALID, inst, parent)
+constexpr int FIT_T = 1024;
+struct FitSmem {
+    RcTopo topo[FIT_T];
+    uint32_t par_int[FIT_T], par_leaf[FIT_T], flag[FIT_T];
+    float box_int[FIT_T][6], box_leaf[FIT_T][6];
+};
+__global__ void __launch_bounds__(FIT_T) k_fit(const RcTri *__restrict__ tris_in, const uint32_t *__restrict__ perm, RcTri *__restrict__ tris,
+                                               const RcBox *__restrict__ inst_boxes, const uint32_t *__restrict__ leaf_map, const uint32_t *__restrict__ n_ptr, uint32_t n_host,
+                                               const RcTopo *__restrict__ topo, const uint32_t *__restrict__ parent, uint32_t *__restrict__ flags, RcBox *__restrict__ boxes,
+                                               RcNode2 *__restrict__ nodes2, uint32_t *__restrict__ ctl) {
+    extern __shared__ __align__(16) unsigned char fit_raw[];
+    FitSmem &S = *reinterpret_cast<FitSmem *>(fit_raw);
+    const uint32_t n = count_of(n_ptr, n_host);
+    const uint32_t tid = threadIdx.x;
+    const uint32_t blk_lo = blockIdx.x * FIT_T + 1u;  // first sorted primitive (1-based) = first internal node number of the range
+    if (blk_lo > n) return;
+    const uint32_t blk_hi = min(blk_lo + FIT_T - 1u, n);
+    const uint32_t p1 = blk_lo + tid;  // this thread's primitive (1-based) and the internal node number it stages
+    if (p1 <= blk_hi) {
+        if (p1 < n) {
+            S.topo[tid] = topo[p1 - 1];
+            S.par_int[tid] = parent[p1 - 1];
+        }
+        S.par_leaf[tid] = parent[n - 1 + p1 - 1];
+        S.flag[tid] = 0;
     }
-    st_box(boxes + (leaf - 1), lo, hi);
-    uint32_t node = par;
-    while (node != RC_INVALID) {
-        __threadfence();  // publish the box written above before signalling
-        uint32_t old = atomicAdd(&flags[node - 1], 1u);
-        if (old == 0) return;  // first arriver: the sibling subtree is not ready
-        RcTopo tp = topo[node - 1];
-        RcBox b0 = ld_box_cg(boxes + (tp.child0 - 1)), b1 = ld_box_cg(boxes + (tp.child1 - 1));
-        f3 l0 = mk3(b0.lo[0], b0.lo[1], b0.lo[2]), h0 = mk3(b0.hi[0], b0.hi[1], b0.hi[2]);
-        f3 l1 = mk3(b1.lo[0], b1.lo[1], b1.lo[2]), h1 = mk3(b1.hi[0], b1.hi[1], b1.hi[2]);
-        uint32_t up = parent[node - 1];
-        if (nodes2) st_node2(nodes2 + (node - 1), l0, h0, l1, h1, tp.child0, tp.child1, up);
-        st_box(boxes + (node - 1), jl_min3(l0, l1), jl_max3(h0, h1));  // get_node_aabb interior branch, :1142-1147
-        node = up;
+    __syncthreads();
+    float r2 = 0.0f;
+    if (p1 <= blk_hi) {
+        const uint32_t p = p1 - 1, leaf = n - 1 + p1;
+        uint32_t node = S.par_leaf[tid];
+        f3 lo, hi;
+        if (tris) {
+            float4 a, b, c;
+            if (tris_in) {
+                const float4 *s = reinterpret_cast<const float4 *>(tris_in + perm[p]);
+                a = s[0]; b = s[1]; c = s[2];
+                float4 *d = reinterpret_cast<float4 *>(tris + p);
+                d[0] = a; d[1] = b; d[2] = c;
+            } else {
+                const float4 *s = reinterpret_cast<const float4 *>(tris + p);
+                a = s[0]; b = s[1]; c = s[2];
+            }
+            const f3 v0 = mk3(a.x, a.y, a.z), v1 = mk3(b.x, b.y, b.z), v2 = mk3(c.x, c.y, c.z);
+            lo = jl_min3(jl_min3(v0, v1), v2);  // get_node_aabb leaf branch, :1148-1158
+            hi = jl_max3(jl_max3(v0, v1), v2);
+            if (nodes2) st_node2(nodes2 + (leaf - 1), v0, v1, v2, mk3(0, 0, 0), RC_INVALID, p1, node);
+            const f3 smin = ctl_bounds_min(ctl), smax = ctl_bounds_max(ctl);
+            r2 = rc_far2(mk3(0.5f * (smin.x + smax.x), 0.5f * (smin.y + smax.y), 0.5f * (smin.z + smax.z)), v0, v1, v2);
+            if (!(r2 == r2)) r2 = INFINITY;  // NaN vertices: infinite radius (no cull)
+        } else {
+            const uint32_t inst = leaf_map[p];
+            const RcBox b = inst_boxes[inst];
+            lo = mk3(b.lo[0], b.lo[1], b.lo[2]);
+            hi = mk3(b.hi[0], b.hi[1], b.hi[2]);
+            if (nodes2) st_node2(nodes2 + (leaf - 1), lo, hi, mk3(0, 0, 0), mk3(0, 0, 0), RC_INVALID, inst, node);
+        }
+        st_box(boxes + (leaf - 1), lo, hi);
+        S.box_leaf[tid][0] = lo.x; S.box_leaf[tid][1] = lo.y; S.box_leaf[tid][2] = lo.z;
+        S.box_leaf[tid][3] = hi.x; S.box_leaf[tid][4] = hi.y; S.box_leaf[tid][5] = hi.z;
+        bool global_phase = false;
+        while (node != RC_INVALID) {
+            bool local = false;
+            if (!global_phase && node >= blk_lo && node <= blk_hi) {
+                const RcTopo &tp = S.topo[node - blk_lo];
+                local = tp.span_lo >= blk_lo && tp.span_hi <= blk_hi;
+            }
+            f3 l0, h0, l1, h1;
+            uint32_t c0, c1, up;
+            if (local) {
+                const uint32_t s = node - blk_lo;
+                __threadfence_block();  // the box written to shared memory above is visible before the arrival is counted
+                if (atomicAdd(&S.flag[s], 1u) == 0u) break;  // first arriver: the sibling subtree is not ready
+                c0 = S.topo[s].child0; c1 = S.topo[s].child1; up = S.par_int[s];
+                const float *b0 = c0 >= n ? S.box_leaf[c0 - (n - 1) - blk_lo] : S.box_int[c0 - blk_lo];
+                const float *b1 = c1 >= n ? S.box_leaf[c1 - (n - 1) - blk_lo] : S.box_int[c1 - blk_lo];
+                l0 = mk3(b0[0], b0[1], b0[2]); h0 = mk3(b0[3], b0[4], b0[5]);
+                l1 = mk3(b1[0], b1[1], b1[2]); h1 = mk3(b1[3], b1[4], b1[5]);
+            } else {
+                global_phase = true;  // every ancestor of a node that spans several blocks does too
+                if (atom_add_release(&flags[node - 1], 1u) == 0u) break;
+                const RcTopo tp = topo[node - 1];
+                c0 = tp.child0; c1 = tp.child1; up = parent[node - 1];
+                const RcBox b0 = ld_box_cg(boxes + (c0 - 1)), b1 = ld_box_cg(boxes + (c1 - 1));
+                l0 = mk3(b0.lo[0], b0.lo[1], b0.lo[2]); h0 = mk3(b0.hi[0], b0.hi[1], b0.hi[2]);
+                l1 = mk3(b1.lo[0], b1.lo[1], b1.lo[2]); h1 = mk3(b1.hi[0], b1.hi[1], b1.hi[2]);
+            }
+            lo = jl_min3(l0, l1);  // get_node_aabb interior branch, :1142-1147
+            hi = jl_max3(h0, h1);
+            if (nodes2) st_node2(nodes2 + (node - 1), l0, h0, l1, h1, c0, c1, up);
+            st_box(boxes + (node - 1), lo, hi);
+            if (local) {
+                float *bi = S.box_int[node - blk_lo];
+                bi[0] = lo.x; bi[1] = lo.y; bi[2] = lo.z; bi[3] = hi.x; bi[4] = hi.y; bi[5] = hi.z;
+            }
+            node = up;
+        }
+    }
+    if (tris) {  // bits of a non-negative float order like the float: one atomicMax per warp that still has lanes here
+        const uint32_t m = __reduce_max_sync(__activemask(), __float_as_uint(r2));
+        if ((tid & 31u) == (uint32_t)(__ffs(__activemask()) - 1)) atomicMax(&ctl[CTL_R2], m);
     }
 }
 
-__global__ void k_collapse(const RcBox *__restrict__ boxes, const RcTopo *__restrict__ topo, uint32_t n, uint32_t leaf_max, const uint32_t *__restrict__ leaf_map,
-                           RcNode4 *__restrict__ nodes4) {
+// BVH2 subtree -> wide node, one thread per BVH2 internal node.  A node that covers <= leaf_max primitives can never be the root
+// of a wide node (its parent turns it into a leaf reference), so it is skipped (about a third of the internal nodes at leaf_max 2).
+// One extra block computes the hull (hull != null): the RC_HULL_BOXES subtrees four levels below the root — together they cover the
+// whole BLAS — give the instance bounds of the wide TLAS (union of the transformed hull boxes).
+__global__ void k_collapse(const RcBox *__restrict__ boxes, const RcTopo *__restrict__ topo, const uint32_t *__restrict__ n_ptr, uint32_t n_host, uint32_t leaf_max,
+                           const uint32_t *__restrict__ leaf_map, RcNode4 *__restrict__ nodes4, RcBox *__restrict__ hull) {
+    const uint32_t n = count_of(n_ptr, n_host);
+    if (n == 0) return;
+    if (hull && blockIdx.x == gridDim.x - 1) {
+        const uint32_t k = threadIdx.x;
+        if (k >= RC_HULL_BOXES) return;
+        uint32_t node = 1;
+#pragma unroll
+        for (int l = 3; l >= 0; l--) {
+            if (node >= n) break;  // a leaf (or the single-leaf tree): stays
+            const RcTopo tp = topo[node - 1];
+            node = (k >> l) & 1u ? tp.child1 : tp.child0;
+        }
+        hull[k] = n == 1 ? boxes[0] : boxes[node - 1];
+        return;
+    }
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // node i+1
     uint32_t n_int = n > 1 ? n - 1 : 1;                   // n == 1: synthetic root over the single leaf
     if (i >= n_int) return;
+    if (i > 0 && n > 1) {
+        const RcTopo tp = topo[i];
+        if (tp.span_hi - tp.span_lo + 1u <= leaf_max) {  // never the head of a wide node: the slot stays empty (zeroed: exported blobs are deterministic)
+            float4 *d = reinterpret_cast<float4 *>(nodes4 + (i + 1));
+            d[0] = d[1] = d[2] = d[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+            return;
+        }
+    }
     RcNode4 nd = rc_collapse_node(i + 1, boxes, topo, n, leaf_max, leaf_map);
     const float4 *s = reinterpret_cast<const float4 *>(&nd);
     float4 *d = reinterpret_cast<float4 *>(nodes4 + (i + 1));
     d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3];
 }
 
-// RC_HULL_BOXES subtree boxes that together cover the BLAS: open the largest-area internal node until the budget is used.
-// One warp, lane 0 does the (tiny) serial selection.
-__global__ void k_blas_hull(const RcBox *__restrict__ boxes, const RcTopo *__restrict__ topo, uint32_t n, RcBox *__restrict__ hull) {
-    if (threadIdx.x != 0) return;
-    uint32_t ids[RC_HULL_BOXES];
-    int cnt = 1;
-    ids[0] = 1;
-    while (cnt < RC_HULL_BOXES) {
-        int best = -1;
-        float best_area = -1.0f;
-        for (int k = 0; k < cnt; k++)
-            if (ids[k] < n) {
-                float a = rc_half_area(boxes[ids[k] - 1]);
-                if (a > best_area) { best_area = a; best = k; }
-            }
-        if (best < 0) break;
-        RcTopo tp = topo[ids[best] - 1];
-        ids[best] = tp.child0;
-        ids[cnt++] = tp.child1;
+// root box -> out6; BLAS builds also finish the bounding sphere (centre of the scene bounds, radius^2 inflated against the rounding
+// of its own evaluation) and copy the valid count next to it, so the host reads everything back in one transfer
+__global__ void k_finish(const RcBox *__restrict__ boxes, float *__restrict__ out6, uint32_t *__restrict__ ctl, RcNode4 *__restrict__ nodes4 = nullptr) {
+    if (ctl && ctl[CTL_N] == 0) return;
+    if (nodes4 && threadIdx.x >= 16 && threadIdx.x < 24) {  // the two wide-node slots no kernel writes (0, and n when there are internal nodes)
+        const uint32_t n = ctl[CTL_N], k = threadIdx.x - 16;
+        reinterpret_cast<float4 *>(nodes4)[k & 3u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n > 1 && k >= 4) reinterpret_cast<float4 *>(nodes4 + n)[k & 3u] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    for (int k = 0; k < RC_HULL_BOXES; k++) {
-        RcBox b;
-        if (k < cnt) b = boxes[ids[k] - 1];
-        else { b.lo[0] = b.lo[1] = b.lo[2] = INFINITY; b.hi[0] = b.hi[1] = b.hi[2] = -INFINITY; b.pad0 = b.pad1 = 0; }
-        hull[k] = b;
-    }
-}
-
-// out6 = root box; sphere4 (nullable) = (centre of the scene bounds, radius^2 inflated against the rounding of its own evaluation)
-__global__ void k_read_root(const RcBox *__restrict__ boxes, float *__restrict__ out6, const uint32_t *__restrict__ bounds = nullptr,
-                            const uint32_t *__restrict__ r2_bits = nullptr, float *__restrict__ sphere4 = nullptr) {
     if (threadIdx.x < 3) out6[threadIdx.x] = boxes[0].lo[threadIdx.x];
     else if (threadIdx.x < 6) out6[threadIdx.x] = boxes[0].hi[threadIdx.x - 3];
-    else if (sphere4 && threadIdx.x < 9) {
+    else if (ctl && threadIdx.x < 9) {
         const int k = threadIdx.x - 6;
-        sphere4[k] = 0.5f * (rc_ordered_to_float(bounds[k]) + rc_ordered_to_float(bounds[3 + k]));
-    } else if (sphere4 && threadIdx.x == 9) {
-        sphere4[3] = __uint_as_float(*r2_bits) * 1.000002f;
+        const f3 smin = ctl_bounds_min(ctl), smax = ctl_bounds_max(ctl);
+        const float lo = k == 0 ? smin.x : (k == 1 ? smin.y : smin.z), hi = k == 0 ? smax.x : (k == 1 ? smax.y : smax.z);
+        out6[6 + k] = 0.5f * (lo + hi);
+    } else if (ctl && threadIdx.x == 9) {
+        out6[9] = __uint_as_float(ctl[CTL_R2]) * 1.000002f;
     }
 }
 
-// codes (sorted) -> topology, fit, BVH2, BVH4
-static void build_tree(cudaStream_t st, const uint32_t *codes_sorted, uint32_t n, const RcTri *tris, const RcBox *inst_boxes, const uint32_t *leaf_map,
-                       uint32_t leaf_max, RcTopo *topo, uint32_t *parent, uint32_t *flags, RcBox *boxes, RcNode2 *nodes2, RcNode4 *nodes4,
-                       const RcBox *inst_boxes_tight = nullptr, RcBox *boxes_tight = nullptr) {
-    const int T = 256;
-    if (n > 1) {
-        k_topology<<<cdiv(n - 1, T), T, 0, st>>>(codes_sorted, n, topo, parent);
-        cudaMemsetAsync(flags, 0, sizeof(uint32_t) * (n - 1), st);
-    } else {
-        cudaMemsetAsync(parent, 0xFF, sizeof(uint32_t), st);  // single leaf: parent = INVALID
+static void launch_fit(cudaStream_t st, uint32_t n_bound, const RcTri *tris_in, const uint32_t *perm, RcTri *tris, const RcBox *inst_boxes, const uint32_t *leaf_map,
+                       const uint32_t *n_ptr, const RcTopo *topo, const uint32_t *parent, uint32_t *flags, RcBox *boxes, RcNode2 *nodes2, uint32_t *ctl) {
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(k_fit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FitSmem));
+        configured = true;
     }
-    k_fit<<<cdiv(n, T), T, 0, st>>>(tris, inst_boxes, leaf_map, n, topo, parent, flags, boxes, nodes2);
+    k_fit<<<cdiv(n_bound, FIT_T), FIT_T, sizeof(FitSmem), st>>>(tris_in, perm, tris, inst_boxes, leaf_map, n_ptr, n_bound, topo, parent, flags, boxes, nodes2, ctl);
+}
+
+// codes (sorted) -> topology, fit, (BVH2,) BVH4.  n_ptr == nullptr: the count is n_bound itself (TLAS).
+static void build_tree(cudaStream_t st, const uint32_t *codes_sorted, const uint32_t *n_ptr, uint32_t n_bound, const RcTri *tris_in, const uint32_t *perm, RcTri *tris,
+                       const RcBox *inst_boxes, const uint32_t *leaf_map, uint32_t leaf_max, RcTopo *topo, uint32_t *parent, uint32_t *flags, RcBox *boxes, RcNode2 *nodes2,
+                       RcNode4 *nodes4, RcBox *hull, uint32_t *ctl, const RcBox *inst_boxes_tight = nullptr, RcBox *boxes_tight = nullptr) {
+    const int T = 256;
+    k_topology<<<cdiv(std::max(1u, n_bound - 1), T), T, 0, st>>>(codes_sorted, n_ptr, n_bound, topo, parent, flags);
+    launch_fit(st, n_bound, tris_in, perm, tris, inst_boxes, leaf_map, n_ptr, topo, parent, flags, boxes, nodes2, ctl);
     if (inst_boxes_tight) {  // wide TLAS from the tighter instance bounds (same topology, second fit without BVH2 output)
-        if (n > 1) cudaMemsetAsync(flags, 0, sizeof(uint32_t) * (n - 1), st);
-        k_fit<<<cdiv(n, T), T, 0, st>>>(nullptr, inst_boxes_tight, leaf_map, n, topo, parent, flags, boxes_tight, nullptr);
+        if (n_bound > 1) cudaMemsetAsync(flags, 0, sizeof(uint32_t) * (n_bound - 1), st);
+        launch_fit(st, n_bound, nullptr, nullptr, nullptr, inst_boxes_tight, leaf_map, n_ptr, topo, parent, flags, boxes_tight, nullptr, nullptr);
         boxes = boxes_tight;
     }
-    k_collapse<<<cdiv(n > 1 ? n - 1 : 1, T), T, 0, st>>>(boxes, topo, n, leaf_max, leaf_map, nodes4);
+    k_collapse<<<cdiv(n_bound > 1 ? n_bound - 1 : 1, T) + (hull ? 1 : 0), T, 0, st>>>(boxes, topo, n_ptr, n_bound, leaf_max, leaf_map, nodes4, hull);
 }
 
 // refit only (topology kept): recompute boxes, BVH2 and BVH4
@@ -492,10 +661,10 @@ static void refit_tree(cudaStream_t st, uint32_t n, const RcBox *inst_boxes, con
                        RcBox *boxes_tight) {
     const int T = 256;
     if (n > 1) cudaMemsetAsync(flags, 0, sizeof(uint32_t) * (n - 1), st);
-    k_fit<<<cdiv(n, T), T, 0, st>>>(nullptr, inst_boxes, leaf_map, n, topo, parent, flags, boxes, nodes2);
+    launch_fit(st, n, nullptr, nullptr, nullptr, inst_boxes, leaf_map, nullptr, topo, parent, flags, boxes, nodes2, nullptr);
     if (n > 1) cudaMemsetAsync(flags, 0, sizeof(uint32_t) * (n - 1), st);
-    k_fit<<<cdiv(n, T), T, 0, st>>>(nullptr, inst_boxes_tight, leaf_map, n, topo, parent, flags, boxes_tight, nullptr);
-    k_collapse<<<cdiv(n > 1 ? n - 1 : 1, T), T, 0, st>>>(boxes_tight, topo, n, leaf_max, leaf_map, nodes4);
+    launch_fit(st, n, nullptr, nullptr, nullptr, inst_boxes_tight, leaf_map, nullptr, topo, parent, flags, boxes_tight, nullptr, nullptr);
+    k_collapse<<<cdiv(n > 1 ? n - 1 : 1, T), T, 0, st>>>(boxes_tight, topo, nullptr, n, leaf_max, leaf_map, nodes4, nullptr);
 }
 
 // =================================================================================================
@@ -503,13 +672,9 @@ static void refit_tree(cudaStream_t st, uint32_t n, const RcBox *inst_boxes, con
 // =================================================================================================
 void rc_free_blas(RcDeviceBlas *b, cudaStream_t st) {
     if (!b) return;
-    if (b->nodes2) cudaFreeAsync(b->nodes2, st);
-    if (b->nodes4) cudaFreeAsync(b->nodes4, st);
-    if (b->tris) cudaFreeAsync(b->tris, st);
-    if (b->hull) cudaFreeAsync(b->hull, st);
-    if (b->normals) cudaFreeAsync(b->normals, st);
-    b->normals = nullptr;
-    b->nodes2 = nullptr; b->nodes4 = nullptr; b->tris = nullptr; b->hull = nullptr; b->n = 0;
+    for (void *p : {(void *)b->nodes2, (void *)b->nodes4, (void *)b->tris, (void *)b->hull, (void *)b->normals, (void *)b->topo, (void *)b->parent})
+        if (p) cudaFreeAsync(p, st);
+    *b = RcDeviceBlas();
 }
 
 // Stream-ordered temporaries that are returned to the pool when the builder leaves scope (also on every error path).
@@ -544,63 +709,126 @@ static bool extent_supported(const float aabb[6], std::string &err) {
     return true;
 }
 
-bool rc_build_blas(cudaStream_t st, const float *d_verts, const uint32_t *d_face_meta, uint32_t n_faces, RcDeviceBlas *out, std::string &err) {
-    *out = RcDeviceBlas();
-    if (n_faces == 0) { err = "Geometry has no valid triangles"; return false; }
-    const int T = 256;
-    RcTemps tmp(st);
-    uint32_t *d_flags = nullptr, *d_pos = nullptr, *d_tile = nullptr, *d_small = nullptr;
-    TMP(d_flags, n_faces);
-    TMP(d_pos, n_faces);
-    TMP(d_tile, cdiv(n_faces, SCAN_TILE));
-    TMP(d_small, 24);  // [0] = valid count, [1] = sphere radius^2 bits, [4..9] = scene bounds (ordered uints), [10..15] = root box, [16..19] = sphere
-    k_face_flags<<<cdiv(n_faces, T), T, 0, st>>>(d_verts, n_faces, d_flags);
-    exclusive_scan_u32(st, d_flags, d_pos, n_faces, d_tile, d_small);
-    uint32_t n = 0;
-    CK(cudaMemcpyAsync(&n, d_small, 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    if (n == 0) { err = "Geometry has no valid triangles"; return false; }  // src/instanced-bvh.jl:601
-    if (n > RC_LEAF_START_MASK - 16u) { err = "BLAS too large (max 2^28 triangles)"; return false; }
-    uint32_t *d_bounds = d_small + 4;
-    RcTri *d_tris_in = nullptr;
-    RcBox *d_tri_boxes = nullptr, *d_boxes = nullptr;
-    uint32_t *d_codes = nullptr, *d_idx = nullptr, *d_codes2 = nullptr, *d_idx2 = nullptr, *d_hist = nullptr, *d_parent = nullptr, *d_fl = nullptr;
-    RcTopo *d_topo = nullptr;
-    TMP(d_tris_in, n);
-    TMP(d_tri_boxes, n);
-    TMP(d_codes, n);
-    TMP(d_idx, n);
-    TMP(d_codes2, n);
-    TMP(d_idx2, n);
-    TMP(d_hist, 256 * (size_t)cdiv(n, RS_TILE) + 256);
-    TMP(d_topo, n - 1);
-    TMP(d_parent, 2 * (size_t)n - 1);
-    TMP(d_fl, n - 1);
-    TMP(d_boxes, 2 * (size_t)n - 1);
-    // the results outlive this call; on failure the caller releases them with rc_free_blas
-    CK(cudaMallocAsync(&out->nodes2, sizeof(RcNode2) * (2 * (size_t)n - 1), st));
-    CK(cudaMallocAsync(&out->nodes4, sizeof(RcNode4) * ((size_t)n + 1), st));
-    CK(cudaMallocAsync(&out->tris, sizeof(RcTri) * (size_t)n, st));
-    CK(cudaMallocAsync(&out->hull, sizeof(RcBox) * RC_HULL_BOXES, st));
-    out->n = n;
-    out->n_faces_in = n_faces;
-
-    k_init_bounds<<<1, 32, 0, st>>>(d_bounds);
-    k_compact_faces<<<cdiv(n_faces, T), T, 0, st>>>(d_verts, d_face_meta, d_flags, d_pos, n_faces, d_tris_in, d_tri_boxes, d_bounds);
-    k_morton_prims<<<cdiv(n, T), T, 0, st>>>(d_tri_boxes, n, d_bounds, d_codes, d_idx);
-    radix_sort_pairs(st, d_codes, d_idx, d_codes2, d_idx2, n, d_hist);
-    cudaMemsetAsync(d_small + 1, 0, 4, st);
-    k_gather_tris<<<cdiv(n, T), T, 0, st>>>(d_tris_in, d_idx, n, out->tris, d_bounds, d_small + 1);
-    build_tree(st, d_codes, n, out->tris, nullptr, nullptr, RC_BLAS_LEAF_MAX, d_topo, d_parent, d_fl, d_boxes, out->nodes2, out->nodes4);
-    k_blas_hull<<<1, 32, 0, st>>>(d_boxes, d_topo, n, out->hull);
-    k_read_root<<<1, 32, 0, st>>>(d_boxes, reinterpret_cast<float *>(d_small + 10), d_bounds, d_small + 1, reinterpret_cast<float *>(d_small + 16));
-    float h_out[10];
-    CK(cudaMemcpyAsync(h_out, d_small + 10, 40, cudaMemcpyDeviceToHost, st));
+// read back {valid count, root box, sphere} and finish the host-side record
+static bool finish_blas(cudaStream_t st, uint32_t *d_ctl, RcDeviceBlas *out, std::string &err) {
+    uint32_t h[CTL_OUT + 10];
+    CK(cudaMemcpyAsync(h, d_ctl, sizeof h, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
-    memcpy(out->root_aabb, h_out, 24);
-    memcpy(out->sphere, h_out + 6, 16);
+    out->n = h[CTL_N];
+    if (out->n == 0) { err = "Geometry has no valid triangles"; return false; }  // src/instanced-bvh.jl:601
+    memcpy(out->root_aabb, h + CTL_OUT, 24);
+    memcpy(out->sphere, h + CTL_OUT + 6, 16);
     return extent_supported(out->root_aabb, err);
+}
+
+bool rc_build_blas(cudaStream_t st, const float *d_verts, const uint32_t *d_face_meta, uint32_t n_faces, uint32_t build_flags, RcDeviceBlas *out, std::string &err) {
+    *out = RcDeviceBlas();
+    if (n_faces == 0) { err = "Geometry has no valid triangles"; return false; }
+    if (n_faces > RC_LEAF_START_MASK - 16u) { err = "BLAS too large (max 2^28 triangles)"; return false; }
+    const uint32_t nf = n_faces;  // upper bound of the valid count: sizes every array and grid; the live count stays on the device
+    const bool keep_bvh2 = build_flags & RC_BUILD_KEEP_BVH2, keep_topo = build_flags & RC_BUILD_ALLOW_REFIT;
+    RcTemps tmp(st);
+    const uint32_t f_tiles = cdiv(nf, FILTER_T), s_tiles = cdiv(nf, RS_TILE);
+    uint32_t *d_ctl = nullptr;
+    RcTri *d_tris_in = nullptr;
+    RcBox *d_boxes = nullptr;
+    uint32_t *d_codes = nullptr, *d_idx = nullptr, *d_codes2 = nullptr, *d_idx2 = nullptr, *d_hist = nullptr, *d_parent = nullptr, *d_fl = nullptr;
+    RcTopo *d_topo = nullptr;
+    TMP(d_ctl, CTL_WORDS + f_tiles);  // control block + the filter's tile states
+    TMP(d_tris_in, nf);
+    TMP(d_codes, nf);
+    TMP(d_idx, nf);
+    TMP(d_codes2, nf);
+    TMP(d_idx2, nf);
+    TMP(d_hist, radix_hist_words(nf));
+    TMP(d_fl, nf);
+    TMP(d_boxes, 2 * (size_t)nf);
+    // the results outlive this call; on failure the caller releases them with rc_free_blas
+    if (keep_topo) {
+        CK(cudaMallocAsync(&out->topo, sizeof(RcTopo) * (size_t)nf, st));
+        CK(cudaMallocAsync(&out->parent, sizeof(uint32_t) * 2 * (size_t)nf, st));
+        d_topo = out->topo;
+        d_parent = out->parent;
+    } else {
+        TMP(d_topo, nf);
+        TMP(d_parent, 2 * (size_t)nf);
+    }
+    if (keep_bvh2) CK(cudaMallocAsync(&out->nodes2, sizeof(RcNode2) * 2 * (size_t)nf, st));
+    CK(cudaMallocAsync(&out->nodes4, sizeof(RcNode4) * ((size_t)nf + 1), st));
+    CK(cudaMallocAsync(&out->tris, sizeof(RcTri) * (size_t)nf, st));
+    CK(cudaMallocAsync(&out->hull, sizeof(RcBox) * RC_HULL_BOXES, st));
+    out->n_faces_in = n_faces;
+
+    CK(cudaMemsetAsync(d_ctl, 0, sizeof(uint32_t) * (CTL_WORDS + f_tiles), st));
+    k_filter<<<f_tiles, FILTER_T, 0, st>>>(d_verts, d_face_meta, n_faces, d_tris_in, d_ctl, d_ctl + CTL_WORDS);
+    k_morton_prims<<<s_tiles, RS_THREADS, 0, st>>>(d_tris_in, d_ctl, d_codes, d_idx, s_tiles, d_hist);
+    uint32_t *codes_sorted = nullptr, *perm = nullptr;
+    radix_sort_pairs(st, d_codes, d_idx, d_codes2, d_idx2, d_ctl + CTL_N, nf, d_hist, true, &codes_sorted, &perm);
+    build_tree(st, codes_sorted, d_ctl + CTL_N, nf, d_tris_in, perm, out->tris, nullptr, nullptr, RC_BLAS_LEAF_MAX, d_topo, d_parent, d_fl, d_boxes, out->nodes2, out->nodes4,
+               out->hull, d_ctl);
+    k_finish<<<1, 32, 0, st>>>(d_boxes, reinterpret_cast<float *>(d_ctl + CTL_OUT), d_ctl, out->nodes4);
+    return finish_blas(st, d_ctl, out, err);
+}
+
+// Vertex update with unchanged topology (update!, src/instanced-bvh.jl:808-857, as a refit): the kept radix tree is re-fitted to the new
+// vertex positions of the same faces.  Allowed when the geometry was built with RC_BUILD_ALLOW_REFIT, the face count is unchanged and
+// the set of degenerate faces is the same (*refitted = false otherwise: the caller rebuilds).
+__global__ void k_refit_gather(const float *__restrict__ verts, uint32_t n_faces, RcTri *__restrict__ tris, uint32_t n, uint32_t *__restrict__ ctl) {
+    // pass A (blockIdx.y == 0): every sorted triangle takes its face's new vertices; a kept face that became degenerate is counted
+    // pass B (blockIdx.y == 1): valid faces of the new soup are counted (must equal n)
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    f3 lo = mk3(INFINITY, INFINITY, INFINITY), hi = mk3(-INFINITY, -INFINITY, -INFINITY);
+    if (blockIdx.y == 0) {
+        if (i < n) {
+            float4 *t = reinterpret_cast<float4 *>(tris + i);
+            const uint32_t face = __float_as_uint(t[2].w);
+            const float *v = verts + (size_t)face * 9;
+            const f3 a = ld3(v), b = ld3(v + 3), c = ld3(v + 6);
+            if (x_is_degenerate(a, b, c)) atomicAdd(&ctl[CTL_TILE], 1u);
+            t[0] = make_float4(a.x, a.y, a.z, t[0].w);
+            t[1] = make_float4(b.x, b.y, b.z, t[1].w);
+            t[2] = make_float4(c.x, c.y, c.z, t[2].w);
+            lo = jl_min3(jl_min3(a, b), c);
+            hi = jl_max3(jl_max3(a, b), c);
+        }
+        bounds_atomic(ctl, lo, hi);
+    } else if (i < n_faces) {
+        const float *v = verts + (size_t)i * 9;
+        if (!x_is_degenerate(ld3(v), ld3(v + 3), ld3(v + 6))) atomicAdd(&ctl[CTL_TILE + 1], 1u);
+    }
+}
+
+bool rc_refit_blas(cudaStream_t st, const float *d_verts, uint32_t n_faces, RcDeviceBlas *b, bool *refitted, std::string &err) {
+    *refitted = false;
+    if (!b->topo || !b->parent || n_faces != b->n_faces_in || b->n == 0) return true;
+    const uint32_t n = b->n;
+    RcTemps tmp(st);
+    uint32_t *d_ctl = nullptr, *d_fl = nullptr;
+    RcBox *d_boxes = nullptr;
+    TMP(d_ctl, CTL_WORDS);
+    TMP(d_fl, n);
+    TMP(d_boxes, 2 * (size_t)n);
+    CK(cudaMemsetAsync(d_ctl, 0, sizeof(uint32_t) * CTL_WORDS, st));
+    // the triangles are updated in place; if the check below fails the caller rebuilds from the new vertices anyway
+    dim3 grid(cdiv(std::max(n, n_faces), 256), 2);
+    k_refit_gather<<<grid, 256, 0, st>>>(d_verts, n_faces, b->tris, n, d_ctl);
+    uint32_t h[CTL_TILE + 2];
+    CK(cudaMemcpyAsync(h, d_ctl, sizeof h, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (h[CTL_TILE] != 0 || h[CTL_TILE + 1] != n) return true;  // the degenerate set changed: primitive numbering would differ
+    uint32_t n_word = n;
+    CK(cudaMemcpyAsync(d_ctl + CTL_N, &n_word, 4, cudaMemcpyHostToDevice, st));
+    if (n > 1) CK(cudaMemsetAsync(d_fl, 0, sizeof(uint32_t) * (n - 1), st));
+    launch_fit(st, n, nullptr, nullptr, b->tris, nullptr, nullptr, nullptr, b->topo, b->parent, d_fl, d_boxes, b->nodes2, d_ctl);
+    k_collapse<<<cdiv(n > 1 ? n - 1 : 1, 256) + 1, 256, 0, st>>>(d_boxes, b->topo, nullptr, n, RC_BLAS_LEAF_MAX, nullptr, b->nodes4, b->hull);
+    k_finish<<<1, 32, 0, st>>>(d_boxes, reinterpret_cast<float *>(d_ctl + CTL_OUT), d_ctl);
+    RcDeviceBlas probe;
+    if (!finish_blas(st, d_ctl, &probe, err)) return false;
+    memcpy(b->root_aabb, probe.root_aabb, 24);
+    memcpy(b->sphere, probe.sphere, 16);
+    *refitted = true;
+    return true;
 }
 
 
@@ -641,8 +869,7 @@ __global__ void k_morton_instances(const rc_instance_desc *__restrict__ inst, co
                                    uint32_t *__restrict__ codes, uint32_t *__restrict__ idx) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    f3 smin = mk3(rc_ordered_to_float(bounds[0]), rc_ordered_to_float(bounds[1]), rc_ordered_to_float(bounds[2]));
-    f3 smax = mk3(rc_ordered_to_float(bounds[3]), rc_ordered_to_float(bounds[4]), rc_ordered_to_float(bounds[5]));
+    f3 smin = ctl_bounds_min(bounds), smax = ctl_bounds_max(bounds);  // bounds = the build's control block
     f3 ext = mk3(jl_max(x_sub(smax.x, smin.x), 1e-6f), jl_max(x_sub(smax.y, smin.y), 1e-6f), jl_max(x_sub(smax.z, smin.z), 1e-6f));
     const rc_instance_desc *d = inst + i;
     const float *la = blas_roots + 6 * (d->blas_index - 1);
@@ -695,8 +922,7 @@ bool rc_build_tlas(cudaStream_t st, const rc_instance_desc *h_inst, uint32_t n, 
     if (n == 0) return true;  // empty TLAS: zero nodes (:969-978)
     const int T = 256;
     uint32_t nb = (uint32_t)blas.size();
-    uint32_t rs_tiles = cdiv(n, RS_TILE);
-    uint32_t *d_codes = nullptr, *d_codes2 = nullptr, *d_idx2 = nullptr, *d_hist = nullptr;
+    uint32_t *d_codes = nullptr, *d_idx = nullptr, *d_codes2 = nullptr, *d_idx2 = nullptr, *d_hist = nullptr;
     RcTemps tmp(st);
     CK(cudaMallocAsync(&t->d_inst, sizeof(rc_instance_desc) * n, st));
     CK(cudaMallocAsync(&t->d_blas_roots, sizeof(float) * 6 * nb, st));
@@ -713,23 +939,25 @@ bool rc_build_tlas(cudaStream_t st, const rc_instance_desc *h_inst, uint32_t n, 
     CK(cudaMallocAsync(&t->boxes, sizeof(RcBox) * (2 * n - 1), st));
     CK(cudaMallocAsync(&t->nodes2, sizeof(RcNode2) * (2 * n - 1), st));
     CK(cudaMallocAsync(&t->nodes4, sizeof(RcNode4) * (n + 1), st));
-    CK(cudaMallocAsync(&t->d_small, sizeof(uint32_t) * 16, st));
+    CK(cudaMallocAsync(&t->d_small, sizeof(uint32_t) * CTL_WORDS, st));
     TMP(d_codes, n);
+    TMP(d_idx, n);
     TMP(d_codes2, n);
     TMP(d_idx2, n);
-    TMP(d_hist, 256 * (size_t)rs_tiles + 256);
+    TMP(d_hist, radix_hist_words(n));
     CK(cudaMemcpyAsync(t->d_blas_roots, blas_roots.data(), sizeof(float) * 6 * nb, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(t->d_blas_ptrs, blas.data(), sizeof(RcBlasPtrs) * nb, cudaMemcpyHostToDevice, st));
     if (!upload_instances(st, t, h_inst, n, err)) return false;
-    uint32_t *d_bounds = t->d_small + 4;
-    k_init_bounds<<<1, 32, 0, st>>>(d_bounds);
-    k_instance_boxes<<<cdiv(n, T), T, 0, st>>>(t->d_inst, t->d_blas_roots, n, t->inst_boxes, d_bounds, t->d_blas_ptrs, t->inst_boxes_tight);
-    k_morton_instances<<<cdiv(n, T), T, 0, st>>>(t->d_inst, t->d_blas_roots, n, d_bounds, d_codes, t->leaf_map);
-    radix_sort_pairs(st, d_codes, t->leaf_map, d_codes2, d_idx2, n, d_hist);  // leaf_map = sorted position -> instance index
-    build_tree(st, d_codes, n, nullptr, t->inst_boxes, t->leaf_map, 1, t->topo, t->parent, t->flags, t->boxes, t->nodes2, t->nodes4, t->inst_boxes_tight,
-               t->boxes_tight);
-    k_read_root<<<1, 32, 0, st>>>(t->boxes, reinterpret_cast<float *>(t->d_small + 10));
-    CK(cudaMemcpyAsync(t->root_aabb, t->d_small + 10, 24, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemsetAsync(t->d_small, 0, sizeof(uint32_t) * CTL_WORDS, st));
+    k_instance_boxes<<<cdiv(n, T), T, 0, st>>>(t->d_inst, t->d_blas_roots, n, t->inst_boxes, t->d_small, t->d_blas_ptrs, t->inst_boxes_tight);
+    k_morton_instances<<<cdiv(n, T), T, 0, st>>>(t->d_inst, t->d_blas_roots, n, t->d_small, d_codes, d_idx);
+    uint32_t *codes_sorted = nullptr, *order = nullptr;
+    radix_sort_pairs(st, d_codes, d_idx, d_codes2, d_idx2, nullptr, n, d_hist, false, &codes_sorted, &order);
+    CK(cudaMemcpyAsync(t->leaf_map, order, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, st));  // leaf_map = sorted position -> instance index
+    build_tree(st, codes_sorted, nullptr, n, nullptr, nullptr, nullptr, t->inst_boxes, t->leaf_map, 1, t->topo, t->parent, t->flags, t->boxes, t->nodes2, t->nodes4, nullptr,
+               nullptr, t->inst_boxes_tight, t->boxes_tight);
+    k_finish<<<1, 32, 0, st>>>(t->boxes, reinterpret_cast<float *>(t->d_small + CTL_OUT), nullptr);
+    CK(cudaMemcpyAsync(t->root_aabb, t->d_small + CTL_OUT, 24, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     return extent_supported(t->root_aabb, err);
@@ -742,8 +970,8 @@ bool rc_refit_tlas(cudaStream_t st, const rc_instance_desc *h_inst, uint32_t n, 
     // update_tlas_leaf_aabbs_kernel! (kernels.jl:487-519) + refit_tlas_aabbs_kernel! (:381-428), then re-quantise the wide nodes
     k_instance_boxes<<<cdiv(n, 256), 256, 0, st>>>(t->d_inst, t->d_blas_roots, n, t->inst_boxes, nullptr, t->d_blas_ptrs, t->inst_boxes_tight);
     refit_tree(st, n, t->inst_boxes, t->leaf_map, 1, t->topo, t->parent, t->flags, t->boxes, t->nodes2, t->nodes4, t->inst_boxes_tight, t->boxes_tight);
-    k_read_root<<<1, 32, 0, st>>>(t->boxes, reinterpret_cast<float *>(t->d_small + 10));
-    CK(cudaMemcpyAsync(t->root_aabb, t->d_small + 10, 24, cudaMemcpyDeviceToHost, st));
+    k_finish<<<1, 32, 0, st>>>(t->boxes, reinterpret_cast<float *>(t->d_small + CTL_OUT), nullptr);
+    CK(cudaMemcpyAsync(t->root_aabb, t->d_small + CTL_OUT, 24, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     return extent_supported(t->root_aabb, err);
@@ -760,7 +988,7 @@ static_assert(sizeof(RcBox) == 32, "blob layout");
 static_assert(sizeof(RcNode2) == 64 && sizeof(RcNode4) == 64 && sizeof(RcTri) == 48, "blob layout");
 
 struct RcBlobHeader {
-    char magic[8];  // "RCBLAS\0\1"
+    char magic[8];  // "RCBLAS\0\2"
     uint32_t abi_version, leaf_max, hull_boxes, n, n_faces_in, has_normals;
     float root_aabb[6];
     uint64_t total_bytes, payload_hash;
@@ -768,13 +996,14 @@ struct RcBlobHeader {
     float sphere[4];  // bounding sphere (centre, radius^2) of the instance-entry cull
 };
 static_assert(sizeof(RcBlobHeader) == 128, "blob header is 128 bytes");
-static const char RC_BLOB_MAGIC[8] = {'R', 'C', 'B', 'L', 'A', 'S', 0, 1};
+static const char RC_BLOB_MAGIC[8] = {'R', 'C', 'B', 'L', 'A', 'S', 0, 2};
 
 static inline uint64_t up64(uint64_t x) { return (x + 63u) & ~(uint64_t)63u; }
 
-static void blob_layout(uint32_t n, bool normals, RcBlobHeader *h) {
+static void blob_layout(uint32_t n, bool normals, bool nodes2, RcBlobHeader *h) {
     uint64_t o = sizeof(RcBlobHeader);
-    h->off_nodes2 = o; o = up64(o + sizeof(RcNode2) * (2 * (uint64_t)n - 1));
+    h->off_nodes2 = nodes2 ? o : 0;  // the reference-layout BVH2 travels only when the geometry was built with RC_BUILD_KEEP_BVH2
+    if (nodes2) o = up64(o + sizeof(RcNode2) * (2 * (uint64_t)n - 1));
     h->off_nodes4 = o; o = up64(o + sizeof(RcNode4) * ((uint64_t)n + 1));
     h->off_tris = o;   o = up64(o + sizeof(RcTri) * (uint64_t)n);
     h->off_hull = o;   o = up64(o + sizeof(RcBox) * RC_HULL_BOXES);
@@ -799,12 +1028,12 @@ static uint64_t blob_hash(const uint8_t *p, uint64_t bytes) {
 
 uint64_t rc_blas_blob_bytes(const RcDeviceBlas &b) {
     RcBlobHeader h;
-    blob_layout(b.n, b.normals != nullptr, &h);
+    blob_layout(b.n, b.normals != nullptr, b.nodes2 != nullptr, &h);
     return h.total_bytes;
 }
 
 bool rc_blas_export(cudaStream_t st, const RcDeviceBlas &b, void *blob, uint64_t capacity, std::string &err) {
-    if (b.n == 0 || !b.nodes2 || !b.nodes4 || !b.tris || !b.hull) { err = "export: geometry is not built"; return false; }
+    if (b.n == 0 || !b.nodes4 || !b.tris || !b.hull) { err = "export: geometry is not built"; return false; }
     RcBlobHeader h;
     memset(&h, 0, sizeof h);
     memcpy(h.magic, RC_BLOB_MAGIC, 8);
@@ -816,20 +1045,18 @@ bool rc_blas_export(cudaStream_t st, const RcDeviceBlas &b, void *blob, uint64_t
     h.has_normals = b.normals ? 1u : 0u;
     memcpy(h.root_aabb, b.root_aabb, 24);
     memcpy(h.sphere, b.sphere, 16);
-    blob_layout(b.n, b.normals != nullptr, &h);
+    blob_layout(b.n, b.normals != nullptr, b.nodes2 != nullptr, &h);
     if (capacity < h.total_bytes) { err = "export: capacity too small"; return false; }
     uint8_t *p = static_cast<uint8_t *>(blob);
     memset(p + sizeof h, 0, h.total_bytes - sizeof h);  // alignment gaps are part of the hashed payload
     const uint64_t n = b.n;
-    CK(cudaMemcpyAsync(p + h.off_nodes2, b.nodes2, sizeof(RcNode2) * (2 * n - 1), cudaMemcpyDeviceToHost, st));
+    if (b.nodes2) CK(cudaMemcpyAsync(p + h.off_nodes2, b.nodes2, sizeof(RcNode2) * (2 * n - 1), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(p + h.off_nodes4, b.nodes4, sizeof(RcNode4) * (n + 1), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(p + h.off_tris, b.tris, sizeof(RcTri) * n, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(p + h.off_hull, b.hull, sizeof(RcBox) * RC_HULL_BOXES, cudaMemcpyDeviceToHost, st));
     if (b.normals) CK(cudaMemcpyAsync(p + h.off_normals, b.normals, sizeof(float) * 9 * n, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    // wide-node slots no kernel writes (slot 0; slot n when there are internal nodes) are zeroed so equal geometry gives equal blobs
-    memset(p + h.off_nodes4, 0, sizeof(RcNode4));
-    if (n > 1) memset(p + h.off_nodes4 + sizeof(RcNode4) * n, 0, sizeof(RcNode4));
+    // (every wide-node slot is written by the builder — unused ones are zeroed — so equal geometry gives equal blobs)
     h.payload_hash = blob_hash(p + sizeof h, h.total_bytes - sizeof h);
     memcpy(p, &h, sizeof h);
     return true;
@@ -837,11 +1064,16 @@ bool rc_blas_export(cudaStream_t st, const RcDeviceBlas &b, void *blob, uint64_t
 
 // structural check of an uploaded blob (rc_validate_blas_elem, rc_build_core.cuh): every reference stays inside the arrays and no
 // cycle is reachable from a root, so a damaged blob can neither send a traversal out of bounds nor make it spin
-__global__ void k_validate_blas(const RcNode2 *__restrict__ nodes2, const RcNode4 *__restrict__ nodes4, const RcTri *__restrict__ tris, uint32_t n,
-                                uint32_t n_faces_in, uint32_t *__restrict__ bad) {
+__global__ void k_validate_static(const RcNode2 *__restrict__ nodes2, const RcTri *__restrict__ tris, uint32_t n, uint32_t n_faces_in, uint32_t *__restrict__ bad) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t errs = rc_validate_blas_elem(i, nodes2, nodes4, tris, n, RC_BLAS_LEAF_MAX, n_faces_in);
+    const uint32_t errs = rc_validate_static_elem(i, nodes2, tris, n, n_faces_in);
     if (errs) atomicAdd(bad, errs);
+}
+// one breadth-first level of the wide-node check; state[0] = violations, state[1] = nodes marked for the next level, mark[k] = level of wide node k
+__global__ void k_validate_wide(uint32_t level, const RcNode4 *__restrict__ nodes4, uint32_t n, uint32_t *__restrict__ mark, uint32_t *__restrict__ state) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t errs = rc_validate_wide_level(i, level, nodes4, n, RC_BLAS_LEAF_MAX, mark, state + 1);
+    if (errs) atomicAdd(state, errs);
 }
 
 // host-side checks of a blob (no GPU involved): magic, layout version, section table, size, payload hash, supported extent
@@ -855,7 +1087,7 @@ static bool blob_check(const void *blob, uint64_t size, RcBlobHeader &h, std::st
     }
     if (h.n == 0 || h.n > RC_LEAF_START_MASK - 16u || h.n_faces_in < h.n) { err = "import: bad triangle count"; return false; }
     RcBlobHeader want = h;
-    blob_layout(h.n, h.has_normals != 0, &want);
+    blob_layout(h.n, h.has_normals != 0, h.off_nodes2 != 0, &want);
     if (want.total_bytes != h.total_bytes || want.off_nodes2 != h.off_nodes2 || want.off_nodes4 != h.off_nodes4 || want.off_tris != h.off_tris ||
         want.off_hull != h.off_hull || want.off_normals != h.off_normals) {
         err = "import: section table does not match the triangle count";
@@ -884,8 +1116,8 @@ bool rc_blas_import(cudaStream_t st, const void *blob, uint64_t size, RcDeviceBl
     const uint64_t n = h.n;
     uint32_t *d_bad = nullptr;
     RcTemps tmp(st);
-    TMP(d_bad, 1);
-    CK(cudaMallocAsync(&out->nodes2, sizeof(RcNode2) * (2 * n - 1), st));
+    TMP(d_bad, n + 3);  // [0] violations, [1] nodes marked by the current level, [2 + k] breadth-first level of wide node k
+    if (h.off_nodes2) CK(cudaMallocAsync(&out->nodes2, sizeof(RcNode2) * (2 * n - 1), st));
     CK(cudaMallocAsync(&out->nodes4, sizeof(RcNode4) * (n + 1), st));
     CK(cudaMallocAsync(&out->tris, sizeof(RcTri) * n, st));
     CK(cudaMallocAsync(&out->hull, sizeof(RcBox) * RC_HULL_BOXES, st));
@@ -894,16 +1126,23 @@ bool rc_blas_import(cudaStream_t st, const void *blob, uint64_t size, RcDeviceBl
     out->n_faces_in = h.n_faces_in;
     memcpy(out->root_aabb, h.root_aabb, 24);
     memcpy(out->sphere, h.sphere, 16);
-    CK(cudaMemcpyAsync(out->nodes2, p + h.off_nodes2, sizeof(RcNode2) * (2 * n - 1), cudaMemcpyHostToDevice, st));
+    if (h.off_nodes2) CK(cudaMemcpyAsync(out->nodes2, p + h.off_nodes2, sizeof(RcNode2) * (2 * n - 1), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(out->nodes4, p + h.off_nodes4, sizeof(RcNode4) * (n + 1), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(out->tris, p + h.off_tris, sizeof(RcTri) * n, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(out->hull, p + h.off_hull, sizeof(RcBox) * RC_HULL_BOXES, cudaMemcpyHostToDevice, st));
     if (h.has_normals) CK(cudaMemcpyAsync(out->normals, p + h.off_normals, sizeof(float) * 9 * n, cudaMemcpyHostToDevice, st));
-    CK(cudaMemsetAsync(d_bad, 0, 4, st));
-    k_validate_blas<<<cdiv((uint32_t)(2 * n), 256), 256, 0, st>>>(out->nodes2, out->nodes4, out->tris, h.n, h.n_faces_in, d_bad);
-    uint32_t bad = 0;
-    CK(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));  // the caller may release the blob on return
+    CK(cudaMemsetAsync(d_bad, 0, sizeof(uint32_t) * (n + 3), st));
+    k_validate_static<<<cdiv((uint32_t)(2 * n), 256), 256, 0, st>>>(out->nodes2, out->tris, h.n, h.n_faces_in, d_bad);
+    uint32_t one = 1, state[2] = {0, 1}, bad = 0;
+    CK(cudaMemcpyAsync(d_bad + 2 + 1, &one, 4, cudaMemcpyHostToDevice, st));  // mark[root] = level 1
+    for (uint32_t level = 1; state[1] != 0 && state[0] == 0; level++) {  // one launch per tree level (a few dozen): an import is not a hot path
+        CK(cudaMemsetAsync(d_bad + 1, 0, 4, st));
+        k_validate_wide<<<cdiv((uint32_t)n + 1, 256), 256, 0, st>>>(level, out->nodes4, h.n, d_bad + 2, d_bad);
+        CK(cudaMemcpyAsync(state, d_bad, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));  // (also: the caller may release the blob on return)
+        if (level > h.n + 1) { state[0]++; break; }  // cannot happen: every node is marked at most once
+    }
+    bad = state[0];
     CK(cudaGetLastError());
     if (bad) { err = "import: blob fails the structural check (" + std::to_string(bad) + " bad references)"; return false; }
     return true;

@@ -14,10 +14,12 @@ struct RcTopo;
 struct RcDeviceBlas {
     uint32_t n = 0;           // valid (non-degenerate) triangles
     uint32_t n_faces_in = 0;  // faces submitted
-    RcNode2 *nodes2 = nullptr;  // 2n-1, reference layout, node k at [k-1]
+    RcNode2 *nodes2 = nullptr;  // 2n-1, reference layout, node k at [k-1]; only with RC_BUILD_KEEP_BVH2 (reference-order mode, BVH2 read-backs)
     RcNode4 *nodes4 = nullptr;  // n+1 slots, indexed by BVH2 internal node number, root = [1]
     RcTri *tris = nullptr;      // n, Morton-sorted
     RcBox *hull = nullptr;      // RC_HULL_BOXES boxes of BVH2 subtrees covering the whole BLAS (tight instance bounds for the wide TLAS)
+    RcTopo *topo = nullptr;     // kept radix tree (RC_BUILD_ALLOW_REFIT): per internal node children + span ...
+    uint32_t *parent = nullptr; // ... and parent links, so a vertex update can re-fit instead of rebuilding
     float *normals = nullptr;   // optional, 9 floats per primitive indexed by primitive_id (rc_set_normals; shading-side data of the wavefront stages)
     float root_aabb[6] = {0, 0, 0, 0, 0, 0};
     float sphere[4] = {0, 0, 0, INFINITY};  // bounding sphere in local space: centre = centre of the root box, radius^2 over all vertices (instance-entry cull)
@@ -55,7 +57,11 @@ struct RcDeviceTlas {
     float root_aabb[6] = {0, 0, 0, 0, 0, 0};
 };
 
-bool rc_build_blas(cudaStream_t st, const float *d_verts, const uint32_t *d_face_meta, uint32_t n_faces, RcDeviceBlas *out, std::string &err);
+// build_flags: RC_BUILD_KEEP_BVH2 | RC_BUILD_ALLOW_REFIT (include/raycore_cuda.h)
+bool rc_build_blas(cudaStream_t st, const float *d_verts, const uint32_t *d_face_meta, uint32_t n_faces, uint32_t build_flags, RcDeviceBlas *out, std::string &err);
+// re-fit a BLAS built with RC_BUILD_ALLOW_REFIT to new vertex positions of the same faces; *refitted = false when that is not possible
+// (no kept topology, face count or degenerate set changed) and the caller has to rebuild
+bool rc_refit_blas(cudaStream_t st, const float *d_verts, uint32_t n_faces, RcDeviceBlas *b, bool *refitted, std::string &err);
 void rc_free_blas(RcDeviceBlas *b, cudaStream_t st);
 // serialised BLAS (host blob <-> device arrays, byte-identical restore; layout in rc_build.cu)
 uint64_t rc_blas_blob_bytes(const RcDeviceBlas &b);

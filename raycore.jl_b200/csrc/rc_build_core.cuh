@@ -163,20 +163,24 @@ RC_HD RcNode4 rc_collapse_node(uint32_t idx, const RcBox *boxes, const RcTopo *t
     return nd;
 }
 
-// Structural check of one element of a BLAS (used on imported blobs): element i covers BVH2 node i+1, wide node i and triangle i.
-// Returns the number of violations.  Checked: (1) every reference stays inside its array — BVH2 internal nodes are 1..n-1 and leaves
-// n..2n-1 (src/instanced-bvh.jl:1293-1295, leaf: child0 == INVALID_NODE, child1 = 1-based primitive), wide nodes in use are
-// 1..max(1, n-1), leaf ranges lie inside the triangle array, prim_id < n, face_index < n_faces_in (rc_set_normals gathers by it);
-// (2) no cycle can be reached from either root: the two children of a BVH2 internal node are distinct and name it as their parent
-// and the root has none, so the 2n-2 child references reach 2n-2 distinct nodes and everything reachable from node 1 is a tree;
-// a wide node's node-children must be BVH2 descendants of it (the collapse opens at most three levels), so wide edges only go down
-// that tree.  A blob that passes cannot send a traversal out of bounds or into an endless loop.  Not checked (harmless for memory
-// safety and termination): that the boxes bound their subtrees and that prim_id values are distinct — import blobs you wrote.
-RC_HD uint32_t rc_validate_blas_elem(uint32_t i, const RcNode2 *nodes2, const RcNode4 *nodes4, const RcTri *tris, uint32_t n, uint32_t leaf_max,
-                                     uint32_t n_faces_in) {
+// Structural check of a BLAS (used on imported blobs).  A blob that passes can neither send a traversal out of bounds nor into an
+// endless loop.  Two parts:
+//   rc_validate_static_elem(i), i = 0 .. 2n-1: triangle i has prim_id < n and face_index < n_faces_in (rc_set_normals gathers by it);
+//       when the blob carries the reference-layout BVH2, node i+1 keeps to the numbering of src/instanced-bvh.jl:1293-1295 (internal
+//       1..n-1, leaves n..2n-1 with child0 == INVALID_NODE and a 1-based primitive in child1), the two children of an internal node
+//       are distinct and name it as their parent, and the root has none — so the 2n-2 child references reach 2n-2 distinct nodes and
+//       everything reachable from node 1 is a tree.
+//   rc_validate_wide_level(i, level), i = 1 .. max(1, n-1), level = 1, 2, ... until a level marks nothing: the wide nodes are checked
+//       in breadth-first order from the root (mark[1] = 1 to start).  A node marked `level` must be a real node (the builder leaves
+//       slots that head no wide node zeroed or stale; they are legal as long as nothing reachable points at them), its leaf ranges must
+//       lie inside the triangle array, its node references inside 1..max(1, n-1), and every node it references must be unmarked so
+//       far — a second reference to a node is what a cycle (or a DAG) reachable from the root needs, and is refused.
+// Not checked (harmless for memory safety and termination): that the boxes bound their subtrees and that prim_id values are
+// distinct — import blobs you wrote.
+RC_HD uint32_t rc_validate_static_elem(uint32_t i, const RcNode2 *nodes2 /* nullable */, const RcTri *tris, uint32_t n, uint32_t n_faces_in) {
     uint32_t errs = 0;
     const uint32_t n_nodes2 = 2u * n - 1u;
-    if (i < n_nodes2) {
+    if (nodes2 && i < n_nodes2) {
         const RcNode2 &nd = nodes2[i];
         if (i == 0u && nd.parent != RC_INVALID) errs++;
         if (i + 1u < n) {
@@ -186,29 +190,41 @@ RC_HD uint32_t rc_validate_blas_elem(uint32_t i, const RcNode2 *nodes2, const Rc
             errs++;
         }
     }
+    if (i < n && (tris[i].prim_id >= n || tris[i].face_index >= n_faces_in)) errs++;
+    return errs;
+}
+// returns violations; *marked counts the nodes this call marked for the next level
+RC_HD uint32_t rc_validate_wide_level(uint32_t i, uint32_t level, const RcNode4 *nodes4, uint32_t n, uint32_t leaf_max, uint32_t *mark /* n + 1 words */,
+                                      uint32_t *marked) {
     const uint32_t last = n > 1u ? n - 1u : 1u;
-    if (i >= 1u && i <= last) {
-        const RcNode4 &w = nodes4[i];
-        const uint32_t c[4] = {w.child0, w.child1, w.child2, w.child3};
-        for (int k = 0; k < 4; k++) {
-            if (c[k] & RC_LEAF_BIT) {
-                const uint32_t count = ((c[k] >> RC_LEAF_COUNT_SHIFT) & 7u) + 1u, start = c[k] & RC_LEAF_START_MASK;
-                if ((c[k] & RC_TLAS_LEAF_TAG) == RC_TLAS_LEAF_TAG || count > leaf_max || start >= n || count > n - start) errs++;
-            } else if (n == 1u || c[k] < 1u || c[k] > last) {
-                errs++;
-            } else {  // must hang below BVH2 node i: at most three parent steps lead from the child to i
-                uint32_t up = c[k];
-                bool below = false;
-                for (int s = 0; s < 3 && !below; s++) {
-                    up = nodes2[up - 1u].parent;
-                    if (up == i) below = true;
-                    else if (up < 1u || up > last) break;
-                }
-                if (!below) errs++;
+    if (i < 1u || i > last || mark[i] != level) return 0u;
+    uint32_t errs = 0;
+    const RcNode4 &w = nodes4[i];
+    const uint32_t c[4] = {w.child0, w.child1, w.child2, w.child3};
+    for (int k = 0; k < 4; k++) {
+        if (k > 0 && c[k] == c[0]) continue;  // an unused slot repeats child 0's reference (rc_types.h): one edge, not two
+        if (c[k] & RC_LEAF_BIT) {
+            const uint32_t count = ((c[k] >> RC_LEAF_COUNT_SHIFT) & 7u) + 1u, start = c[k] & RC_LEAF_START_MASK;
+            if ((c[k] & RC_TLAS_LEAF_TAG) == RC_TLAS_LEAF_TAG || count > leaf_max || start >= n || count > n - start) errs++;
+        } else if (n == 1u || c[k] < 1u || c[k] > last) {
+            errs++;  // (an empty slot fails here: reference 0)
+        } else {
+#if RC_ON_DEVICE
+            const uint32_t old = atomicCAS(&mark[c[k]], 0u, level + 1u);
+#else
+            const uint32_t old = mark[c[k]];
+            if (old == 0u) mark[c[k]] = level + 1u;
+#endif
+            if (old != 0u) errs++;
+            else {
+#if RC_ON_DEVICE
+                atomicAdd(marked, 1u);
+#else
+                ++*marked;
+#endif
             }
         }
     }
-    if (i < n && (tris[i].prim_id >= n || tris[i].face_index >= n_faces_in)) errs++;
     return errs;
 }
 

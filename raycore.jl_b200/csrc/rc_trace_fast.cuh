@@ -160,13 +160,17 @@ __device__ __forceinline__ float2 rc_q2f_pair(uint32_t w, int j) {
 // Two FMAs per issue slot: fma.rn.f32x2 (FFMA2 on sm_100a) with the scale and offset broadcast from scalar registers
 // (SASS: FFMA2 R8, R8.F32x2.HI_LO, R0.F32, R13.F32).  The node step is issue / ALU bound (profiles/r1_trace_c3_v20: issue slots 80 %,
 // FMA pipe 32 %), so halving the 24 slab FMAs' issue slots is free throughput.  Each component is an IEEE RN fma, same bits as fmaf.
+// Measured (profiles/README.md r2): -1.7 % on the instanced scene, +2.4 % on the single-instance variant (its 56-register budget has
+// no room for the aligned register pairs), so only the multi-instance variant uses the packed form.
 #ifndef RC_FFMA2
 #define RC_FFMA2 1
 #endif
+template <bool PACKED>
 __device__ __forceinline__ float2 rc_fma2(float2 q, float a, float b) {
 #if defined(RC_WARPSIM) || !RC_FFMA2
     return make_float2(fmaf(q.x, a, b), fmaf(q.y, a, b));
 #else
+    if (!PACKED) return make_float2(fmaf(q.x, a, b), fmaf(q.y, a, b));
     unsigned long long qq, aa, bb, r;
     asm("mov.b64 %0, {%1, %2};" : "=l"(qq) : "f"(q.x), "f"(q.y));
     asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(a));
@@ -463,8 +467,8 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, SINGLE ? RC_MIN_BLOCKS_SINGL
                 float tn[4];
 #pragma unroll
                 for (int j = 0; j < 2; j++) {
-                    const float2 tnx = rc_fma2(rc_q2f_pair(nx, j), ax, bx), tny = rc_fma2(rc_q2f_pair(ny, j), ay, by), tnz = rc_fma2(rc_q2f_pair(nz, j), az, bz);
-                    const float2 tfx = rc_fma2(rc_q2f_pair(fx, j), ax, bx), tfy = rc_fma2(rc_q2f_pair(fy, j), ay, by), tfz = rc_fma2(rc_q2f_pair(fz, j), az, bz);
+                    const float2 tnx = rc_fma2<!SINGLE>(rc_q2f_pair(nx, j), ax, bx), tny = rc_fma2<!SINGLE>(rc_q2f_pair(ny, j), ay, by), tnz = rc_fma2<!SINGLE>(rc_q2f_pair(nz, j), az, bz);
+                    const float2 tfx = rc_fma2<!SINGLE>(rc_q2f_pair(fx, j), ax, bx), tfy = rc_fma2<!SINGLE>(rc_q2f_pair(fy, j), ay, by), tfz = rc_fma2<!SINGLE>(rc_q2f_pair(fz, j), az, bz);
                     const float lo0 = fmaxf(fmaxf(tnx.x, tny.x), fmaxf(tnz.x, t_min));
                     const float hi0 = fminf(fminf(tfx.x, tfy.x), tfz.x);
                     const float lo1 = fmaxf(fmaxf(tnx.y, tny.y), fmaxf(tnz.y, t_min));

@@ -196,13 +196,17 @@ class StaticTLAS:
 class TLAS:
     """Mutable top-level acceleration structure, `AbstractAccel` (src/instanced-bvh.jl:261-358)."""
 
-    def __init__(self, device: Optional[int] = None):
+    def __init__(self, device: Optional[int] = None, *, keep_bvh2: bool = False, allow_refit: bool = False):
+        """keep_bvh2: also emit the reference-layout BVH2 of every geometry (RC_BUILD_KEEP_BVH2: reference-order mode, read_blas_nodes);
+        allow_refit: keep the radix tree so `update(..., refit=True)` can re-fit moved vertices (RC_BUILD_ALLOW_REFIT)."""
         self._lib = L.load()
         ctx = C.c_void_p()
         rc = self._lib.rc_create(-1 if device is None else int(device), C.byref(ctx))
         if rc != L.RC_OK:
             raise RaycoreError(rc, self._lib.rc_last_error(None).decode())
         self._ctx = ctx
+        if keep_bvh2 or allow_refit:
+            self._ck(self._lib.rc_set_build_flags(ctx, (L.RC_BUILD_KEEP_BVH2 if keep_bvh2 else 0) | (L.RC_BUILD_ALLOW_REFIT if allow_refit else 0)))
         self._meshes = {}  # handle id -> (verts, face_meta) kept to materialise Triangle results
         self._static: Optional[StaticTLAS] = None
         self._generation = 0
@@ -323,12 +327,17 @@ class TLAS:
             raise ValueError("device transforms must be float32 with 12 values per instance")
         self._ck(self._lib.rc_update_transforms_device(self._ctx, handle.id, transforms.ptr, None, transforms.count // 12))
 
-    def update(self, handle: TLASHandle, mesh, face_meta=None):
-        """update!(tlas, handle, new_geometry) — :808-857."""
+    def update(self, handle: TLASHandle, mesh, face_meta=None, refit: bool = False) -> bool:
+        """update!(tlas, handle, new_geometry) — :808-857.  refit=True asks for a re-fit of the kept radix tree (RC_UPDATE_REFIT: same faces,
+        moved vertices, geometry built with allow_refit); returns True when the library re-fitted, False when it rebuilt."""
         v = self._verts(mesh)
         fm = None if face_meta is None else np.ascontiguousarray(face_meta, np.uint32)
-        self._ck(self._lib.rc_update_geometry(self._ctx, handle.id, v.ctypes.data, len(v), None if fm is None else fm.ctypes.data, 0))
-        self._meshes[handle.id] = (v, fm)
+        self._ck(self._lib.rc_update_geometry(self._ctx, handle.id, v.ctypes.data, len(v), None if fm is None else fm.ctypes.data, L.RC_UPDATE_REFIT if refit else 0))
+        refitted = bool(self._lib.rc_last_update_refitted(self._ctx))
+        old = self._meshes.get(handle.id)
+        self._meshes[handle.id] = (v, old[1] if refitted and old is not None else fm)  # a refit keeps the geometry's metadata
+        self._face_cache.clear()
+        return refitted
 
     def sync(self) -> "TLAS":
         """sync!(tlas) — :894-921."""

@@ -65,7 +65,7 @@ def main():
 
     # ---- C2 extras: any_hit and reference-order mode on the 1M-triangle mesh --------------------------------------------
     verts = W.bumpy_sphere(709)
-    tl = rc.TLAS()
+    tl = rc.TLAS(keep_bvh2=True)
     tl.push(verts, None, instance_id=1)
     tl.sync()
     rays = W.interior_rays(NR, 77, radius=0.8)

@@ -79,7 +79,7 @@ class GpuEngine:
 
         self.name = "cuda-ref" if reference_order else "cuda-wide"
         self.reference_order = reference_order
-        self.tlas = rc.TLAS()
+        self.tlas = rc.TLAS(keep_bvh2=True)  # the parity tests read the BVH2 back and use the reference-order mode
         self.handles = []
         for p in pushes:
             verts, fm, xf, ids = _norm_push(p)

@@ -321,7 +321,7 @@ uint32_t hs_check_wide(void *b) {
 // 1 wide-node child index past the last node, 2 leaf range past the triangle array, 3 BVH2 child out of range, 4 BVH2 leaf
 // primitive out of range, 5 triangle prim_id out of range, 6 TLAS-tagged reference inside a BLAS, 7 wide node naming itself as a child
 // (a cycle: the traversal would never end), 8 BVH2 node naming itself as a child, 9 triangle face_index past the submitted faces,
-// 10 wide child that is in range but not below its node.  `where` picks the element.
+// 10 a reference to the root, 11 one wide node referenced twice, 12 a referenced wide slot that is empty.  `where` picks the element.
 uint32_t hs_validate_blas(void *b, int corrupt, uint32_t where) {
     HsBlas *B = (HsBlas *)b;
     HsTree &t = B->tree;
@@ -329,7 +329,14 @@ uint32_t hs_validate_blas(void *b, int corrupt, uint32_t where) {
     std::vector<RcNode2> nodes2 = t.nodes2;
     std::vector<RcNode4> nodes4 = t.nodes4;
     std::vector<RcTri> tris = B->tris;
-    const uint32_t w = 1 + where % last;
+    // wide-node faults are injected into a node the traversal can reach (slots nothing points at may hold anything: they are never read)
+    std::vector<uint32_t> reach{1};
+    for (size_t q = 0; q < reach.size() && n > 1; q++) {
+        const uint32_t c[4] = {nodes4[reach[q]].child0, nodes4[reach[q]].child1, nodes4[reach[q]].child2, nodes4[reach[q]].child3};
+        for (int k = 0; k < 4; k++)
+            if (!(c[k] & RC_LEAF_BIT) && (k == 0 || c[k] != c[0])) reach.push_back(c[k]);
+    }
+    const uint32_t w = reach[where % reach.size()];
     switch (corrupt) {
         case 1: nodes4[w].child1 = last + 1; break;
         case 2: nodes4[w].child0 = RC_LEAF_BIT | ((RC_BLAS_LEAF_MAX - 1u) << RC_LEAF_COUNT_SHIFT) | (n - RC_BLAS_LEAF_MAX + 1u); break;
@@ -337,14 +344,30 @@ uint32_t hs_validate_blas(void *b, int corrupt, uint32_t where) {
         case 4: nodes2[n - 1 + where % n].child1 = n + 1; break;
         case 5: tris[where % n].prim_id = n; break;
         case 6: nodes4[w].child2 = RC_TLAS_LEAF_TAG | 0u; break;
-        case 7: nodes4[w].child0 = w; break;
+        case 7: nodes4[w].child1 = w; break;
         case 8: if (n > 1) nodes2[where % (n - 1)].child0 = 1 + where % (n - 1); else nodes2[0].child0 = 1; break;
         case 9: tris[where % n].face_index = B->n_faces_in; break;
-        case 10: nodes4[w].child3 = 1; break;  // the root is below no node
+        case 10: nodes4[w].child3 = 1; break;  // nothing may point at the root
+        case 11: {  // two nodes naming the same child (in-degree 2: the shape a cycle reachable from the root needs)
+            if (reach.size() > 2) nodes4[reach[1]].child1 = reach.back() == reach[1] ? reach[2] : reach.back(); else nodes4[1].child1 = 1;
+            break;
+        }
+        case 12: {  // a referenced slot that is empty
+            uint32_t c = nodes4[1].child0;
+            if (!(c & RC_LEAF_BIT)) memset(&nodes4[c], 0, sizeof(RcNode4)); else nodes4[1].child0 = last + 7;
+            break;
+        }
         default: break;
     }
     uint32_t bad = 0;
-    for (uint32_t i = 0; i < 2 * n; i++) bad += rc_validate_blas_elem(i, nodes2.data(), nodes4.data(), tris.data(), n, RC_BLAS_LEAF_MAX, B->n_faces_in);
+    for (uint32_t i = 0; i < 2 * n; i++) bad += rc_validate_static_elem(i, nodes2.data(), tris.data(), n, B->n_faces_in);
+    std::vector<uint32_t> mark(n + 1, 0u);
+    mark[1] = 1;
+    uint32_t marked = 1;
+    for (uint32_t level = 1; marked != 0 && bad == 0 && level <= n + 1; level++) {  // the loop of rc_blas_import
+        marked = 0;
+        for (uint32_t i = 1; i <= last; i++) bad += rc_validate_wide_level(i, level, nodes4.data(), n, RC_BLAS_LEAF_MAX, mark.data(), &marked);
+    }
     return bad;
 }
 

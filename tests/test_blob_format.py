@@ -15,8 +15,9 @@ def _up64(x):
     return (x + 63) & ~63
 
 
-def make_blob(verts, normals=False):
-    """A blob with the library's layout: header + BVH2 nodes (64 B) + wide-node slots (zero here) + sorted triangles + hull (+ normals)."""
+def make_blob(verts, normals=False, bvh2=True):
+    """A blob with the library's layout: header [+ BVH2 nodes (64 B), only for geometry built with RC_BUILD_KEEP_BVH2] + wide-node slots
+    (zero here) + sorted triangles + hull (+ normals)."""
     b = hs.HsBlas(verts)
     n = b.n
     order = b.order()
@@ -24,19 +25,21 @@ def make_blob(verts, normals=False):
     keep = np.nonzero(~W.is_degenerate(v))[0]
     hdr = np.zeros(1, T.BLOB_HEADER_DTYPE)
     o = 128
-    hdr["off_nodes2"] = o; o = _up64(o + 64 * (2 * n - 1))
+    if bvh2:
+        hdr["off_nodes2"] = o; o = _up64(o + 64 * (2 * n - 1))
     hdr["off_nodes4"] = o; o = _up64(o + 64 * (n + 1))
     hdr["off_tris"] = o; o = _up64(o + 48 * n)
     hdr["off_hull"] = o; o = _up64(o + 32 * 16)
     if normals:
         hdr["off_normals"] = o; o = _up64(o + 36 * n)
-    hdr["magic"], hdr["abi_version"], hdr["leaf_max"], hdr["hull_boxes"] = b"RCBLAS\x00\x01", 1, 2, 16
+    hdr["magic"], hdr["abi_version"], hdr["leaf_max"], hdr["hull_boxes"] = b"RCBLAS\x00\x02", 1, 2, 16
     hdr["n"], hdr["n_faces_in"], hdr["has_normals"], hdr["total_bytes"] = n, len(v), int(normals), o
     hdr["root_aabb"] = b.root()
     blob = np.zeros(o, np.uint8)
-    nodes = np.zeros((2 * n - 1, 64), np.uint8)
-    nodes[:, :60] = b.nodes2().view(np.uint8).reshape(-1, 60)
-    blob[int(hdr["off_nodes2"][0]):][: nodes.size] = nodes.reshape(-1)
+    if bvh2:
+        nodes = np.zeros((2 * n - 1, 64), np.uint8)
+        nodes[:, :60] = b.nodes2().view(np.uint8).reshape(-1, 60)
+        blob[int(hdr["off_nodes2"][0]):][: nodes.size] = nodes.reshape(-1)
     tri = np.zeros(n, T.BLOB_TRI_DTYPE)
     src = v[keep][order]
     tri["v0"], tri["v1"], tri["v2"] = src[:, 0:3], src[:, 3:6], src[:, 6:9]
@@ -70,8 +73,12 @@ def test_wellformed_blob_is_accepted_and_parsed(normals):
 
 
 def test_single_triangle_blob_size():
-    blob = make_blob(np.array([[0, 0, 1, 1, 0, 1, 0, 1, 1]], np.float32))
+    tri = np.array([[0, 0, 1, 1, 0, 1, 0, 1, 1]], np.float32)
+    blob = make_blob(tri)
     assert blob.nbytes == 128 + 64 + 128 + 64 + 512 and T.check_exported(blob) == (1, 1, False)
+    # the default build carries no reference-layout BVH2: the section is simply absent (off_nodes2 == 0)
+    blob = make_blob(tri, bvh2=False)
+    assert blob.nbytes == 128 + 128 + 64 + 512 and T.check_exported(blob) == (1, 1, False) and T.blob_header(blob)["off_nodes2"] == 0
 
 
 def test_damaged_blobs_are_refused_on_the_host():

@@ -38,7 +38,7 @@ def _scene():
 
 def test_export_import_round_trip_is_byte_identical():
     sphere, box, xs, xb, ids = _scene()
-    a = rc.TLAS()
+    a = rc.TLAS(keep_bvh2=True)
     hs_ = a.push(sphere, list(xs), instance_ids=ids)
     hb = a.push(box, list(xb))
     rng = np.random.default_rng(5)
@@ -61,7 +61,7 @@ def test_export_import_round_trip_is_byte_identical():
     keep = np.array([i for i in range(len(box)) if i != 5])
     assert np.array_equal(faces[keep], box[keep]) and not faces[5].any()
 
-    b = rc.TLAS()
+    b = rc.TLAS(keep_bvh2=True)
     gs = b.push_exported(blob_s.tobytes(), list(xs), instance_ids=ids)  # bytes and arrays are both accepted
     gb = b.push_exported(blob_b, list(xb))
     assert b.n_geometries() == 2 and b.n_instances() == 42 and b.dirty
@@ -108,7 +108,7 @@ def test_export_import_round_trip_is_byte_identical():
 
 def test_single_triangle_and_size_query():
     tri = np.array([[0, 0, 1, 1, 0, 1, 0, 1, 1]], F)
-    a = rc.TLAS()
+    a = rc.TLAS(keep_bvh2=True)
     h = a.push(tri)
     a.sync()
     size = C.c_uint64()
@@ -117,7 +117,7 @@ def test_single_triangle_and_size_query():
     assert size.value == blob.nbytes == 128 + 64 + 128 + 64 + 512  # header, 1 BVH2 node, 2 wide slots, 1 triangle (48 -> 64), hull
     small = np.zeros(blob.nbytes - 1, np.uint8)
     assert a._lib.rc_export_geometry(a._ctx, h.id, small.ctypes.data, small.nbytes, C.byref(size)) == L.RC_ERR_INVALID_ARGUMENT
-    b = rc.TLAS()
+    b = rc.TLAS(keep_bvh2=True)
     b.push_exported(blob)
     b.sync()
     rays = np.zeros(2, RAY_DTYPE)
@@ -136,11 +136,11 @@ def test_single_triangle_and_size_query():
 
 
 def test_damaged_blobs_are_refused():
-    a = rc.TLAS()
+    a = rc.TLAS(keep_bvh2=True)
     h = a.push(np.concatenate([W.box_mesh(), np.zeros((1, 9), F)]))  # 13 submitted faces, 12 kept
     a.sync()
     blob = a.export_geometry(h)
-    b = rc.TLAS()
+    b = rc.TLAS(keep_bvh2=True)
 
     def refused(x, what):
         with pytest.raises(rc.RaycoreError) as e:

@@ -112,5 +112,5 @@ def test_blob_structural_check_accepts_built_trees_and_catches_faults():
                 assert hb.validate(corrupt, where) >= 1, (hb.n, corrupt, where)
             if hb.n > 1:
                 # 1: child index past the last node; 7 / 10: references that stay in range but would make a traversal cycle
-                for corrupt in (1, 7, 10):
+                for corrupt in (1, 7, 10, 11, 12):
                     assert hb.validate(corrupt, where) >= 1, (hb.n, corrupt, where)

@@ -5,5 +5,5 @@ out=$1; shift
 : > $out
 for v in "$@"; do
   RAYCORE_CUDA_LIB=build/variants/$v/libraycore_cuda.so python tools/exp_variant.py --log2rays 24 >> $out 2>> $out.err
-  RAYCORE_CUDA_LIB=build/variants/$v/libraycore_cuda.so python tools/exp_variant.py --c2 --log2rays 23 >> $out 2>> $out.err
+  [ -n "$SKIP_C2" ] || RAYCORE_CUDA_LIB=build/variants/$v/libraycore_cuda.so python tools/exp_variant.py --c2 --log2rays 23 >> $out 2>> $out.err
 done
