@@ -90,6 +90,11 @@ typedef struct rc_context rc_context; /* one mutable TLAS (src/instanced-bvh.jl:
 #define RC_HITS_ON_DEVICE 0x2u  /* hits pointer is device memory */
 #define RC_MODE_REFERENCE_ORDER 0x4u /* traverse the reference-identical BVH2 in the reference's own order
                                         (bit-identical results incl. ties); default = wide BVH4 fast path */
+#define RC_MODE_WATERTIGHT 0x400u /* triangle test = the reference's watertight intersect_triangle (src/triangle_mesh.jl:168-201: dominant-axis
+                                     permutation, shear, signed edge functions) instead of fast_intersect_triangle (Moeller-Trumbore, the
+                                     reference's traversal default and this library's): no ray slips between two triangles that share an
+                                     edge.  Hit / miss and ids can differ from the default mode at edges; t, u, v differ in the last bits.
+                                     Combines with RC_MODE_REFERENCE_ORDER; not with RC_COUNTERS */
 #define RC_COUNTERS 0x8u        /* accumulate per-ray work counters (rc_get_counters) — instrumented build of the same kernel */
 #define RC_VERTS_ON_DEVICE 0x10u /* rc_push / rc_update_geometry: verts (and face_meta) are device pointers */
 #define RC_NO_SYNC 0x20u        /* trace: do not cudaStreamSynchronize before returning (device buffers only) */

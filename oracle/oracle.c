@@ -173,6 +173,48 @@ int orc_intersect_triangle(const float o[3], const float dir[3], const float v0[
     return 1;
 }
 
+/* intersect_triangle, src/triangle_mesh.jl:168-201 with _to_ray_coordinate_space (:84-117), _edge_function (:24-30), _argmax (:78-88):
+ * the watertight (pbrt) test — permute so the dominant direction axis is z, shear the vertices into ray space, signed edge functions.
+ * The reference tests t against ray.t_max only; a traversal passes the closest t so far there and also honours t_min, as
+ * closest_hit does for Moeller-Trumbore (:1792).  u, v = barycentric weights of v1, v2 (edges[2], edges[3] * inv_det).
+ * is_degenerate(vs) (:171) is not re-tested: the builder filtered those faces with the same rule. */
+int orc_intersect_triangle_watertight(const float o[3], const float dir[3], const float v0[3], const float v1[3], const float v2[3],
+                                      float t_min, float t_max, float *t_out, float *u_out, float *v_out) {
+    int kz = 0; /* _argmax(map(abs, ray.d)): first maximum */
+    float mx = fabsf(dir[0]);
+    for (int i = 0; i < 3; i++) if (fabsf(dir[i]) > mx) { mx = fabsf(dir[i]); kz = i; }
+    int kx = kz + 1; if (kx == 3) kx = 0;
+    int ky = kx + 1; if (ky == 3) ky = 0;
+    float dx = dir[kx], dy = dir[ky], dz = dir[kz];
+    float denom = 1.0f / dz;
+    float shx = -dx * denom, shy = -dy * denom, shz = denom;
+    float rkz = o[kz];
+    const float *vs[3] = {v0, v1, v2};
+    float tx[3], ty[3], tz[3];
+    for (int i = 0; i < 3; i++) {
+        const float *v = vs[i];
+        float vox = v[kx] - o[kx], voy = v[ky] - o[ky], voz = v[kz] - o[kz];
+        tx[i] = vox + shx * (v[kz] - rkz);
+        ty[i] = voy + shy * (v[kz] - rkz);
+        tz[i] = voz + 0.0f;
+    }
+    float e0 = tx[1] * ty[2] - ty[1] * tx[2];
+    float e1 = tx[2] * ty[0] - ty[2] * tx[0];
+    float e2 = tx[0] * ty[1] - ty[0] * tx[1];
+    if (e0 == 0.0f && e1 == 0.0f && e2 == 0.0f) return 0;                                   /* iszero(edges) */
+    if ((e0 < 0.0f || e1 < 0.0f || e2 < 0.0f) && (e0 > 0.0f || e1 > 0.0f || e2 > 0.0f)) return 0;
+    float det = (e0 + e1) + e2;
+    if (det == 0.0f) return 0;                                                               /* det ≈ 0f0 */
+    float t_scaled = ((e0 * tz[0]) * shz + (e1 * tz[1]) * shz) + (e2 * tz[2]) * shz;
+    if (det < 0.0f && (t_scaled >= 0.0f || t_scaled < t_max * det)) return 0;
+    if (det > 0.0f && (t_scaled <= 0.0f || t_scaled > t_max * det)) return 0;
+    float inv_det = 1.0f / det;
+    float t = t_scaled * inv_det;
+    if (t < t_min) return 0;
+    *t_out = t; *u_out = e1 * inv_det; *v_out = e2 * inv_det;
+    return 1;
+}
+
 void orc_intersect_bbox(const float o[3], const float inv_d[3], const float pmin[3], const float pmax[3],
                         float t_min, float t_max, float *out_min, float *out_max) { /* :1841-1859 */
     float f[3], n[3], tmx[3], tmn[3];
@@ -522,7 +564,9 @@ static inline void intersect_internal_node(const orc_node2 *nd, const float inv_
 }
 
 /* flat_prim (nullable): 0-based position of the hit triangle in all_blas_prims */
-static void traverse(const orc_tlas *tl, const orc_ray *ray, int any, orc_hit *out, orc_counters *cnt, uint32_t *flat_prim) {
+/* mode: bit 0 = any_hit, bit 1 = the watertight triangle test instead of Moeller-Trumbore (the library's RC_MODE_WATERTIGHT) */
+static void traverse(const orc_tlas *tl, const orc_ray *ray, int mode, orc_hit *out, orc_counters *cnt, uint32_t *flat_prim) {
+    const int any = mode & 1, wt = (mode >> 1) & 1;
     memset(out, 0, sizeof *out);
     if (tl->n_instances == 0) return; /* reference indexes an empty array here (UB); tests require a miss (test_tlas_stress.jl:828) */
     float world_d[3];
@@ -576,7 +620,8 @@ static void traverse(const orc_tlas *tl, const orc_ray *ray, int any, orc_hit *o
         } else {
             float t, u, v;
             if (cnt) cnt->tri_tests++;
-            if (orc_intersect_triangle(ray_o, ray_d, nd->aabb0_min, nd->aabb0_max, nd->aabb1_min, ray_mint, ray_maxt, &t, &u, &v)) {
+            if (wt ? orc_intersect_triangle_watertight(ray_o, ray_d, nd->aabb0_min, nd->aabb0_max, nd->aabb1_min, ray_mint, ray_maxt, &t, &u, &v)
+                   : orc_intersect_triangle(ray_o, ray_d, nd->aabb0_min, nd->aabb0_max, nd->aabb1_min, ray_mint, ray_maxt, &t, &u, &v)) {
                 if (any) { /* :2106-2115 */
                     const orc_instance *inst = &tl->instances[current_instance];
                     const orc_tri *tri = &tl->all_blas_prims[tl->descs[inst->blas_index - 1].primitives_offset + nd->child1 - 1];
@@ -649,6 +694,9 @@ void orc_trace_closest(const orc_tlas *t, const orc_ray *rays, orc_hit *hits, ui
 }
 void orc_trace_any(const orc_tlas *t, const orc_ray *rays, orc_hit *hits, uint64_t n, int threads, orc_counters *sum) {
     trace_batch(t, rays, hits, n, threads, 1, sum);
+}
+void orc_trace_mode(const orc_tlas *t, const orc_ray *rays, orc_hit *hits, uint64_t n, int threads, int mode, orc_counters *sum) {
+    trace_batch(t, rays, hits, n, threads, mode, sum);
 }
 
 /* ------------------------------------------------------------------ analysis, src/kernels.jl */

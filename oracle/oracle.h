@@ -145,6 +145,10 @@ void orc_any_hit(const orc_tlas *t, const orc_ray *ray, orc_hit *out, orc_counte
 /* OpenMP over rays, as the reference's Threads.@threads over rays (src/kernels.jl:64,82) */
 void orc_trace_closest(const orc_tlas *t, const orc_ray *rays, orc_hit *hits, uint64_t n, int threads, orc_counters *sum);
 void orc_trace_any(const orc_tlas *t, const orc_ray *rays, orc_hit *hits, uint64_t n, int threads, orc_counters *sum);
+/* mode: bit 0 = any_hit, bit 1 = watertight triangle test (src/triangle_mesh.jl:168-201) instead of Moeller-Trumbore */
+void orc_trace_mode(const orc_tlas *t, const orc_ray *rays, orc_hit *hits, uint64_t n, int threads, int mode, orc_counters *sum);
+int orc_intersect_triangle_watertight(const float o[3], const float d[3], const float v0[3], const float v1[3], const float v2[3],
+                                      float t_min, float t_max, float *t_out, float *u_out, float *v_out); /* triangle_mesh.jl:168-201 */
 int orc_max_threads(void);
 
 /* ---- analysis (src/kernels.jl) ---- */

@@ -128,6 +128,10 @@ def lib():
         for name in ("orc_trace_closest", "orc_trace_any"):
             getattr(L, name).restype = None
             getattr(L, name).argtypes = [C.POINTER(_Tlas), vp, vp, C.c_uint64, C.c_int, C.POINTER(_Counters)]
+        L.orc_trace_mode.restype = None
+        L.orc_trace_mode.argtypes = [C.POINTER(_Tlas), vp, vp, C.c_uint64, C.c_int, C.c_int, C.POINTER(_Counters)]
+        L.orc_intersect_triangle_watertight.restype = C.c_int
+        L.orc_intersect_triangle_watertight.argtypes = [fp, fp, fp, fp, fp, C.c_float, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.orc_max_threads.restype = C.c_int
         L.orc_generate_ray_grid.restype = None
         L.orc_generate_ray_grid.argtypes = [fp, fp, C.c_uint32, vp, fp]
@@ -238,6 +242,14 @@ def intersect_triangle(o, d, v0, v1, v2, t_min=0.0, closest_t=np.inf):
     t, u, v = C.c_float(), C.c_float(), C.c_float()
     arrs = [_f(x, 3) for x in (o, d, v0, v1, v2)]
     ok = lib().orc_intersect_triangle(*[_fp(a) for a in arrs], float(t_min), float(closest_t), C.byref(t), C.byref(u), C.byref(v))
+    return bool(ok), t.value, u.value, v.value
+
+
+def intersect_triangle_watertight(o, d, v0, v1, v2, t_min=0.0, t_max=np.inf):
+    """intersect_triangle (src/triangle_mesh.jl:168-201): (hit, t, u, v) with u, v the barycentric weights of v1, v2"""
+    t, u, v = C.c_float(), C.c_float(), C.c_float()
+    arrs = [_f(x, 3) for x in (o, d, v0, v1, v2)]
+    ok = lib().orc_intersect_triangle_watertight(*[_fp(a) for a in arrs], float(t_min), float(t_max), C.byref(t), C.byref(u), C.byref(v))
     return bool(ok), t.value, u.value, v.value
 
 
@@ -372,10 +384,15 @@ class OracleTLAS:
             return hits, {k: getattr(cnt, k) for k, _ in _Counters._fields_}
         return hits
 
-    def closest_hit(self, rays, threads=0, counters=False):
+    def closest_hit(self, rays, threads=0, counters=False, watertight=False):
+        """watertight: the reference's pbrt-style triangle test (src/triangle_mesh.jl:168-201) instead of fast_intersect_triangle"""
+        if watertight:
+            return self._trace(lambda *a: lib().orc_trace_mode(*a[:5], 2, a[5]), rays, threads, counters)
         return self._trace(lib().orc_trace_closest, rays, threads, counters)
 
-    def any_hit(self, rays, threads=0, counters=False):
+    def any_hit(self, rays, threads=0, counters=False, watertight=False):
+        if watertight:
+            return self._trace(lambda *a: lib().orc_trace_mode(*a[:5], 3, a[5]), rays, threads, counters)
         return self._trace(lib().orc_trace_any, rays, threads, counters)
 
     def generate_ray_grid(self, direction, grid):

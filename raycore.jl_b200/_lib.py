@@ -34,6 +34,7 @@ RC_WAVE_NO_JITTER = 0x40
 RC_BUILD_KEEP_BVH2 = 0x80
 RC_BUILD_ALLOW_REFIT = 0x100
 RC_UPDATE_REFIT = 0x200
+RC_MODE_WATERTIGHT = 0x400
 RC_MAX_LIGHTS = 16
 
 RC_SYNC_NONE, RC_SYNC_REFIT, RC_SYNC_REBUILD = 0, 1, 2

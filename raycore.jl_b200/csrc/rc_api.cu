@@ -375,7 +375,7 @@ int32_t rc_update_geometry(rc_context *ctx, uint32_t handle, const float *verts,
             ctx->dirty = true;  // the root box moved: the TLAS is rebuilt over the same BLAS table at the next sync (update! marks dirty, :855)
             return RC_OK;
         }
-        // not refittable (the degenerate set changed): the triangles were overwritten in place, fall through to a rebuild from the new soup
+        // not refittable (the degenerate set changed; nothing was touched): fall through to a rebuild from the new soup
     }
     RcDeviceBlas nb;
     rc = build_blas_from(ctx, verts, n_faces, face_meta, flags | (old.nodes2 ? RC_BUILD_KEEP_BVH2 : 0u) | (old.topo ? RC_BUILD_ALLOW_REFIT : 0u), &nb);
@@ -699,6 +699,8 @@ static int32_t trace_common(rc_context *ctx, const rc_ray *rays, rc_hit *hits, u
         for (const RcDeviceBlas &B : ctx->blas)
             if (!B.nodes2) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "RC_MODE_REFERENCE_ORDER needs the reference-layout BVH2: build the geometry with RC_BUILD_KEEP_BVH2");
     L.count = flags & RC_COUNTERS;
+    L.watertight = flags & RC_MODE_WATERTIGHT;
+    if (L.watertight && L.count) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "RC_COUNTERS is not available together with RC_MODE_WATERTIGHT");
     L.work = ctx->d_work;
     L.counters = ctx->d_counters;
     L.overflow = ctx->d_overflow;

@@ -774,29 +774,36 @@ bool rc_build_blas(cudaStream_t st, const float *d_verts, const uint32_t *d_face
 // Vertex update with unchanged topology (update!, src/instanced-bvh.jl:808-857, as a refit): the kept radix tree is re-fitted to the new
 // vertex positions of the same faces.  Allowed when the geometry was built with RC_BUILD_ALLOW_REFIT, the face count is unchanged and
 // the set of degenerate faces is the same (*refitted = false otherwise: the caller rebuilds).
-__global__ void k_refit_gather(const float *__restrict__ verts, uint32_t n_faces, RcTri *__restrict__ tris, uint32_t n, uint32_t *__restrict__ ctl) {
-    // pass A (blockIdx.y == 0): every sorted triangle takes its face's new vertices; a kept face that became degenerate is counted
-    // pass B (blockIdx.y == 1): valid faces of the new soup are counted (must equal n)
+// pass A (blockIdx.y == 0): a kept face that is degenerate in the new soup is counted; pass B (blockIdx.y == 1): the valid faces of the
+// new soup are counted (must equal n).  Together: the degenerate set is unchanged.  Nothing is written to the geometry.
+__global__ void k_refit_check(const float *__restrict__ verts, uint32_t n_faces, const RcTri *__restrict__ tris, uint32_t n, uint32_t *__restrict__ ctl) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    f3 lo = mk3(INFINITY, INFINITY, INFINITY), hi = mk3(-INFINITY, -INFINITY, -INFINITY);
     if (blockIdx.y == 0) {
         if (i < n) {
-            float4 *t = reinterpret_cast<float4 *>(tris + i);
-            const uint32_t face = __float_as_uint(t[2].w);
-            const float *v = verts + (size_t)face * 9;
-            const f3 a = ld3(v), b = ld3(v + 3), c = ld3(v + 6);
-            if (x_is_degenerate(a, b, c)) atomicAdd(&ctl[CTL_TILE], 1u);
-            t[0] = make_float4(a.x, a.y, a.z, t[0].w);
-            t[1] = make_float4(b.x, b.y, b.z, t[1].w);
-            t[2] = make_float4(c.x, c.y, c.z, t[2].w);
-            lo = jl_min3(jl_min3(a, b), c);
-            hi = jl_max3(jl_max3(a, b), c);
+            const float *v = verts + (size_t)tris[i].face_index * 9;
+            if (x_is_degenerate(ld3(v), ld3(v + 3), ld3(v + 6))) atomicAdd(&ctl[CTL_TILE], 1u);
         }
-        bounds_atomic(ctl, lo, hi);
     } else if (i < n_faces) {
         const float *v = verts + (size_t)i * 9;
         if (!x_is_degenerate(ld3(v), ld3(v + 3), ld3(v + 6))) atomicAdd(&ctl[CTL_TILE + 1], 1u);
     }
+}
+// every sorted triangle takes its face's new vertices (ids kept); scene bounds for the bounding sphere
+__global__ void k_refit_apply(const float *__restrict__ verts, RcTri *__restrict__ tris, uint32_t n, uint32_t *__restrict__ ctl) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    f3 lo = mk3(INFINITY, INFINITY, INFINITY), hi = mk3(-INFINITY, -INFINITY, -INFINITY);
+    if (i < n) {
+        float4 *t = reinterpret_cast<float4 *>(tris + i);
+        const float4 t0 = t[0], t1 = t[1], t2 = t[2];
+        const float *v = verts + (size_t)__float_as_uint(t2.w) * 9;
+        const f3 a = ld3(v), b = ld3(v + 3), c = ld3(v + 6);
+        t[0] = make_float4(a.x, a.y, a.z, t0.w);
+        t[1] = make_float4(b.x, b.y, b.z, t1.w);
+        t[2] = make_float4(c.x, c.y, c.z, t2.w);
+        lo = jl_min3(jl_min3(a, b), c);
+        hi = jl_max3(jl_max3(a, b), c);
+    }
+    bounds_atomic(ctl, lo, hi);
 }
 
 bool rc_refit_blas(cudaStream_t st, const float *d_verts, uint32_t n_faces, RcDeviceBlas *b, bool *refitted, std::string &err) {
@@ -810,13 +817,15 @@ bool rc_refit_blas(cudaStream_t st, const float *d_verts, uint32_t n_faces, RcDe
     TMP(d_fl, n);
     TMP(d_boxes, 2 * (size_t)n);
     CK(cudaMemsetAsync(d_ctl, 0, sizeof(uint32_t) * CTL_WORDS, st));
-    // the triangles are updated in place; if the check below fails the caller rebuilds from the new vertices anyway
+    // check first, touch the geometry only when the refit is certain (a refused update leaves the old geometry intact, as update! does, :837)
     dim3 grid(cdiv(std::max(n, n_faces), 256), 2);
-    k_refit_gather<<<grid, 256, 0, st>>>(d_verts, n_faces, b->tris, n, d_ctl);
+    k_refit_check<<<grid, 256, 0, st>>>(d_verts, n_faces, b->tris, n, d_ctl);
     uint32_t h[CTL_TILE + 2];
     CK(cudaMemcpyAsync(h, d_ctl, sizeof h, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (h[CTL_TILE] != 0 || h[CTL_TILE + 1] != n) return true;  // the degenerate set changed: primitive numbering would differ
+    CK(cudaMemsetAsync(d_ctl + CTL_TILE, 0, 8, st));
+    k_refit_apply<<<cdiv(n, 256), 256, 0, st>>>(d_verts, b->tris, n, d_ctl);
     uint32_t n_word = n;
     CK(cudaMemcpyAsync(d_ctl + CTL_N, &n_word, 4, cudaMemcpyHostToDevice, st));
     if (n > 1) CK(cudaMemsetAsync(d_fl, 0, sizeof(uint32_t) * (n - 1), st));

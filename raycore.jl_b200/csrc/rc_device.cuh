@@ -177,6 +177,62 @@ RC_HD bool x_intersect_triangle(f3 o, f3 dir, f3 v0, f3 v1, f3 v2, float t_min, 
     return true;
 }
 
+// intersect_triangle, src/triangle_mesh.jl:168-201 (+ _to_ray_coordinate_space :84-117, _edge_function :24-30, _argmax :78-88): the
+// reference's WATERTIGHT (pbrt) test — the dominant direction axis becomes z, the vertices are sheared into ray space, and the hit
+// is decided by the signs of three edge functions, so a ray through a shared edge or vertex of a closed mesh can never slip
+// between two triangles (Moeller-Trumbore can: tests/test_gpu_fullsize.py counts the leaks).  Same operation order as the Julia
+// code, no FMA.  The reference tests t against ray.t_max only; a traversal passes the closest t so far and also honours t_min as
+// closest_hit does for Moeller-Trumbore (:1792).  u, v = barycentric weights of v1, v2 (edges[2], edges[3] .* inv_det).
+// is_degenerate(vs) (:171) is not re-tested: the builder filtered those faces with the same rule.
+RC_HD bool x_intersect_triangle_watertight(f3 o, f3 dir, f3 v0, f3 v1, f3 v2, float t_min, float t_max, float &t, float &u, float &v) {
+    const float ax = fabsf(dir.x), ay = fabsf(dir.y), az = fabsf(dir.z);
+    int kz = 0;  // _argmax: first maximum
+    float mx = ax;
+    if (ay > mx) { mx = ay; kz = 1; }
+    if (az > mx) { mx = az; kz = 2; }
+    // permutation (kx, ky, kz) = (kz + 1, kz + 2, kz) mod 3
+#define RC_PERM(p, X, Y, Z)                                        \
+    {                                                              \
+        X = kz == 0 ? p.y : (kz == 1 ? p.z : p.x);                 \
+        Y = kz == 0 ? p.z : (kz == 1 ? p.x : p.y);                 \
+        Z = kz == 0 ? p.x : (kz == 1 ? p.y : p.z);                 \
+    }
+    float dx, dy, dz, ox, oy, oz;
+    RC_PERM(dir, dx, dy, dz)
+    RC_PERM(o, ox, oy, oz)
+    const float denom = x_div(1.0f, dz);
+    const float shx = x_mul(-dx, denom), shy = x_mul(-dy, denom), shz = denom;
+    float px[3], py[3], pz[3];
+    const f3 vs[3] = {v0, v1, v2};
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        float vx, vy, vz;
+        RC_PERM(vs[i], vx, vy, vz)
+        const float voz = x_sub(vz, oz);
+        px[i] = x_add(x_sub(vx, ox), x_mul(shx, voz));
+        py[i] = x_add(x_sub(vy, oy), x_mul(shy, voz));
+        pz[i] = x_add(voz, 0.0f);  // the reference adds Point3f(.., .., 0f0): -0 becomes +0
+    }
+#undef RC_PERM
+    const float e0 = x_sub(x_mul(px[1], py[2]), x_mul(py[1], px[2]));
+    const float e1 = x_sub(x_mul(px[2], py[0]), x_mul(py[2], px[0]));
+    const float e2 = x_sub(x_mul(px[0], py[1]), x_mul(py[0], px[1]));
+    if (e0 == 0.0f && e1 == 0.0f && e2 == 0.0f) return false;
+    if ((e0 < 0.0f || e1 < 0.0f || e2 < 0.0f) && (e0 > 0.0f || e1 > 0.0f || e2 > 0.0f)) return false;
+    const float det = x_add(x_add(e0, e1), e2);
+    if (det == 0.0f) return false;
+    const float ts = x_add(x_add(x_mul(x_mul(e0, pz[0]), shz), x_mul(x_mul(e1, pz[1]), shz)), x_mul(x_mul(e2, pz[2]), shz));
+    if (det < 0.0f && (ts >= 0.0f || ts < x_mul(t_max, det))) return false;
+    if (det > 0.0f && (ts <= 0.0f || ts > x_mul(t_max, det))) return false;
+    const float inv_det = x_div(1.0f, det);
+    const float th = x_mul(ts, inv_det);
+    if (th < t_min) return false;
+    t = th;
+    u = x_mul(e1, inv_det);
+    v = x_mul(e2, inv_det);
+    return true;
+}
+
 // fast_intersect_bbox, src/instanced-bvh.jl:1841-1859 (exact, Julia min/max)
 RC_HD void x_intersect_bbox(f3 o, f3 inv, f3 pmin, f3 pmax, float t_min, float t_max, float &out_min, float &out_max) {
     float ox = x_mul(-o.x, inv.x), oy = x_mul(-o.y, inv.y), oz = x_mul(-o.z, inv.z);

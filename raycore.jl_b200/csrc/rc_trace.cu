@@ -13,7 +13,7 @@
 #include "rc_trace_core.cuh"
 #include "rc_trace_fast.cuh"
 
-template <bool ANY, bool COUNT>
+template <bool ANY, bool COUNT, bool WT>
 __global__ void __launch_bounds__(RC_TRACE_THREADS) k_trace(RcScene sc, const rc_ray *__restrict__ rays, rc_hit *__restrict__ hits, unsigned long long n,
                                                             unsigned long long *__restrict__ work, RcCounters *__restrict__ counters, uint32_t *__restrict__ overflow) {
     RcLocalCounters lc = {0, 0, 0, 0, 0};
@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS) k_trace(RcScene sc, const rc
         if (i >= n) break;
         rc_ray r = rc_load_ray(rays, i);
         rc_hit h;
-        if (!rc_trace_reference_order<ANY, COUNT>(sc, r, h, &lc)) atomicAdd(overflow + 1, 1u);
+        if (!rc_trace_reference_order<ANY, COUNT, WT>(sc, r, h, &lc)) atomicAdd(overflow + 1, 1u);
         rc_store_hit(hits, i, h);
         traced++;
     }
@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS) k_trace(RcScene sc, const rc
 
 // Re-trace the rays whose short (shared-memory) stack overflowed in k_trace_wide with the deep-stack generic body.
 // overflow[0] = rays flagged by the fast kernel (exit immediately when 0), overflow[1] = rays no stack could hold (error).
-template <bool ANY>
+template <bool ANY, bool WT>
 __global__ void __launch_bounds__(RC_TRACE_THREADS) k_trace_fixup(RcScene sc, const rc_ray *__restrict__ rays, rc_hit *__restrict__ hits, unsigned long long n,
                                                                   uint32_t *__restrict__ overflow) {
     if (*reinterpret_cast<volatile uint32_t *>(overflow) == 0) return;
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS) k_trace_fixup(RcScene sc, co
         if (hits[i].hit != RC_OVERFLOW_MARK) continue;
         rc_ray r = rc_load_ray(rays, i);
         rc_hit h;
-        if (!rc_trace_wide<ANY, false>(sc, r, h, nullptr)) atomicAdd(overflow + 1, 1u);
+        if (!rc_trace_wide<ANY, false, WT>(sc, r, h, nullptr)) atomicAdd(overflow + 1, 1u);
         rc_store_hit(hits, i, h);
     }
 }
@@ -74,24 +74,37 @@ bool rc_launch_trace(cudaStream_t st, const RcTraceLaunch &L, std::string &err) 
         if (blocks < 1) blocks = 1;
 #define RC_ARGS L.scene, L.rays, L.hits, L.n, L.work, L.counters, L.overflow
 #define RC_WARGS L.scene, RcIoArrays{L.rays, L.hits}, L.n, L.work, L.counters, L.overflow
+        const bool single = L.scene.n_instances == 1u;
         if (L.wide) {
-#define RC_LAUNCH_WIDE(A, C)                                                                                                  \
-    {                                                                                                                         \
-        if (L.scene.n_instances == 1u) k_trace_wide<A, C, RcIoArrays, true><<<blocks, RC_TRACE_THREADS, 0, st>>>(RC_WARGS);   \
-        else k_trace_wide<A, C, RcIoArrays, false><<<blocks, RC_TRACE_THREADS, 0, st>>>(RC_WARGS);                            \
+            // (ANY, COUNT, SINGLE, WT): the instrumented build exists for Moeller-Trumbore only
+#define RC_LAUNCH_WIDE(A, C, S, W) k_trace_wide<A, C, RcIoArrays, S, W><<<blocks, RC_TRACE_THREADS, 0, st>>>(RC_WARGS)
+#define RC_PICK_SINGLE(A, C, W)                                      \
+    {                                                                \
+        if (single) RC_LAUNCH_WIDE(A, C, true, W);                   \
+        else RC_LAUNCH_WIDE(A, C, false, W);                         \
     }
-            if (L.any) { if (L.count) RC_LAUNCH_WIDE(true, true) else RC_LAUNCH_WIDE(true, false) }
-            else { if (L.count) RC_LAUNCH_WIDE(false, true) else RC_LAUNCH_WIDE(false, false) }
+            if (L.watertight) { if (L.any) RC_PICK_SINGLE(true, false, true) else RC_PICK_SINGLE(false, false, true) }
+            else if (L.any) { if (L.count) RC_PICK_SINGLE(true, true, false) else RC_PICK_SINGLE(true, false, false) }
+            else { if (L.count) RC_PICK_SINGLE(false, true, false) else RC_PICK_SINGLE(false, false, false) }
+#undef RC_PICK_SINGLE
 #undef RC_LAUNCH_WIDE
+        } else if (L.watertight) {
+            if (L.any) k_trace<true, false, true><<<blocks, RC_TRACE_THREADS, 0, st>>>(RC_ARGS);
+            else k_trace<false, false, true><<<blocks, RC_TRACE_THREADS, 0, st>>>(RC_ARGS);
         } else {
-            if (L.any) { if (L.count) k_trace<true, true><<<blocks, RC_TRACE_THREADS, 0, st>>>(RC_ARGS); else k_trace<true, false><<<blocks, RC_TRACE_THREADS, 0, st>>>(RC_ARGS); }
-            else { if (L.count) k_trace<false, true><<<blocks, RC_TRACE_THREADS, 0, st>>>(RC_ARGS); else k_trace<false, false><<<blocks, RC_TRACE_THREADS, 0, st>>>(RC_ARGS); }
+            if (L.any) { if (L.count) k_trace<true, true, false><<<blocks, RC_TRACE_THREADS, 0, st>>>(RC_ARGS); else k_trace<true, false, false><<<blocks, RC_TRACE_THREADS, 0, st>>>(RC_ARGS); }
+            else { if (L.count) k_trace<false, true, false><<<blocks, RC_TRACE_THREADS, 0, st>>>(RC_ARGS); else k_trace<false, false, false><<<blocks, RC_TRACE_THREADS, 0, st>>>(RC_ARGS); }
         }
 #undef RC_ARGS
 #undef RC_WARGS
         if (L.wide) {
-            if (L.any) k_trace_fixup<true><<<blocks, RC_TRACE_THREADS, 0, st>>>(L.scene, L.rays, L.hits, L.n, L.overflow);
-            else k_trace_fixup<false><<<blocks, RC_TRACE_THREADS, 0, st>>>(L.scene, L.rays, L.hits, L.n, L.overflow);
+            if (L.watertight) {
+                if (L.any) k_trace_fixup<true, true><<<blocks, RC_TRACE_THREADS, 0, st>>>(L.scene, L.rays, L.hits, L.n, L.overflow);
+                else k_trace_fixup<false, true><<<blocks, RC_TRACE_THREADS, 0, st>>>(L.scene, L.rays, L.hits, L.n, L.overflow);
+            } else {
+                if (L.any) k_trace_fixup<true, false><<<blocks, RC_TRACE_THREADS, 0, st>>>(L.scene, L.rays, L.hits, L.n, L.overflow);
+                else k_trace_fixup<false, false><<<blocks, RC_TRACE_THREADS, 0, st>>>(L.scene, L.rays, L.hits, L.n, L.overflow);
+            }
         }
     }
     cudaError_t e = cudaGetLastError();

@@ -56,7 +56,7 @@ struct RcLocalCounters {
 
 // ------------------------------------------------------------------------------------------------
 // Reference-order traversal.  Returns false on stack overflow.
-template <bool ANY, bool COUNT>
+template <bool ANY, bool COUNT, bool WT = false>
 RC_HD bool rc_trace_reference_order(const RcScene &sc, const rc_ray &ray, rc_hit &out, RcLocalCounters *cnt, const RcTri **tri_out = nullptr) {
     rc_write_miss(out);
     if (tri_out) *tri_out = nullptr;
@@ -119,7 +119,8 @@ RC_HD bool rc_trace_reference_order(const RcScene &sc, const rc_ray &ray, rc_hit
             f3 v0 = mk3(q0.x, q0.y, q0.z), v1 = mk3(u2f(q0.w), q1.x, q1.y), v2 = mk3(q1.z, u2f(q1.w), q2.x);
             float t, u, v;
             if (COUNT) cnt->tri_tests++;
-            if (x_intersect_triangle(ray_o, ray_d, v0, v1, v2, ray_mint, ray_maxt, t, u, v)) {
+            if (WT ? x_intersect_triangle_watertight(ray_o, ray_d, v0, v1, v2, ray_mint, ray_maxt, t, u, v)
+                   : x_intersect_triangle(ray_o, ray_d, v0, v1, v2, ray_mint, ray_maxt, t, u, v)) {
                 ray_maxt = t;
                 closest_instance = current_instance;
                 closest_prim = child1;  // 1-based sorted primitive index
@@ -207,7 +208,7 @@ RC_HD void rc_wide_node_test(const rc_f4 &n0, const rc_f4 &n1, const rc_f4 &n2, 
     }
 }
 
-template <bool ANY, bool COUNT>
+template <bool ANY, bool COUNT, bool WT = false>
 RC_HD bool rc_trace_wide(const RcScene &sc, const rc_ray &ray, rc_hit &out, RcLocalCounters *cnt, const RcTri **tri_out = nullptr) {
     rc_write_miss(out);
     if (tri_out) *tri_out = nullptr;
@@ -267,7 +268,8 @@ RC_HD bool rc_trace_wide(const RcScene &sc, const rc_ray &ray, rc_hit &out, RcLo
                 rc_f4 a = rc_load16(tp), b = rc_load16(tp + 16), c = rc_load16(tp + 32);
                 float t, u, v;
                 if (COUNT) cnt->tri_tests++;
-                if (x_intersect_triangle(ray_o, ray_d, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), ray_mint, ray_maxt, t, u, v)) {
+                if (WT ? x_intersect_triangle_watertight(ray_o, ray_d, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), ray_mint, ray_maxt, t, u, v)
+                       : x_intersect_triangle(ray_o, ray_d, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), ray_mint, ray_maxt, t, u, v)) {
                     if (t == t) {  // a NaN t (ray in the triangle's plane) is rejected here; documented deviation
                         ray_maxt = t;
                         closest_instance = current_instance;

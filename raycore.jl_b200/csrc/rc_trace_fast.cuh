@@ -215,7 +215,8 @@ struct RcIoArrays {
 
 // IO: where ray i comes from and where its result goes (RcIoArrays for rc_trace_*; rc_analysis.cu plugs in an on-the-fly
 // view-factor ray generator + matrix accumulator, so the analysis kernels run on the same scheduler).
-template <bool ANY, bool COUNT, class IO, bool SINGLE = false>
+// WT: the watertight triangle test (RC_MODE_WATERTIGHT) instead of Moeller-Trumbore in the T step; everything else is the same kernel.
+template <bool ANY, bool COUNT, class IO, bool SINGLE = false, bool WT = false>
 __global__ void __launch_bounds__(RC_TRACE_THREADS, SINGLE ? RC_MIN_BLOCKS_SINGLE : RC_MIN_BLOCKS) k_trace_wide(RcScene sc, IO io, unsigned long long n,
                                                                  unsigned long long *__restrict__ work, RcCounters *__restrict__ counters,
                                                                  uint32_t *__restrict__ overflow) {
@@ -403,7 +404,8 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, SINGLE ? RC_MIN_BLOCKS_SINGL
                 const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
                 float t, u, v;
                 if (COUNT) lc.tri_tests++;
-                if (x_intersect_triangle(o, d, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), t_min, t_max, t, u, v) && t == t) {
+                if ((WT ? x_intersect_triangle_watertight(o, d, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), t_min, t_max, t, u, v)
+                        : x_intersect_triangle(o, d, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), t_min, t_max, t, u, v)) && t == t) {
                     t_max = t;
                     best_inst = cur_inst;
                     best_prim = __float_as_uint(a.w);

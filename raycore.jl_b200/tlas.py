@@ -162,13 +162,14 @@ class StaticTLAS:
             raise RaycoreError(L.RC_ERR_NOT_SYNCED, "stale StaticTLAS: the TLAS was rebuilt; re-adapt per dispatch (src/instanced-bvh.jl:221-226)")
 
     # queries ---------------------------------------------------------------------------------
-    def trace_closest(self, rays, reference_order=False, counters=False) -> np.ndarray:
+    def trace_closest(self, rays, reference_order=False, counters=False, watertight=False) -> np.ndarray:
+        """watertight=True: the reference's watertight triangle test (src/triangle_mesh.jl:168-201) instead of Moeller-Trumbore"""
         self._check()
-        return self._owner._trace(rays, any_hit=False, reference_order=reference_order, counters=counters)
+        return self._owner._trace(rays, any_hit=False, reference_order=reference_order, counters=counters, watertight=watertight)
 
-    def trace_any(self, rays, reference_order=False, counters=False) -> np.ndarray:
+    def trace_any(self, rays, reference_order=False, counters=False, watertight=False) -> np.ndarray:
         self._check()
-        return self._owner._trace(rays, any_hit=True, reference_order=reference_order, counters=counters)
+        return self._owner._trace(rays, any_hit=True, reference_order=reference_order, counters=counters, watertight=watertight)
 
     def closest_hit(self, ray: Ray, **kw):
         """(hit, Triangle, t, bary(w,u,v), instance_idx 1-based) — src/instanced-bvh.jl:1902-2024."""
@@ -457,10 +458,10 @@ class TLAS:
         return out
 
     # -- queries --------------------------------------------------------------------------------
-    def _trace(self, rays, any_hit, reference_order=False, counters=False) -> np.ndarray:
+    def _trace(self, rays, any_hit, reference_order=False, counters=False, watertight=False) -> np.ndarray:
         rays = _as_rays(rays)
         hits = np.zeros(len(rays), HIT_DTYPE)
-        flags = (L.RC_MODE_REFERENCE_ORDER if reference_order else 0) | (L.RC_COUNTERS if counters else 0)
+        flags = (L.RC_MODE_REFERENCE_ORDER if reference_order else 0) | (L.RC_COUNTERS if counters else 0) | (L.RC_MODE_WATERTIGHT if watertight else 0)
         fn = self._lib.rc_trace_any if any_hit else self._lib.rc_trace_closest
         if len(rays):
             self._ck(fn(self._ctx, rays.ctypes.data, hits.ctypes.data, len(rays), flags))

@@ -38,8 +38,8 @@ class OracleEngine:
         self.instances = instances_of(pushes, orc.mat3x4_inverse)
         self.tlas = orc.OracleTLAS(self.blas, self.instances.view(orc.INSTANCE_DTYPE))
 
-    def trace(self, rays, any_hit=False, **kw):
-        return self.tlas.any_hit(rays) if any_hit else self.tlas.closest_hit(rays)
+    def trace(self, rays, any_hit=False, watertight=False, **kw):
+        return self.tlas.any_hit(rays, watertight=watertight) if any_hit else self.tlas.closest_hit(rays, watertight=watertight)
 
     def world_bound(self):
         return self.tlas.root_aabb
@@ -53,8 +53,8 @@ class HostsimEngine:
         self.instances = instances_of(pushes, hs.mat3x4_inverse)
         self.scene = hs.HsScene(self.blas, self.instances)
 
-    def trace(self, rays, any_hit=False, **kw):
-        return self.scene.trace(rays, any_hit=any_hit, wide=self.wide)
+    def trace(self, rays, any_hit=False, watertight=False, **kw):
+        return self.scene.trace(rays, any_hit=any_hit, wide=self.wide, watertight=watertight)
 
     def world_bound(self):
         return self.scene.root()
@@ -86,9 +86,10 @@ class GpuEngine:
             self.handles.append(self.tlas.push(verts, list(xf), instance_ids=ids, face_meta=fm))
         self.tlas.sync()
 
-    def trace(self, rays, any_hit=False, **kw):
+    def trace(self, rays, any_hit=False, watertight=False, **kw):
         st = self.tlas.adapt()
-        return st.trace_any(rays, reference_order=self.reference_order) if any_hit else st.trace_closest(rays, reference_order=self.reference_order)
+        fn = st.trace_any if any_hit else st.trace_closest
+        return fn(rays, reference_order=self.reference_order, watertight=watertight)
 
     def world_bound(self):
         b = self.tlas.world_bound()

@@ -257,6 +257,19 @@ void hs_scene_root(void *s, float *out6) { memcpy(out6, ((HsScene *)s)->tlas.roo
 void hs_scene_free(void *s) { delete (HsScene *)s; }
 
 // returns number of rays whose traversal stack overflowed
+// the same per-ray bodies with the watertight triangle test (RC_MODE_WATERTIGHT)
+uint32_t hs_trace_watertight(void *s, const rc_ray *rays, rc_hit *hits, uint64_t n, int any, int wide) {
+    HsScene *S = (HsScene *)s;
+    uint32_t overflow = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        bool ok;
+        if (wide) ok = any ? rc_trace_wide<true, false, true>(S->scene, rays[i], hits[i], nullptr) : rc_trace_wide<false, false, true>(S->scene, rays[i], hits[i], nullptr);
+        else ok = any ? rc_trace_reference_order<true, false, true>(S->scene, rays[i], hits[i], nullptr) : rc_trace_reference_order<false, false, true>(S->scene, rays[i], hits[i], nullptr);
+        if (!ok) overflow++;
+    }
+    return overflow;
+}
+
 uint32_t hs_trace(void *s, const rc_ray *rays, rc_hit *hits, uint64_t n, int any, int wide, uint64_t *counters /* nullable, 5 */) {
     HsScene *S = (HsScene *)s;
     uint32_t overflow = 0;

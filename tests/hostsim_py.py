@@ -32,6 +32,8 @@ def lib():
         L.hs_scene_tlas_nodes2.argtypes = [vp, vp]
         L.hs_scene_root.argtypes = [vp, vp]
         L.hs_scene_free.argtypes = [vp]
+        L.hs_trace_watertight.restype = C.c_uint32
+        L.hs_trace_watertight.argtypes = [vp, vp, vp, C.c_uint64, C.c_int, C.c_int]
         L.hs_trace.restype = C.c_uint32
         L.hs_trace.argtypes = [vp, vp, vp, C.c_uint64, C.c_int, C.c_int, vp]
         L.hs_primary_rays.restype = None
@@ -122,9 +124,13 @@ class HsScene:
         lib().hs_shadow_rays(self.p, rays.ctypes.data, hits.ctypes.data, len(rays), table, lights.ctypes.data, len(lights), shadow_bias, out.ctypes.data)
         return out
 
-    def trace(self, rays, any_hit=False, wide=True, counters=False):
+    def trace(self, rays, any_hit=False, wide=True, counters=False, watertight=False):
         rays = np.ascontiguousarray(rays, RAY_DTYPE)
         hits = np.zeros(len(rays), HIT_DTYPE)
+        if watertight:
+            ov = lib().hs_trace_watertight(self.p, rays.ctypes.data, hits.ctypes.data, len(rays), int(any_hit), int(wide))
+            assert ov == 0, f"{ov} traversal stack overflows"
+            return hits
         cnt = (C.c_uint64 * 5)()
         ov = lib().hs_trace(self.p, rays.ctypes.data, hits.ctypes.data, len(rays), int(any_hit), int(wide), cnt)
         assert ov == 0, f"{ov} traversal stack overflows"

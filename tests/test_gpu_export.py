@@ -52,7 +52,7 @@ def test_export_import_round_trip_is_byte_identical():
 
     blob_s, blob_b = a.export_geometry(hs_), a.export_geometry(hb)
     hd_s, hd_b = T.blob_header(blob_s), T.blob_header(blob_b)
-    assert hd_s["magic"] == b"RCBLAS\x00\x01" and hd_s["total_bytes"] == blob_s.nbytes and hd_s["has_normals"] == 0
+    assert hd_s["magic"] == b"RCBLAS\x00\x02" and hd_s["total_bytes"] == blob_s.nbytes and hd_s["has_normals"] == 0
     assert hd_b["n"] == len(W.box_mesh()) and hd_b["n_faces_in"] == len(box) and hd_b["has_normals"] == 1
     assert blob_hash(blob_s[128:].tobytes()) == int(hd_s["payload_hash"])
     assert np.array_equal(a.export_geometry(hs_), blob_s), "export is not deterministic"
