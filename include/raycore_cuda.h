@@ -311,6 +311,38 @@ int32_t rc_ipc_close(rc_context *ctx, void *ptr);
 int32_t rc_peer_copy_async(rc_context *ctx, void *dst, const void *src, size_t bytes, uint32_t slot);
 int32_t rc_stream_wait_copy(rc_context *ctx, uint32_t slot);
 
+/* ---- several GPUs of one node behind one handle ---------------------------------------------------------
+ * One process, all devices, inside the library: an rc_multi owns one context per device; the scene is replicated (every mutation is
+ * applied to every device — the builder is deterministic, the replicas are byte-identical) and queries are sharded with no data-path
+ * collective.  The reference's only parallelism on this path is Threads.@threads over rays / source triangles (src/kernels.jl:64,82);
+ * this is the same split across GPUs.  devices == NULL / n_devices == 0: every visible device.  Errors: rc_multi_last_error. */
+typedef struct rc_multi rc_multi;
+int32_t rc_multi_create(const int32_t *devices, uint32_t n_devices, rc_multi **out);
+int32_t rc_multi_destroy(rc_multi *m);
+const char *rc_multi_last_error(const rc_multi *m); /* m may be NULL: last creation error */
+uint32_t rc_multi_device_count(const rc_multi *m);
+/* the k-th device's context, for everything that is not sharded (introspection, read-backs, the wavefront stages): treat it as read-only —
+ * mutating one replica alone makes the replicas diverge */
+rc_context *rc_multi_context(rc_multi *m, uint32_t k);
+/* push! / delete! / update_transform(s)! / update! / sync! on every replica (same arguments and results as the single-device calls; host
+ * pointers only — each device uploads its own copy, concurrently) */
+int32_t rc_multi_push(rc_multi *m, const float *verts, uint32_t n_faces, const uint32_t *face_meta, const float *transforms, const float *inv_transforms,
+                      const uint32_t *instance_ids, uint32_t n_instances, uint32_t flags, uint32_t *handle_out);
+int32_t rc_multi_delete(rc_multi *m, uint32_t handle, int32_t *deleted);
+int32_t rc_multi_update_transforms(rc_multi *m, uint32_t handle, const float *transforms, const float *inv_transforms, uint32_t n);
+int32_t rc_multi_update_geometry(rc_multi *m, uint32_t handle, const float *verts, uint32_t n_faces, const uint32_t *face_meta, uint32_t flags);
+int32_t rc_multi_sync(rc_multi *m, int32_t *action);
+/* closest_hit / any_hit over n rays, rays [k n / G, (k+1) n / G) on device k; results are byte-identical to the single-device call.
+ * Host buffers (flags without RC_*_ON_DEVICE): every device stages its own slice straight from / to the caller's arrays over its own
+ * host link — H2D, trace and D2H of all devices overlap, nothing hops through a root GPU (pin the arrays, e.g. rc_host_alloc, for full
+ * PCIe rate).  Device buffers (both RC_RAYS_ON_DEVICE and RC_HITS_ON_DEVICE, memory of the FIRST device): every device's traversal kernel
+ * reads its ray slice and stores its hit records through the NVLink peer mapping directly — the gather is the kernel's epilogue. */
+int32_t rc_multi_trace_closest(rc_multi *m, const rc_ray *rays, rc_hit *hits, uint64_t n, uint32_t flags);
+int32_t rc_multi_trace_any(rc_multi *m, const rc_ray *rays, rc_hit *hits, uint64_t n, uint32_t flags);
+/* view_factors(tlas; rays_per_triangle) into the caller's host matrix (n_prims x n_prims, row-major [src][hit]): source rows
+ * [k N / G, (k+1) N / G) are computed on device k and copied to their place; no exchange between the devices. */
+int32_t rc_multi_view_factors(rc_multi *m, uint32_t rays_per_triangle, uint64_t seed, uint32_t *out, uint64_t *skipped);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,7 +9,7 @@ from ._lib import (  # noqa: F401
     HIT_DTYPE, INSTANCE_DTYPE, NODE2_DTYPE, RAY_DTYPE, RC_SYNC_NONE, RC_SYNC_REBUILD, RC_SYNC_REFIT, RaycoreError,
 )
 from .tlas import (  # noqa: F401
-    BLAS4, INVALID_HANDLE, Bounds3, DeviceQueue, Ray, any_hit4, build_blas4, closest_hit4, RayHit, StaticTLAS, TLAS, TLASHandle, Triangle, build_static_tlas, empty_triangle,
+    BLAS4, INVALID_HANDLE, Bounds3, DeviceQueue, Ray, any_hit4, build_blas4, closest_hit4, RayHit, StaticTLAS, TLAS, MultiTLAS, TLASHandle, Triangle, build_static_tlas, empty_triangle,
     mat4_to_mat3x4, tlas_from_meshes,
 )
 

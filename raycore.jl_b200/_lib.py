@@ -82,6 +82,8 @@ EXPORTS = [
     "rc_shadow_visibility",
     "rc_device_alloc", "rc_device_free", "rc_host_alloc", "rc_host_free", "rc_memcpy_h2d", "rc_memcpy_d2h",
     "rc_ipc_export", "rc_ipc_open", "rc_ipc_close", "rc_peer_copy_async", "rc_stream_wait_copy",
+    "rc_multi_create", "rc_multi_destroy", "rc_multi_last_error", "rc_multi_device_count", "rc_multi_context", "rc_multi_push", "rc_multi_delete",
+    "rc_multi_update_transforms", "rc_multi_update_geometry", "rc_multi_sync", "rc_multi_trace_closest", "rc_multi_trace_any", "rc_multi_view_factors",
 ]  # fmt: skip
 
 
@@ -175,6 +177,19 @@ def load():
         "rc_ipc_close": (i32, [vp, vp]),
         "rc_peer_copy_async": (i32, [vp, vp, vp, C.c_size_t, u32]),
         "rc_stream_wait_copy": (i32, [vp, u32]),
+        "rc_multi_create": (i32, [vp, u32, C.POINTER(vp)]),
+        "rc_multi_destroy": (i32, [vp]),
+        "rc_multi_last_error": (C.c_char_p, [vp]),
+        "rc_multi_device_count": (u32, [vp]),
+        "rc_multi_context": (vp, [vp, u32]),
+        "rc_multi_push": (i32, [vp, vp, u32, vp, vp, vp, vp, u32, u32, pu32]),
+        "rc_multi_delete": (i32, [vp, u32, pi32]),
+        "rc_multi_update_transforms": (i32, [vp, u32, vp, vp, u32]),
+        "rc_multi_update_geometry": (i32, [vp, u32, vp, u32, vp, u32]),
+        "rc_multi_sync": (i32, [vp, pi32]),
+        "rc_multi_trace_closest": (i32, [vp, vp, vp, u64, u32]),
+        "rc_multi_trace_any": (i32, [vp, vp, vp, u64, u32]),
+        "rc_multi_view_factors": (i32, [vp, u32, u64, vp, C.POINTER(u64)]),
     }
     assert set(sig) == set(EXPORTS)
     for name, (res, args) in sig.items():

@@ -1169,7 +1169,7 @@ int32_t rc_device_free(rc_context *ctx, void *ptr) {
 int32_t rc_host_alloc(rc_context *ctx, size_t bytes, void **out) {
     if (!ctx || !out) return RC_ERR_INVALID_ARGUMENT;
     RC_ENTER(ctx);
-    RC_CUDA(ctx, cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    RC_CUDA(ctx, cudaHostAlloc(out, bytes, cudaHostAllocPortable));  // pinned for every device of the process (rc_multi_* stage from it on all of them)
     return RC_OK;
 }
 int32_t rc_host_free(rc_context *ctx, void *ptr) {

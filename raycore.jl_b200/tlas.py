@@ -641,6 +641,90 @@ class TLAS:
         return q
 
 
+class MultiTLAS:
+    """One scene replicated on several GPUs of this node, queries sharded over them — inside the library, one process (rc_multi_*,
+    SURVEY §8e).  Mutations mirror TLAS; `trace_closest` / `trace_any` / `view_factors` return exactly what a single-device TLAS returns."""
+
+    def __init__(self, devices: Optional[Sequence[int]] = None):
+        self._lib = L.load()
+        m = C.c_void_p()
+        dv = None if devices is None else np.ascontiguousarray(devices, np.int32)
+        rc = self._lib.rc_multi_create(None if dv is None else dv.ctypes.data, 0 if dv is None else len(dv), C.byref(m))
+        if rc != L.RC_OK:
+            raise RaycoreError(rc, self._lib.rc_multi_last_error(None).decode())
+        self._m = m
+
+    def _ck(self, rc):
+        if rc != L.RC_OK:
+            raise RaycoreError(rc, self._lib.rc_multi_last_error(self._m).decode())
+
+    @property
+    def n_devices(self) -> int:
+        return int(self._lib.rc_multi_device_count(self._m))
+
+    def free(self):
+        if getattr(self, "_m", None):
+            self._lib.rc_multi_destroy(self._m)
+            self._m = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def push(self, mesh, transform=None, *, instance_id: int = 0, instance_ids: Optional[Sequence[int]] = None, face_meta=None, inv_transform=None) -> TLASHandle:
+        v = TLAS._verts(mesh)
+        xf, inv, ids, m = TLAS._instance_args(transform, instance_id, instance_ids, inv_transform)
+        fm = None if face_meta is None else np.ascontiguousarray(face_meta, np.uint32)
+        h = C.c_uint32()
+        self._ck(self._lib.rc_multi_push(self._m, v.ctypes.data, len(v), None if fm is None else fm.ctypes.data, xf.ctypes.data, None if inv is None else inv.ctypes.data,
+                                         None if ids is None else ids.ctypes.data, m, 0, C.byref(h)))
+        return TLASHandle(h.value)
+
+    def delete(self, handle: TLASHandle) -> bool:
+        d = C.c_int32()
+        self._ck(self._lib.rc_multi_delete(self._m, handle.id, C.byref(d)))
+        return bool(d.value)
+
+    def update_transforms(self, handle: TLASHandle, transforms):
+        xf = np.ascontiguousarray([mat4_to_mat3x4(t) for t in transforms], np.float32)
+        self._ck(self._lib.rc_multi_update_transforms(self._m, handle.id, xf.ctypes.data, None, len(xf)))
+
+    def update(self, handle: TLASHandle, mesh, face_meta=None, refit: bool = False):
+        v = TLAS._verts(mesh)
+        fm = None if face_meta is None else np.ascontiguousarray(face_meta, np.uint32)
+        self._ck(self._lib.rc_multi_update_geometry(self._m, handle.id, v.ctypes.data, len(v), None if fm is None else fm.ctypes.data, L.RC_UPDATE_REFIT if refit else 0))
+
+    def sync(self) -> int:
+        a = C.c_int32()
+        self._ck(self._lib.rc_multi_sync(self._m, C.byref(a)))
+        return a.value
+
+    def _trace(self, rays, any_hit, watertight=False):
+        rays = _as_rays(rays)
+        hits = np.zeros(len(rays), HIT_DTYPE)
+        fn = self._lib.rc_multi_trace_any if any_hit else self._lib.rc_multi_trace_closest
+        if len(rays):
+            self._ck(fn(self._m, rays.ctypes.data, hits.ctypes.data, len(rays), L.RC_MODE_WATERTIGHT if watertight else 0))
+        return hits
+
+    def trace_closest(self, rays, **kw) -> np.ndarray:
+        return self._trace(rays, False, **kw)
+
+    def trace_any(self, rays, **kw) -> np.ndarray:
+        return self._trace(rays, True, **kw)
+
+    def view_factors(self, rays_per_triangle: int = 10000, seed: int = 0) -> np.ndarray:
+        n = C.c_uint32()
+        self._ck(self._lib.rc_sizes(self._lib.rc_multi_context(self._m, 0), None, None, C.byref(n), None))
+        out = np.zeros((n.value, n.value), np.uint32)
+        sk = C.c_uint64()
+        if n.value:
+            self._ck(self._lib.rc_multi_view_factors(self._m, rays_per_triangle, seed, out.ctypes.data, C.byref(sk)))
+        return out
+
+
 def build_static_tlas(meshes, metadata_fn=None, device: Optional[int] = None) -> StaticTLAS:
     """TLAS(meshes, metadata_fn) — src/instanced-bvh.jl:2276-2324: one BLAS + identity instance per mesh,
     instance_id = mesh index (1-based), metadata = metadata_fn(mesh_idx, face_idx) (both 1-based)."""

@@ -57,3 +57,38 @@ def test_two_ranks_nccl(tmp_path):
     out = str(tmp_path / "result.txt")
     mp.spawn(_worker, args=(2, 29700 + (os.getpid() % 1000), out), nprocs=2, join=True)
     assert open(out).read() == "ok"
+
+
+def test_multi_tlas_in_library_matches_single_device():
+    """rc_multi_* (one process, every visible GPU, inside the library): replicated scene, sharded rays / view-factor rows; the results are
+    byte-identical to a single-device TLAS.  Runs with one GPU too (one shard); the pure-C twin is tests/cabi/cabi_multi.c."""
+    import raycore_b200 as rc
+    from raycore_b200 import workloads as W
+
+    mesh, xf = W.bumpy_sphere(24), list(W.random_trs(40, 3, extent=6.0))
+    m, s = rc.MultiTLAS(), rc.TLAS()
+    assert m.n_devices >= 1
+    hm, hs = m.push(mesh, xf), s.push(mesh, xf)
+    assert hm.id == hs.id and m.sync() == rc.RC_SYNC_REBUILD
+    s.sync()
+    rays = np.concatenate([W.box_rays(150_001, 1, half=8.0), W.interior_rays(50_000, 2, radius=7.0)])
+    assert m.trace_closest(rays).tobytes() == s.trace_closest(rays).tobytes()
+    assert np.array_equal(m.trace_any(rays)["hit"], s.trace_any(rays)["hit"])
+    assert m.trace_closest(rays, watertight=True).tobytes() == s.trace_closest(rays, watertight=True).tobytes()
+    xf2 = [t.copy() for t in xf]
+    for t in xf2:
+        t[3] += 0.5
+    m.update_transforms(hm, xf2)
+    s.update_transforms(hs, xf2)
+    assert m.sync() == rc.RC_SYNC_REFIT
+    s.sync()
+    assert m.trace_closest(rays).tobytes() == s.trace_closest(rays).tobytes()
+    assert m.delete(hm) and s.delete(hs)
+    # view factors: one mesh, dense metadata, rows sharded over the devices
+    keep = ~W.is_degenerate(mesh)
+    meta = np.zeros(len(mesh), np.uint32)
+    meta[keep] = 1 + np.arange(keep.sum())
+    m.push(mesh, None, face_meta=meta); s.push(mesh, None, face_meta=meta)
+    m.sync(); s.sync()
+    assert np.array_equal(m.view_factors(200, seed=5), s.view_factors(200, seed=5))
+    m.free(); s.free()

@@ -10,5 +10,5 @@ mkdir -p $out
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 ARCH="-gencode arch=compute_100a,code=sm_100a"
 $NVCC -O3 -std=c++17 $ARCH -lineinfo -Xcompiler -fPIC,-ffp-contract=off,-Wall -Xptxas -v --expt-relaxed-constexpr "$@" -c rc_trace.cu -o $out/rc_trace.o 2> $out/rc_trace.ptxas.log || (cat $out/rc_trace.ptxas.log; false)
-$NVCC -shared $ARCH -o $out/libraycore_cuda.so rc_api.o rc_build.o $out/rc_trace.o rc_analysis.o rc_collide.o rc_wavefront.o
+$NVCC -shared $ARCH -o $out/libraycore_cuda.so rc_api.o rc_build.o $out/rc_trace.o rc_analysis.o rc_collide.o rc_wavefront.o rc_multi.o
 echo "$name: $(grep -A2 'k_trace_wideILb0ELb0E10RcIoArraysLb0' $out/rc_trace.ptxas.log | grep -o 'Used [0-9]* registers\|[0-9]* bytes spill stores' | tr '\n' ' ')"
