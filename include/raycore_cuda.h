@@ -95,6 +95,7 @@ typedef struct rc_context rc_context; /* one mutable TLAS (src/instanced-bvh.jl:
                                      reference's traversal default and this library's): no ray slips between two triangles that share an
                                      edge.  Hit / miss and ids can differ from the default mode at edges; t, u, v differ in the last bits.
                                      Combines with RC_MODE_REFERENCE_ORDER; not with RC_COUNTERS */
+#define RC_IGNORE_TMIN 0x800u /* closest-hit trace: treat ray.tmin as 0 (what closest_hit4 does, src/bvh4.jl:610); default wide path only */
 #define RC_COUNTERS 0x8u        /* accumulate per-ray work counters (rc_get_counters) — instrumented build of the same kernel */
 #define RC_VERTS_ON_DEVICE 0x10u /* rc_push / rc_update_geometry: verts (and face_meta) are device pointers */
 #define RC_NO_SYNC 0x20u        /* trace: do not cudaStreamSynchronize before returning (device buffers only) */
@@ -310,6 +311,36 @@ int32_t rc_ipc_close(rc_context *ctx, void *ptr);
  * rc_wait() drains the copy stream. */
 int32_t rc_peer_copy_async(rc_context *ctx, void *dst, const void *src, size_t bytes, uint32_t slot);
 int32_t rc_stream_wait_copy(rc_context *ctx, uint32_t slot);
+
+/* ---- BLAS4 / build_blas4 / closest_hit4 / any_hit4 (src/bvh4.jl:154-163, 511-523, 606-766; exported at src/Raycore.jl:105) -------------
+ * One geometry traversed on its own 4-wide BVH, without a TLAS.  The library's wide BVH is exactly that structure, so a BLAS4 is a
+ * geometry under one identity instance (the single-instance kernel variant has no top level).  The reference's 120-byte BVHNode4
+ * (full float boxes, src/bvh4.jl:40-72) is not reproduced: rc_blas4_read_nodes returns this library's 64-byte quantised nodes. */
+typedef struct rc_blas4 rc_blas4;
+/* wide node, 64 bytes: child k's box = origin + q * scale per axis, lo planes rounded down / hi planes rounded up (conservative), byte k of
+ * every q word = child k; s* = scale * 2^24; child reference: wide-node index, or 0x80000000 | (count-1) << 28 | first sorted triangle;
+ * an unused slot repeats child 0 under an inverted box (qlo = 255, qhi = 0).  Slot 0 and slots that head no wide node are zero. */
+typedef struct rc_wide_node {
+    float origin[3], sx;
+    uint32_t qlo[3], qhi_x;
+    uint32_t qhi_y, qhi_z, child01[2];
+    uint32_t child23[2];
+    float sy, sz;
+} rc_wide_node;
+/* build_blas4(primitives) — :511-523.  Same vertex / metadata / flag conventions as rc_push; "Cannot build BLAS4 from empty primitive
+ * list" (:513) when no valid triangle is left.  Errors of a failed build: rc_blas4_last_error(NULL). */
+int32_t rc_blas4_build(int32_t device, const float *verts, uint32_t n_faces, const uint32_t *face_meta, uint32_t flags, rc_blas4 **out);
+int32_t rc_blas4_destroy(rc_blas4 *b);
+const char *rc_blas4_last_error(const rc_blas4 *b);
+/* n_primitives = length(blas.primitives); n_node_slots = wide-node slots incl. slot 0 (root = slot 1); root_aabb = blas.root_aabb */
+int32_t rc_blas4_info(const rc_blas4 *b, uint32_t *n_primitives, uint32_t *n_node_slots, float root_aabb[6]);
+/* closest_hit4(blas, ray) / any_hit4(blas, ray) — :606-766, batched like rc_trace_*; ray.tmin is ignored as the reference does (:610);
+ * hit.instance_id = instance_custom_index = 0.  Flags: RC_RAYS_ON_DEVICE, RC_HITS_ON_DEVICE, RC_NO_SYNC, RC_MODE_WATERTIGHT. */
+int32_t rc_blas4_trace_closest(rc_blas4 *b, const rc_ray *rays, rc_hit *hits, uint64_t n, uint32_t flags);
+int32_t rc_blas4_trace_any(rc_blas4 *b, const rc_ray *rays, rc_hit *hits, uint64_t n, uint32_t flags);
+int32_t rc_blas4_read_nodes(rc_blas4 *b, rc_wide_node *out, uint32_t capacity);
+/* the context behind the BLAS4 (read-backs such as rc_read_blas_order / rc_read_blas_faces, streams, timers) */
+rc_context *rc_blas4_context(rc_blas4 *b);
 
 /* ---- several GPUs of one node behind one handle ---------------------------------------------------------
  * One process, all devices, inside the library: an rc_multi owns one context per device; the scene is replicated (every mutation is

@@ -35,6 +35,10 @@ RC_BUILD_KEEP_BVH2 = 0x80
 RC_BUILD_ALLOW_REFIT = 0x100
 RC_UPDATE_REFIT = 0x200
 RC_MODE_WATERTIGHT = 0x400
+RC_IGNORE_TMIN = 0x800
+WIDE_NODE_DTYPE = np.dtype([("origin", "<f4", 3), ("sx", "<f4"), ("qlo", "<u4", 3), ("qhi_x", "<u4"), ("qhi_y", "<u4"), ("qhi_z", "<u4"), ("child01", "<u4", 2),
+                            ("child23", "<u4", 2), ("sy", "<f4"), ("sz", "<f4")])  # rc_wide_node
+assert WIDE_NODE_DTYPE.itemsize == 64
 RC_MAX_LIGHTS = 16
 
 RC_SYNC_NONE, RC_SYNC_REFIT, RC_SYNC_REBUILD = 0, 1, 2
@@ -82,6 +86,7 @@ EXPORTS = [
     "rc_shadow_visibility",
     "rc_device_alloc", "rc_device_free", "rc_host_alloc", "rc_host_free", "rc_memcpy_h2d", "rc_memcpy_d2h",
     "rc_ipc_export", "rc_ipc_open", "rc_ipc_close", "rc_peer_copy_async", "rc_stream_wait_copy",
+    "rc_blas4_build", "rc_blas4_destroy", "rc_blas4_last_error", "rc_blas4_info", "rc_blas4_trace_closest", "rc_blas4_trace_any", "rc_blas4_read_nodes", "rc_blas4_context",
     "rc_multi_create", "rc_multi_destroy", "rc_multi_last_error", "rc_multi_device_count", "rc_multi_context", "rc_multi_push", "rc_multi_delete",
     "rc_multi_update_transforms", "rc_multi_update_geometry", "rc_multi_sync", "rc_multi_trace_closest", "rc_multi_trace_any", "rc_multi_view_factors",
 ]  # fmt: skip
@@ -177,6 +182,14 @@ def load():
         "rc_ipc_close": (i32, [vp, vp]),
         "rc_peer_copy_async": (i32, [vp, vp, vp, C.c_size_t, u32]),
         "rc_stream_wait_copy": (i32, [vp, u32]),
+        "rc_blas4_build": (i32, [i32, vp, u32, vp, u32, C.POINTER(vp)]),
+        "rc_blas4_destroy": (i32, [vp]),
+        "rc_blas4_last_error": (C.c_char_p, [vp]),
+        "rc_blas4_info": (i32, [vp, pu32, pu32, vp]),
+        "rc_blas4_trace_closest": (i32, [vp, vp, vp, u64, u32]),
+        "rc_blas4_trace_any": (i32, [vp, vp, vp, u64, u32]),
+        "rc_blas4_read_nodes": (i32, [vp, vp, u32]),
+        "rc_blas4_context": (vp, [vp]),
         "rc_multi_create": (i32, [vp, u32, C.POINTER(vp)]),
         "rc_multi_destroy": (i32, [vp]),
         "rc_multi_last_error": (C.c_char_p, [vp]),

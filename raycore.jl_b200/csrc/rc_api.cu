@@ -49,6 +49,7 @@ struct rc_context {
     unsigned long long *d_work = nullptr;
     RcCounters *d_counters = nullptr;
     uint32_t *d_overflow = nullptr;
+    uint32_t *h_err = nullptr;  // pinned host word: the hard-error counter is read back with the copy queued BEFORE a call's final sync (no extra round trip)
     rc_ray *d_rays = nullptr;
     rc_hit *d_hits = nullptr;
     size_t cap_rays = 0, cap_hits = 0;
@@ -172,6 +173,8 @@ int32_t rc_create(int32_t device, rc_context **out) {
     CREATE_CK(cudaMalloc(&ctx->d_overflow, 4 * sizeof(uint32_t)));  // [0] rays flagged for k_trace_fixup, [1] hard errors, [2] flagged-ray scratch of the inline re-trace policies
     CREATE_CK(cudaMemset(ctx->d_counters, 0, sizeof(RcCounters)));
     CREATE_CK(cudaMemset(ctx->d_overflow, 0, 4 * sizeof(uint32_t)));
+    CREATE_CK(cudaHostAlloc(&ctx->h_err, sizeof(uint32_t), cudaHostAllocDefault));
+    *ctx->h_err = 0;
     // keep freed blocks cached in the stream-ordered pool: rebuild-per-frame workloads reuse them
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -196,6 +199,7 @@ int32_t rc_destroy(rc_context *ctx) {
     if (ctx->d_flat) cudaFreeAsync(ctx->d_flat, ctx->stream);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_work); cudaFree(ctx->d_counters); cudaFree(ctx->d_overflow);
+    if (ctx->h_err) cudaFreeHost(ctx->h_err);
     if (ctx->d_rays) cudaFree(ctx->d_rays);
     if (ctx->d_hits) cudaFree(ctx->d_hits);
     if (ctx->d_normal_ptrs) cudaFree(ctx->d_normal_ptrs);
@@ -673,6 +677,18 @@ static int32_t ensure_capacity(rc_context *ctx, void **buf, size_t *cap, size_t 
     return RC_OK;
 }
 
+// queue the read-back of the hard-error counter on the context stream; the caller's own final cudaStreamSynchronize completes it and
+// overflow_result() then only looks at host memory (a per-ray caller pays one sync per trace, not two)
+static inline void queue_overflow_read(rc_context *ctx) { cudaMemcpyAsync(ctx->h_err, ctx->d_overflow + 1, 4, cudaMemcpyDeviceToHost, ctx->stream); }
+static int32_t overflow_result(rc_context *ctx) {
+    const uint32_t ov = *ctx->h_err;
+    if (ov) {
+        *ctx->h_err = 0;
+        cudaMemsetAsync(ctx->d_overflow + 1, 0, 4, ctx->stream);
+        RC_FAIL(ctx, RC_ERR_STACK_OVERFLOW, "traversal stack overflow for " + std::to_string(ov) + " ray(s)");
+    }
+    return RC_OK;
+}
 static int32_t check_overflow(rc_context *ctx) {
     uint32_t ov = 0;
     RC_CUDA(ctx, cudaMemcpyAsync(&ov, ctx->d_overflow + 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -700,6 +716,8 @@ static int32_t trace_common(rc_context *ctx, const rc_ray *rays, rc_hit *hits, u
             if (!B.nodes2) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "RC_MODE_REFERENCE_ORDER needs the reference-layout BVH2: build the geometry with RC_BUILD_KEEP_BVH2");
     L.count = flags & RC_COUNTERS;
     L.watertight = flags & RC_MODE_WATERTIGHT;
+    L.zero_tmin = flags & RC_IGNORE_TMIN;
+    if (L.zero_tmin && !L.wide) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "RC_IGNORE_TMIN is not available together with RC_MODE_REFERENCE_ORDER");
     if (L.watertight && L.count) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "RC_COUNTERS is not available together with RC_MODE_WATERTIGHT");
     L.work = ctx->d_work;
     L.counters = ctx->d_counters;
@@ -714,9 +732,10 @@ static int32_t trace_common(rc_context *ctx, const rc_ray *rays, rc_hit *hits, u
         cudaEventRecord(ctx->ev_t1, ctx->stream);
         ctx->last_launches = 1;
         if (flags & RC_NO_SYNC) return RC_OK;
+        queue_overflow_read(ctx);
         RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         cudaEventElapsedTime(&ctx->last_ms, ctx->ev_t0, ctx->ev_t1);
-        return check_overflow(ctx);
+        return overflow_result(ctx);
     }
     // host buffers: stage through device memory in chunks; H2D of chunk c+1, trace of chunk c and D2H of chunk c-1 overlap
     const rc_ray *d_rays = rays;
@@ -752,11 +771,12 @@ static int32_t trace_common(rc_context *ctx, const rc_ray *rays, rc_hit *hits, u
         }
     }
     cudaEventRecord(ctx->ev_t1, ctx->stream);
+    queue_overflow_read(ctx);
     RC_CUDA(ctx, cudaStreamSynchronize(ctx->s_h2d));
     RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     RC_CUDA(ctx, cudaStreamSynchronize(ctx->s_d2h));
     cudaEventElapsedTime(&ctx->last_ms, ctx->ev_t0, ctx->ev_t1);
-    return check_overflow(ctx);
+    return overflow_result(ctx);
 }
 
 int32_t rc_trace_closest(rc_context *ctx, const rc_ray *rays, rc_hit *hits, uint64_t n, uint32_t flags) { return trace_common(ctx, rays, hits, n, flags, false); }
@@ -1152,6 +1172,73 @@ int32_t rc_shadow_visibility(rc_context *ctx, const rc_ray *rays, const rc_hit *
     return finish_stage(ctx, flags, 2, true);
 }
 
+
+// ------------------------------------------------------------------------------------------------ BLAS4 (src/bvh4.jl)
+// A BLAS4 is one geometry traversed on its own 4-wide BVH: the library's wide BVH is exactly that, so the object is a private context
+// holding the geometry under one identity instance (the single-instance kernel variant skips the top level entirely).
+struct rc_blas4 {
+    rc_context *ctx = nullptr;
+    std::string last_error;
+};
+static std::string g_blas4_error;
+static_assert(sizeof(rc_wide_node) == sizeof(RcNode4), "rc_wide_node is the public name of the wide-node layout");
+
+int32_t rc_blas4_build(int32_t device, const float *verts, uint32_t n_faces, const uint32_t *face_meta, uint32_t flags, rc_blas4 **out) {  // build_blas4, :511-523
+    if (!out) return RC_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    rc_context *ctx = nullptr;
+    int32_t rc = rc_create(device, &ctx);
+    if (rc != RC_OK) { g_blas4_error = g_create_error; return rc; }
+    const float ident[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    uint32_t h = 0;
+    rc = rc_push(ctx, verts, n_faces, face_meta, ident, ident, nullptr, 1, flags & (RC_VERTS_ON_DEVICE | RC_BUILD_KEEP_BVH2 | RC_BUILD_ALLOW_REFIT), &h);
+    if (rc == RC_OK) rc = rc_sync(ctx, nullptr);
+    if (rc != RC_OK) {
+        g_blas4_error = rc == RC_ERR_NO_VALID_TRIANGLES ? "Cannot build BLAS4 from empty primitive list" : ctx->last_error;  // :513
+        rc_destroy(ctx);
+        return rc;
+    }
+    rc_blas4 *b = new rc_blas4();
+    b->ctx = ctx;
+    *out = b;
+    return RC_OK;
+}
+int32_t rc_blas4_destroy(rc_blas4 *b) {
+    if (!b) return RC_OK;
+    rc_destroy(b->ctx);
+    delete b;
+    return RC_OK;
+}
+const char *rc_blas4_last_error(const rc_blas4 *b) { return b ? b->ctx->last_error.c_str() : g_blas4_error.c_str(); }
+rc_context *rc_blas4_context(rc_blas4 *b) { return b ? b->ctx : nullptr; }
+int32_t rc_blas4_info(const rc_blas4 *b, uint32_t *n_primitives, uint32_t *n_node_slots, float root_aabb[6]) {
+    if (!b) return RC_ERR_INVALID_ARGUMENT;
+    RC_LOCK(b->ctx);
+    const RcDeviceBlas &B = b->ctx->blas[0];
+    if (n_primitives) *n_primitives = B.n;
+    if (n_node_slots) *n_node_slots = B.n + 1;
+    if (root_aabb) memcpy(root_aabb, B.root_aabb, 24);
+    return RC_OK;
+}
+// closest_hit4 / any_hit4 (:606-766): ray.t_min is ignored as the reference does (ray_mint = 0, :610)
+int32_t rc_blas4_trace_closest(rc_blas4 *b, const rc_ray *rays, rc_hit *hits, uint64_t n, uint32_t flags) {
+    if (!b) return RC_ERR_INVALID_ARGUMENT;
+    return trace_common(b->ctx, rays, hits, n, flags | RC_IGNORE_TMIN, false);
+}
+int32_t rc_blas4_trace_any(rc_blas4 *b, const rc_ray *rays, rc_hit *hits, uint64_t n, uint32_t flags) {
+    if (!b) return RC_ERR_INVALID_ARGUMENT;
+    return trace_common(b->ctx, rays, hits, n, flags | RC_IGNORE_TMIN, true);
+}
+int32_t rc_blas4_read_nodes(rc_blas4 *b, rc_wide_node *out, uint32_t capacity) {
+    if (!b || !out) return RC_ERR_INVALID_ARGUMENT;
+    rc_context *ctx = b->ctx;
+    RC_ENTER(ctx);
+    const RcDeviceBlas &B = ctx->blas[0];
+    if (capacity < B.n + 1) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "capacity too small");
+    RC_CUDA(ctx, cudaMemcpyAsync(out, B.nodes4, sizeof(RcNode4) * ((size_t)B.n + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    RC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RC_OK;
+}
 
 // ------------------------------------------------------------------------------------------------ memory helpers
 int32_t rc_device_alloc(rc_context *ctx, size_t bytes, void **out) {

@@ -632,10 +632,13 @@ __global__ void k_finish(const RcBox *__restrict__ boxes, float *__restrict__ ou
 
 static void launch_fit(cudaStream_t st, uint32_t n_bound, const RcTri *tris_in, const uint32_t *perm, RcTri *tris, const RcBox *inst_boxes, const uint32_t *leaf_map,
                        const uint32_t *n_ptr, const RcTopo *topo, const uint32_t *parent, uint32_t *flags, RcBox *boxes, RcNode2 *nodes2, uint32_t *ctl) {
-    static bool configured = false;
-    if (!configured) {
+    // the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute (several devices build concurrently under rc_multi_*)
+    static bool configured[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
         cudaFuncSetAttribute(k_fit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FitSmem));
-        configured = true;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     k_fit<<<cdiv(n_bound, FIT_T), FIT_T, sizeof(FitSmem), st>>>(tris_in, perm, tris, inst_boxes, leaf_map, n_ptr, n_bound, topo, parent, flags, boxes, nodes2, ctl);
 }

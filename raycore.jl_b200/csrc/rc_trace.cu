@@ -73,7 +73,7 @@ bool rc_launch_trace(cudaStream_t st, const RcTraceLaunch &L, std::string &err) 
         int blocks = (int)(want < cap ? want : cap);
         if (blocks < 1) blocks = 1;
 #define RC_ARGS L.scene, L.rays, L.hits, L.n, L.work, L.counters, L.overflow
-#define RC_WARGS L.scene, RcIoArrays{L.rays, L.hits}, L.n, L.work, L.counters, L.overflow
+#define RC_WARGS L.scene, RcIoArrays{L.rays, L.hits, L.zero_tmin}, L.n, L.work, L.counters, L.overflow
         const bool single = L.scene.n_instances == 1u;
         if (L.wide) {
             // (ANY, COUNT, SINGLE, WT): the instrumented build exists for Moeller-Trumbore only

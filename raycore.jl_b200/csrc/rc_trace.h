@@ -16,6 +16,7 @@ struct RcTraceLaunch {
     rc_hit *hits;        // device
     unsigned long long n;
     bool any, wide, count;
+    bool zero_tmin = false;    // RC_IGNORE_TMIN (wide path only)
     bool watertight = false;   // RC_MODE_WATERTIGHT: the reference's watertight triangle test instead of Moeller-Trumbore
     unsigned long long *work;  // device work counter (zeroed by the launcher)
     RcCounters *counters;      // device, only with count

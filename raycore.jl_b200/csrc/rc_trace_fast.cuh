@@ -209,7 +209,12 @@ struct RcIoArrays {
     static constexpr uint32_t kFetchMinSingle = RC_FETCH_MIN_SINGLE, kTWSingle = RC_T_W_SINGLE;
     const rc_ray *rays;
     rc_hit *hits;
-    __device__ __forceinline__ rc_ray load(unsigned long long i) const { return rc_load_ray(rays, i); }
+    bool zero_tmin;  // closest_hit4 / any_hit4 ignore ray.t_min (src/bvh4.jl:610, :700)
+    __device__ __forceinline__ rc_ray load(unsigned long long i) const {
+        rc_ray r = rc_load_ray(rays, i);
+        if (zero_tmin) r.tmin = 0.0f;
+        return r;
+    }
     __device__ __forceinline__ void store(unsigned long long i, const rc_hit &h) const { rc_store_hit(hits, i, h); }
 };
 

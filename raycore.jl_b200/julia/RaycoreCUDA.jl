@@ -17,6 +17,8 @@ import Raycore: Mat3x4f, mat4_to_mat3x4, mat3x4_inverse, TLASHandle, RTRay, RTHi
 const lib = get(ENV, "RAYCORE_CUDA_LIB", "libraycore_cuda")
 
 const RC_RAYS_ON_DEVICE = UInt32(0x1); const RC_HITS_ON_DEVICE = UInt32(0x2); const RC_MODE_REFERENCE_ORDER = UInt32(0x4)
+const RC_BUILD_KEEP_BVH2 = UInt32(0x80); const RC_BUILD_ALLOW_REFIT = UInt32(0x100); const RC_UPDATE_REFIT = UInt32(0x200)
+const RC_MODE_WATERTIGHT = UInt32(0x400)
 
 struct RcError <: Exception; code::Int32; msg::String; end
 function check(ctx, rc::Int32)
@@ -31,21 +33,67 @@ mutable struct CuStaticTLAS{T} <: Raycore.AbstractAdaptedAccel
     generation::Int
 end
 
+"What triangle_of needs from a pushed mesh, decomposed once at push! time (not per hit)."
+struct MeshSource
+    verts::Vector{Point3f}; norms::Vector{Raycore.Normal3f}; uvs::Vector{Point2f}; indices::Vector{UInt32}
+end
+function MeshSource(nmesh)
+    fs = decompose(TriangleFace{UInt32}, nmesh); uvs_raw = GeometryBasics.decompose_uv(nmesh)
+    MeshSource(decompose(Point3f, nmesh), Raycore.Normal3f.(decompose_normals(nmesh)), isnothing(uvs_raw) ? Point2f[] : Point2f.(uvs_raw), collect(reinterpret(UInt32, fs)))
+end
+
 mutable struct CuTLAS <: Raycore.AbstractAccel
     ctx::Ptr{Cvoid}
-    meshes::Dict{UInt32, Vector}           # handle id => filtered-order Vector{Triangle} source (input order)
+    meshes::Dict{UInt32, MeshSource}       # handle id => decomposed source mesh (input order)
     prim_to_face::Dict{UInt32, Vector{UInt32}}
+    inst_handles::Vector{UInt32}           # instance position => handle id, refreshed by sync!
+    inst_blas::Vector{UInt32}              # instance position => blas_index, refreshed by sync!
     static_tlas::Union{Nothing, CuStaticTLAS}
     generation::Int
-    function CuTLAS(device::Integer = -1)
+    # keep_bvh2 / allow_refit: RC_BUILD_KEEP_BVH2 (reference-order mode, BVH2 read-backs) / RC_BUILD_ALLOW_REFIT (update!(...; refit = true))
+    function CuTLAS(device::Integer = -1; keep_bvh2::Bool = false, allow_refit::Bool = false)
         ref = Ref{Ptr{Cvoid}}(C_NULL)
         rc = ccall((:rc_create, lib), Int32, (Int32, Ref{Ptr{Cvoid}}), device, ref)
         rc == 0 || error(unsafe_string(ccall((:rc_last_error, lib), Cstring, (Ptr{Cvoid},), C_NULL)))
-        t = new(ref[], Dict(), Dict(), nothing, 0)
+        t = new(ref[], Dict(), Dict(), UInt32[], UInt32[], nothing, 0)
+        flags = (keep_bvh2 ? RC_BUILD_KEEP_BVH2 : UInt32(0)) | (allow_refit ? RC_BUILD_ALLOW_REFIT : UInt32(0))
+        flags != 0 && check(t.ctx, ccall((:rc_set_build_flags, lib), Int32, (Ptr{Cvoid}, UInt32), t.ctx, flags))
         finalizer(free!, t)                                    # finalizer(free!, tlas), src/instanced-bvh.jl:355
         t
     end
 end
+
+# ---- the reference's convenience constructors (src/instanced-bvh.jl:2276-2324, 2361-2378) ----------------------------------
+"""
+    CuTLAS(primitives, metadata_fn; device = -1) -> CuStaticTLAS      (TLAS(primitives, metadata_fn), :2276-2324)
+
+One BLAS per primitive with a single identity instance, `Triangle.metadata = metadata_fn(mesh_idx, face_idx)` (face index counted before the
+degenerate filter, :2303) and `InstanceDescriptor.instance_id = mesh_idx` (:2316).  Like the reference's, the result is the traversable
+(adapted) structure.  The hit record carries 32 bits of metadata: `metadata_fn` must return a 4-byte isbits value (UInt32, Int32, Float32, ...).
+"""
+function CuTLAS(primitives::AbstractVector, metadata_fn::Function; device::Integer = -1)
+    sizeof(typeof(metadata_fn(1, 1))) == 4 || error("metadata_fn must return a 4-byte isbits value (the hit record carries 32 bits of metadata)")
+    t = CuTLAS(device)
+    for (mi, prim) in enumerate(primitives)
+        gb_mesh = prim isa GeometryBasics.Mesh ? prim : GeometryBasics.uv_normal_mesh(prim)      # :2291
+        v, _, nmesh = soup(gb_mesh)
+        meta = UInt32[reinterpret(UInt32, metadata_fn(mi, i)) for i in 1:size(v, 2)]
+        push_soup!(t, v, meta, nmesh, [Mat4f(I)]; instance_ids = UInt32[mi])
+    end
+    return Adapt.adapt(nothing, t)
+end
+"""
+    CuTLAS(meshes::AbstractVector{<:GeometryBasics.Mesh}; device = -1) -> (CuTLAS, Vector{TLASHandle})      (TLAS(meshes), :2361-2378)
+"""
+function CuTLAS(meshes::AbstractVector{<:GeometryBasics.Mesh}; device::Integer = -1, kw...)
+    isempty(meshes) && error("Cannot create TLAS from empty mesh list")                           # :2362
+    t = CuTLAS(device; kw...)
+    handles = TLASHandle[push!(t, m) for m in meshes]
+    sync!(t)
+    return t, handles
+end
+Base.eltype(::CuTLAS) = Triangle{UInt32}                                                          # :2335-2338
+Base.eltype(::CuStaticTLAS{T}) where {T} = T                                                      # :2340-2342
 
 function free!(t::CuTLAS)
     t.ctx == C_NULL && return nothing
@@ -69,6 +117,9 @@ function Base.push!(t::CuTLAS, mesh::GeometryBasics.Mesh, transforms::AbstractVe
     instance_ids !== nothing && length(instance_ids) != length(transforms) &&
         throw(ArgumentError("instance_ids length $(length(instance_ids)) != transforms length $(length(transforms))"))
     v, meta, nmesh = soup(mesh)
+    return push_soup!(t, v, meta, nmesh, transforms; instance_ids)
+end
+function push_soup!(t::CuTLAS, v::Matrix{Float32}, meta, nmesh, transforms::AbstractVector{Mat4f}; instance_ids = nothing)
     xf = [mat4_to_mat3x4(m) for m in transforms]
     inv = [mat3x4_inverse(m) for m in xf]          # computed with Raycore's own code => bit-identical descriptors
     ids = instance_ids === nothing ? C_NULL : UInt32.(instance_ids)
@@ -77,7 +128,7 @@ function Base.push!(t::CuTLAS, mesh::GeometryBasics.Mesh, transforms::AbstractVe
         (Ptr{Cvoid}, Ptr{Float32}, UInt32, Ptr{UInt32}, Ptr{Float32}, Ptr{Float32}, Ptr{UInt32}, UInt32, UInt32, Ref{UInt32}),
         t.ctx, v, size(v, 2), meta === nothing ? C_NULL : meta, reinterpret(Float32, xf), reinterpret(Float32, inv), ids,
         length(xf), 0, h))
-    t.meshes[h[]] = [nmesh]
+    t.meshes[h[]] = MeshSource(nmesh)
     return TLASHandle(h[])
 end
 Base.push!(t::CuTLAS, mesh::GeometryBasics.Mesh, transform::Mat4f = Mat4f(I); instance_id::UInt32 = UInt32(0), sbt_offset::UInt32 = UInt32(0)) =
@@ -109,7 +160,7 @@ function push_exported!(t::CuTLAS, blob::Vector{UInt8}, mesh::GeometryBasics.Mes
     h = Ref{UInt32}(0)
     check(t.ctx, ccall((:rc_push_exported, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, UInt64, Ptr{Float32}, Ptr{Float32}, Ptr{UInt32}, UInt32, Ref{UInt32}),
         t.ctx, blob, length(blob), reinterpret(Float32, xf), reinterpret(Float32, inv), ids, length(xf), h))
-    t.meshes[h[]] = [GeometryBasics.expand_faceviews(mesh)]
+    t.meshes[h[]] = MeshSource(GeometryBasics.expand_faceviews(mesh))
     return TLASHandle(h[])
 end
 
@@ -128,17 +179,27 @@ function update_transform!(t::CuTLAS, h::TLASHandle, m::Union{Mat4f, Mat3x4f})
     is_valid(t, h) && n != 1 && error("Handle has $n instances, use update_transforms! for multiple")
     update_transforms!(t, h, [m isa Mat4f ? mat4_to_mat3x4(m) : m])
 end
-function update!(t::CuTLAS, h::TLASHandle, mesh)
+"update!(tlas, handle, mesh) (:808-857).  `refit = true`: re-fit the kept radix tree when only vertices moved (needs `allow_refit`); returns whether the library re-fitted."
+function update!(t::CuTLAS, h::TLASHandle, mesh; refit::Bool = false)
     v, meta, nmesh = soup(mesh)
     check(t.ctx, ccall((:rc_update_geometry, lib), Int32, (Ptr{Cvoid}, UInt32, Ptr{Float32}, UInt32, Ptr{UInt32}, UInt32),
-        t.ctx, h.id, v, size(v, 2), meta === nothing ? C_NULL : meta, 0))
-    t.meshes[h.id] = [nmesh]; nothing
+        t.ctx, h.id, v, size(v, 2), meta === nothing ? C_NULL : meta, refit ? RC_UPDATE_REFIT : UInt32(0)))
+    t.meshes[h.id] = MeshSource(nmesh)
+    return ccall((:rc_last_update_refitted, lib), Int32, (Ptr{Cvoid},), t.ctx) != 0
 end
 
 function sync!(t::CuTLAS)
     a = Ref{Int32}(0); check(t.ctx, ccall((:rc_sync, lib), Int32, (Ptr{Cvoid}, Ref{Int32}), t.ctx, a))
     if a[] == 2 || t.static_tlas === nothing           # rebuild => new adapted object; refit keeps identity (test_mesh_update.jl:214)
         t.generation += 1; t.static_tlas = CuStaticTLAS{Triangle{UInt32}}(t, t.generation); empty!(t.prim_to_face)
+        # instance position => (handle, BLAS) tables for triangle_of: read once per rebuild, not per hit (compaction renumbers both)
+        n = ccall((:rc_n_total_instances, lib), UInt32, (Ptr{Cvoid},), t.ctx)
+        t.inst_handles = Vector{UInt32}(undef, n); t.inst_blas = Vector{UInt32}(undef, n)
+        ccall((:rc_get_instance_handles, lib), Int32, (Ptr{Cvoid}, Ptr{UInt32}, UInt32), t.ctx, t.inst_handles, n)
+        for hid in unique(t.inst_handles)
+            d = get_instances(t, TLASHandle(hid))
+            for (k, p) in enumerate(findall(==(hid), t.inst_handles)); t.inst_blas[p] = d[k].blas_index; end
+        end
     end
     return t
 end
@@ -182,21 +243,82 @@ closest_hit(s::CuStaticTLAS, ray::Raycore.AbstractRay) =
 any_hit(s::CuStaticTLAS, ray::Raycore.AbstractRay) =
     hit_tuple(s, trace_closest_hits!([RTHitResult(0, 0, 0, 0, 0, 0, 0, 0)], [RTRay(ray.o..., 0f0, ray.d..., ray.t_max)], s; any = true)[1], h -> triangle_of(s.owner, h))
 
-"Materialise Raycore's Triangle (vertices, normals, uv, metadata) for a hit from the caller-side copy of the mesh (rc_read_blas_faces)."
+"Materialise Raycore's Triangle (vertices, normals, uv, metadata) for a hit from the caller-side copy of the mesh: two table look-ups and one build_triangle per hit (the mesh was decomposed at push! time, the instance tables at sync!)."
 function triangle_of(t::CuTLAS, h::RTHitResult)
-    handles = Vector{UInt32}(undef, ccall((:rc_n_total_instances, lib), UInt32, (Ptr{Cvoid},), t.ctx))
-    ccall((:rc_get_instance_handles, lib), Int32, (Ptr{Cvoid}, Ptr{UInt32}, UInt32), t.ctx, handles, length(handles))
-    hid = handles[h.instance_id + 1]
-    nmesh = t.meshes[hid][1]
-    blas = get_instances(t, TLASHandle(hid))[1].blas_index
+    hid = t.inst_handles[h.instance_id + 1]
+    blas = t.inst_blas[h.instance_id + 1]
     faces = get!(t.prim_to_face, blas) do
         n = ccall((:rc_blas_n_prims, lib), UInt32, (Ptr{Cvoid}, UInt32), t.ctx, blas); out = Vector{UInt32}(undef, n)
         ccall((:rc_read_blas_faces, lib), Int32, (Ptr{Cvoid}, UInt32, Ptr{UInt32}, UInt32), t.ctx, blas, out, n); out
     end
-    face = faces[h.primitive_id + 1] + 1
-    fs = decompose(TriangleFace{UInt32}, nmesh); verts = decompose(Point3f, nmesh); norms = Raycore.Normal3f.(decompose_normals(nmesh))
-    uvs_raw = GeometryBasics.decompose_uv(nmesh); uvs = isnothing(uvs_raw) ? Point2f[] : Point2f.(uvs_raw)
-    Raycore.build_triangle(verts, norms, uvs, collect(reinterpret(UInt32, fs)), face, h._pad2)      # _pad2 carries Triangle.metadata
+    m = t.meshes[hid]
+    Raycore.build_triangle(m.verts, m.norms, m.uvs, m.indices, faces[h.primitive_id + 1] + 1, h._pad2)      # _pad2 carries Triangle.metadata
+end
+
+# ---- BLAS4 / build_blas4 / closest_hit4 / any_hit4 (src/bvh4.jl:154-163, 511-523, 606-766) --------------------------------
+"One geometry on its own 4-wide BVH (rc_blas4_*): the library's wide BVH under an identity instance."
+mutable struct CuBLAS4
+    ptr::Ptr{Cvoid}
+    primitives::Vector            # the caller's Triangles, in input order (closest_hit4 returns one of them)
+    prim_to_input::Vector{UInt32} # primitive_id (position after the degenerate filter) => index into `primitives` (0-based)
+end
+"build_blas4(primitives) (:511-523) on the GPU; `primitives::AbstractVector{<:Triangle}` as in the reference."
+function build_blas4_cuda(primitives::AbstractVector{<:Triangle}; device::Integer = -1)
+    isempty(primitives) && error("Cannot build BLAS4 from empty primitive list")                    # :513
+    v = Matrix{Float32}(undef, 9, length(primitives))
+    for (i, tri) in enumerate(primitives), k in 1:3, c in 1:3; v[3 * (k - 1) + c, i] = tri.vertices[k][c]; end
+    meta = UInt32[reinterpret(UInt32, tri.metadata) for tri in primitives]
+    ref = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:rc_blas4_build, lib), Int32, (Int32, Ptr{Float32}, UInt32, Ptr{UInt32}, UInt32, Ref{Ptr{Cvoid}}), device, v, size(v, 2), meta, 0, ref)
+    rc == 0 || error(unsafe_string(ccall((:rc_blas4_last_error, lib), Cstring, (Ptr{Cvoid},), C_NULL)))
+    n = Ref{UInt32}(0); ccall((:rc_blas4_info, lib), Int32, (Ptr{Cvoid}, Ref{UInt32}, Ptr{UInt32}, Ptr{Float32}), ref[], n, C_NULL, C_NULL)
+    faces = Vector{UInt32}(undef, n[])
+    ccall((:rc_read_blas_faces, lib), Int32, (Ptr{Cvoid}, UInt32, Ptr{UInt32}, UInt32), ccall((:rc_blas4_context, lib), Ptr{Cvoid}, (Ptr{Cvoid},), ref[]), 1, faces, n[])
+    b = CuBLAS4(ref[], collect(primitives), faces)
+    finalizer(x -> (x.ptr != C_NULL && ccall((:rc_blas4_destroy, lib), Int32, (Ptr{Cvoid},), x.ptr); x.ptr = C_NULL), b)
+    b
+end
+function trace4!(hits::Vector{RTHitResult}, rays::Vector{RTRay}, b::CuBLAS4; any = false, flags = UInt32(0))
+    f = any ? :rc_blas4_trace_any : :rc_blas4_trace_closest
+    rc = ccall((f, lib), Int32, (Ptr{Cvoid}, Ptr{RTRay}, Ptr{RTHitResult}, UInt64, UInt32), b.ptr, rays, hits, length(rays), flags)
+    rc == 0 || error(unsafe_string(ccall((:rc_blas4_last_error, lib), Cstring, (Ptr{Cvoid},), b.ptr)))
+    hits
+end
+function hit_tuple4(b::CuBLAS4, h::RTHitResult)                                                         # (hit, primitive, distance, barycentric), :606
+    h.hit == 0 && return (false, Raycore.empty_triangle(eltype(b.primitives)), 0f0, SVector{3, Float32}(0, 0, 0))
+    (true, b.primitives[b.prim_to_input[h.primitive_id + 1] + 1], h.t, SVector{3, Float32}(1f0 - h.bary_u - h.bary_v, h.bary_u, h.bary_v))
+end
+Raycore.closest_hit4(b::CuBLAS4, ray::Raycore.AbstractRay) =
+    hit_tuple4(b, trace4!([RTHitResult(0, 0, 0, 0, 0, 0, 0, 0)], [RTRay(ray.o..., ray.t_min, ray.d..., ray.t_max)], b)[1])
+Raycore.any_hit4(b::CuBLAS4, ray::Raycore.AbstractRay) =
+    hit_tuple4(b, trace4!([RTHitResult(0, 0, 0, 0, 0, 0, 0, 0)], [RTRay(ray.o..., 0f0, ray.d..., ray.t_max)], b; any = true)[1])
+
+# ---- several GPUs behind one handle (rc_multi_*): replicated scene, sharded queries, one process ------------------------------
+mutable struct CuMultiTLAS
+    ptr::Ptr{Cvoid}
+end
+function CuMultiTLAS(devices::Union{Nothing, AbstractVector{<:Integer}} = nothing)
+    ref = Ref{Ptr{Cvoid}}(C_NULL); dv = devices === nothing ? Int32[] : Int32.(devices)
+    rc = ccall((:rc_multi_create, lib), Int32, (Ptr{Int32}, UInt32, Ref{Ptr{Cvoid}}), isempty(dv) ? C_NULL : dv, length(dv), ref)
+    rc == 0 || error(unsafe_string(ccall((:rc_multi_last_error, lib), Cstring, (Ptr{Cvoid},), C_NULL)))
+    m = CuMultiTLAS(ref[]); finalizer(x -> (x.ptr != C_NULL && ccall((:rc_multi_destroy, lib), Int32, (Ptr{Cvoid},), x.ptr); x.ptr = C_NULL), m); m
+end
+mcheck(m::CuMultiTLAS, rc::Int32) = rc == 0 ? nothing : error(unsafe_string(ccall((:rc_multi_last_error, lib), Cstring, (Ptr{Cvoid},), m.ptr)))
+function Base.push!(m::CuMultiTLAS, mesh::GeometryBasics.Mesh, transforms::AbstractVector{Mat4f}; instance_ids = nothing)
+    v, meta, _ = soup(mesh); xf = [mat4_to_mat3x4(x) for x in transforms]; inv = [mat3x4_inverse(x) for x in xf]; h = Ref{UInt32}(0)
+    mcheck(m, ccall((:rc_multi_push, lib), Int32, (Ptr{Cvoid}, Ptr{Float32}, UInt32, Ptr{UInt32}, Ptr{Float32}, Ptr{Float32}, Ptr{UInt32}, UInt32, UInt32, Ref{UInt32}),
+        m.ptr, v, size(v, 2), meta === nothing ? C_NULL : meta, reinterpret(Float32, xf), reinterpret(Float32, inv), instance_ids === nothing ? C_NULL : UInt32.(instance_ids), length(xf), 0, h))
+    TLASHandle(h[])
+end
+sync!(m::CuMultiTLAS) = (mcheck(m, ccall((:rc_multi_sync, lib), Int32, (Ptr{Cvoid}, Ptr{Int32}), m.ptr, C_NULL)); m)
+"closest hits of `rays`, sharded over every device of the handle; identical to the single-device result"
+trace_closest_hits!(hits::Vector{RTHitResult}, rays::Vector{RTRay}, m::CuMultiTLAS; any = false, flags = UInt32(0)) =
+    (mcheck(m, ccall((any ? :rc_multi_trace_any : :rc_multi_trace_closest, lib), Int32, (Ptr{Cvoid}, Ptr{RTRay}, Ptr{RTHitResult}, UInt64, UInt32), m.ptr, rays, hits, length(rays), flags)); hits)
+function Raycore.view_factors(m::CuMultiTLAS; rays_per_triangle = 10000, seed = 0)
+    n = Ref{UInt32}(0); ccall((:rc_sizes, lib), Int32, (Ptr{Cvoid}, Ptr{UInt32}, Ptr{UInt32}, Ref{UInt32}, Ptr{UInt32}), ccall((:rc_multi_context, lib), Ptr{Cvoid}, (Ptr{Cvoid}, UInt32), m.ptr, 0), C_NULL, C_NULL, n, C_NULL)
+    out = zeros(UInt32, n[], n[]); sk = Ref{UInt64}(0)
+    mcheck(m, ccall((:rc_multi_view_factors, lib), Int32, (Ptr{Cvoid}, UInt32, UInt64, Ptr{UInt32}, Ref{UInt64}), m.ptr, rays_per_triangle, seed, out, sk))
+    permutedims(out)
 end
 
 # ---- analysis (src/kernels.jl) -----------------------------------------------------------------------------------------

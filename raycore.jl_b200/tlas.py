@@ -760,37 +760,80 @@ class BLAS4:
         v = np.ascontiguousarray(np.asarray(primitives, np.float32).reshape(-1, 9))
         if len(v) == 0:
             raise RaycoreError(L.RC_ERR_NO_VALID_TRIANGLES, "Cannot build BLAS4 from empty primitive list")  # src/bvh4.jl:513
-        self._tlas = TLAS(device)
-        self._handle = self._tlas.push(v, None, face_meta=face_meta)
-        self._tlas.sync()
+        self._lib = L.load()
+        fm = None if face_meta is None else np.ascontiguousarray(face_meta, np.uint32)
+        b = C.c_void_p()
+        rc = self._lib.rc_blas4_build(-1 if device is None else int(device), v.ctypes.data, len(v), None if fm is None else fm.ctypes.data, 0, C.byref(b))
+        if rc != L.RC_OK:
+            raise RaycoreError(rc, self._lib.rc_blas4_last_error(None).decode())
+        self._b, self._verts, self._faces = b, v, None
+
+    def _ck(self, rc):
+        if rc != L.RC_OK:
+            raise RaycoreError(rc, self._lib.rc_blas4_last_error(self._b).decode())
+
+    def _info(self):
+        n, slots, box = C.c_uint32(), C.c_uint32(), np.zeros(6, np.float32)
+        self._ck(self._lib.rc_blas4_info(self._b, C.byref(n), C.byref(slots), box.ctypes.data))
+        return n.value, slots.value, box
 
     @property
     def root_aabb(self) -> Bounds3:
-        return self._tlas.world_bound()
+        box = self._info()[2]
+        return Bounds3(box[:3].copy(), box[3:].copy())
 
     @property
     def n_primitives(self) -> int:
-        return self._tlas.sizes()["blas_prims"]
+        return self._info()[0]
 
-    def _rays(self, rays):
-        r = _as_rays(rays).copy()
-        r["t_min"] = 0.0
-        return r
+    def nodes(self) -> np.ndarray:
+        """the wide nodes (rc_wide_node records, slot 0 unused, root = slot 1)"""
+        out = np.zeros(self._info()[1], L.WIDE_NODE_DTYPE)
+        self._ck(self._lib.rc_blas4_read_nodes(self._b, out.ctypes.data, len(out)))
+        return out
 
-    def trace_closest4(self, rays) -> np.ndarray:
-        return self._tlas._trace(self._rays(rays), any_hit=False)
+    def _trace(self, rays, any_hit, watertight=False) -> np.ndarray:
+        rays = _as_rays(rays)
+        hits = np.zeros(len(rays), HIT_DTYPE)
+        fn = self._lib.rc_blas4_trace_any if any_hit else self._lib.rc_blas4_trace_closest
+        if len(rays):
+            self._ck(fn(self._b, rays.ctypes.data, hits.ctypes.data, len(rays), L.RC_MODE_WATERTIGHT if watertight else 0))
+        return hits
 
-    def trace_any4(self, rays) -> np.ndarray:
-        return self._tlas._trace(self._rays(rays), any_hit=True)
+    def trace_closest4(self, rays, **kw) -> np.ndarray:
+        return self._trace(rays, False, **kw)
+
+    def trace_any4(self, rays, **kw) -> np.ndarray:
+        return self._trace(rays, True, **kw)
+
+    def _tuple(self, h):
+        if not h["hit"]:
+            return False, empty_triangle(), np.float32(0), np.zeros(3, np.float32)
+        if self._faces is None:
+            n = self.n_primitives
+            self._faces = np.zeros(n, np.uint32)
+            rc = self._lib.rc_read_blas_faces(self._lib.rc_blas4_context(self._b), 1, self._faces.ctypes.data, n)
+            self._ck(rc)
+        u, v = np.float32(h["bary_u"]), np.float32(h["bary_v"])
+        tri = Triangle(self._verts[int(self._faces[int(h["primitive_id"])])].reshape(3, 3).copy(), np.uint32(h["meta"]))
+        return True, tri, np.float32(h["t"]), np.array([np.float32(1.0) - u - v, u, v], np.float32)
 
     def closest_hit4(self, ray: Ray):
-        return self._tlas._tuple_from_hit(self.trace_closest4([ray])[0], any_hit=False)[:4]
+        return self._tuple(self.trace_closest4([ray])[0])
 
     def any_hit4(self, ray: Ray):
-        return self._tlas._tuple_from_hit(self.trace_any4([ray])[0], any_hit=True)[:4]
+        return self._tuple(self.trace_any4([ray])[0])
 
     def free(self):
-        self._tlas.free()
+        if getattr(self, "_b", None):
+            self._lib.rc_blas4_destroy(self._b)
+            self._b = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 def build_blas4(primitives, face_meta=None, device: Optional[int] = None) -> BLAS4:
