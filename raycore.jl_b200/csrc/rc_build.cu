@@ -31,8 +31,9 @@ static inline uint32_t cdiv(uint64_t a, uint32_t b) { return (uint32_t)((a + b -
 // Control block of one build (u32 words, zeroed by one memset): the builder's kernels communicate through it.
 //   [CTL_N] valid primitives   [CTL_R2] bits of the bounding-sphere radius^2   [CTL_BOUNDS..+6) scene bounds, encoded so that 0 is the
 //   identity of atomicMax: word k < 3 holds ~ordered(min_k), word 3+k holds ordered(max_k)   [CTL_TILE] tile ticket of k_filter
+//   [CTL_NSPAN] length of the fit's spanning-node list
 //   [CTL_OUT..+10) floats read back by the host: root box (6), sphere (4)
-enum { CTL_N = 0, CTL_R2 = 1, CTL_BOUNDS = 2, CTL_TILE = 8, CTL_OUT = 16, CTL_WORDS = 32 };
+enum { CTL_N = 0, CTL_R2 = 1, CTL_BOUNDS = 2, CTL_TILE = 8, CTL_NSPAN = 10, CTL_OUT = 16, CTL_WORDS = 32 };
 
 __device__ __forceinline__ f3 ctl_bounds_min(const uint32_t *ctl) {
     return mk3(rc_ordered_to_float(~ctl[CTL_BOUNDS]), rc_ordered_to_float(~ctl[CTL_BOUNDS + 1]), rc_ordered_to_float(~ctl[CTL_BOUNDS + 2]));
@@ -321,26 +322,46 @@ __device__ __forceinline__ void bounds_atomic(uint32_t *ctl, f3 lo, f3 hi) {
 // exact degenerate test, stable compaction by a decoupled look-back scan over the 1024-face tiles (tile tickets are handed out in
 // arrival order, so a tile only ever waits for tiles that are already running), compacted RcTri records (prim_id = compacted slot),
 // scene bounds.  The last tile publishes the valid count.
-constexpr int FILTER_T = 1024;
+// Memory: the 36-byte faces of a tile are staged through shared memory with fully coalesced (16-byte when aligned) loads — a thread
+// reading its own 9 floats straight from global memory touches 9 x 36 sectors per warp —, and the 48-byte records leave through the
+// same buffer as one contiguous run of coalesced 16-byte stores (the valid faces of a tile are consecutive in the compacted array).
+constexpr int FILTER_T = 256;  // small tiles, many resident blocks: the phases of a tile (load, look-back, store) are barrier-separated and only overlap across blocks
+constexpr int FILTER_SMEM = FILTER_T * 48;  // bytes: the tile's records (>= the tile's 36-byte faces)
 __global__ void __launch_bounds__(FILTER_T) k_filter(const float *__restrict__ verts, const uint32_t *__restrict__ face_meta, uint32_t n_faces, RcTri *__restrict__ tris_in,
                                                      uint32_t *__restrict__ ctl, uint32_t *__restrict__ tile_state) {
+    __shared__ __align__(16) unsigned char filter_raw[FILTER_SMEM];
+    float *stage = reinterpret_cast<float *>(filter_raw);
     __shared__ uint32_t s_tile, s_warp[32], s_prefix, s_total;
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(&ctl[CTL_TILE], 1u);
     __syncthreads();
     const uint32_t tile = s_tile, i = tile * FILTER_T + tid;
+    const uint32_t faces_here = min((uint32_t)FILTER_T, n_faces - tile * FILTER_T);
+    {
+        const float *src = verts + (size_t)tile * FILTER_T * 9;
+        const uint32_t words = faces_here * 9u;
+        if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0u) {
+            const float4 *s4 = reinterpret_cast<const float4 *>(src);
+            float4 *d4 = reinterpret_cast<float4 *>(stage);
+            for (uint32_t k = tid; k < words / 4u; k += FILTER_T) d4[k] = __ldcs(s4 + k);  // read once
+            for (uint32_t k = (words & ~3u) + tid; k < words; k += FILTER_T) stage[k] = src[k];
+        } else {
+            for (uint32_t k = tid; k < words; k += FILTER_T) stage[k] = src[k];
+        }
+    }
+    __syncthreads();
     bool valid = false;
     f3 a = mk3(0, 0, 0), b = a, c = a;
     if (i < n_faces) {
-        const float *v = verts + (size_t)i * 9;
+        const float *v = stage + tid * 9u;  // stride 9 words: conflict-free
         a = ld3(v); b = ld3(v + 3); c = ld3(v + 6);
         valid = !x_is_degenerate(a, b, c);
     }
     const uint32_t bal = __ballot_sync(0xFFFFFFFFu, valid);
     if (lane == 0) s_warp[wid] = __popc(bal);
-    __syncthreads();
+    __syncthreads();  // (also: every thread has read its face, the staging buffer can take the records)
     if (wid == 0) {
-        const uint32_t cnt = s_warp[lane], inc = warp_incl_scan(cnt);
+        const uint32_t cnt = lane < FILTER_T / 32 ? s_warp[lane] : 0u, inc = warp_incl_scan(cnt);
         s_warp[lane] = inc - cnt;
         const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 31);
         // look back: state word = flag << 30 | count, flag 1 = this tile's own count, 2 = inclusive prefix up to and including the tile
@@ -368,18 +389,23 @@ __global__ void __launch_bounds__(FILTER_T) k_filter(const float *__restrict__ v
             s_total = total;
         }
     }
-    __syncthreads();
     f3 lo = mk3(INFINITY, INFINITY, INFINITY), hi = mk3(-INFINITY, -INFINITY, -INFINITY);
+    __syncthreads();
     if (valid) {
-        const uint32_t k = s_prefix + s_warp[wid] + __popc(bal & ((1u << lane) - 1u));
-        float4 *d = reinterpret_cast<float4 *>(tris_in + k);
+        const uint32_t r = s_warp[wid] + __popc(bal & ((1u << lane) - 1u)), k = s_prefix + r;  // rank in the tile, compacted slot
+        float4 *d = reinterpret_cast<float4 *>(stage) + 3u * r;
         d[0] = make_float4(a.x, a.y, a.z, __uint_as_float(k));
         d[1] = make_float4(b.x, b.y, b.z, __uint_as_float(face_meta ? face_meta[i] : i + 1u));  // :595
         d[2] = make_float4(c.x, c.y, c.z, __uint_as_float(i));
         lo = jl_min3(jl_min3(a, b), c);  // world_bound(tri), triangle_mesh.jl:37
         hi = jl_max3(jl_max3(a, b), c);
     }
-    bounds_atomic(ctl, lo, hi);
+    bounds_atomic(ctl, lo, hi);  // (contains a __syncthreads: the records are complete)
+    {
+        const float4 *s4 = reinterpret_cast<const float4 *>(stage);
+        float4 *d4 = reinterpret_cast<float4 *>(tris_in + s_prefix);
+        for (uint32_t k = tid; k < 3u * s_total; k += FILTER_T) d4[k] = s4[k];
+    }
     if (tid == 0 && tile == gridDim.x - 1) ctl[CTL_N] = s_prefix + s_total;
 }
 
@@ -422,28 +448,18 @@ __global__ void __launch_bounds__(RS_THREADS) k_morton_prims(const RcTri *__rest
 // =================================================================================================
 // Topology, fit, BVH2 emission, collapse (shared by BLAS and TLAS)
 // =================================================================================================
-__global__ void k_topology(const uint32_t *__restrict__ codes, const uint32_t *__restrict__ n_ptr, uint32_t n_host, RcTopo *__restrict__ topo, uint32_t *__restrict__ parent,
-                           uint32_t *__restrict__ flags) {
+__global__ void k_topology(const uint32_t *__restrict__ codes, const uint32_t *__restrict__ n_ptr, uint32_t n_host, RcTopo *__restrict__ topo, uint32_t *__restrict__ parent) {
     const uint32_t n = count_of(n_ptr, n_host);
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // internal node i+1
     if (n == 1 && i == 0) parent[0] = RC_INVALID;  // single leaf: no internal node, the leaf's parent is INVALID
     if (i + 1 >= n) return;
     RcTopo t = rc_topology_for_node((int)(i + 1), codes, (int)n);
     topo[i] = t;
-    flags[i] = 0;  // arrival counter of the fit
     parent[t.child0 - 1] = i + 1;  // set_parents_for_node, kernels.jl:159-180
     parent[t.child1 - 1] = i + 1;
     if (i == 0) parent[0] = RC_INVALID;
 }
 
-__device__ __forceinline__ RcBox ld_box_cg(const RcBox *p) {
-    const float4 *q = reinterpret_cast<const float4 *>(p);
-    float4 a = __ldcg(q), b = __ldcg(q + 1);
-    RcBox r;
-    r.lo[0] = a.x; r.lo[1] = a.y; r.lo[2] = a.z; r.pad0 = 0;
-    r.hi[0] = b.x; r.hi[1] = b.y; r.hi[2] = b.z; r.pad1 = 0;
-    return r;
-}
 __device__ __forceinline__ void st_box(RcBox *p, f3 lo, f3 hi) {
     float4 *q = reinterpret_cast<float4 *>(p);
     q[0] = make_float4(lo.x, lo.y, lo.z, 0.f);
@@ -456,27 +472,85 @@ __device__ __forceinline__ void st_node2(RcNode2 *p, f3 a0n, f3 a0x, f3 a1n, f3 
     q[2] = make_float4(a1n.z, a1x.x, a1x.y, a1x.z);
     q[3] = make_float4(__uint_as_float(c0), __uint_as_float(c1), __uint_as_float(par), 0.f);
 }
+__device__ __forceinline__ void st_node4(RcNode4 *p, const RcNode4 &nd) {
+    const float4 *s = reinterpret_cast<const float4 *>(&nd);
+    float4 *d = reinterpret_cast<float4 *>(p);
+    d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3];
+}
+__device__ __forceinline__ void st_node4_zero(RcNode4 *p) {
+    float4 *d = reinterpret_cast<float4 *>(p);
+    d[0] = d[1] = d[2] = d[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
 
-// Bottom-up fit (refit_aabbs_kernel!, kernels.jl:239-286 / :381-428): one thread per leaf writes the leaf's box and climbs; the
-// second arriver at an internal node computes it.  A block owns FIT_T consecutive leaves, and every internal node whose span lies
-// inside that range (all but ~2 n / FIT_T of them) is fitted through shared memory — arrival counters, boxes, topology and parent
-// links of the range are staged there, so a level of the climb costs shared-memory latency instead of an L2 round trip and a
-// device-scope fence.  Only the nodes spanning several blocks use the global protocol (box in global memory, release-ordered
-// counter bump, children read back with ld.cg).  1 M triangles: 154 us -> see profiles/README.md r2.
+// Bottom-up fit (refit_aabbs_kernel!, kernels.jl:239-286 / :381-428) without a dependency chain through global memory.
+//
+// A block of k_fit_local owns FIT_T consecutive sorted leaves and the internal nodes of the same numbers.  Every internal node whose
+// span lies inside that range (all but a few per block) is fitted in shared memory — arrival counters, boxes, topology and parent
+// links of the range are staged there — and collapsed into its wide node from the same shared-memory copies, so the boxes and the
+// topology are not read back from global memory at all.  The climb of a thread ends at the first ancestor that reaches beyond the
+// block; the subtree it finished is one of the block's maximal in-block subtrees ("segments").  The segments hang off the two root
+// paths that end at the block's boundaries, so there are at most 2 x 64 of them (the common-prefix length, 0..63, grows along a path
+// of the radix tree).  The block stores, for every segment, the union of the leaf boxes from its first leaf to the end of the block
+// (sfx) and from the start of the block to its last leaf (pfx).
+//
+// A node that spans several blocks ("spanning node") starts at a segment start and ends at a segment end, hence
+//     box(node) = sfx[first leaf] u (whole blocks in between) u pfx[last leaf]
+// and k_fit_span evaluates that with one warp per spanning node and no ordering between nodes: min / max are exact and the
+// reference's min / max (NaN-propagating, -0 < +0) are associative and commutative on the GPU (canonical NaN), so the union over
+// the leaves gives the bits the pairwise climb gives.  (The round-1 kernel climbed the spanning levels with a release-ordered
+// atomic + ld.cg per level: ~25 dependent L2 round trips on the critical path of every block, 184 us for 1 M triangles.)
 //   BLAS build (tris_in != null): sorted triangle p = tris_in[perm[p]] is gathered here and written to tris; leaf box = its bounds;
 //                                 leaf node = (v0,v1,v2,0 | INVALID, p+1, parent); the bounding-sphere radius is reduced on the way
 //   BLAS refit (tris_in == null, tris != null): the triangles are already in place
 //   TLAS (tris == null): leaf box = inst_boxes[leaf_map[p]], leaf node = (lo,hi,0,0 | INVALID, inst, parent)
-constexpr int FIT_T = 1024;
+#ifndef RC_FIT_T
+#define RC_FIT_T 512
+#endif
+constexpr int FIT_T = RC_FIT_T;  // 48 registers x 512 threads: two blocks per SM, so one block's barriers and gather latency overlap the other's work
+constexpr int FIT_SEG_MAX = 128;
+struct FitSeg {  // 64 B; the table of a block is sorted by position, entry 0 starts at the block's first leaf (its sfx = the whole block)
+    uint32_t s, e, count, overflow;
+    float sfx[6], pfx[6];
+};
+static_assert(sizeof(FitSeg) == 64, "segment table entry");
+struct FitWork {  // per-fit scratch: segment tables [blocks][FIT_SEG_MAX], spanning-node list [blocks * FIT_SEG_MAX], its length
+    FitSeg *seg;
+    uint32_t *span_list;
+    uint32_t *span_count;
+};
+static size_t fit_work_bytes(uint32_t n_bound) {
+    const size_t blocks = cdiv(n_bound, FIT_T);
+    return blocks * FIT_SEG_MAX * (sizeof(FitSeg) + sizeof(uint32_t)) + 64;
+}
+static FitWork fit_work_at(void *base, uint32_t n_bound) {
+    const size_t blocks = cdiv(n_bound, FIT_T);
+    FitWork w;
+    w.seg = reinterpret_cast<FitSeg *>(base);
+    w.span_list = reinterpret_cast<uint32_t *>(w.seg + blocks * FIT_SEG_MAX);
+    w.span_count = w.span_list + blocks * FIT_SEG_MAX;
+    return w;
+}
 struct FitSmem {
     RcTopo topo[FIT_T];
     uint32_t par_int[FIT_T], par_leaf[FIT_T], flag[FIT_T];
     float box_int[FIT_T][6], box_leaf[FIT_T][6];
+    uint32_t seg_s[FIT_SEG_MAX], seg_e[FIT_SEG_MAX];
+    float seg_box[FIT_SEG_MAX][6];
+    uint32_t nseg;
 };
-__global__ void __launch_bounds__(FIT_T) k_fit(const RcTri *__restrict__ tris_in, const uint32_t *__restrict__ perm, RcTri *__restrict__ tris,
-                                               const RcBox *__restrict__ inst_boxes, const uint32_t *__restrict__ leaf_map, const uint32_t *__restrict__ n_ptr, uint32_t n_host,
-                                               const RcTopo *__restrict__ topo, const uint32_t *__restrict__ parent, uint32_t *__restrict__ flags, RcBox *__restrict__ boxes,
-                                               RcNode2 *__restrict__ nodes2, uint32_t *__restrict__ ctl) {
+__device__ __forceinline__ RcBox box_from6(const float *b) {
+    RcBox r;
+    r.lo[0] = b[0]; r.lo[1] = b[1]; r.lo[2] = b[2]; r.pad0 = 0.f;
+    r.hi[0] = b[3]; r.hi[1] = b[4]; r.hi[2] = b[5]; r.pad1 = 0.f;
+    return r;
+}
+// build_list: append this block's spanning nodes to work.span_list (skipped when a list of the same topology is already there)
+// nodes4 != null: collapse the in-block nodes into their wide nodes here (leaf_max, leaf_map as in rc_collapse_node)
+__global__ void __launch_bounds__(FIT_T) k_fit_local(const RcTri *__restrict__ tris_in, const uint32_t *__restrict__ perm, RcTri *__restrict__ tris,
+                                                     const RcBox *__restrict__ inst_boxes, const uint32_t *__restrict__ leaf_map, const uint32_t *__restrict__ n_ptr,
+                                                     uint32_t n_host, const RcTopo *__restrict__ topo, const uint32_t *__restrict__ parent, RcBox *__restrict__ boxes,
+                                                     RcNode2 *__restrict__ nodes2, uint32_t *__restrict__ ctl, FitWork work, bool build_list, RcNode4 *__restrict__ nodes4,
+                                                     uint32_t leaf_max) {
     extern __shared__ __align__(16) unsigned char fit_raw[];
     FitSmem &S = *reinterpret_cast<FitSmem *>(fit_raw);
     const uint32_t n = count_of(n_ptr, n_host);
@@ -485,20 +559,23 @@ __global__ void __launch_bounds__(FIT_T) k_fit(const RcTri *__restrict__ tris_in
     if (blk_lo > n) return;
     const uint32_t blk_hi = min(blk_lo + FIT_T - 1u, n);
     const uint32_t p1 = blk_lo + tid;  // this thread's primitive (1-based) and the internal node number it stages
-    if (p1 <= blk_hi) {
-        if (p1 < n) {
+    const bool has_leaf = p1 <= blk_hi, has_node = p1 <= blk_hi && p1 < n;
+    if (has_leaf) {
+        if (has_node) {
             S.topo[tid] = topo[p1 - 1];
             S.par_int[tid] = parent[p1 - 1];
         }
         S.par_leaf[tid] = parent[n - 1 + p1 - 1];
         S.flag[tid] = 0;
     }
+    if (tid == 0) S.nseg = 0;
     __syncthreads();
     float r2 = 0.0f;
-    if (p1 <= blk_hi) {
+    uint32_t node = RC_INVALID, cs = p1, ce = p1;  // parent of / span of the subtree this thread has finished
+    f3 lo = mk3(0, 0, 0), hi = lo;
+    if (has_leaf) {
         const uint32_t p = p1 - 1, leaf = n - 1 + p1;
-        uint32_t node = S.par_leaf[tid];
-        f3 lo, hi;
+        node = S.par_leaf[tid];
         if (tris) {
             float4 a, b, c;
             if (tris_in) {
@@ -527,147 +604,287 @@ __global__ void __launch_bounds__(FIT_T) k_fit(const RcTri *__restrict__ tris_in
         st_box(boxes + (leaf - 1), lo, hi);
         S.box_leaf[tid][0] = lo.x; S.box_leaf[tid][1] = lo.y; S.box_leaf[tid][2] = lo.z;
         S.box_leaf[tid][3] = hi.x; S.box_leaf[tid][4] = hi.y; S.box_leaf[tid][5] = hi.z;
-        bool global_phase = false;
-        while (node != RC_INVALID) {
+    }
+    __syncthreads();
+    // The climb, one level per round with a block barrier between rounds: a thread that holds a finished subtree counts its arrival at the
+    // parent; the second arriver — both children's boxes were stored in earlier rounds — fits the parent and carries on.  (Barrier-
+    // ordered: no fences, clean under racecheck; a 1024-leaf range of a Morton-ordered tree is 12-20 levels deep.)
+    bool active = has_leaf;
+    for (;;) {
+        if (active) {
             bool local = false;
-            if (!global_phase && node >= blk_lo && node <= blk_hi) {
+            if (node != RC_INVALID && node >= blk_lo && node <= blk_hi) {
                 const RcTopo &tp = S.topo[node - blk_lo];
                 local = tp.span_lo >= blk_lo && tp.span_hi <= blk_hi;
             }
-            f3 l0, h0, l1, h1;
-            uint32_t c0, c1, up;
-            if (local) {
-                const uint32_t s = node - blk_lo;
-                __threadfence_block();  // the box written to shared memory above is visible before the arrival is counted
-                if (atomicAdd(&S.flag[s], 1u) == 0u) break;  // first arriver: the sibling subtree is not ready
-                c0 = S.topo[s].child0; c1 = S.topo[s].child1; up = S.par_int[s];
-                const float *b0 = c0 >= n ? S.box_leaf[c0 - (n - 1) - blk_lo] : S.box_int[c0 - blk_lo];
-                const float *b1 = c1 >= n ? S.box_leaf[c1 - (n - 1) - blk_lo] : S.box_int[c1 - blk_lo];
-                l0 = mk3(b0[0], b0[1], b0[2]); h0 = mk3(b0[3], b0[4], b0[5]);
-                l1 = mk3(b1[0], b1[1], b1[2]); h1 = mk3(b1[3], b1[4], b1[5]);
+            if (!local) {  // the parent reaches beyond the block (or there is none): [cs, ce] is a segment
+                const uint32_t k = atomicAdd(&S.nseg, 1u);
+                if (k < (uint32_t)FIT_SEG_MAX) {
+                    S.seg_s[k] = cs; S.seg_e[k] = ce;
+                    S.seg_box[k][0] = lo.x; S.seg_box[k][1] = lo.y; S.seg_box[k][2] = lo.z;
+                    S.seg_box[k][3] = hi.x; S.seg_box[k][4] = hi.y; S.seg_box[k][5] = hi.z;
+                }
+                active = false;
             } else {
-                global_phase = true;  // every ancestor of a node that spans several blocks does too
-                if (atom_add_release(&flags[node - 1], 1u) == 0u) break;
-                const RcTopo tp = topo[node - 1];
-                c0 = tp.child0; c1 = tp.child1; up = parent[node - 1];
-                const RcBox b0 = ld_box_cg(boxes + (c0 - 1)), b1 = ld_box_cg(boxes + (c1 - 1));
-                l0 = mk3(b0.lo[0], b0.lo[1], b0.lo[2]); h0 = mk3(b0.hi[0], b0.hi[1], b0.hi[2]);
-                l1 = mk3(b1.lo[0], b1.lo[1], b1.lo[2]); h1 = mk3(b1.hi[0], b1.hi[1], b1.hi[2]);
+                const uint32_t s = node - blk_lo;
+                if (atomicAdd(&S.flag[s], 1u) == 0u) active = false;  // first arriver: the sibling subtree is not ready
             }
+        }
+        if (active) {  // second arriver: both children's boxes were stored before the last barrier
+            const uint32_t s = node - blk_lo;
+            const uint32_t c0 = S.topo[s].child0, c1 = S.topo[s].child1, up = S.par_int[s];
+            const float *b0 = c0 >= n ? S.box_leaf[c0 - (n - 1) - blk_lo] : S.box_int[c0 - blk_lo];
+            const float *b1 = c1 >= n ? S.box_leaf[c1 - (n - 1) - blk_lo] : S.box_int[c1 - blk_lo];
+            const f3 l0 = mk3(b0[0], b0[1], b0[2]), h0 = mk3(b0[3], b0[4], b0[5]);
+            const f3 l1 = mk3(b1[0], b1[1], b1[2]), h1 = mk3(b1[3], b1[4], b1[5]);
             lo = jl_min3(l0, l1);  // get_node_aabb interior branch, :1142-1147
             hi = jl_max3(h0, h1);
             if (nodes2) st_node2(nodes2 + (node - 1), l0, h0, l1, h1, c0, c1, up);
             st_box(boxes + (node - 1), lo, hi);
-            if (local) {
-                float *bi = S.box_int[node - blk_lo];
-                bi[0] = lo.x; bi[1] = lo.y; bi[2] = lo.z; bi[3] = hi.x; bi[4] = hi.y; bi[5] = hi.z;
-            }
+            float *bi = S.box_int[s];
+            bi[0] = lo.x; bi[1] = lo.y; bi[2] = lo.z; bi[3] = hi.x; bi[4] = hi.y; bi[5] = hi.z;
+            cs = S.topo[s].span_lo; ce = S.topo[s].span_hi;
             node = up;
         }
+        if (!__syncthreads_or(active)) break;
     }
-    if (tris) {  // bits of a non-negative float order like the float: one atomicMax per warp that still has lanes here
-        const uint32_t m = __reduce_max_sync(__activemask(), __float_as_uint(r2));
-        if ((tid & 31u) == (uint32_t)(__ffs(__activemask()) - 1)) atomicMax(&ctl[CTL_R2], m);
+    if (tris) {  // bits of a non-negative float order like the float: one atomicMax per warp (lanes without a leaf carry 0)
+        const uint32_t m = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(r2));
+        if ((tid & 31u) == 0u) atomicMax(&ctl[CTL_R2], m);
+    }
+    __syncthreads();
+    // ---- segment table: position-sorted entries with the suffix / prefix unions of the block's segments
+    const uint32_t m_all = S.nseg, m = min(m_all, (uint32_t)FIT_SEG_MAX);
+    if (tid < m) {
+        const uint32_t sj = S.seg_s[tid], ej = S.seg_e[tid];
+        uint32_t rank = 0;
+        f3 slo = mk3(INFINITY, INFINITY, INFINITY), shi = mk3(-INFINITY, -INFINITY, -INFINITY), plo = slo, phi = shi;
+        for (uint32_t k = 0; k < m; k++) {
+            const uint32_t sk = S.seg_s[k];
+            const f3 kl = mk3(S.seg_box[k][0], S.seg_box[k][1], S.seg_box[k][2]), kh = mk3(S.seg_box[k][3], S.seg_box[k][4], S.seg_box[k][5]);
+            rank += sk < sj ? 1u : 0u;
+            if (sk >= sj) { slo = jl_min3(slo, kl); shi = jl_max3(shi, kh); }
+            if (sk <= sj) { plo = jl_min3(plo, kl); phi = jl_max3(phi, kh); }
+        }
+        FitSeg e;
+        e.s = sj; e.e = ej; e.count = m; e.overflow = m_all > (uint32_t)FIT_SEG_MAX ? 1u : 0u;
+        e.sfx[0] = slo.x; e.sfx[1] = slo.y; e.sfx[2] = slo.z; e.sfx[3] = shi.x; e.sfx[4] = shi.y; e.sfx[5] = shi.z;
+        e.pfx[0] = plo.x; e.pfx[1] = plo.y; e.pfx[2] = plo.z; e.pfx[3] = phi.x; e.pfx[4] = phi.y; e.pfx[5] = phi.z;
+        const float4 *src = reinterpret_cast<const float4 *>(&e);
+        float4 *dst = reinterpret_cast<float4 *>(work.seg + (size_t)blockIdx.x * FIT_SEG_MAX + rank);
+        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+    }
+    // ---- this block's internal nodes: spanning ones go to the list, the others are collapsed from shared memory
+    bool spanning = false;
+    RcTopo tp = {0, 0, 0, 0};
+    if (has_node) {
+        tp = S.topo[tid];
+        spanning = tp.span_lo < blk_lo || tp.span_hi > blk_hi;
+    }
+    if (build_list) {
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, spanning);
+        uint32_t base = 0;
+        if ((tid & 31u) == 0u && bal) base = atomicAdd(work.span_count, (uint32_t)__popc(bal));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (spanning) work.span_list[base + __popc(bal & ((1u << (tid & 31u)) - 1u))] = p1;
+    }
+    if (nodes4) {
+        // a third of the nodes head no wide node: the others are compacted into a dense list first, so the (long) collapse runs with full warps
+        const bool own = has_node && !spanning;
+        const bool skip = own && p1 > 1u && tp.span_hi - tp.span_lo + 1u <= leaf_max;  // never the head of a wide node: the slot stays empty (zeroed: exported blobs are deterministic)
+        if (skip) st_node4_zero(nodes4 + p1);
+        const uint32_t lane = tid & 31u, wid = tid >> 5;
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, own && !skip);
+        uint32_t *list = S.flag, *woff = S.par_leaf;  // the arrival counters and the leaves' parent links are dead since the climb's last barrier
+        if (lane == 0) woff[wid] = __popc(bal);
+        __syncthreads();
+        if (wid == 0) {
+            const uint32_t c = lane < FIT_T / 32 ? woff[lane] : 0u, inc = warp_incl_scan(c);
+            woff[lane] = inc - c;
+            if (lane == 31) woff[32] = inc;
+        }
+        __syncthreads();
+        if (own && !skip) list[woff[wid] + __popc(bal & ((1u << lane) - 1u))] = p1;
+        __syncthreads();
+        if (tid < woff[32]) {
+            const uint32_t v = list[tid];
+            const RcNode4 nd = rc_collapse_node_t(
+                v, [&](uint32_t c) -> RcBox { return box_from6(c >= n ? S.box_leaf[c - (n - 1) - blk_lo] : S.box_int[c - blk_lo]); },
+                [&](uint32_t c) -> RcTopo { return S.topo[c - blk_lo]; }, n, leaf_max, leaf_map);
+            st_node4(nodes4 + v, nd);
+        }
     }
 }
 
-// BVH2 subtree -> wide node, one thread per BVH2 internal node.  A node that covers <= leaf_max primitives can never be the root
-// of a wide node (its parent turns it into a leaf reference), so it is skipped (about a third of the internal nodes at leaf_max 2).
-// One extra block computes the hull (hull != null): the RC_HULL_BOXES subtrees four levels below the root — together they cover the
-// whole BLAS — give the instance bounds of the wide TLAS (union of the transformed hull boxes).
-__global__ void k_collapse(const RcBox *__restrict__ boxes, const RcTopo *__restrict__ topo, const uint32_t *__restrict__ n_ptr, uint32_t n_host, uint32_t leaf_max,
-                           const uint32_t *__restrict__ leaf_map, RcNode4 *__restrict__ nodes4, RcBox *__restrict__ hull) {
+// union of the leaf boxes of sorted positions [a, b] (1-based), which lie in different blocks, a at a segment start and b at a segment
+// end of their blocks; warp-cooperative, every lane returns the result
+__device__ __forceinline__ void fit_range_box(const FitSeg *__restrict__ seg, uint32_t a, uint32_t b, f3 &lo, f3 &hi) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t bA = (a - 1u) / FIT_T, bB = (b - 1u) / FIT_T;
+    const FitSeg *tA = seg + (size_t)bA * FIT_SEG_MAX, *tB = seg + (size_t)bB * FIT_SEG_MAX;
+    const uint32_t mA = tA[0].count, mB = tB[0].count;
+    uint32_t ia = 0xFFFFFFFFu, ib = 0xFFFFFFFFu;
+#pragma unroll
+    for (uint32_t q = 0; q < FIT_SEG_MAX / 32; q++) {
+        const uint32_t j = q * 32u + lane;
+        if (j < mA && tA[j].s == a) ia = j;
+        if (j < mB && tB[j].e == b) ib = j;
+    }
+    ia = __reduce_min_sync(0xFFFFFFFFu, ia);
+    ib = __reduce_min_sync(0xFFFFFFFFu, ib);
+    lo = mk3(INFINITY, INFINITY, INFINITY);
+    hi = mk3(-INFINITY, -INFINITY, -INFINITY);
+    if (bB > bA + 1u) {  // whole blocks in between: lane-strided, then a butterfly
+        for (uint32_t k = bA + 1u + lane; k < bB; k += 32u) {
+            const float *x = seg[(size_t)k * FIT_SEG_MAX].sfx;
+            lo = jl_min3(lo, mk3(x[0], x[1], x[2]));
+            hi = jl_max3(hi, mk3(x[3], x[4], x[5]));
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const f3 ol = mk3(__shfl_xor_sync(0xFFFFFFFFu, lo.x, d), __shfl_xor_sync(0xFFFFFFFFu, lo.y, d), __shfl_xor_sync(0xFFFFFFFFu, lo.z, d));
+            const f3 oh = mk3(__shfl_xor_sync(0xFFFFFFFFu, hi.x, d), __shfl_xor_sync(0xFFFFFFFFu, hi.y, d), __shfl_xor_sync(0xFFFFFFFFu, hi.z, d));
+            lo = jl_min3(lo, ol);
+            hi = jl_max3(hi, oh);
+        }
+    }
+    if (ia != 0xFFFFFFFFu && ib != 0xFFFFFFFFu) {
+        const float *x = tA[ia].sfx, *y = tB[ib].pfx;
+        lo = jl_min3(jl_min3(lo, mk3(x[0], x[1], x[2])), mk3(y[0], y[1], y[2]));
+        hi = jl_max3(jl_max3(hi, mk3(x[3], x[4], x[5])), mk3(y[3], y[4], y[5]));
+    } else {  // cannot happen for a radix tree (see k_fit_local); poison the box so that a broken invariant is loud, not subtle
+        lo = hi = mk3(__int_as_float(0x7FFFFFFF), __int_as_float(0x7FFFFFFF), __int_as_float(0x7FFFFFFF));
+    }
+}
+__device__ __forceinline__ bool fit_is_spanning(const RcTopo &t) { return (t.span_lo - 1u) / FIT_T != (t.span_hi - 1u) / FIT_T; }
+
+// boxes (and BVH2 records) of the spanning nodes: one warp per node, no ordering between nodes
+__global__ void __launch_bounds__(256) k_fit_span(const uint32_t *__restrict__ n_ptr, uint32_t n_host, const RcTopo *__restrict__ topo, const uint32_t *__restrict__ parent,
+                                                  RcBox *__restrict__ boxes, RcNode2 *__restrict__ nodes2, FitWork work) {
+    const uint32_t n = count_of(n_ptr, n_host);
+    const uint32_t count = *work.span_count, lane = threadIdx.x & 31u;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < count; w += warps) {
+        const uint32_t v = work.span_list[w];
+        const RcTopo tp = topo[v - 1];
+        f3 lo, hi;
+        fit_range_box(work.seg, tp.span_lo, tp.span_hi, lo, hi);
+        if (lane == 0) st_box(boxes + (v - 1), lo, hi);
+        if (nodes2) {  // the BVH2 record holds the children's boxes: a spanning child's box comes from the same formula
+            f3 cl[2], ch[2];
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const uint32_t c = k == 0 ? tp.child0 : tp.child1;
+                bool span_c = false;
+                RcTopo tc = {0, 0, 0, 0};
+                if (c < n) { tc = topo[c - 1]; span_c = fit_is_spanning(tc); }
+                if (span_c) {
+                    fit_range_box(work.seg, tc.span_lo, tc.span_hi, cl[k], ch[k]);
+                } else {  // written by k_fit_local (an earlier launch)
+                    const RcBox b = boxes[c - 1];
+                    cl[k] = mk3(b.lo[0], b.lo[1], b.lo[2]);
+                    ch[k] = mk3(b.hi[0], b.hi[1], b.hi[2]);
+                }
+            }
+            if (lane == 0) st_node2(nodes2 + (v - 1), cl[0], ch[0], cl[1], ch[1], tp.child0, tp.child1, parent[v - 1]);
+        }
+    }
+}
+
+// Wide nodes of the spanning BVH2 nodes (global arrays; the in-block ones were collapsed by k_fit_local), one thread per node.  A BVH2
+// node covering <= leaf_max primitives can never be the root of a wide node (its parent turns it into a leaf reference): zeroed.
+// The last block finishes the build:
+//   hull (hull != null): the RC_HULL_BOXES subtrees four levels below the root — together they cover the whole BLAS — give the instance
+//     bounds of the wide TLAS (union of the transformed hull boxes);
+//   n == 1: the synthetic root over the single leaf;  the two wide-node slots nothing else writes (0, and n) are zeroed;
+//   out10 (nullable): root box (6 floats); with ctl also the bounding sphere of a BLAS (centre of the scene bounds, radius^2 inflated
+//     against the rounding of its own evaluation), next to the valid count, so the host reads everything back in one transfer.
+__global__ void __launch_bounds__(256) k_collapse_span(const RcBox *__restrict__ boxes, const RcTopo *__restrict__ topo, const uint32_t *__restrict__ n_ptr, uint32_t n_host,
+                                                       uint32_t leaf_max, const uint32_t *__restrict__ leaf_map, RcNode4 *__restrict__ nodes4, RcBox *__restrict__ hull,
+                                                       FitWork work, float *__restrict__ out10, const uint32_t *__restrict__ ctl, const RcBox *__restrict__ root_boxes) {
     const uint32_t n = count_of(n_ptr, n_host);
     if (n == 0) return;
-    if (hull && blockIdx.x == gridDim.x - 1) {
+    if (blockIdx.x == gridDim.x - 1) {
         const uint32_t k = threadIdx.x;
-        if (k >= RC_HULL_BOXES) return;
-        uint32_t node = 1;
+        if (hull && k < RC_HULL_BOXES) {
+            uint32_t node = 1;
 #pragma unroll
-        for (int l = 3; l >= 0; l--) {
-            if (node >= n) break;  // a leaf (or the single-leaf tree): stays
-            const RcTopo tp = topo[node - 1];
-            node = (k >> l) & 1u ? tp.child1 : tp.child0;
+            for (int l = 3; l >= 0; l--) {
+                if (node >= n) break;  // a leaf (or the single-leaf tree): stays
+                const RcTopo tp = topo[node - 1];
+                node = (k >> l) & 1u ? tp.child1 : tp.child0;
+            }
+            hull[k] = n == 1 ? boxes[0] : boxes[node - 1];
         }
-        hull[k] = n == 1 ? boxes[0] : boxes[node - 1];
+        if (nodes4) {
+            if (k == 32 && n == 1) st_node4(nodes4 + 1, rc_collapse_node(1, boxes, topo, n, leaf_max, leaf_map));
+            if (k == 33) st_node4_zero(nodes4);
+            if (k == 34 && n > 1) st_node4_zero(nodes4 + n);
+        }
+        if (out10) {
+            const RcBox *rb = root_boxes ? root_boxes : boxes;
+            if (k >= 64 && k < 67) out10[k - 64] = rb[0].lo[k - 64];
+            else if (k >= 67 && k < 70) out10[k - 64] = rb[0].hi[k - 67];
+            else if (ctl && k >= 70 && k < 73) {
+                const int a = k - 70;
+                const f3 smin = ctl_bounds_min(ctl), smax = ctl_bounds_max(ctl);
+                const float lo = a == 0 ? smin.x : (a == 1 ? smin.y : smin.z), hi = a == 0 ? smax.x : (a == 1 ? smax.y : smax.z);
+                out10[6 + a] = 0.5f * (lo + hi);
+            } else if (ctl && k == 73) {
+                out10[9] = __uint_as_float(ctl[CTL_R2]) * 1.000002f;
+            }
+        }
         return;
     }
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // node i+1
-    uint32_t n_int = n > 1 ? n - 1 : 1;                   // n == 1: synthetic root over the single leaf
-    if (i >= n_int) return;
-    if (i > 0 && n > 1) {
-        const RcTopo tp = topo[i];
-        if (tp.span_hi - tp.span_lo + 1u <= leaf_max) {  // never the head of a wide node: the slot stays empty (zeroed: exported blobs are deterministic)
-            float4 *d = reinterpret_cast<float4 *>(nodes4 + (i + 1));
-            d[0] = d[1] = d[2] = d[3] = make_float4(0.f, 0.f, 0.f, 0.f);
-            return;
-        }
-    }
-    RcNode4 nd = rc_collapse_node(i + 1, boxes, topo, n, leaf_max, leaf_map);
-    const float4 *s = reinterpret_cast<const float4 *>(&nd);
-    float4 *d = reinterpret_cast<float4 *>(nodes4 + (i + 1));
-    d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3];
-}
-
-// root box -> out6; BLAS builds also finish the bounding sphere (centre of the scene bounds, radius^2 inflated against the rounding
-// of its own evaluation) and copy the valid count next to it, so the host reads everything back in one transfer
-__global__ void k_finish(const RcBox *__restrict__ boxes, float *__restrict__ out6, uint32_t *__restrict__ ctl, RcNode4 *__restrict__ nodes4 = nullptr) {
-    if (ctl && ctl[CTL_N] == 0) return;
-    if (nodes4 && threadIdx.x >= 16 && threadIdx.x < 24) {  // the two wide-node slots no kernel writes (0, and n when there are internal nodes)
-        const uint32_t n = ctl[CTL_N], k = threadIdx.x - 16;
-        reinterpret_cast<float4 *>(nodes4)[k & 3u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (n > 1 && k >= 4) reinterpret_cast<float4 *>(nodes4 + n)[k & 3u] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    if (threadIdx.x < 3) out6[threadIdx.x] = boxes[0].lo[threadIdx.x];
-    else if (threadIdx.x < 6) out6[threadIdx.x] = boxes[0].hi[threadIdx.x - 3];
-    else if (ctl && threadIdx.x < 9) {
-        const int k = threadIdx.x - 6;
-        const f3 smin = ctl_bounds_min(ctl), smax = ctl_bounds_max(ctl);
-        const float lo = k == 0 ? smin.x : (k == 1 ? smin.y : smin.z), hi = k == 0 ? smax.x : (k == 1 ? smax.y : smax.z);
-        out6[6 + k] = 0.5f * (lo + hi);
-    } else if (ctl && threadIdx.x == 9) {
-        out6[9] = __uint_as_float(ctl[CTL_R2]) * 1.000002f;
+    if (!nodes4) return;
+    const uint32_t count = *work.span_count, threads = (gridDim.x - 1) * blockDim.x;
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < count; w += threads) {
+        const uint32_t v = work.span_list[w];
+        const RcTopo tp = topo[v - 1];
+        if (v > 1u && tp.span_hi - tp.span_lo + 1u <= leaf_max) st_node4_zero(nodes4 + v);
+        else st_node4(nodes4 + v, rc_collapse_node(v, boxes, topo, n, leaf_max, leaf_map));
     }
 }
 
-static void launch_fit(cudaStream_t st, uint32_t n_bound, const RcTri *tris_in, const uint32_t *perm, RcTri *tris, const RcBox *inst_boxes, const uint32_t *leaf_map,
-                       const uint32_t *n_ptr, const RcTopo *topo, const uint32_t *parent, uint32_t *flags, RcBox *boxes, RcNode2 *nodes2, uint32_t *ctl) {
+// One fit of a built topology: leaf boxes -> boxes of every node (+ BVH2 records) (+ wide nodes, hull, finishing read-back words).
+struct FitJob {
+    uint32_t n_bound = 0;            // sizes the grids; the live count is *n_ptr (device) or n_bound itself
+    const uint32_t *n_ptr = nullptr;
+    const RcTri *tris_in = nullptr;  // leaf source, see k_fit_local
+    const uint32_t *perm = nullptr;
+    RcTri *tris = nullptr;
+    const RcBox *inst_boxes = nullptr;
+    const uint32_t *leaf_map = nullptr;
+    const RcTopo *topo = nullptr;
+    const uint32_t *parent = nullptr;
+    RcBox *boxes = nullptr;
+    RcNode2 *nodes2 = nullptr;       // nullable
+    RcNode4 *nodes4 = nullptr;       // nullable: no collapse
+    uint32_t leaf_max = 1;
+    RcBox *hull = nullptr;           // nullable
+    uint32_t *ctl = nullptr;         // BLAS control block (bounds -> sphere), nullable
+    float *out10 = nullptr;          // nullable: root box (+ sphere) for the host
+    const RcBox *root_boxes = nullptr;  // out10's root box comes from this fit's boxes unless given (TLAS: the reference boxes)
+    bool build_list = true;          // false: work.span_list / span_count already hold this topology's spanning nodes
+};
+static void run_fit(cudaStream_t st, const FitJob &j, const FitWork &work) {
     // the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute (several devices build concurrently under rc_multi_*)
     static bool configured[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !configured[dev]) {
-        cudaFuncSetAttribute(k_fit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FitSmem));
+        cudaFuncSetAttribute(k_fit_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FitSmem));
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
-    k_fit<<<cdiv(n_bound, FIT_T), FIT_T, sizeof(FitSmem), st>>>(tris_in, perm, tris, inst_boxes, leaf_map, n_ptr, n_bound, topo, parent, flags, boxes, nodes2, ctl);
-}
-
-// codes (sorted) -> topology, fit, (BVH2,) BVH4.  n_ptr == nullptr: the count is n_bound itself (TLAS).
-static void build_tree(cudaStream_t st, const uint32_t *codes_sorted, const uint32_t *n_ptr, uint32_t n_bound, const RcTri *tris_in, const uint32_t *perm, RcTri *tris,
-                       const RcBox *inst_boxes, const uint32_t *leaf_map, uint32_t leaf_max, RcTopo *topo, uint32_t *parent, uint32_t *flags, RcBox *boxes, RcNode2 *nodes2,
-                       RcNode4 *nodes4, RcBox *hull, uint32_t *ctl, const RcBox *inst_boxes_tight = nullptr, RcBox *boxes_tight = nullptr) {
-    const int T = 256;
-    k_topology<<<cdiv(std::max(1u, n_bound - 1), T), T, 0, st>>>(codes_sorted, n_ptr, n_bound, topo, parent, flags);
-    launch_fit(st, n_bound, tris_in, perm, tris, inst_boxes, leaf_map, n_ptr, topo, parent, flags, boxes, nodes2, ctl);
-    if (inst_boxes_tight) {  // wide TLAS from the tighter instance bounds (same topology, second fit without BVH2 output)
-        if (n_bound > 1) cudaMemsetAsync(flags, 0, sizeof(uint32_t) * (n_bound - 1), st);
-        launch_fit(st, n_bound, nullptr, nullptr, nullptr, inst_boxes_tight, leaf_map, n_ptr, topo, parent, flags, boxes_tight, nullptr, nullptr);
-        boxes = boxes_tight;
-    }
-    k_collapse<<<cdiv(n_bound > 1 ? n_bound - 1 : 1, T) + (hull ? 1 : 0), T, 0, st>>>(boxes, topo, n_ptr, n_bound, leaf_max, leaf_map, nodes4, hull);
-}
-
-// refit only (topology kept): recompute boxes, BVH2 and BVH4
-static void refit_tree(cudaStream_t st, uint32_t n, const RcBox *inst_boxes, const uint32_t *leaf_map, uint32_t leaf_max, const RcTopo *topo,
-                       const uint32_t *parent, uint32_t *flags, RcBox *boxes, RcNode2 *nodes2, RcNode4 *nodes4, const RcBox *inst_boxes_tight,
-                       RcBox *boxes_tight) {
-    const int T = 256;
-    if (n > 1) cudaMemsetAsync(flags, 0, sizeof(uint32_t) * (n - 1), st);
-    launch_fit(st, n, nullptr, nullptr, nullptr, inst_boxes, leaf_map, nullptr, topo, parent, flags, boxes, nodes2, nullptr);
-    if (n > 1) cudaMemsetAsync(flags, 0, sizeof(uint32_t) * (n - 1), st);
-    launch_fit(st, n, nullptr, nullptr, nullptr, inst_boxes_tight, leaf_map, nullptr, topo, parent, flags, boxes_tight, nullptr, nullptr);
-    k_collapse<<<cdiv(n > 1 ? n - 1 : 1, T), T, 0, st>>>(boxes_tight, topo, nullptr, n, leaf_max, leaf_map, nodes4, nullptr);
+    const uint32_t blocks = cdiv(j.n_bound, FIT_T);
+    k_fit_local<<<blocks, FIT_T, sizeof(FitSmem), st>>>(j.tris_in, j.perm, j.tris, j.inst_boxes, j.leaf_map, j.n_ptr, j.n_bound, j.topo, j.parent, j.boxes, j.nodes2, j.ctl, work,
+                                                        j.build_list, j.nodes4, j.leaf_max);
+    // at most FIT_SEG_MAX spanning nodes per block; one warp each, grid-stride
+    const uint32_t span_bound = blocks > 1 ? blocks * FIT_SEG_MAX : 0u;
+    if (span_bound) k_fit_span<<<std::min(cdiv(span_bound, 8), 148u * 8u), 256, 0, st>>>(j.n_ptr, j.n_bound, j.topo, j.parent, j.boxes, j.nodes2, work);
+    if (j.nodes4 || j.hull || j.out10)
+        k_collapse_span<<<(span_bound && j.nodes4 ? std::min(cdiv(span_bound, 256), 148u * 4u) : 0u) + 1u, 256, 0, st>>>(j.boxes, j.topo, j.n_ptr, j.n_bound, j.leaf_max, j.leaf_map,
+                                                                                                                         j.nodes4, j.hull, work, j.out10, j.ctl, j.root_boxes);
 }
 
 // =================================================================================================
@@ -736,7 +953,7 @@ bool rc_build_blas(cudaStream_t st, const float *d_verts, const uint32_t *d_face
     uint32_t *d_ctl = nullptr;
     RcTri *d_tris_in = nullptr;
     RcBox *d_boxes = nullptr;
-    uint32_t *d_codes = nullptr, *d_idx = nullptr, *d_codes2 = nullptr, *d_idx2 = nullptr, *d_hist = nullptr, *d_parent = nullptr, *d_fl = nullptr;
+    uint32_t *d_codes = nullptr, *d_idx = nullptr, *d_codes2 = nullptr, *d_idx2 = nullptr, *d_hist = nullptr, *d_parent = nullptr;
     RcTopo *d_topo = nullptr;
     TMP(d_ctl, CTL_WORDS + f_tiles);  // control block + the filter's tile states
     TMP(d_tris_in, nf);
@@ -745,7 +962,8 @@ bool rc_build_blas(cudaStream_t st, const float *d_verts, const uint32_t *d_face
     TMP(d_codes2, nf);
     TMP(d_idx2, nf);
     TMP(d_hist, radix_hist_words(nf));
-    TMP(d_fl, nf);
+    unsigned char *d_work = nullptr;
+    TMP(d_work, fit_work_bytes(nf));
     TMP(d_boxes, 2 * (size_t)nf);
     // the results outlive this call; on failure the caller releases them with rc_free_blas
     if (keep_topo) {
@@ -768,9 +986,16 @@ bool rc_build_blas(cudaStream_t st, const float *d_verts, const uint32_t *d_face
     k_morton_prims<<<s_tiles, RS_THREADS, 0, st>>>(d_tris_in, d_ctl, d_codes, d_idx, s_tiles, d_hist);
     uint32_t *codes_sorted = nullptr, *perm = nullptr;
     radix_sort_pairs(st, d_codes, d_idx, d_codes2, d_idx2, d_ctl + CTL_N, nf, d_hist, true, &codes_sorted, &perm);
-    build_tree(st, codes_sorted, d_ctl + CTL_N, nf, d_tris_in, perm, out->tris, nullptr, nullptr, RC_BLAS_LEAF_MAX, d_topo, d_parent, d_fl, d_boxes, out->nodes2, out->nodes4,
-               out->hull, d_ctl);
-    k_finish<<<1, 32, 0, st>>>(d_boxes, reinterpret_cast<float *>(d_ctl + CTL_OUT), d_ctl, out->nodes4);
+    k_topology<<<cdiv(std::max(1u, nf - 1), 256), 256, 0, st>>>(codes_sorted, d_ctl + CTL_N, nf, d_topo, d_parent);
+    FitWork work = fit_work_at(d_work, nf);
+    work.span_count = d_ctl + CTL_NSPAN;  // zeroed with the control block
+    FitJob job;
+    job.n_bound = nf; job.n_ptr = d_ctl + CTL_N;
+    job.tris_in = d_tris_in; job.perm = perm; job.tris = out->tris;
+    job.topo = d_topo; job.parent = d_parent; job.boxes = d_boxes; job.nodes2 = out->nodes2;
+    job.nodes4 = out->nodes4; job.leaf_max = RC_BLAS_LEAF_MAX; job.hull = out->hull;
+    job.ctl = d_ctl; job.out10 = reinterpret_cast<float *>(d_ctl + CTL_OUT);
+    run_fit(st, job, work);
     return finish_blas(st, d_ctl, out, err);
 }
 
@@ -814,10 +1039,11 @@ bool rc_refit_blas(cudaStream_t st, const float *d_verts, uint32_t n_faces, RcDe
     if (!b->topo || !b->parent || n_faces != b->n_faces_in || b->n == 0) return true;
     const uint32_t n = b->n;
     RcTemps tmp(st);
-    uint32_t *d_ctl = nullptr, *d_fl = nullptr;
+    uint32_t *d_ctl = nullptr;
+    unsigned char *d_work = nullptr;
     RcBox *d_boxes = nullptr;
     TMP(d_ctl, CTL_WORDS);
-    TMP(d_fl, n);
+    TMP(d_work, fit_work_bytes(n));
     TMP(d_boxes, 2 * (size_t)n);
     CK(cudaMemsetAsync(d_ctl, 0, sizeof(uint32_t) * CTL_WORDS, st));
     // check first, touch the geometry only when the refit is certain (a refused update leaves the old geometry intact, as update! does, :837)
@@ -831,10 +1057,14 @@ bool rc_refit_blas(cudaStream_t st, const float *d_verts, uint32_t n_faces, RcDe
     k_refit_apply<<<cdiv(n, 256), 256, 0, st>>>(d_verts, b->tris, n, d_ctl);
     uint32_t n_word = n;
     CK(cudaMemcpyAsync(d_ctl + CTL_N, &n_word, 4, cudaMemcpyHostToDevice, st));
-    if (n > 1) CK(cudaMemsetAsync(d_fl, 0, sizeof(uint32_t) * (n - 1), st));
-    launch_fit(st, n, nullptr, nullptr, b->tris, nullptr, nullptr, nullptr, b->topo, b->parent, d_fl, d_boxes, b->nodes2, d_ctl);
-    k_collapse<<<cdiv(n > 1 ? n - 1 : 1, 256) + 1, 256, 0, st>>>(d_boxes, b->topo, nullptr, n, RC_BLAS_LEAF_MAX, nullptr, b->nodes4, b->hull);
-    k_finish<<<1, 32, 0, st>>>(d_boxes, reinterpret_cast<float *>(d_ctl + CTL_OUT), d_ctl);
+    FitWork work = fit_work_at(d_work, n);
+    work.span_count = d_ctl + CTL_NSPAN;  // zero since the memset of the control block
+    FitJob job;
+    job.n_bound = n; job.tris = b->tris;
+    job.topo = b->topo; job.parent = b->parent; job.boxes = d_boxes; job.nodes2 = b->nodes2;
+    job.nodes4 = b->nodes4; job.leaf_max = RC_BLAS_LEAF_MAX; job.hull = b->hull;
+    job.ctl = d_ctl; job.out10 = reinterpret_cast<float *>(d_ctl + CTL_OUT);
+    run_fit(st, job, work);
     RcDeviceBlas probe;
     if (!finish_blas(st, d_ctl, &probe, err)) return false;
     memcpy(b->root_aabb, probe.root_aabb, 24);
@@ -914,7 +1144,7 @@ __global__ void k_instance_records(const rc_instance_desc *__restrict__ inst, co
 void rc_free_tlas(RcDeviceTlas *t, cudaStream_t st) {
     if (!t) return;
     for (void *p : {(void *)t->nodes2, (void *)t->nodes4, (void *)t->rec, (void *)t->aux, (void *)t->d_inst, (void *)t->d_blas_roots, (void *)t->d_blas_ptrs,
-                    (void *)t->inst_boxes, (void *)t->inst_boxes_tight, (void *)t->boxes_tight, (void *)t->leaf_map, (void *)t->topo, (void *)t->parent, (void *)t->flags, (void *)t->boxes, (void *)t->d_small})
+                    (void *)t->inst_boxes, (void *)t->inst_boxes_tight, (void *)t->boxes_tight, (void *)t->leaf_map, (void *)t->topo, (void *)t->parent, (void *)t->fit_work, (void *)t->boxes, (void *)t->d_small})
         if (p) cudaFreeAsync(p, st);
     *t = RcDeviceTlas();
 }
@@ -924,6 +1154,24 @@ static bool upload_instances(cudaStream_t st, RcDeviceTlas *t, const rc_instance
     CK(cudaMemcpyAsync(t->d_inst, h_inst, sizeof(rc_instance_desc) * n, cudaMemcpyHostToDevice, st));
     k_instance_records<<<cdiv(n, 256), 256, 0, st>>>(t->d_inst, t->d_blas_ptrs, n, t->rec, t->aux);
     return true;
+}
+
+// The two fits of a TLAS over one topology: the reference-identical instance boxes give the BVH2 (read-backs, reference-order mode) and the
+// root box; the tighter hull-derived boxes give the wide nodes.  The spanning-node list depends on the topology only: built by the first
+// fit after a (re)build (its counter, t->d_small[CTL_NSPAN], is zero then) and reused by every later fit.
+static void fit_tlas(cudaStream_t st, RcDeviceTlas *t, bool fresh_topology) {
+    FitWork work = fit_work_at(t->fit_work, t->n);
+    work.span_count = t->d_small + CTL_NSPAN;
+    FitJob ref;
+    ref.n_bound = t->n; ref.inst_boxes = t->inst_boxes; ref.leaf_map = t->leaf_map;
+    ref.topo = t->topo; ref.parent = t->parent; ref.boxes = t->boxes; ref.nodes2 = t->nodes2;
+    ref.build_list = fresh_topology;
+    run_fit(st, ref, work);
+    FitJob tight = ref;
+    tight.inst_boxes = t->inst_boxes_tight; tight.boxes = t->boxes_tight; tight.nodes2 = nullptr;
+    tight.nodes4 = t->nodes4; tight.leaf_max = 1; tight.build_list = false;
+    tight.out10 = reinterpret_cast<float *>(t->d_small + CTL_OUT); tight.root_boxes = t->boxes;
+    run_fit(st, tight, work);
 }
 
 bool rc_build_tlas(cudaStream_t st, const rc_instance_desc *h_inst, uint32_t n, const std::vector<RcBlasPtrs> &blas, const std::vector<float> &blas_roots,
@@ -947,7 +1195,7 @@ bool rc_build_tlas(cudaStream_t st, const rc_instance_desc *h_inst, uint32_t n, 
     CK(cudaMallocAsync(&t->leaf_map, sizeof(uint32_t) * n, st));
     CK(cudaMallocAsync(&t->topo, sizeof(RcTopo) * std::max(1u, n - 1), st));
     CK(cudaMallocAsync(&t->parent, sizeof(uint32_t) * (2 * n - 1), st));
-    CK(cudaMallocAsync(&t->flags, sizeof(uint32_t) * std::max(1u, n - 1), st));
+    CK(cudaMallocAsync(&t->fit_work, fit_work_bytes(n), st));
     CK(cudaMallocAsync(&t->boxes, sizeof(RcBox) * (2 * n - 1), st));
     CK(cudaMallocAsync(&t->nodes2, sizeof(RcNode2) * (2 * n - 1), st));
     CK(cudaMallocAsync(&t->nodes4, sizeof(RcNode4) * (n + 1), st));
@@ -966,9 +1214,8 @@ bool rc_build_tlas(cudaStream_t st, const rc_instance_desc *h_inst, uint32_t n, 
     uint32_t *codes_sorted = nullptr, *order = nullptr;
     radix_sort_pairs(st, d_codes, d_idx, d_codes2, d_idx2, nullptr, n, d_hist, false, &codes_sorted, &order);
     CK(cudaMemcpyAsync(t->leaf_map, order, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, st));  // leaf_map = sorted position -> instance index
-    build_tree(st, codes_sorted, nullptr, n, nullptr, nullptr, nullptr, t->inst_boxes, t->leaf_map, 1, t->topo, t->parent, t->flags, t->boxes, t->nodes2, t->nodes4, nullptr,
-               nullptr, t->inst_boxes_tight, t->boxes_tight);
-    k_finish<<<1, 32, 0, st>>>(t->boxes, reinterpret_cast<float *>(t->d_small + CTL_OUT), nullptr);
+    k_topology<<<cdiv(std::max(1u, n - 1), T), T, 0, st>>>(codes_sorted, nullptr, n, t->topo, t->parent);
+    fit_tlas(st, t, true);
     CK(cudaMemcpyAsync(t->root_aabb, t->d_small + CTL_OUT, 24, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
@@ -981,8 +1228,7 @@ bool rc_refit_tlas(cudaStream_t st, const rc_instance_desc *h_inst, uint32_t n, 
     if (!upload_instances(st, t, h_inst, n, err)) return false;
     // update_tlas_leaf_aabbs_kernel! (kernels.jl:487-519) + refit_tlas_aabbs_kernel! (:381-428), then re-quantise the wide nodes
     k_instance_boxes<<<cdiv(n, 256), 256, 0, st>>>(t->d_inst, t->d_blas_roots, n, t->inst_boxes, nullptr, t->d_blas_ptrs, t->inst_boxes_tight);
-    refit_tree(st, n, t->inst_boxes, t->leaf_map, 1, t->topo, t->parent, t->flags, t->boxes, t->nodes2, t->nodes4, t->inst_boxes_tight, t->boxes_tight);
-    k_finish<<<1, 32, 0, st>>>(t->boxes, reinterpret_cast<float *>(t->d_small + CTL_OUT), nullptr);
+    fit_tlas(st, t, false);
     CK(cudaMemcpyAsync(t->root_aabb, t->d_small + CTL_OUT, 24, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());

@@ -51,7 +51,7 @@ struct RcDeviceTlas {
     uint32_t *leaf_map = nullptr;  // sorted position -> instance index
     RcTopo *topo = nullptr;
     uint32_t *parent = nullptr;
-    uint32_t *flags = nullptr;
+    unsigned char *fit_work = nullptr;  // segment tables + spanning-node list of the fit (rc_build.cu), kept for refits
     RcBox *boxes = nullptr;
     uint32_t *d_small = nullptr;
     float root_aabb[6] = {0, 0, 0, 0, 0, 0};

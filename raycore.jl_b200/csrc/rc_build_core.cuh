@@ -78,15 +78,18 @@ RC_HD uint32_t rc_quant_exponent(float extent) {
     return e;
 }
 
-// Conservative 8-bit plane codes: decoded lo plane <= v (floor), decoded hi plane >= v (ceil)
+// Conservative 8-bit plane codes: decoded lo plane <= v (floor), decoded hi plane >= v (ceil).  scale = 2^(e-127) with
+// 1 <= e <= RC_QUANT_EXP_MAX, so x / scale == x * 2^(127-e) bit for bit (an exact scaling, one rounding either way, and the
+// reciprocal is a normal float): a multiply instead of an IEEE division (24 of them per wide node were 13 % of k_fit_local).
+RC_HD float rc_quant_inv_scale(float scale) { return u2f((254u << 23) - f2u(scale)); }
 RC_HD uint32_t rc_quant_lo(float v, float origin, float scale) {
-    float q = floorf((v - origin) / scale);
+    float q = floorf((v - origin) * rc_quant_inv_scale(scale));
     q = q < 0.0f ? 0.0f : (q > 255.0f ? 255.0f : q);
     while (q > 0.0f && fmaf(q, scale, origin) > v) q -= 1.0f;
     return (uint32_t)q;
 }
 RC_HD uint32_t rc_quant_hi(float v, float origin, float scale) {
-    float q = ceilf((v - origin) / scale);
+    float q = ceilf((v - origin) * rc_quant_inv_scale(scale));
     q = q < 0.0f ? 0.0f : (q > 255.0f ? 255.0f : q);
     while (q < 255.0f && fmaf(q, scale, origin) < v) q += 1.0f;
     return (uint32_t)q;
@@ -97,31 +100,41 @@ RC_HD uint32_t rc_quant_hi(float v, float origin, float scale) {
 //   leaf_map (nullable): sorted position -> payload index (TLAS: instance index), only with leaf_max == 1.
 // A BVH2 node covering <= leaf_max primitives becomes a leaf reference, otherwise the child with the
 // largest surface area is opened until four slots are used (greedy; precedent: src/bvh4.jl:234-277).
-RC_HD RcNode4 rc_collapse_node(uint32_t idx, const RcBox *boxes, const RcTopo *topo, uint32_t n, uint32_t leaf_max, const uint32_t *leaf_map) {
+// box_of(c) / topo_of(c): own box of BVH2 node c / topology record of internal node c (1-based numbers) — global arrays in k_collapse_span,
+// the block's shared-memory copies in k_fit_local.
+template <class BoxOf, class TopoOf>
+RC_HD RcNode4 rc_collapse_node_t(uint32_t idx, BoxOf box_of, TopoOf topo_of, uint32_t n, uint32_t leaf_max, const uint32_t *leaf_map) {
     uint32_t slots[4];
     int ns = 0;
-    auto count_of = [&](uint32_t c) -> uint32_t { return c >= n ? 1u : (topo[c - 1].span_hi - topo[c - 1].span_lo + 1u); };
-    const RcBox own = boxes[idx - 1];
+    auto count_of = [&](uint32_t c) -> uint32_t {
+        if (c >= n) return 1u;
+        const RcTopo t = topo_of(c);
+        return t.span_hi - t.span_lo + 1u;
+    };
+    const RcBox own = box_of(idx);
     uint32_t own_count = count_of(idx);
     if (idx >= n || own_count <= leaf_max) {
         slots[ns++] = idx;  // degenerate root: whole BLAS is one leaf
     } else {
-        slots[ns++] = topo[idx - 1].child0;
-        slots[ns++] = topo[idx - 1].child1;
+        {
+            const RcTopo t = topo_of(idx);
+            slots[ns++] = t.child0;
+            slots[ns++] = t.child1;
+        }
         while (ns < 4) {
             int best = -1;
             float best_area = -1.0f;
             for (int k = 0; k < ns; k++) {
                 uint32_t c = slots[k];
                 if (c < n && count_of(c) > leaf_max) {
-                    float a = rc_half_area(boxes[c - 1]);
+                    float a = rc_half_area(box_of(c));
                     if (a > best_area) { best_area = a; best = k; }
                 }
             }
             if (best < 0) break;
-            uint32_t c = slots[best];
-            slots[best] = topo[c - 1].child0;
-            slots[ns++] = topo[c - 1].child1;
+            const RcTopo t = topo_of(slots[best]);
+            slots[best] = t.child0;
+            slots[ns++] = t.child1;
         }
     }
     RcNode4 nd;
@@ -138,7 +151,7 @@ RC_HD RcNode4 rc_collapse_node(uint32_t idx, const RcBox *boxes, const RcTopo *t
             continue;
         }
         uint32_t c = slots[k];
-        const RcBox b = boxes[c - 1];
+        const RcBox b = box_of(c);
         qlo[0] |= rc_quant_lo(b.lo[0], nd.ox, sx) << (8 * k);
         qlo[1] |= rc_quant_lo(b.lo[1], nd.oy, sy) << (8 * k);
         qlo[2] |= rc_quant_lo(b.lo[2], nd.oz, sz) << (8 * k);
@@ -150,7 +163,7 @@ RC_HD RcNode4 rc_collapse_node(uint32_t idx, const RcBox *boxes, const RcTopo *t
             uint32_t pos = c - n;  // 0-based sorted position
             ch[k] = leaf_map ? (RC_TLAS_LEAF_TAG | leaf_map[pos]) : (RC_LEAF_BIT | pos);
         } else if (cnt <= leaf_max) {
-            uint32_t pos = topo[c - 1].span_lo - 1u;
+            uint32_t pos = topo_of(c).span_lo - 1u;
             ch[k] = RC_LEAF_BIT | ((cnt - 1u) << RC_LEAF_COUNT_SHIFT) | (leaf_map ? leaf_map[pos] : pos);
         } else {
             ch[k] = c;
@@ -161,6 +174,11 @@ RC_HD RcNode4 rc_collapse_node(uint32_t idx, const RcBox *boxes, const RcTopo *t
     for (int k = ns; k < 4; k++) ch[k] = ch[0];
     nd.child0 = ch[0]; nd.child1 = ch[1]; nd.child2 = ch[2]; nd.child3 = ch[3];
     return nd;
+}
+
+RC_HD RcNode4 rc_collapse_node(uint32_t idx, const RcBox *boxes, const RcTopo *topo, uint32_t n, uint32_t leaf_max, const uint32_t *leaf_map) {
+    return rc_collapse_node_t(
+        idx, [&](uint32_t c) -> RcBox { return boxes[c - 1]; }, [&](uint32_t c) -> RcTopo { return topo[c - 1]; }, n, leaf_max, leaf_map);
 }
 
 // Structural check of a BLAS (used on imported blobs).  A blob that passes can neither send a traversal out of bounds nor into an

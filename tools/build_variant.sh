@@ -9,6 +9,11 @@ out=../../build/variants/$name
 mkdir -p $out
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 ARCH="-gencode arch=compute_100a,code=sm_100a"
-$NVCC -O3 -std=c++17 $ARCH -lineinfo -Xcompiler -fPIC,-ffp-contract=off,-Wall -Xptxas -v --expt-relaxed-constexpr "$@" -c rc_trace.cu -o $out/rc_trace.o 2> $out/rc_trace.ptxas.log || (cat $out/rc_trace.ptxas.log; false)
-$NVCC -shared $ARCH -o $out/libraycore_cuda.so rc_api.o rc_build.o $out/rc_trace.o rc_analysis.o rc_collide.o rc_wavefront.o rc_multi.o
-echo "$name: $(grep -A2 'k_trace_wideILb0ELb0E10RcIoArraysLb0' $out/rc_trace.ptxas.log | grep -o 'Used [0-9]* registers\|[0-9]* bytes spill stores' | tr '\n' ' ')"
+src=${VARIANT_SRC:-rc_trace}   # VARIANT_SRC=rc_build: vary the builder instead of the traversal kernels
+$NVCC -O3 -std=c++17 $ARCH -lineinfo -Xcompiler -fPIC,-ffp-contract=off,-Wall -Xptxas -v --expt-relaxed-constexpr "$@" -c $src.cu -o $out/$src.o 2> $out/$src.ptxas.log || (cat $out/$src.ptxas.log; false)
+objs=""
+for o in rc_api rc_build rc_trace rc_analysis rc_collide rc_wavefront rc_multi; do
+  if [ $o = $src ]; then objs="$objs $out/$o.o"; else objs="$objs $o.o"; fi
+done
+$NVCC -shared $ARCH -o $out/libraycore_cuda.so $objs
+[ $src = rc_trace ] && echo "$name: $(grep -A2 'k_trace_wideILb0ELb0E10RcIoArraysLb0' $out/rc_trace.ptxas.log | grep -o 'Used [0-9]* registers\|[0-9]* bytes spill stores' | tr '\n' ' ')"

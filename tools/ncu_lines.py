@@ -24,11 +24,15 @@ for ln in sec.splitlines():
         continue
     if re.match(r"\s+/\*[0-9a-f]{4,}\*/", ln):
         line_of.append(cur)
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + os.environ.get("NCU_KERNEL", ".*"), "-c", "1"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr = rows[1]
 ci = {h: i for i, h in enumerate(hdr)}
 data = rows[2:]
+for k, r in enumerate(data):  # several launches of the kernel in the report: the first one
+    if r and r[0] == "Kernel Name":
+        data = data[:k]
+        break
 assert len(data) == len(line_of), (len(data), len(line_of))
 agg = {}
 for r, lo in zip(data, line_of):

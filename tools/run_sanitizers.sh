@@ -1,0 +1,30 @@
+#!/bin/bash
+# run_sanitizers.sh OUTDIR — compute-sanitizer (memcheck, racecheck, synccheck, initcheck) over smoke() and the randomised-scene /
+# builder / refit / lifecycle GPU tests.  One log per tool under OUTDIR plus a summary line each; the logs of the shipped
+# library are committed under profiles/.  racecheck covers the shared-memory stack of k_trace_wide and the block-local fit of k_fit;
+# memcheck covers the speculative row-above-the-top stores and the atomic climb's global traffic.
+out=${1:-gpurun_out/sanitizer}
+mkdir -p "$out"
+export PYTHONUNBUFFERED=1
+san=/usr/local/cuda/bin/compute-sanitizer
+tests="tests/test_gpu_fuzz.py tests/test_gpu_refit.py tests/test_gpu_lifecycle.py tests/test_watertight.py"
+for tool in memcheck racecheck synccheck initcheck; do
+  extra=""
+  [ "$tool" = racecheck ] && extra="--racecheck-report all --print-limit 200000"
+  log="$out/${tool}_smoke.log"
+  timeout 300 $san --tool $tool $extra --error-exitcode 99 --print-limit 50 python __graft_entry__.py smoke > "$log" 2>&1
+  echo "$tool smoke rc=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|LEAK SUMMARY' "$log" | tr '\n' ' ')" | tee -a "$out/summary.txt"
+  log="$out/${tool}_tests.log"
+  sel="not two_ranks"
+  [ "$tool" = racecheck ] && sel="test_random_scene_parity and (0 or 4 or 8) or refit or watertight"   # racecheck is ~100x slower: a subset
+  timeout 900 $san --tool $tool $extra --error-exitcode 99 --print-limit 50 python -m pytest $tests -m gpu -q -x -k "$sel" > "$log" 2>&1
+  echo "$tool tests rc=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|LEAK SUMMARY| passed| failed' "$log" | tr '\n' ' ')" | tee -a "$out/summary.txt"
+  if [ "$tool" = racecheck ]; then   # hazards per kernel and source line (the full logs are large: only this digest is kept)
+    for f in "$out/racecheck_smoke.log" "$out/racecheck_tests.log"; do
+      echo "== $f" >> "$out/racecheck_digest.txt"
+      grep -E "^=========     (Write|Read) Thread" "$f" | sed -E 's/Thread \([0-9,]+\) at //; s/\(.*\)\+0x[0-9a-f]+ in / /' | sort | uniq -c | sort -rn | head -40 >> "$out/racecheck_digest.txt"
+      grep -E "RACECHECK SUMMARY" "$f" >> "$out/racecheck_digest.txt"
+      head -c 200000 "$f" > "$f.head"; mv "$f.head" "$f"
+    done
+  fi
+done
