@@ -30,10 +30,10 @@ static inline uint32_t cdiv(uint64_t a, uint32_t b) { return (uint32_t)((a + b -
 
 // Control block of one build (u32 words, zeroed by one memset): the builder's kernels communicate through it.
 //   [CTL_N] valid primitives   [CTL_R2] bits of the bounding-sphere radius^2   [CTL_BOUNDS..+6) scene bounds, encoded so that 0 is the
-//   identity of atomicMax: word k < 3 holds ~ordered(min_k), word 3+k holds ordered(max_k)   [CTL_TILE] tile ticket of k_filter
-//   [CTL_NSPAN] length of the fit's spanning-node list
+//   identity of atomicMax: word k < 3 holds ~ordered(min_k), word 3+k holds ordered(max_k)   [CTL_TILE] scratch of the refit check
+//   [CTL_NSPAN] length of the fit's spanning-node list   [CTL_BAR] arrival counter of k_front's grid barriers   [CTL_ERR] internal-invariant flag
 //   [CTL_OUT..+10) floats read back by the host: root box (6), sphere (4)
-enum { CTL_N = 0, CTL_R2 = 1, CTL_BOUNDS = 2, CTL_TILE = 8, CTL_NSPAN = 10, CTL_OUT = 16, CTL_WORDS = 32 };
+enum { CTL_N = 0, CTL_R2 = 1, CTL_BOUNDS = 2, CTL_TILE = 8, CTL_NSPAN = 10, CTL_BAR = 11, CTL_ERR = 15, CTL_OUT = 16, CTL_WORDS = 32 };
 
 __device__ __forceinline__ f3 ctl_bounds_min(const uint32_t *ctl) {
     return mk3(rc_ordered_to_float(~ctl[CTL_BOUNDS]), rc_ordered_to_float(~ctl[CTL_BOUNDS + 1]), rc_ordered_to_float(~ctl[CTL_BOUNDS + 2]));
@@ -41,22 +41,8 @@ __device__ __forceinline__ f3 ctl_bounds_min(const uint32_t *ctl) {
 __device__ __forceinline__ f3 ctl_bounds_max(const uint32_t *ctl) {
     return mk3(rc_ordered_to_float(ctl[CTL_BOUNDS + 3]), rc_ordered_to_float(ctl[CTL_BOUNDS + 4]), rc_ordered_to_float(ctl[CTL_BOUNDS + 5]));
 }
-// the element count of a build: on the device (BLAS: written by k_filter) or a host constant (TLAS)
+// the element count of a build: on the device (BLAS: written by k_front) or a host constant (TLAS)
 __device__ __forceinline__ uint32_t count_of(const uint32_t *n_ptr, uint32_t n_host) { return n_ptr ? *n_ptr : n_host; }
-
-__device__ __forceinline__ uint32_t ld_relaxed(const uint32_t *p) {
-    uint32_t v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_relaxed(uint32_t *p, uint32_t v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-// release-ordered counter bump: the stores before it are visible to whoever observes the new count (no L1 invalidation on this side,
-// unlike __threadfence(), which costs a CCTL.IVALL per call)
-__device__ __forceinline__ uint32_t atom_add_release(uint32_t *p, uint32_t v) {
-    uint32_t old;
-    asm volatile("atom.release.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
-    return old;
-}
 
 // =================================================================================================
 // Scan (exclusive, u32) — block tiles of 2048 + single-block scan of the tile sums (used by the collision broad phase)
@@ -165,130 +151,7 @@ constexpr int RS_DIGITS = 1 << RS_BITS;
 constexpr int RS_PASSES = 3;
 constexpr int RS_DPT = RS_DIGITS / RS_THREADS;  // digits per thread in the table steps
 
-__global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ n_ptr, uint32_t n_host, int shift, uint32_t tiles,
-                                                          uint32_t *__restrict__ hist) {
-    __shared__ uint32_t sh[RS_DIGITS];
-    const uint32_t n = count_of(n_ptr, n_host);
-#pragma unroll
-    for (int k = 0; k < RS_DPT; k++) sh[threadIdx.x + k * RS_THREADS] = 0;
-    __syncthreads();
-    uint32_t base = blockIdx.x * RS_TILE;
-#pragma unroll
-    for (int i = 0; i < RS_ITEMS; i++) {
-        uint32_t idx = base + i * RS_THREADS + threadIdx.x;
-        if (idx < n) atomicAdd(&sh[(keys[idx] >> shift) & (RS_DIGITS - 1u)], 1u);
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < RS_DPT; k++) {
-        const uint32_t d = threadIdx.x + k * RS_THREADS;
-        hist[(size_t)d * tiles + blockIdx.x] = sh[d];
-    }
-}
-
-__global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in, uint32_t *__restrict__ keys_out,
-                                                             uint32_t *__restrict__ vals_out, const uint32_t *__restrict__ n_ptr, uint32_t n_host, int shift, uint32_t tiles,
-                                                             const uint32_t *__restrict__ offs, const uint32_t *__restrict__ totals) {
-    __shared__ uint32_t wh[RS_WARPS][RS_DIGITS];
-    __shared__ uint32_t sm[33];
-    const uint32_t n = count_of(n_ptr, n_host);
-    if ((uint64_t)blockIdx.x * RS_TILE >= n) return;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < RS_WARPS * RS_DIGITS; i += RS_THREADS) (&wh[0][0])[i] = 0;
-    __syncthreads();
-    // warp w owns the contiguous chunk [w*256, (w+1)*256) of the tile; item i of lane l = chunk + i*32 + l,
-    // so (i, l) lexicographic order == memory order and ranks are stable.
-    const uint32_t base = blockIdx.x * RS_TILE + wid * (32 * RS_ITEMS);
-    uint32_t key[RS_ITEMS], val[RS_ITEMS], rank[RS_ITEMS], dig[RS_ITEMS];
-    const uint32_t lt_mask = (1u << lane) - 1u;
-#pragma unroll
-    for (int i = 0; i < RS_ITEMS; i++) {
-        uint32_t idx = base + i * 32 + lane;
-        bool ok = idx < n;
-        key[i] = ok ? keys_in[idx] : 0xFFFFFFFFu;
-        val[i] = ok ? vals_in[idx] : 0u;
-        dig[i] = ok ? ((key[i] >> shift) & (RS_DIGITS - 1u)) : (uint32_t)RS_DIGITS;  // RS_DIGITS = padding lane group
-        uint32_t peers = __match_any_sync(0xFFFFFFFFu, dig[i]);
-        uint32_t leader = __ffs(peers) - 1;
-        uint32_t prev = 0;
-        if (ok && lane == (int)leader) {
-            prev = wh[wid][dig[i]];
-            wh[wid][dig[i]] = prev + __popc(peers);
-        }
-        prev = __shfl_sync(0xFFFFFFFFu, prev, leader);
-        rank[i] = prev + __popc(peers & lt_mask);
-        __syncwarp();
-    }
-    // keys with a smaller digit: exclusive scan of the 1024 row totals, RS_DPT consecutive digits per thread
-    uint32_t tot[RS_DPT], local = 0;
-#pragma unroll
-    for (int k = 0; k < RS_DPT; k++) { tot[k] = totals[threadIdx.x * RS_DPT + k]; local += tot[k]; }
-    uint32_t total_;
-    uint32_t digit_base = block_excl_scan(local, sm, total_);  // (includes a __syncthreads: the per-warp counts are complete)
-#pragma unroll
-    for (int k = 0; k < RS_DPT; k++) {  // digit d: turn the per-warp counts into exclusive prefixes starting at the global offset
-        const uint32_t d = threadIdx.x * RS_DPT + k;
-        uint32_t off = digit_base + offs[(size_t)d * tiles + blockIdx.x];
-        digit_base += tot[k];
-#pragma unroll
-        for (int w = 0; w < RS_WARPS; w++) {
-            uint32_t c = wh[w][d];
-            wh[w][d] = off;
-            off += c;
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < RS_ITEMS; i++) {
-        if (dig[i] < (uint32_t)RS_DIGITS) {
-            uint32_t pos = wh[wid][dig[i]] + rank[i];
-            keys_out[pos] = key[i];
-            vals_out[pos] = val[i];
-        }
-    }
-}
-
-// Row-wise exclusive scan of the digit-major table hist[RS_DIGITS][tiles] in place, one warp per digit row:
-// each lane sums a contiguous segment (independent loads), one warp scan orders the segments, the lane rewrites its segment.
-// The row totals go to totals[RS_DIGITS]; k_radix_scatter turns them into the per-digit bases itself, so no single-block pass
-// over the whole table is needed.
-__global__ void __launch_bounds__(256) k_scan_rows(uint32_t *__restrict__ hist, uint32_t tiles, uint32_t *__restrict__ totals) {
-    const uint32_t lane = threadIdx.x & 31, d = blockIdx.x * 8 + (threadIdx.x >> 5);
-    uint32_t *row = hist + (size_t)d * tiles;
-    const uint32_t seg = (tiles + 31) / 32, lo = min(lane * seg, tiles), hi = min(lo + seg, tiles);
-    uint32_t sum = 0;
-    for (uint32_t i = lo; i < hi; i++) sum += row[i];
-    const uint32_t inc = warp_incl_scan(sum);
-    uint32_t run = inc - sum;
-    for (uint32_t i = lo; i < hi; i++) {
-        const uint32_t v = row[i];
-        row[i] = run;
-        run += v;
-    }
-    if (lane == 31) totals[d] = inc;
-}
-
 static size_t radix_hist_words(uint32_t n_bound) { return (size_t)RS_DIGITS * cdiv(n_bound, RS_TILE) + RS_DIGITS; }
-
-// Sorts (keys, vals) by the low 30 bits of the keys.  n_bound sizes the grids; the live count is *n_ptr (device) or n_bound itself.
-// pass0_hist_done: the producer of the keys already wrote the pass-0 tile histograms (same tiling).  With three passes the sorted
-// pairs end up in (keys_tmp, vals_tmp): returned through the out pointers.
-static void radix_sort_pairs(cudaStream_t st, uint32_t *keys, uint32_t *vals, uint32_t *keys_tmp, uint32_t *vals_tmp, const uint32_t *n_ptr, uint32_t n_bound, uint32_t *hist,
-                             bool pass0_hist_done, uint32_t **keys_sorted, uint32_t **vals_sorted) {
-    uint32_t tiles = cdiv(n_bound, RS_TILE);
-    uint32_t *ki = keys, *vi = vals, *ko = keys_tmp, *vo = vals_tmp;
-    uint32_t *totals = hist + (size_t)RS_DIGITS * tiles;
-    for (int pass = 0; pass < RS_PASSES; pass++) {
-        int shift = pass * RS_BITS;
-        if (pass > 0 || !pass0_hist_done) k_radix_hist<<<tiles, RS_THREADS, 0, st>>>(ki, n_ptr, n_bound, shift, tiles, hist);
-        k_scan_rows<<<RS_DIGITS / 8, 256, 0, st>>>(hist, tiles, totals);
-        k_radix_scatter<<<tiles, RS_THREADS, 0, st>>>(ki, vi, ko, vo, n_ptr, n_bound, shift, tiles, hist, totals);
-        std::swap(ki, ko);
-        std::swap(vi, vo);
-    }
-    *keys_sorted = ki;
-    *vals_sorted = vi;
-}
 
 // =================================================================================================
 // BLAS front end: filter + stable compaction + bounds in one pass, then Morton codes (+ the first radix histogram)
@@ -318,131 +181,303 @@ __device__ __forceinline__ void bounds_atomic(uint32_t *ctl, f3 lo, f3 hi) {
     }
 }
 
-// One pass over the submitted faces (is_degenerate_face :573-577 + the compaction the reference does with filter!, :591-600):
-// exact degenerate test, stable compaction by a decoupled look-back scan over the 1024-face tiles (tile tickets are handed out in
-// arrival order, so a tile only ever waits for tiles that are already running), compacted RcTri records (prim_id = compacted slot),
-// scene bounds.  The last tile publishes the valid count.
-// Memory: the 36-byte faces of a tile are staged through shared memory with fully coalesced (16-byte when aligned) loads — a thread
-// reading its own 9 floats straight from global memory touches 9 x 36 sectors per warp —, and the 48-byte records leave through the
-// same buffer as one contiguous run of coalesced 16-byte stores (the valid faces of a tile are consecutive in the compacted array).
-constexpr int FILTER_T = 256;  // small tiles, many resident blocks: the phases of a tile (load, look-back, store) are barrier-separated and only overlap across blocks
-constexpr int FILTER_SMEM = FILTER_T * 48;  // bytes: the tile's records (>= the tile's 36-byte faces)
-__global__ void __launch_bounds__(FILTER_T) k_filter(const float *__restrict__ verts, const uint32_t *__restrict__ face_meta, uint32_t n_faces, RcTri *__restrict__ tris_in,
-                                                     uint32_t *__restrict__ ctl, uint32_t *__restrict__ tile_state) {
-    __shared__ __align__(16) unsigned char filter_raw[FILTER_SMEM];
-    float *stage = reinterpret_cast<float *>(filter_raw);
-    __shared__ uint32_t s_tile, s_warp[32], s_prefix, s_total;
-    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(&ctl[CTL_TILE], 1u);
+// =================================================================================================
+// The front end as ONE persistent cooperative kernel: filter + stable compaction + scene bounds, Morton codes, and the three radix passes,
+// separated by grid barriers instead of kernel boundaries (a launch boundary costs 3-5 us of drain + ramp; the 1 M-triangle front end was
+// 10 dependent launches).  Every block is resident (cooperative launch, grid <= occupancy x SMs) and loops over its tiles:
+//   F   per 2048-face tile: exact degenerate test, valid count -> tile_counts; scene bounds (one set of atomics per block)     | barrier
+//   M   prefix of the tile over tile_counts (no look-back chain), faces re-read (L2), compacted RcTri records, Morton codes    | barrier
+//   per pass: H per-tile digit histograms | barrier | R row scans of the digit-major table + digit totals | barrier | S stable scatter | barrier
+// Data that other blocks wrote earlier in the same launch is read with ld.cg (L1 is not coherent across a grid barrier).
+// The TLAS build runs the same kernel without F / M (its keys come from k_morton_instances).
+// =================================================================================================
+constexpr int FT_TILE = 2048;  // faces per filter tile (8 per thread): 1 M faces are 490 tiles, one per resident block
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+#ifdef RC_FRONT_PROF  // diagnosis build (tools/build_variant.sh): block 0 prints the time of every phase boundary
+__device__ __forceinline__ unsigned long long prof_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define RC_PROF_MARK(name) if (blockIdx.x == 0 && threadIdx.x == 0 && prof_k < 48) { prof_t[prof_k] = prof_now(); prof_name[prof_k++] = name; }
+#define RC_PROF_DUMP() if (blockIdx.x == 0 && threadIdx.x == 0) { for (int q = 0; q < prof_k; q++) printf("k_front %-10s %8llu ns\n", prof_name[q], prof_t[q] - (q ? prof_t[q - 1] : prof_t0)); }
+#else
+#define RC_PROF_MARK(name)
+#define RC_PROF_DUMP()
+#endif
+__device__ __forceinline__ void grid_barrier(uint32_t *bar, uint32_t &target) {
+    target += gridDim.x;
     __syncthreads();
-    const uint32_t tile = s_tile, i = tile * FILTER_T + tid;
-    const uint32_t faces_here = min((uint32_t)FILTER_T, n_faces - tile * FILTER_T);
-    {
-        const float *src = verts + (size_t)tile * FILTER_T * 9;
-        const uint32_t words = faces_here * 9u;
-        if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0u) {
-            const float4 *s4 = reinterpret_cast<const float4 *>(src);
-            float4 *d4 = reinterpret_cast<float4 *>(stage);
-            for (uint32_t k = tid; k < words / 4u; k += FILTER_T) d4[k] = __ldcs(s4 + k);  // read once
-            for (uint32_t k = (words & ~3u) + tid; k < words; k += FILTER_T) stage[k] = src[k];
-        } else {
-            for (uint32_t k = tid; k < words; k += FILTER_T) stage[k] = src[k];
-        }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        while (ld_acquire(bar) < target) __nanosleep(40);  // back off: hundreds of pollers on one L2 line delay the arrivals they wait for
+        __threadfence();
     }
     __syncthreads();
-    bool valid = false;
-    f3 a = mk3(0, 0, 0), b = a, c = a;
-    if (i < n_faces) {
-        const float *v = stage + tid * 9u;  // stride 9 words: conflict-free
-        a = ld3(v); b = ld3(v + 3); c = ld3(v + 6);
-        valid = !x_is_degenerate(a, b, c);
-    }
-    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, valid);
-    if (lane == 0) s_warp[wid] = __popc(bal);
-    __syncthreads();  // (also: every thread has read its face, the staging buffer can take the records)
-    if (wid == 0) {
-        const uint32_t cnt = lane < FILTER_T / 32 ? s_warp[lane] : 0u, inc = warp_incl_scan(cnt);
-        s_warp[lane] = inc - cnt;
-        const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 31);
-        // look back: state word = flag << 30 | count, flag 1 = this tile's own count, 2 = inclusive prefix up to and including the tile
-        uint32_t excl = 0;
-        if (tile > 0) {
-            if (lane == 0) st_relaxed(&tile_state[tile], (1u << 30) | total);
-            int base = (int)tile;
-            for (;;) {
-                const int t = base - 1 - (int)lane;
-                uint32_t st;
-                do { st = t >= 0 ? ld_relaxed(&tile_state[t]) : (2u << 30); } while (__any_sync(0xFFFFFFFFu, (st >> 30) == 0u));
-                const uint32_t incl_mask = __ballot_sync(0xFFFFFFFFu, (st >> 30) == 2u);
-                const uint32_t use = incl_mask ? ((2u << (__ffs(incl_mask) - 1)) - 1u) : 0xFFFFFFFFu;  // lanes up to the nearest inclusive prefix
-                uint32_t v = (use >> lane) & 1u ? (st & 0x3FFFFFFFu) : 0u;
+}
+struct FrontArgs {
+    const float *verts;         // null: sort only (n = n_host, keys / vals already in keys0 / vals0)
+    const uint32_t *face_meta;  // nullable
+    uint32_t n_faces;
+    RcTri *tris_in;
+    uint32_t *tile_counts;      // cdiv(n_faces, FT_TILE)
+    uint32_t *ctl;              // bounds, CTL_N
+    uint32_t *keys0, *vals0, *keys1, *vals1;  // three passes: the sorted pairs end up in (keys1, vals1)
+    uint32_t n_host;
+    uint32_t *hist;             // RS_DIGITS x tiles_stride, then RS_DIGITS totals
+    uint32_t tiles_stride;
+    uint32_t *bar;              // zeroed
+};
+__device__ __forceinline__ f3 ldcg3(const uint32_t *ctl, int k, bool inv) {
+    const uint32_t a = __ldcg(ctl + k), b = __ldcg(ctl + k + 1), c = __ldcg(ctl + k + 2);
+    return inv ? mk3(rc_ordered_to_float(~a), rc_ordered_to_float(~b), rc_ordered_to_float(~c)) : mk3(rc_ordered_to_float(a), rc_ordered_to_float(b), rc_ordered_to_float(c));
+}
+__global__ void __launch_bounds__(RS_THREADS, 4) k_front(const FrontArgs A) {
+    __shared__ uint32_t wh[RS_WARPS][RS_DIGITS];
+    __shared__ uint32_t sm[40];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5, lt_mask = (1u << lane) - 1u;
+    uint32_t target = 0, n = A.n_host;
+#ifdef RC_FRONT_PROF
+    unsigned long long prof_t0 = prof_now(), prof_t[48];
+    const char *prof_name[48];
+    int prof_k = 0;
+#endif
+    if (A.verts) {
+        const uint32_t f_tiles = (A.n_faces + FT_TILE - 1) / FT_TILE;
+        // ---- F: valid faces per tile, scene bounds
+        f3 lo = mk3(INFINITY, INFINITY, INFINITY), hi = mk3(-INFINITY, -INFINITY, -INFINITY);
+        for (uint32_t t = blockIdx.x; t < f_tiles; t += gridDim.x) {
+            uint32_t cnt = 0;
 #pragma unroll
-                for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
-                excl += v;
-                if (incl_mask) break;
-                base -= 32;
+            for (int it = 0; it < FT_TILE / RS_THREADS; it++) {
+                const uint32_t i = t * FT_TILE + it * RS_THREADS + tid;
+                if (i < A.n_faces) {
+                    const float *v = A.verts + (size_t)i * 9;
+                    const f3 a = ld3(v), b = ld3(v + 3), c = ld3(v + 6);
+                    if (!x_is_degenerate(a, b, c)) {
+                        cnt++;
+                        lo = jl_min3(lo, jl_min3(jl_min3(a, b), c));  // world_bound(tri), triangle_mesh.jl:37
+                        hi = jl_max3(hi, jl_max3(jl_max3(a, b), c));
+                    }
+                }
+            }
+            cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
+            if (lane == 0) sm[wid] = cnt;
+            __syncthreads();
+            if (tid == 0) {
+                uint32_t s = 0;
+#pragma unroll
+                for (int w = 0; w < RS_WARPS; w++) s += sm[w];
+                A.tile_counts[t] = s;
+            }
+            __syncthreads();
+        }
+        bounds_atomic(A.ctl, lo, hi);
+        RC_PROF_MARK("F")
+        grid_barrier(A.bar, target);
+        RC_PROF_MARK("F-barrier")
+        // ---- M: compacted records + Morton codes (calculate_morton_code_for_prim, kernels.jl:88-98; extent unguarded, :1388)
+        const f3 smin = ldcg3(A.ctl, CTL_BOUNDS, true), smax = ldcg3(A.ctl, CTL_BOUNDS + 3, false);
+        const f3 ext = x_sub3(smax, smin);
+        uint32_t total = 0;
+        {   // every block needs the valid count
+            uint32_t s = 0;
+            for (uint32_t k = tid; k < f_tiles; k += RS_THREADS) s += __ldcg(A.tile_counts + k);
+            uint32_t tot_;
+            block_excl_scan(s, sm, tot_);
+            total = tot_;
+        }
+        n = total;
+        if (blockIdx.x == 0 && tid == 0) A.ctl[CTL_N] = n;
+        for (uint32_t t = blockIdx.x; t < f_tiles; t += gridDim.x) {
+            uint32_t s = 0;
+            for (uint32_t k = tid; k < t; k += RS_THREADS) s += __ldcg(A.tile_counts + k);
+            uint32_t prefix;
+            block_excl_scan(s, sm, prefix);  // (its total = the faces kept before this tile)
+            // warp w owns the contiguous faces [w * 256, (w + 1) * 256) of the tile; item `it` of lane l = chunk + it * 32 + l, so (it, l)
+            // lexicographic order == face order and the ranks are stable (filter! keeps the order, src/instanced-bvh.jl:591-600)
+            constexpr int ITEMS = FT_TILE / RS_THREADS;
+            uint32_t bal[ITEMS], wsum = 0;
+#pragma unroll
+            for (int it = 0; it < ITEMS; it++) {
+                const uint32_t i = t * FT_TILE + wid * (32 * ITEMS) + it * 32 + lane;
+                bool valid = false;
+                if (i < A.n_faces) {
+                    const float *v = A.verts + (size_t)i * 9;
+                    valid = !x_is_degenerate(ld3(v), ld3(v + 3), ld3(v + 6));
+                }
+                bal[it] = __ballot_sync(0xFFFFFFFFu, valid);
+                wsum += __popc(bal[it]);
+            }
+            uint32_t tile_total;
+            const uint32_t woff = block_excl_scan(lane == 0 ? wsum : 0u, sm, tile_total);  // exclusive over the threads: lane 0 of warp w holds the warps before it
+            uint32_t base = prefix + __shfl_sync(0xFFFFFFFFu, woff, 0);
+#pragma unroll
+            for (int it = 0; it < ITEMS; it++) {
+                if ((bal[it] >> lane) & 1u) {
+                    const uint32_t i = t * FT_TILE + wid * (32 * ITEMS) + it * 32 + lane;
+                    const uint32_t k = base + __popc(bal[it] & lt_mask);
+                    const float *v = A.verts + (size_t)i * 9;  // (second read of the face: L1)
+                    const f3 a = ld3(v), b = ld3(v + 3), c = ld3(v + 6);
+                    float4 *d = reinterpret_cast<float4 *>(A.tris_in + k);
+                    d[0] = make_float4(a.x, a.y, a.z, __uint_as_float(k));
+                    d[1] = make_float4(b.x, b.y, b.z, __uint_as_float(A.face_meta ? A.face_meta[i] : i + 1u));  // :595
+                    d[2] = make_float4(c.x, c.y, c.z, __uint_as_float(i));
+                    const f3 blo = jl_min3(jl_min3(a, b), c), bhi = jl_max3(jl_max3(a, b), c);
+                    const f3 ctr = mk3(x_mul(0.5f, x_add(blo.x, bhi.x)), x_mul(0.5f, x_add(blo.y, bhi.y)), x_mul(0.5f, x_add(blo.z, bhi.z)));
+                    const f3 nrm = mk3(x_div(x_sub(ctr.x, smin.x), ext.x), x_div(x_sub(ctr.y, smin.y), ext.y), x_div(x_sub(ctr.z, smin.z), ext.z));
+                    A.keys0[k] = rc_morton30(nrm);
+                    A.vals0[k] = k;
+                }
+                base += __popc(bal[it]);
             }
         }
-        if (lane == 0) {
-            st_relaxed(&tile_state[tile], (2u << 30) | (excl + total));
-            s_prefix = excl;
-            s_total = total;
+        RC_PROF_MARK("M")
+        grid_barrier(A.bar, target);
+        RC_PROF_MARK("M-barrier")
+    }
+    if (n == 0) return;  // (uniform over the grid)
+    const uint32_t tiles = (n + RS_TILE - 1) / RS_TILE, stride = A.tiles_stride;
+    uint32_t *totals = A.hist + (size_t)RS_DIGITS * stride;
+    uint32_t *ki = A.keys0, *vi = A.vals0, *ko = A.keys1, *vo = A.vals1;
+    for (int pass = 0; pass < RS_PASSES; pass++) {
+        const int shift = pass * RS_BITS;
+        // ---- H: per-tile digit histograms -> hist[digit * stride + tile]
+        uint32_t *sh = &wh[0][0];
+        for (uint32_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+#pragma unroll
+            for (int k = 0; k < RS_DPT; k++) sh[tid + k * RS_THREADS] = 0;
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < RS_ITEMS; i++) {
+                const uint32_t idx = t * RS_TILE + i * RS_THREADS + tid;
+                if (idx < n) atomicAdd(&sh[(__ldcg(ki + idx) >> shift) & (RS_DIGITS - 1u)], 1u);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < RS_DPT; k++) {
+                const uint32_t d = tid + k * RS_THREADS;
+                A.hist[(size_t)d * stride + t] = sh[d];
+            }
+            __syncthreads();
         }
+        RC_PROF_MARK("H")
+        grid_barrier(A.bar, target);
+        RC_PROF_MARK("H-barrier")
+        // ---- R: row-wise exclusive scan of the digit-major table, one warp per digit row; row totals -> totals[]
+        // (rows are dealt to the blocks round-robin — warp 0 of every block first —, a row is read with coalesced, independent loads: 16 in
+        // flight per lane, so a row of <= 512 tiles costs one L2 round trip)
+        for (uint32_t d = blockIdx.x + wid * gridDim.x; d < (uint32_t)RS_DIGITS; d += gridDim.x * RS_WARPS) {
+            uint32_t *row = A.hist + (size_t)d * stride;
+            uint32_t run = 0;
+            for (uint32_t base = 0; base < tiles; base += 32u * 16u) {
+                uint32_t v[16];
+#pragma unroll
+                for (int u = 0; u < 16; u++) {
+                    const uint32_t i = base + u * 32u + lane;
+                    v[u] = i < tiles ? __ldcg(row + i) : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < 16; u++) {
+                    const uint32_t i = base + u * 32u + lane;
+                    const uint32_t inc = warp_incl_scan(v[u]);
+                    if (i < tiles) row[i] = run + inc - v[u];
+                    run += __shfl_sync(0xFFFFFFFFu, inc, 31);
+                }
+            }
+            if (lane == 0) totals[d] = run;
+        }
+        RC_PROF_MARK("R")
+        grid_barrier(A.bar, target);
+        RC_PROF_MARK("R-barrier")
+        // ---- S: stable in-tile ranking (warp match_any) + scatter; the digit bases come from the row totals
+        for (uint32_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+            for (int i = tid; i < RS_WARPS * RS_DIGITS; i += RS_THREADS) (&wh[0][0])[i] = 0;
+            __syncthreads();
+            // warp w owns the contiguous chunk [w*256, (w+1)*256) of the tile; item i of lane l = chunk + i*32 + l,
+            // so (i, l) lexicographic order == memory order and ranks are stable.
+            const uint32_t base = t * RS_TILE + wid * (32 * RS_ITEMS);
+            uint32_t key[RS_ITEMS], val[RS_ITEMS], rank[RS_ITEMS], dig[RS_ITEMS];
+#pragma unroll
+            for (int i = 0; i < RS_ITEMS; i++) {
+                const uint32_t idx = base + i * 32 + lane;
+                const bool ok = idx < n;
+                key[i] = ok ? __ldcg(ki + idx) : 0xFFFFFFFFu;
+                val[i] = ok ? __ldcg(vi + idx) : 0u;
+            }
+#pragma unroll
+            for (int i = 0; i < RS_ITEMS; i++) {
+                const bool ok = base + i * 32 + lane < n;
+                dig[i] = ok ? ((key[i] >> shift) & (RS_DIGITS - 1u)) : (uint32_t)RS_DIGITS;  // RS_DIGITS = padding lane group
+                const uint32_t peers = __match_any_sync(0xFFFFFFFFu, dig[i]);
+                const uint32_t leader = __ffs(peers) - 1;
+                uint32_t prev = 0;
+                if (ok && lane == leader) {
+                    prev = wh[wid][dig[i]];
+                    wh[wid][dig[i]] = prev + __popc(peers);
+                }
+                prev = __shfl_sync(0xFFFFFFFFu, prev, leader);
+                rank[i] = prev + __popc(peers & lt_mask);
+                __syncwarp();
+            }
+            // keys with a smaller digit: exclusive scan of the 1024 row totals, RS_DPT consecutive digits per thread
+            uint32_t tot[RS_DPT], local = 0;
+#pragma unroll
+            for (int k = 0; k < RS_DPT; k++) { tot[k] = __ldcg(totals + tid * RS_DPT + k); local += tot[k]; }
+            uint32_t total_;
+            uint32_t digit_base = block_excl_scan(local, sm, total_);  // (includes a __syncthreads: the per-warp counts are complete)
+#pragma unroll
+            for (int k = 0; k < RS_DPT; k++) {  // digit d: turn the per-warp counts into exclusive prefixes starting at the global offset
+                const uint32_t d = tid * RS_DPT + k;
+                uint32_t off = digit_base + __ldcg(A.hist + (size_t)d * stride + t);
+                digit_base += tot[k];
+#pragma unroll
+                for (int w = 0; w < RS_WARPS; w++) {
+                    const uint32_t c = wh[w][d];
+                    wh[w][d] = off;
+                    off += c;
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < RS_ITEMS; i++) {
+                if (dig[i] < (uint32_t)RS_DIGITS) {
+                    const uint32_t pos = wh[wid][dig[i]] + rank[i];
+                    ko[pos] = key[i];
+                    vo[pos] = val[i];
+                }
+            }
+            __syncthreads();
+        }
+        RC_PROF_MARK("S")
+        if (pass + 1 < RS_PASSES) grid_barrier(A.bar, target);
+        RC_PROF_MARK("S-barrier")
+        if (pass + 1 == RS_PASSES) { RC_PROF_DUMP() }
+        uint32_t *tk = ki; ki = ko; ko = tk;
+        uint32_t *tv = vi; vi = vo; vo = tv;
     }
-    f3 lo = mk3(INFINITY, INFINITY, INFINITY), hi = mk3(-INFINITY, -INFINITY, -INFINITY);
-    __syncthreads();
-    if (valid) {
-        const uint32_t r = s_warp[wid] + __popc(bal & ((1u << lane) - 1u)), k = s_prefix + r;  // rank in the tile, compacted slot
-        float4 *d = reinterpret_cast<float4 *>(stage) + 3u * r;
-        d[0] = make_float4(a.x, a.y, a.z, __uint_as_float(k));
-        d[1] = make_float4(b.x, b.y, b.z, __uint_as_float(face_meta ? face_meta[i] : i + 1u));  // :595
-        d[2] = make_float4(c.x, c.y, c.z, __uint_as_float(i));
-        lo = jl_min3(jl_min3(a, b), c);  // world_bound(tri), triangle_mesh.jl:37
-        hi = jl_max3(jl_max3(a, b), c);
-    }
-    bounds_atomic(ctl, lo, hi);  // (contains a __syncthreads: the records are complete)
-    {
-        const float4 *s4 = reinterpret_cast<const float4 *>(stage);
-        float4 *d4 = reinterpret_cast<float4 *>(tris_in + s_prefix);
-        for (uint32_t k = tid; k < 3u * s_total; k += FILTER_T) d4[k] = s4[k];
-    }
-    if (tid == 0 && tile == gridDim.x - 1) ctl[CTL_N] = s_prefix + s_total;
 }
 
-// calculate_morton_code_for_prim, kernels.jl:88-98 (extent unguarded, :1388), one RS_TILE of compacted triangles per block; also the
-// block's digit histogram of the first radix pass.
-__global__ void __launch_bounds__(RS_THREADS) k_morton_prims(const RcTri *__restrict__ tris_in, const uint32_t *__restrict__ ctl, uint32_t *__restrict__ codes,
-                                                            uint32_t *__restrict__ idx, uint32_t tiles, uint32_t *__restrict__ hist) {
-    __shared__ uint32_t sh[RS_DIGITS];
-    const uint32_t n = ctl[CTL_N];
-#pragma unroll
-    for (int k = 0; k < RS_DPT; k++) sh[threadIdx.x + k * RS_THREADS] = 0;
-    __syncthreads();
-    if ((uint64_t)blockIdx.x * RS_TILE < n) {
-        const f3 smin = ctl_bounds_min(ctl), smax = ctl_bounds_max(ctl);
-        const f3 ext = x_sub3(smax, smin);
-#pragma unroll 2
-        for (int it = 0; it < RS_ITEMS; it++) {
-            const uint32_t i = blockIdx.x * RS_TILE + it * RS_THREADS + threadIdx.x;
-            if (i >= n) break;
-            const float4 *t = reinterpret_cast<const float4 *>(tris_in + i);
-            const float4 p = t[0], q = t[1], r = t[2];
-            const f3 a = mk3(p.x, p.y, p.z), b = mk3(q.x, q.y, q.z), c3 = mk3(r.x, r.y, r.z);
-            const f3 lo = jl_min3(jl_min3(a, b), c3), hi = jl_max3(jl_max3(a, b), c3);
-            const f3 c = mk3(x_mul(0.5f, x_add(lo.x, hi.x)), x_mul(0.5f, x_add(lo.y, hi.y)), x_mul(0.5f, x_add(lo.z, hi.z)));
-            const f3 nrm = mk3(x_div(x_sub(c.x, smin.x), ext.x), x_div(x_sub(c.y, smin.y), ext.y), x_div(x_sub(c.z, smin.z), ext.z));
-            const uint32_t code = rc_morton30(nrm);
-            codes[i] = code;
-            idx[i] = i;
-            atomicAdd(&sh[code & (RS_DIGITS - 1u)], 1u);
-        }
+// grid of the front-end kernel: one block per tile, capped at what is co-resident on this device
+static bool launch_front(cudaStream_t st, FrontArgs &A, uint32_t tiles_wanted, std::string &err) {
+    static int max_blocks[64] = {0};
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    int cap = (dev >= 0 && dev < 64) ? max_blocks[dev] : 0;
+    if (cap == 0) {
+        int per_sm = 0, sms = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_front, RS_THREADS, 0));
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        cap = per_sm * sms;
+        if (cap < 1) { err = "k_front does not fit on this device"; return false; }
+        if (dev >= 0 && dev < 64) max_blocks[dev] = cap;
     }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < RS_DPT; k++) {
-        const uint32_t d = threadIdx.x + k * RS_THREADS;
-        hist[(size_t)d * tiles + blockIdx.x] = sh[d];
-    }
+    // at least 128 blocks: the row scans of a pass are 1024 independent rows, one warp each
+    const uint32_t grid = std::min(std::max(tiles_wanted, 128u), (uint32_t)cap);
+    void *args[] = {(void *)&A};
+    CK(cudaLaunchCooperativeKernel((const void *)k_front, dim3(grid), dim3(RS_THREADS), args, 0, st));
+    return true;
 }
 
 // =================================================================================================
@@ -513,21 +548,22 @@ struct FitSeg {  // 64 B; the table of a block is sorted by position, entry 0 st
     float sfx[6], pfx[6];
 };
 static_assert(sizeof(FitSeg) == 64, "segment table entry");
-struct FitWork {  // per-fit scratch: segment tables [blocks][FIT_SEG_MAX], spanning-node list [blocks * FIT_SEG_MAX], its length
+struct FitWork {  // per-fit scratch: segment tables [blocks][FIT_SEG_MAX], spanning-node list [blocks * FIT_SEG_MAX] of (node, span_lo, span_hi, -), its length
     FitSeg *seg;
-    uint32_t *span_list;
+    uint4 *span_list;
     uint32_t *span_count;
+    uint32_t *err_flag;  // set when a block found more than FIT_SEG_MAX segments (impossible for a radix tree; checked by the host, never silent)
 };
 static size_t fit_work_bytes(uint32_t n_bound) {
     const size_t blocks = cdiv(n_bound, FIT_T);
-    return blocks * FIT_SEG_MAX * (sizeof(FitSeg) + sizeof(uint32_t)) + 64;
+    return blocks * FIT_SEG_MAX * (sizeof(FitSeg) + sizeof(uint4)) + 64;
 }
 static FitWork fit_work_at(void *base, uint32_t n_bound) {
     const size_t blocks = cdiv(n_bound, FIT_T);
     FitWork w;
     w.seg = reinterpret_cast<FitSeg *>(base);
-    w.span_list = reinterpret_cast<uint32_t *>(w.seg + blocks * FIT_SEG_MAX);
-    w.span_count = w.span_list + blocks * FIT_SEG_MAX;
+    w.span_list = reinterpret_cast<uint4 *>(w.seg + blocks * FIT_SEG_MAX);
+    w.span_count = reinterpret_cast<uint32_t *>(w.span_list + blocks * FIT_SEG_MAX);
     return w;
 }
 struct FitSmem {
@@ -655,6 +691,7 @@ __global__ void __launch_bounds__(FIT_T) k_fit_local(const RcTri *__restrict__ t
     __syncthreads();
     // ---- segment table: position-sorted entries with the suffix / prefix unions of the block's segments
     const uint32_t m_all = S.nseg, m = min(m_all, (uint32_t)FIT_SEG_MAX);
+    if (tid == 0 && m_all > (uint32_t)FIT_SEG_MAX) atomicOr(work.err_flag, 1u);
     if (tid < m) {
         const uint32_t sj = S.seg_s[tid], ej = S.seg_e[tid];
         uint32_t rank = 0;
@@ -673,6 +710,9 @@ __global__ void __launch_bounds__(FIT_T) k_fit_local(const RcTri *__restrict__ t
         const float4 *src = reinterpret_cast<const float4 *>(&e);
         float4 *dst = reinterpret_cast<float4 *>(work.seg + (size_t)blockIdx.x * FIT_SEG_MAX + rank);
         dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+    } else if (tid < (uint32_t)FIT_SEG_MAX) {  // unused entries: position 0 matches no (1-based) leaf, so a reader needs no count
+        float4 *dst = reinterpret_cast<float4 *>(work.seg + (size_t)blockIdx.x * FIT_SEG_MAX + tid);
+        dst[0] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     // ---- this block's internal nodes: spanning ones go to the list, the others are collapsed from shared memory
     bool spanning = false;
@@ -686,7 +726,7 @@ __global__ void __launch_bounds__(FIT_T) k_fit_local(const RcTri *__restrict__ t
         uint32_t base = 0;
         if ((tid & 31u) == 0u && bal) base = atomicAdd(work.span_count, (uint32_t)__popc(bal));
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (spanning) work.span_list[base + __popc(bal & ((1u << (tid & 31u)) - 1u))] = p1;
+        if (spanning) work.span_list[base + __popc(bal & ((1u << (tid & 31u)) - 1u))] = make_uint4(p1, tp.span_lo, tp.span_hi, 0u);
     }
     if (nodes4) {
         // a third of the nodes head no wide node: the others are compacted into a dense list first, so the (long) collapse runs with full warps
@@ -722,13 +762,12 @@ __device__ __forceinline__ void fit_range_box(const FitSeg *__restrict__ seg, ui
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t bA = (a - 1u) / FIT_T, bB = (b - 1u) / FIT_T;
     const FitSeg *tA = seg + (size_t)bA * FIT_SEG_MAX, *tB = seg + (size_t)bB * FIT_SEG_MAX;
-    const uint32_t mA = tA[0].count, mB = tB[0].count;
     uint32_t ia = 0xFFFFFFFFu, ib = 0xFFFFFFFFu;
 #pragma unroll
     for (uint32_t q = 0; q < FIT_SEG_MAX / 32; q++) {
         const uint32_t j = q * 32u + lane;
-        if (j < mA && tA[j].s == a) ia = j;
-        if (j < mB && tB[j].e == b) ib = j;
+        if (tA[j].s == a) ia = j;
+        if (tB[j].e == b) ib = j;
     }
     ia = __reduce_min_sync(0xFFFFFFFFu, ia);
     ib = __reduce_min_sync(0xFFFFFFFFu, ib);
@@ -765,12 +804,13 @@ __global__ void __launch_bounds__(256) k_fit_span(const uint32_t *__restrict__ n
     const uint32_t count = *work.span_count, lane = threadIdx.x & 31u;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < count; w += warps) {
-        const uint32_t v = work.span_list[w];
-        const RcTopo tp = topo[v - 1];
+        const uint4 ent = work.span_list[w];
+        const uint32_t v = ent.x;
         f3 lo, hi;
-        fit_range_box(work.seg, tp.span_lo, tp.span_hi, lo, hi);
+        fit_range_box(work.seg, ent.y, ent.z, lo, hi);
         if (lane == 0) st_box(boxes + (v - 1), lo, hi);
         if (nodes2) {  // the BVH2 record holds the children's boxes: a spanning child's box comes from the same formula
+            const RcTopo tp = topo[v - 1];
             f3 cl[2], ch[2];
 #pragma unroll
             for (int k = 0; k < 2; k++) {
@@ -839,9 +879,9 @@ __global__ void __launch_bounds__(256) k_collapse_span(const RcBox *__restrict__
     if (!nodes4) return;
     const uint32_t count = *work.span_count, threads = (gridDim.x - 1) * blockDim.x;
     for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < count; w += threads) {
-        const uint32_t v = work.span_list[w];
-        const RcTopo tp = topo[v - 1];
-        if (v > 1u && tp.span_hi - tp.span_lo + 1u <= leaf_max) st_node4_zero(nodes4 + v);
+        const uint4 ent = work.span_list[w];
+        const uint32_t v = ent.x;
+        if (v > 1u && ent.z - ent.y + 1u <= leaf_max) st_node4_zero(nodes4 + v);
         else st_node4(nodes4 + v, rc_collapse_node(v, boxes, topo, n, leaf_max, leaf_map));
     }
 }
@@ -936,6 +976,7 @@ static bool finish_blas(cudaStream_t st, uint32_t *d_ctl, RcDeviceBlas *out, std
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     out->n = h[CTL_N];
+    if (h[CTL_ERR]) { err = "internal error: fit segment table overflow"; return false; }
     if (out->n == 0) { err = "Geometry has no valid triangles"; return false; }  // src/instanced-bvh.jl:601
     memcpy(out->root_aabb, h + CTL_OUT, 24);
     memcpy(out->sphere, h + CTL_OUT + 6, 16);
@@ -949,13 +990,13 @@ bool rc_build_blas(cudaStream_t st, const float *d_verts, const uint32_t *d_face
     const uint32_t nf = n_faces;  // upper bound of the valid count: sizes every array and grid; the live count stays on the device
     const bool keep_bvh2 = build_flags & RC_BUILD_KEEP_BVH2, keep_topo = build_flags & RC_BUILD_ALLOW_REFIT;
     RcTemps tmp(st);
-    const uint32_t f_tiles = cdiv(nf, FILTER_T), s_tiles = cdiv(nf, RS_TILE);
+    const uint32_t f_tiles = cdiv(nf, FT_TILE), s_tiles = cdiv(nf, RS_TILE);
     uint32_t *d_ctl = nullptr;
     RcTri *d_tris_in = nullptr;
     RcBox *d_boxes = nullptr;
     uint32_t *d_codes = nullptr, *d_idx = nullptr, *d_codes2 = nullptr, *d_idx2 = nullptr, *d_hist = nullptr, *d_parent = nullptr;
     RcTopo *d_topo = nullptr;
-    TMP(d_ctl, CTL_WORDS + f_tiles);  // control block + the filter's tile states
+    TMP(d_ctl, CTL_WORDS + f_tiles);  // control block + the filter's per-tile valid counts
     TMP(d_tris_in, nf);
     TMP(d_codes, nf);
     TMP(d_idx, nf);
@@ -981,14 +1022,18 @@ bool rc_build_blas(cudaStream_t st, const float *d_verts, const uint32_t *d_face
     CK(cudaMallocAsync(&out->hull, sizeof(RcBox) * RC_HULL_BOXES, st));
     out->n_faces_in = n_faces;
 
-    CK(cudaMemsetAsync(d_ctl, 0, sizeof(uint32_t) * (CTL_WORDS + f_tiles), st));
-    k_filter<<<f_tiles, FILTER_T, 0, st>>>(d_verts, d_face_meta, n_faces, d_tris_in, d_ctl, d_ctl + CTL_WORDS);
-    k_morton_prims<<<s_tiles, RS_THREADS, 0, st>>>(d_tris_in, d_ctl, d_codes, d_idx, s_tiles, d_hist);
-    uint32_t *codes_sorted = nullptr, *perm = nullptr;
-    radix_sort_pairs(st, d_codes, d_idx, d_codes2, d_idx2, d_ctl + CTL_N, nf, d_hist, true, &codes_sorted, &perm);
+    CK(cudaMemsetAsync(d_ctl, 0, sizeof(uint32_t) * CTL_WORDS, st));
+    FrontArgs fa;
+    fa.verts = d_verts; fa.face_meta = d_face_meta; fa.n_faces = n_faces; fa.tris_in = d_tris_in;
+    fa.tile_counts = d_ctl + CTL_WORDS; fa.ctl = d_ctl;
+    fa.keys0 = d_codes; fa.vals0 = d_idx; fa.keys1 = d_codes2; fa.vals1 = d_idx2;
+    fa.n_host = 0; fa.hist = d_hist; fa.tiles_stride = s_tiles; fa.bar = d_ctl + CTL_BAR;
+    if (!launch_front(st, fa, f_tiles, err)) return false;
+    uint32_t *codes_sorted = d_codes2, *perm = d_idx2;
     k_topology<<<cdiv(std::max(1u, nf - 1), 256), 256, 0, st>>>(codes_sorted, d_ctl + CTL_N, nf, d_topo, d_parent);
     FitWork work = fit_work_at(d_work, nf);
     work.span_count = d_ctl + CTL_NSPAN;  // zeroed with the control block
+    work.err_flag = d_ctl + CTL_ERR;
     FitJob job;
     job.n_bound = nf; job.n_ptr = d_ctl + CTL_N;
     job.tris_in = d_tris_in; job.perm = perm; job.tris = out->tris;
@@ -1059,6 +1104,7 @@ bool rc_refit_blas(cudaStream_t st, const float *d_verts, uint32_t n_faces, RcDe
     CK(cudaMemcpyAsync(d_ctl + CTL_N, &n_word, 4, cudaMemcpyHostToDevice, st));
     FitWork work = fit_work_at(d_work, n);
     work.span_count = d_ctl + CTL_NSPAN;  // zero since the memset of the control block
+    work.err_flag = d_ctl + CTL_ERR;
     FitJob job;
     job.n_bound = n; job.tris = b->tris;
     job.topo = b->topo; job.parent = b->parent; job.boxes = d_boxes; job.nodes2 = b->nodes2;
@@ -1156,12 +1202,25 @@ static bool upload_instances(cudaStream_t st, RcDeviceTlas *t, const rc_instance
     return true;
 }
 
+// read back {invariant flag, root box} (adjacent words of the control block) and finish the host-side record
+static bool finish_tlas(cudaStream_t st, RcDeviceTlas *t, std::string &err) {
+    uint32_t h[7];
+    static_assert(CTL_ERR + 1 == CTL_OUT, "one transfer");
+    CK(cudaMemcpyAsync(h, t->d_small + CTL_ERR, sizeof h, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    if (h[0]) { err = "internal error: fit segment table overflow"; return false; }
+    memcpy(t->root_aabb, h + 1, 24);
+    return extent_supported(t->root_aabb, err);
+}
+
 // The two fits of a TLAS over one topology: the reference-identical instance boxes give the BVH2 (read-backs, reference-order mode) and the
 // root box; the tighter hull-derived boxes give the wide nodes.  The spanning-node list depends on the topology only: built by the first
 // fit after a (re)build (its counter, t->d_small[CTL_NSPAN], is zero then) and reused by every later fit.
 static void fit_tlas(cudaStream_t st, RcDeviceTlas *t, bool fresh_topology) {
     FitWork work = fit_work_at(t->fit_work, t->n);
     work.span_count = t->d_small + CTL_NSPAN;
+    work.err_flag = t->d_small + CTL_ERR;
     FitJob ref;
     ref.n_bound = t->n; ref.inst_boxes = t->inst_boxes; ref.leaf_map = t->leaf_map;
     ref.topo = t->topo; ref.parent = t->parent; ref.boxes = t->boxes; ref.nodes2 = t->nodes2;
@@ -1211,15 +1270,16 @@ bool rc_build_tlas(cudaStream_t st, const rc_instance_desc *h_inst, uint32_t n, 
     CK(cudaMemsetAsync(t->d_small, 0, sizeof(uint32_t) * CTL_WORDS, st));
     k_instance_boxes<<<cdiv(n, T), T, 0, st>>>(t->d_inst, t->d_blas_roots, n, t->inst_boxes, t->d_small, t->d_blas_ptrs, t->inst_boxes_tight);
     k_morton_instances<<<cdiv(n, T), T, 0, st>>>(t->d_inst, t->d_blas_roots, n, t->d_small, d_codes, d_idx);
-    uint32_t *codes_sorted = nullptr, *order = nullptr;
-    radix_sort_pairs(st, d_codes, d_idx, d_codes2, d_idx2, nullptr, n, d_hist, false, &codes_sorted, &order);
+    FrontArgs fa;
+    fa.verts = nullptr; fa.face_meta = nullptr; fa.n_faces = 0; fa.tris_in = nullptr; fa.tile_counts = nullptr; fa.ctl = t->d_small;
+    fa.keys0 = d_codes; fa.vals0 = d_idx; fa.keys1 = d_codes2; fa.vals1 = d_idx2;
+    fa.n_host = n; fa.hist = d_hist; fa.tiles_stride = cdiv(n, RS_TILE); fa.bar = t->d_small + CTL_BAR;
+    if (!launch_front(st, fa, cdiv(n, RS_TILE), err)) return false;
+    uint32_t *codes_sorted = d_codes2, *order = d_idx2;
     CK(cudaMemcpyAsync(t->leaf_map, order, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, st));  // leaf_map = sorted position -> instance index
     k_topology<<<cdiv(std::max(1u, n - 1), T), T, 0, st>>>(codes_sorted, nullptr, n, t->topo, t->parent);
     fit_tlas(st, t, true);
-    CK(cudaMemcpyAsync(t->root_aabb, t->d_small + CTL_OUT, 24, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    CK(cudaGetLastError());
-    return extent_supported(t->root_aabb, err);
+    return finish_tlas(st, t, err);
 }
 
 bool rc_refit_tlas(cudaStream_t st, const rc_instance_desc *h_inst, uint32_t n, RcDeviceTlas *t, std::string &err) {
@@ -1229,10 +1289,7 @@ bool rc_refit_tlas(cudaStream_t st, const rc_instance_desc *h_inst, uint32_t n, 
     // update_tlas_leaf_aabbs_kernel! (kernels.jl:487-519) + refit_tlas_aabbs_kernel! (:381-428), then re-quantise the wide nodes
     k_instance_boxes<<<cdiv(n, 256), 256, 0, st>>>(t->d_inst, t->d_blas_roots, n, t->inst_boxes, nullptr, t->d_blas_ptrs, t->inst_boxes_tight);
     fit_tlas(st, t, false);
-    CK(cudaMemcpyAsync(t->root_aabb, t->d_small + CTL_OUT, 24, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    CK(cudaGetLastError());
-    return extent_supported(t->root_aabb, err);
+    return finish_tlas(st, t, err);
 }
 
 // =================================================================================================

@@ -16,4 +16,4 @@ for o in rc_api rc_build rc_trace rc_analysis rc_collide rc_wavefront rc_multi; 
   if [ $o = $src ]; then objs="$objs $out/$o.o"; else objs="$objs $o.o"; fi
 done
 $NVCC -shared $ARCH -o $out/libraycore_cuda.so $objs
-[ $src = rc_trace ] && echo "$name: $(grep -A2 'k_trace_wideILb0ELb0E10RcIoArraysLb0' $out/rc_trace.ptxas.log | grep -o 'Used [0-9]* registers\|[0-9]* bytes spill stores' | tr '\n' ' ')"
+[ $src != rc_trace ] || echo "$name: $(grep -A2 'k_trace_wideILb0ELb0E10RcIoArraysLb0' $out/rc_trace.ptxas.log | grep -o 'Used [0-9]* registers\|[0-9]* bytes spill stores' | tr '\n' ' ')"
