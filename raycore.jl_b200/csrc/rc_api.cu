@@ -338,6 +338,13 @@ int32_t rc_update_transforms_device(rc_context *ctx, uint32_t handle, const floa
     if (!ctx) return RC_ERR_INVALID_ARGUMENT;
     RC_ENTER(ctx);
     if (!d_transforms) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "rc_update_transforms_device: transforms is NULL");
+    {   // validate before touching the caller's buffer (a wrong count must not read 48 * m bytes of it)
+        HandleInfo *hi = nullptr;
+        int32_t rc = find_handle(ctx, handle, &hi);
+        if (rc != RC_OK) return rc;
+        if (m != hi->count)
+            RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "Transform count (" + std::to_string(m) + ") != instance count (" + std::to_string(hi->count) + ")");
+    }
     std::vector<float> xf(12 * (size_t)m), inv(d_inv_transforms ? 12 * (size_t)m : 0);
     if (m) {
         RC_CUDA(ctx, cudaMemcpyAsync(xf.data(), d_transforms, xf.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
@@ -474,6 +481,36 @@ static void compact_instances(rc_context *ctx) {
     ctx->instances.swap(ni);
 }
 
+// L2 residency hint (experiment switch, off by default: profiles/README.md r2 has the measurement).  RC_L2_PERSIST=1: the wide nodes of the
+// largest geometry are marked persisting for the kernels of the context's stream (cudaAccessPolicyWindow; the ray / hit streams are
+// already evict-first), up to the device's persisting-L2 carve-out.  Meant for one large mesh (C2: 64 MB of wide nodes share the 126 MB
+// L2 with a 1 GiB ray / hit stream); an instanced scene's working set is a few MB and stays resident anyway.
+static void configure_l2_window(rc_context *ctx) {
+    static const int mode = [] { const char *e = getenv("RC_L2_PERSIST"); return e ? atoi(e) : 0; }();
+    if (!mode) return;
+    cudaStreamAttrValue v;
+    memset(&v, 0, sizeof v);
+    const RcDeviceBlas *big = nullptr;
+    for (const RcDeviceBlas &B : ctx->blas)
+        if (B.nodes4 && (!big || B.n > big->n)) big = &B;
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+    if (big && max_persist > 0 && max_window > 0) {
+        const size_t bytes = sizeof(RcNode4) * ((size_t)big->n + 1), window = bytes < (size_t)max_window ? bytes : (size_t)max_window;
+        const size_t carve = window < (size_t)max_persist ? window : (size_t)max_persist;
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+        v.accessPolicyWindow.base_ptr = (void *)big->nodes4;
+        v.accessPolicyWindow.num_bytes = window;
+        v.accessPolicyWindow.hitRatio = mode == 2 ? 0.6f : (float)((double)carve / (double)window);
+        v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        if (getenv("RC_L2_PERSIST_VERBOSE")) fprintf(stderr, "rc: L2 window %zu B, carve-out %zu B (max %d), hit ratio %.2f\n", window, carve, max_persist, v.accessPolicyWindow.hitRatio);
+    }
+    cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &v);
+    cudaGetLastError();
+}
+
 static int32_t rebuild(rc_context *ctx) {  // rebuild_bvh! :962-993 + build_flat_blas_arrays! :470-517 + rebuild_static_tlas! :930-959
     bool any_deleted = false;
     for (auto &kv : ctx->handles) any_deleted |= kv.second.deleted;
@@ -508,6 +545,7 @@ static int32_t rebuild(rc_context *ctx) {  // rebuild_bvh! :962-993 + build_flat
     ctx->transforms_dirty = false;
     ctx->built = true;
     ctx->vf_map_built = false;
+    configure_l2_window(ctx);
     return RC_OK;
 }
 

@@ -7,6 +7,8 @@ host simulation of the device code and the CUDA path are all checked against the
 three that alters a single bit of a hit record shows up without the other two.
 
     python tests/golden/make_golden.py          # rewrites the fixtures (deterministic)
+    python tests/golden/make_golden.py --export-inputs DIR   # scenes + rays as <scene>_inputs.npz for tests/golden/make_ref_golden.jl
+                                                              # (the real Raycore.jl, where Julia is available -> tests/golden/ref_<scene>.npz)
 """
 import hashlib
 import os
@@ -51,7 +53,24 @@ def digest(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
+def export_inputs(outdir):
+    os.makedirs(outdir, exist_ok=True)
+    for name, (pushes, rays) in scenes().items():
+        d = {"n_pushes": np.array([len(pushes)], np.int64), "rays": np.ascontiguousarray(rays).view(np.float32).reshape(len(rays), 8)}
+        for k, (verts, meta, xf, ids) in enumerate(pushes):
+            d[f"verts_{k}"] = np.ascontiguousarray(verts, np.float32).reshape(-1, 9)
+            d[f"xf_{k}"] = np.ascontiguousarray(xf, np.float32).reshape(-1, 12)
+            if meta is not None:
+                d[f"meta_{k}"] = np.ascontiguousarray(meta, np.uint32)
+            if ids is not None:
+                d[f"ids_{k}"] = np.ascontiguousarray(ids, np.uint32)
+        np.savez(os.path.join(outdir, name + "_inputs.npz"), **d)
+        print("wrote", name + "_inputs.npz")
+
+
 def main():
+    if "--export-inputs" in sys.argv:
+        return export_inputs(sys.argv[sys.argv.index("--export-inputs") + 1])
     import engines
 
     for name, (pushes, rays) in scenes().items():

@@ -67,7 +67,7 @@ def _check_properties(g, o, rays, label, sample=1 << 17, max_tie_frac=2e-3):
     sm = rs.choice(len(rays), sample, replace=False)
     b = o.trace(rays[sm])
     cls = parity.classify(a[sm], b, parity.make_graze_verifier(orc, rays[sm], a[sm], o.instances, o.tris))
-    parity.assert_parity(cls, len(sm), max_tie_frac=max_tie_frac, label=label)
+    parity.assert_parity(cls, len(sm), max_tie_frac=max_tie_frac, label=label, max_graze=0, max_nan=0)  # BASELINE configs: the measured zeros
     return a
 
 

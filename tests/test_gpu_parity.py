@@ -110,7 +110,7 @@ def test_readme_sphere_c1():
     rays = W.pinhole_rays(1024, 1024, camera_pos=(0, 0, 0))
     a, b = g.trace(rays), o.trace(rays)
     cls = parity.classify(a, b, parity.make_graze_verifier(orc, rays, a, o.instances, o.tris))
-    s = parity.assert_parity(cls, len(rays), label="README sphere")
+    s = parity.assert_parity(cls, len(rays), label="README sphere", max_graze=0, max_nan=0)  # C1 of BASELINE.json: the measured zeros
     assert b["hit"].mean() > 0.1 and s["exact"] >= 0.999 * len(rays)
 
 

@@ -8,16 +8,17 @@ mkdir -p "$out"
 export PYTHONUNBUFFERED=1
 san=/usr/local/cuda/bin/compute-sanitizer
 tests="tests/test_gpu_fuzz.py tests/test_gpu_refit.py tests/test_gpu_lifecycle.py tests/test_watertight.py"
-for tool in memcheck racecheck synccheck initcheck; do
+for tool in ${TOOLS:-memcheck racecheck synccheck initcheck}; do
   extra=""
-  [ "$tool" = racecheck ] && extra="--racecheck-report all --print-limit 200000"
+  limit=50
+  [ "$tool" = racecheck ] && extra="--racecheck-report all" && limit=200000
   log="$out/${tool}_smoke.log"
-  timeout 300 $san --tool $tool $extra --error-exitcode 99 --print-limit 50 python __graft_entry__.py smoke > "$log" 2>&1
+  timeout 300 $san --tool $tool $extra --error-exitcode 99 --print-limit $limit python __graft_entry__.py smoke > "$log" 2>&1
   echo "$tool smoke rc=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|LEAK SUMMARY' "$log" | tr '\n' ' ')" | tee -a "$out/summary.txt"
   log="$out/${tool}_tests.log"
   sel="not two_ranks"
   [ "$tool" = racecheck ] && sel="test_random_scene_parity and (0 or 4 or 8) or refit or watertight"   # racecheck is ~100x slower: a subset
-  timeout 900 $san --tool $tool $extra --error-exitcode 99 --print-limit 50 python -m pytest $tests -m gpu -q -x -k "$sel" > "$log" 2>&1
+  timeout 900 $san --tool $tool $extra --error-exitcode 99 --print-limit $limit python -m pytest $tests -m gpu -q -x -k "$sel" > "$log" 2>&1
   echo "$tool tests rc=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|LEAK SUMMARY| passed| failed' "$log" | tr '\n' ' ')" | tee -a "$out/summary.txt"
   if [ "$tool" = racecheck ]; then   # hazards per kernel and source line (the full logs are large: only this digest is kept)
     for f in "$out/racecheck_smoke.log" "$out/racecheck_tests.log"; do
