@@ -1178,7 +1178,8 @@ __global__ void k_instance_records(const rc_instance_desc *__restrict__ inst, co
     for (int k = 0; k < 12; k++) r.inv[k] = d->inv_transform[k];
     r.nodes4 = b.nodes4;
     r.tris = b.tris;
-    for (int k = 0; k < 4; k++) { r.sphere[k] = b.sphere[k]; r.pad[k] = 0.f; }
+    for (int k = 0; k < 4; k++) r.sphere[k] = b.sphere[k];
+    rc_world_sphere(d->transform, b.sphere, r.wsphere);
     rec[i] = r;
     RcInstanceAux a;
     a.nodes2 = b.nodes2;

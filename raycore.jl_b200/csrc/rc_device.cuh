@@ -244,6 +244,24 @@ RC_HD void x_intersect_bbox(f3 o, f3 inv, f3 pmin, f3 pmax, float t_min, float t
     out_min = jl_max(jl_max(jl_max(mnx, mny), mnz), t_min);
 }
 
+// World-space bounding sphere of an instance: the BLAS's local sphere (centre, radius^2) under the local->world transform xf (Mat3x4f rows).
+// The radius grows by at most the largest singular value of the 3x3 part; its square is bounded by the infinity norm of M^T M (exact for
+// rotation x uniform scale, conservative otherwise), with 1e-5 of head-room for the float evaluation.  radius^2 = +Inf (no cull) survives.
+RC_HD void rc_world_sphere(const float *xf, const float *sphere, float *out) {
+    const f3 c = x_transform_point(xf, mk3(sphere[0], sphere[1], sphere[2]));
+    float g[3][3];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) g[i][j] = xf[i] * xf[j] + xf[4 + i] * xf[4 + j] + xf[8 + i] * xf[8 + j];  // column i . column j
+    float s = 0.0f;
+    for (int i = 0; i < 3; i++) {
+        const float row = fabsf(g[i][0]) + fabsf(g[i][1]) + fabsf(g[i][2]);
+        s = row > s ? row : s;
+    }
+    out[0] = c.x; out[1] = c.y; out[2] = c.z;
+    const float r2 = sphere[3] * s * 1.00001f;
+    out[3] = (r2 == r2) ? r2 : INFINITY;  // 0 * Inf, NaN transforms: no cull
+}
+
 // expand_bits / morton_code_30bit, src/instanced-bvh.jl:1177-1200
 RC_HD uint32_t rc_expand_bits(uint32_t x) {
     x = (x * 0x00010001u) & 0xFF0000FFu;

@@ -89,6 +89,9 @@ __device__ __forceinline__ void rc_store_hit(rc_hit *hits, unsigned long long i,
 #ifndef RC_PARK_INSTANCE
 #define RC_PARK_INSTANCE 0
 #endif
+#ifndef RC_WINV_SMEM
+#define RC_WINV_SMEM 1  // C3: 9.58 -> 9.49 ms per 2^24 rays (profiles/README.md r2)
+#endif
 #ifndef RC_MIN_BLOCKS
 #define RC_MIN_BLOCKS 8     // 64 registers -> 32 resident warps per SM (swept 6..10 in r1: 8 is best, 9+ spills)
 #endif
@@ -111,6 +114,17 @@ __device__ __forceinline__ void rc_store_hit(rc_hit *hits, unsigned long long i,
 // subnormal inputs, so the single-instruction .ftz form gives the same bits unless a component exceeds 2^126 (subnormal result),
 // which takes the full form behind one warp-rarely-taken branch.  (The three reciprocals of a level change were 14 % of the
 // instanced kernel's warp instructions at 4/32 lanes, profiles/r1_trace_c3_v20.)
+#ifndef RC_WARPSIM
+// cold path of rc_fast_inv3, out of line: kept as a call so that the hot path carries neither its ~100 instructions nor the register
+// moves of a two-sided join (they were 4.8 % of the instanced kernel's warp instructions at 5/32 lanes, profiles/r2_trace_c3_final)
+static __device__ __noinline__ f3 rc_slow_inv3(float x, float y, float z) {
+    f3 r;
+    asm("rcp.approx.f32 %0, %1;" : "=f"(r.x) : "f"(x));
+    asm("rcp.approx.f32 %0, %1;" : "=f"(r.y) : "f"(y));
+    asm("rcp.approx.f32 %0, %1;" : "=f"(r.z) : "f"(z));
+    return r;
+}
+#endif
 __device__ __forceinline__ f3 rc_fast_inv3(f3 d) {
     const float ooeps = 1.0e-5f;
     const float x = fabsf(d.x) > ooeps ? d.x : copysignf(ooeps, d.x);
@@ -120,15 +134,10 @@ __device__ __forceinline__ f3 rc_fast_inv3(f3 d) {
 #ifdef RC_WARPSIM
     r.x = 1.0f / x; r.y = 1.0f / y; r.z = 1.0f / z;  // host stand-in for MUFU.RCP (<= 1 ulp apart; only the conservative box test sees it)
 #else
-    if (fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z)) > 8.5070591730234616e37f) {  // 2^126: 1/x would be subnormal
-        asm("rcp.approx.f32 %0, %1;" : "=f"(r.x) : "f"(x));
-        asm("rcp.approx.f32 %0, %1;" : "=f"(r.y) : "f"(y));
-        asm("rcp.approx.f32 %0, %1;" : "=f"(r.z) : "f"(z));
-    } else {
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(x));
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(y));
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.z) : "f"(z));
-    }
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(y));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.z) : "f"(z));
+    if (__builtin_expect(fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z)) > 8.5070591730234616e37f, 0)) r = rc_slow_inv3(x, y, z);  // 2^126: 1/x is subnormal
 #endif
     return r;
 }
@@ -201,6 +210,16 @@ __device__ __forceinline__ bool rc_misses_sphere(f3 o, f3 d, float4 sph, float t
     // the line misses the sphere, or the origin is outside and the closest approach lies behind it (b > 0: moving away)
     return l2 > r2s || (oc2 > r2s && b > 0.0f);
 }
+// the same test without the "behind the origin" clause (cheaper; the box test has already dealt with most of those)
+__device__ __forceinline__ bool rc_line_misses_sphere(f3 o, f3 d, float4 sph) {
+    const float ocx = o.x - sph.x, ocy = o.y - sph.y, ocz = o.z - sph.z;
+    const float a = fmaf(d.x, d.x, fmaf(d.y, d.y, d.z * d.z));
+    const float b = fmaf(ocx, d.x, fmaf(ocy, d.y, ocz * d.z));
+    const float oc2 = fmaf(ocx, ocx, fmaf(ocy, ocy, ocz * ocz));
+    const float s = __fdividef(b, a);
+    const float lx = fmaf(-s, d.x, ocx), ly = fmaf(-s, d.y, ocy), lz = fmaf(-s, d.z, ocz);
+    return fmaf(lx, lx, fmaf(ly, ly, lz * lz)) > fmaf(1.1e-6f, sph.w + oc2, sph.w);
+}
 
 // Ray source / hit sink of the batched entry points: RTRay array in, RTHitResult array out.
 struct RcIoArrays {
@@ -226,7 +245,8 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, SINGLE ? RC_MIN_BLOCKS_SINGL
                                                                  unsigned long long *__restrict__ work, RcCounters *__restrict__ counters,
                                                                  uint32_t *__restrict__ overflow) {
     // rows: 0 guard (always RC_INVALID), 1..RC_SSTACK live entries, +4 scratch (<= 3 pushes past the limit before the overflow check, + 1 rejected store)
-    __shared__ uint32_t sstack[(RC_SSTACK + 5) * RC_TRACE_THREADS];
+    // (+3 rows with RC_WINV_SMEM: the world ray's reciprocal direction, so the return to the top level reloads it instead of recomputing it)
+    __shared__ uint32_t sstack[(RC_SSTACK + 5 + (RC_WINV_SMEM && !SINGLE ? 3 : 0)) * RC_TRACE_THREADS];
     const uint32_t FULL = 0xFFFFFFFFu;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, lt_mask = (1u << lane) - 1u;
     RcLocalCounters lc = {0, 0, 0, 0, 0};
@@ -273,13 +293,39 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, SINGLE ? RC_MIN_BLOCKS_SINGL
         cur = RC_TOP();                                                                   \
         spa -= RC_ROW;                                                                    \
         o = wo; d = wd;                                                                   \
-        inv = rc_fast_inv3(d);                  \
+        if (RC_WINV_SMEM) {                                                               \
+            inv.x = __uint_as_float(sbase[(RC_SSTACK + 5) * RC_ROW]);                     \
+            inv.y = __uint_as_float(sbase[(RC_SSTACK + 6) * RC_ROW]);                     \
+            inv.z = __uint_as_float(sbase[(RC_SSTACK + 7) * RC_ROW]);                     \
+        } else {                                                                          \
+            inv = rc_fast_inv3(d);                                                        \
+        }                                                                                 \
+    }
+    // RC_WORLD_CULL (experiment, off): a lane that has just reached an instance leaf tests the ray against the instance's WORLD-space
+    // bounding sphere right here in the settle (one 16-byte load, ~20 instructions, no transform).  On the instanced scene C3 three of four
+    // instance leaves are culled that way, level steps drop from 16.5 to 6.7 per 32 rays and the CPU model predicts -6.9 % — but the test
+    // then runs, a few lanes wide, in the settle of almost every top-level node step, and the B200 measures +7 % (9.57 -> 10.24 ms per 2^24
+    // rays, results CRC-identical; profiles/README.md r2).  The level step's own local-space sphere test stays.
+#ifndef RC_WORLD_CULL
+#define RC_WORLD_CULL 0
+#endif
+#ifndef RC_WCULL_LINE_ONLY
+#define RC_WCULL_LINE_ONLY 0
+#endif
+#define RC_SETTLE_WCULL()                                                                                          \
+    if (!SINGLE && RC_WORLD_CULL && cur_inst < 0 && (cur + 0x40000000u) < 0x2FFFFFFFu) {                           \
+        const float4 ws_ = __ldg(reinterpret_cast<const float4 *>(reinterpret_cast<const char *>(sc.inst + (cur & RC_LEAF_START_MASK)) + 80)); \
+        if (RC_WCULL_LINE_ONLY ? rc_line_misses_sphere(o, d, ws_) : rc_misses_sphere(o, d, ws_, t_max)) {         \
+            cur = RC_TOP();                                                                                        \
+            spa -= RC_ROW;                                                                                         \
+        }                                                                                                          \
     }
     // after a step: park a freshly reached BLAS leaf (so the lane can keep descending) and recompute the lane's vote
 #define RC_SETTLE()                                                                                                \
     {                                                                                                              \
         RC_SETTLE_LEAVE()                                                                                          \
         if (spa > sbase + RC_SSTACK * RC_ROW) { ovf = true; cur = RC_INVALID; leaf = 0; spa = sbase; RC_CLEAR_PINST() } \
+        RC_SETTLE_WCULL()                                                                                          \
         const bool park_ = ((cur ^ RC_LEAF_BIT) < 0x40000000u) && leaf == 0; /* BLAS leaf reference */              \
         const uint32_t top_ = RC_TOP();                                                                            \
         leaf = park_ ? cur : leaf;                                                                                 \
@@ -388,6 +434,11 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, SINGLE ? RC_MIN_BLOCKS_SINGL
                     } else {
                         o = wo; d = wd;
                         inv = rc_fast_inv3(d);
+                        if (RC_WINV_SMEM) {
+                            sbase[(RC_SSTACK + 5) * RC_ROW] = __float_as_uint(inv.x);
+                            sbase[(RC_SSTACK + 6) * RC_ROW] = __float_as_uint(inv.y);
+                            sbase[(RC_SSTACK + 7) * RC_ROW] = __float_as_uint(inv.z);
+                        }
                         cur_inst = -1;
                         nodes = sc.tlas4;
                     }
@@ -510,6 +561,7 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, SINGLE ? RC_MIN_BLOCKS_SINGL
 #undef RC_SETTLE_VOTE
 #undef RC_CLEAR_PINST
 #undef RC_SETTLE_LEAVE
+#undef RC_SETTLE_WCULL
 #undef RC_ENTER_INSTANCE
     if (COUNT) {
         atomicAdd(&counters->rays, traced);

@@ -59,7 +59,8 @@ struct __attribute__((aligned(32))) RcInstanceRec {
     const RcNode4 *nodes4;   // BLAS wide nodes (root = index 1)
     const RcTri *tris;
     float sphere[4];         // centre xyz, radius^2 (conservative: every vertex lies inside); radius^2 = +Inf disables the test
-    float pad[4];
+    float wsphere[4];        // the same sphere in world space (centre, radius^2 scaled by the transform's largest stretch, rc_world_sphere): only read by the
+                             // RC_WORLD_CULL experiment of rc_trace_fast.cuh (cull in the settle, before any transform is fetched; measured slower, off)
 };
 
 // Cold per-instance data (hit write-back and the reference-order path)

@@ -210,6 +210,7 @@ void *hs_scene_build(void **blas, uint32_t n_blas, const rc_instance_desc *inst,
         S->rec[i].nodes4 = B->tree.nodes4.data();
         S->rec[i].tris = B->tris.data();
         memcpy(S->rec[i].sphere, B->sphere, 16);
+        rc_world_sphere(inst[i].transform, B->sphere, S->rec[i].wsphere);
         S->aux[i].nodes2 = B->tree.nodes2.data();
         S->aux[i].n_prims = B->tree.n;
         S->aux[i].custom_index = inst[i].instance_id;
