@@ -392,9 +392,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.gather == "auto":
-        # measured on the 8 x B200 box (profiles/r1_scaling.md): in-kernel remote stores are free up to 4 ranks; at 8 ranks the 32-byte
-        # stores of 7 senders load rank 0's NVLink ingress, so the copy engines push whole buffers while the next step traces
-        args.gather = "fused" if world <= 4 else "peer-copy"
+        # measured on this workload (profiles/r2_scaling.md, C3 strong scaling): the copy engines pushing whole double-buffered hit
+        # buffers while the next step traces beat the traversal kernel's own remote stores at every N (2 GPUs 3.49 vs 3.30, 4 GPUs
+        # 6.94 vs 6.55 Grays/s: the 32-byte NVLink stores cost the issue-bound kernel 6 %); `--gather fused` keeps the in-kernel path
+        args.gather = "peer-copy"
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)

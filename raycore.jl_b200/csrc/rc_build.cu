@@ -582,7 +582,7 @@ __device__ __forceinline__ RcBox box_from6(const float *b) {
 }
 // build_list: append this block's spanning nodes to work.span_list (skipped when a list of the same topology is already there)
 // nodes4 != null: collapse the in-block nodes into their wide nodes here (leaf_max, leaf_map as in rc_collapse_node)
-__global__ void __launch_bounds__(FIT_T) k_fit_local(const RcTri *__restrict__ tris_in, const uint32_t *__restrict__ perm, RcTri *__restrict__ tris,
+__global__ void __launch_bounds__(FIT_T, FIT_T <= 512 ? 3 : 1) k_fit_local(const RcTri *__restrict__ tris_in, const uint32_t *__restrict__ perm, RcTri *__restrict__ tris,
                                                      const RcBox *__restrict__ inst_boxes, const uint32_t *__restrict__ leaf_map, const uint32_t *__restrict__ n_ptr,
                                                      uint32_t n_host, const RcTopo *__restrict__ topo, const uint32_t *__restrict__ parent, RcBox *__restrict__ boxes,
                                                      RcNode2 *__restrict__ nodes2, uint32_t *__restrict__ ctl, FitWork work, bool build_list, RcNode4 *__restrict__ nodes4,

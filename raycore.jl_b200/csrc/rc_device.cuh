@@ -81,15 +81,30 @@ RC_HD float x_sqrt(float a) { return sqrtf(a); }
 #endif
 
 // Julia min/max on Float32 (base/math.jl): NaN-propagating, -0 < +0.
+// On the device this is exactly PTX min.NaN.f32 / max.NaN.f32 (one FMNMX): NaN in -> canonical NaN out (what x - y gives for a NaN input
+// on the GPU as well), -0 orders below +0, equal inputs return their common value.  The portable form below is what the host simulation
+// and the oracle's restatement evaluate; the byte-exact BVH2 / hit-record tests compare the two.
 RC_HD float jl_min(float x, float y) {
+#if RC_ON_DEVICE
+    float r;
+    asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(y));
+    return r;
+#else
     float diff = x_sub(x, y);
     float arg = rc_signbit(diff) ? x : y;
     return (rc_isnan(x) || rc_isnan(y)) ? diff : arg;
+#endif
 }
 RC_HD float jl_max(float x, float y) {
+#if RC_ON_DEVICE
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(y));
+    return r;
+#else
     float diff = x_sub(x, y);
     float arg = rc_signbit(diff) ? y : x;
     return (rc_isnan(x) || rc_isnan(y)) ? diff : arg;
+#endif
 }
 
 RC_HD f3 x_sub3(f3 a, f3 b) { return mk3(x_sub(a.x, b.x), x_sub(a.y, b.y), x_sub(a.z, b.z)); }

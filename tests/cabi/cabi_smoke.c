@@ -1,6 +1,7 @@
 /* Pure-C driver of the drop-in boundary (include/raycore_cuda.h): no Python, no torch — what a cgo / ccall / JNI binding sees.
  * Mirrors test/test_instanced_bvh.jl:283-301 (a quad with metadata 42 hit at t = 1, a miss beside it) plus a two-instance push,
- * a transform update (refit) and an any-hit query.  Exit code 0 = all checks passed. */
+ * a transform update (refit), an any-hit query, the watertight mode, a vertex-update refit and the BLAS4 entry points.
+ * Exit code 0 = all checks passed. */
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -72,6 +73,51 @@ int main(void) {
         free(blob);
         CHECK(rc_destroy(ctx2) == RC_OK);
         CHECK(same && refused);
+    }
+
+    /* watertight mode (the reference's intersect_triangle, src/triangle_mesh.jl:168-201): a ray through the quad's shared diagonal hits */
+    {
+        rc_ray diag = {{0.5f, 0.5f, 1.0f}, 0.0f, {0, 0, -1}, INFINITY};
+        rc_hit hd;
+        CHECK(rc_trace_closest(ctx, &diag, &hd, 1, RC_MODE_WATERTIGHT) == RC_OK && hd.hit == 1 && fabsf(hd.t - 1.0f) < 1e-6f);
+        CHECK(rc_trace_any(ctx, &diag, &hd, 1, RC_MODE_WATERTIGHT) == RC_OK && hd.hit == 1);
+    }
+
+    /* vertex update as a refit (update!, src/instanced-bvh.jl:808-857): the geometry was built with RC_BUILD_ALLOW_REFIT, the quad moves to
+     * z = -1 with the same faces => the kept radix tree is re-fitted, no rebuild of the BLAS */
+    {
+        rc_context *c3 = NULL;
+        CHECK(rc_create(-1, &c3) == RC_OK && rc_set_build_flags(c3, RC_BUILD_ALLOW_REFIT) == RC_OK);
+        uint32_t h3 = 0;
+        CHECK(rc_push(c3, quad, 2, meta, xf, NULL, NULL, 1, 0, &h3) == RC_OK && rc_sync(c3, &action) == RC_OK);
+        float moved[18];
+        memcpy(moved, quad, sizeof quad);
+        for (int k = 2; k < 18; k += 3) moved[k] = -1.0f;
+        int ok = rc_update_geometry(c3, h3, moved, 2, meta, RC_UPDATE_REFIT) == RC_OK && rc_last_update_refitted(c3) == 1 &&
+                 rc_sync(c3, &action) == RC_OK && rc_trace_closest(c3, rays, hits, 1, 0) == RC_OK && hits[0].hit == 1 &&
+                 fabsf(hits[0].t - 2.0f) < 1e-6f;
+        CHECK(rc_destroy(c3) == RC_OK);
+        CHECK(ok);
+        CHECK(rc_trace_closest(ctx, rays, hits, 3, 0) == RC_OK); /* (restore hits[] for the checks below) */
+    }
+
+    /* BLAS4 / build_blas4 / closest_hit4 / any_hit4 (src/bvh4.jl:511-766): one geometry on its own wide BVH, ray.tmin ignored (:610) */
+    {
+        rc_blas4 *b4 = NULL;
+        CHECK(rc_blas4_build(-1, quad, 2, meta, 0, &b4) == RC_OK);
+        uint32_t n_prims = 0, n_slots = 0;
+        float box[6];
+        CHECK(rc_blas4_info(b4, &n_prims, &n_slots, box) == RC_OK && n_prims == 2 && n_slots == 3 && box[0] == -1.0f && box[3] == 1.0f);
+        rc_ray r4 = {{0.25f, 0.25f, 1.0f}, 5.0f /* tmin beyond the hit: ignored */, {0, 0, -1}, INFINITY};
+        rc_hit h4;
+        CHECK(rc_blas4_trace_closest(b4, &r4, &h4, 1, 0) == RC_OK && h4.hit == 1 && fabsf(h4.t - 1.0f) < 1e-6f && h4.metadata == 42);
+        CHECK(rc_blas4_trace_any(b4, &r4, &h4, 1, 0) == RC_OK && h4.hit == 1);
+        rc_wide_node nodes[3];
+        CHECK(rc_blas4_read_nodes(b4, nodes, 3) == RC_OK && (nodes[1].child01[0] & 0x80000000u) != 0u); /* the root's first child is a leaf */
+        rc_blas4 *none = NULL;
+        const float flat[9] = {0, 0, 0, 1, 1, 1, 2, 2, 2}; /* degenerate: "Cannot build BLAS4 from empty primitive list" (:513) */
+        CHECK(rc_blas4_build(-1, flat, 1, NULL, 0, &none) == RC_ERR_NO_VALID_TRIANGLES && none == NULL);
+        CHECK(rc_blas4_destroy(b4) == RC_OK);
     }
 
     /* error behaviour of the handle API (src/instanced-bvh.jl:715-718) */

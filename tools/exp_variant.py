@@ -19,13 +19,13 @@ from raycore_b200 import workloads as W  # noqa: E402
 L = rc._lib
 
 
-def dev_trace(tlas, d_r, n, any_hit=False, reps=7):
+def dev_trace(tlas, d_r, n, any_hit=False, reps=7, extra_flags=0):
     lib, ctx = tlas._lib, tlas._ctx
     d_h = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
     fn = lib.rc_trace_any if any_hit else lib.rc_trace_closest
     ms = []
     for _ in range(reps + 2):
-        assert fn(ctx, d_r.data_ptr(), d_h.data_ptr(), n, L.RC_RAYS_ON_DEVICE | L.RC_HITS_ON_DEVICE) == 0, lib.rc_last_error(ctx)
+        assert fn(ctx, d_r.data_ptr(), d_h.data_ptr(), n, L.RC_RAYS_ON_DEVICE | L.RC_HITS_ON_DEVICE | extra_flags) == 0, lib.rc_last_error(ctx)
         ms.append(lib.rc_last_kernel_ms(ctx))
     return sorted(ms[2:])[len(ms[2:]) // 2], zlib.crc32(d_h.cpu().numpy().tobytes())
 
@@ -69,6 +69,9 @@ def main():
     out["closest_ms"], out["closest_crc"] = dev_trace(tl, d_r, n)
     out["any_ms"], out["any_crc"] = dev_trace(tl, d_r, n, any_hit=True)
     out["closest_Mrays_s"] = n / out["closest_ms"] / 1e3
+    if "--watertight" in sys.argv:  # the same launches with RC_MODE_WATERTIGHT (hit / miss can differ at edges: no CRC comparison with the default)
+        out["wt_closest_ms"], _ = dev_trace(tl, d_r, n, extra_flags=L.RC_MODE_WATERTIGHT)
+        out["wt_any_ms"], _ = dev_trace(tl, d_r, n, any_hit=True, extra_flags=L.RC_MODE_WATERTIGHT)
     print(json.dumps(out))
 
 
