@@ -550,20 +550,22 @@ struct FitSeg {  // 64 B; the table of a block is sorted by position, entry 0 st
 static_assert(sizeof(FitSeg) == 64, "segment table entry");
 struct FitWork {  // per-fit scratch: segment tables [blocks][FIT_SEG_MAX], spanning-node list [blocks * FIT_SEG_MAX] of (node, span_lo, span_hi, -), its length
     FitSeg *seg;
+    unsigned char *pos_idx;  // per sorted position: rank (in its block's table) of the segment that starts or ends there, 0xFF = none
     uint4 *span_list;
     uint32_t *span_count;
     uint32_t *err_flag;  // set when a block found more than FIT_SEG_MAX segments (impossible for a radix tree; checked by the host, never silent)
 };
 static size_t fit_work_bytes(uint32_t n_bound) {
     const size_t blocks = cdiv(n_bound, FIT_T);
-    return blocks * FIT_SEG_MAX * (sizeof(FitSeg) + sizeof(uint4)) + 64;
+    return blocks * FIT_SEG_MAX * (sizeof(FitSeg) + sizeof(uint4)) + blocks * FIT_T + 64;
 }
 static FitWork fit_work_at(void *base, uint32_t n_bound) {
     const size_t blocks = cdiv(n_bound, FIT_T);
     FitWork w;
     w.seg = reinterpret_cast<FitSeg *>(base);
     w.span_list = reinterpret_cast<uint4 *>(w.seg + blocks * FIT_SEG_MAX);
-    w.span_count = reinterpret_cast<uint32_t *>(w.span_list + blocks * FIT_SEG_MAX);
+    w.pos_idx = reinterpret_cast<unsigned char *>(w.span_list + blocks * FIT_SEG_MAX);
+    w.span_count = reinterpret_cast<uint32_t *>(w.pos_idx + blocks * FIT_T);
     return w;
 }
 struct FitSmem {
@@ -573,6 +575,7 @@ struct FitSmem {
     uint32_t seg_s[FIT_SEG_MAX], seg_e[FIT_SEG_MAX];
     float seg_box[FIT_SEG_MAX][6];
     uint32_t nseg;
+    uint32_t pos_idx[FIT_T / 4];  // bytes, see FitWork::pos_idx
 };
 __device__ __forceinline__ RcBox box_from6(const float *b) {
     RcBox r;
@@ -605,6 +608,7 @@ __global__ void __launch_bounds__(FIT_T, FIT_T <= 512 ? 3 : 1) k_fit_local(const
         S.flag[tid] = 0;
     }
     if (tid == 0) S.nseg = 0;
+    if (tid < FIT_T / 4) S.pos_idx[tid] = 0xFFFFFFFFu;
     __syncthreads();
     float r2 = 0.0f;
     uint32_t node = RC_INVALID, cs = p1, ce = p1;  // parent of / span of the subtree this thread has finished
@@ -710,10 +714,12 @@ __global__ void __launch_bounds__(FIT_T, FIT_T <= 512 ? 3 : 1) k_fit_local(const
         const float4 *src = reinterpret_cast<const float4 *>(&e);
         float4 *dst = reinterpret_cast<float4 *>(work.seg + (size_t)blockIdx.x * FIT_SEG_MAX + rank);
         dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
-    } else if (tid < (uint32_t)FIT_SEG_MAX) {  // unused entries: position 0 matches no (1-based) leaf, so a reader needs no count
-        float4 *dst = reinterpret_cast<float4 *>(work.seg + (size_t)blockIdx.x * FIT_SEG_MAX + tid);
-        dst[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        // (segments are disjoint: a position is the start or the end of at most one of them)
+        reinterpret_cast<unsigned char *>(S.pos_idx)[sj - blk_lo] = (unsigned char)rank;
+        reinterpret_cast<unsigned char *>(S.pos_idx)[ej - blk_lo] = (unsigned char)rank;
     }
+    __syncthreads();
+    if (tid < FIT_T / 4) reinterpret_cast<uint32_t *>(work.pos_idx)[(size_t)blockIdx.x * (FIT_T / 4) + tid] = S.pos_idx[tid];
     // ---- this block's internal nodes: spanning ones go to the list, the others are collapsed from shared memory
     bool spanning = false;
     RcTopo tp = {0, 0, 0, 0};
@@ -757,37 +763,31 @@ __global__ void __launch_bounds__(FIT_T, FIT_T <= 512 ? 3 : 1) k_fit_local(const
 }
 
 // union of the leaf boxes of sorted positions [a, b] (1-based), which lie in different blocks, a at a segment start and b at a segment
-// end of their blocks; warp-cooperative, every lane returns the result
-__device__ __forceinline__ void fit_range_box(const FitSeg *__restrict__ seg, uint32_t a, uint32_t b, f3 &lo, f3 &hi) {
-    const uint32_t lane = threadIdx.x & 31u;
+// end of their blocks; cooperative over a group of FIT_G consecutive lanes (mask = the group's lanes), every lane returns the result
+constexpr uint32_t FIT_G = 32;  // a warp per node: with 8-lane groups the few nodes that span hundreds of blocks take 4x longer and set the kernel time (52 vs 18 us)
+__device__ __forceinline__ void fit_range_box(const FitSeg *__restrict__ seg, const unsigned char *__restrict__ pos_idx, uint32_t a, uint32_t b, uint32_t mask, f3 &lo,
+                                              f3 &hi) {
+    const uint32_t gl = threadIdx.x & (FIT_G - 1u);
     const uint32_t bA = (a - 1u) / FIT_T, bB = (b - 1u) / FIT_T;
     const FitSeg *tA = seg + (size_t)bA * FIT_SEG_MAX, *tB = seg + (size_t)bB * FIT_SEG_MAX;
-    uint32_t ia = 0xFFFFFFFFu, ib = 0xFFFFFFFFu;
-#pragma unroll
-    for (uint32_t q = 0; q < FIT_SEG_MAX / 32; q++) {
-        const uint32_t j = q * 32u + lane;
-        if (tA[j].s == a) ia = j;
-        if (tB[j].e == b) ib = j;
-    }
-    ia = __reduce_min_sync(0xFFFFFFFFu, ia);
-    ib = __reduce_min_sync(0xFFFFFFFFu, ib);
+    const uint32_t ia = pos_idx[a - 1u], ib = pos_idx[b - 1u];  // (the same address in every lane of the group: one transaction)
     lo = mk3(INFINITY, INFINITY, INFINITY);
     hi = mk3(-INFINITY, -INFINITY, -INFINITY);
-    if (bB > bA + 1u) {  // whole blocks in between: lane-strided, then a butterfly
-        for (uint32_t k = bA + 1u + lane; k < bB; k += 32u) {
+    if (bB > bA + 1u) {  // whole blocks in between: lane-strided, then a butterfly over the group
+        for (uint32_t k = bA + 1u + gl; k < bB; k += FIT_G) {
             const float *x = seg[(size_t)k * FIT_SEG_MAX].sfx;
             lo = jl_min3(lo, mk3(x[0], x[1], x[2]));
             hi = jl_max3(hi, mk3(x[3], x[4], x[5]));
         }
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            const f3 ol = mk3(__shfl_xor_sync(0xFFFFFFFFu, lo.x, d), __shfl_xor_sync(0xFFFFFFFFu, lo.y, d), __shfl_xor_sync(0xFFFFFFFFu, lo.z, d));
-            const f3 oh = mk3(__shfl_xor_sync(0xFFFFFFFFu, hi.x, d), __shfl_xor_sync(0xFFFFFFFFu, hi.y, d), __shfl_xor_sync(0xFFFFFFFFu, hi.z, d));
+        for (int d = FIT_G / 2; d > 0; d >>= 1) {
+            const f3 ol = mk3(__shfl_xor_sync(mask, lo.x, d), __shfl_xor_sync(mask, lo.y, d), __shfl_xor_sync(mask, lo.z, d));
+            const f3 oh = mk3(__shfl_xor_sync(mask, hi.x, d), __shfl_xor_sync(mask, hi.y, d), __shfl_xor_sync(mask, hi.z, d));
             lo = jl_min3(lo, ol);
             hi = jl_max3(hi, oh);
         }
     }
-    if (ia != 0xFFFFFFFFu && ib != 0xFFFFFFFFu) {
+    if (ia < (uint32_t)FIT_SEG_MAX && ib < (uint32_t)FIT_SEG_MAX && tA[ia].s == a && tB[ib].e == b) {
         const float *x = tA[ia].sfx, *y = tB[ib].pfx;
         lo = jl_min3(jl_min3(lo, mk3(x[0], x[1], x[2])), mk3(y[0], y[1], y[2]));
         hi = jl_max3(jl_max3(hi, mk3(x[3], x[4], x[5])), mk3(y[3], y[4], y[5]));
@@ -797,18 +797,20 @@ __device__ __forceinline__ void fit_range_box(const FitSeg *__restrict__ seg, ui
 }
 __device__ __forceinline__ bool fit_is_spanning(const RcTopo &t) { return (t.span_lo - 1u) / FIT_T != (t.span_hi - 1u) / FIT_T; }
 
-// boxes (and BVH2 records) of the spanning nodes: one warp per node, no ordering between nodes
+// boxes (and BVH2 records) of the spanning nodes: a group of FIT_G lanes per node (the kernel is a chain of 3 dependent loads per node, so the
+// parallelism is in nodes, not in lanes), no ordering between nodes
 __global__ void __launch_bounds__(256) k_fit_span(const uint32_t *__restrict__ n_ptr, uint32_t n_host, const RcTopo *__restrict__ topo, const uint32_t *__restrict__ parent,
                                                   RcBox *__restrict__ boxes, RcNode2 *__restrict__ nodes2, FitWork work) {
     const uint32_t n = count_of(n_ptr, n_host);
-    const uint32_t count = *work.span_count, lane = threadIdx.x & 31u;
-    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < count; w += warps) {
+    const uint32_t count = *work.span_count, lane = threadIdx.x & 31u, gl = lane & (FIT_G - 1u);
+    const uint32_t mask = (FIT_G == 32u ? 0xFFFFFFFFu : ((1u << (FIT_G & 31u)) - 1u) << (lane & ~(FIT_G - 1u)));
+    const uint32_t groups = (gridDim.x * blockDim.x) / FIT_G;
+    for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) / FIT_G; w < count; w += groups) {
         const uint4 ent = work.span_list[w];
         const uint32_t v = ent.x;
         f3 lo, hi;
-        fit_range_box(work.seg, ent.y, ent.z, lo, hi);
-        if (lane == 0) st_box(boxes + (v - 1), lo, hi);
+        fit_range_box(work.seg, work.pos_idx, ent.y, ent.z, mask, lo, hi);
+        if (gl == 0) st_box(boxes + (v - 1), lo, hi);
         if (nodes2) {  // the BVH2 record holds the children's boxes: a spanning child's box comes from the same formula
             const RcTopo tp = topo[v - 1];
             f3 cl[2], ch[2];
@@ -819,14 +821,14 @@ __global__ void __launch_bounds__(256) k_fit_span(const uint32_t *__restrict__ n
                 RcTopo tc = {0, 0, 0, 0};
                 if (c < n) { tc = topo[c - 1]; span_c = fit_is_spanning(tc); }
                 if (span_c) {
-                    fit_range_box(work.seg, tc.span_lo, tc.span_hi, cl[k], ch[k]);
+                    fit_range_box(work.seg, work.pos_idx, tc.span_lo, tc.span_hi, mask, cl[k], ch[k]);
                 } else {  // written by k_fit_local (an earlier launch)
                     const RcBox b = boxes[c - 1];
                     cl[k] = mk3(b.lo[0], b.lo[1], b.lo[2]);
                     ch[k] = mk3(b.hi[0], b.hi[1], b.hi[2]);
                 }
             }
-            if (lane == 0) st_node2(nodes2 + (v - 1), cl[0], ch[0], cl[1], ch[1], tp.child0, tp.child1, parent[v - 1]);
+            if (gl == 0) st_node2(nodes2 + (v - 1), cl[0], ch[0], cl[1], ch[1], tp.child0, tp.child1, parent[v - 1]);
         }
     }
 }
@@ -919,9 +921,9 @@ static void run_fit(cudaStream_t st, const FitJob &j, const FitWork &work) {
     const uint32_t blocks = cdiv(j.n_bound, FIT_T);
     k_fit_local<<<blocks, FIT_T, sizeof(FitSmem), st>>>(j.tris_in, j.perm, j.tris, j.inst_boxes, j.leaf_map, j.n_ptr, j.n_bound, j.topo, j.parent, j.boxes, j.nodes2, j.ctl, work,
                                                         j.build_list, j.nodes4, j.leaf_max);
-    // at most FIT_SEG_MAX spanning nodes per block; one warp each, grid-stride
+    // at most FIT_SEG_MAX spanning nodes per block; a group of FIT_G lanes each, grid-stride
     const uint32_t span_bound = blocks > 1 ? blocks * FIT_SEG_MAX : 0u;
-    if (span_bound) k_fit_span<<<std::min(cdiv(span_bound, 8), 148u * 8u), 256, 0, st>>>(j.n_ptr, j.n_bound, j.topo, j.parent, j.boxes, j.nodes2, work);
+    if (span_bound) k_fit_span<<<std::min(cdiv(span_bound, 256 / FIT_G), 148u * 8u), 256, 0, st>>>(j.n_ptr, j.n_bound, j.topo, j.parent, j.boxes, j.nodes2, work);
     if (j.nodes4 || j.hull || j.out10)
         k_collapse_span<<<(span_bound && j.nodes4 ? std::min(cdiv(span_bound, 256), 148u * 4u) : 0u) + 1u, 256, 0, st>>>(j.boxes, j.topo, j.n_ptr, j.n_bound, j.leaf_max, j.leaf_map,
                                                                                                                          j.nodes4, j.hull, work, j.out10, j.ctl, j.root_boxes);

@@ -187,6 +187,11 @@ void hs_blas_nodes2(void *b, rc_bvh_node2 *out) {
     for (size_t i = 0; i < B->tree.nodes2.size(); i++) memcpy(&out[i], &B->tree.nodes2[i], sizeof(rc_bvh_node2));
 }
 void hs_blas_root(void *b, float *out6) { memcpy(out6, ((HsBlas *)b)->tree.root, 24); }
+// the wide nodes (n + 1 slots of 64 bytes, slot 0 unused): what k_fit_local / k_collapse_span must reproduce byte for byte
+void hs_blas_nodes4(void *b, void *out) {
+    HsBlas *B = (HsBlas *)b;
+    memcpy(out, B->tree.nodes4.data(), B->tree.nodes4.size() * sizeof(RcNode4));
+}
 void hs_blas_order(void *b, uint32_t *out) {
     HsBlas *B = (HsBlas *)b;
     for (size_t i = 0; i < B->tris.size(); i++) out[i] = B->tris[i].prim_id;

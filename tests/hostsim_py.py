@@ -21,7 +21,7 @@ def lib():
         L.hs_blas_build.argtypes = [vp, C.c_uint32, vp]
         L.hs_blas_n.restype = C.c_uint32
         L.hs_blas_n.argtypes = [vp]
-        for f in ("hs_blas_nodes2", "hs_blas_root", "hs_blas_order"):
+        for f in ("hs_blas_nodes2", "hs_blas_root", "hs_blas_order", "hs_blas_nodes4"):
             getattr(L, f).restype = None
             getattr(L, f).argtypes = [vp, vp]
         L.hs_blas_free.argtypes = [vp]
@@ -72,6 +72,12 @@ class HsBlas:
     def order(self):
         out = np.zeros(self.n, np.uint32)
         lib().hs_blas_order(self.p, out.ctypes.data)
+        return out
+
+    def nodes4(self):
+        """the wide nodes as raw 64-byte records (n + 1 slots, slot 0 unused)"""
+        out = np.zeros((self.n + 1, 64), np.uint8)
+        lib().hs_blas_nodes4(self.p, out.ctypes.data)
         return out
 
     def check_wide(self):

@@ -38,6 +38,58 @@ def test_builder_bit_exact_vs_oracle():
         g.tlas.free()
 
 
+def _builder_stress_meshes():
+    """triangle soups that exercise the builder's block structure: sizes around the 512-leaf fit blocks and the 2048-key sort tiles, long
+    runs of identical Morton codes (index tie-break chains: the deepest radix trees), an exponentially spaced comb (one-sided tree),
+    and a soup with degenerate faces sprinkled in (compaction offsets)"""
+    rs = np.random.RandomState(7)
+    out = {}
+    for n in (1, 2, 3, 5, 511, 512, 513, 1023, 1024, 1025, 1537, 2047, 2048, 2049, 5000):
+        c = rs.uniform(-10, 10, (n, 1, 3))
+        out[f"soup{n}"] = (c + rs.uniform(-0.3, 0.3, (n, 3, 3))).reshape(n, 9).astype(np.float32)
+    one = np.array([[0, 0, 0, 1, 0, 0, 0, 1, 0]], np.float32)
+    out["duplicates"] = np.concatenate([np.repeat(one, 3000, axis=0), out["soup511"], np.repeat(one + 5, 700, axis=0)])
+    k = np.arange(1400)
+    x = (1.02 ** k)[:, None].astype(np.float32)
+    out["comb"] = np.concatenate([x, 0 * x, 0 * x, x + 0.5 * x, 0 * x, 0 * x, x, 0.5 * x, 0 * x], axis=1).astype(np.float32)
+    holes = out["soup5000"].copy()
+    holes[rs.rand(5000) < 0.3, 3:] = np.tile(holes[rs.rand(5000) < 0.3][:1, :3], 2)  # v1 = v2 = one fixed point: zero-area faces
+    out["holes"] = holes
+    return out
+
+
+@pytest.mark.parametrize("name", sorted(_builder_stress_meshes()))
+def test_builder_block_structure_bit_exact(name):
+    """BVH2 byte-identical to the oracle's and every reachable wide node byte-identical to the host collapse of the same BVH2, on meshes
+    chosen to hit the fit's block boundaries, spanning-node formula, segment tables and the cooperative front end's tile boundaries"""
+    import raycore_b200 as rc
+    import hostsim_py as hs
+
+    verts = _builder_stress_meshes()[name]
+    ob = orc.OracleBLAS.from_verts(verts)
+    g = engines.GpuEngine([(verts, None, [kat.I34], None)])
+    assert g.tlas.read_blas_order(1).tolist() == ob.prims["input_index"].tolist()
+    assert g.tlas.read_blas_nodes(1).tobytes() == ob.nodes.tobytes(), "GPU BVH2 differs from the reference restatement"
+    g.tlas.free()
+    b4 = rc.build_blas4(verts)  # default build flags: no BVH2 emission
+    wide = b4.nodes().view(np.uint8).reshape(-1, 64)
+    host = hs.HsBlas(verts).nodes4()
+    assert wide.shape == host.shape
+    child = wide.view(np.uint32).reshape(-1, 16)
+    seen, todo = set(), [1]
+    while todo:
+        k = todo.pop()
+        if k in seen:
+            continue
+        seen.add(k)
+        assert wide[k].tobytes() == host[k].tobytes(), f"wide node {k} differs"
+        for c in child[k, [10, 11, 12, 13]]:
+            if not (c & 0x80000000):
+                todo.append(int(c))
+    assert not wide[0].any() and (len(ob.nodes) == 1 or not wide[-1].any())  # the two slots nothing references are zeroed
+    b4.free()
+
+
 def test_tlas_bit_exact_vs_oracle():
     pushes = _scene_instanced()
     o, g = engines.OracleEngine(pushes), engines.GpuEngine(pushes)
