@@ -141,6 +141,34 @@ def main():
     out["C3_instanced_and_C5_refit"] = c3
     tl.free()
 
+    # ---- C5 (iii): per-frame mesh (vertex) update of the test_mesh_update workload: update!(tlas, handle, mesh) as a rebuild and as a
+    # refit of the kept radix tree, then sync! and 10 M any_hit shadow rays (device-resident vertices: rc_update_geometry, CUDA events) ---
+    c5 = {}
+    for tess, label in ((72, "10k"), (709, "1M")):
+        base_v = W.bumpy_sphere(tess)
+        tl = rc.TLAS(allow_refit=True)
+        lib, ctx = tl._lib, tl._ctx
+        h = tl.push(base_v, list(W.random_trs(64 if tess == 72 else 1, 3, extent=6.0)))
+        tl.sync()
+        frames = {"rebuild_ms": [], "refit_ms": [], "sync_after_ms": []}
+        for f in range(1, 5):
+            moved = (base_v.reshape(-1, 3) * (1.0 + 0.02 * f * np.sin(7.0 * base_v.reshape(-1, 3)[:, :1] + f))).astype(np.float32).reshape(-1, 9)
+            d_v = torch.from_numpy(moved).cuda()
+            for mode, key in ((0, "rebuild_ms"), (L.RC_UPDATE_REFIT, "refit_ms")):
+                assert lib.rc_update_geometry(ctx, h.id, d_v.data_ptr(), len(moved), None, L.RC_VERTS_ON_DEVICE | mode) == 0, lib.rc_last_error(ctx)
+                assert bool(lib.rc_last_update_refitted(ctx)) == bool(mode)
+                frames[key].append(float(lib.rc_last_build_ms(ctx)))
+                t0 = time.time()
+                tl.sync()
+                frames["sync_after_ms"].append(1e3 * (time.time() - t0))
+            del d_v
+        sh = W.box_rays(10_000_000 if not args.quick else 1_000_000, 98, half=8.0 if tess == 72 else 1.5)
+        sh["t_max"] = 6.0
+        c5[label] = {"triangles": tl.sizes()["blas_prims"], "update_rebuild_ms": min(frames["rebuild_ms"]), "update_refit_ms": min(frames["refit_ms"]),
+                     "sync_after_update_ms": min(frames["sync_after_ms"]), "any_hit_shadow_10M_Mrays_s": dev_trace(tl, sh, any_hit=True)[0]}
+        tl.free()
+    out["C5_mesh_update"] = c5
+
     # ---- C4: view factors, 5 x bumpy_sphere(72), 1000 rays per triangle -----------------------------------------------------
     meshes = W.viewfactor_scene(72)
     tl = rc.TLAS()
