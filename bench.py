@@ -651,7 +651,7 @@ def main():
                "parity_on_sample": {k: int(len(v)) for k, v in cls.items()}}
 
     if build is not None:
-        build["blas_build_ms_10k_triangles_c3"] = blas_build_ms_10k
+        build["blas_build_ms_10k_triangles_c3_first_build_in_process"] = blas_build_ms_10k  # cold: lazy module load, one-time function attributes and occupancy query
     line = {
         "metric": "closest_hit Mrays/s (incoherent)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
