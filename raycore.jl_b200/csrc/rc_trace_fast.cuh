@@ -221,6 +221,37 @@ __device__ __forceinline__ bool rc_line_misses_sphere(f3 o, f3 d, float4 sph) {
     return fmaf(lx, lx, fmaf(ly, ly, lz * lz)) > fmaf(1.1e-6f, sph.w + oc2, sph.w);
 }
 
+// How a lane addresses its column of the shared-memory stack.  RcStk<false>: a generic pointer (the warp simulator, and the any-hit
+// variants).  RcStk<true>: ONE 32-bit register holding the address in the shared window, st.shared / ld.shared with immediate row
+// offsets — with the pointer form the compiler carried two copies of the top (one as an address, one for the depth compare) and bumped
+// both on every push, and the ALU pipe is this kernel's limiter: closest_hit on C3 9.25 -> 8.90 ms (profiles/README.md r2).  The any-hit
+// variants keep the pointer form (the address form costs them 8 bytes of spills: 6.26 -> 6.49 ms).
+#ifndef RC_STACK_ADDR32
+#define RC_STACK_ADDR32 1
+#endif
+template <bool A32>
+struct RcStk {
+    typedef uint32_t *ptr;
+    static constexpr int ROW = RC_TRACE_THREADS;
+    static __device__ __forceinline__ ptr base(uint32_t *sstack, uint32_t tid) { return sstack + tid; }
+    static __device__ __forceinline__ uint32_t ld(ptr b, int off) { return b[off]; }
+    static __device__ __forceinline__ void st(ptr b, int off, uint32_t v) { b[off] = v; }
+};
+#ifndef RC_WARPSIM
+template <>
+struct RcStk<true> {
+    typedef uint32_t ptr;
+    static constexpr int ROW = RC_TRACE_THREADS * 4;
+    static __device__ __forceinline__ ptr base(uint32_t *sstack, uint32_t tid) { return (uint32_t)__cvta_generic_to_shared(sstack + tid); }
+    static __device__ __forceinline__ uint32_t ld(ptr b, int off) {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(b + (uint32_t)off));
+        return v;
+    }
+    static __device__ __forceinline__ void st(ptr b, int off, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(b + (uint32_t)off), "r"(v)); }
+};
+#endif
+
 // Ray source / hit sink of the batched entry points: RTRay array in, RTHitResult array out.
 struct RcIoArrays {
     // scheduler constants of the multi-instance variant for this ray source (see above): a cheap refill (one 32-B load) can run early
@@ -236,6 +267,34 @@ struct RcIoArrays {
     }
     __device__ __forceinline__ void store(unsigned long long i, const rc_hit &h) const { rc_store_hit(hits, i, h); }
 };
+
+// RC_VOTE_LUT: the vote word from a 32-entry constant table indexed by the reference's top nibble (+16 with a leaf parked) instead of
+// three range tests and four selects
+#ifndef RC_VOTE_LUT
+#define RC_VOTE_LUT 1  // C3: 8.89 -> 8.83 ms per 2^24 rays
+#endif
+#if RC_VOTE_LUT
+// vote word by (leaf parked ? 16 : 0) + top nibble of the lane's next reference: 0-7 wide node, 8-B a second BLAS leaf (waits for the T step),
+// C-D instance leaf (index < 2^28), E level sentinel (waits for the parked leaf; without one the settle has already left the level),
+// F RC_INVALID (finished).  Second half: the single-instance variants (no level step).
+#ifdef RC_WARPSIM
+static const uint32_t rc_vote_lut[64] = {
+#else
+static __constant__ uint32_t rc_vote_lut[64] = {
+#endif
+#define N_ RC_VOTE_N
+#define T_ RC_VOTE_T
+#define X_ RC_VOTE_X
+#define F_ RC_VOTE_F
+    N_, N_, N_, N_, N_, N_, N_, N_, 0, 0, 0, 0, X_, X_, 0, F_,
+    N_ | T_, N_ | T_, N_ | T_, N_ | T_, N_ | T_, N_ | T_, N_ | T_, N_ | T_, T_, T_, T_, T_, T_, T_, T_, T_,
+    N_, N_, N_, N_, N_, N_, N_, N_, 0, 0, 0, 0, 0, 0, 0, F_,
+    N_ | T_, N_ | T_, N_ | T_, N_ | T_, N_ | T_, N_ | T_, N_ | T_, N_ | T_, T_, T_, T_, T_, T_, T_, T_, T_};
+#undef N_
+#undef T_
+#undef X_
+#undef F_
+#endif
 
 // IO: where ray i comes from and where its result goes (RcIoArrays for rc_trace_*; rc_analysis.cu plugs in an on-the-fly
 // view-factor ray generator + matrix accumulator, so the analysis kernels run on the same scheduler).
@@ -254,8 +313,16 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, SINGLE ? RC_MIN_BLOCKS_SINGL
     f3 wo = mk3(0, 0, 0), wd = mk3(0, 0, 0), o = wo, d = wd, inv = wo;
     float t_min = 0.f, t_max = 0.f, hit_u = 0.f, hit_v = 0.f;
     int cur_inst = -1, best_inst = -1;
-    uint32_t *const sbase = sstack + tid;  // row 0 of this lane's column (the guard row)
-    uint32_t *spa = sbase;                 // top of the stack
+#ifdef RC_WARPSIM
+    typedef RcStk<false> STK;
+#else
+    typedef RcStk<(RC_STACK_ADDR32 != 0) && !ANY> STK;
+#endif
+    const typename STK::ptr sbase = STK::base(sstack, tid);  // row 0 of this lane's column (the guard row)
+    typename STK::ptr spa = sbase;                           // top of the stack
+#define RC_ROW STK::ROW
+#define RC_LD_OFF(base, off) STK::ld((base), (off))
+#define RC_ST_OFF(base, off, v) STK::st((base), (off), (v))
     uint32_t best_prim = 0, best_meta = 0;
     const RcTri *tris = nullptr;
     const RcNode4 *nodes = sc.tlas4;
@@ -275,13 +342,23 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, SINGLE ? RC_MIN_BLOCKS_SINGL
     // push is accepted, so a rejected value is simply overwritten by the next push (rows above the top are don't-care).  Row 0 is
     // a guard row that always holds RC_INVALID, so the speculative read of an empty stack is harmless and neither push nor pop
     // needs a clamp.
-#define RC_ROW RC_TRACE_THREADS
+#ifndef RC_PUSH_PRED
+#define RC_PUSH_PRED 1
+#endif
+#if RC_PUSH_PRED  // experiment: predicated store + predicated pointer bump (one ALU-pipe instruction less per push than SEL + IADD)
+#define RC_PUSH_IF(cond, v)              \
+    if (cond) {                          \
+        RC_ST_OFF(spa, RC_ROW, (v));     \
+        spa += RC_ROW;                   \
+    }
+#else
 #define RC_PUSH_IF(cond, v)              \
     {                                    \
-        spa[RC_ROW] = (v);               \
+        RC_ST_OFF(spa, RC_ROW, (v));     \
         spa += (cond) ? RC_ROW : 0;      \
     }
-#define RC_TOP() (*spa)
+#endif
+#define RC_TOP() RC_LD_OFF(spa, 0)
 #define RC_DEPTH() ((uint32_t)(spa - sbase) / RC_ROW)
     // A lane whose next reference is the level sentinel (and has no leaf parked) returns to the TLAS right here in the settle
     // instead of voting for a level-change step: the leave is ~10 instructions, a scheduler round for it costs more (+3.2 % on the
@@ -294,9 +371,9 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, SINGLE ? RC_MIN_BLOCKS_SINGL
         spa -= RC_ROW;                                                                    \
         o = wo; d = wd;                                                                   \
         if (RC_WINV_SMEM) {                                                               \
-            inv.x = __uint_as_float(sbase[(RC_SSTACK + 5) * RC_ROW]);                     \
-            inv.y = __uint_as_float(sbase[(RC_SSTACK + 6) * RC_ROW]);                     \
-            inv.z = __uint_as_float(sbase[(RC_SSTACK + 7) * RC_ROW]);                     \
+            inv.x = __uint_as_float(RC_LD_OFF(sbase, (RC_SSTACK + 5) * RC_ROW));                     \
+            inv.y = __uint_as_float(RC_LD_OFF(sbase, (RC_SSTACK + 6) * RC_ROW));                     \
+            inv.z = __uint_as_float(RC_LD_OFF(sbase, (RC_SSTACK + 7) * RC_ROW));                     \
         } else {                                                                          \
             inv = rc_fast_inv3(d);                                                        \
         }                                                                                 \
@@ -320,18 +397,38 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, SINGLE ? RC_MIN_BLOCKS_SINGL
             spa -= RC_ROW;                                                                                         \
         }                                                                                                          \
     }
-    // after a step: park a freshly reached BLAS leaf (so the lane can keep descending) and recompute the lane's vote
-#define RC_SETTLE()                                                                                                \
-    {                                                                                                              \
-        RC_SETTLE_LEAVE()                                                                                          \
-        if (spa > sbase + RC_SSTACK * RC_ROW) { ovf = true; cur = RC_INVALID; leaf = 0; spa = sbase; RC_CLEAR_PINST() } \
-        RC_SETTLE_WCULL()                                                                                          \
-        const bool park_ = ((cur ^ RC_LEAF_BIT) < 0x40000000u) && leaf == 0; /* BLAS leaf reference */              \
+// the short-stack overflow path never runs on real scenes: keep it a branch (an empty volatile asm stops the if-conversion that turned it
+// into four selects on every settle; the ALU pipe is the limiter)
+#ifndef RC_OVF_BRANCH
+#define RC_OVF_BRANCH 1
+#endif
+#if RC_OVF_BRANCH && !defined(RC_WARPSIM)
+#define RC_COLD_PATH() asm volatile("");
+#else
+#define RC_COLD_PATH()
+#endif
+#ifndef RC_PARK_PRED
+#define RC_PARK_PRED 0
+#endif
+#if RC_PARK_PRED  // experiment: the park as a predicated block instead of four selects
+#define RC_SETTLE_PARK()                                                                                           \
+        if (park_) { leaf = cur; leaf_k = 0u; cur = RC_TOP(); spa -= RC_ROW; }
+#else
+#define RC_SETTLE_PARK()                                                                                           \
         const uint32_t top_ = RC_TOP();                                                                            \
         leaf = park_ ? cur : leaf;                                                                                 \
         leaf_k = park_ ? 0u : leaf_k;                                                                              \
         cur = park_ ? top_ : cur;                                                                                  \
-        spa -= park_ ? RC_ROW : 0;                                                                                 \
+        spa -= park_ ? RC_ROW : 0;
+#endif
+    // after a step: park a freshly reached BLAS leaf (so the lane can keep descending) and recompute the lane's vote
+#define RC_SETTLE()                                                                                                \
+    {                                                                                                              \
+        RC_SETTLE_LEAVE()                                                                                          \
+        if (spa > sbase + RC_SSTACK * RC_ROW) { RC_COLD_PATH() ovf = true; cur = RC_INVALID; leaf = 0; spa = sbase; RC_CLEAR_PINST() } \
+        RC_SETTLE_WCULL()                                                                                          \
+        const bool park_ = ((cur ^ RC_LEAF_BIT) < 0x40000000u) && leaf == 0; /* BLAS leaf reference */              \
+        RC_SETTLE_PARK()                                                                                           \
         RC_SETTLE_VOTE()                                                                                           \
     }
     /* instance leaf = [0xC0000000, RC_SENTINEL); a sentinel still here waits for the parked leaf and is left by the T step's settle */
@@ -346,10 +443,14 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, SINGLE ? RC_MIN_BLOCKS_SINGL
         if (!SINGLE) vote |= (pinst != 0) ? RC_VOTE_X : 0u;
 #else
 #define RC_CLEAR_PINST()
+#if RC_VOTE_LUT
+#define RC_SETTLE_VOTE() vote = rc_vote_lut[(SINGLE ? 32u : 0u) + (cur >> 28) + (leaf ? 16u : 0u)];
+#else
 #define RC_SETTLE_VOTE()                                                                                           \
         vote = ((int)cur >= 0) ? RC_VOTE_N : 0u;                                                                   \
         vote |= leaf ? RC_VOTE_T : ((cur == RC_INVALID) ? RC_VOTE_F : 0u);                                         \
         if (!SINGLE) vote |= ((cur + 0x40000000u) < 0x2FFFFFFFu) ? RC_VOTE_X : 0u;
+#endif
 #endif
 
     // enter instance `index`: its world->local transform applied with the reference's exact arithmetic (:1961-1977).  `entered_` tells
@@ -389,7 +490,11 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, SINGLE ? RC_MIN_BLOCKS_SINGL
         const uint32_t votes = __reduce_add_sync(FULL, vote);
         RC_SIM_ITER()
         if (votes == 0) break;  // every lane is dead
+#ifdef RC_WARPSIM
         const uint32_t nN = votes & 0xFFu, nT = (votes >> 8) & 0xFFu, nX = (votes >> 16) & 0xFFu, nF = votes >> 24;
+#else  // one PRMT per count (a shift + a mask each otherwise: the scheduler header runs 32 lanes wide in every iteration)
+        const uint32_t nN = __byte_perm(votes, 0u, 0x4440u), nT = __byte_perm(votes, 0u, 0x4441u), nX = __byte_perm(votes, 0u, 0x4442u), nF = votes >> 24;
+#endif
 
         if (nF > 0 && (nF >= FETCH_MIN || (votes & 0x00FFFFFFu) == 0)) {
             // ---- F: retire + refill (warp-cooperative) -----------------------------------------------------------------
@@ -423,8 +528,8 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, SINGLE ? RC_MIN_BLOCKS_SINGL
                     wo = w.o; wd = w.d;
                     t_min = w.t_min; t_max = w.t_max;
                     best_inst = -1; ovf = false;
-                    sbase[0] = RC_INVALID;       // guard row
-                    sbase[RC_ROW] = RC_INVALID;  // stack bottom: popping it ends the ray
+                    RC_ST_OFF(sbase, 0, RC_INVALID);       // guard row
+                    RC_ST_OFF(sbase, RC_ROW, RC_INVALID);  // stack bottom: popping it ends the ray
                     spa = sbase + RC_ROW;
                     if (single) {  // straight into the only instance: no top-level node step, no sentinel, no return step
                         bool in_;
@@ -435,9 +540,9 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, SINGLE ? RC_MIN_BLOCKS_SINGL
                         o = wo; d = wd;
                         inv = rc_fast_inv3(d);
                         if (RC_WINV_SMEM) {
-                            sbase[(RC_SSTACK + 5) * RC_ROW] = __float_as_uint(inv.x);
-                            sbase[(RC_SSTACK + 6) * RC_ROW] = __float_as_uint(inv.y);
-                            sbase[(RC_SSTACK + 7) * RC_ROW] = __float_as_uint(inv.z);
+                            RC_ST_OFF(sbase, (RC_SSTACK + 5) * RC_ROW, __float_as_uint(inv.x));
+                            RC_ST_OFF(sbase, (RC_SSTACK + 6) * RC_ROW, __float_as_uint(inv.y));
+                            RC_ST_OFF(sbase, (RC_SSTACK + 7) * RC_ROW, __float_as_uint(inv.z));
                         }
                         cur_inst = -1;
                         nodes = sc.tlas4;
@@ -547,8 +652,13 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, SINGLE ? RC_MIN_BLOCKS_SINGL
                 if (COUNT && RC_DEPTH() > lc.max_stack) lc.max_stack = RC_DEPTH();
                 const uint32_t top = RC_TOP();
                 const uint32_t rn = e0 ? r0 : (e1 ? r1 : (e2 ? r2 : r3));
+#if RC_PARK_PRED
+                cur = rn;
+                if (!any_hit) { cur = top; spa -= RC_ROW; }
+#else
                 cur = any_hit ? rn : top;
                 spa -= any_hit ? 0 : RC_ROW;
+#endif
                 RC_SETTLE()
             }
         }
@@ -557,8 +667,11 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS, SINGLE ? RC_MIN_BLOCKS_SINGL
 #undef RC_TOP
 #undef RC_DEPTH
 #undef RC_ROW
+#undef RC_LD_OFF
+#undef RC_ST_OFF
 #undef RC_SETTLE
 #undef RC_SETTLE_VOTE
+#undef RC_SETTLE_PARK
 #undef RC_CLEAR_PINST
 #undef RC_SETTLE_LEAVE
 #undef RC_SETTLE_WCULL
