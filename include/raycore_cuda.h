@@ -114,7 +114,7 @@ enum { RC_SYNC_NONE = 0, RC_SYNC_REFIT = 1, RC_SYNC_REBUILD = 2 };
 int32_t rc_create(int32_t device, rc_context **out);
 /* free!(tlas) — src/instanced-bvh.jl:383-399 */
 int32_t rc_destroy(rc_context *ctx);
-const char *rc_last_error(const rc_context *ctx); /* ctx may be NULL: last creation error */
+const char *rc_last_error(const rc_context *ctx); /* ctx may be NULL: the calling thread's last creation / blob-check error */
 int32_t rc_abi_version(void);
 /* the context's CUDA stream (cudaStream_t) — all work of this context is ordered on it */
 void *rc_stream(rc_context *ctx);

@@ -24,7 +24,7 @@ struct HandleInfo {
     bool deleted;
 };
 
-std::string g_create_error;
+thread_local std::string g_create_error;  // message of a failed rc_create / rc_check_exported on this thread (read back by the same thread with rc_last_error(NULL))
 
 }  // namespace
 
@@ -1218,7 +1218,7 @@ struct rc_blas4 {
     rc_context *ctx = nullptr;
     std::string last_error;
 };
-static std::string g_blas4_error;
+static thread_local std::string g_blas4_error;
 static_assert(sizeof(rc_wide_node) == sizeof(RcNode4), "rc_wide_node is the public name of the wide-node layout");
 
 int32_t rc_blas4_build(int32_t device, const float *verts, uint32_t n_faces, const uint32_t *face_meta, uint32_t flags, rc_blas4 **out) {  // build_blas4, :511-523

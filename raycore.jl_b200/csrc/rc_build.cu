@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <string>
 #include <vector>
@@ -461,17 +462,17 @@ __global__ void __launch_bounds__(RS_THREADS, 4) k_front(const FrontArgs A) {
 
 // grid of the front-end kernel: one block per tile, capped at what is co-resident on this device
 static bool launch_front(cudaStream_t st, FrontArgs &A, uint32_t tiles_wanted, std::string &err) {
-    static int max_blocks[64] = {0};
+    static std::atomic<int> max_blocks[64];  // per device; several host threads build concurrently under rc_multi_* (zero-initialised)
     int dev = 0;
     CK(cudaGetDevice(&dev));
-    int cap = (dev >= 0 && dev < 64) ? max_blocks[dev] : 0;
+    int cap = (dev >= 0 && dev < 64) ? max_blocks[dev].load(std::memory_order_relaxed) : 0;
     if (cap == 0) {
         int per_sm = 0, sms = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_front, RS_THREADS, 0));
         CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         cap = per_sm * sms;
         if (cap < 1) { err = "k_front does not fit on this device"; return false; }
-        if (dev >= 0 && dev < 64) max_blocks[dev] = cap;
+        if (dev >= 0 && dev < 64) max_blocks[dev].store(cap, std::memory_order_relaxed);
     }
     // at least 128 blocks: the row scans of a pass are 1024 independent rows, one warp each
     const uint32_t grid = std::min(std::max(tiles_wanted, 128u), (uint32_t)cap);
@@ -911,12 +912,12 @@ struct FitJob {
 };
 static void run_fit(cudaStream_t st, const FitJob &j, const FitWork &work) {
     // the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute (several devices build concurrently under rc_multi_*)
-    static bool configured[64] = {false};
+    static std::atomic<bool> configured[64];  // (zero-initialised; setting the attribute twice is harmless)
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || !configured[dev]) {
+    if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_relaxed)) {
         cudaFuncSetAttribute(k_fit_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FitSmem));
-        if (dev >= 0 && dev < 64) configured[dev] = true;
+        if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_relaxed);
     }
     const uint32_t blocks = cdiv(j.n_bound, FIT_T);
     k_fit_local<<<blocks, FIT_T, sizeof(FitSmem), st>>>(j.tris_in, j.perm, j.tris, j.inst_boxes, j.leaf_map, j.n_ptr, j.n_bound, j.topo, j.parent, j.boxes, j.nodes2, j.ctl, work,

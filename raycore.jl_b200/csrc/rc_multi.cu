@@ -28,7 +28,7 @@ struct rc_multi {
 };
 
 namespace {
-std::string g_multi_create_error;
+thread_local std::string g_multi_create_error;
 
 // run fn(k) for every device on its own host thread; returns the first non-zero status (and remembers that device's message)
 template <class F>
