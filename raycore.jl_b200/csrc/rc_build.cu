@@ -556,28 +556,30 @@ struct FitWork {  // per-fit scratch: segment tables [blocks][FIT_SEG_MAX], span
     uint32_t *span_count;
     uint32_t *err_flag;  // set when a block found more than FIT_SEG_MAX segments (impossible for a radix tree; checked by the host, never silent)
 };
-static size_t fit_work_bytes(uint32_t n_bound) {
-    const size_t blocks = cdiv(n_bound, FIT_T);
-    return blocks * FIT_SEG_MAX * (sizeof(FitSeg) + sizeof(uint4)) + blocks * FIT_T + 64;
+static size_t fit_work_bytes(uint32_t n_bound, uint32_t fit_t = FIT_T) {
+    const size_t blocks = cdiv(n_bound, fit_t);
+    return blocks * FIT_SEG_MAX * (sizeof(FitSeg) + sizeof(uint4)) + blocks * fit_t + 64;
 }
-static FitWork fit_work_at(void *base, uint32_t n_bound) {
-    const size_t blocks = cdiv(n_bound, FIT_T);
+static FitWork fit_work_at(void *base, uint32_t n_bound, uint32_t fit_t = FIT_T) {
+    const size_t blocks = cdiv(n_bound, fit_t);
     FitWork w;
     w.seg = reinterpret_cast<FitSeg *>(base);
     w.span_list = reinterpret_cast<uint4 *>(w.seg + blocks * FIT_SEG_MAX);
     w.pos_idx = reinterpret_cast<unsigned char *>(w.span_list + blocks * FIT_SEG_MAX);
-    w.span_count = reinterpret_cast<uint32_t *>(w.pos_idx + blocks * FIT_T);
+    w.span_count = reinterpret_cast<uint32_t *>(w.pos_idx + blocks * fit_t);
     return w;
 }
-struct FitSmem {
-    RcTopo topo[FIT_T];
-    uint32_t par_int[FIT_T], par_leaf[FIT_T], flag[FIT_T];
-    float box_int[FIT_T][6], box_leaf[FIT_T][6];
+template <int T>  // T = leaves per fit block = threads per block (FIT_T for the multi-launch path, SB_T inside the small-build kernel)
+struct FitSmemT {
+    RcTopo topo[T];
+    uint32_t par_int[T], par_leaf[T], flag[T];
+    float box_int[T][6], box_leaf[T][6];
     uint32_t seg_s[FIT_SEG_MAX], seg_e[FIT_SEG_MAX];
     float seg_box[FIT_SEG_MAX][6];
     uint32_t nseg;
-    uint32_t pos_idx[FIT_T / 4];  // bytes, see FitWork::pos_idx
+    uint32_t pos_idx[T / 4];  // bytes, see FitWork::pos_idx
 };
+using FitSmem = FitSmemT<FIT_T>;
 __device__ __forceinline__ RcBox box_from6(const float *b) {
     RcBox r;
     r.lo[0] = b[0]; r.lo[1] = b[1]; r.lo[2] = b[2]; r.pad0 = 0.f;
@@ -586,18 +588,18 @@ __device__ __forceinline__ RcBox box_from6(const float *b) {
 }
 // build_list: append this block's spanning nodes to work.span_list (skipped when a list of the same topology is already there)
 // nodes4 != null: collapse the in-block nodes into their wide nodes here (leaf_max, leaf_map as in rc_collapse_node)
-__global__ void __launch_bounds__(FIT_T, FIT_T <= 512 ? 3 : 1) k_fit_local(const RcTri *__restrict__ tris_in, const uint32_t *__restrict__ perm, RcTri *__restrict__ tris,
+template <int T>
+__device__ __forceinline__ void fit_local_body(unsigned char *fit_raw, const uint32_t block, const RcTri *__restrict__ tris_in, const uint32_t *__restrict__ perm, RcTri *__restrict__ tris,
                                                      const RcBox *__restrict__ inst_boxes, const uint32_t *__restrict__ leaf_map, const uint32_t *__restrict__ n_ptr,
                                                      uint32_t n_host, const RcTopo *__restrict__ topo, const uint32_t *__restrict__ parent, RcBox *__restrict__ boxes,
                                                      RcNode2 *__restrict__ nodes2, uint32_t *__restrict__ ctl, FitWork work, bool build_list, RcNode4 *__restrict__ nodes4,
                                                      uint32_t leaf_max) {
-    extern __shared__ __align__(16) unsigned char fit_raw[];
-    FitSmem &S = *reinterpret_cast<FitSmem *>(fit_raw);
+    FitSmemT<T> &S = *reinterpret_cast<FitSmemT<T> *>(fit_raw);
     const uint32_t n = count_of(n_ptr, n_host);
     const uint32_t tid = threadIdx.x;
-    const uint32_t blk_lo = blockIdx.x * FIT_T + 1u;  // first sorted primitive (1-based) = first internal node number of the range
+    const uint32_t blk_lo = block * T + 1u;  // first sorted primitive (1-based) = first internal node number of the range
     if (blk_lo > n) return;
-    const uint32_t blk_hi = min(blk_lo + FIT_T - 1u, n);
+    const uint32_t blk_hi = min(blk_lo + T - 1u, n);
     const uint32_t p1 = blk_lo + tid;  // this thread's primitive (1-based) and the internal node number it stages
     const bool has_leaf = p1 <= blk_hi, has_node = p1 <= blk_hi && p1 < n;
     if (has_leaf) {
@@ -609,7 +611,7 @@ __global__ void __launch_bounds__(FIT_T, FIT_T <= 512 ? 3 : 1) k_fit_local(const
         S.flag[tid] = 0;
     }
     if (tid == 0) S.nseg = 0;
-    if (tid < FIT_T / 4) S.pos_idx[tid] = 0xFFFFFFFFu;
+    if (tid < T / 4) S.pos_idx[tid] = 0xFFFFFFFFu;
     __syncthreads();
     float r2 = 0.0f;
     uint32_t node = RC_INVALID, cs = p1, ce = p1;  // parent of / span of the subtree this thread has finished
@@ -713,14 +715,14 @@ __global__ void __launch_bounds__(FIT_T, FIT_T <= 512 ? 3 : 1) k_fit_local(const
         e.sfx[0] = slo.x; e.sfx[1] = slo.y; e.sfx[2] = slo.z; e.sfx[3] = shi.x; e.sfx[4] = shi.y; e.sfx[5] = shi.z;
         e.pfx[0] = plo.x; e.pfx[1] = plo.y; e.pfx[2] = plo.z; e.pfx[3] = phi.x; e.pfx[4] = phi.y; e.pfx[5] = phi.z;
         const float4 *src = reinterpret_cast<const float4 *>(&e);
-        float4 *dst = reinterpret_cast<float4 *>(work.seg + (size_t)blockIdx.x * FIT_SEG_MAX + rank);
+        float4 *dst = reinterpret_cast<float4 *>(work.seg + (size_t)block * FIT_SEG_MAX + rank);
         dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
         // (segments are disjoint: a position is the start or the end of at most one of them)
         reinterpret_cast<unsigned char *>(S.pos_idx)[sj - blk_lo] = (unsigned char)rank;
         reinterpret_cast<unsigned char *>(S.pos_idx)[ej - blk_lo] = (unsigned char)rank;
     }
     __syncthreads();
-    if (tid < FIT_T / 4) reinterpret_cast<uint32_t *>(work.pos_idx)[(size_t)blockIdx.x * (FIT_T / 4) + tid] = S.pos_idx[tid];
+    if (tid < T / 4) reinterpret_cast<uint32_t *>(work.pos_idx)[(size_t)block * (T / 4) + tid] = S.pos_idx[tid];
     // ---- this block's internal nodes: spanning ones go to the list, the others are collapsed from shared memory
     bool spanning = false;
     RcTopo tp = {0, 0, 0, 0};
@@ -746,7 +748,7 @@ __global__ void __launch_bounds__(FIT_T, FIT_T <= 512 ? 3 : 1) k_fit_local(const
         if (lane == 0) woff[wid] = __popc(bal);
         __syncthreads();
         if (wid == 0) {
-            const uint32_t c = lane < FIT_T / 32 ? woff[lane] : 0u, inc = warp_incl_scan(c);
+            const uint32_t c = lane < T / 32 ? woff[lane] : 0u, inc = warp_incl_scan(c);
             woff[lane] = inc - c;
             if (lane == 31) woff[32] = inc;
         }
@@ -763,13 +765,23 @@ __global__ void __launch_bounds__(FIT_T, FIT_T <= 512 ? 3 : 1) k_fit_local(const
     }
 }
 
+__global__ void __launch_bounds__(FIT_T, FIT_T <= 512 ? 3 : 1) k_fit_local(const RcTri *__restrict__ tris_in, const uint32_t *__restrict__ perm, RcTri *__restrict__ tris,
+                                                     const RcBox *__restrict__ inst_boxes, const uint32_t *__restrict__ leaf_map, const uint32_t *__restrict__ n_ptr,
+                                                     uint32_t n_host, const RcTopo *__restrict__ topo, const uint32_t *__restrict__ parent, RcBox *__restrict__ boxes,
+                                                     RcNode2 *__restrict__ nodes2, uint32_t *__restrict__ ctl, FitWork work, bool build_list, RcNode4 *__restrict__ nodes4,
+                                                     uint32_t leaf_max) {
+    extern __shared__ __align__(16) unsigned char fit_raw[];
+    fit_local_body<FIT_T>(fit_raw, blockIdx.x, tris_in, perm, tris, inst_boxes, leaf_map, n_ptr, n_host, topo, parent, boxes, nodes2, ctl, work, build_list, nodes4, leaf_max);
+}
+
 // union of the leaf boxes of sorted positions [a, b] (1-based), which lie in different blocks, a at a segment start and b at a segment
 // end of their blocks; cooperative over a group of FIT_G consecutive lanes (mask = the group's lanes), every lane returns the result
 constexpr uint32_t FIT_G = 32;  // a warp per node: with 8-lane groups the few nodes that span hundreds of blocks take 4x longer and set the kernel time (52 vs 18 us)
+template <int T>
 __device__ __forceinline__ void fit_range_box(const FitSeg *__restrict__ seg, const unsigned char *__restrict__ pos_idx, uint32_t a, uint32_t b, uint32_t mask, f3 &lo,
                                               f3 &hi) {
     const uint32_t gl = threadIdx.x & (FIT_G - 1u);
-    const uint32_t bA = (a - 1u) / FIT_T, bB = (b - 1u) / FIT_T;
+    const uint32_t bA = (a - 1u) / T, bB = (b - 1u) / T;
     const FitSeg *tA = seg + (size_t)bA * FIT_SEG_MAX, *tB = seg + (size_t)bB * FIT_SEG_MAX;
     const uint32_t ia = pos_idx[a - 1u], ib = pos_idx[b - 1u];  // (the same address in every lane of the group: one transaction)
     lo = mk3(INFINITY, INFINITY, INFINITY);
@@ -796,12 +808,14 @@ __device__ __forceinline__ void fit_range_box(const FitSeg *__restrict__ seg, co
         lo = hi = mk3(__int_as_float(0x7FFFFFFF), __int_as_float(0x7FFFFFFF), __int_as_float(0x7FFFFFFF));
     }
 }
-__device__ __forceinline__ bool fit_is_spanning(const RcTopo &t) { return (t.span_lo - 1u) / FIT_T != (t.span_hi - 1u) / FIT_T; }
+template <int T>
+__device__ __forceinline__ bool fit_is_spanning(const RcTopo &t) { return (t.span_lo - 1u) / T != (t.span_hi - 1u) / T; }
 
 // boxes (and BVH2 records) of the spanning nodes: a group of FIT_G lanes per node (the kernel is a chain of 3 dependent loads per node, so the
 // parallelism is in nodes, not in lanes), no ordering between nodes
-__global__ void __launch_bounds__(256) k_fit_span(const uint32_t *__restrict__ n_ptr, uint32_t n_host, const RcTopo *__restrict__ topo, const uint32_t *__restrict__ parent,
-                                                  RcBox *__restrict__ boxes, RcNode2 *__restrict__ nodes2, FitWork work) {
+template <int T>
+__device__ __forceinline__ void fit_span_body(const uint32_t *__restrict__ n_ptr, uint32_t n_host, const RcTopo *__restrict__ topo, const uint32_t *__restrict__ parent,
+                                              RcBox *__restrict__ boxes, RcNode2 *__restrict__ nodes2, FitWork work) {
     const uint32_t n = count_of(n_ptr, n_host);
     const uint32_t count = *work.span_count, lane = threadIdx.x & 31u, gl = lane & (FIT_G - 1u);
     const uint32_t mask = (FIT_G == 32u ? 0xFFFFFFFFu : ((1u << (FIT_G & 31u)) - 1u) << (lane & ~(FIT_G - 1u)));
@@ -810,7 +824,7 @@ __global__ void __launch_bounds__(256) k_fit_span(const uint32_t *__restrict__ n
         const uint4 ent = work.span_list[w];
         const uint32_t v = ent.x;
         f3 lo, hi;
-        fit_range_box(work.seg, work.pos_idx, ent.y, ent.z, mask, lo, hi);
+        fit_range_box<T>(work.seg, work.pos_idx, ent.y, ent.z, mask, lo, hi);
         if (gl == 0) st_box(boxes + (v - 1), lo, hi);
         if (nodes2) {  // the BVH2 record holds the children's boxes: a spanning child's box comes from the same formula
             const RcTopo tp = topo[v - 1];
@@ -820,9 +834,9 @@ __global__ void __launch_bounds__(256) k_fit_span(const uint32_t *__restrict__ n
                 const uint32_t c = k == 0 ? tp.child0 : tp.child1;
                 bool span_c = false;
                 RcTopo tc = {0, 0, 0, 0};
-                if (c < n) { tc = topo[c - 1]; span_c = fit_is_spanning(tc); }
+                if (c < n) { tc = topo[c - 1]; span_c = fit_is_spanning<T>(tc); }
                 if (span_c) {
-                    fit_range_box(work.seg, work.pos_idx, tc.span_lo, tc.span_hi, mask, cl[k], ch[k]);
+                    fit_range_box<T>(work.seg, work.pos_idx, tc.span_lo, tc.span_hi, mask, cl[k], ch[k]);
                 } else {  // written by k_fit_local (an earlier launch)
                     const RcBox b = boxes[c - 1];
                     cl[k] = mk3(b.lo[0], b.lo[1], b.lo[2]);
@@ -834,6 +848,11 @@ __global__ void __launch_bounds__(256) k_fit_span(const uint32_t *__restrict__ n
     }
 }
 
+__global__ void __launch_bounds__(256) k_fit_span(const uint32_t *__restrict__ n_ptr, uint32_t n_host, const RcTopo *__restrict__ topo, const uint32_t *__restrict__ parent,
+                                                  RcBox *__restrict__ boxes, RcNode2 *__restrict__ nodes2, FitWork work) {
+    fit_span_body<FIT_T>(n_ptr, n_host, topo, parent, boxes, nodes2, work);
+}
+
 // Wide nodes of the spanning BVH2 nodes (global arrays; the in-block ones were collapsed by k_fit_local), one thread per node.  A BVH2
 // node covering <= leaf_max primitives can never be the root of a wide node (its parent turns it into a leaf reference): zeroed.
 // The last block finishes the build:
@@ -842,9 +861,9 @@ __global__ void __launch_bounds__(256) k_fit_span(const uint32_t *__restrict__ n
 //   n == 1: the synthetic root over the single leaf;  the two wide-node slots nothing else writes (0, and n) are zeroed;
 //   out10 (nullable): root box (6 floats); with ctl also the bounding sphere of a BLAS (centre of the scene bounds, radius^2 inflated
 //     against the rounding of its own evaluation), next to the valid count, so the host reads everything back in one transfer.
-__global__ void __launch_bounds__(256) k_collapse_span(const RcBox *__restrict__ boxes, const RcTopo *__restrict__ topo, const uint32_t *__restrict__ n_ptr, uint32_t n_host,
-                                                       uint32_t leaf_max, const uint32_t *__restrict__ leaf_map, RcNode4 *__restrict__ nodes4, RcBox *__restrict__ hull,
-                                                       FitWork work, float *__restrict__ out10, const uint32_t *__restrict__ ctl, const RcBox *__restrict__ root_boxes) {
+__device__ __forceinline__ void collapse_span_body(const RcBox *__restrict__ boxes, const RcTopo *__restrict__ topo, const uint32_t *__restrict__ n_ptr, uint32_t n_host,
+                                                   uint32_t leaf_max, const uint32_t *__restrict__ leaf_map, RcNode4 *__restrict__ nodes4, RcBox *__restrict__ hull,
+                                                   FitWork work, float *__restrict__ out10, const uint32_t *__restrict__ ctl, const RcBox *__restrict__ root_boxes) {
     const uint32_t n = count_of(n_ptr, n_host);
     if (n == 0) return;
     if (blockIdx.x == gridDim.x - 1) {
@@ -887,6 +906,271 @@ __global__ void __launch_bounds__(256) k_collapse_span(const RcBox *__restrict__
         if (v > 1u && ent.z - ent.y + 1u <= leaf_max) st_node4_zero(nodes4 + v);
         else st_node4(nodes4 + v, rc_collapse_node(v, boxes, topo, n, leaf_max, leaf_map));
     }
+}
+
+__global__ void __launch_bounds__(256) k_collapse_span(const RcBox *__restrict__ boxes, const RcTopo *__restrict__ topo, const uint32_t *__restrict__ n_ptr, uint32_t n_host,
+                                                       uint32_t leaf_max, const uint32_t *__restrict__ leaf_map, RcNode4 *__restrict__ nodes4, RcBox *__restrict__ hull,
+                                                       FitWork work, float *__restrict__ out10, const uint32_t *__restrict__ ctl, const RcBox *__restrict__ root_boxes) {
+    collapse_span_body(boxes, topo, n_ptr, n_host, leaf_max, leaf_map, nodes4, hull, work, out10, ctl, root_boxes);
+}
+
+// =================================================================================================
+// Small meshes (<= SB_MAX_FACES faces): the WHOLE BLAS build as one cooperative kernel.  The five-launch path above spends a small build
+// waiting: 8,192 faces are 4 radix tiles (4 working blocks per phase), every phase is a chain of L2 round trips, and the kernel
+// boundaries cost as much as the kernels (131 us, of which the kernels themselves are 110).  Here a block of SB_T threads owns SB_T
+// faces / sorted leaves / internal nodes in every phase, the grid is cdiv(faces, SB_T) <= 12 blocks, and
+//   F   one face per thread: exact degenerate test, scene bounds, valid count of the block                                   | grid barrier
+//   M   compacted RcTri records + Morton codes (the reference's arithmetic, as in k_front)                                    | grid barrier
+//   S   EVERY block sorts ALL keys in its own shared memory (stable LSD radix, 4 passes of 8 bits, warp-striped ranking through
+//       shared-memory atomicOr peer masks, per-(digit, warp) u16 counters scanned in digit-major order) — redundant work on SMs that would otherwise idle at a barrier,
+//       and the sorted keys end up where the next phase wants them
+//   T   Karras topology of the block's own nodes straight from the sorted keys in shared memory; parent links scattered        | grid barrier
+//   the fit of the five-launch path, its bodies reused as they are: fit_local_body<SB_T> | barrier | fit_span_body<SB_T> | barrier |
+//   collapse_span_body (the last block finishes: hull, sphere, read-back words).
+// Same arithmetic, same output arrays (tris, wide nodes, hull, BVH2 / kept topology when requested) byte for byte.
+// =================================================================================================
+#ifndef RC_SMALL_BUILD
+#define RC_SMALL_BUILD 1
+#endif
+constexpr int SB_T = 1024;
+constexpr int SB_ITEMS_MAX = 12;
+constexpr uint32_t SB_MAX_FACES = RC_SMALL_BUILD ? SB_T * SB_ITEMS_MAX : 0;  // 12,288
+constexpr int SB_DIGITS = 256;
+constexpr uint32_t SB_CNT_ROW_WORDS = 17;  // a digit's 32 u16 counters (one per warp) + one word of padding: rows of 17 words put the 32 digits a warp looks up in one instruction into different banks
+constexpr size_t SB_CNT_BYTES = ((size_t)SB_DIGITS * SB_CNT_ROW_WORDS * 4 + 15) & ~(size_t)15;
+constexpr size_t SB_SORT_BYTES = (size_t)SB_T * SB_ITEMS_MAX * 6 + SB_CNT_BYTES + (size_t)SB_DIGITS * 32 * 4;  // keys u32 + values u16 + counters u16 [digit][warp] + tags u32 [warp][digit]
+constexpr size_t SB_SMEM_BYTES = SB_SORT_BYTES > sizeof(FitSmemT<SB_T>) ? SB_SORT_BYTES : sizeof(FitSmemT<SB_T>);
+struct SmallArgs {
+    const float *verts;
+    const uint32_t *face_meta;  // nullable
+    uint32_t n_faces;
+    RcTri *tris_in;
+    uint32_t *tile_counts;  // gridDim words
+    uint32_t *ctl;
+    uint32_t *keys;   // n_faces: Morton codes of the compacted faces (unsorted)
+    uint32_t *perm;   // n_faces: sorted position -> compacted index
+    RcTopo *topo;
+    uint32_t *parent;
+    RcTri *tris;
+    RcBox *boxes;
+    RcNode2 *nodes2;  // nullable
+    RcNode4 *nodes4;
+    RcBox *hull;
+    uint32_t leaf_max;
+    FitWork work;     // laid out for SB_T leaves per block
+};
+#ifdef RC_FRONT_PROF
+__device__ unsigned long long g_sb_t[96];
+__device__ const char *g_sb_n[96];
+__device__ int g_sb_k;
+#define SB_MARK(name) if (blockIdx.x == 0 && threadIdx.x == 0 && g_sb_k < 96) { g_sb_t[g_sb_k] = prof_now(); g_sb_n[g_sb_k++] = name; }
+#else
+#define SB_MARK(name)
+#endif
+// keys (global, unsorted, n of them) -> skey / sval: the keys sorted (stable) and the original position of every sorted key.
+// Warp w owns the contiguous chunk [w * 32 * ITEMS, ...); item i of lane l = chunk + i * 32 + l, so (i, l) order == memory order.
+template <int ITEMS>
+__device__ __forceinline__ void sb_sort(const uint32_t *__restrict__ gkeys, const uint32_t n, uint32_t *skey, unsigned short *sval, unsigned short *cnt, uint32_t *tag, uint32_t *sm) {
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5, lt_mask = (1u << lane) - 1u;
+    const uint32_t base = wid * (32u * ITEMS);
+    uint32_t key[ITEMS], val[ITEMS], rank[ITEMS], dig[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++) {
+        const uint32_t idx = base + i * 32 + lane;
+        key[i] = idx < n ? __ldcg(gkeys + idx) : 0xFFFFFFFFu;
+        val[i] = idx;
+    }
+    reinterpret_cast<uint4 *>(tag)[tid] = make_uint4(0u, 0u, 0u, 0u);  // 32 warps x 256 tag words, zero between rows
+    reinterpret_cast<uint4 *>(tag)[tid + SB_T] = make_uint4(0u, 0u, 0u, 0u);
+    SB_MARK("load")
+    uint32_t *const my_cnt_words = reinterpret_cast<uint32_t *>(cnt) + (tid >> 2) * SB_CNT_ROW_WORDS + (tid & 3u) * 4u;  // the scan's 8 entries of this thread: digit tid / 4, warps (tid % 4) * 8 ..
+#pragma unroll 1
+    for (int pass = 0; pass < 4; pass++) {
+        const int shift = pass * 8;
+#pragma unroll
+        for (int k = 0; k < 4; k++) my_cnt_words[k] = 0u;
+        __syncthreads();
+        SB_MARK("zero")
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+            // Stable rank of the item among the warp's items of the same digit.  __match_any_sync would give the peer mask in one instruction,
+            // but MATCH occupies the SM for ~85 cycles per call when the lanes' digits are mostly distinct (45 us for the sort of 8 k keys);
+            // instead every lane ORs its bit into the warp's tag word of its digit (shared-memory atomic) and reads the mask back.
+            const bool ok = base + i * 32 + lane < n;
+            dig[i] = ok ? ((key[i] >> shift) & 255u) : (uint32_t)SB_DIGITS;  // SB_DIGITS = padding lane: no rank, not scattered
+            uint32_t *tg = tag + wid * 256u + (dig[i] & 255u);
+            unsigned short *ct = cnt + (dig[i] & 255u) * (2u * SB_CNT_ROW_WORDS) + wid;
+            if (ok) atomicOr(tg, 1u << lane);
+            __syncwarp();
+            const uint32_t peers = ok ? *reinterpret_cast<volatile uint32_t *>(tg) : (1u << lane);
+            __syncwarp();
+            const uint32_t leader = __ffs(peers) - 1;
+            uint32_t prev = 0;
+            if (ok && lane == leader) {
+                *reinterpret_cast<volatile uint32_t *>(tg) = 0u;
+                prev = *ct;
+                *ct = (unsigned short)(prev + __popc(peers));
+            }
+            prev = __shfl_sync(0xFFFFFFFFu, prev, leader);
+            rank[i] = prev + __popc(peers & lt_mask);
+            __syncwarp();
+        }
+        SB_MARK("rank-t0")
+        __syncthreads();
+        SB_MARK("rank")
+        {   // exclusive scan of the counters in digit-major order (8 consecutive entries per thread)
+            uint32_t w[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) w[k] = my_cnt_words[k];
+            uint32_t e[8], local = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) { e[2 * k] = w[k] & 0xFFFFu; e[2 * k + 1] = w[k] >> 16; local += e[2 * k] + e[2 * k + 1]; }
+            uint32_t total_;
+            uint32_t off = block_excl_scan(local, sm, total_);
+            uint32_t o[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) { o[k] = off; off += e[k]; }
+#pragma unroll
+            for (int k = 0; k < 4; k++) my_cnt_words[k] = o[2 * k] | (o[2 * k + 1] << 16);
+        }
+        __syncthreads();
+        SB_MARK("scan")
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+            if (dig[i] < (uint32_t)SB_DIGITS) {
+                const uint32_t pos = cnt[dig[i] * (2u * SB_CNT_ROW_WORDS) + wid] + rank[i];
+                skey[pos] = key[i];
+                sval[pos] = (unsigned short)val[i];
+            }
+        }
+        __syncthreads();
+        SB_MARK("scatter")
+        if (pass < 3) {
+#pragma unroll
+            for (int i = 0; i < ITEMS; i++) {
+                const uint32_t idx = base + i * 32 + lane;
+                key[i] = idx < n ? skey[idx] : 0xFFFFFFFFu;
+                val[i] = idx < n ? sval[idx] : 0u;
+            }
+        }
+    }
+}
+__global__ void __launch_bounds__(SB_T, 1) k_build_small(const SmallArgs A) {
+    extern __shared__ __align__(16) unsigned char sb_raw[];
+    __shared__ uint32_t sm[40];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, lt_mask = (1u << lane) - 1u;
+    uint32_t target = 0;
+    uint32_t *bar = A.ctl + CTL_BAR;
+#ifdef RC_FRONT_PROF
+    unsigned long long prof_t0 = prof_now(), prof_t[48];
+    const char *prof_name[48];
+    int prof_k = 0;
+#endif
+    // ---- F: one face per thread
+    const uint32_t face = blockIdx.x * SB_T + tid;
+    bool valid = false;
+    f3 a = mk3(0, 0, 0), b = a, c = a;
+    f3 lo = mk3(INFINITY, INFINITY, INFINITY), hi = mk3(-INFINITY, -INFINITY, -INFINITY);
+    if (face < A.n_faces) {
+        const float *v = A.verts + (size_t)face * 9;
+        a = ld3(v); b = ld3(v + 3); c = ld3(v + 6);
+        valid = !x_is_degenerate(a, b, c);
+        if (valid) {
+            lo = jl_min3(jl_min3(a, b), c);  // world_bound(tri), triangle_mesh.jl:37
+            hi = jl_max3(jl_max3(a, b), c);
+        }
+    }
+    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, valid);
+    uint32_t tile_total;
+    const uint32_t woff = block_excl_scan(lane == 0 ? (uint32_t)__popc(bal) : 0u, sm, tile_total);  // lane 0 of warp w: valid faces of the warps before it
+    const uint32_t wbase = __shfl_sync(0xFFFFFFFFu, woff, 0);
+    if (tid == 0) A.tile_counts[blockIdx.x] = tile_total;
+    bounds_atomic(A.ctl, lo, hi);
+    RC_PROF_MARK("F")
+    grid_barrier(bar, target);
+    RC_PROF_MARK("F-barrier")
+    // ---- M: compacted records (filter! keeps the order, src/instanced-bvh.jl:591-600) + Morton codes (kernels.jl:88-98; extent unguarded, :1388)
+    uint32_t prefix = 0, n = 0;
+    for (uint32_t k = 0; k < gridDim.x; k++) {
+        const uint32_t cnt = __ldcg(A.tile_counts + k);
+        prefix += k < blockIdx.x ? cnt : 0u;
+        n += cnt;
+    }
+    if (blockIdx.x == 0 && tid == 0) A.ctl[CTL_N] = n;
+    if (valid) {
+        const f3 smin = ldcg3(A.ctl, CTL_BOUNDS, true), smax = ldcg3(A.ctl, CTL_BOUNDS + 3, false);
+        const f3 ext = x_sub3(smax, smin);
+        const uint32_t k = prefix + wbase + __popc(bal & lt_mask);
+        float4 *d = reinterpret_cast<float4 *>(A.tris_in + k);
+        d[0] = make_float4(a.x, a.y, a.z, __uint_as_float(k));
+        d[1] = make_float4(b.x, b.y, b.z, __uint_as_float(A.face_meta ? A.face_meta[face] : face + 1u));  // :595
+        d[2] = make_float4(c.x, c.y, c.z, __uint_as_float(face));
+        const f3 ctr = mk3(x_mul(0.5f, x_add(lo.x, hi.x)), x_mul(0.5f, x_add(lo.y, hi.y)), x_mul(0.5f, x_add(lo.z, hi.z)));
+        const f3 nrm = mk3(x_div(x_sub(ctr.x, smin.x), ext.x), x_div(x_sub(ctr.y, smin.y), ext.y), x_div(x_sub(ctr.z, smin.z), ext.z));
+        A.keys[k] = rc_morton30(nrm);
+    }
+    RC_PROF_MARK("M")
+    grid_barrier(bar, target);
+    RC_PROF_MARK("M-barrier")
+    if (n == 0) return;  // (uniform over the grid)
+    // ---- S: every block sorts all keys
+    uint32_t *skey = reinterpret_cast<uint32_t *>(sb_raw);
+    unsigned short *sval = reinterpret_cast<unsigned short *>(sb_raw + (size_t)SB_T * SB_ITEMS_MAX * 4);
+    unsigned short *cnt = reinterpret_cast<unsigned short *>(sb_raw + (size_t)SB_T * SB_ITEMS_MAX * 6);
+    uint32_t *tag = reinterpret_cast<uint32_t *>(sb_raw + (size_t)SB_T * SB_ITEMS_MAX * 6 + SB_CNT_BYTES);
+    const uint32_t items = (n + SB_T - 1) / SB_T;
+    if (items <= 1) sb_sort<1>(A.keys, n, skey, sval, cnt, tag, sm);
+    else if (items <= 2) sb_sort<2>(A.keys, n, skey, sval, cnt, tag, sm);
+    else if (items <= 4) sb_sort<4>(A.keys, n, skey, sval, cnt, tag, sm);
+    else if (items <= 8) sb_sort<8>(A.keys, n, skey, sval, cnt, tag, sm);
+    else sb_sort<SB_ITEMS_MAX>(A.keys, n, skey, sval, cnt, tag, sm);
+    RC_PROF_MARK("S")
+#ifdef RC_FRONT_PROF
+    if (blockIdx.x == 0 && tid == 0) { for (int q = 1; q < g_sb_k; q++) printf("  sort %-8s %6llu ns\n", g_sb_n[q], g_sb_t[q] - g_sb_t[q - 1]); g_sb_k = 0; }
+#endif
+    // ---- T: topology of this block's internal nodes (k_topology's arithmetic on the shared-memory keys), the block's share of the permutation
+    {
+        const uint32_t p1 = blockIdx.x * SB_T + tid + 1u;  // internal node number / 1-based sorted position
+        if (p1 <= n) A.perm[p1 - 1u] = sval[p1 - 1u];
+        if (n == 1u && p1 == 1u) A.parent[0] = RC_INVALID;
+        if (p1 < n) {
+            const RcTopo t = rc_topology_for_node((int)p1, skey, (int)n);
+            A.topo[p1 - 1u] = t;
+            A.parent[t.child0 - 1u] = p1;  // set_parents_for_node, kernels.jl:159-180
+            A.parent[t.child1 - 1u] = p1;
+            if (p1 == 1u) A.parent[0] = RC_INVALID;
+        }
+    }
+    RC_PROF_MARK("T")
+    grid_barrier(bar, target);  // (its block barrier also retires the sort's shared memory: the fit lays its own arrays over it)
+    RC_PROF_MARK("T-barrier")
+    const uint32_t *n_ptr = A.ctl + CTL_N;
+    fit_local_body<SB_T>(sb_raw, blockIdx.x, A.tris_in, A.perm, A.tris, nullptr, nullptr, n_ptr, A.n_faces, A.topo, A.parent, A.boxes, A.nodes2, A.ctl, A.work, true, A.nodes4,
+                         A.leaf_max);
+    RC_PROF_MARK("fit-local")
+    grid_barrier(bar, target);
+    RC_PROF_MARK("L-barrier")
+    if (gridDim.x > 1) {
+        fit_span_body<SB_T>(n_ptr, A.n_faces, A.topo, A.parent, A.boxes, A.nodes2, A.work);
+        RC_PROF_MARK("fit-span")
+        grid_barrier(bar, target);
+        RC_PROF_MARK("P-barrier")
+    }
+    collapse_span_body(A.boxes, A.topo, n_ptr, A.n_faces, A.leaf_max, nullptr, A.nodes4, A.hull, A.work, reinterpret_cast<float *>(A.ctl + CTL_OUT), A.ctl, nullptr);
+    RC_PROF_MARK("collapse")
+    RC_PROF_DUMP()
+}
+static bool launch_small(cudaStream_t st, SmallArgs &A, std::string &err) {
+    static std::atomic<bool> configured[64];  // per device (zero-initialised; setting the attribute twice is harmless)
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_relaxed)) {
+        CK(cudaFuncSetAttribute(k_build_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SB_SMEM_BYTES));
+        if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_relaxed);
+    }
+    void *args[] = {(void *)&A};
+    CK(cudaLaunchCooperativeKernel((const void *)k_build_small, dim3(cdiv(A.n_faces, SB_T)), dim3(SB_T), args, SB_SMEM_BYTES, st));
+    return true;
 }
 
 // One fit of a built topology: leaf boxes -> boxes of every node (+ BVH2 records) (+ wide nodes, hull, finishing read-back words).
@@ -999,15 +1283,18 @@ bool rc_build_blas(cudaStream_t st, const float *d_verts, const uint32_t *d_face
     RcBox *d_boxes = nullptr;
     uint32_t *d_codes = nullptr, *d_idx = nullptr, *d_codes2 = nullptr, *d_idx2 = nullptr, *d_hist = nullptr, *d_parent = nullptr;
     RcTopo *d_topo = nullptr;
-    TMP(d_ctl, CTL_WORDS + f_tiles);  // control block + the filter's per-tile valid counts
+    const bool small = nf <= SB_MAX_FACES;  // one cooperative kernel instead of the five launches (k_build_small)
+    TMP(d_ctl, CTL_WORDS + std::max(f_tiles, cdiv(nf, SB_T)));  // control block + the filter's per-tile valid counts
     TMP(d_tris_in, nf);
     TMP(d_codes, nf);
     TMP(d_idx, nf);
-    TMP(d_codes2, nf);
-    TMP(d_idx2, nf);
-    TMP(d_hist, radix_hist_words(nf));
+    if (!small) {
+        TMP(d_codes2, nf);
+        TMP(d_idx2, nf);
+        TMP(d_hist, radix_hist_words(nf));
+    }
     unsigned char *d_work = nullptr;
-    TMP(d_work, fit_work_bytes(nf));
+    TMP(d_work, small ? fit_work_bytes(nf, SB_T) : fit_work_bytes(nf));
     TMP(d_boxes, 2 * (size_t)nf);
     // the results outlive this call; on failure the caller releases them with rc_free_blas
     if (keep_topo) {
@@ -1026,6 +1313,18 @@ bool rc_build_blas(cudaStream_t st, const float *d_verts, const uint32_t *d_face
     out->n_faces_in = n_faces;
 
     CK(cudaMemsetAsync(d_ctl, 0, sizeof(uint32_t) * CTL_WORDS, st));
+    if (small) {
+        SmallArgs sa;
+        sa.verts = d_verts; sa.face_meta = d_face_meta; sa.n_faces = n_faces; sa.tris_in = d_tris_in;
+        sa.tile_counts = d_ctl + CTL_WORDS; sa.ctl = d_ctl; sa.keys = d_codes; sa.perm = d_idx;
+        sa.topo = d_topo; sa.parent = d_parent; sa.tris = out->tris; sa.boxes = d_boxes; sa.nodes2 = out->nodes2;
+        sa.nodes4 = out->nodes4; sa.hull = out->hull; sa.leaf_max = RC_BLAS_LEAF_MAX;
+        sa.work = fit_work_at(d_work, nf, SB_T);
+        sa.work.span_count = d_ctl + CTL_NSPAN;  // zeroed with the control block
+        sa.work.err_flag = d_ctl + CTL_ERR;
+        if (!launch_small(st, sa, err)) return false;
+        return finish_blas(st, d_ctl, out, err);
+    }
     FrontArgs fa;
     fa.verts = d_verts; fa.face_meta = d_face_meta; fa.n_faces = n_faces; fa.tris_in = d_tris_in;
     fa.tile_counts = d_ctl + CTL_WORDS; fa.ctl = d_ctl;
