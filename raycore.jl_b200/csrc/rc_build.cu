@@ -202,9 +202,17 @@ __device__ __forceinline__ uint32_t ld_acquire(const uint32_t *p) {
 __device__ __forceinline__ unsigned long long prof_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define RC_PROF_MARK(name) if (blockIdx.x == 0 && threadIdx.x == 0 && prof_k < 48) { prof_t[prof_k] = prof_now(); prof_name[prof_k++] = name; }
 #define RC_PROF_DUMP() if (blockIdx.x == 0 && threadIdx.x == 0) { for (int q = 0; q < prof_k; q++) printf("k_front %-10s %8llu ns\n", prof_name[q], prof_t[q] - (q ? prof_t[q - 1] : prof_t0)); }
+// finer marks inside the phases of k_build_small (device-global so that the shared bodies can set them)
+__device__ unsigned long long g_sb_t[96];
+__device__ const char *g_sb_n[96];
+__device__ int g_sb_k;
+#define SB_MARK(name) if (blockIdx.x == 0 && threadIdx.x == 0 && g_sb_k < 96) { g_sb_t[g_sb_k] = prof_now(); g_sb_n[g_sb_k++] = name; }
+#define SB_DUMP(what) if (blockIdx.x == 0 && threadIdx.x == 0) { for (int q = 1; q < g_sb_k; q++) printf("  %s %-8s %6llu ns\n", what, g_sb_n[q], g_sb_t[q] - g_sb_t[q - 1]); g_sb_k = 0; }
 #else
 #define RC_PROF_MARK(name)
 #define RC_PROF_DUMP()
+#define SB_MARK(name)
+#define SB_DUMP(what)
 #endif
 __device__ __forceinline__ void grid_barrier(uint32_t *bar, uint32_t &target) {
     target += gridDim.x;
@@ -610,9 +618,11 @@ __device__ __forceinline__ void fit_local_body(unsigned char *fit_raw, const uin
         S.par_leaf[tid] = parent[n - 1 + p1 - 1];
         S.flag[tid] = 0;
     }
+    SB_MARK("enter")
     if (tid == 0) S.nseg = 0;
     if (tid < T / 4) S.pos_idx[tid] = 0xFFFFFFFFu;
     __syncthreads();
+    SB_MARK("stage")
     float r2 = 0.0f;
     uint32_t node = RC_INVALID, cs = p1, ce = p1;  // parent of / span of the subtree this thread has finished
     f3 lo = mk3(0, 0, 0), hi = lo;
@@ -649,6 +659,7 @@ __device__ __forceinline__ void fit_local_body(unsigned char *fit_raw, const uin
         S.box_leaf[tid][3] = hi.x; S.box_leaf[tid][4] = hi.y; S.box_leaf[tid][5] = hi.z;
     }
     __syncthreads();
+    SB_MARK("leaves")
     // The climb, one level per round with a block barrier between rounds: a thread that holds a finished subtree counts its arrival at the
     // parent; the second arriver — both children's boxes were stored in earlier rounds — fits the parent and carries on.  (Barrier-
     // ordered: no fences, clean under racecheck; a 1024-leaf range of a Morton-ordered tree is 12-20 levels deep.)
@@ -656,8 +667,11 @@ __device__ __forceinline__ void fit_local_body(unsigned char *fit_raw, const uin
     for (;;) {
         if (active) {
             bool local = false;
+            uint32_t s = 0;
+            RcTopo tp = {0, 0, 0, 0};
             if (node != RC_INVALID && node >= blk_lo && node <= blk_hi) {
-                const RcTopo &tp = S.topo[node - blk_lo];
+                s = node - blk_lo;
+                tp = S.topo[s];
                 local = tp.span_lo >= blk_lo && tp.span_hi <= blk_hi;
             }
             if (!local) {  // the parent reaches beyond the block (or there is none): [cs, ce] is a segment
@@ -668,29 +682,28 @@ __device__ __forceinline__ void fit_local_body(unsigned char *fit_raw, const uin
                     S.seg_box[k][3] = hi.x; S.seg_box[k][4] = hi.y; S.seg_box[k][5] = hi.z;
                 }
                 active = false;
+            } else if (atomicAdd(&S.flag[s], 1u) == 0u) {
+                active = false;  // first arriver: the sibling subtree is not ready
             } else {
-                const uint32_t s = node - blk_lo;
-                if (atomicAdd(&S.flag[s], 1u) == 0u) active = false;  // first arriver: the sibling subtree is not ready
+                // second arriver: its own box is in registers, the sibling's was stored before the last barrier
+                const bool me_left = cs == tp.span_lo;  // the left child covers [span_lo, split]
+                const uint32_t sib = me_left ? tp.child1 : tp.child0, up = S.par_int[s];
+                const float *bs = sib >= n ? S.box_leaf[sib - (n - 1) - blk_lo] : S.box_int[sib - blk_lo];
+                const f3 ls = mk3(bs[0], bs[1], bs[2]), hs = mk3(bs[3], bs[4], bs[5]);
+                const f3 l0 = me_left ? lo : ls, h0 = me_left ? hi : hs, l1 = me_left ? ls : lo, h1 = me_left ? hs : hi;
+                lo = jl_min3(l0, l1);  // get_node_aabb interior branch, :1142-1147
+                hi = jl_max3(h0, h1);
+                if (nodes2) st_node2(nodes2 + (node - 1), l0, h0, l1, h1, tp.child0, tp.child1, up);
+                st_box(boxes + (node - 1), lo, hi);
+                float *bi = S.box_int[s];
+                bi[0] = lo.x; bi[1] = lo.y; bi[2] = lo.z; bi[3] = hi.x; bi[4] = hi.y; bi[5] = hi.z;
+                cs = tp.span_lo; ce = tp.span_hi;
+                node = up;
             }
-        }
-        if (active) {  // second arriver: both children's boxes were stored before the last barrier
-            const uint32_t s = node - blk_lo;
-            const uint32_t c0 = S.topo[s].child0, c1 = S.topo[s].child1, up = S.par_int[s];
-            const float *b0 = c0 >= n ? S.box_leaf[c0 - (n - 1) - blk_lo] : S.box_int[c0 - blk_lo];
-            const float *b1 = c1 >= n ? S.box_leaf[c1 - (n - 1) - blk_lo] : S.box_int[c1 - blk_lo];
-            const f3 l0 = mk3(b0[0], b0[1], b0[2]), h0 = mk3(b0[3], b0[4], b0[5]);
-            const f3 l1 = mk3(b1[0], b1[1], b1[2]), h1 = mk3(b1[3], b1[4], b1[5]);
-            lo = jl_min3(l0, l1);  // get_node_aabb interior branch, :1142-1147
-            hi = jl_max3(h0, h1);
-            if (nodes2) st_node2(nodes2 + (node - 1), l0, h0, l1, h1, c0, c1, up);
-            st_box(boxes + (node - 1), lo, hi);
-            float *bi = S.box_int[s];
-            bi[0] = lo.x; bi[1] = lo.y; bi[2] = lo.z; bi[3] = hi.x; bi[4] = hi.y; bi[5] = hi.z;
-            cs = S.topo[s].span_lo; ce = S.topo[s].span_hi;
-            node = up;
         }
         if (!__syncthreads_or(active)) break;
     }
+    SB_MARK("climb")
     if (tris) {  // bits of a non-negative float order like the float: one atomicMax per warp (lanes without a leaf carry 0)
         const uint32_t m = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(r2));
         if ((tid & 31u) == 0u) atomicMax(&ctl[CTL_R2], m);
@@ -723,6 +736,7 @@ __device__ __forceinline__ void fit_local_body(unsigned char *fit_raw, const uin
     }
     __syncthreads();
     if (tid < T / 4) reinterpret_cast<uint32_t *>(work.pos_idx)[(size_t)block * (T / 4) + tid] = S.pos_idx[tid];
+    SB_MARK("segtab")
     // ---- this block's internal nodes: spanning ones go to the list, the others are collapsed from shared memory
     bool spanning = false;
     RcTopo tp = {0, 0, 0, 0};
@@ -755,6 +769,7 @@ __device__ __forceinline__ void fit_local_body(unsigned char *fit_raw, const uin
         __syncthreads();
         if (own && !skip) list[woff[wid] + __popc(bal & ((1u << lane) - 1u))] = p1;
         __syncthreads();
+        SB_MARK("compact")
         if (tid < woff[32]) {
             const uint32_t v = list[tid];
             const RcNode4 nd = rc_collapse_node_t(
@@ -762,6 +777,7 @@ __device__ __forceinline__ void fit_local_body(unsigned char *fit_raw, const uin
                 [&](uint32_t c) -> RcTopo { return S.topo[c - blk_lo]; }, n, leaf_max, leaf_map);
             st_node4(nodes4 + v, nd);
         }
+        SB_MARK("collapse")
     }
 }
 
@@ -904,7 +920,7 @@ __device__ __forceinline__ void collapse_span_body(const RcBox *__restrict__ box
         const uint4 ent = work.span_list[w];
         const uint32_t v = ent.x;
         if (v > 1u && ent.z - ent.y + 1u <= leaf_max) st_node4_zero(nodes4 + v);
-        else st_node4(nodes4 + v, rc_collapse_node(v, boxes, topo, n, leaf_max, leaf_map));
+        else st_node4(nodes4 + v, rc_collapse_node_cached(v, boxes, topo, n, leaf_max, leaf_map));
     }
 }
 
@@ -938,7 +954,7 @@ constexpr uint32_t SB_MAX_FACES = RC_SMALL_BUILD ? SB_T * SB_ITEMS_MAX : 0;  // 
 constexpr int SB_DIGITS = 256;
 constexpr uint32_t SB_CNT_ROW_WORDS = 17;  // a digit's 32 u16 counters (one per warp) + one word of padding: rows of 17 words put the 32 digits a warp looks up in one instruction into different banks
 constexpr size_t SB_CNT_BYTES = ((size_t)SB_DIGITS * SB_CNT_ROW_WORDS * 4 + 15) & ~(size_t)15;
-constexpr size_t SB_SORT_BYTES = (size_t)SB_T * SB_ITEMS_MAX * 6 + SB_CNT_BYTES + (size_t)SB_DIGITS * 32 * 4;  // keys u32 + values u16 + counters u16 [digit][warp] + tags u32 [warp][digit]
+constexpr size_t SB_SORT_BYTES = (size_t)SB_T * SB_ITEMS_MAX * 6 + 2 * SB_CNT_BYTES + (size_t)SB_DIGITS * 32 * 4;  // keys u32 + values u16 + 2 x counters u16 [digit][warp] + tags u32 [warp][digit]
 constexpr size_t SB_SMEM_BYTES = SB_SORT_BYTES > sizeof(FitSmemT<SB_T>) ? SB_SORT_BYTES : sizeof(FitSmemT<SB_T>);
 struct SmallArgs {
     const float *verts;
@@ -959,14 +975,6 @@ struct SmallArgs {
     uint32_t leaf_max;
     FitWork work;     // laid out for SB_T leaves per block
 };
-#ifdef RC_FRONT_PROF
-__device__ unsigned long long g_sb_t[96];
-__device__ const char *g_sb_n[96];
-__device__ int g_sb_k;
-#define SB_MARK(name) if (blockIdx.x == 0 && threadIdx.x == 0 && g_sb_k < 96) { g_sb_t[g_sb_k] = prof_now(); g_sb_n[g_sb_k++] = name; }
-#else
-#define SB_MARK(name)
-#endif
 // keys (global, unsorted, n of them) -> skey / sval: the keys sorted (stable) and the original position of every sorted key.
 // Warp w owns the contiguous chunk [w * 32 * ITEMS, ...); item i of lane l = chunk + i * 32 + l, so (i, l) order == memory order.
 template <int ITEMS>
@@ -980,29 +988,46 @@ __device__ __forceinline__ void sb_sort(const uint32_t *__restrict__ gkeys, cons
         key[i] = idx < n ? __ldcg(gkeys + idx) : 0xFFFFFFFFu;
         val[i] = idx;
     }
-    reinterpret_cast<uint4 *>(tag)[tid] = make_uint4(0u, 0u, 0u, 0u);  // 32 warps x 256 tag words, zero between rows
-    reinterpret_cast<uint4 *>(tag)[tid + SB_T] = make_uint4(0u, 0u, 0u, 0u);
+    {   // tag table, 32 warps x 256 words; a word is zero between the rows that use it
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int k = 0; k < 2; k++) reinterpret_cast<uint4 *>(tag)[tid + k * SB_T] = z;
+    }
     SB_MARK("load")
-    uint32_t *const my_cnt_words = reinterpret_cast<uint32_t *>(cnt) + (tid >> 2) * SB_CNT_ROW_WORDS + (tid & 3u) * 4u;  // the scan's 8 entries of this thread: digit tid / 4, warps (tid % 4) * 8 ..
+    // the scan's 8 entries of this thread: digit tid / 4, warps (tid % 4) * 8 ..; two counter tables, the idle one is cleared during the scan
+    const uint32_t my_cnt_off = (tid >> 2) * SB_CNT_ROW_WORDS + (tid & 3u) * 4u;
+#pragma unroll
+    for (int k = 0; k < 4; k++) reinterpret_cast<uint32_t *>(cnt)[my_cnt_off + k] = 0u;
+    __syncthreads();
 #pragma unroll 1
     for (int pass = 0; pass < 4; pass++) {
         const int shift = pass * 8;
+        unsigned short *const cnt_p = cnt + (pass & 1) * (SB_CNT_BYTES / 2);
+        uint32_t *const my_cnt_words = reinterpret_cast<uint32_t *>(cnt_p) + my_cnt_off;
+        uint32_t *const other_cnt_words = reinterpret_cast<uint32_t *>(cnt + ((pass & 1) ^ 1) * (SB_CNT_BYTES / 2)) + my_cnt_off;
+        if (pass > 0) {
 #pragma unroll
-        for (int k = 0; k < 4; k++) my_cnt_words[k] = 0u;
-        __syncthreads();
-        SB_MARK("zero")
+            for (int i = 0; i < ITEMS; i++) {
+                const uint32_t idx = base + i * 32 + lane;
+                key[i] = idx < n ? skey[idx] : 0xFFFFFFFFu;
+                val[i] = idx < n ? sval[idx] : 0u;
+            }
+        }
+        // Stable rank of every item among the warp's items of the same digit, row by row (a row = 32 consecutive keys, one per lane).
+        // __match_any_sync would give the peer mask in one instruction, but MATCH occupies the SM for ~85 cycles per call when the lanes'
+        // digits are mostly distinct (45 us for the sort of 8 k keys); instead every lane ORs its bit into the warp's tag word of its
+        // digit (shared-memory atomic) and reads the mask back.  (Keeping the atomic of row i + 1 in flight while row i is finished, with
+        // two tag tables, measured slower: 2.8 instead of 2.5 us per pass.)
+        const uint32_t bit = 1u << lane;
 #pragma unroll
         for (int i = 0; i < ITEMS; i++) {
-            // Stable rank of the item among the warp's items of the same digit.  __match_any_sync would give the peer mask in one instruction,
-            // but MATCH occupies the SM for ~85 cycles per call when the lanes' digits are mostly distinct (45 us for the sort of 8 k keys);
-            // instead every lane ORs its bit into the warp's tag word of its digit (shared-memory atomic) and reads the mask back.
             const bool ok = base + i * 32 + lane < n;
             dig[i] = ok ? ((key[i] >> shift) & 255u) : (uint32_t)SB_DIGITS;  // SB_DIGITS = padding lane: no rank, not scattered
             uint32_t *tg = tag + wid * 256u + (dig[i] & 255u);
-            unsigned short *ct = cnt + (dig[i] & 255u) * (2u * SB_CNT_ROW_WORDS) + wid;
-            if (ok) atomicOr(tg, 1u << lane);
+            unsigned short *ct = cnt_p + (dig[i] & 255u) * (2u * SB_CNT_ROW_WORDS) + wid;
+            if (ok) atomicOr(tg, bit);
             __syncwarp();
-            const uint32_t peers = ok ? *reinterpret_cast<volatile uint32_t *>(tg) : (1u << lane);
+            const uint32_t peers = ok ? *reinterpret_cast<volatile uint32_t *>(tg) : bit;
             __syncwarp();
             const uint32_t leader = __ffs(peers) - 1;
             uint32_t prev = 0;
@@ -1013,7 +1038,7 @@ __device__ __forceinline__ void sb_sort(const uint32_t *__restrict__ gkeys, cons
             }
             prev = __shfl_sync(0xFFFFFFFFu, prev, leader);
             rank[i] = prev + __popc(peers & lt_mask);
-            __syncwarp();
+            __syncwarp();  // the cleared tag word is used again by the next row
         }
         SB_MARK("rank-t0")
         __syncthreads();
@@ -1031,28 +1056,23 @@ __device__ __forceinline__ void sb_sort(const uint32_t *__restrict__ gkeys, cons
 #pragma unroll
             for (int k = 0; k < 8; k++) { o[k] = off; off += e[k]; }
 #pragma unroll
-            for (int k = 0; k < 4; k++) my_cnt_words[k] = o[2 * k] | (o[2 * k + 1] << 16);
+            for (int k = 0; k < 4; k++) {
+                my_cnt_words[k] = o[2 * k] | (o[2 * k + 1] << 16);
+                other_cnt_words[k] = 0u;
+            }
         }
         __syncthreads();
         SB_MARK("scan")
 #pragma unroll
         for (int i = 0; i < ITEMS; i++) {
             if (dig[i] < (uint32_t)SB_DIGITS) {
-                const uint32_t pos = cnt[dig[i] * (2u * SB_CNT_ROW_WORDS) + wid] + rank[i];
+                const uint32_t pos = cnt_p[dig[i] * (2u * SB_CNT_ROW_WORDS) + wid] + rank[i];
                 skey[pos] = key[i];
                 sval[pos] = (unsigned short)val[i];
             }
         }
         __syncthreads();
         SB_MARK("scatter")
-        if (pass < 3) {
-#pragma unroll
-            for (int i = 0; i < ITEMS; i++) {
-                const uint32_t idx = base + i * 32 + lane;
-                key[i] = idx < n ? skey[idx] : 0xFFFFFFFFu;
-                val[i] = idx < n ? sval[idx] : 0u;
-            }
-        }
     }
 }
 __global__ void __launch_bounds__(SB_T, 1) k_build_small(const SmallArgs A) {
@@ -1117,7 +1137,7 @@ __global__ void __launch_bounds__(SB_T, 1) k_build_small(const SmallArgs A) {
     uint32_t *skey = reinterpret_cast<uint32_t *>(sb_raw);
     unsigned short *sval = reinterpret_cast<unsigned short *>(sb_raw + (size_t)SB_T * SB_ITEMS_MAX * 4);
     unsigned short *cnt = reinterpret_cast<unsigned short *>(sb_raw + (size_t)SB_T * SB_ITEMS_MAX * 6);
-    uint32_t *tag = reinterpret_cast<uint32_t *>(sb_raw + (size_t)SB_T * SB_ITEMS_MAX * 6 + SB_CNT_BYTES);
+    uint32_t *tag = reinterpret_cast<uint32_t *>(sb_raw + (size_t)SB_T * SB_ITEMS_MAX * 6 + 2 * SB_CNT_BYTES);
     const uint32_t items = (n + SB_T - 1) / SB_T;
     if (items <= 1) sb_sort<1>(A.keys, n, skey, sval, cnt, tag, sm);
     else if (items <= 2) sb_sort<2>(A.keys, n, skey, sval, cnt, tag, sm);
@@ -1125,9 +1145,7 @@ __global__ void __launch_bounds__(SB_T, 1) k_build_small(const SmallArgs A) {
     else if (items <= 8) sb_sort<8>(A.keys, n, skey, sval, cnt, tag, sm);
     else sb_sort<SB_ITEMS_MAX>(A.keys, n, skey, sval, cnt, tag, sm);
     RC_PROF_MARK("S")
-#ifdef RC_FRONT_PROF
-    if (blockIdx.x == 0 && tid == 0) { for (int q = 1; q < g_sb_k; q++) printf("  sort %-8s %6llu ns\n", g_sb_n[q], g_sb_t[q] - g_sb_t[q - 1]); g_sb_k = 0; }
-#endif
+    SB_DUMP("sort")
     // ---- T: topology of this block's internal nodes (k_topology's arithmetic on the shared-memory keys), the block's share of the permutation
     {
         const uint32_t p1 = blockIdx.x * SB_T + tid + 1u;  // internal node number / 1-based sorted position
@@ -1148,6 +1166,7 @@ __global__ void __launch_bounds__(SB_T, 1) k_build_small(const SmallArgs A) {
     fit_local_body<SB_T>(sb_raw, blockIdx.x, A.tris_in, A.perm, A.tris, nullptr, nullptr, n_ptr, A.n_faces, A.topo, A.parent, A.boxes, A.nodes2, A.ctl, A.work, true, A.nodes4,
                          A.leaf_max);
     RC_PROF_MARK("fit-local")
+    SB_DUMP("fit")
     grid_barrier(bar, target);
     RC_PROF_MARK("L-barrier")
     if (gridDim.x > 1) {
@@ -1284,18 +1303,31 @@ bool rc_build_blas(cudaStream_t st, const float *d_verts, const uint32_t *d_face
     uint32_t *d_codes = nullptr, *d_idx = nullptr, *d_codes2 = nullptr, *d_idx2 = nullptr, *d_hist = nullptr, *d_parent = nullptr;
     RcTopo *d_topo = nullptr;
     const bool small = nf <= SB_MAX_FACES;  // one cooperative kernel instead of the five launches (k_build_small)
-    TMP(d_ctl, CTL_WORDS + std::max(f_tiles, cdiv(nf, SB_T)));  // control block + the filter's per-tile valid counts
-    TMP(d_tris_in, nf);
-    TMP(d_codes, nf);
-    TMP(d_idx, nf);
+    // every temporary of the build comes out of ONE stream-ordered allocation: a small build is as long as a dozen cudaMallocAsync /
+    // cudaFreeAsync calls on the host, and the GPU waits for the launch behind them
+    size_t arena_bytes = 0;
+    auto carve = [&](size_t bytes) { const size_t at = arena_bytes; arena_bytes += (bytes + 255) & ~(size_t)255; return at; };
+    const size_t o_ctl = carve(sizeof(uint32_t) * (CTL_WORDS + std::max(f_tiles, cdiv(nf, SB_T))));  // control block + the filter's per-tile valid counts
+    const size_t o_tris_in = carve(sizeof(RcTri) * (size_t)nf);
+    const size_t o_codes = carve(sizeof(uint32_t) * (size_t)nf), o_idx = carve(sizeof(uint32_t) * (size_t)nf);
+    const size_t o_codes2 = small ? 0 : carve(sizeof(uint32_t) * (size_t)nf), o_idx2 = small ? 0 : carve(sizeof(uint32_t) * (size_t)nf);
+    const size_t o_hist = small ? 0 : carve(sizeof(uint32_t) * radix_hist_words(nf));
+    const size_t o_work = carve(small ? fit_work_bytes(nf, SB_T) : fit_work_bytes(nf));
+    const size_t o_boxes = carve(sizeof(RcBox) * 2 * (size_t)nf);
+    const size_t o_topo = keep_topo ? 0 : carve(sizeof(RcTopo) * (size_t)nf), o_parent = keep_topo ? 0 : carve(sizeof(uint32_t) * 2 * (size_t)nf);
+    unsigned char *arena = nullptr;
+    TMP(arena, arena_bytes);
+    d_ctl = reinterpret_cast<uint32_t *>(arena + o_ctl);
+    d_tris_in = reinterpret_cast<RcTri *>(arena + o_tris_in);
+    d_codes = reinterpret_cast<uint32_t *>(arena + o_codes);
+    d_idx = reinterpret_cast<uint32_t *>(arena + o_idx);
     if (!small) {
-        TMP(d_codes2, nf);
-        TMP(d_idx2, nf);
-        TMP(d_hist, radix_hist_words(nf));
+        d_codes2 = reinterpret_cast<uint32_t *>(arena + o_codes2);
+        d_idx2 = reinterpret_cast<uint32_t *>(arena + o_idx2);
+        d_hist = reinterpret_cast<uint32_t *>(arena + o_hist);
     }
-    unsigned char *d_work = nullptr;
-    TMP(d_work, small ? fit_work_bytes(nf, SB_T) : fit_work_bytes(nf));
-    TMP(d_boxes, 2 * (size_t)nf);
+    unsigned char *d_work = arena + o_work;
+    d_boxes = reinterpret_cast<RcBox *>(arena + o_boxes);
     // the results outlive this call; on failure the caller releases them with rc_free_blas
     if (keep_topo) {
         CK(cudaMallocAsync(&out->topo, sizeof(RcTopo) * (size_t)nf, st));
@@ -1303,8 +1335,8 @@ bool rc_build_blas(cudaStream_t st, const float *d_verts, const uint32_t *d_face
         d_topo = out->topo;
         d_parent = out->parent;
     } else {
-        TMP(d_topo, nf);
-        TMP(d_parent, 2 * (size_t)nf);
+        d_topo = reinterpret_cast<RcTopo *>(arena + o_topo);
+        d_parent = reinterpret_cast<uint32_t *>(arena + o_parent);
     }
     if (keep_bvh2) CK(cudaMallocAsync(&out->nodes2, sizeof(RcNode2) * 2 * (size_t)nf, st));
     CK(cudaMallocAsync(&out->nodes4, sizeof(RcNode4) * ((size_t)nf + 1), st));

@@ -181,6 +181,108 @@ RC_HD RcNode4 rc_collapse_node(uint32_t idx, const RcBox *boxes, const RcTopo *t
         idx, [&](uint32_t c) -> RcBox { return boxes[c - 1]; }, [&](uint32_t c) -> RcTopo { return topo[c - 1]; }, n, leaf_max, leaf_map);
 }
 
+// rc_collapse_node with every BVH2 record fetched once and the fetches of a step independent of each other: a slot carries the count, box,
+// children and first position of its node, so opening a slot is ONE round of loads (its two children) instead of a chain of ~10
+// dependent ones.  For the global-memory callers (k_collapse_span: a spanning node was ~40 dependent L2 round trips); same selection
+// order and arithmetic, bit-identical result.  No dynamically indexed arrays (they would live in local memory).
+struct RcCollapseSlot {
+    uint32_t node, count, c0, c1, first;  // first: 0-based sorted position of the first primitive
+    RcBox box;
+};
+RC_HD RcCollapseSlot rc_collapse_fetch(uint32_t c, const RcBox *boxes, const RcTopo *topo, uint32_t n) {
+    RcCollapseSlot s;
+    s.node = c;
+    s.box = boxes[c - 1];
+    if (c >= n) {
+        s.count = 1u; s.c0 = 0u; s.c1 = 0u; s.first = c - n;
+    } else {
+        const RcTopo t = topo[c - 1];
+        s.count = t.span_hi - t.span_lo + 1u; s.c0 = t.child0; s.c1 = t.child1; s.first = t.span_lo - 1u;
+    }
+    return s;
+}
+RC_HD RcNode4 rc_collapse_node_cached(uint32_t idx, const RcBox *boxes, const RcTopo *topo, uint32_t n, uint32_t leaf_max, const uint32_t *leaf_map) {
+    const RcCollapseSlot own = rc_collapse_fetch(idx, boxes, topo, n);
+    RcCollapseSlot sl[4];
+    int ns = 0;
+    if (idx >= n || own.count <= leaf_max) {
+        sl[0] = own;  // degenerate root: whole BLAS is one leaf
+        ns = 1;
+    } else {
+        sl[0] = rc_collapse_fetch(own.c0, boxes, topo, n);
+        sl[1] = rc_collapse_fetch(own.c1, boxes, topo, n);
+        ns = 2;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int stage = 2; stage < 4; stage++) {  // open the slot with the largest area until four are used
+            if (ns != stage) break;
+            int best = -1;
+            float best_area = -1.0f;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int k = 0; k < 3; k++) {
+                if (k < stage && sl[k].node < n && sl[k].count > leaf_max) {
+                    const float a = rc_half_area(sl[k].box);
+                    if (a > best_area) { best_area = a; best = k; }
+                }
+            }
+            if (best < 0) break;
+            uint32_t c0 = 0, c1 = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int k = 0; k < 3; k++)
+                if (k == best) { c0 = sl[k].c0; c1 = sl[k].c1; }
+            const RcCollapseSlot a = rc_collapse_fetch(c0, boxes, topo, n), b = rc_collapse_fetch(c1, boxes, topo, n);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int k = 0; k < 3; k++)
+                if (k == best) sl[k] = a;
+            sl[stage] = b;
+            ns = stage + 1;
+        }
+    }
+    RcNode4 nd;
+    nd.ox = own.box.lo[0]; nd.oy = own.box.lo[1]; nd.oz = own.box.lo[2];
+    const uint32_t ex = rc_quant_exponent(own.box.hi[0] - own.box.lo[0]);
+    const uint32_t ey = rc_quant_exponent(own.box.hi[1] - own.box.lo[1]);
+    const uint32_t ez = rc_quant_exponent(own.box.hi[2] - own.box.lo[2]);
+    nd.sx = u2f((ex + 24u) << 23); nd.sy = u2f((ey + 24u) << 23); nd.sz = u2f((ez + 24u) << 23);
+    const float sx = u2f(ex << 23), sy = u2f(ey << 23), sz = u2f(ez << 23);
+    uint32_t qlo[3] = {0, 0, 0}, qhi[3] = {0, 0, 0}, ch[4] = {0, 0, 0, 0};
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 4; k++) {
+        if (k >= ns) {  // unused slot: inverted box + child 0's reference (filled in below)
+            for (int a = 0; a < 3; a++) qlo[a] |= 255u << (8 * k);
+            continue;
+        }
+        const RcCollapseSlot &c = sl[k];
+        qlo[0] |= rc_quant_lo(c.box.lo[0], nd.ox, sx) << (8 * k);
+        qlo[1] |= rc_quant_lo(c.box.lo[1], nd.oy, sy) << (8 * k);
+        qlo[2] |= rc_quant_lo(c.box.lo[2], nd.oz, sz) << (8 * k);
+        qhi[0] |= rc_quant_hi(c.box.hi[0], nd.ox, sx) << (8 * k);
+        qhi[1] |= rc_quant_hi(c.box.hi[1], nd.oy, sy) << (8 * k);
+        qhi[2] |= rc_quant_hi(c.box.hi[2], nd.oz, sz) << (8 * k);
+        if (c.node >= n) ch[k] = leaf_map ? (RC_TLAS_LEAF_TAG | leaf_map[c.first]) : (RC_LEAF_BIT | c.first);
+        else if (c.count <= leaf_max) ch[k] = RC_LEAF_BIT | ((c.count - 1u) << RC_LEAF_COUNT_SHIFT) | (leaf_map ? leaf_map[c.first] : c.first);
+        else ch[k] = c.node;
+    }
+    nd.qlox = qlo[0]; nd.qloy = qlo[1]; nd.qloz = qlo[2];
+    nd.qhix = qhi[0]; nd.qhiy = qhi[1]; nd.qhiz = qhi[2];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 1; k < 4; k++)
+        if (k >= ns) ch[k] = ch[0];
+    nd.child0 = ch[0]; nd.child1 = ch[1]; nd.child2 = ch[2]; nd.child3 = ch[3];
+    return nd;
+}
+
 // Structural check of a BLAS (used on imported blobs).  A blob that passes can neither send a traversal out of bounds nor into an
 // endless loop.  Two parts:
 //   rc_validate_static_elem(i), i = 0 .. 2n-1: triangle i has prim_id < n and face_index < n_faces_in (rc_set_normals gathers by it);

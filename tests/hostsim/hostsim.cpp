@@ -58,6 +58,7 @@ void set_box(RcBox &b, f3 lo, f3 hi) {
     b.hi[0] = hi.x; b.hi[1] = hi.y; b.hi[2] = hi.z; b.pad1 = 0;
 }
 
+unsigned long long g_collapse_checked = 0, g_collapse_mismatch = 0;
 // stands in for k_topology + k_fit + k_collapse
 void build_tree(HsTree &t, const std::vector<uint32_t> &codes_sorted, const RcTri *tris, const std::vector<RcBox> *inst_boxes, uint32_t leaf_max) {
     uint32_t n = (uint32_t)codes_sorted.size();
@@ -106,8 +107,14 @@ void build_tree(HsTree &t, const std::vector<uint32_t> &codes_sorted, const RcTr
         }
     }
     uint32_t n_int = n > 1 ? n - 1 : 1;
-    for (uint32_t i = 0; i < n_int; i++)
-        t.nodes4[i + 1] = rc_collapse_node(i + 1, t.boxes.data(), t.topo.data(), n, leaf_max, t.leaf_map.empty() ? nullptr : t.leaf_map.data());
+    for (uint32_t i = 0; i < n_int; i++) {
+        const uint32_t *lm = t.leaf_map.empty() ? nullptr : t.leaf_map.data();
+        t.nodes4[i + 1] = rc_collapse_node(i + 1, t.boxes.data(), t.topo.data(), n, leaf_max, lm);
+        // the fetch-once form k_collapse_span uses for the spanning nodes must give the same bytes
+        const RcNode4 c = rc_collapse_node_cached(i + 1, t.boxes.data(), t.topo.data(), n, leaf_max, lm);
+        g_collapse_checked++;
+        if (memcmp(&c, &t.nodes4[i + 1], sizeof c) != 0) g_collapse_mismatch++;
+    }
     for (int k = 0; k < 3; k++) { t.root[k] = t.boxes[0].lo[k]; t.root[3 + k] = t.boxes[0].hi[k]; }
 }
 
@@ -124,6 +131,9 @@ void stable_sort_pairs(std::vector<uint32_t> &codes, std::vector<uint32_t> &idx)
 }  // namespace
 
 extern "C" {
+
+// rc_collapse_node_cached against rc_collapse_node over every wide node built so far in this process: {checked, mismatches}
+void hs_collapse_cached_stats(unsigned long long *out2) { out2[0] = g_collapse_checked; out2[1] = g_collapse_mismatch; }
 
 void *hs_blas_build(const float *verts, uint32_t n_faces, const uint32_t *face_meta) {
     std::vector<RcTri> tris_in;

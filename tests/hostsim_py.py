@@ -40,6 +40,8 @@ def lib():
         L.hs_primary_rays.argtypes = [vp, vp, vp, vp, C.c_float, C.c_float, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, vp]
         L.hs_shadow_rays.restype = None
         L.hs_shadow_rays.argtypes = [vp, vp, vp, C.c_uint64, vp, vp, C.c_uint32, C.c_float, vp]
+        L.hs_collapse_cached_stats.restype = None
+        L.hs_collapse_cached_stats.argtypes = [vp]
         L.hs_check_wide.restype = C.c_uint32
         L.hs_check_wide.argtypes = [vp]
         L.hs_trace_warpsim.restype = C.c_uint32
@@ -48,6 +50,13 @@ def lib():
         L.hs_validate_blas.argtypes = [vp, C.c_int, C.c_uint32]
         _lib = L
     return _lib
+
+
+def collapse_cached_stats():
+    """(wide nodes checked, mismatches) of rc_collapse_node_cached against rc_collapse_node over every tree built in this process."""
+    out = np.zeros(2, np.uint64)
+    lib().hs_collapse_cached_stats(out.ctypes.data)
+    return int(out[0]), int(out[1])
 
 
 class HsBlas:

@@ -34,6 +34,16 @@ def test_builder_bit_exact_vs_oracle():
         assert hb.check_wide() == 0, "a quantised child box does not contain its exact box"
 
 
+def test_collapse_fetch_once_form_is_bit_identical():
+    """k_collapse_span collapses the spanning nodes with rc_collapse_node_cached (each BVH2 record fetched once); the host build runs it
+    beside rc_collapse_node for every wide node (BLAS: 2-triangle leaves; TLAS: tagged instance leaves through leaf_map)."""
+    for verts in (kat.TRI, W.quad_mesh(), W.box_mesh(), W.uv_sphere(9), W.bumpy_sphere(31)):
+        hs.HsBlas(verts)
+    engines.HostsimEngine(_scene_instanced())
+    checked, bad = hs.collapse_cached_stats()
+    assert checked > 2000 and bad == 0
+
+
 def test_tlas_bit_exact_vs_oracle():
     pushes = _scene_instanced()
     o = engines.OracleEngine(pushes)
