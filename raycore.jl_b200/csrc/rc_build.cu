@@ -662,7 +662,9 @@ __device__ __forceinline__ void fit_local_body(unsigned char *fit_raw, const uin
     SB_MARK("leaves")
     // The climb, one level per round with a block barrier between rounds: a thread that holds a finished subtree counts its arrival at the
     // parent; the second arriver — both children's boxes were stored in earlier rounds — fits the parent and carries on.  (Barrier-
-    // ordered: no fences, clean under racecheck; a 1024-leaf range of a Morton-ordered tree is 12-20 levels deep.)
+    // ordered: no fences, clean under racecheck; a 1024-leaf range of a Morton-ordered tree is 12-20 levels deep.  Letting a thread climb
+    // several levels per round when the sibling arrived in an earlier round was measured slower: the rounds are issue-bound, not
+    // barrier-bound.)
     bool active = has_leaf;
     for (;;) {
         if (active) {
@@ -915,8 +917,9 @@ __device__ __forceinline__ void collapse_span_body(const RcBox *__restrict__ box
         return;
     }
     if (!nodes4) return;
-    const uint32_t count = *work.span_count, threads = (gridDim.x - 1) * blockDim.x;
-    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < count; w += threads) {
+    // (entry w goes to block w mod nb: a short list is spread over the SMs instead of filling the first blocks' warps)
+    const uint32_t count = *work.span_count, nb = gridDim.x - 1, threads = nb * blockDim.x;
+    for (uint32_t w = threadIdx.x * nb + blockIdx.x; w < count; w += threads) {
         const uint4 ent = work.span_list[w];
         const uint32_t v = ent.x;
         if (v > 1u && ent.z - ent.y + 1u <= leaf_max) st_node4_zero(nodes4 + v);
@@ -933,29 +936,31 @@ __global__ void __launch_bounds__(256) k_collapse_span(const RcBox *__restrict__
 // =================================================================================================
 // Small meshes (<= SB_MAX_FACES faces): the WHOLE BLAS build as one cooperative kernel.  The five-launch path above spends a small build
 // waiting: 8,192 faces are 4 radix tiles (4 working blocks per phase), every phase is a chain of L2 round trips, and the kernel
-// boundaries cost as much as the kernels (131 us, of which the kernels themselves are 110).  Here a block of SB_T threads owns SB_T
-// faces / sorted leaves / internal nodes in every phase, the grid is cdiv(faces, SB_T) <= 12 blocks, and
+// boundaries cost as much as the kernels (131 us, of which the kernels themselves are 110).  Here a block (SB_T threads) owns SB_FT
+// faces / sorted leaves / internal nodes in every phase, the grid is cdiv(faces, SB_FT) <= 48 blocks, and
 //   F   one face per thread: exact degenerate test, scene bounds, valid count of the block                                   | grid barrier
 //   M   compacted RcTri records + Morton codes (the reference's arithmetic, as in k_front)                                    | grid barrier
-//   S   EVERY block sorts ALL keys in its own shared memory (stable LSD radix, 4 passes of 8 bits, warp-striped ranking through
-//       shared-memory atomicOr peer masks, per-(digit, warp) u16 counters scanned in digit-major order) — redundant work on SMs that would otherwise idle at a barrier,
-//       and the sorted keys end up where the next phase wants them
-//   T   Karras topology of the block's own nodes straight from the sorted keys in shared memory; parent links scattered        | grid barrier
-//   the fit of the five-launch path, its bodies reused as they are: fit_local_body<SB_T> | barrier | fit_span_body<SB_T> | barrier |
+//   S1  the block sorts its own run of SB_FT keys by counting (rank = keys of the run that are smaller, or equal and earlier: stable)    | grid barrier
+//   S2  every block reads all runs into shared memory and places ITS keys: final position = rank in the run + for every other run the
+//       number of its keys that are smaller (later runs) or not larger (earlier runs: they hold the earlier faces) — one binary
+//       search per (key, run), 4 threads per key; sorted keys and the permutation go to global memory                                    | grid barrier
+//       (A full shared-memory radix sort of all keys in every block — 4 passes of 8 bits, atomicOr peer masks for the ranks — took 22 us
+//       of a 65 us build, a MATCH-based one 45 us; this merge of sorted runs is the same stable order for a fraction of the work.)
+//   T   every block reads the sorted keys into shared memory; Karras topology of the block's own nodes from there; parent links scattered  | grid barrier
+//   the fit of the five-launch path, its bodies reused as they are: fit_local_body<SB_FT> | barrier | fit_span_body<SB_FT> | barrier |
 //   collapse_span_body (the last block finishes: hull, sphere, read-back words).
 // Same arithmetic, same output arrays (tris, wide nodes, hull, BVH2 / kept topology when requested) byte for byte.
 // =================================================================================================
 #ifndef RC_SMALL_BUILD
 #define RC_SMALL_BUILD 1
 #endif
-constexpr int SB_T = 1024;
+constexpr int SB_T = 1024;   // threads per block: the sort wants many warps
+constexpr int SB_FT = 256;   // faces / sorted leaves / internal nodes a block owns in the other phases: 8,192 faces spread over 32 SMs (the climb and the
+                             // collapse are issue-bound per SM: with 1,024 leaves per block they took 9 + 4.5 us of a 65 us build)
 constexpr int SB_ITEMS_MAX = 12;
 constexpr uint32_t SB_MAX_FACES = RC_SMALL_BUILD ? SB_T * SB_ITEMS_MAX : 0;  // 12,288
-constexpr int SB_DIGITS = 256;
-constexpr uint32_t SB_CNT_ROW_WORDS = 17;  // a digit's 32 u16 counters (one per warp) + one word of padding: rows of 17 words put the 32 digits a warp looks up in one instruction into different banks
-constexpr size_t SB_CNT_BYTES = ((size_t)SB_DIGITS * SB_CNT_ROW_WORDS * 4 + 15) & ~(size_t)15;
-constexpr size_t SB_SORT_BYTES = (size_t)SB_T * SB_ITEMS_MAX * 6 + 2 * SB_CNT_BYTES + (size_t)SB_DIGITS * 32 * 4;  // keys u32 + values u16 + 2 x counters u16 [digit][warp] + tags u32 [warp][digit]
-constexpr size_t SB_SMEM_BYTES = SB_SORT_BYTES > sizeof(FitSmemT<SB_T>) ? SB_SORT_BYTES : sizeof(FitSmemT<SB_T>);
+constexpr size_t SB_SORT_BYTES = (size_t)SB_MAX_FACES * 4 + SB_FT * 4;  // all keys + the rank accumulators of the block's run
+constexpr size_t SB_SMEM_BYTES = SB_SORT_BYTES > sizeof(FitSmemT<SB_FT>) ? SB_SORT_BYTES : sizeof(FitSmemT<SB_FT>);
 struct SmallArgs {
     const float *verts;
     const uint32_t *face_meta;  // nullable
@@ -963,8 +968,9 @@ struct SmallArgs {
     RcTri *tris_in;
     uint32_t *tile_counts;  // gridDim words
     uint32_t *ctl;
-    uint32_t *keys;   // n_faces: Morton codes of the compacted faces (unsorted)
+    uint32_t *keys;   // n_faces: Morton codes of the compacted faces; after the merge: the sorted codes
     uint32_t *perm;   // n_faces: sorted position -> compacted index
+    uint32_t *run_keys, *run_idx;  // n_faces each: the sorted runs (SB_FT keys each) between the two sort phases
     RcTopo *topo;
     uint32_t *parent;
     RcTri *tris;
@@ -973,108 +979,8 @@ struct SmallArgs {
     RcNode4 *nodes4;
     RcBox *hull;
     uint32_t leaf_max;
-    FitWork work;     // laid out for SB_T leaves per block
+    FitWork work;     // laid out for SB_FT leaves per block
 };
-// keys (global, unsorted, n of them) -> skey / sval: the keys sorted (stable) and the original position of every sorted key.
-// Warp w owns the contiguous chunk [w * 32 * ITEMS, ...); item i of lane l = chunk + i * 32 + l, so (i, l) order == memory order.
-template <int ITEMS>
-__device__ __forceinline__ void sb_sort(const uint32_t *__restrict__ gkeys, const uint32_t n, uint32_t *skey, unsigned short *sval, unsigned short *cnt, uint32_t *tag, uint32_t *sm) {
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5, lt_mask = (1u << lane) - 1u;
-    const uint32_t base = wid * (32u * ITEMS);
-    uint32_t key[ITEMS], val[ITEMS], rank[ITEMS], dig[ITEMS];
-#pragma unroll
-    for (int i = 0; i < ITEMS; i++) {
-        const uint32_t idx = base + i * 32 + lane;
-        key[i] = idx < n ? __ldcg(gkeys + idx) : 0xFFFFFFFFu;
-        val[i] = idx;
-    }
-    {   // tag table, 32 warps x 256 words; a word is zero between the rows that use it
-        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-        for (int k = 0; k < 2; k++) reinterpret_cast<uint4 *>(tag)[tid + k * SB_T] = z;
-    }
-    SB_MARK("load")
-    // the scan's 8 entries of this thread: digit tid / 4, warps (tid % 4) * 8 ..; two counter tables, the idle one is cleared during the scan
-    const uint32_t my_cnt_off = (tid >> 2) * SB_CNT_ROW_WORDS + (tid & 3u) * 4u;
-#pragma unroll
-    for (int k = 0; k < 4; k++) reinterpret_cast<uint32_t *>(cnt)[my_cnt_off + k] = 0u;
-    __syncthreads();
-#pragma unroll 1
-    for (int pass = 0; pass < 4; pass++) {
-        const int shift = pass * 8;
-        unsigned short *const cnt_p = cnt + (pass & 1) * (SB_CNT_BYTES / 2);
-        uint32_t *const my_cnt_words = reinterpret_cast<uint32_t *>(cnt_p) + my_cnt_off;
-        uint32_t *const other_cnt_words = reinterpret_cast<uint32_t *>(cnt + ((pass & 1) ^ 1) * (SB_CNT_BYTES / 2)) + my_cnt_off;
-        if (pass > 0) {
-#pragma unroll
-            for (int i = 0; i < ITEMS; i++) {
-                const uint32_t idx = base + i * 32 + lane;
-                key[i] = idx < n ? skey[idx] : 0xFFFFFFFFu;
-                val[i] = idx < n ? sval[idx] : 0u;
-            }
-        }
-        // Stable rank of every item among the warp's items of the same digit, row by row (a row = 32 consecutive keys, one per lane).
-        // __match_any_sync would give the peer mask in one instruction, but MATCH occupies the SM for ~85 cycles per call when the lanes'
-        // digits are mostly distinct (45 us for the sort of 8 k keys); instead every lane ORs its bit into the warp's tag word of its
-        // digit (shared-memory atomic) and reads the mask back.  (Keeping the atomic of row i + 1 in flight while row i is finished, with
-        // two tag tables, measured slower: 2.8 instead of 2.5 us per pass.)
-        const uint32_t bit = 1u << lane;
-#pragma unroll
-        for (int i = 0; i < ITEMS; i++) {
-            const bool ok = base + i * 32 + lane < n;
-            dig[i] = ok ? ((key[i] >> shift) & 255u) : (uint32_t)SB_DIGITS;  // SB_DIGITS = padding lane: no rank, not scattered
-            uint32_t *tg = tag + wid * 256u + (dig[i] & 255u);
-            unsigned short *ct = cnt_p + (dig[i] & 255u) * (2u * SB_CNT_ROW_WORDS) + wid;
-            if (ok) atomicOr(tg, bit);
-            __syncwarp();
-            const uint32_t peers = ok ? *reinterpret_cast<volatile uint32_t *>(tg) : bit;
-            __syncwarp();
-            const uint32_t leader = __ffs(peers) - 1;
-            uint32_t prev = 0;
-            if (ok && lane == leader) {
-                *reinterpret_cast<volatile uint32_t *>(tg) = 0u;
-                prev = *ct;
-                *ct = (unsigned short)(prev + __popc(peers));
-            }
-            prev = __shfl_sync(0xFFFFFFFFu, prev, leader);
-            rank[i] = prev + __popc(peers & lt_mask);
-            __syncwarp();  // the cleared tag word is used again by the next row
-        }
-        SB_MARK("rank-t0")
-        __syncthreads();
-        SB_MARK("rank")
-        {   // exclusive scan of the counters in digit-major order (8 consecutive entries per thread)
-            uint32_t w[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) w[k] = my_cnt_words[k];
-            uint32_t e[8], local = 0;
-#pragma unroll
-            for (int k = 0; k < 4; k++) { e[2 * k] = w[k] & 0xFFFFu; e[2 * k + 1] = w[k] >> 16; local += e[2 * k] + e[2 * k + 1]; }
-            uint32_t total_;
-            uint32_t off = block_excl_scan(local, sm, total_);
-            uint32_t o[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++) { o[k] = off; off += e[k]; }
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                my_cnt_words[k] = o[2 * k] | (o[2 * k + 1] << 16);
-                other_cnt_words[k] = 0u;
-            }
-        }
-        __syncthreads();
-        SB_MARK("scan")
-#pragma unroll
-        for (int i = 0; i < ITEMS; i++) {
-            if (dig[i] < (uint32_t)SB_DIGITS) {
-                const uint32_t pos = cnt_p[dig[i] * (2u * SB_CNT_ROW_WORDS) + wid] + rank[i];
-                skey[pos] = key[i];
-                sval[pos] = (unsigned short)val[i];
-            }
-        }
-        __syncthreads();
-        SB_MARK("scatter")
-    }
-}
 __global__ void __launch_bounds__(SB_T, 1) k_build_small(const SmallArgs A) {
     extern __shared__ __align__(16) unsigned char sb_raw[];
     __shared__ uint32_t sm[40];
@@ -1087,11 +993,11 @@ __global__ void __launch_bounds__(SB_T, 1) k_build_small(const SmallArgs A) {
     int prof_k = 0;
 #endif
     // ---- F: one face per thread
-    const uint32_t face = blockIdx.x * SB_T + tid;
+    const uint32_t face = blockIdx.x * SB_FT + tid;
     bool valid = false;
     f3 a = mk3(0, 0, 0), b = a, c = a;
     f3 lo = mk3(INFINITY, INFINITY, INFINITY), hi = mk3(-INFINITY, -INFINITY, -INFINITY);
-    if (face < A.n_faces) {
+    if (tid < (uint32_t)SB_FT && face < A.n_faces) {
         const float *v = A.verts + (size_t)face * 9;
         a = ld3(v); b = ld3(v + 3); c = ld3(v + 6);
         valid = !x_is_degenerate(a, b, c);
@@ -1111,10 +1017,12 @@ __global__ void __launch_bounds__(SB_T, 1) k_build_small(const SmallArgs A) {
     RC_PROF_MARK("F-barrier")
     // ---- M: compacted records (filter! keeps the order, src/instanced-bvh.jl:591-600) + Morton codes (kernels.jl:88-98; extent unguarded, :1388)
     uint32_t prefix = 0, n = 0;
-    for (uint32_t k = 0; k < gridDim.x; k++) {
-        const uint32_t cnt = __ldcg(A.tile_counts + k);
-        prefix += k < blockIdx.x ? cnt : 0u;
-        n += cnt;
+    {   // one load per thread + a block scan (a serial loop over the <= 48 counts was 5 us: one L2 round trip each)
+        const uint32_t cnt = tid < gridDim.x ? __ldcg(A.tile_counts + tid) : 0u;
+        const uint32_t ex = block_excl_scan(cnt, sm, n);
+        if (tid == blockIdx.x) sm[36] = ex;
+        __syncthreads();
+        prefix = sm[36];
     }
     if (blockIdx.x == 0 && tid == 0) A.ctl[CTL_N] = n;
     if (valid) {
@@ -1133,23 +1041,84 @@ __global__ void __launch_bounds__(SB_T, 1) k_build_small(const SmallArgs A) {
     grid_barrier(bar, target);
     RC_PROF_MARK("M-barrier")
     if (n == 0) return;  // (uniform over the grid)
-    // ---- S: every block sorts all keys
+    // ---- S1: the block's run (compacted faces [run0, run0 + len)) sorted by counting, 4 threads per key
     uint32_t *skey = reinterpret_cast<uint32_t *>(sb_raw);
-    unsigned short *sval = reinterpret_cast<unsigned short *>(sb_raw + (size_t)SB_T * SB_ITEMS_MAX * 4);
-    unsigned short *cnt = reinterpret_cast<unsigned short *>(sb_raw + (size_t)SB_T * SB_ITEMS_MAX * 6);
-    uint32_t *tag = reinterpret_cast<uint32_t *>(sb_raw + (size_t)SB_T * SB_ITEMS_MAX * 6 + 2 * SB_CNT_BYTES);
-    const uint32_t items = (n + SB_T - 1) / SB_T;
-    if (items <= 1) sb_sort<1>(A.keys, n, skey, sval, cnt, tag, sm);
-    else if (items <= 2) sb_sort<2>(A.keys, n, skey, sval, cnt, tag, sm);
-    else if (items <= 4) sb_sort<4>(A.keys, n, skey, sval, cnt, tag, sm);
-    else if (items <= 8) sb_sort<8>(A.keys, n, skey, sval, cnt, tag, sm);
-    else sb_sort<SB_ITEMS_MAX>(A.keys, n, skey, sval, cnt, tag, sm);
+    uint32_t *srank = skey + SB_MAX_FACES;
+    const uint32_t runs = (n + SB_FT - 1) / SB_FT, run0 = blockIdx.x * SB_FT;
+    const uint32_t len = blockIdx.x < runs ? min((uint32_t)SB_FT, n - run0) : 0u;
+    const uint32_t ki = tid & (SB_FT - 1u), kq = tid / SB_FT;  // key of the run, quarter of the work on it
+    if (tid < (uint32_t)SB_FT) {
+        skey[tid] = tid < len ? __ldcg(A.keys + run0 + tid) : 0xFFFFFFFFu;  // (padding never counts: codes are < 2^30)
+        srank[tid] = 0u;
+    }
+    __syncthreads();
+    {
+        const uint32_t mine = skey[ki];
+        if (ki < len) {
+            uint32_t c = 0;
+#pragma unroll 8
+            for (uint32_t j = kq * (SB_FT / 4); j < (kq + 1u) * (SB_FT / 4); j++) {
+                const uint32_t other = skey[j];  // (the same address in every lane: a broadcast)
+                c += (other < mine || (other == mine && j < ki)) ? 1u : 0u;
+            }
+            atomicAdd(&srank[ki], c);
+        }
+        __syncthreads();
+        if (tid < len) {
+            const uint32_t pos = run0 + srank[tid];
+            A.run_keys[pos] = mine;
+            A.run_idx[pos] = run0 + tid;
+        }
+    }
+    SB_MARK("s1")
+    grid_barrier(bar, target);
+    SB_MARK("s1-bar")
+    // ---- S2: all runs into shared memory; the block merges its own run into the final order
+    for (uint32_t k = tid; k < n; k += SB_T) skey[k] = __ldcg(A.run_keys + k);
+    if (tid < (uint32_t)SB_FT) srank[tid] = 0u;
+    __syncthreads();
+    SB_MARK("s2-load")
+    {
+        const uint32_t mine = ki < len ? skey[run0 + ki] : 0u;
+        if (ki < len) {
+            uint32_t c = 0;
+            for (uint32_t r = kq; r < runs; r += SB_T / SB_FT) {
+                if (r == blockIdx.x) continue;
+                const uint32_t *rk = skey + r * SB_FT;
+                const uint32_t rl = min((uint32_t)SB_FT, n - r * SB_FT);
+                const uint32_t bound = mine + (r < blockIdx.x ? 1u : 0u);  // keys of earlier runs also precede when equal
+                uint32_t lo = 0;  // number of keys of the run below the bound
+#pragma unroll
+                for (uint32_t step = SB_FT; step > 0; step >>= 1)
+                    if (lo + step <= rl && rk[lo + step - 1u] < bound) lo += step;
+                c += lo;
+            }
+            atomicAdd(&srank[ki], c);
+        }
+        __syncthreads();
+        if (tid < len) {
+            const uint32_t pos = tid + srank[tid];
+            A.keys[pos] = mine;  // (the unsorted codes were last read before the barrier above)
+            A.perm[pos] = __ldcg(A.run_idx + run0 + tid);
+        }
+    }
+    SB_MARK("s2")
+    grid_barrier(bar, target);
+    SB_MARK("s2-bar")
+    for (uint32_t k = tid; k < n; k += SB_T) skey[k] = __ldcg(A.keys + k);
+    __syncthreads();
     RC_PROF_MARK("S")
     SB_DUMP("sort")
     // ---- T: topology of this block's internal nodes (k_topology's arithmetic on the shared-memory keys), the block's share of the permutation
     {
-        const uint32_t p1 = blockIdx.x * SB_T + tid + 1u;  // internal node number / 1-based sorted position
-        if (p1 <= n) A.perm[p1 - 1u] = sval[p1 - 1u];
+        const uint32_t p1 = tid < (uint32_t)SB_FT ? blockIdx.x * SB_FT + tid + 1u : 0xFFFFFFF0u;  // internal node number / 1-based sorted position (none for the other threads)
+        // the sorted triangle record is gathered here, behind the topology search (the fit then finds its triangles in place, like a refit)
+        float4 g0 = make_float4(0, 0, 0, 0), g1 = g0, g2 = g0;
+        if (p1 <= n) {
+            const uint32_t k = __ldcg(A.perm + (p1 - 1u));
+            const float4 *src = reinterpret_cast<const float4 *>(A.tris_in + k);
+            g0 = __ldcg(src); g1 = __ldcg(src + 1); g2 = __ldcg(src + 2);
+        }
         if (n == 1u && p1 == 1u) A.parent[0] = RC_INVALID;
         if (p1 < n) {
             const RcTopo t = rc_topology_for_node((int)p1, skey, (int)n);
@@ -1158,19 +1127,23 @@ __global__ void __launch_bounds__(SB_T, 1) k_build_small(const SmallArgs A) {
             A.parent[t.child1 - 1u] = p1;
             if (p1 == 1u) A.parent[0] = RC_INVALID;
         }
+        if (p1 <= n) {
+            float4 *dst = reinterpret_cast<float4 *>(A.tris + (p1 - 1u));
+            dst[0] = g0; dst[1] = g1; dst[2] = g2;
+        }
     }
     RC_PROF_MARK("T")
     grid_barrier(bar, target);  // (its block barrier also retires the sort's shared memory: the fit lays its own arrays over it)
     RC_PROF_MARK("T-barrier")
     const uint32_t *n_ptr = A.ctl + CTL_N;
-    fit_local_body<SB_T>(sb_raw, blockIdx.x, A.tris_in, A.perm, A.tris, nullptr, nullptr, n_ptr, A.n_faces, A.topo, A.parent, A.boxes, A.nodes2, A.ctl, A.work, true, A.nodes4,
+    fit_local_body<SB_FT>(sb_raw, blockIdx.x, nullptr, A.perm, A.tris, nullptr, nullptr, n_ptr, A.n_faces, A.topo, A.parent, A.boxes, A.nodes2, A.ctl, A.work, true, A.nodes4,
                          A.leaf_max);
     RC_PROF_MARK("fit-local")
     SB_DUMP("fit")
     grid_barrier(bar, target);
     RC_PROF_MARK("L-barrier")
     if (gridDim.x > 1) {
-        fit_span_body<SB_T>(n_ptr, A.n_faces, A.topo, A.parent, A.boxes, A.nodes2, A.work);
+        fit_span_body<SB_FT>(n_ptr, A.n_faces, A.topo, A.parent, A.boxes, A.nodes2, A.work);
         RC_PROF_MARK("fit-span")
         grid_barrier(bar, target);
         RC_PROF_MARK("P-barrier")
@@ -1188,7 +1161,7 @@ static bool launch_small(cudaStream_t st, SmallArgs &A, std::string &err) {
         if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_relaxed);
     }
     void *args[] = {(void *)&A};
-    CK(cudaLaunchCooperativeKernel((const void *)k_build_small, dim3(cdiv(A.n_faces, SB_T)), dim3(SB_T), args, SB_SMEM_BYTES, st));
+    CK(cudaLaunchCooperativeKernel((const void *)k_build_small, dim3(cdiv(A.n_faces, SB_FT)), dim3(SB_T), args, SB_SMEM_BYTES, st));
     return true;
 }
 
@@ -1276,9 +1249,24 @@ static bool extent_supported(const float aabb[6], std::string &err) {
 }
 
 // read back {valid count, root box, sphere} and finish the host-side record
+// page-locked landing zone of the builders' small read-backs, one per host thread (a pageable destination turns the copy into a staged,
+// blocking transfer); falls back to the caller's stack buffer when the allocation fails
+static uint32_t *pinned_words(uint32_t *fallback) {
+    thread_local uint32_t *p = nullptr;
+    thread_local bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *q = nullptr;
+        if (cudaHostAlloc(&q, 256, cudaHostAllocPortable) == cudaSuccess) p = static_cast<uint32_t *>(q);
+        else (void)cudaGetLastError();
+    }
+    return p ? p : fallback;
+}
 static bool finish_blas(cudaStream_t st, uint32_t *d_ctl, RcDeviceBlas *out, std::string &err) {
-    uint32_t h[CTL_OUT + 10];
-    CK(cudaMemcpyAsync(h, d_ctl, sizeof h, cudaMemcpyDeviceToHost, st));
+    uint32_t h_stack[CTL_OUT + 10];
+    uint32_t *h = pinned_words(h_stack);
+    static_assert(sizeof h_stack <= 256, "pinned landing zone");
+    CK(cudaMemcpyAsync(h, d_ctl, sizeof h_stack, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     out->n = h[CTL_N];
@@ -1307,12 +1295,12 @@ bool rc_build_blas(cudaStream_t st, const float *d_verts, const uint32_t *d_face
     // cudaFreeAsync calls on the host, and the GPU waits for the launch behind them
     size_t arena_bytes = 0;
     auto carve = [&](size_t bytes) { const size_t at = arena_bytes; arena_bytes += (bytes + 255) & ~(size_t)255; return at; };
-    const size_t o_ctl = carve(sizeof(uint32_t) * (CTL_WORDS + std::max(f_tiles, cdiv(nf, SB_T))));  // control block + the filter's per-tile valid counts
+    const size_t o_ctl = carve(sizeof(uint32_t) * (CTL_WORDS + std::max(f_tiles, cdiv(nf, SB_FT))));  // control block + the filter's per-tile valid counts
     const size_t o_tris_in = carve(sizeof(RcTri) * (size_t)nf);
     const size_t o_codes = carve(sizeof(uint32_t) * (size_t)nf), o_idx = carve(sizeof(uint32_t) * (size_t)nf);
-    const size_t o_codes2 = small ? 0 : carve(sizeof(uint32_t) * (size_t)nf), o_idx2 = small ? 0 : carve(sizeof(uint32_t) * (size_t)nf);
+    const size_t o_codes2 = carve(sizeof(uint32_t) * (size_t)nf), o_idx2 = carve(sizeof(uint32_t) * (size_t)nf);
     const size_t o_hist = small ? 0 : carve(sizeof(uint32_t) * radix_hist_words(nf));
-    const size_t o_work = carve(small ? fit_work_bytes(nf, SB_T) : fit_work_bytes(nf));
+    const size_t o_work = carve(small ? fit_work_bytes(nf, SB_FT) : fit_work_bytes(nf));
     const size_t o_boxes = carve(sizeof(RcBox) * 2 * (size_t)nf);
     const size_t o_topo = keep_topo ? 0 : carve(sizeof(RcTopo) * (size_t)nf), o_parent = keep_topo ? 0 : carve(sizeof(uint32_t) * 2 * (size_t)nf);
     unsigned char *arena = nullptr;
@@ -1321,11 +1309,9 @@ bool rc_build_blas(cudaStream_t st, const float *d_verts, const uint32_t *d_face
     d_tris_in = reinterpret_cast<RcTri *>(arena + o_tris_in);
     d_codes = reinterpret_cast<uint32_t *>(arena + o_codes);
     d_idx = reinterpret_cast<uint32_t *>(arena + o_idx);
-    if (!small) {
-        d_codes2 = reinterpret_cast<uint32_t *>(arena + o_codes2);
-        d_idx2 = reinterpret_cast<uint32_t *>(arena + o_idx2);
-        d_hist = reinterpret_cast<uint32_t *>(arena + o_hist);
-    }
+    d_codes2 = reinterpret_cast<uint32_t *>(arena + o_codes2);
+    d_idx2 = reinterpret_cast<uint32_t *>(arena + o_idx2);
+    if (!small) d_hist = reinterpret_cast<uint32_t *>(arena + o_hist);
     unsigned char *d_work = arena + o_work;
     d_boxes = reinterpret_cast<RcBox *>(arena + o_boxes);
     // the results outlive this call; on failure the caller releases them with rc_free_blas
@@ -1348,10 +1334,10 @@ bool rc_build_blas(cudaStream_t st, const float *d_verts, const uint32_t *d_face
     if (small) {
         SmallArgs sa;
         sa.verts = d_verts; sa.face_meta = d_face_meta; sa.n_faces = n_faces; sa.tris_in = d_tris_in;
-        sa.tile_counts = d_ctl + CTL_WORDS; sa.ctl = d_ctl; sa.keys = d_codes; sa.perm = d_idx;
+        sa.tile_counts = d_ctl + CTL_WORDS; sa.ctl = d_ctl; sa.keys = d_codes; sa.perm = d_idx; sa.run_keys = d_codes2; sa.run_idx = d_idx2;
         sa.topo = d_topo; sa.parent = d_parent; sa.tris = out->tris; sa.boxes = d_boxes; sa.nodes2 = out->nodes2;
         sa.nodes4 = out->nodes4; sa.hull = out->hull; sa.leaf_max = RC_BLAS_LEAF_MAX;
-        sa.work = fit_work_at(d_work, nf, SB_T);
+        sa.work = fit_work_at(d_work, nf, SB_FT);
         sa.work.span_count = d_ctl + CTL_NSPAN;  // zeroed with the control block
         sa.work.err_flag = d_ctl + CTL_ERR;
         if (!launch_small(st, sa, err)) return false;
@@ -1539,9 +1525,10 @@ static bool upload_instances(cudaStream_t st, RcDeviceTlas *t, const rc_instance
 
 // read back {invariant flag, root box} (adjacent words of the control block) and finish the host-side record
 static bool finish_tlas(cudaStream_t st, RcDeviceTlas *t, std::string &err) {
-    uint32_t h[7];
+    uint32_t h_stack[7];
+    uint32_t *h = pinned_words(h_stack);
     static_assert(CTL_ERR + 1 == CTL_OUT, "one transfer");
-    CK(cudaMemcpyAsync(h, t->d_small + CTL_ERR, sizeof h, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h, t->d_small + CTL_ERR, sizeof h_stack, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     if (h[0]) { err = "internal error: fit segment table overflow"; return false; }
