@@ -32,7 +32,7 @@ static inline uint32_t cdiv(uint64_t a, uint32_t b) { return (uint32_t)((a + b -
 // Control block of one build (u32 words, zeroed by one memset): the builder's kernels communicate through it.
 //   [CTL_N] valid primitives   [CTL_R2] bits of the bounding-sphere radius^2   [CTL_BOUNDS..+6) scene bounds, encoded so that 0 is the
 //   identity of atomicMax: word k < 3 holds ~ordered(min_k), word 3+k holds ordered(max_k)   [CTL_TILE] scratch of the refit check
-//   [CTL_NSPAN] length of the fit's spanning-node list   [CTL_BAR] arrival counter of k_front's grid barriers   [CTL_ERR] internal-invariant flag
+//   [CTL_NSPAN] length of the fit's spanning-node list   [CTL_BAR] arrival counter of the grid barriers (k_tlas_small: + 1 = blocks that have left)   [CTL_ERR] internal-invariant flag
 //   [CTL_OUT..+10) floats read back by the host: root box (6), sphere (4)
 enum { CTL_N = 0, CTL_R2 = 1, CTL_BOUNDS = 2, CTL_TILE = 8, CTL_NSPAN = 10, CTL_BAR = 11, CTL_ERR = 15, CTL_OUT = 16, CTL_WORDS = 32 };
 
@@ -957,8 +957,11 @@ __global__ void __launch_bounds__(256) k_collapse_span(const RcBox *__restrict__
 constexpr int SB_T = 1024;   // threads per block: the sort wants many warps
 constexpr int SB_FT = 256;   // faces / sorted leaves / internal nodes a block owns in the other phases: 8,192 faces spread over 32 SMs (the climb and the
                              // collapse are issue-bound per SM: with 1,024 leaves per block they took 9 + 4.5 us of a 65 us build)
-constexpr int SB_ITEMS_MAX = 12;
-constexpr uint32_t SB_MAX_FACES = RC_SMALL_BUILD ? SB_T * SB_ITEMS_MAX : 0;  // 12,288
+#ifndef RC_SB_ITEMS_MAX
+#define RC_SB_ITEMS_MAX 32
+#endif
+constexpr int SB_ITEMS_MAX = RC_SB_ITEMS_MAX;  // x SB_T = the largest small build: 32,768 faces = 128 blocks (all co-resident: one block per SM), 128 KB of keys in shared memory
+constexpr uint32_t SB_MAX_FACES = RC_SMALL_BUILD ? SB_T * SB_ITEMS_MAX : 0;
 constexpr size_t SB_SORT_BYTES = (size_t)SB_MAX_FACES * 4 + SB_FT * 4;  // all keys + the rank accumulators of the block's run
 constexpr size_t SB_SMEM_BYTES = SB_SORT_BYTES > sizeof(FitSmemT<SB_FT>) ? SB_SORT_BYTES : sizeof(FitSmemT<SB_FT>);
 struct SmallArgs {
@@ -981,6 +984,78 @@ struct SmallArgs {
     uint32_t leaf_max;
     FitWork work;     // laid out for SB_FT leaves per block
 };
+// The stable sort of the small-build kernels (S1 / S2 above) + the sorted keys into every block's shared memory.
+//   keys[0..n): codes in input order; on return: the sorted codes (also in skey[0..n)), perm[p] = input position of sorted position p.
+// Every thread of every block calls it (two grid barriers inside).
+__device__ __forceinline__ void sb_sort_runs(uint32_t *__restrict__ keys, uint32_t *__restrict__ run_keys, uint32_t *__restrict__ run_idx, uint32_t *__restrict__ perm,
+                                             const uint32_t n, uint32_t *skey, uint32_t *bar, uint32_t &target) {
+    const uint32_t tid = threadIdx.x;
+    // ---- S1: the block's run (compacted faces [run0, run0 + len)) sorted by counting, 4 threads per key
+    uint32_t *srank = skey + SB_MAX_FACES;
+    const uint32_t runs = (n + SB_FT - 1) / SB_FT, run0 = blockIdx.x * SB_FT;
+    const uint32_t len = blockIdx.x < runs ? min((uint32_t)SB_FT, n - run0) : 0u;
+    const uint32_t ki = tid & (SB_FT - 1u), kq = tid / SB_FT;  // key of the run, quarter of the work on it
+    if (tid < (uint32_t)SB_FT) {
+        skey[tid] = tid < len ? __ldcg(keys + run0 + tid) : 0xFFFFFFFFu;  // (padding never counts: codes are < 2^30)
+        srank[tid] = 0u;
+    }
+    __syncthreads();
+    {
+        const uint32_t mine = skey[ki];
+        if (ki < len) {
+            uint32_t c = 0;
+#pragma unroll 8
+            for (uint32_t j = kq * (SB_FT / 4); j < (kq + 1u) * (SB_FT / 4); j++) {
+                const uint32_t other = skey[j];  // (the same address in every lane: a broadcast)
+                c += (other < mine || (other == mine && j < ki)) ? 1u : 0u;
+            }
+            atomicAdd(&srank[ki], c);
+        }
+        __syncthreads();
+        if (tid < len) {
+            const uint32_t pos = run0 + srank[tid];
+            run_keys[pos] = mine;
+            run_idx[pos] = run0 + tid;
+        }
+    }
+    SB_MARK("s1")
+    grid_barrier(bar, target);
+    SB_MARK("s1-bar")
+    // ---- S2: all runs into shared memory; the block merges its own run into the final order
+    for (uint32_t k = tid; k < n; k += SB_T) skey[k] = __ldcg(run_keys + k);
+    if (tid < (uint32_t)SB_FT) srank[tid] = 0u;
+    __syncthreads();
+    SB_MARK("s2-load")
+    {
+        const uint32_t mine = ki < len ? skey[run0 + ki] : 0u;
+        if (ki < len) {
+            uint32_t c = 0;
+            for (uint32_t r = kq; r < runs; r += SB_T / SB_FT) {
+                if (r == blockIdx.x) continue;
+                const uint32_t *rk = skey + r * SB_FT;
+                const uint32_t rl = min((uint32_t)SB_FT, n - r * SB_FT);
+                const uint32_t bound = mine + (r < blockIdx.x ? 1u : 0u);  // keys of earlier runs also precede when equal
+                uint32_t lo = 0;  // number of keys of the run below the bound
+#pragma unroll
+                for (uint32_t step = SB_FT; step > 0; step >>= 1)
+                    if (lo + step <= rl && rk[lo + step - 1u] < bound) lo += step;
+                c += lo;
+            }
+            atomicAdd(&srank[ki], c);
+        }
+        __syncthreads();
+        if (tid < len) {
+            const uint32_t pos = tid + srank[tid];
+            keys[pos] = mine;  // (the unsorted codes were last read before the barrier above)
+            perm[pos] = __ldcg(run_idx + run0 + tid);
+        }
+    }
+    SB_MARK("s2")
+    grid_barrier(bar, target);
+    SB_MARK("s2-bar")
+    for (uint32_t k = tid; k < n; k += SB_T) skey[k] = __ldcg(keys + k);
+    __syncthreads();
+}
 __global__ void __launch_bounds__(SB_T, 1) k_build_small(const SmallArgs A) {
     extern __shared__ __align__(16) unsigned char sb_raw[];
     __shared__ uint32_t sm[40];
@@ -1041,72 +1116,8 @@ __global__ void __launch_bounds__(SB_T, 1) k_build_small(const SmallArgs A) {
     grid_barrier(bar, target);
     RC_PROF_MARK("M-barrier")
     if (n == 0) return;  // (uniform over the grid)
-    // ---- S1: the block's run (compacted faces [run0, run0 + len)) sorted by counting, 4 threads per key
     uint32_t *skey = reinterpret_cast<uint32_t *>(sb_raw);
-    uint32_t *srank = skey + SB_MAX_FACES;
-    const uint32_t runs = (n + SB_FT - 1) / SB_FT, run0 = blockIdx.x * SB_FT;
-    const uint32_t len = blockIdx.x < runs ? min((uint32_t)SB_FT, n - run0) : 0u;
-    const uint32_t ki = tid & (SB_FT - 1u), kq = tid / SB_FT;  // key of the run, quarter of the work on it
-    if (tid < (uint32_t)SB_FT) {
-        skey[tid] = tid < len ? __ldcg(A.keys + run0 + tid) : 0xFFFFFFFFu;  // (padding never counts: codes are < 2^30)
-        srank[tid] = 0u;
-    }
-    __syncthreads();
-    {
-        const uint32_t mine = skey[ki];
-        if (ki < len) {
-            uint32_t c = 0;
-#pragma unroll 8
-            for (uint32_t j = kq * (SB_FT / 4); j < (kq + 1u) * (SB_FT / 4); j++) {
-                const uint32_t other = skey[j];  // (the same address in every lane: a broadcast)
-                c += (other < mine || (other == mine && j < ki)) ? 1u : 0u;
-            }
-            atomicAdd(&srank[ki], c);
-        }
-        __syncthreads();
-        if (tid < len) {
-            const uint32_t pos = run0 + srank[tid];
-            A.run_keys[pos] = mine;
-            A.run_idx[pos] = run0 + tid;
-        }
-    }
-    SB_MARK("s1")
-    grid_barrier(bar, target);
-    SB_MARK("s1-bar")
-    // ---- S2: all runs into shared memory; the block merges its own run into the final order
-    for (uint32_t k = tid; k < n; k += SB_T) skey[k] = __ldcg(A.run_keys + k);
-    if (tid < (uint32_t)SB_FT) srank[tid] = 0u;
-    __syncthreads();
-    SB_MARK("s2-load")
-    {
-        const uint32_t mine = ki < len ? skey[run0 + ki] : 0u;
-        if (ki < len) {
-            uint32_t c = 0;
-            for (uint32_t r = kq; r < runs; r += SB_T / SB_FT) {
-                if (r == blockIdx.x) continue;
-                const uint32_t *rk = skey + r * SB_FT;
-                const uint32_t rl = min((uint32_t)SB_FT, n - r * SB_FT);
-                const uint32_t bound = mine + (r < blockIdx.x ? 1u : 0u);  // keys of earlier runs also precede when equal
-                uint32_t lo = 0;  // number of keys of the run below the bound
-#pragma unroll
-                for (uint32_t step = SB_FT; step > 0; step >>= 1)
-                    if (lo + step <= rl && rk[lo + step - 1u] < bound) lo += step;
-                c += lo;
-            }
-            atomicAdd(&srank[ki], c);
-        }
-        __syncthreads();
-        if (tid < len) {
-            const uint32_t pos = tid + srank[tid];
-            A.keys[pos] = mine;  // (the unsorted codes were last read before the barrier above)
-            A.perm[pos] = __ldcg(A.run_idx + run0 + tid);
-        }
-    }
-    SB_MARK("s2")
-    grid_barrier(bar, target);
-    SB_MARK("s2-bar")
-    for (uint32_t k = tid; k < n; k += SB_T) skey[k] = __ldcg(A.keys + k);
-    __syncthreads();
+    sb_sort_runs(A.keys, A.run_keys, A.run_idx, A.perm, n, skey, bar, target);
     RC_PROF_MARK("S")
     SB_DUMP("sort")
     // ---- T: topology of this block's internal nodes (k_topology's arithmetic on the shared-memory keys), the block's share of the permutation
@@ -1163,6 +1174,158 @@ static bool launch_small(cudaStream_t st, SmallArgs &A, std::string &err) {
     void *args[] = {(void *)&A};
     CK(cudaLaunchCooperativeKernel((const void *)k_build_small, dim3(cdiv(A.n_faces, SB_FT)), dim3(SB_T), args, SB_SMEM_BYTES, st));
     return true;
+}
+
+// The same for a TLAS of <= SB_MAX_FACES instances — build (instance records + boxes, Morton codes, sort, topology, the two fits over one
+// topology) or refit (records + boxes + the two fits) as one cooperative kernel instead of 12 / 8 launches: a one-instance TLAS (every
+// sync! after a mesh update) was 0.13 ms of launch boundaries, the refit of 10,000 instances 0.19 ms.
+struct TlasSmallArgs {
+    const rc_instance_desc *inst;
+    const float *blas_roots;
+    const RcBlasPtrs *blas;
+    uint32_t n;
+    bool refit;  // topology, leaf_map and the spanning-node list are kept
+    RcInstanceRec *rec;
+    RcInstanceAux *aux;
+    RcBox *inst_boxes, *inst_boxes_tight;
+    uint32_t *ctl;
+    uint32_t *keys, *run_keys, *run_idx;  // build only
+    uint32_t *leaf_map;
+    RcTopo *topo;
+    uint32_t *parent;
+    RcBox *boxes, *boxes_tight;
+    RcNode2 *nodes2;
+    RcNode4 *nodes4;
+    FitWork work_ref, work_tight;  // two sets of segment tables (the fits run back to back), one spanning-node list
+};
+__device__ __forceinline__ void instance_record(const rc_instance_desc *d, const RcBlasPtrs &b, RcInstanceRec *rec, RcInstanceAux *aux) {
+    RcInstanceRec r;
+    for (int k = 0; k < 12; k++) r.inv[k] = d->inv_transform[k];
+    r.nodes4 = b.nodes4;
+    r.tris = b.tris;
+    for (int k = 0; k < 4; k++) r.sphere[k] = b.sphere[k];
+    rc_world_sphere(d->transform, b.sphere, r.wsphere);
+    *rec = r;
+    RcInstanceAux a;
+    a.nodes2 = b.nodes2;
+    a.n_prims = b.n;
+    a.custom_index = d->instance_id;
+    *aux = a;
+}
+// reference box (8 corners of the BLAS root box, kernels.jl:38-62) and the tighter hull-derived box of one instance
+__device__ __forceinline__ void instance_boxes(const rc_instance_desc *d, const float *blas_roots, const RcBlasPtrs *blas, f3 &lo, f3 &hi, f3 &tl, f3 &th) {
+    rc_instance_world_aabb(d->transform, blas_roots + 6 * (d->blas_index - 1), lo, hi);
+    const RcBox *hull = blas[d->blas_index - 1].hull;
+    tl = mk3(INFINITY, INFINITY, INFINITY);
+    th = mk3(-INFINITY, -INFINITY, -INFINITY);
+    for (int k = 0; k < RC_HULL_BOXES; k++) {
+        RcBox hb = hull[k];
+        if (!(hb.lo[0] <= hb.hi[0])) continue;
+        float loc[6] = {hb.lo[0], hb.lo[1], hb.lo[2], hb.hi[0], hb.hi[1], hb.hi[2]};
+        f3 a, b;
+        rc_instance_world_aabb(d->transform, loc, a, b);
+        tl = mk3(fminf(tl.x, a.x), fminf(tl.y, a.y), fminf(tl.z, a.z));
+        th = mk3(fmaxf(th.x, b.x), fmaxf(th.y, b.y), fmaxf(th.z, b.z));
+    }
+    tl = mk3(fmaxf(tl.x, lo.x), fmaxf(tl.y, lo.y), fmaxf(tl.z, lo.z));  // never larger than the reference box
+    th = mk3(fminf(th.x, hi.x), fminf(th.y, hi.y), fminf(th.z, hi.z));
+}
+__global__ void __launch_bounds__(SB_T, 1) k_tlas_small(const TlasSmallArgs A) {
+    extern __shared__ __align__(16) unsigned char sb_raw[];
+    const uint32_t tid = threadIdx.x, n = A.n;
+    uint32_t target = 0;
+    uint32_t *bar = A.ctl + CTL_BAR;
+    // ---- I: records, reference boxes (+ scene bounds for a build), tight boxes; one instance per thread (SB_FT per block)
+    const uint32_t i = blockIdx.x * SB_FT + tid;
+    const bool mine = tid < (uint32_t)SB_FT && i < n;
+    f3 lo = mk3(INFINITY, INFINITY, INFINITY), hi = mk3(-INFINITY, -INFINITY, -INFINITY);
+    if (mine) {
+        const rc_instance_desc *d = A.inst + i;
+        instance_record(d, A.blas[d->blas_index - 1], A.rec + i, A.aux + i);
+        f3 tl, th;
+        instance_boxes(d, A.blas_roots, A.blas, lo, hi, tl, th);
+        st_box(A.inst_boxes + i, lo, hi);
+        st_box(A.inst_boxes_tight + i, tl, th);
+    }
+    if (!A.refit) {
+        bounds_atomic(A.ctl, lo, hi);
+        grid_barrier(bar, target);
+        // ---- M: calculate_tlas_morton_code, kernels.jl:295-313; extent clamp :1517-1521
+        if (mine) {
+            const f3 smin = ldcg3(A.ctl, CTL_BOUNDS, true), smax = ldcg3(A.ctl, CTL_BOUNDS + 3, false);
+            const f3 ext = mk3(jl_max(x_sub(smax.x, smin.x), 1e-6f), jl_max(x_sub(smax.y, smin.y), 1e-6f), jl_max(x_sub(smax.z, smin.z), 1e-6f));
+            const rc_instance_desc *d = A.inst + i;
+            const float *la = A.blas_roots + 6 * (d->blas_index - 1);
+            const f3 lc = mk3(x_mul(0.5f, x_add(la[0], la[3])), x_mul(0.5f, x_add(la[1], la[4])), x_mul(0.5f, x_add(la[2], la[5])));
+            const f3 wc = x_transform_point(d->transform, lc);
+            const f3 nrm = mk3(x_div(x_sub(wc.x, smin.x), ext.x), x_div(x_sub(wc.y, smin.y), ext.y), x_div(x_sub(wc.z, smin.z), ext.z));
+            A.keys[i] = rc_morton30(nrm);
+        }
+        grid_barrier(bar, target);
+        uint32_t *skey = reinterpret_cast<uint32_t *>(sb_raw);
+        sb_sort_runs(A.keys, A.run_keys, A.run_idx, A.leaf_map, n, skey, bar, target);  // leaf_map = sorted position -> instance index
+        // ---- T
+        const uint32_t p1 = tid < (uint32_t)SB_FT ? blockIdx.x * SB_FT + tid + 1u : 0xFFFFFFF0u;
+        if (n == 1u && p1 == 1u) A.parent[0] = RC_INVALID;
+        if (p1 < n) {
+            const RcTopo t = rc_topology_for_node((int)p1, skey, (int)n);
+            A.topo[p1 - 1u] = t;
+            A.parent[t.child0 - 1u] = p1;
+            A.parent[t.child1 - 1u] = p1;
+            if (p1 == 1u) A.parent[0] = RC_INVALID;
+        }
+    }
+    grid_barrier(bar, target);
+    // ---- the two fits over the one topology: reference boxes -> BVH2 + root box, tight boxes -> wide nodes
+    fit_local_body<SB_FT>(sb_raw, blockIdx.x, nullptr, nullptr, nullptr, A.inst_boxes, A.leaf_map, nullptr, n, A.topo, A.parent, A.boxes, A.nodes2, nullptr, A.work_ref, !A.refit,
+                          nullptr, 1u);
+    __syncthreads();
+    fit_local_body<SB_FT>(sb_raw, blockIdx.x, nullptr, nullptr, nullptr, A.inst_boxes_tight, A.leaf_map, nullptr, n, A.topo, A.parent, A.boxes_tight, nullptr, nullptr, A.work_tight,
+                          false, A.nodes4, 1u);
+    grid_barrier(bar, target);
+    if (gridDim.x > 1) {
+        fit_span_body<SB_FT>(nullptr, n, A.topo, A.parent, A.boxes, A.nodes2, A.work_ref);
+        fit_span_body<SB_FT>(nullptr, n, A.topo, A.parent, A.boxes_tight, nullptr, A.work_tight);
+        grid_barrier(bar, target);
+    }
+    collapse_span_body(A.boxes_tight, A.topo, nullptr, n, 1u, A.leaf_map, A.nodes4, nullptr, A.work_tight, reinterpret_cast<float *>(A.ctl + CTL_OUT), nullptr, A.boxes);
+    // the last block out leaves the barrier's arrival counter at zero for the next refit (every block has passed the last barrier by then)
+    if (tid == 0 && atomicAdd(bar + 1, 1u) == gridDim.x - 1u) { bar[0] = 0u; bar[1] = 0u; }
+}
+static bool launch_tlas_small(cudaStream_t st, TlasSmallArgs &A, std::string &err) {
+    static std::atomic<bool> configured[64];
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_relaxed)) {
+        CK(cudaFuncSetAttribute(k_tlas_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SB_SMEM_BYTES));
+        if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_relaxed);
+    }
+    void *args[] = {(void *)&A};
+    CK(cudaLaunchCooperativeKernel((const void *)k_tlas_small, dim3(cdiv(A.n, SB_FT)), dim3(SB_T), args, SB_SMEM_BYTES, st));
+    return true;
+}
+
+// Largest input the small-build kernels take on the current device: every block of the cooperative grid must be resident at once (one
+// block of SB_T threads and SB_SMEM_BYTES per SM), so the limit is min(SB_MAX_FACES, SMs x SB_FT); 0 when the kernels do not fit at all.
+static uint32_t small_build_limit() {
+    static std::atomic<uint32_t> limit[64];  // per device, 0 = not asked yet, 1 = unusable
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+    uint32_t v = limit[dev].load(std::memory_order_relaxed);
+    if (v == 0) {
+        int sms = 0, per_sm_b = 0, per_sm_t = 0;
+        bool ok = cudaFuncSetAttribute(k_build_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SB_SMEM_BYTES) == cudaSuccess &&
+                  cudaFuncSetAttribute(k_tlas_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SB_SMEM_BYTES) == cudaSuccess &&
+                  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
+                  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, k_build_small, SB_T, SB_SMEM_BYTES) == cudaSuccess &&
+                  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_t, k_tlas_small, SB_T, SB_SMEM_BYTES) == cudaSuccess;
+        if (!ok) (void)cudaGetLastError();
+        const uint64_t blocks = ok ? (uint64_t)sms * (uint64_t)std::min(per_sm_b, per_sm_t) : 0;
+        v = (uint32_t)std::min<uint64_t>(SB_MAX_FACES, blocks * SB_FT);
+        if (v == 0) v = 1;
+        limit[dev].store(v, std::memory_order_relaxed);
+    }
+    return v == 1 ? 0 : v;
 }
 
 // One fit of a built topology: leaf boxes -> boxes of every node (+ BVH2 records) (+ wide nodes, hull, finishing read-back words).
@@ -1290,7 +1453,7 @@ bool rc_build_blas(cudaStream_t st, const float *d_verts, const uint32_t *d_face
     RcBox *d_boxes = nullptr;
     uint32_t *d_codes = nullptr, *d_idx = nullptr, *d_codes2 = nullptr, *d_idx2 = nullptr, *d_hist = nullptr, *d_parent = nullptr;
     RcTopo *d_topo = nullptr;
-    const bool small = nf <= SB_MAX_FACES;  // one cooperative kernel instead of the five launches (k_build_small)
+    const bool small = nf <= small_build_limit();  // one cooperative kernel instead of the five launches (k_build_small)
     // every temporary of the build comes out of ONE stream-ordered allocation: a small build is as long as a dozen cudaMallocAsync /
     // cudaFreeAsync calls on the host, and the GPU waits for the launch behind them
     size_t arena_bytes = 0;
@@ -1555,41 +1718,71 @@ static void fit_tlas(cudaStream_t st, RcDeviceTlas *t, bool fresh_topology) {
     run_fit(st, tight, work);
 }
 
+static TlasSmallArgs tlas_small_args(RcDeviceTlas *t, bool refit) {
+    TlasSmallArgs a;
+    a.inst = t->d_inst; a.blas_roots = t->d_blas_roots; a.blas = t->d_blas_ptrs; a.n = t->n; a.refit = refit;
+    a.rec = t->rec; a.aux = t->aux; a.inst_boxes = t->inst_boxes; a.inst_boxes_tight = t->inst_boxes_tight;
+    a.ctl = t->d_small; a.keys = a.run_keys = a.run_idx = nullptr;
+    a.leaf_map = t->leaf_map; a.topo = t->topo; a.parent = t->parent;
+    a.boxes = t->boxes; a.boxes_tight = t->boxes_tight; a.nodes2 = t->nodes2; a.nodes4 = t->nodes4;
+    a.work_ref = fit_work_at(t->fit_work, t->n, SB_FT);
+    a.work_tight = fit_work_at(t->fit_work + fit_work_bytes(t->n, SB_FT), t->n, SB_FT);
+    a.work_tight.span_list = a.work_ref.span_list;  // the spanning nodes depend on the topology only
+    a.work_ref.span_count = a.work_tight.span_count = t->d_small + CTL_NSPAN;
+    a.work_ref.err_flag = a.work_tight.err_flag = t->d_small + CTL_ERR;
+    return a;
+}
+
 bool rc_build_tlas(cudaStream_t st, const rc_instance_desc *h_inst, uint32_t n, const std::vector<RcBlasPtrs> &blas, const std::vector<float> &blas_roots,
                    RcDeviceTlas *t, std::string &err) {
-    rc_free_tlas(t, st);
+    uint32_t nb = (uint32_t)blas.size();
+    // a rebuild with the same instance count (every sync! after a mesh update) keeps the device arrays: 16 cudaFreeAsync + 16 cudaMallocAsync
+    // were a third of a small rebuild
+    const bool reuse = n > 0 && t->n == n && t->nodes4 && t->n_blas_cap >= nb;
+    if (!reuse) rc_free_tlas(t, st);
     for (int k = 0; k < 3; k++) { t->root_aabb[k] = INFINITY; t->root_aabb[3 + k] = -INFINITY; }  // Bounds3()
     t->n = n;
     if (n == 0) return true;  // empty TLAS: zero nodes (:969-978)
     const int T = 256;
-    uint32_t nb = (uint32_t)blas.size();
     uint32_t *d_codes = nullptr, *d_idx = nullptr, *d_codes2 = nullptr, *d_idx2 = nullptr, *d_hist = nullptr;
     RcTemps tmp(st);
-    CK(cudaMallocAsync(&t->d_inst, sizeof(rc_instance_desc) * n, st));
-    CK(cudaMallocAsync(&t->d_blas_roots, sizeof(float) * 6 * nb, st));
-    CK(cudaMallocAsync(&t->d_blas_ptrs, sizeof(RcBlasPtrs) * nb, st));
-    CK(cudaMallocAsync(&t->rec, sizeof(RcInstanceRec) * n, st));
-    CK(cudaMallocAsync(&t->aux, sizeof(RcInstanceAux) * n, st));
-    CK(cudaMallocAsync(&t->inst_boxes, sizeof(RcBox) * n, st));
-    CK(cudaMallocAsync(&t->inst_boxes_tight, sizeof(RcBox) * n, st));
-    CK(cudaMallocAsync(&t->boxes_tight, sizeof(RcBox) * (2 * n - 1), st));
-    CK(cudaMallocAsync(&t->leaf_map, sizeof(uint32_t) * n, st));
-    CK(cudaMallocAsync(&t->topo, sizeof(RcTopo) * std::max(1u, n - 1), st));
-    CK(cudaMallocAsync(&t->parent, sizeof(uint32_t) * (2 * n - 1), st));
-    CK(cudaMallocAsync(&t->fit_work, fit_work_bytes(n), st));
-    CK(cudaMallocAsync(&t->boxes, sizeof(RcBox) * (2 * n - 1), st));
-    CK(cudaMallocAsync(&t->nodes2, sizeof(RcNode2) * (2 * n - 1), st));
-    CK(cudaMallocAsync(&t->nodes4, sizeof(RcNode4) * (n + 1), st));
-    CK(cudaMallocAsync(&t->d_small, sizeof(uint32_t) * CTL_WORDS, st));
+    const bool small = n <= small_build_limit();  // one cooperative kernel (k_tlas_small); its two fits keep a set of segment tables each
+    if (!reuse) {
+        CK(cudaMallocAsync(&t->d_inst, sizeof(rc_instance_desc) * n, st));
+        CK(cudaMallocAsync(&t->d_blas_roots, sizeof(float) * 6 * nb, st));
+        CK(cudaMallocAsync(&t->d_blas_ptrs, sizeof(RcBlasPtrs) * nb, st));
+        CK(cudaMallocAsync(&t->rec, sizeof(RcInstanceRec) * n, st));
+        CK(cudaMallocAsync(&t->aux, sizeof(RcInstanceAux) * n, st));
+        CK(cudaMallocAsync(&t->inst_boxes, sizeof(RcBox) * n, st));
+        CK(cudaMallocAsync(&t->inst_boxes_tight, sizeof(RcBox) * n, st));
+        CK(cudaMallocAsync(&t->boxes_tight, sizeof(RcBox) * (2 * n - 1), st));
+        CK(cudaMallocAsync(&t->leaf_map, sizeof(uint32_t) * n, st));
+        CK(cudaMallocAsync(&t->topo, sizeof(RcTopo) * std::max(1u, n - 1), st));
+        CK(cudaMallocAsync(&t->parent, sizeof(uint32_t) * (2 * n - 1), st));
+        CK(cudaMallocAsync(&t->fit_work, small ? 2 * fit_work_bytes(n, SB_FT) : fit_work_bytes(n), st));
+        CK(cudaMallocAsync(&t->boxes, sizeof(RcBox) * (2 * n - 1), st));
+        CK(cudaMallocAsync(&t->nodes2, sizeof(RcNode2) * (2 * n - 1), st));
+        CK(cudaMallocAsync(&t->nodes4, sizeof(RcNode4) * (n + 1), st));
+        CK(cudaMallocAsync(&t->d_small, sizeof(uint32_t) * CTL_WORDS, st));
+        t->n_blas_cap = nb;
+    }
+    CK(cudaMemcpyAsync(t->d_blas_roots, blas_roots.data(), sizeof(float) * 6 * nb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(t->d_blas_ptrs, blas.data(), sizeof(RcBlasPtrs) * nb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(t->d_small, 0, sizeof(uint32_t) * CTL_WORDS, st));
+    if (small) {
+        TMP(d_codes, 3 * (size_t)n);  // codes, run codes, run indices
+        CK(cudaMemcpyAsync(t->d_inst, h_inst, sizeof(rc_instance_desc) * n, cudaMemcpyHostToDevice, st));
+        TlasSmallArgs sa = tlas_small_args(t, false);
+        sa.keys = d_codes; sa.run_keys = d_codes + n; sa.run_idx = d_codes + 2 * (size_t)n;
+        if (!launch_tlas_small(st, sa, err)) return false;
+        return finish_tlas(st, t, err);
+    }
     TMP(d_codes, n);
     TMP(d_idx, n);
     TMP(d_codes2, n);
     TMP(d_idx2, n);
     TMP(d_hist, radix_hist_words(n));
-    CK(cudaMemcpyAsync(t->d_blas_roots, blas_roots.data(), sizeof(float) * 6 * nb, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(t->d_blas_ptrs, blas.data(), sizeof(RcBlasPtrs) * nb, cudaMemcpyHostToDevice, st));
     if (!upload_instances(st, t, h_inst, n, err)) return false;
-    CK(cudaMemsetAsync(t->d_small, 0, sizeof(uint32_t) * CTL_WORDS, st));
     k_instance_boxes<<<cdiv(n, T), T, 0, st>>>(t->d_inst, t->d_blas_roots, n, t->inst_boxes, t->d_small, t->d_blas_ptrs, t->inst_boxes_tight);
     k_morton_instances<<<cdiv(n, T), T, 0, st>>>(t->d_inst, t->d_blas_roots, n, t->d_small, d_codes, d_idx);
     FrontArgs fa;
@@ -1607,6 +1800,12 @@ bool rc_build_tlas(cudaStream_t st, const rc_instance_desc *h_inst, uint32_t n, 
 bool rc_refit_tlas(cudaStream_t st, const rc_instance_desc *h_inst, uint32_t n, RcDeviceTlas *t, std::string &err) {
     if (n == 0) return true;
     if (n != t->n) { err = "refit: instance count changed"; return false; }
+    if (n <= small_build_limit()) {  // records, boxes and both fits in one cooperative kernel
+        CK(cudaMemcpyAsync(t->d_inst, h_inst, sizeof(rc_instance_desc) * n, cudaMemcpyHostToDevice, st));
+        TlasSmallArgs sa = tlas_small_args(t, true);
+        if (!launch_tlas_small(st, sa, err)) return false;
+        return finish_tlas(st, t, err);
+    }
     if (!upload_instances(st, t, h_inst, n, err)) return false;
     // update_tlas_leaf_aabbs_kernel! (kernels.jl:487-519) + refit_tlas_aabbs_kernel! (:381-428), then re-quantise the wide nodes
     k_instance_boxes<<<cdiv(n, 256), 256, 0, st>>>(t->d_inst, t->d_blas_roots, n, t->inst_boxes, nullptr, t->d_blas_ptrs, t->inst_boxes_tight);

@@ -38,6 +38,7 @@ struct RcBlasPtrs {  // device-visible BLAS table entry
 
 struct RcDeviceTlas {
     uint32_t n = 0;
+    uint32_t n_blas_cap = 0;  // entries d_blas_roots / d_blas_ptrs were allocated for
     RcNode2 *nodes2 = nullptr;
     RcNode4 *nodes4 = nullptr;
     RcInstanceRec *rec = nullptr;

@@ -40,12 +40,12 @@ def test_builder_bit_exact_vs_oracle():
 
 def _builder_stress_meshes():
     """triangle soups that exercise the builder's block structure: sizes around the 256-face blocks / sorted runs of the small-build
-    kernel (<= 12,288 faces) and its upper limit, around the 512-leaf fit blocks and the 2048-key sort tiles of the five-launch path
+    kernel (<= 32,768 faces) and its upper limit, around the 512-leaf fit blocks and the 2048-key sort tiles of the five-launch path
     above it, long runs of identical Morton codes (index tie-break chains: the deepest radix trees; equal keys across sorted runs), an
     exponentially spaced comb (one-sided tree), and soups with degenerate faces sprinkled in (compaction offsets)"""
     rs = np.random.RandomState(7)
     out = {}
-    for n in (1, 2, 3, 5, 255, 256, 257, 511, 512, 513, 1023, 1024, 1025, 1537, 2047, 2048, 2049, 5000, 12287, 12288, 12289, 12800, 14335, 14336, 14337):
+    for n in (1, 2, 3, 5, 255, 256, 257, 511, 512, 513, 1023, 1024, 1025, 1537, 2047, 2048, 2049, 5000, 12800, 32767, 32768, 32769, 33792, 34815, 34816, 34817):
         c = rs.uniform(-10, 10, (n, 1, 3))
         out[f"soup{n}"] = (c + rs.uniform(-0.3, 0.3, (n, 3, 3))).reshape(n, 9).astype(np.float32)
     one = np.array([[0, 0, 0, 1, 0, 0, 0, 1, 0]], np.float32)
@@ -56,9 +56,9 @@ def _builder_stress_meshes():
     holes = out["soup5000"].copy()
     holes[rs.rand(5000) < 0.3, 3:] = np.tile(holes[rs.rand(5000) < 0.3][:1, :3], 2)  # v1 = v2 = one fixed point: zero-area faces
     out["holes"] = holes
-    # the same two shapes on the five-launch path (> 12,288 faces)
-    out["duplicates_large"] = np.concatenate([np.repeat(one, 9000, axis=0), out["soup5000"], np.repeat(one + 5, 2100, axis=0)])
-    big = np.concatenate([out["soup12800"], out["soup5000"] + 30.0])
+    # the same two shapes on the five-launch path (> 32,768 faces)
+    out["duplicates_large"] = np.concatenate([np.repeat(one, 22000, axis=0), out["soup12800"], np.repeat(one + 5, 2100, axis=0)])
+    big = np.concatenate([out["soup33792"], out["soup5000"] + 30.0])
     mask = rs.rand(len(big)) < 0.3
     big[mask, 3:] = np.tile(big[mask][:1, :3], 2)
     out["holes_large"] = big

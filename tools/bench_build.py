@@ -24,7 +24,7 @@ def main():
     xf = W.identity3x4()
     hh, dd = C.c_uint32(), C.c_int32()
     out = {"lib": os.environ.get("RAYCORE_CUDA_LIB", "default")}
-    sizes = ((65, "8k"), (355, "250k"), (709, "1M"), (1418, "4M"))
+    sizes = ((65, "8k"), (96, "18k"), (128, "32k"), (160, "50k"), (355, "250k"), (709, "1M"), (1418, "4M"))
     if "--once" in sys.argv:
         sizes = ((int(sys.argv[sys.argv.index("--once") + 1]), "once"),)
     flags = L.RC_VERTS_ON_DEVICE | (L.RC_BUILD_KEEP_BVH2 if "--bvh2" in sys.argv else 0)
