@@ -110,6 +110,49 @@ def test_tlas_bit_exact_vs_oracle():
     assert s["tlas_nodes"] == 2 * 317 - 1 and s["blas_prims"] == o.tlas.c.n_blas_prims and s["blas_nodes"] == o.tlas.c.n_blas_nodes
 
 
+@pytest.mark.parametrize("n_inst", [1, 2, 255, 256, 257, 1025, 5000, 32768, 32769])
+def test_tlas_block_structure_bit_exact(n_inst):
+    """TLAS builds and refits around the block sizes of the one-kernel path (k_tlas_small: 256 instances per block, <= 32,768 instances) and
+    on the multi-launch path just above it: BVH2 + root box byte-identical to the oracle's after the build AND after a refit with new
+    transforms; a run of concentric instances (equal Morton codes across sorted runs: the index tie-break) in every scene; wide-TLAS
+    traversal exact against the oracle."""
+    rs = np.random.RandomState(n_inst)
+    ext = max(4.0, 1.5 * n_inst ** (1 / 3))
+
+    def transforms(seed):
+        xf = W.random_trs(n_inst, seed, extent=ext)
+        if n_inst >= 255:  # 200 instances around one centre: equal Morton codes (the box mesh is centred), nested boxes of distinct sizes (no exact t ties)
+            m = xf[40].reshape(3, 4).copy()
+            for k in range(200):
+                mk = m.copy()
+                mk[:, :3] *= np.float32(1.0 + 0.004 * k)
+                xf[40 + k] = mk.reshape(12)
+        return xf
+
+    verts = W.box_mesh()
+    xf0, xf1 = transforms(3), transforms(4)
+    g = engines.GpuEngine([(verts, None, xf0, None)])
+    o = engines.OracleEngine([(verts, None, xf0, None)])
+    for step in (0, 1):
+        if step == 1:  # refit_tlas! keeps the topology of the build (:2197-2222): the oracle re-fits its own TLAS to the new transforms
+            import raycore_b200 as rc
+            g.tlas.update_transforms(g.handles[0], list(xf1))
+            g.tlas.sync()
+            assert g.tlas.last_sync_action == rc.RC_SYNC_REFIT
+            moved = engines.instances_of([(verts, None, xf1, None)], orc.mat3x4_inverse)
+            o.instances[:] = moved
+            o.tlas.instances[:] = moved.view(orc.INSTANCE_DTYPE)
+            o.tlas.refit()
+        assert g.tlas.read_tlas_nodes().tobytes() == o.tlas.nodes.tobytes(), f"TLAS BVH2 differs (step {step})"
+        assert np.array_equal(g.world_bound(), o.tlas.root_aabb)
+        rays = W.box_rays(20000, 11 + step, half=1.1 * ext)
+        a, b = g.trace(rays), o.trace(rays)
+        cls = parity.classify(a, b, parity.make_graze_verifier(orc, rays, a, o.instances, o.tris))
+        parity.assert_parity(cls, len(rays), label=f"tlas {n_inst} step {step}")
+    g.tlas.free()
+    del rs
+
+
 @pytest.mark.parametrize("any_hit", [False, True])
 def test_reference_order_traversal_bit_exact(any_hit):
     pushes = _scene_instanced()
