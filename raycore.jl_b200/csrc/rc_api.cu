@@ -8,6 +8,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -28,6 +29,40 @@ thread_local std::string g_create_error;  // message of a failed rc_create / rc_
 
 }  // namespace
 
+// Page-locked storage for the host mirror of the instance descriptors: the TLAS build / refit uploads it every sync!, and from pageable
+// memory that copy (1 MB for 10,000 instances) is staged by the driver at a few GB/s — most of a refit frame.  Falls back to malloc when
+// page-locked memory cannot be had (a 64-byte header remembers which).
+template <class T>
+struct RcPinnedAlloc {
+    using value_type = T;
+    RcPinnedAlloc() = default;
+    template <class U>
+    RcPinnedAlloc(const RcPinnedAlloc<U> &) {}
+    T *allocate(size_t n) {
+        const size_t bytes = n * sizeof(T) + 64;
+        void *p = nullptr;
+        if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) == cudaSuccess) {
+            *static_cast<uint64_t *>(p) = 1;
+        } else {
+            (void)cudaGetLastError();
+            p = malloc(bytes);
+            if (!p) throw std::bad_alloc();
+            *static_cast<uint64_t *>(p) = 0;
+        }
+        return reinterpret_cast<T *>(static_cast<char *>(p) + 64);
+    }
+    void deallocate(T *q, size_t) {
+        char *p = reinterpret_cast<char *>(q) - 64;
+        if (*reinterpret_cast<uint64_t *>(p)) cudaFreeHost(p);
+        else free(p);
+    }
+    template <class U>
+    bool operator==(const RcPinnedAlloc<U> &) const { return true; }
+    template <class U>
+    bool operator!=(const RcPinnedAlloc<U> &) const { return false; }
+};
+typedef std::vector<rc_instance_desc, RcPinnedAlloc<rc_instance_desc>> RcInstanceVec;
+
 struct rc_context {
     // queries on a synced TLAS may come from several host threads at once (the reference calls them under Threads.@threads,
     // src/kernels.jl:64,82); entry points that touch the GPU or the shared launch resources serialise on this lock (RC_ENTER)
@@ -37,7 +72,7 @@ struct rc_context {
     bool owns_stream = true;
     std::string last_error;
     std::vector<RcDeviceBlas> blas;           // blas_index b+1 <-> blas[b]
-    std::vector<rc_instance_desc> instances;  // host mirror of tlas.instances
+    RcInstanceVec instances;                  // host mirror of tlas.instances (page-locked: uploaded by every sync!)
     std::map<uint32_t, HandleInfo> handles;   // ordered by id (Julia: Dict{TLASHandle,UnitRange})
     bool dirty = true, transforms_dirty = false, built = false, last_update_refitted = false;
     uint32_t build_flags = 0;  // RC_BUILD_* defaults of this context (rc_set_build_flags; initialised from the RC_BUILD_FLAGS environment variable)
@@ -265,6 +300,8 @@ static uint32_t append_blas_with_instances(rc_context *ctx, const RcDeviceBlas &
     ctx->blas.push_back(b);
     uint32_t blas_idx = (uint32_t)ctx->blas.size();  // :607
     uint32_t start = (uint32_t)ctx->instances.size();
+    if (ctx->instances.capacity() < (size_t)start + m)  // (page-locked allocations are slow: grow by at least half)
+        ctx->instances.reserve(std::max((size_t)start + m, ctx->instances.capacity() + ctx->instances.capacity() / 2));
     for (uint32_t i = 0; i < m; i++) {
         rc_instance_desc d;
         d.blas_index = blas_idx;
@@ -455,14 +492,34 @@ int32_t rc_push_exported(rc_context *ctx, const void *blob, uint64_t size, const
 // compact_instances!, :996-1065.  Handles are visited in ascending id order (Julia iterates its Dict in hash
 // order, which no caller can rely on); unreferenced BLASes are freed and blas_index values remapped.
 static void compact_instances(rc_context *ctx) {
-    std::vector<rc_instance_desc> ni;
-    ni.reserve(ctx->instances.size());
-    for (auto it = ctx->handles.begin(); it != ctx->handles.end();) {
-        if (it->second.deleted) { it = ctx->handles.erase(it); continue; }
-        uint32_t ns = (uint32_t)ni.size();
-        ni.insert(ni.end(), ctx->instances.begin() + it->second.start, ctx->instances.begin() + it->second.start + it->second.count);
-        it->second.start = ns;
-        ++it;
+    // in place: the list is kept in ascending handle order (push! appends under the largest id, this pass keeps the order), so a live
+    // range only ever moves towards the front — no second page-locked buffer (allocating one costs milliseconds)
+    RcInstanceVec &ni = ctx->instances;
+    size_t w = 0;
+    bool ordered = true;
+    for (auto it = ctx->handles.begin(); it != ctx->handles.end(); ++it)
+        if (!it->second.deleted) { ordered = ordered && it->second.start >= w; w += it->second.count; }
+    if (ordered) {
+        w = 0;
+        for (auto it = ctx->handles.begin(); it != ctx->handles.end();) {
+            if (it->second.deleted) { it = ctx->handles.erase(it); continue; }
+            if (it->second.start != w && it->second.count) memmove(ni.data() + w, ni.data() + it->second.start, sizeof(rc_instance_desc) * it->second.count);
+            it->second.start = (uint32_t)w;
+            w += it->second.count;
+            ++it;
+        }
+        ni.resize(w);
+    } else {  // (not reachable through the API; kept so that a broken invariant costs time, not correctness)
+        RcInstanceVec tmp;
+        tmp.reserve(ni.size());
+        for (auto it = ctx->handles.begin(); it != ctx->handles.end();) {
+            if (it->second.deleted) { it = ctx->handles.erase(it); continue; }
+            uint32_t ns = (uint32_t)tmp.size();
+            tmp.insert(tmp.end(), ni.begin() + it->second.start, ni.begin() + it->second.start + it->second.count);
+            it->second.start = ns;
+            ++it;
+        }
+        ni.swap(tmp);
     }
     std::vector<uint32_t> remap(ctx->blas.size() + 1, 0);
     for (auto &d : ni) remap[d.blas_index] = 1;
@@ -478,7 +535,6 @@ static void compact_instances(rc_context *ctx) {
         for (auto &d : ni) d.blas_index = remap[d.blas_index];
         ctx->blas.swap(nb);
     }
-    ctx->instances.swap(ni);
 }
 
 // L2 residency hint (experiment switch, off by default: profiles/README.md r2 has the measurement).  RC_L2_PERSIST=1: the wide nodes of the
