@@ -1,12 +1,14 @@
-// rc_build.cu — GPU LBVH builder for sm_100a: degenerate filter + stable compaction (single pass, decoupled look-back), scene bounds,
-// 30-bit Morton codes, hand-written stable LSD radix sort (3 passes of 10 bits), Karras radix tree, block-local bottom-up fit,
-// collapse to the quantised BVH4 the fast traversal uses, optional reference-layout BVH2 emission.
+// rc_build.cu — GPU LBVH builder for sm_100a: degenerate filter + stable compaction, scene bounds, 30-bit Morton codes, hand-written stable
+// sorts (large inputs: LSD radix, 3 passes of 10 bits, inside one cooperative front-end kernel; small inputs: counting sort of 256-key runs +
+// merge by binary searches), Karras radix tree, block-local bottom-up fit, collapse to the quantised BVH4 the fast traversal uses, optional
+// reference-layout BVH2 emission.
 //
 // Replaces build_blas (src/instanced-bvh.jl:1376-1443), build_tlas_topology (:1485-1594),
 // refit_tlas! (:2197-2222) and kernels K0-K11 of src/instanced-bvh-kernels.jl.  Everything runs on
-// the caller's stream.  A BLAS build is 15 dependent launches with NO host round trip in the middle: the number of valid
-// triangles stays on the device (every kernel reads it from the build's control block), and the only device->host traffic is
-// one 44-byte read-back at the end (valid count, root box, bounding sphere).
+// the caller's stream.  A BLAS build is 5 dependent launches — ONE cooperative kernel for <= 32,768 faces (k_build_small), likewise a TLAS
+// of <= 32,768 instances (k_tlas_small) — with NO host round trip in the middle: the number of valid triangles stays on the device
+// (every kernel reads it from the build's control block), and the only device->host traffic is one 104-byte read-back at the end
+// (valid count, root box, bounding sphere, invariant flag).
 #include <cuda_runtime.h>
 
 #include <algorithm>
