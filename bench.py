@@ -414,7 +414,7 @@ def main():
     tlas = rc.TLAS(local)
     lib, ctx = tlas._lib, tlas._ctx
     t0 = time.time()
-    tlas.push(blas_verts, list(xf))
+    c3_handle = tlas.push(blas_verts, list(xf))
     tlas.sync()
     scene_ms = 1e3 * (time.time() - t0)
     blas_build_ms_10k = float(lib.rc_last_build_ms(ctx))
@@ -588,6 +588,21 @@ def main():
                 extras.update(c2)
             except Exception as e:  # noqa: BLE001
                 extras["c2_error"] = repr(e)
+            try:  # C5 refit frames on the headline scene (after every timed region): update_transforms! + sync! of all 10,000 instances
+                h0 = c3_handle
+                if build is not None:
+                    rs = np.random.RandomState(5)
+                    ms = []
+                    for _ in range(6):
+                        xf2 = xf.copy()
+                        xf2[:, [3, 7, 11]] += rs.uniform(-0.5, 0.5, (len(xf), 3)).astype(np.float32)
+                        tlas.update_transforms(h0, list(xf2))
+                        t0 = time.perf_counter()
+                        tlas.sync()
+                        ms.append(1e3 * (time.perf_counter() - t0))
+                    build["tlas_refit_sync_ms_10k_instances"] = float(np.median(ms[1:]))
+            except Exception as e:  # noqa: BLE001
+                extras["tlas_refit_error"] = repr(e)
 
     if rank != 0:
         if world > 1:
