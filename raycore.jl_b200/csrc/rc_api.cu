@@ -3,6 +3,7 @@
 // with all geometry work on the GPU (rc_build.cu), and the batched query / analysis entry points.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -63,6 +64,8 @@ struct RcPinnedAlloc {
 };
 typedef std::vector<rc_instance_desc, RcPinnedAlloc<rc_instance_desc>> RcInstanceVec;
 
+#define RC_OVF_LIST_CAP 65536u  // rays with an overflowed short stack that a trace call can list for its fix-up pass (more: the pass scans)
+
 struct rc_context {
     // queries on a synced TLAS may come from several host threads at once (the reference calls them under Threads.@threads,
     // src/kernels.jl:64,82); entry points that touch the GPU or the shared launch resources serialise on this lock (RC_ENTER)
@@ -84,6 +87,7 @@ struct rc_context {
     unsigned long long *d_work = nullptr;
     RcCounters *d_counters = nullptr;
     uint32_t *d_overflow = nullptr;
+    uint32_t ovf_cap = RC_OVF_LIST_CAP;  // entries of the overflow list a trace may use (RC_OVF_LIST_CAP environment variable: smaller, 0 = none; tests)
     uint32_t *h_err = nullptr;  // pinned host word: the hard-error counter is read back with the copy queued BEFORE a call's final sync (no extra round trip)
     rc_ray *d_rays = nullptr;
     rc_hit *d_hits = nullptr;
@@ -203,7 +207,7 @@ int32_t rc_create(int32_t device, rc_context **out) {
     }
     CREATE_CK(cudaEventCreate(&ctx->ev_t0));
     CREATE_CK(cudaEventCreate(&ctx->ev_t1));
-    CREATE_CK(cudaMalloc(&ctx->d_work, sizeof(unsigned long long)));
+    CREATE_CK(cudaMalloc(&ctx->d_work, sizeof(unsigned long long) * (2 + RC_OVF_LIST_CAP)));  // work counter, overflow-list length, overflow list (rc_trace.h)
     CREATE_CK(cudaMalloc(&ctx->d_counters, sizeof(RcCounters)));
     CREATE_CK(cudaMalloc(&ctx->d_overflow, 4 * sizeof(uint32_t)));  // [0] rays flagged for k_trace_fixup, [1] hard errors, [2] flagged-ray scratch of the inline re-trace policies
     CREATE_CK(cudaMemset(ctx->d_counters, 0, sizeof(RcCounters)));
@@ -217,6 +221,7 @@ int32_t rc_create(int32_t device, rc_context **out) {
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
     }
     ctx->max_blocks = rc_trace_max_blocks(device);
+    if (const char *e = getenv("RC_OVF_LIST_CAP")) ctx->ovf_cap = std::min<uint32_t>((uint32_t)strtoul(e, nullptr, 0), RC_OVF_LIST_CAP);
     if (const char *e = getenv("RC_BUILD_FLAGS")) ctx->build_flags = (uint32_t)strtoul(e, nullptr, 0) & (RC_BUILD_KEEP_BVH2 | RC_BUILD_ALLOW_REFIT);
 #undef CREATE_CK
     *out = ctx;
@@ -814,6 +819,7 @@ static int32_t trace_common(rc_context *ctx, const rc_ray *rays, rc_hit *hits, u
     if (L.zero_tmin && !L.wide) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "RC_IGNORE_TMIN is not available together with RC_MODE_REFERENCE_ORDER");
     if (L.watertight && L.count) RC_FAIL(ctx, RC_ERR_INVALID_ARGUMENT, "RC_COUNTERS is not available together with RC_MODE_WATERTIGHT");
     L.work = ctx->d_work;
+    L.ovf_cap = ctx->ovf_cap;
     L.counters = ctx->d_counters;
     L.overflow = ctx->d_overflow;
     L.max_blocks = ctx->max_blocks;

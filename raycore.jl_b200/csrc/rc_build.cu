@@ -217,6 +217,10 @@ __device__ int g_sb_k;
 #define SB_DUMP(what)
 #endif
 __device__ __forceinline__ void grid_barrier(uint32_t *bar, uint32_t &target) {
+    if (gridDim.x == 1) {  // a one-block grid (tiny meshes, the one-instance TLAS of every single-mesh scene): the block barrier is the grid barrier
+        __syncthreads();
+        return;
+    }
     target += gridDim.x;
     __syncthreads();
     if (threadIdx.x == 0) {

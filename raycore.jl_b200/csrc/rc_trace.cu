@@ -39,13 +39,20 @@ __global__ void __launch_bounds__(RC_TRACE_THREADS) k_trace(RcScene sc, const rc
 
 // Re-trace the rays whose short (shared-memory) stack overflowed in k_trace_wide with the deep-stack generic body.
 // overflow[0] = rays flagged by the fast kernel (exit immediately when 0), overflow[1] = rays no stack could hold (error).
+// ovf_list (nullable): ovf_list[0] = number of flagged rays the fast kernel listed, entries from [1], capacity ovf_cap; when the list holds
+// every flagged ray only those are visited, otherwise every hit record is scanned for the mark.
 template <bool ANY, bool WT>
 __global__ void __launch_bounds__(RC_TRACE_THREADS) k_trace_fixup(RcScene sc, const rc_ray *__restrict__ rays, rc_hit *__restrict__ hits, unsigned long long n,
-                                                                  uint32_t *__restrict__ overflow) {
-    if (*reinterpret_cast<volatile uint32_t *>(overflow) == 0) return;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+                                                                  uint32_t *__restrict__ overflow, const unsigned long long *__restrict__ ovf_list, uint32_t ovf_cap, bool zero_tmin) {
+    const uint32_t flagged = *reinterpret_cast<volatile uint32_t *>(overflow);
+    if (flagged == 0) return;
+    const bool listed = ovf_list && flagged <= ovf_cap && ovf_list[0] == flagged;
+    const unsigned long long count = listed ? flagged : n;
+    for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long i = listed ? ovf_list[1 + k] : k;
         if (hits[i].hit != RC_OVERFLOW_MARK) continue;
         rc_ray r = rc_load_ray(rays, i);
+        if (zero_tmin) r.tmin = 0.0f;
         rc_hit h;
         if (!rc_trace_wide<ANY, false, WT>(sc, r, h, nullptr)) atomicAdd(overflow + 1, 1u);
         rc_store_hit(hits, i, h);
@@ -65,7 +72,7 @@ bool rc_launch_trace(cudaStream_t st, const RcTraceLaunch &L, std::string &err) 
     if (L.scene.n_instances == 0) {  // empty TLAS: every ray misses (test/test_tlas_stress.jl:808-831)
         k_fill_miss<<<(unsigned)((L.n + 255) / 256), 256, 0, st>>>(L.hits, L.n);
     } else {
-        cudaMemsetAsync(L.work, 0, sizeof(unsigned long long), st);
+        cudaMemsetAsync(L.work, 0, sizeof(unsigned long long) * (L.ovf_cap ? 2 : 1), st);
         cudaMemsetAsync(L.overflow, 0, sizeof(uint32_t), st);
         unsigned long long want = (L.n + RC_TRACE_THREADS - 1) / RC_TRACE_THREADS;
         // the single-instance variant is compiled for RC_MIN_BLOCKS_SINGLE resident CTAs per SM (fewer registers: no world-ray copy)
@@ -73,7 +80,7 @@ bool rc_launch_trace(cudaStream_t st, const RcTraceLaunch &L, std::string &err) 
         int blocks = (int)(want < cap ? want : cap);
         if (blocks < 1) blocks = 1;
 #define RC_ARGS L.scene, L.rays, L.hits, L.n, L.work, L.counters, L.overflow
-#define RC_WARGS L.scene, RcIoArrays{L.rays, L.hits, L.zero_tmin}, L.n, L.work, L.counters, L.overflow
+#define RC_WARGS L.scene, RcIoArrays{L.rays, L.hits, L.zero_tmin, L.ovf_cap ? L.work + 1 : nullptr, L.ovf_cap}, L.n, L.work, L.counters, L.overflow
         const bool single = L.scene.n_instances == 1u;
         if (L.wide) {
             // (ANY, COUNT, SINGLE, WT): the instrumented build exists for Moeller-Trumbore only
@@ -99,11 +106,11 @@ bool rc_launch_trace(cudaStream_t st, const RcTraceLaunch &L, std::string &err) 
 #undef RC_WARGS
         if (L.wide) {
             if (L.watertight) {
-                if (L.any) k_trace_fixup<true, true><<<blocks, RC_TRACE_THREADS, 0, st>>>(L.scene, L.rays, L.hits, L.n, L.overflow);
-                else k_trace_fixup<false, true><<<blocks, RC_TRACE_THREADS, 0, st>>>(L.scene, L.rays, L.hits, L.n, L.overflow);
+                if (L.any) k_trace_fixup<true, true><<<blocks, RC_TRACE_THREADS, 0, st>>>(L.scene, L.rays, L.hits, L.n, L.overflow, L.ovf_cap ? L.work + 1 : nullptr, L.ovf_cap, L.zero_tmin);
+                else k_trace_fixup<false, true><<<blocks, RC_TRACE_THREADS, 0, st>>>(L.scene, L.rays, L.hits, L.n, L.overflow, L.ovf_cap ? L.work + 1 : nullptr, L.ovf_cap, L.zero_tmin);
             } else {
-                if (L.any) k_trace_fixup<true, false><<<blocks, RC_TRACE_THREADS, 0, st>>>(L.scene, L.rays, L.hits, L.n, L.overflow);
-                else k_trace_fixup<false, false><<<blocks, RC_TRACE_THREADS, 0, st>>>(L.scene, L.rays, L.hits, L.n, L.overflow);
+                if (L.any) k_trace_fixup<true, false><<<blocks, RC_TRACE_THREADS, 0, st>>>(L.scene, L.rays, L.hits, L.n, L.overflow, L.ovf_cap ? L.work + 1 : nullptr, L.ovf_cap, L.zero_tmin);
+                else k_trace_fixup<false, false><<<blocks, RC_TRACE_THREADS, 0, st>>>(L.scene, L.rays, L.hits, L.n, L.overflow, L.ovf_cap ? L.work + 1 : nullptr, L.ovf_cap, L.zero_tmin);
             }
         }
     }

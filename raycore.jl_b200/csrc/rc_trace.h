@@ -18,7 +18,9 @@ struct RcTraceLaunch {
     bool any, wide, count;
     bool zero_tmin = false;    // RC_IGNORE_TMIN (wide path only)
     bool watertight = false;   // RC_MODE_WATERTIGHT: the reference's watertight triangle test instead of Moeller-Trumbore
-    unsigned long long *work;  // device work counter (zeroed by the launcher)
+    unsigned long long *work;  // device work counter (zeroed by the launcher); with ovf_cap > 0: followed by the overflow list (work[1] = its
+                               // length, work[2 ..] = ray indices, RcIoArrays::ovf_list), so that one memset clears both counters
+    uint32_t ovf_cap = 0;
     RcCounters *counters;      // device, only with count
     uint32_t *overflow;        // device, incremented per ray whose traversal stack overflowed
     int max_blocks;            // persistent grid size (SMs x resident CTAs)

@@ -272,6 +272,16 @@ def test_deep_trees_short_stack_fixup():
     a2 = gq.trace(rays)
     assert a2.tobytes() == a.tobytes()
     assert np.array_equal(gq.trace(rays, any_hit=True)["hit"], o.trace(rays, any_hit=True)["hit"])
+    # the fast kernel lists the flagged rays for the fix-up pass; with a list that is too short (or none) the pass scans the hit records instead
+    import os
+    for cap in ("2", "0"):
+        os.environ["RC_OVF_LIST_CAP"] = cap
+        try:
+            g2 = engines.GpuEngine(pushes)
+        finally:
+            del os.environ["RC_OVF_LIST_CAP"]
+        assert g2.trace(rays).tobytes() == a.tobytes(), f"fix-up pass with RC_OVF_LIST_CAP={cap}"
+        g2.tlas.free()
 
 
 def test_edge_case_rays_and_geometry():
