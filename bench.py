@@ -134,6 +134,41 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
+def host_placement(local, world):
+    """N > 1: run this rank's host threads (ray generation, the pinned staging buffers' first touch, the staging pipeline) on the CPUs NVML
+    names as local to its GPU, when the container lets it; returns what was found for the JSON line.  The end-to-end number of a multi-GPU
+    box is set by its host links, so the line also carries what the box looks like (`nvidia-smi topo -m`, rank 0)."""
+    info = {}
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        near = {64 * w + b for w, v in enumerate(words) for b in range(64) if (v >> b) & 1}
+        allowed = set(os.sched_getaffinity(0))
+        info["gpu_local_cpus"] = len(near)
+        info["allowed_cpus"] = len(allowed)
+        both = near & allowed
+        info["usable_local_cpus"] = len(both)
+        if world > 1 and both and both != allowed and len(both) >= max(2, len(allowed) // world):
+            os.sched_setaffinity(0, both)
+            info["pinned_to_local_cpus"] = True
+    except Exception as e:  # noqa: BLE001  (placement is an optimisation, never a failure)
+        info["error"] = repr(e)[:120]
+    return info
+
+
+def box_topology():
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+        rows = [" ".join(l.split()) for l in out.splitlines() if l.startswith("GPU") or l.lstrip().startswith("GPU0")]
+        return rows[:10]
+    except Exception as e:  # noqa: BLE001
+        return [repr(e)[:120]]
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe): one `nvidia-smi -lms 20`
     process is read continuously; only samples stamped between mark_start() and mark_end() are summarised."""
@@ -400,6 +435,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    placement = host_placement(local, world)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     total = args.rays
@@ -672,7 +708,7 @@ def main():
         "metric": "closest_hit Mrays/s (incoherent)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": bench_config(world, total),
-        "run": {"rays_per_rank": n, "hit_rate": hit_rate, "tlas_nodes": sizes["tlas_nodes"], "blas_triangles": sizes["blas_prims"], "scene_push_sync_ms": scene_ms,
+        "run": {"host_placement": placement, "box_topology": box_topology() if world > 1 else None, "rays_per_rank": n, "hit_rate": hit_rate, "tlas_nodes": sizes["tlas_nodes"], "blas_triangles": sizes["blas_prims"], "scene_push_sync_ms": scene_ms,
                 "ray_generation_s": gen_s,
                 "delivery": {"fused": "each rank's traversal kernel stores its hit records straight into rank 0's buffer through CUDA-IPC peer pointers over NVLink (no separate collective)",
                              "peer-copy": "each rank traces into double-buffered local hit buffers; the copy engine pushes a finished buffer into rank 0's CUDA-IPC-mapped buffer over NVLink while the next step traces (the closing event waits for the last pushes)",
