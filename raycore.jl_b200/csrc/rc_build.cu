@@ -1744,7 +1744,7 @@ bool rc_build_tlas(cudaStream_t st, const rc_instance_desc *h_inst, uint32_t n, 
     uint32_t nb = (uint32_t)blas.size();
     // a rebuild with the same instance count (every sync! after a mesh update) keeps the device arrays: 16 cudaFreeAsync + 16 cudaMallocAsync
     // were a third of a small rebuild
-    const bool reuse = n > 0 && t->n == n && t->nodes4 && t->n_blas_cap >= nb;
+    const bool reuse = n > 0 && t->n == n && t->nodes4 && t->d_small && t->n_blas_cap >= nb;  // (d_small is the last array allocated: a complete set)
     if (!reuse) rc_free_tlas(t, st);
     for (int k = 0; k < 3; k++) { t->root_aabb[k] = INFINITY; t->root_aabb[3 + k] = -INFINITY; }  // Bounds3()
     t->n = n;
