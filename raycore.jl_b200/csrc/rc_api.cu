@@ -850,11 +850,22 @@ static int32_t trace_common(rc_context *ctx, const rc_ray *rays, rc_hit *hits, u
         if (rc != RC_OK) return rc;
         d_hits = ctx->d_hits;
     }
-    static const uint64_t chunk = [] { const char *e = getenv("RC_HOST_CHUNK_RAYS"); uint64_t v = e ? strtoull(e, nullptr, 10) : 0; return v ? v : (1ull << 20); }();
+    // Chunk schedule: the copies of chunk c+1 / c-1 hide behind the trace of chunk c, but the first chunk's upload and the last chunk's trace +
+    // download hide behind nothing, and every launch of the persistent kernel costs ~0.2 ms of ramp and tail (a ray is ~80 us of lane time).
+    // So: large chunks in the middle (2 M rays; RC_HOST_CHUNK_RAYS), a geometric ramp from 128 K at the start and back down at the end.
+    // Measured on C3, 10^8 rays from pinned host memory, on a box whose links give 1.53-1.56 Grays/s: fixed 1 M chunks 1.41, fixed 2 M
+    // 1.46-1.47, fixed 4 M 1.45, this schedule 1.47 (profiles/README.md) — the ramps matter for calls of a few million rays, where a
+    // fixed 2 M chunk would not overlap anything.
+    static const uint64_t chunk_max = [] { const char *e = getenv("RC_HOST_CHUNK_RAYS"); uint64_t v = e ? strtoull(e, nullptr, 10) : 0; return v ? v : (1ull << 21); }();
+    const uint64_t chunk_min = std::min<uint64_t>(chunk_max, 1ull << 17);
     cudaEventRecord(ctx->ev_t0, ctx->stream);
     int c = 0;
-    for (uint64_t off = 0; off < n; off += chunk, c++) {
-        uint64_t cn = n - off < chunk ? n - off : chunk;
+    uint64_t ramp = chunk_min;
+    for (uint64_t off = 0, cn = 0; off < n; off += cn, c++, ramp = std::min(chunk_max, ramp * 2)) {
+        const uint64_t rem = n - off;
+        cn = ramp;
+        if (rem <= cn) cn = rem;
+        else if (rem < 2 * cn) cn = std::max(chunk_min, rem / 2);
         int e = c % rc_context::NEV;
         if (!rays_dev) {
             RC_CUDA(ctx, cudaMemcpyAsync((void *)(d_rays + off), rays + off, cn * sizeof(rc_ray), cudaMemcpyHostToDevice, ctx->s_h2d));
