@@ -593,7 +593,7 @@ def main():
         e2e = {"value": total * e_steps / e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": total * 32, "d2h_bytes_per_step": total * 32, "steps": e_steps,
                "host_link_roof": {"Mrays_s": total / pcie_s / 1e6, "GBs_each_way": total * 32 / pcie_s / 1e9,
                                   "how": "the same pinned buffers copied H2D and D2H concurrently by every rank with no kernel in between (max over ranks): what the box's host links give at 32 + 32 B per ray"},
-               "note": "every rank stages its own slice from / to its own pinned host buffers (three streams: H2D, trace, D2H overlapped in 1 M-ray chunks)"}
+               "note": "every rank stages its own slice from / to its own pinned host buffers (three streams: H2D, trace, D2H overlapped in chunks of up to 2 M rays)"}
         del h_hits
 
     # ---- instrumented pass: per-ray work of the shipped kernel ---------------------------------
