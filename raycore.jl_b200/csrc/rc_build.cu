@@ -943,7 +943,7 @@ __global__ void __launch_bounds__(256) k_collapse_span(const RcBox *__restrict__
 // Small meshes (<= SB_MAX_FACES faces): the WHOLE BLAS build as one cooperative kernel.  The five-launch path above spends a small build
 // waiting: 8,192 faces are 4 radix tiles (4 working blocks per phase), every phase is a chain of L2 round trips, and the kernel
 // boundaries cost as much as the kernels (131 us, of which the kernels themselves are 110).  Here a block (SB_T threads) owns SB_FT
-// faces / sorted leaves / internal nodes in every phase, the grid is cdiv(faces, SB_FT) <= 48 blocks, and
+// faces / sorted leaves / internal nodes in every phase, the grid is cdiv(faces, SB_FT) <= 128 blocks (all resident: one per SM), and
 //   F   one face per thread: exact degenerate test, scene bounds, valid count of the block                                   | grid barrier
 //   M   compacted RcTri records + Morton codes (the reference's arithmetic, as in k_front)                                    | grid barrier
 //   S1  the block sorts its own run of SB_FT keys by counting (rank = keys of the run that are smaller, or equal and earlier: stable)    | grid barrier
