@@ -1568,6 +1568,77 @@ __global__ void k_refit_apply(const float *__restrict__ verts, RcTri *__restrict
     bounds_atomic(ctl, lo, hi);
 }
 
+// The vertex-update refit of a small geometry (<= small_build_limit() faces) as one cooperative kernel, with no host decision in the middle:
+// the check (is the degenerate set unchanged?) is a phase, its verdict is uniform over the grid after a barrier, and a refused refit leaves
+// the geometry untouched and says so in ctl[CTL_REFUSED] (the multi-launch path reads the two counts back and decides on the host).
+enum { CTL_REFUSED = 12 };
+struct RefitSmallArgs {
+    const float *verts;
+    uint32_t n_faces, n;
+    RcTri *tris;
+    const RcTopo *topo;
+    const uint32_t *parent;
+    RcBox *boxes;
+    RcNode2 *nodes2;
+    RcNode4 *nodes4;
+    RcBox *hull;
+    uint32_t *ctl;
+    FitWork work;  // laid out for SB_FT leaves per block
+};
+__global__ void __launch_bounds__(SB_T, 1) k_refit_small(const RefitSmallArgs A) {
+    extern __shared__ __align__(16) unsigned char sb_raw[];
+    __shared__ uint32_t red[2];
+    const uint32_t tid = threadIdx.x, n = A.n;
+    uint32_t target = 0;
+    uint32_t *bar = A.ctl + CTL_BAR;
+    const uint32_t i = tid < (uint32_t)SB_FT ? blockIdx.x * SB_FT + tid : 0xFFFFFFFFu;
+    // ---- check: a kept face that is degenerate in the new soup / the valid faces of the new soup (must equal n)
+    if (tid < 2) red[tid] = 0;
+    __syncthreads();
+    if (i < n) {
+        const float *v = A.verts + (size_t)A.tris[i].face_index * 9;
+        if (x_is_degenerate(ld3(v), ld3(v + 3), ld3(v + 6))) atomicAdd(&red[0], 1u);
+    }
+    if (i < A.n_faces) {
+        const float *v = A.verts + (size_t)i * 9;
+        if (!x_is_degenerate(ld3(v), ld3(v + 3), ld3(v + 6))) atomicAdd(&red[1], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (red[0]) atomicAdd(&A.ctl[CTL_TILE], red[0]);
+        if (red[1]) atomicAdd(&A.ctl[CTL_TILE + 1], red[1]);
+        if (blockIdx.x == 0) A.ctl[CTL_N] = n;
+    }
+    grid_barrier(bar, target);
+    if (__ldcg(A.ctl + CTL_TILE) != 0u || __ldcg(A.ctl + CTL_TILE + 1) != n) {  // (uniform over the grid)
+        if (blockIdx.x == 0 && tid == 0) A.ctl[CTL_REFUSED] = 1u;
+        return;
+    }
+    // ---- apply: every sorted triangle takes its face's new vertices (ids kept); scene bounds for the bounding sphere
+    f3 lo = mk3(INFINITY, INFINITY, INFINITY), hi = mk3(-INFINITY, -INFINITY, -INFINITY);
+    if (i < n) {
+        float4 *t = reinterpret_cast<float4 *>(A.tris + i);
+        const float4 t0 = t[0], t1 = t[1], t2 = t[2];
+        const float *v = A.verts + (size_t)__float_as_uint(t2.w) * 9;
+        const f3 a = ld3(v), b = ld3(v + 3), c = ld3(v + 6);
+        t[0] = make_float4(a.x, a.y, a.z, t0.w);
+        t[1] = make_float4(b.x, b.y, b.z, t1.w);
+        t[2] = make_float4(c.x, c.y, c.z, t2.w);
+        lo = jl_min3(jl_min3(a, b), c);
+        hi = jl_max3(jl_max3(a, b), c);
+    }
+    bounds_atomic(A.ctl, lo, hi);
+    grid_barrier(bar, target);
+    const uint32_t *n_ptr = A.ctl + CTL_N;
+    fit_local_body<SB_FT>(sb_raw, blockIdx.x, nullptr, nullptr, A.tris, nullptr, nullptr, n_ptr, n, A.topo, A.parent, A.boxes, A.nodes2, A.ctl, A.work, true, A.nodes4, RC_BLAS_LEAF_MAX);
+    grid_barrier(bar, target);
+    if (gridDim.x > 1) {
+        fit_span_body<SB_FT>(n_ptr, n, A.topo, A.parent, A.boxes, A.nodes2, A.work);
+        grid_barrier(bar, target);
+    }
+    collapse_span_body(A.boxes, A.topo, n_ptr, n, RC_BLAS_LEAF_MAX, nullptr, A.nodes4, A.hull, A.work, reinterpret_cast<float *>(A.ctl + CTL_OUT), A.ctl, nullptr);
+}
+
 bool rc_refit_blas(cudaStream_t st, const float *d_verts, uint32_t n_faces, RcDeviceBlas *b, bool *refitted, std::string &err) {
     *refitted = false;
     if (!b->topo || !b->parent || n_faces != b->n_faces_in || b->n == 0) return true;
@@ -1576,10 +1647,42 @@ bool rc_refit_blas(cudaStream_t st, const float *d_verts, uint32_t n_faces, RcDe
     uint32_t *d_ctl = nullptr;
     unsigned char *d_work = nullptr;
     RcBox *d_boxes = nullptr;
+    const bool small = n_faces <= small_build_limit();
     TMP(d_ctl, CTL_WORDS);
-    TMP(d_work, fit_work_bytes(n));
+    TMP(d_work, small ? fit_work_bytes(n, SB_FT) : fit_work_bytes(n));
     TMP(d_boxes, 2 * (size_t)n);
     CK(cudaMemsetAsync(d_ctl, 0, sizeof(uint32_t) * CTL_WORDS, st));
+    if (small) {
+        static std::atomic<bool> configured[64];
+        int dev = 0;
+        CK(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_relaxed)) {
+            CK(cudaFuncSetAttribute(k_refit_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SB_SMEM_BYTES));
+            if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_relaxed);
+        }
+        RefitSmallArgs ra;
+        ra.verts = d_verts; ra.n_faces = n_faces; ra.n = n; ra.tris = b->tris; ra.topo = b->topo; ra.parent = b->parent;
+        ra.boxes = d_boxes; ra.nodes2 = b->nodes2; ra.nodes4 = b->nodes4; ra.hull = b->hull; ra.ctl = d_ctl;
+        ra.work = fit_work_at(d_work, n, SB_FT);
+        ra.work.span_count = d_ctl + CTL_NSPAN;
+        ra.work.err_flag = d_ctl + CTL_ERR;
+        void *args[] = {(void *)&ra};
+        CK(cudaLaunchCooperativeKernel((const void *)k_refit_small, dim3(cdiv(n_faces, SB_FT)), dim3(SB_T), args, SB_SMEM_BYTES, st));
+        uint32_t h_stack[CTL_OUT + 10];
+        uint32_t *h = pinned_words(h_stack);
+        CK(cudaMemcpyAsync(h, d_ctl, sizeof h_stack, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        if (h[CTL_REFUSED]) return true;  // the degenerate set changed: primitive numbering would differ (the geometry was not touched)
+        if (h[CTL_ERR]) { err = "internal error: fit segment table overflow"; return false; }
+        float root[6];
+        memcpy(root, h + CTL_OUT, 24);
+        if (!extent_supported(root, err)) return false;
+        memcpy(b->root_aabb, root, 24);
+        memcpy(b->sphere, h + CTL_OUT + 6, 16);
+        *refitted = true;
+        return true;
+    }
     // check first, touch the geometry only when the refit is certain (a refused update leaves the old geometry intact, as update! does, :837)
     dim3 grid(cdiv(std::max(n, n_faces), 256), 2);
     k_refit_check<<<grid, 256, 0, st>>>(d_verts, n_faces, b->tris, n, d_ctl);
